@@ -1,0 +1,130 @@
+"""ctypes binding of ``libconanmp.so`` (the C ABI declared in ``include/conanmp.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``build.build_library()``.
+There is no fallback of any kind: if the shared object is missing, or a kernel
+is asked to run without a CUDA device, the call raises.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libconanmp.so")
+
+P, I, L, F, D, S = c_void_p, c_int, c_int64, c_float, c_double, c_size_t
+
+# name -> (restype, argtypes); mirrors include/conanmp.h one to one
+SIGNATURES = {
+    "cmp_last_error_string": (c_char_p, []),
+    "cmp_version": (I, []),
+    "cmp_device_is_sm100": (I, []),
+    "cmp_batch_to_segments": (I, [P, L, L, P, P, P]),
+    "cmp_radius_csr_workspace": (S, [L, L]),
+    "cmp_radius_csr": (I, [P, P, L, L, D, I, I, L, P, P, P, P, P, P, P, P, P, S, P, P]),
+    "cmp_csr_to_edge_index": (I, [P, P, L, L, P, P]),
+    "cmp_gemm_workspace": (S, [L, L, L]),
+    "cmp_gemm_f32": (I, [I, I, L, L, L, P, L, P, L, P, L, P, I, P, L, P, S, P]),
+    "cmp_colsum_workspace": (S, [L, L]),
+    "cmp_colsum_f32": (I, [P, L, L, L, P, P, S, P]),
+    "cmp_act_fwd": (I, [P, P, L, I, P]),
+    "cmp_act_bwd": (I, [P, P, P, L, I, P]),
+    "cmp_rbf_gaussian_fwd": (I, [P, L, P, I, F, P, L, P]),
+    "cmp_embedding_fwd": (I, [P, L, P, I, I, P, P, P]),
+    "cmp_embedding_bwd_workspace": (S, [L, I, I]),
+    "cmp_embedding_bwd": (I, [P, L, P, I, I, I, P, P, S, P]),
+    "cmp_cfconv_message_fwd": (I, [P, P, P, P, P, L, I, F, P, P]),
+    "cmp_cfconv_message_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, F, P, P, P]),
+    "cmp_segment_sum_fwd": (I, [P, P, L, I, P, P]),
+    "cmp_segment_sum_bwd": (I, [P, P, L, I, P, P]),
+    "cmp_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, I, F, P]),
+}
+
+ACT_NONE, ACT_SSP, ACT_SILU = 0, 1, 2
+PREC_FP32, PREC_BF16 = 0, 1
+STATUS_UNSORTED_BATCH, STATUS_BAD_ATOMIC_NUMBER, STATUS_EDGE_OVERFLOW = 1, 2, 4
+
+_lib = None
+_launches = 0  # number of C-ABI compute calls issued (bench.py reports it)
+
+
+class ConanMPError(RuntimeError):
+    pass
+
+
+def register(extra: dict):
+    """Let sibling modules (fused kernels added later) declare more entry points."""
+    SIGNATURES.update(extra)
+    if _lib is not None:
+        _bind(_lib, extra)
+
+
+def _bind(lib, table):
+    for name, (res, args) in table.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+
+
+def lib():
+    """Load the shared library once; raise loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ConanMPError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU or PyTorch fallback for these kernels.")
+        handle = ctypes.CDLL(LIB_PATH)
+        _bind(handle, SIGNATURES)
+        _lib = handle
+    return _lib
+
+
+def launches() -> int:
+    return _launches
+
+
+def reset_launches():
+    global _launches
+    _launches = 0
+
+
+def ptr(t, dtype=None):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ConanMPError("conanmp kernels need CUDA tensors (there is no CPU path); got a tensor on " + str(t.device))
+    if dtype is not None and t.dtype != dtype:
+        raise ConanMPError(f"expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ConanMPError("expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point on the current stream; raise on a non-zero code."""
+    global _launches
+    fn = getattr(lib(), name)
+    rc = fn(*args, stream())
+    _launches += 1
+    if rc != 0:
+        msg = lib().cmp_last_error_string().decode("utf-8", "replace")
+        exc = ValueError if rc in (-1, -2) else ConanMPError
+        raise exc(f"{name} failed ({rc}): {msg}")
+
+
+def size_query(name, *args) -> int:
+    return int(getattr(lib(), name)(*args))
+
+
+def workspace(nbytes: int, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)

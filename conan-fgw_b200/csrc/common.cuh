@@ -1,0 +1,71 @@
+// Shared host/device helpers for libconanmp (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "conanmp.h"
+
+namespace cmp {
+
+void set_error(const char* fmt, ...);
+
+#define CMP_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      ::cmp::set_error(__VA_ARGS__);  \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+// Every launch is followed by this: catches bad launch configurations without synchronising.
+#define CMP_LAUNCH_CHECK(what)                                                         \
+  do {                                                                                 \
+    cudaError_t e__ = cudaPeekAtLastError();                                           \
+    if (e__ != cudaSuccess) {                                                          \
+      ::cmp::set_error("%s: CUDA launch failed: %s", (what), cudaGetErrorString(e__)); \
+      (void)cudaGetLastError();                                                        \
+      return CMP_ECUDA;                                                                \
+    }                                                                                  \
+  } while (0)
+
+inline cudaStream_t as_stream(cmp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int sm_count();
+
+constexpr float kLn2 = 0.69314718055994530942f;
+constexpr float kPi = 3.14159265358979323846f;
+
+// softplus(x) - ln2 with torch's threshold (F.softplus: beta=1, threshold=20).
+__device__ __forceinline__ float ssp(float x) {
+  float sp = (x > 20.0f) ? x : log1pf(expf(x));
+  return sp - kLn2;
+}
+
+__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float silu(float x) { return x * sigmoidf(x); }
+
+// d/dx silu(x)
+__device__ __forceinline__ float silu_grad(float x) {
+  float s = sigmoidf(x);
+  return s * (1.0f + x * (1.0f - s));
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == CMP_ACT_SSP) return ssp(x);
+  if (act == CMP_ACT_SILU) return silu(x);
+  return x;
+}
+
+// SchNet cosine cutoff (PyG CFConv): no d < cutoff mask.
+__device__ __forceinline__ float cos_cutoff_nomask(float d, float pi_over_cutoff) {
+  return 0.5f * (cosf(d * pi_over_cutoff) + 1.0f);
+}
+
+}  // namespace cmp

@@ -1,0 +1,382 @@
+// Dense fp32 building blocks: tiled SIMT GEMM with fused epilogue + deterministic split-K,
+// column sums, activations, Adam.  These are the exact-fp32 ("parity") node/edge GEMMs and the
+// generic-shape path; the fused tcgen05 kernels (cfconv_tc.cu) take over for the hot shapes.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace cmp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess &&
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) {
+    cached = n;
+  } else {
+    (void)cudaGetLastError();
+    return 148;  // B200; not cached so a later call with a device present can correct it
+  }
+  return cached;
+}
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 16, GEMM_THREADS = 256;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                int64_t ldb, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int act,
+                const float* __restrict__ residual, int64_t ldr, float* __restrict__ partial, int kchunk) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = min(K, kbeg + kchunk);
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    // ---- stage A tile (BM x BK) ----
+#pragma unroll
+    for (int r = 0; r < (BM * BK) / GEMM_THREADS; ++r) {
+      int e = tid + r * GEMM_THREADS;
+      int m, k;
+      if (TA) { m = e & (BM - 1); k = e >> 7; } else { k = e & (BK - 1); m = e >> 4; }
+      int gm = m0 + m, gk = k0 + k;
+      float v = 0.0f;
+      if (gm < M && gk < kend) v = TA ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk];
+      As[k][m] = v;
+    }
+    // ---- stage B tile (BK x BN) ----
+#pragma unroll
+    for (int r = 0; r < (BN * BK) / GEMM_THREADS; ++r) {
+      int e = tid + r * GEMM_THREADS;
+      int n, k;
+      if (TB) { k = e & (BK - 1); n = e >> 4; } else { n = e & (BN - 1); k = e >> 6; }
+      int gn = n0 + n, gk = k0 + k;
+      float v = 0.0f;
+      if (gn < N && gk < kend) v = TB ? B[(int64_t)gn * ldb + gk] : B[(int64_t)gk * ldb + gn];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  if (gridDim.z > 1) {
+    float* P = partial + (int64_t)blockIdx.z * M * N;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int gm = m0 + ty * 8 + i;
+      if (gm >= M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        int gn = n0 + tx * 4 + j;
+        if (gn < N) P[(int64_t)gm * N + gn] = acc[i][j];
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int gm = m0 + ty * 8 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[gn];
+      v = apply_act(v, act);
+      if (residual) v += residual[(int64_t)gm * ldr + gn];
+      C[(int64_t)gm * ldc + gn] = v;
+    }
+  }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, int64_t M, int64_t N,
+                                     float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int act,
+                                     const float* __restrict__ residual, int64_t ldr) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  int64_t m = idx / N, n = idx - m * N;
+  float v = 0.0f;
+  for (int s = 0; s < S; ++s) v += partial[(int64_t)s * M * N + idx];  // fixed order: deterministic
+  if (bias) v += bias[n];
+  v = apply_act(v, act);
+  if (residual) v += residual[m * ldr + n];
+  C[m * ldc + n] = v;
+}
+
+struct SplitPlan {
+  int S;
+  int kchunk;
+};
+
+SplitPlan plan_split(int64_t M, int64_t N, int64_t K) {
+  int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
+  int sms = sm_count();
+  SplitPlan p{1, (int)(ceil_div(K, BK) * BK)};
+  if (tiles >= sms || K <= 512) return p;
+  int64_t want = ceil_div(2 * (int64_t)sms, tiles);
+  int64_t maxS = ceil_div(K, 256);
+  int64_t S = want < maxS ? want : maxS;
+  if (S <= 1) return p;
+  int64_t kchunk = ceil_div(ceil_div(K, S), BK) * BK;
+  p.kchunk = (int)kchunk;
+  p.S = (int)ceil_div(K, kchunk);
+  return p;
+}
+
+// ---- column sums ------------------------------------------------------------------------
+constexpr int CS_ROWS = 8;  // blockDim.y
+
+__global__ void colsum_stage1_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int N, int rows_per_chunk,
+                                     float* __restrict__ partial) {
+  __shared__ float red[CS_ROWS][33];
+  int n = blockIdx.x * 32 + threadIdx.x;
+  int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+  int64_t r1 = r0 + rows_per_chunk;
+  if (r1 > M) r1 = M;
+  float s = 0.0f;
+  if (n < N)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += CS_ROWS) s += X[r * ldx + n];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    float t = 0.0f;
+#pragma unroll
+    for (int y = 0; y < CS_ROWS; ++y) t += red[y][threadIdx.x];
+    partial[(int64_t)blockIdx.y * N + n] = t;
+  }
+}
+
+__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float t = 0.0f;
+  for (int c = 0; c < chunks; ++c) t += partial[(int64_t)c * N + n];
+  out[n] = t;
+}
+
+int colsum_chunks(int64_t M) {
+  int64_t c = ceil_div(M, 512);
+  if (c < 1) c = 1;
+  if (c > 1024) c = 1024;
+  return (int)c;
+}
+
+// ---- elementwise --------------------------------------------------------------------------
+__global__ void act_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int act) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) y[i] = apply_act(x[i], act);
+}
+
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ saved, float* __restrict__ dx,
+                               int64_t n, int act) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float g = dy[i];
+    if (act == CMP_ACT_SSP) {
+      // saved = y = softplus(x) - ln2  =>  sigmoid(x) = 1 - exp(-(y + ln2)) = 1 - 0.5 * exp(-y)
+      g *= 1.0f - 0.5f * expf(-saved[i]);
+    } else if (act == CMP_ACT_SILU) {
+      g *= silu_grad(saved[i]);
+    }
+    dx[i] = g;
+  }
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+                            float bc1, float bc2_sqrt, float grad_scale) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float gi = g[i] * grad_scale;
+    float pi = p[i];
+    if (wd != 0.0f) gi += wd * pi;
+    float mi = b1 * m[i] + (1.0f - b1) * gi;
+    float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+int ew_blocks(int64_t n) {
+  int64_t b = ceil_div(n, 256);
+  int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+}  // namespace cmp
+
+using namespace cmp;
+
+extern "C" const char* cmp_last_error_string(void) { return g_err; }
+extern "C" int cmp_version(void) { return 100; }
+
+extern "C" int cmp_device_is_sm100(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return major == 10;
+}
+
+extern "C" size_t cmp_gemm_workspace(int64_t M, int64_t N, int64_t K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  SplitPlan p = plan_split(M, N, K);
+  return p.S > 1 ? align_up((size_t)p.S * M * N * sizeof(float), 256) : 0;
+}
+
+extern "C" int cmp_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                            const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias, int act,
+                            const float* residual, int64_t ldr, void* workspace, size_t workspace_bytes,
+                            cmp_stream_t stream) {
+  CMP_REQUIRE(M >= 0 && N >= 0 && K >= 0, CMP_EINVAL, "cmp_gemm_f32: negative size");
+  if (M == 0 || N == 0) return CMP_OK;
+  CMP_REQUIRE(M < ((int64_t)1 << 31) && N < ((int64_t)1 << 31) && K < ((int64_t)1 << 31), CMP_EUNSUPPORTED,
+              "cmp_gemm_f32: sizes must fit int32");
+  CMP_REQUIRE(C && (K == 0 || (A && B)), CMP_EINVAL, "cmp_gemm_f32: null pointer");
+  CMP_REQUIRE(!(transA && transB), CMP_EUNSUPPORTED, "cmp_gemm_f32: transA && transB is not provided");
+  CMP_REQUIRE(act >= CMP_ACT_NONE && act <= CMP_ACT_SILU, CMP_EINVAL, "cmp_gemm_f32: unknown activation %d", act);
+  SplitPlan p = (K > 0) ? plan_split(M, N, K) : SplitPlan{1, BK};
+  float* partial = nullptr;
+  if (p.S > 1) {
+    size_t need = (size_t)p.S * M * N * sizeof(float);
+    CMP_REQUIRE(workspace && workspace_bytes >= need, CMP_EWORKSPACE, "cmp_gemm_f32: workspace too small (%zu < %zu)",
+                workspace_bytes, need);
+    partial = reinterpret_cast<float*>(workspace);
+  }
+  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), (unsigned)p.S);
+  CMP_REQUIRE(grid.y <= 65535u * 1024u, CMP_EUNSUPPORTED, "cmp_gemm_f32: M too large");
+  cudaStream_t st = as_stream(stream);
+  // grid.y limit is 65535: fold very tall problems by looping the launch over row bands
+  const int64_t band_rows = (int64_t)65535 * BM;
+  for (int64_t mb = 0; mb < M; mb += band_rows) {
+    int64_t Mb = (M - mb < band_rows) ? (M - mb) : band_rows;
+    dim3 g((unsigned)ceil_div(N, BN), (unsigned)ceil_div(Mb, BM), (unsigned)p.S);
+    const float* Ab = transA ? A + mb : A + mb * lda;
+    float* Cb = C + mb * ldc;
+    const float* Rb = residual ? residual + mb * ldr : nullptr;
+    float* Pb = partial;  // split-K is only planned for short problems (single band)
+    if (!transA && transB)
+      gemm_f32_kernel<false, true><<<g, GEMM_THREADS, 0, st>>>((int)Mb, (int)N, (int)K, Ab, lda, B, ldb, Cb, ldc, bias,
+                                                              act, Rb, ldr, Pb, p.kchunk);
+    else if (!transA && !transB)
+      gemm_f32_kernel<false, false><<<g, GEMM_THREADS, 0, st>>>((int)Mb, (int)N, (int)K, Ab, lda, B, ldb, Cb, ldc,
+                                                               bias, act, Rb, ldr, Pb, p.kchunk);
+    else
+      gemm_f32_kernel<true, false><<<g, GEMM_THREADS, 0, st>>>((int)Mb, (int)N, (int)K, Ab, lda, B, ldb, Cb, ldc, bias,
+                                                              act, Rb, ldr, Pb, p.kchunk);
+    CMP_LAUNCH_CHECK("cmp_gemm_f32");
+  }
+  if (p.S > 1) {
+    int64_t total = M * N;
+    splitk_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(partial, p.S, M, N, C, ldc, bias, act,
+                                                                        residual, ldr);
+    CMP_LAUNCH_CHECK("cmp_gemm_f32(split-K reduce)");
+  }
+  return CMP_OK;
+}
+
+extern "C" size_t cmp_colsum_workspace(int64_t M, int64_t N) {
+  if (M <= 0 || N <= 0) return 0;
+  return align_up((size_t)colsum_chunks(M) * N * sizeof(float), 256);
+}
+
+extern "C" int cmp_colsum_f32(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* workspace,
+                              size_t workspace_bytes, cmp_stream_t stream) {
+  CMP_REQUIRE(M >= 0 && N >= 0, CMP_EINVAL, "cmp_colsum_f32: negative size");
+  if (N == 0) return CMP_OK;
+  CMP_REQUIRE(out, CMP_EINVAL, "cmp_colsum_f32: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (M == 0) {
+    CMP_REQUIRE(cudaMemsetAsync(out, 0, N * sizeof(float), st) == cudaSuccess, CMP_ECUDA, "cmp_colsum_f32: memset");
+    return CMP_OK;
+  }
+  CMP_REQUIRE(X, CMP_EINVAL, "cmp_colsum_f32: null pointer");
+  int chunks = colsum_chunks(M);
+  CMP_REQUIRE(workspace && workspace_bytes >= (size_t)chunks * N * sizeof(float), CMP_EWORKSPACE,
+              "cmp_colsum_f32: workspace too small");
+  int rows_per_chunk = (int)ceil_div(M, chunks);
+  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)chunks);
+  colsum_stage1_kernel<<<grid, dim3(32, CS_ROWS), 0, st>>>(X, ldx, M, (int)N, rows_per_chunk,
+                                                          reinterpret_cast<float*>(workspace));
+  CMP_LAUNCH_CHECK("cmp_colsum_f32(stage1)");
+  colsum_stage2_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>(reinterpret_cast<float*>(workspace), chunks, (int)N,
+                                                                  out);
+  CMP_LAUNCH_CHECK("cmp_colsum_f32(stage2)");
+  return CMP_OK;
+}
+
+extern "C" int cmp_act_fwd(const float* x, float* y, int64_t n, int act, cmp_stream_t stream) {
+  CMP_REQUIRE(n >= 0, CMP_EINVAL, "cmp_act_fwd: negative size");
+  if (n == 0) return CMP_OK;
+  CMP_REQUIRE(x && y, CMP_EINVAL, "cmp_act_fwd: null pointer");
+  CMP_REQUIRE(act >= CMP_ACT_NONE && act <= CMP_ACT_SILU, CMP_EINVAL, "cmp_act_fwd: unknown activation %d", act);
+  act_fwd_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(x, y, n, act);
+  CMP_LAUNCH_CHECK("cmp_act_fwd");
+  return CMP_OK;
+}
+
+extern "C" int cmp_act_bwd(const float* dy, const float* saved, float* dx, int64_t n, int act, cmp_stream_t stream) {
+  CMP_REQUIRE(n >= 0, CMP_EINVAL, "cmp_act_bwd: negative size");
+  if (n == 0) return CMP_OK;
+  CMP_REQUIRE(dy && dx && (saved || act == CMP_ACT_NONE), CMP_EINVAL, "cmp_act_bwd: null pointer");
+  CMP_REQUIRE(act >= CMP_ACT_NONE && act <= CMP_ACT_SILU, CMP_EINVAL, "cmp_act_bwd: unknown activation %d", act);
+  act_bwd_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(dy, saved, dx, n, act);
+  CMP_LAUNCH_CHECK("cmp_act_bwd");
+  return CMP_OK;
+}
+
+extern "C" int cmp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                             cmp_stream_t stream) {
+  CMP_REQUIRE(n >= 0 && step >= 1, CMP_EINVAL, "cmp_adam_step: bad size/step");
+  if (n == 0) return CMP_OK;
+  CMP_REQUIRE(param && grad && exp_avg && exp_avg_sq, CMP_EINVAL, "cmp_adam_step: null pointer");
+  float bc1 = 1.0f - powf(beta1, (float)step);
+  float bc2 = sqrtf(1.0f - powf(beta2, (float)step));
+  adam_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                          weight_decay, bc1, bc2, grad_scale);
+  CMP_LAUNCH_CHECK("cmp_adam_step");
+  return CMP_OK;
+}

@@ -1,0 +1,341 @@
+// Neighbour-list kernels: sorted batch -> conformer segments -> destination-sorted CSR
+// (+ source-sorted transpose).  One CTA per conformer; a conformer's coordinates live in
+// shared memory while its n*n pair tests run.  Integer outputs are bit-exact against
+// oracle/radius.py (torch-cluster CUDA truncation rule).
+#include "common.cuh"
+
+namespace cmp {
+namespace {
+
+constexpr int kGraphThreads = 128;
+constexpr int kSmemAtoms = 2048;  // conformers up to this size are staged in shared memory
+
+__global__ void batch_to_segments_kernel(const int64_t* __restrict__ batch, int64_t N, int64_t G,
+                                         int32_t* __restrict__ seg_ptr, int* status) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (N == 0) {
+    if (i <= G) seg_ptr[i] = 0;
+    return;
+  }
+  if (i >= N) return;
+  int64_t b = batch[i];
+  int64_t prev = (i == 0) ? -1 : batch[i - 1];
+  if (b < prev || b < 0) atomicOr(status, CMP_STATUS_UNSORTED_BATCH);
+  if (b >= G) {
+    atomicOr(status, CMP_STATUS_UNSORTED_BATCH);
+    b = G - 1;
+  }
+  for (int64_t g = prev + 1; g <= b; ++g)
+    if (g >= 0 && g < G) seg_ptr[g] = (int32_t)i;
+  if (i == N - 1)
+    for (int64_t g = b + 1; g <= G; ++g) seg_ptr[g] = (int32_t)N;
+}
+
+// d2 exactly as the oracle: each product and each sum individually rounded.
+__device__ __forceinline__ float dist2_nofma(float ax, float ay, float az, float bx, float by, float bz) {
+  float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+struct PosView {
+  const float* x;
+  const float* y;
+  const float* z;
+  int stride;  // 1 for shared SoA, 3 for global AoS
+  __device__ __forceinline__ void get(int j, float& px, float& py, float& pz) const {
+    px = x[j * stride];
+    py = y[j * stride];
+    pz = z[j * stride];
+  }
+};
+
+__device__ __forceinline__ PosView stage_positions(const float* __restrict__ pos, int s, int n, float* smem) {
+  PosView v;
+  if (n <= kSmemAtoms) {
+    for (int t = threadIdx.x; t < n * 3; t += blockDim.x) {
+      int a = t / 3, c = t - a * 3;
+      smem[c * kSmemAtoms + a] = pos[(int64_t)s * 3 + t];
+    }
+    __syncthreads();
+    v.x = smem;
+    v.y = smem + kSmemAtoms;
+    v.z = smem + 2 * kSmemAtoms;
+    v.stride = 1;
+  } else {
+    v.x = pos + (int64_t)s * 3;
+    v.y = v.x + 1;
+    v.z = v.x + 2;
+    v.stride = 3;
+  }
+  return v;
+}
+
+// pass 1: out-degree (as a target) of each atom + per-conformer edge totals
+__global__ void __launch_bounds__(kGraphThreads)
+radius_count_kernel(const float* __restrict__ pos, const int32_t* __restrict__ seg_ptr, float r2, int cap,
+                    int loop, int32_t* __restrict__ deg, int32_t* __restrict__ conf_edges) {
+  __shared__ float spos[3 * kSmemAtoms];
+  __shared__ int warp_sums[kGraphThreads / 32];
+  const int g = blockIdx.x;
+  const int s = seg_ptr[g], e = seg_ptr[g + 1], n = e - s;
+  PosView P = stage_positions(pos, s, n, spos);
+  int local = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float xi, yi, zi;
+    P.get(i, xi, yi, zi);
+    int count = 0, d = 0;
+    for (int j = 0; j < n; ++j) {
+      float xj, yj, zj;
+      P.get(j, xj, yj, zj);
+      if (dist2_nofma(xj, yj, zj, xi, yi, zi) < r2) {
+        if (loop || j != i) ++d;
+        if (++count >= cap) break;
+      }
+    }
+    deg[s + i] = d;
+    local += d;
+  }
+  for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kGraphThreads / 32; ++w) t += warp_sums[w];
+    conf_edges[g] = t;
+  }
+}
+
+// pass 2: exclusive scan of per-conformer totals (single CTA, any G)
+__global__ void __launch_bounds__(1024)
+scan_conformers_kernel(const int32_t* __restrict__ conf_edges, int64_t G, int32_t* __restrict__ conf_edge_ptr) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int64_t base = 0; base < G; base += 1024) {
+    int64_t i = base + threadIdx.x;
+    int v = (i < G) ? conf_edges[i] : 0;
+    int inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      int t = warp_tot[lane];
+      int ti = t;
+      for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, ti, o);
+        if (lane >= o) ti += u;
+      }
+      warp_tot[lane] = ti - t;  // exclusive offset of each warp
+    }
+    __syncthreads();
+    int carry = carry_s;
+    if (i < G) conf_edge_ptr[i] = carry + warp_tot[w] + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_tot[w] + inc;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) conf_edge_ptr[G] = carry_s;
+}
+
+// pass 3: fill col/dist(/evec) in CSR order, then the source-sorted transpose
+__global__ void __launch_bounds__(kGraphThreads)
+radius_fill_kernel(const float* __restrict__ pos, const int32_t* __restrict__ seg_ptr, float r2, int cap, int loop,
+                   int64_t cap_E, int64_t N, int64_t G, const int32_t* __restrict__ deg,
+                   const int32_t* __restrict__ conf_edge_ptr, int32_t* __restrict__ rowptr,
+                   int32_t* __restrict__ col, float* __restrict__ dist, float* __restrict__ evec,
+                   int32_t* __restrict__ rowptr_t, int32_t* __restrict__ col_t, int32_t* __restrict__ eid_t,
+                   int32_t* __restrict__ tcount, int* status) {
+  __shared__ float spos[3 * kSmemAtoms];
+  const int g = blockIdx.x;
+  const int s = seg_ptr[g], e = seg_ptr[g + 1], n = e - s;
+  const int ebase = conf_edge_ptr[g];
+  PosView P = stage_positions(pos, s, n, spos);
+
+  // row offsets: warp 0 scans the degrees of this conformer
+  if (threadIdx.x < 32) {
+    int carry = ebase;
+    for (int base = 0; base < n; base += 32) {
+      int i = base + threadIdx.x;
+      int v = (i < n) ? deg[s + i] : 0;
+      int inc = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)threadIdx.x >= o) inc += t;
+      }
+      if (i < n) rowptr[s + i] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (g == G - 1 && threadIdx.x == 0) rowptr[N] = conf_edge_ptr[G];
+  }
+  __syncthreads();
+  if ((int64_t)conf_edge_ptr[g + 1] > cap_E) {
+    if (threadIdx.x == 0) atomicOr(status, CMP_STATUS_EDGE_OVERFLOW);
+    return;  // capacity exceeded: this conformer's edges are not written
+  }
+
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float xi, yi, zi;
+    P.get(i, xi, yi, zi);
+    int count = 0;
+    int w = rowptr[s + i];
+    for (int j = 0; j < n; ++j) {
+      float xj, yj, zj;
+      P.get(j, xj, yj, zj);
+      if (dist2_nofma(xj, yj, zj, xi, yi, zi) < r2) {
+        if (loop || j != i) {
+          col[w] = s + j;
+          float dx = xj - xi, dy = yj - yi, dz = zj - zi;
+          dist[w] = (j == i) ? 0.0f : sqrtf(dx * dx + dy * dy + dz * dz);
+          if (evec) {
+            evec[3 * (int64_t)w + 0] = dx;
+            evec[3 * (int64_t)w + 1] = dy;
+            evec[3 * (int64_t)w + 2] = dz;
+          }
+          ++w;
+        }
+        if (++count >= cap) break;
+      }
+    }
+  }
+  if (!rowptr_t) return;
+  __syncthreads();  // this CTA's col[] rows are now visible to all of its threads
+
+  // transpose: for source j, the rows i (ascending) whose sorted col list contains j
+  auto find_in_row = [&](int i, int j) -> int {
+    int lo = rowptr[s + i];
+    int hi = (i + 1 < n) ? rowptr[s + i + 1] : conf_edge_ptr[g + 1];
+    int target = s + j;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      int c = col[mid];
+      if (c == target) return mid;
+      if (c < target) lo = mid + 1; else hi = mid;
+    }
+    return -1;
+  };
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    int c = 0;
+    for (int i = 0; i < n; ++i) c += (find_in_row(i, j) >= 0);
+    tcount[s + j] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int carry = ebase;
+    for (int base = 0; base < n; base += 32) {
+      int j = base + threadIdx.x;
+      int v = (j < n) ? tcount[s + j] : 0;
+      int inc = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)threadIdx.x >= o) inc += t;
+      }
+      if (j < n) rowptr_t[s + j] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (g == G - 1 && threadIdx.x == 0) rowptr_t[N] = conf_edge_ptr[G];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    int w = rowptr_t[s + j];
+    for (int i = 0; i < n; ++i) {
+      int p = find_in_row(i, j);
+      if (p >= 0) {
+        col_t[w] = s + i;
+        eid_t[w] = p;
+        ++w;
+      }
+    }
+  }
+}
+
+__global__ void csr_to_edge_index_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                         int64_t N, int64_t E, int64_t* __restrict__ ei) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int b = rowptr[i], e = rowptr[i + 1];
+  for (int k = b; k < e && k < E; ++k) {
+    ei[k] = col[k];
+    ei[E + k] = i;
+  }
+}
+
+__global__ void set_i32_kernel(int32_t* p, int64_t n, int32_t v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+}  // namespace cmp
+
+using namespace cmp;
+
+extern "C" int cmp_batch_to_segments(const int64_t* batch, int64_t N, int64_t G, int32_t* seg_ptr, int* status,
+                                     cmp_stream_t stream) {
+  CMP_REQUIRE(N >= 0 && G >= 0, CMP_EINVAL, "cmp_batch_to_segments: negative size");
+  CMP_REQUIRE(seg_ptr && status && (batch || N == 0), CMP_EINVAL, "cmp_batch_to_segments: null pointer");
+  CMP_REQUIRE(N < (int64_t)1 << 31, CMP_EUNSUPPORTED, "cmp_batch_to_segments: N must fit int32");
+  int64_t work = (N == 0) ? G + 1 : N;
+  int blocks = (int)ceil_div(work, 256);
+  batch_to_segments_kernel<<<blocks, 256, 0, as_stream(stream)>>>(batch, N, G, seg_ptr, status);
+  CMP_LAUNCH_CHECK("cmp_batch_to_segments");
+  return CMP_OK;
+}
+
+extern "C" size_t cmp_radius_csr_workspace(int64_t N, int64_t G) {
+  // deg[N] + tcount[N] + conf_edges[G]
+  return align_up((size_t)(2 * N + G + 8) * sizeof(int32_t), 256);
+}
+
+extern "C" int cmp_radius_csr(const float* pos, const int32_t* seg_ptr, int64_t N, int64_t G, double r,
+                              int max_num_neighbors, int loop, int64_t cap_E, int32_t* rowptr, int32_t* col,
+                              float* dist, float* evec, int32_t* rowptr_t, int32_t* col_t, int32_t* eid_t,
+                              int32_t* conf_edge_ptr, void* workspace, size_t workspace_bytes, int* status,
+                              cmp_stream_t stream) {
+  CMP_REQUIRE(N >= 0 && G >= 0 && cap_E >= 0, CMP_EINVAL, "cmp_radius_csr: negative size");
+  CMP_REQUIRE(seg_ptr && rowptr && conf_edge_ptr && status, CMP_EINVAL, "cmp_radius_csr: null pointer");
+  CMP_REQUIRE((pos && col && dist) || N == 0, CMP_EINVAL, "cmp_radius_csr: null pointer");
+  CMP_REQUIRE((rowptr_t != nullptr) == (col_t != nullptr) && (col_t != nullptr) == (eid_t != nullptr), CMP_EINVAL,
+              "cmp_radius_csr: rowptr_t/col_t/eid_t must be given together");
+  CMP_REQUIRE(max_num_neighbors >= 1, CMP_EINVAL, "cmp_radius_csr: max_num_neighbors must be >= 1");
+  CMP_REQUIRE(workspace_bytes >= cmp_radius_csr_workspace(N, G) && workspace, CMP_EWORKSPACE,
+              "cmp_radius_csr: workspace too small (%zu < %zu)", workspace_bytes, cmp_radius_csr_workspace(N, G));
+  CMP_REQUIRE(N * (int64_t)(max_num_neighbors + 1) < ((int64_t)1 << 31), CMP_EUNSUPPORTED,
+              "cmp_radius_csr: edge count must fit int32");
+  cudaStream_t st = as_stream(stream);
+  if (N == 0 || G == 0) {
+    set_i32_kernel<<<1, 32, 0, st>>>(rowptr, 1, 0);
+    if (rowptr_t) set_i32_kernel<<<1, 32, 0, st>>>(rowptr_t, 1, 0);
+    set_i32_kernel<<<(int)ceil_div(G + 1, 256), 256, 0, st>>>(conf_edge_ptr, G + 1, 0);
+    CMP_LAUNCH_CHECK("cmp_radius_csr(empty)");
+    return CMP_OK;
+  }
+  int32_t* deg = reinterpret_cast<int32_t*>(workspace);
+  int32_t* tcount = deg + N;
+  int32_t* conf_edges = tcount + N;
+  const float r2 = (float)(r * r);
+  const int cap = loop ? max_num_neighbors : max_num_neighbors + 1;
+  radius_count_kernel<<<(unsigned)G, kGraphThreads, 0, st>>>(pos, seg_ptr, r2, cap, loop, deg, conf_edges);
+  CMP_LAUNCH_CHECK("cmp_radius_csr(count)");
+  scan_conformers_kernel<<<1, 1024, 0, st>>>(conf_edges, G, conf_edge_ptr);
+  CMP_LAUNCH_CHECK("cmp_radius_csr(scan)");
+  radius_fill_kernel<<<(unsigned)G, kGraphThreads, 0, st>>>(pos, seg_ptr, r2, cap, loop, cap_E, N, G, deg,
+                                                            conf_edge_ptr, rowptr, col, dist, evec, rowptr_t,
+                                                            col_t, eid_t, tcount, status);
+  CMP_LAUNCH_CHECK("cmp_radius_csr(fill)");
+  return CMP_OK;
+}
+
+extern "C" int cmp_csr_to_edge_index(const int32_t* rowptr, const int32_t* col, int64_t N, int64_t E,
+                                     int64_t* edge_index, cmp_stream_t stream) {
+  CMP_REQUIRE(N >= 0 && E >= 0, CMP_EINVAL, "cmp_csr_to_edge_index: negative size");
+  if (N == 0 || E == 0) return CMP_OK;
+  CMP_REQUIRE(rowptr && col && edge_index, CMP_EINVAL, "cmp_csr_to_edge_index: null pointer");
+  csr_to_edge_index_kernel<<<(int)ceil_div(N, 256), 256, 0, as_stream(stream)>>>(rowptr, col, N, E, edge_index);
+  CMP_LAUNCH_CHECK("cmp_csr_to_edge_index");
+  return CMP_OK;
+}

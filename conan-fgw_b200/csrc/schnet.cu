@@ -1,0 +1,302 @@
+// SchNet pieces of the exact-fp32 path: Gaussian RBF, embedding, CFConv message/aggregate (CSR
+// gather-reduce, deterministic), sum readout.  The E x F filter is materialised only on this
+// path; the fused tcgen05 kernel (cfconv_tc.cu) keeps it on chip.
+#include "common.cuh"
+
+namespace cmp {
+namespace {
+
+__global__ void rbf_gaussian_kernel(const float* __restrict__ d, int64_t E, const float* __restrict__ offset, int Ng,
+                                    float coeff, float* __restrict__ out, int64_t ldo) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = E * Ng;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; idx < total; idx += stride) {
+    int64_t e = idx / Ng;
+    int k = (int)(idx - e * Ng);
+    float t = d[e] - offset[k];
+    out[e * ldo + k] = expf(coeff * (t * t));
+  }
+}
+
+__global__ void embedding_fwd_kernel(const int64_t* __restrict__ z, int64_t N, const float* __restrict__ w, int V,
+                                     int H, float* __restrict__ out, int* status) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t total = N * H;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; idx < total; idx += stride) {
+    int64_t i = idx / H;
+    int c = (int)(idx - i * H);
+    int64_t zi = z[i];
+    if (zi < 0 || zi >= V) {
+      if (c == 0) atomicOr(status, CMP_STATUS_BAD_ATOMIC_NUMBER);
+      out[idx] = 0.0f;
+    } else {
+      out[idx] = w[zi * H + c];
+    }
+  }
+}
+
+// stage 1: each CTA owns a contiguous chunk of atoms and accumulates dweight rows in shared memory
+// sequentially (fixed order); stage 2 sums the chunk partials in chunk order.
+__global__ void embedding_bwd_stage1(const int64_t* __restrict__ z, int64_t N, const float* __restrict__ dout, int V,
+                                     int H, int chunk, float* __restrict__ partial) {
+  extern __shared__ float acc[];  // [V][H]
+  for (int t = threadIdx.x; t < V * H; t += blockDim.x) acc[t] = 0.0f;
+  __syncthreads();
+  int64_t i0 = (int64_t)blockIdx.x * chunk;
+  int64_t i1 = i0 + chunk;
+  if (i1 > N) i1 = N;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    for (int64_t i = i0; i < i1; ++i) {
+      int64_t zi = z[i];
+      if (zi >= 0 && zi < V) acc[zi * H + c] += dout[i * H + c];
+    }
+  }
+  __syncthreads();
+  float* P = partial + (int64_t)blockIdx.x * V * H;
+  for (int t = threadIdx.x; t < V * H; t += blockDim.x) P[t] = acc[t];
+}
+
+__global__ void embedding_bwd_stage2(const float* __restrict__ partial, int chunks, int V, int H, int padding_idx,
+                                     float* __restrict__ dweight) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= V * H) return;
+  float s = 0.0f;
+  for (int c = 0; c < chunks; ++c) s += partial[(int64_t)c * V * H + t];
+  if (t / H == padding_idx) s = 0.0f;
+  dweight[t] = s;
+}
+
+int embedding_chunk(int64_t N) {
+  int64_t c = ceil_div(N, 512);
+  return (int)(c < 1024 ? 1024 : c);
+}
+
+// One warp per target row; lanes stride the channel axis (float4 when F % 4 == 0).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+cfconv_message_fwd_kernel(const float* __restrict__ xprime, const float* __restrict__ filt,
+                          const float* __restrict__ dist, const int32_t* __restrict__ rowptr,
+                          const int32_t* __restrict__ col, int64_t N, int F, float cutoff, float* __restrict__ agg) {
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  int b = rowptr[row], e = rowptr[row + 1];
+  for (int c = lane * VEC; c < F; c += 32 * VEC) {
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.0f;
+    for (int k = b; k < e; ++k) {
+      int j = col[k];
+      float C = 0.5f * (cosf(dist[k] * kPi / cutoff) + 1.0f);
+      if (VEC == 4) {
+        float4 x = *reinterpret_cast<const float4*>(xprime + (int64_t)j * F + c);
+        float4 w = *reinterpret_cast<const float4*>(filt + (int64_t)k * F + c);
+        acc[0] += x.x * (w.x * C);
+        acc[1 % VEC] += x.y * (w.y * C);
+        acc[2 % VEC] += x.z * (w.z * C);
+        acc[3 % VEC] += x.w * (w.w * C);
+      } else {
+        acc[0] += xprime[(int64_t)j * F + c] * (filt[(int64_t)k * F + c] * C);
+      }
+    }
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(agg + row * F + c) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+    } else {
+      agg[row * F + c] = acc[0];
+    }
+  }
+}
+
+// dfilt[e] = g[dst(e)] * xprime[col[e]] * C(e)   (warp per target row)
+__global__ void __launch_bounds__(256)
+cfconv_dfilt_kernel(const float* __restrict__ g, const float* __restrict__ xprime, const float* __restrict__ dist,
+                    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N, int F,
+                    float cutoff, float* __restrict__ dfilt) {
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  int b = rowptr[row], e = rowptr[row + 1];
+  for (int k = b; k < e; ++k) {
+    int j = col[k];
+    float C = 0.5f * (cosf(dist[k] * kPi / cutoff) + 1.0f);
+    for (int c = lane; c < F; c += 32)
+      dfilt[(int64_t)k * F + c] = g[row * F + c] * xprime[(int64_t)j * F + c] * C;
+  }
+}
+
+// dxprime[j] = sum over the transposed row of j   (warp per source atom; fixed order)
+__global__ void __launch_bounds__(256)
+cfconv_dx_kernel(const float* __restrict__ g, const float* __restrict__ filt, const float* __restrict__ dist,
+                 const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
+                 const int32_t* __restrict__ eid_t, int64_t N, int F, float cutoff, float* __restrict__ dx) {
+  int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  int b = rowptr_t[row], e = rowptr_t[row + 1];
+  for (int c = lane; c < F; c += 32) {
+    float acc = 0.0f;
+    for (int k = b; k < e; ++k) {
+      int i = col_t[k];
+      int eid = eid_t[k];
+      float C = 0.5f * (cosf(dist[eid] * kPi / cutoff) + 1.0f);
+      acc += g[(int64_t)i * F + c] * (filt[(int64_t)eid * F + c] * C);
+    }
+    dx[row * F + c] = acc;
+  }
+}
+
+__global__ void segment_sum_fwd_kernel(const float* __restrict__ x, const int32_t* __restrict__ seg_ptr, int C,
+                                       float* __restrict__ out) {
+  int g = blockIdx.x;
+  int s = seg_ptr[g], e = seg_ptr[g + 1];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.0f;
+    for (int i = s; i < e; ++i) acc += x[(int64_t)i * C + c];
+    out[(int64_t)g * C + c] = acc;
+  }
+}
+
+__global__ void segment_sum_bwd_kernel(const float* __restrict__ dout, const int32_t* __restrict__ seg_ptr, int C,
+                                       float* __restrict__ dx) {
+  int g = blockIdx.x;
+  int s = seg_ptr[g], e = seg_ptr[g + 1];
+  int64_t total = (int64_t)(e - s) * C;
+  for (int64_t t = threadIdx.x; t < total; t += blockDim.x) {
+    int c = (int)(t % C);
+    dx[(int64_t)s * C + t] = dout[(int64_t)g * C + c];
+  }
+}
+
+int grid1d(int64_t n, int per_block = 256) {
+  int64_t b = ceil_div(n, per_block);
+  int64_t cap = (int64_t)sm_count() * 32;
+  if (b < 1) b = 1;
+  return (int)(b < cap ? b : cap);
+}
+
+}  // namespace
+}  // namespace cmp
+
+using namespace cmp;
+
+extern "C" int cmp_rbf_gaussian_fwd(const float* d, int64_t E, const float* offset, int Ng, float coeff, float* out,
+                                    int64_t ldo, cmp_stream_t stream) {
+  CMP_REQUIRE(E >= 0 && Ng >= 1 && ldo >= Ng, CMP_EINVAL, "cmp_rbf_gaussian_fwd: bad size");
+  if (E == 0) return CMP_OK;
+  CMP_REQUIRE(d && offset && out, CMP_EINVAL, "cmp_rbf_gaussian_fwd: null pointer");
+  rbf_gaussian_kernel<<<grid1d(E * Ng), 256, 0, as_stream(stream)>>>(d, E, offset, Ng, coeff, out, ldo);
+  CMP_LAUNCH_CHECK("cmp_rbf_gaussian_fwd");
+  return CMP_OK;
+}
+
+extern "C" int cmp_embedding_fwd(const int64_t* z, int64_t N, const float* weight, int V, int H, float* out,
+                                 int* status, cmp_stream_t stream) {
+  CMP_REQUIRE(N >= 0 && V >= 1 && H >= 1, CMP_EINVAL, "cmp_embedding_fwd: bad size");
+  if (N == 0) return CMP_OK;
+  CMP_REQUIRE(z && weight && out && status, CMP_EINVAL, "cmp_embedding_fwd: null pointer");
+  embedding_fwd_kernel<<<grid1d(N * H), 256, 0, as_stream(stream)>>>(z, N, weight, V, H, out, status);
+  CMP_LAUNCH_CHECK("cmp_embedding_fwd");
+  return CMP_OK;
+}
+
+extern "C" size_t cmp_embedding_bwd_workspace(int64_t N, int V, int H) {
+  if (N <= 0) return 256;
+  int64_t chunks = ceil_div(N, embedding_chunk(N));
+  return align_up((size_t)chunks * V * H * sizeof(float), 256);
+}
+
+extern "C" int cmp_embedding_bwd(const int64_t* z, int64_t N, const float* dout, int V, int H, int padding_idx,
+                                 float* dweight, void* workspace, size_t workspace_bytes, cmp_stream_t stream) {
+  CMP_REQUIRE(N >= 0 && V >= 1 && H >= 1, CMP_EINVAL, "cmp_embedding_bwd: bad size");
+  CMP_REQUIRE(dweight, CMP_EINVAL, "cmp_embedding_bwd: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (N == 0) {
+    CMP_REQUIRE(cudaMemsetAsync(dweight, 0, (size_t)V * H * sizeof(float), st) == cudaSuccess, CMP_ECUDA,
+                "cmp_embedding_bwd: memset failed");
+    return CMP_OK;
+  }
+  CMP_REQUIRE(z && dout, CMP_EINVAL, "cmp_embedding_bwd: null pointer");
+  size_t smem = (size_t)V * H * sizeof(float);
+  CMP_REQUIRE(smem <= 227 * 1024, CMP_EUNSUPPORTED, "cmp_embedding_bwd: V*H*4 = %zu bytes exceeds shared memory", smem);
+  int chunk = embedding_chunk(N);
+  int chunks = (int)ceil_div(N, chunk);
+  CMP_REQUIRE(workspace && workspace_bytes >= (size_t)chunks * V * H * sizeof(float), CMP_EWORKSPACE,
+              "cmp_embedding_bwd: workspace too small");
+  if (cudaFuncSetAttribute(embedding_bwd_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+      cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("cmp_embedding_bwd: cannot opt in to %zu bytes of shared memory", smem);
+    return CMP_ECUDA;
+  }
+  int threads = H < 256 ? ((H + 31) / 32) * 32 : 256;
+  embedding_bwd_stage1<<<chunks, threads, smem, st>>>(z, N, dout, V, H, chunk, reinterpret_cast<float*>(workspace));
+  CMP_LAUNCH_CHECK("cmp_embedding_bwd(stage1)");
+  embedding_bwd_stage2<<<(unsigned)ceil_div((int64_t)V * H, 256), 256, 0, st>>>(reinterpret_cast<float*>(workspace),
+                                                                               chunks, V, H, padding_idx, dweight);
+  CMP_LAUNCH_CHECK("cmp_embedding_bwd(stage2)");
+  return CMP_OK;
+}
+
+extern "C" int cmp_cfconv_message_fwd(const float* xprime, const float* filt, const float* dist, const int32_t* rowptr,
+                                      const int32_t* col, int64_t N, int F, float cutoff, float* agg,
+                                      cmp_stream_t stream) {
+  CMP_REQUIRE(N >= 0 && F >= 1 && cutoff > 0.0f, CMP_EINVAL, "cmp_cfconv_message_fwd: bad size");
+  if (N == 0) return CMP_OK;
+  CMP_REQUIRE(xprime && rowptr && agg, CMP_EINVAL, "cmp_cfconv_message_fwd: null pointer");
+  unsigned blocks = (unsigned)ceil_div(N * 32, 256);
+  bool vec = (F % 4 == 0) && (((uintptr_t)xprime | (uintptr_t)filt | (uintptr_t)agg) % 16 == 0);
+  if (vec)
+    cfconv_message_fwd_kernel<4><<<blocks, 256, 0, as_stream(stream)>>>(xprime, filt, dist, rowptr, col, N, F, cutoff,
+                                                                        agg);
+  else
+    cfconv_message_fwd_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(xprime, filt, dist, rowptr, col, N, F, cutoff,
+                                                                        agg);
+  CMP_LAUNCH_CHECK("cmp_cfconv_message_fwd");
+  return CMP_OK;
+}
+
+extern "C" int cmp_cfconv_message_bwd(const float* g, const float* xprime, const float* filt, const float* dist,
+                                      const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t,
+                                      const int32_t* col_t, const int32_t* eid_t, int64_t N, int F, float cutoff,
+                                      float* dfilt, float* dxprime, cmp_stream_t stream) {
+  CMP_REQUIRE(N >= 0 && F >= 1 && cutoff > 0.0f, CMP_EINVAL, "cmp_cfconv_message_bwd: bad size");
+  if (N == 0) return CMP_OK;
+  CMP_REQUIRE(g && rowptr, CMP_EINVAL, "cmp_cfconv_message_bwd: null pointer");
+  unsigned blocks = (unsigned)ceil_div(N * 32, 256);
+  if (dfilt) {
+    CMP_REQUIRE(xprime && col && dist, CMP_EINVAL, "cmp_cfconv_message_bwd: null pointer (dfilt inputs)");
+    cfconv_dfilt_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, xprime, dist, rowptr, col, N, F, cutoff, dfilt);
+    CMP_LAUNCH_CHECK("cmp_cfconv_message_bwd(dfilt)");
+  }
+  if (dxprime) {
+    CMP_REQUIRE(rowptr_t && col_t && eid_t && filt && dist, CMP_EINVAL,
+                "cmp_cfconv_message_bwd: null pointer (dxprime inputs)");
+    cfconv_dx_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, filt, dist, rowptr_t, col_t, eid_t, N, F, cutoff,
+                                                            dxprime);
+    CMP_LAUNCH_CHECK("cmp_cfconv_message_bwd(dx)");
+  }
+  return CMP_OK;
+}
+
+extern "C" int cmp_segment_sum_fwd(const float* x, const int32_t* seg_ptr, int64_t G, int C, float* out,
+                                   cmp_stream_t stream) {
+  CMP_REQUIRE(G >= 0 && C >= 1, CMP_EINVAL, "cmp_segment_sum_fwd: bad size");
+  if (G == 0) return CMP_OK;
+  CMP_REQUIRE(seg_ptr && out, CMP_EINVAL, "cmp_segment_sum_fwd: null pointer");
+  int threads = C < 256 ? ((C + 31) / 32) * 32 : 256;
+  segment_sum_fwd_kernel<<<(unsigned)G, threads, 0, as_stream(stream)>>>(x, seg_ptr, C, out);
+  CMP_LAUNCH_CHECK("cmp_segment_sum_fwd");
+  return CMP_OK;
+}
+
+extern "C" int cmp_segment_sum_bwd(const float* dout, const int32_t* seg_ptr, int64_t G, int C, float* dx,
+                                   cmp_stream_t stream) {
+  CMP_REQUIRE(G >= 0 && C >= 1, CMP_EINVAL, "cmp_segment_sum_bwd: bad size");
+  if (G == 0) return CMP_OK;
+  CMP_REQUIRE(dout && seg_ptr, CMP_EINVAL, "cmp_segment_sum_bwd: null pointer");
+  segment_sum_bwd_kernel<<<(unsigned)G, 256, 0, as_stream(stream)>>>(dout, seg_ptr, C, dx);
+  CMP_LAUNCH_CHECK("cmp_segment_sum_bwd");
+  return CMP_OK;
+}

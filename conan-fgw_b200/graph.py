@@ -1,0 +1,168 @@
+"""Neighbour lists: the drop-in for ``radius_graph`` / ``RadiusInteractionGraph``.
+
+Reference call sites replaced (paths in the reference tree):
+``conan_fgw/src/model/graph_embeddings/schnet_no_sum.py:160,208,342`` (through
+PyG ``RadiusInteractionGraph``), ``torch_geometric_visnet.py:331-347``
+(``Distance``), ``visnet.py:90,276``.
+
+The CUDA kernels emit a destination-sorted CSR (``rowptr``/``col``/``dist``) plus
+its source-sorted transpose.  ``radius_graph`` keeps PyG's signature and returns
+the PyG-format ``edge_index`` (canonical order: target-major, source ascending =
+the order torch-cluster's CUDA kernel produces); the returned tensor carries the
+CSR as ``edge_index._cmp_graph`` so that downstream modules of this package do
+not rebuild it.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+class NeighborList:
+    """Device-resident CSR neighbour list of a batch of conformers."""
+
+    def __init__(self, N, G, cap_E, device):
+        i32 = dict(dtype=torch.int32, device=device)
+        self.N, self.G, self.cap_E = int(N), int(G), int(cap_E)
+        self.seg_ptr = torch.empty(G + 1, **i32)
+        self.conf_edge_ptr = torch.empty(G + 1, **i32)
+        self.rowptr = torch.empty(N + 1, **i32)
+        self.col = torch.empty(max(cap_E, 1), **i32)
+        self.dist = torch.empty(max(cap_E, 1), dtype=torch.float32, device=device)
+        self.evec = None
+        self.rowptr_t = self.col_t = self.eid_t = None
+        self.status = torch.zeros(1, **i32)
+        self.cutoff = None
+        self.loop = False
+        self._E = None
+        self._edge_index = None
+        self._checked = False
+
+    @property
+    def E(self) -> int:
+        """Edge count (first access synchronises with the device)."""
+        if self._E is None:
+            self._E = int(self.rowptr[self.N].item()) if self.N > 0 else 0
+            self.check()
+        return self._E
+
+    def check(self):
+        """Raise for device-detected input errors (synchronises once)."""
+        if self._checked:
+            return
+        s = int(self.status.item())
+        self._checked = True
+        if s & _lib.STATUS_UNSORTED_BATCH:
+            raise ValueError("radius_graph: 'batch' must be sorted non-decreasing with ids in [0, num_graphs)")
+        if s & _lib.STATUS_EDGE_OVERFLOW:
+            raise RuntimeError("radius_graph: neighbour capacity overflow")
+        if s & _lib.STATUS_BAD_ATOMIC_NUMBER:
+            raise ValueError("atomic numbers must lie in [0, 100)")
+
+    def edge_index(self) -> torch.Tensor:
+        if self._edge_index is None:
+            E = self.E
+            ei = torch.empty(2, E, dtype=torch.int64, device=self.rowptr.device)
+            if E:
+                _lib.call("cmp_csr_to_edge_index", _lib.ptr(self.rowptr), _lib.ptr(self.col), self.N, E, _lib.ptr(ei))
+            ei._cmp_graph = self
+            self._edge_index = ei
+        return self._edge_index
+
+    def edge_weight(self) -> torch.Tensor:
+        w = self.dist[: self.E]
+        w._cmp_graph = self
+        return w
+
+
+def num_graphs_of(batch: torch.Tensor, num_graphs: Optional[int] = None) -> int:
+    if num_graphs is not None:
+        return int(num_graphs)
+    if batch.numel() == 0:
+        return 0
+    return int(batch[-1].item()) + 1  # batch is sorted: the last id is the largest (host sync)
+
+
+def build_neighbor_list(pos: torch.Tensor, batch: Optional[torch.Tensor], r: float, max_num_neighbors: int = 32,
+                        loop: bool = False, num_graphs: Optional[int] = None, want_evec: bool = False,
+                        want_transpose: bool = True) -> NeighborList:
+    if not pos.is_cuda:
+        raise _lib.ConanMPError("build_neighbor_list: pos must be a CUDA tensor (no CPU path)")
+    if pos.dim() != 2 or pos.size(1) != 3:
+        raise ValueError("pos must be [N, 3]")
+    pos = pos.detach().to(torch.float32).contiguous()
+    N = pos.size(0)
+    dev = pos.device
+    if batch is None:
+        batch = torch.zeros(N, dtype=torch.int64, device=dev)
+        num_graphs = 1 if N else 0
+    if batch.numel() != N:
+        raise ValueError("batch and pos disagree on the number of atoms")
+    batch = batch.to(torch.int64).contiguous()
+    G = num_graphs_of(batch, num_graphs)
+    cap = max_num_neighbors if loop else max_num_neighbors + 1
+    nl = NeighborList(N, G, N * cap, dev)
+    nl.cutoff, nl.loop = float(r), bool(loop)
+    i32 = dict(dtype=torch.int32, device=dev)
+    if want_evec:
+        nl.evec = torch.empty(max(nl.cap_E, 1), 3, dtype=torch.float32, device=dev)
+    if want_transpose:
+        nl.rowptr_t = torch.empty(N + 1, **i32)
+        nl.col_t = torch.empty(max(nl.cap_E, 1), **i32)
+        nl.eid_t = torch.empty(max(nl.cap_E, 1), **i32)
+    _lib.call("cmp_batch_to_segments", _lib.ptr(batch), N, G, _lib.ptr(nl.seg_ptr), _lib.ptr(nl.status))
+    ws_bytes = _lib.size_query("cmp_radius_csr_workspace", N, G)
+    ws = _lib.workspace(ws_bytes, dev)
+    _lib.call("cmp_radius_csr", _lib.ptr(pos), _lib.ptr(nl.seg_ptr), N, G, float(r), int(max_num_neighbors),
+              int(bool(loop)), nl.cap_E, _lib.ptr(nl.rowptr), _lib.ptr(nl.col), _lib.ptr(nl.dist),
+              _lib.ptr(nl.evec), _lib.ptr(nl.rowptr_t), _lib.ptr(nl.col_t), _lib.ptr(nl.eid_t),
+              _lib.ptr(nl.conf_edge_ptr), _lib.ptr(ws), ws.numel(), _lib.ptr(nl.status))
+    return nl
+
+
+def radius_graph(x: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None, loop: bool = False,
+                 max_num_neighbors: int = 32, flow: str = "source_to_target", num_workers: int = 1) -> torch.Tensor:
+    """``torch_geometric.nn.radius_graph`` drop-in (CUDA truncation rule, see ``oracle/radius.py``)."""
+    assert flow in ("source_to_target", "target_to_source")
+    nl = build_neighbor_list(x, batch, r, max_num_neighbors, loop)
+    ei = nl.edge_index()
+    if flow == "target_to_source":
+        return ei.flip(0)
+    return ei
+
+
+def graph_from_edge_index(edge_index: torch.Tensor, edge_weight: torch.Tensor, num_nodes: int):
+    """CSR view of an arbitrary ``edge_index`` (generic ``InteractionBlock`` entry, e.g. the covalent
+    graph of ``schnet_no_sum.py:166-174``).  Returns ``(graph, perm)``; ``perm`` reorders per-edge
+    tensors into CSR order (None when the input already is target-major)."""
+    tagged = getattr(edge_index, "_cmp_graph", None)
+    if tagged is not None and tagged.N == num_nodes:
+        return tagged, None
+    dev = edge_index.device
+    src, dst = edge_index[0], edge_index[1]
+    E = src.numel()
+    key = dst * num_nodes + src
+    perm = None
+    if E > 1 and bool((key[1:] < key[:-1]).any()):
+        perm = torch.argsort(key, stable=True)
+        src, dst = src[perm], dst[perm]
+    nl = NeighborList(num_nodes, 0, E, dev)
+    nl._E = E
+    nl._checked = True
+    counts = torch.bincount(dst, minlength=num_nodes)
+    nl.rowptr = torch.cat([counts.new_zeros(1), counts.cumsum(0)]).to(torch.int32)
+    nl.col = src.to(torch.int32).contiguous() if E else nl.col
+    w = edge_weight if perm is None else edge_weight[perm]
+    nl.dist = w.to(torch.float32).contiguous() if E else nl.dist
+    # transpose (source-major, target ascending)
+    tkey = src * num_nodes + dst
+    tperm = torch.argsort(tkey, stable=True)
+    tcounts = torch.bincount(src, minlength=num_nodes)
+    nl.rowptr_t = torch.cat([tcounts.new_zeros(1), tcounts.cumsum(0)]).to(torch.int32)
+    nl.col_t = dst[tperm].to(torch.int32).contiguous() if E else nl.col
+    nl.eid_t = tperm.to(torch.int32).contiguous() if E else nl.col
+    return nl, perm

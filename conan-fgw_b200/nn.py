@@ -1,0 +1,226 @@
+"""PyG-signature modules of the SchNet stack, backed by the sm_100a kernels.
+
+Drop-in for the names ConAN imports from torch-geometric 2.3.0
+(``conan_fgw/src/model/graph_embeddings/schnet_no_sum.py:6-9``, ``dimenet.py:9``,
+``visnet.py:11``): ``SchNet, InteractionBlock, CFConv, GaussianSmearing,
+ShiftedSoftplus, RadiusInteractionGraph, radius_graph``.  Constructor orders,
+attribute names and ``state_dict`` keys equal PyG's -
+including the aliased ``interactions.{t}.conv.nn.*`` entries - so existing ConAN
+checkpoints load with ``strict=True``.
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Callable, Optional
+
+import torch
+from torch import nn
+
+from . import _lib, ops
+from .graph import NeighborList, build_neighbor_list, graph_from_edge_index, radius_graph  # noqa: F401
+
+
+class Linear(nn.Linear):
+    """``torch.nn.Linear`` parameters and init, forward through ``cmp_gemm_f32``."""
+
+    def forward(self, x, act=_lib.ACT_NONE, residual=None):
+        return ops.linear(x, self.weight, self.bias, act, residual)
+
+
+class ShiftedSoftplus(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.shift = math.log(2.0)
+
+    def forward(self, x):
+        return ops.shifted_softplus(x)
+
+
+class GaussianSmearing(nn.Module):
+    def __init__(self, start: float = 0.0, stop: float = 5.0, num_gaussians: int = 50):
+        super().__init__()
+        offset = torch.linspace(start, stop, num_gaussians)
+        self.coeff = -0.5 / (offset[1] - offset[0]).item() ** 2
+        self.register_buffer("offset", offset)
+
+    def forward(self, dist):
+        out = ops.gaussian_rbf(dist, self.offset, self.coeff)
+        # remember what this expansion was computed from, so CFConv can run the fused geometric kernel
+        out._cmp_rbf_of = (dist, self)
+        return out
+
+
+class RadiusInteractionGraph(nn.Module):
+    def __init__(self, cutoff: float = 10.0, max_num_neighbors: int = 32):
+        super().__init__()
+        self.cutoff = cutoff
+        self.max_num_neighbors = max_num_neighbors
+
+    def neighbor_list(self, pos, batch, num_graphs=None) -> NeighborList:
+        return build_neighbor_list(pos, batch, self.cutoff, self.max_num_neighbors, loop=False,
+                                   num_graphs=num_graphs)
+
+    def forward(self, pos, batch):
+        nl = self.neighbor_list(pos, batch)
+        return nl.edge_index(), nl.edge_weight()
+
+
+class SumAggregation(nn.Module):
+    """``aggr_resolver('add')``: ``readout(x, index, dim=0)`` over a sorted index."""
+
+    def forward(self, x, index=None, ptr=None, dim_size=None, dim=0, seg_ptr=None):
+        if dim not in (0, -2):
+            raise ValueError("SumAggregation: only dim=0 is provided")
+        if index is None and seg_ptr is None:
+            seg_ptr = torch.tensor([0, x.size(0)], dtype=torch.int32, device=x.device)
+            return ops.segment_sum(x, seg_ptr, 1)
+        if seg_ptr is None:
+            seg_ptr, G = ops.segments_from_batch(index, dim_size)
+        else:
+            G = seg_ptr.numel() - 1
+        return ops.segment_sum(x, seg_ptr, G)
+
+
+class CFConv(nn.Module):
+    """Continuous-filter convolution (PyG ``CFConv``, aggr='add')."""
+
+    def __init__(self, in_channels: int, out_channels: int, num_filters: int, nn: nn.Sequential, cutoff: float):
+        super().__init__()
+        self.lin1 = Linear(in_channels, num_filters, bias=False)
+        self.lin2 = Linear(num_filters, out_channels)
+        self.nn = nn
+        self.cutoff = cutoff
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        torch.nn.init.xavier_uniform_(self.lin1.weight)
+        torch.nn.init.xavier_uniform_(self.lin2.weight)
+        self.lin2.bias.data.fill_(0)
+
+    def filter(self, edge_attr):
+        """``self.nn(edge_attr)``: Linear -> ShiftedSoftplus -> Linear with the activation fused."""
+        net = self.nn
+        if (isinstance(net, torch.nn.Sequential) and len(net) == 3 and isinstance(net[0], Linear)
+                and isinstance(net[1], ShiftedSoftplus) and isinstance(net[2], Linear)):
+            return net[2](net[0](edge_attr, act=_lib.ACT_SSP))
+        return net(edge_attr)
+
+    def forward(self, x, edge_index, edge_weight, edge_attr, graph: Optional[NeighborList] = None,
+                act=_lib.ACT_NONE):
+        if graph is None:
+            graph, perm = graph_from_edge_index(edge_index, edge_weight, x.size(0))
+            if perm is not None:
+                edge_attr = edge_attr[perm]
+        W = self.filter(edge_attr)
+        xp = self.lin1(x)
+        agg = ops.cfconv_message(xp, W, graph, self.cutoff)
+        return self.lin2(agg, act=act)
+
+
+class InteractionBlock(nn.Module):
+    def __init__(self, hidden_channels: int, num_gaussians: int, num_filters: int, cutoff: float):
+        super().__init__()
+        self.mlp = nn.Sequential(
+            Linear(num_gaussians, num_filters),
+            ShiftedSoftplus(),
+            Linear(num_filters, num_filters),
+        )
+        self.conv = CFConv(hidden_channels, hidden_channels, num_filters, self.mlp, cutoff)
+        self.act = ShiftedSoftplus()
+        self.lin = Linear(hidden_channels, hidden_channels)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        torch.nn.init.xavier_uniform_(self.mlp[0].weight)
+        self.mlp[0].bias.data.fill_(0)
+        torch.nn.init.xavier_uniform_(self.mlp[2].weight)
+        self.mlp[2].bias.data.fill_(0)
+        self.conv.reset_parameters()
+        torch.nn.init.xavier_uniform_(self.lin.weight)
+        self.lin.bias.data.fill_(0)
+
+    def forward(self, x, edge_index, edge_weight, edge_attr, graph: Optional[NeighborList] = None,
+                residual=None):
+        # conv -> ssp (fused into conv.lin2's epilogue) -> lin (+ residual fused when the caller passes it)
+        y = self.conv(x, edge_index, edge_weight, edge_attr, graph=graph, act=_lib.ACT_SSP)
+        return self.lin(y, residual=residual)
+
+
+class SchNet(nn.Module):
+    """PyG 2.3.0 ``SchNet`` (positional constructor order as used at ``schnet_no_sum.py:109-122``)."""
+
+    def __init__(self, hidden_channels: int = 128, num_filters: int = 128, num_interactions: int = 6,
+                 num_gaussians: int = 50, cutoff: float = 10.0, interaction_graph: Optional[Callable] = None,
+                 max_num_neighbors: int = 32, readout: str = "add", dipole: bool = False,
+                 mean: Optional[float] = None, std: Optional[float] = None, atomref=None):
+        super().__init__()
+        if dipole or atomref is not None:
+            raise NotImplementedError("dipole / atomref variants are not instantiated by ConAN (SURVEY.md 2.1)")
+        if readout not in ("add", "sum"):
+            raise NotImplementedError("only the sum readout ConAN uses is provided")
+        self.hidden_channels = hidden_channels
+        self.num_filters = num_filters
+        self.num_interactions = num_interactions
+        self.num_gaussians = num_gaussians
+        self.cutoff = cutoff
+        self.dipole = dipole
+        self.mean, self.std, self.scale = mean, std, None
+        self.sum_aggr = SumAggregation()
+        self.readout = SumAggregation()
+        self.embedding = nn.Embedding(100, hidden_channels, padding_idx=0)
+        self.interaction_graph = interaction_graph if interaction_graph is not None else \
+            RadiusInteractionGraph(cutoff, max_num_neighbors)
+        self.distance_expansion = GaussianSmearing(0.0, cutoff, num_gaussians)
+        self.interactions = nn.ModuleList(
+            InteractionBlock(hidden_channels, num_gaussians, num_filters, cutoff) for _ in range(num_interactions))
+        self.lin1 = Linear(hidden_channels, hidden_channels // 2)
+        self.act = ShiftedSoftplus()
+        self.lin2 = Linear(hidden_channels // 2, 1)
+        self.register_buffer("initial_atomref", None)
+        self.atomref = None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.embedding.reset_parameters()
+        for blk in self.interactions:
+            blk.reset_parameters()
+        torch.nn.init.xavier_uniform_(self.lin1.weight)
+        self.lin1.bias.data.fill_(0)
+        torch.nn.init.xavier_uniform_(self.lin2.weight)
+        self.lin2.bias.data.fill_(0)
+
+    # -- trunk shared by every forward variant ------------------------------------------------
+    def embed(self, z, status=None):
+        return ops.embedding(z, self.embedding.weight, self.embedding.padding_idx, status)
+
+    def trunk(self, z, pos, batch, num_graphs=None):
+        """Embedding + T interaction blocks.  Returns ``(h[N,H], graph)``."""
+        ig = self.interaction_graph
+        if isinstance(ig, RadiusInteractionGraph):
+            graph = ig.neighbor_list(pos, batch, num_graphs)
+            h = self.embed(z, graph.status)
+            edge_index = None
+            edge_weight = graph.edge_weight()      # first host sync: also surfaces device-side input errors
+        else:  # user supplied interaction graph: generic path
+            edge_index, edge_weight = ig(pos, batch)
+            graph, perm = graph_from_edge_index(edge_index, edge_weight, z.numel())
+            if perm is not None:
+                edge_weight = edge_weight[perm]
+            h = self.embed(z, graph.status)
+        edge_attr = self.distance_expansion(edge_weight)
+        for blk in self.interactions:
+            h = blk(h, edge_index, edge_weight, edge_attr, graph=graph, residual=h)
+        return h, graph
+
+    def forward(self, z, pos, batch=None, num_graphs=None):
+        batch = torch.zeros_like(z) if batch is None else batch
+        h, graph = self.trunk(z, pos, batch, num_graphs)
+        h = self.lin2(self.lin1(h, act=_lib.ACT_SSP))
+        if self.mean is not None and self.std is not None:
+            h = h * self.std + self.mean
+        seg = graph.seg_ptr if graph.G else None
+        out = self.readout(h, batch, dim=0, seg_ptr=seg)
+        if self.scale is not None:
+            out = self.scale * out
+        return out

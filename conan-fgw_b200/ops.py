@@ -1,0 +1,257 @@
+"""Autograd wrappers around the C ABI (one ``torch.autograd.Function`` per kernel family).
+
+PyTorch owns every tensor; the wrappers only pass device pointers and sizes on
+the current stream.  Nothing here falls back to a PyTorch implementation.
+"""
+
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_SILU, ACT_SSP, call, ptr
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise _lib.ConanMPError(f"conanmp ops compute in float32, got {t.dtype}")
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------
+# dense
+# ------------------------------------------------------------------------------------------
+
+def gemm(a, b, trans_a=False, trans_b=True, bias=None, act=ACT_NONE, residual=None, out=None):
+    """``out[M,N] = act(op(a) @ op(b) + bias) + residual`` through ``cmp_gemm_f32``."""
+    a, b = _f32c(a), _f32c(b)
+    if trans_a:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if trans_b:
+        N, Kb = b.shape
+    else:
+        Kb, N = b.shape
+    if K != Kb:
+        raise ValueError(f"gemm: inner dimensions differ ({K} vs {Kb})")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    if bias is not None:
+        bias = _f32c(bias)
+    if residual is not None:
+        residual = _f32c(residual)
+    ws_bytes = _lib.size_query("cmp_gemm_workspace", M, N, K)
+    ws = _lib.workspace(ws_bytes, a.device) if ws_bytes else None
+    call("cmp_gemm_f32", int(trans_a), int(trans_b), M, N, K, ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out),
+         out.stride(0), ptr(bias), int(act), ptr(residual), residual.stride(0) if residual is not None else 0,
+         ptr(ws), ws.numel() if ws is not None else 0)
+    return out
+
+
+def colsum(x):
+    x = _f32c(x)
+    M, N = x.shape
+    out = torch.empty(N, dtype=torch.float32, device=x.device)
+    ws_bytes = _lib.size_query("cmp_colsum_workspace", M, N)
+    ws = _lib.workspace(ws_bytes, x.device)
+    call("cmp_colsum_f32", ptr(x), x.stride(0), M, N, ptr(out), ptr(ws), ws.numel())
+    return out
+
+
+def act_bwd(dy, saved, act):
+    dy = _f32c(dy)
+    dx = torch.empty_like(dy)
+    call("cmp_act_bwd", ptr(dy), ptr(_f32c(saved)) if saved is not None else None, ptr(dx), dy.numel(), int(act))
+    return dx
+
+
+class _LinearFn(Function):
+    """y = act(x W^T + b) [+ residual]; replaces torch.nn.Linear (+ ShiftedSoftplus) on the path."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, residual):
+        if act != ACT_NONE and residual is not None:
+            raise ValueError("linear: an activation and a residual cannot be fused in the same call")
+        if act == ACT_SILU:
+            raise ValueError("linear: SiLU needs the pre-activation saved; use linear(...) then silu(...)")
+        lead = x.shape[:-1]
+        x2 = _f32c(x.reshape(-1, x.shape[-1]))
+        res2 = residual.reshape(-1, weight.shape[0]) if residual is not None else None
+        y = gemm(x2, weight, False, True, bias, act, res2)
+        ctx.act = act
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.lead = lead
+        ctx.save_for_backward(x2, weight, y if act != ACT_NONE else None)
+        return y.reshape(*lead, weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, y = ctx.saved_tensors
+        dy2 = _f32c(dy.reshape(-1, weight.shape[0]))
+        g = act_bwd(dy2, y, ctx.act) if ctx.act != ACT_NONE else dy2
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(g, weight, False, False).reshape(*ctx.lead, weight.shape[1])   # g[M,N] @ W[N,K]
+        if ctx.needs_input_grad[1]:
+            dw = gemm(g, x2, True, False)                                            # g^T[N,M] @ x[M,K]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(g)
+        if ctx.has_res and ctx.needs_input_grad[4]:
+            dres = dy
+        return dx, dw, db, None, dres
+
+
+def linear(x, weight, bias=None, act=ACT_NONE, residual=None):
+    return _LinearFn.apply(x, weight, bias, act, residual)
+
+
+class _ActFn(Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        x = _f32c(x)
+        y = torch.empty_like(x)
+        call("cmp_act_fwd", ptr(x), ptr(y), x.numel(), int(act))
+        ctx.act = act
+        ctx.save_for_backward(y if act == ACT_SSP else x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (saved,) = ctx.saved_tensors
+        return act_bwd(dy, saved, ctx.act), None
+
+
+def shifted_softplus(x):
+    return _ActFn.apply(x, ACT_SSP)
+
+
+def silu(x):
+    return _ActFn.apply(x, ACT_SILU)
+
+
+# ------------------------------------------------------------------------------------------
+# SchNet pieces
+# ------------------------------------------------------------------------------------------
+
+def gaussian_rbf(dist, offset, coeff):
+    """GaussianSmearing.forward: ``exp(coeff * (d - offset_k)^2)`` -> ``[E, Ng]`` (no gradient: the
+    reference never differentiates through positions, ``derivative=False``)."""
+    d = _f32c(dist.detach().reshape(-1))
+    E, Ng = d.numel(), offset.numel()
+    out = torch.empty(E, Ng, dtype=torch.float32, device=d.device)
+    call("cmp_rbf_gaussian_fwd", ptr(d), E, ptr(_f32c(offset)), Ng, float(coeff), ptr(out), Ng)
+    return out
+
+
+class _EmbeddingFn(Function):
+    @staticmethod
+    def forward(ctx, z, weight, padding_idx, status):
+        z = z.to(torch.int64).contiguous()
+        weight = _f32c(weight)
+        N, (V, H) = z.numel(), weight.shape
+        out = torch.empty(N, H, dtype=torch.float32, device=weight.device)
+        call("cmp_embedding_fwd", ptr(z), N, ptr(weight), V, H, ptr(out), ptr(status))
+        ctx.save_for_backward(z)
+        ctx.shape = (V, H)
+        ctx.padding_idx = -1 if padding_idx is None else int(padding_idx)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (z,) = ctx.saved_tensors
+        V, H = ctx.shape
+        dout = _f32c(dout)
+        dw = torch.empty(V, H, dtype=torch.float32, device=dout.device)
+        ws_bytes = _lib.size_query("cmp_embedding_bwd_workspace", z.numel(), V, H)
+        ws = _lib.workspace(ws_bytes, dout.device)
+        call("cmp_embedding_bwd", ptr(z), z.numel(), ptr(dout), V, H, ctx.padding_idx, ptr(dw), ptr(ws), ws.numel())
+        return None, dw, None, None
+
+
+def embedding(z, weight, padding_idx=None, status=None):
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=weight.device)
+    return _EmbeddingFn.apply(z, weight, padding_idx, status)
+
+
+class _CFConvMessageFn(Function):
+    """agg_i = sum_{j->i} x'_j * filt_ij * C(d_ij)  (PyG CFConv.propagate/message)."""
+
+    @staticmethod
+    def forward(ctx, xprime, filt, graph, cutoff):
+        xprime, filt = _f32c(xprime), _f32c(filt)
+        N, F = xprime.shape
+        if filt.shape[0] != graph.E or filt.shape[1] != F:
+            raise ValueError("cfconv: filter must be [E, num_filters] in CSR edge order")
+        agg = torch.empty(N, F, dtype=torch.float32, device=xprime.device)
+        call("cmp_cfconv_message_fwd", ptr(xprime), ptr(filt), ptr(graph.dist), ptr(graph.rowptr), ptr(graph.col),
+             N, F, float(cutoff), ptr(agg))
+        ctx.graph, ctx.cutoff = graph, float(cutoff)
+        ctx.save_for_backward(xprime, filt)
+        return agg
+
+    @staticmethod
+    def backward(ctx, g):
+        xprime, filt = ctx.saved_tensors
+        graph = ctx.graph
+        g = _f32c(g)
+        N, F = xprime.shape
+        dx = torch.empty_like(xprime) if ctx.needs_input_grad[0] else None
+        dfilt = torch.empty_like(filt) if ctx.needs_input_grad[1] else None
+        if dx is not None and graph.rowptr_t is None:
+            raise _lib.ConanMPError("cfconv backward needs the transposed neighbour list")
+        call("cmp_cfconv_message_bwd", ptr(g), ptr(xprime), ptr(filt), ptr(graph.dist), ptr(graph.rowptr),
+             ptr(graph.col), ptr(graph.rowptr_t), ptr(graph.col_t), ptr(graph.eid_t), N, F, ctx.cutoff,
+             ptr(dfilt), ptr(dx))
+        return dx, dfilt, None, None
+
+
+def cfconv_message(xprime, filt, graph, cutoff):
+    return _CFConvMessageFn.apply(xprime, filt, graph, cutoff)
+
+
+class _SegmentSumFn(Function):
+    @staticmethod
+    def forward(ctx, x, seg_ptr, G):
+        x = _f32c(x)
+        C = x.shape[1]
+        out = torch.empty(G, C, dtype=torch.float32, device=x.device)
+        call("cmp_segment_sum_fwd", ptr(x), ptr(seg_ptr), G, C, ptr(out))
+        ctx.save_for_backward(seg_ptr)
+        ctx.N, ctx.G, ctx.C = x.shape[0], G, C
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (seg_ptr,) = ctx.saved_tensors
+        dout = _f32c(dout)
+        dx = torch.zeros(ctx.N, ctx.C, dtype=torch.float32, device=dout.device)
+        call("cmp_segment_sum_bwd", ptr(dout), ptr(seg_ptr), ctx.G, ctx.C, ptr(dx))
+        return dx, None, None
+
+
+def segment_sum(x, seg_ptr, G):
+    """Sum readout over sorted, contiguous segments (``seg_ptr int32[G+1]``)."""
+    return _SegmentSumFn.apply(x, seg_ptr, int(G))
+
+
+def segments_from_batch(batch, num_graphs=None):
+    from .graph import num_graphs_of
+
+    batch = batch.to(torch.int64).contiguous()
+    G = num_graphs_of(batch, num_graphs)
+    seg = torch.empty(G + 1, dtype=torch.int32, device=batch.device)
+    status = torch.zeros(1, dtype=torch.int32, device=batch.device)
+    call("cmp_batch_to_segments", ptr(batch), batch.numel(), G, ptr(seg), ptr(status))
+    return seg, G
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+              grad_scale=1.0):
+    """Fused Adam on flat fp32 buffers (in place)."""
+    call("cmp_adam_step", ptr(param, torch.float32), ptr(grad, torch.float32), ptr(exp_avg, torch.float32),
+         ptr(exp_avg_sq, torch.float32), param.numel(), float(lr), float(betas[0]), float(betas[1]), float(eps),
+         float(weight_decay), int(step), float(grad_scale))

@@ -1,0 +1,180 @@
+/*
+ * conanmp.h - C ABI of libconanmp.so, the sm_100a kernels behind the ConAN
+ * message-passing backbone (SchNet / ViSNet + radius graph).
+ *
+ * The reference (duyhominhnguyen/conan-fgw) has no native boundary of its own:
+ * its hot path is a chain of Python calls into torch-geometric 2.3.0 /
+ * torch-cluster 1.6.1 / ATen.  Each entry point below therefore cites the
+ * reference-side Python call it replaces (paths relative to the reference root,
+ * "sns.py" = conan_fgw/src/model/graph_embeddings/schnet_no_sum.py,
+ * "tgv.py" = conan_fgw/src/model/graph_embeddings/torch_geometric_visnet.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless
+ *     its name ends in _host.  The caller (PyTorch) owns all memory; the library
+ *     never allocates, frees or retains device memory.
+ *   - every function enqueues on `stream` and returns immediately: 0 on success,
+ *     a negative CMP_E* code on a rejected call (see cmp_last_error_string()).
+ *     No call synchronises the device, so all of them are CUDA-graph capturable.
+ *   - data-dependent errors that only the device can see (unsorted batch,
+ *     atomic number out of range) are reported by setting bits in a caller
+ *     provided `int* status` word (CMP_STATUS_*), checked by the host lazily.
+ *   - row-major dense matrices with an explicit leading dimension (elements).
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef CONANMP_H_
+#define CONANMP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* cmp_stream_t; /* a cudaStream_t */
+
+/* return codes */
+#define CMP_OK 0
+#define CMP_EINVAL (-1)     /* bad size / null pointer / misaligned pointer */
+#define CMP_EUNSUPPORTED (-2) /* shape not supported by this kernel family */
+#define CMP_EWORKSPACE (-3) /* workspace too small */
+#define CMP_ECUDA (-4)      /* a CUDA runtime call failed (launch configuration ...) */
+
+/* device-side status bits */
+#define CMP_STATUS_UNSORTED_BATCH 1
+#define CMP_STATUS_BAD_ATOMIC_NUMBER 2
+#define CMP_STATUS_EDGE_OVERFLOW 4
+
+/* activation selector of the dense epilogues */
+#define CMP_ACT_NONE 0
+#define CMP_ACT_SSP 1   /* shifted softplus: softplus(x) - ln 2  (PyG ShiftedSoftplus, sns.py:179) */
+#define CMP_ACT_SILU 2  /* x * sigmoid(x)                         (tgv.py:518-519) */
+
+/* numerics of the fused tensor-core kernels */
+#define CMP_PREC_FP32 0  /* split-precision tensor-core GEMMs, fp32-grade (parity mode) */
+#define CMP_PREC_BF16 1  /* single-pass bf16 operands, fp32 accumulate (throughput mode) */
+
+const char* cmp_last_error_string(void);
+int cmp_version(void);
+/* 1 when the running device is compute capability 10.x (tcgen05 kernels usable) */
+int cmp_device_is_sm100(void);
+
+/* ------------------------------------------------------------------------- *
+ * Neighbour lists
+ * ------------------------------------------------------------------------- */
+
+/* seg_ptr[g] = first atom of conformer g (g = 0..G), from a sorted batch vector.
+ * Replaces the bucketize() inside torch_cluster.radius; sets
+ * CMP_STATUS_UNSORTED_BATCH when batch decreases anywhere. */
+int cmp_batch_to_segments(const int64_t* batch, int64_t N, int64_t G, int32_t* seg_ptr,
+                          int* status, cmp_stream_t stream);
+
+/* Destination-sorted CSR radius graph per conformer.
+ * Replaces radius_graph()/RadiusInteractionGraph.forward (sns.py:160,208,342;
+ * tgv.py:331-347; conan_fgw/src/model/graph_embeddings/visnet.py:90,276) with
+ * torch-cluster's CUDA truncation rule: for target i keep the first `cap`
+ * candidates j (ascending, self included) with
+ *   ((dx*dx)+(dy*dy))+(dz*dz) < (float)((double)r*r)      (fp32, no FMA),
+ * cap = max_num_neighbors + (loop ? 0 : 1); self pairs dropped when !loop.
+ *
+ * Three launches, no host sync:
+ *   rowptr int32[N+1]   CSR offsets by target atom (rowptr[N] = E)
+ *   col    int32[cap_E] source atom of each edge, ascending inside a row
+ *   dist   float[cap_E] |pos[src]-pos[dst]|  (0 on self loops)
+ *   evec   float[cap_E*3] or NULL: pos[src]-pos[dst]          (ViSNet Distance)
+ *   rowptr_t/col_t/eid_t (each may be NULL together): the same edges grouped by
+ *     SOURCE atom (col_t = target, ascending; eid_t = index into col/dist) - the
+ *     adjacency transpose the backward pass gathers through.
+ *   conf_edge_ptr int32[G+1]: first edge of each conformer.
+ * cap_E = capacity of col/dist; N*cap always suffices.  Overflow sets
+ * CMP_STATUS_EDGE_OVERFLOW and truncates.
+ * workspace: cmp_radius_csr_workspace(N, G) bytes. */
+size_t cmp_radius_csr_workspace(int64_t N, int64_t G);
+int cmp_radius_csr(const float* pos, const int32_t* seg_ptr, int64_t N, int64_t G, double r,
+                   int max_num_neighbors, int loop, int64_t cap_E, int32_t* rowptr, int32_t* col,
+                   float* dist, float* evec, int32_t* rowptr_t, int32_t* col_t, int32_t* eid_t,
+                   int32_t* conf_edge_ptr, void* workspace, size_t workspace_bytes, int* status,
+                   cmp_stream_t stream);
+
+/* CSR -> PyG edge_index int64[2, E] (row 0 = source j, row 1 = target i). */
+int cmp_csr_to_edge_index(const int32_t* rowptr, const int32_t* col, int64_t N, int64_t E,
+                          int64_t* edge_index, cmp_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * Dense building blocks (fp32)
+ * ------------------------------------------------------------------------- */
+
+/* C[M,N] = act(opA(A) * opB(B) + bias[N]) + residual[M,N]
+ *   transA = 0: A is [M,K] (lda);  1: A is stored [K,M] (lda)
+ *   transB = 1: B is stored [N,K] (ldb) - a torch Linear weight; 0: B is [K,N]
+ * Replaces every torch.nn.Linear on the path (PyG CFConv.lin1/lin2/nn,
+ * InteractionBlock.lin, sns.py:177-179,225-231) and their autograd GEMMs.
+ * bias / residual may be NULL.  workspace is used for split-K partial sums:
+ * cmp_gemm_workspace(M,N,K) bytes. */
+size_t cmp_gemm_workspace(int64_t M, int64_t N, int64_t K);
+int cmp_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A,
+                 int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, const float* bias,
+                 int act, const float* residual, int64_t ldr, void* workspace,
+                 size_t workspace_bytes, cmp_stream_t stream);
+
+/* out[N] = sum_m X[m, :]  (bias gradients); deterministic two-stage reduction.
+ * workspace: cmp_colsum_workspace(M, N). */
+size_t cmp_colsum_workspace(int64_t M, int64_t N);
+int cmp_colsum_f32(const float* X, int64_t ldx, int64_t M, int64_t N, float* out, void* workspace,
+                   size_t workspace_bytes, cmp_stream_t stream);
+
+/* y = act(x) elementwise, and dx = dy * act'(.) computed from the forward
+ * OUTPUT y for SSP (sigmoid(x) = 1 - exp(-y)/2) or the forward INPUT x for SILU. */
+int cmp_act_fwd(const float* x, float* y, int64_t n, int act, cmp_stream_t stream);
+int cmp_act_bwd(const float* dy, const float* saved, float* dx, int64_t n, int act,
+                cmp_stream_t stream);
+
+/* ------------------------------------------------------------------------- *
+ * SchNet pieces
+ * ------------------------------------------------------------------------- */
+
+/* GaussianSmearing.forward (PyG; sns.py:161): out[e,k] = exp(coeff*(d[e]-offset[k])^2). */
+int cmp_rbf_gaussian_fwd(const float* d, int64_t E, const float* offset, int Ng, float coeff,
+                         float* out, int64_t ldo, cmp_stream_t stream);
+
+/* Embedding(100, H, padding_idx=0) forward / weight gradient (sns.py:159).
+ * bwd is deterministic; workspace cmp_embedding_bwd_workspace(N, V, H). */
+int cmp_embedding_fwd(const int64_t* z, int64_t N, const float* weight, int V, int H, float* out,
+                      int* status, cmp_stream_t stream);
+size_t cmp_embedding_bwd_workspace(int64_t N, int V, int H);
+int cmp_embedding_bwd(const int64_t* z, int64_t N, const float* dout, int V, int H, int padding_idx,
+                      float* dweight, void* workspace, size_t workspace_bytes, cmp_stream_t stream);
+
+/* CFConv message + aggregation (PyG CFConv.forward/message):
+ *   agg[i,:] = sum_{e in row i} xprime[col[e],:] * filt[e,:] * C(dist[e]),
+ *   C(d) = 0.5*(cos(d*pi/cutoff)+1)            (no d<cutoff mask in SchNet)
+ * deterministic: edges of a row are summed in CSR order. */
+int cmp_cfconv_message_fwd(const float* xprime, const float* filt, const float* dist,
+                           const int32_t* rowptr, const int32_t* col, int64_t N, int F,
+                           float cutoff, float* agg, cmp_stream_t stream);
+/* Backward of the above for upstream gradient g[N,F]:
+ *   dfilt[e,:]  = g[dst(e),:] * xprime[col[e],:] * C(dist[e])
+ *   dxprime[j,:] = sum_{e' in row_t j} g[col_t[e'],:] * filt[eid_t[e'],:] * C(dist[eid_t[e']]) */
+int cmp_cfconv_message_bwd(const float* g, const float* xprime, const float* filt,
+                           const float* dist, const int32_t* rowptr, const int32_t* col,
+                           const int32_t* rowptr_t, const int32_t* col_t, const int32_t* eid_t,
+                           int64_t N, int F, float cutoff, float* dfilt, float* dxprime,
+                           cmp_stream_t stream);
+
+/* Sum readout over sorted segments (PyG SumAggregation; sns.py:184,353) and its
+ * backward (broadcast of dout[g] to the atoms of g). */
+int cmp_segment_sum_fwd(const float* x, const int32_t* seg_ptr, int64_t G, int C, float* out,
+                        cmp_stream_t stream);
+int cmp_segment_sum_bwd(const float* dout, const int32_t* seg_ptr, int64_t G, int C, float* dx,
+                        cmp_stream_t stream);
+
+/* Fused Adam step on flat fp32 buffers (the optimiser of model/common.py:368-370). */
+int cmp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                  float grad_scale, cmp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONANMP_H_ */
