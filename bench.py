@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py - ConAN-SchNet conformers/s, fwd+bwd training step (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[1] - ConAN-SchNet fwd+bwd training step,
+Lipophilicity-shaped: 128 molecules x K=5 conformers x 27 atoms per GPU (weak scaling),
+SchNet defaults H=F=128, T=6 interactions, 50 Gaussians, cutoff 10 A, 32 neighbours max;
+synthetic geometry, random-init weights.  One step = radius graph + forward +
+MSE loss + backward (+ NCCL gradient all-reduce when N>1) + fused Adam.
+
+Printed JSON line: `value` = device-resident inputs, CUDA-event timed, max over ranks;
+`e2e` = same step through the public API from pinned HOST buffers (H2D of z/pos/batch/targets and
+D2H of the loss inside the timed region); `roofline` = dominant kernel, timed live with CUDA events
+on the launching stream; `cpu_baseline` = the CPU oracle (oracle/, a port of the reference's PyG op
+sequence) on a bounded sample of the same workload on this host's cores.
+`--impl reference` times that CPU path alone with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+MODEL_CFG = dict(hidden_channels=128, num_filters=128, num_interactions=6, num_gaussians=50, cutoff=10.0)
+WORKLOAD = "cfg2_lipo_train"
+METRIC = "ConAN-SchNet conformers/sec fwd+bwd"
+UNIT = "conformers/s"
+CPU_SAMPLE_MOLECULES = 16
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0,
+                source="fallback (B200_PROFILING.md)")
+
+
+def algorithmic_flops(N, E, T=6, H=128, F=128, Ng=50, fwd_bwd=True):
+    """per edge per block 2*(Ng*F + F*F), per atom per block 3*2*H*F; bwd = 2x fwd."""
+    fwd = T * (2.0 * (Ng * F + F * F) * E + 3 * 2.0 * H * F * N)
+    return fwd * (3.0 if fwd_bwd else 1.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.proc, self.lines, self.index = None, [], index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1])), pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# -----------------------------------------------------------------------------------------------
+# CPU path (oracle = port of the reference's PyG op sequence); used by cpu_baseline and --impl reference
+# -----------------------------------------------------------------------------------------------
+
+def cpu_step_factory(molecules, threads):
+    import conan_fgw_b200 as cmp
+    from oracle import schnet as osn
+
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = osn.SchNetNoSum(None, **MODEL_CFG)
+    head = torch.nn.Linear(MODEL_CFG["hidden_channels"] // 2, 1)
+    params = list(model.parameters()) + list(head.parameters())
+    opt = torch.optim.Adam(params, lr=1e-3)
+    c = cmp.synthetic.CONFIGS[WORKLOAD]
+    b = cmp.synthetic.make_batch(molecules, c["num_conformers"], c["atoms"], seed=1234)
+    tg = torch.Generator().manual_seed(99)
+    targets = torch.randn(molecules, 1, generator=tg)
+    K = c["num_conformers"]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        emb = model(b.z, b.pos, b.batch)
+        pred = head(emb.view(-1, K, emb.size(1)).mean(dim=1))
+        loss = torch.nn.functional.mse_loss(pred, targets)
+        loss.backward()
+        opt.step()
+        return float(loss.item())
+
+    return step, molecules * K
+
+
+def time_cpu(molecules, steps, warmup, threads):
+    step, conformers = cpu_step_factory(molecules, threads)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    total = sum(ts)
+    return conformers * steps / total, total / steps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    c_mol = CPU_SAMPLE_MOLECULES
+    value, per_step = time_cpu(c_mol, max(1, args.steps), max(1, args.warmup), threads)
+    sample = (f"{c_mol} of the 128 molecules x 5 conformers x 27 atoms per step (same generator, same model); "
+              f"conformers/s scales linearly in molecules")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_molecules": c_mol, **MODEL_CFG},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -----------------------------------------------------------------------------------------------
+# GPU path
+# -----------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import conan_fgw_b200 as cmp
+    from conan_fgw_b200 import _lib
+    from conan_fgw_b200.dp import RegressionStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cmp.build_library()
+
+    c = cmp.synthetic.CONFIGS[WORKLOAD]
+    B, K, n = c["num_molecules"], c["num_conformers"], c["atoms"]
+    # weak scaling: every rank owns its own B molecules (different seed per rank)
+    host = cmp.synthetic.make_batch(B, K, n, seed=1234 + rank).pin()
+    tg = torch.Generator().manual_seed(99 + rank)
+    targets_h = torch.randn(B, 1, generator=tg).pin_memory()
+    G = host.num_graphs
+
+    torch.manual_seed(0)
+    model = cmp.SchNetNoSum(None, **MODEL_CFG).to(dev)
+    trainer = RegressionStep(model, MODEL_CFG["hidden_channels"] // 2, K, lr=1e-3)
+
+    d = host.to(dev)
+    targets = targets_h.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def resident_step():
+        return trainer.step(d.z, d.pos, d.batch, targets, G)
+
+    def e2e_step():
+        z = host.z.to(dev, non_blocking=True)
+        pos = host.pos.to(dev, non_blocking=True)
+        bt = host.batch.to(dev, non_blocking=True)
+        tg_ = targets_h.to(dev, non_blocking=True)
+        loss = trainer.step(z, pos, bt, tg_, G)
+        return float(loss.item())          # D2H read of the step's result
+
+    def timed(step_fn, steps, timer_names=None):
+        evs = []
+        sync_all()
+        _lib.reset_launches()
+        if timer_names:
+            _lib.timer = _lib.KernelTimer(timer_names)
+        for _ in range(steps):
+            flush.zero_()                                # L2 flush between timed iterations (untimed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_fn()
+            e1.record()
+            evs.append((e0, e1))
+        sync_all()
+        kt = _lib.timer
+        _lib.timer = None
+        launches = _lib.launches()
+        total_ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, kt
+
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    e2e_step()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dominant = ["cmp_gemm_f32"]
+    total_ms, launches, kt = timed(resident_step, args.steps, dominant)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms, _, _ = timed(e2e_step, args.steps)
+
+    value = world * G * args.steps / (total_ms * 1e-3)
+    e2e_value = world * G * args.steps / (e2e_ms * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in (host.z, host.pos, host.batch, targets_h))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant kernel (timed live above, on the launching stream)
+    pk = peaks()
+    E = int(model.interaction_graph.neighbor_list(d.pos, d.batch, G).E)
+    N = d.z.numel()
+    summ = kt.summary() if kt else {}
+    n_l, k_ms, k_work = summ.get(dominant[0], (0, 0.0, 0.0))
+    achieved = (k_work / (k_ms * 1e-3) / 1e12) if k_ms > 0 else None
+    roofline = {
+        "kernel": "gemm_f32_kernel (exact-fp32 SIMT GEMM: filter MLP on E rows + node linears + their gradients)",
+        "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"],
+        "unit": "TFLOP/s", "frac": (achieved / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])) if achieved else None,
+        "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+        "launches_timed": n_l, "kernel_ms_per_step": k_ms / args.steps if args.steps else None,
+        "step_share": (k_ms / total_ms) if total_ms else None,
+        "algorithmic_flops_per_step": algorithmic_flops(N, E),
+        "step_tflops": algorithmic_flops(N, E) * args.steps / (total_ms * 1e-3) / 1e12,
+    }
+
+    # CPU baseline: bounded sample of the same workload on this host's cores
+    threads = os.cpu_count() or 1
+    cpu_value, cpu_step = time_cpu(CPU_SAMPLE_MOLECULES, 2, 1, threads)
+    cpu_baseline = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": f"{CPU_SAMPLE_MOLECULES} of 128 molecules x 5 conformers x 27 atoms, 1 warm-up + 2 timed "
+                              f"fwd+bwd+Adam steps of oracle.schnet.SchNetNoSum ({cpu_step:.2f} s/step)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "molecules_per_gpu": B, "conformers_per_molecule": K, "atoms_per_conformer": n,
+                   "conformers_per_gpu": G, "atoms": N, "edges": E, **MODEL_CFG, "max_num_neighbors": 32,
+                   "step": "radius graph + fwd + MSE + bwd + grad all-reduce (N>1) + Adam",
+                   "l2": "256 MiB buffer written between timed iterations (L2 flush, untimed)",
+                   "parallelism": f"dp{world}"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,8 @@ P, I, L, F, D, S = c_void_p, c_int, c_int64, c_float, c_double, c_size_t
 SIGNATURES = {
     "cmp_last_error_string": (c_char_p, []),
     "cmp_version": (I, []),
+    "cmp_launch_count": (ctypes.c_longlong, []),
+    "cmp_launch_count_reset": (None, []),
     "cmp_device_is_sm100": (I, []),
     "cmp_batch_to_segments": (I, [P, L, L, P, P, P]),
     "cmp_radius_csr_workspace": (S, [L, L]),
@@ -85,12 +87,12 @@ def lib():
 
 
 def launches() -> int:
-    return _launches
+    """Kernels launched by libconanmp in this process (counted inside the library)."""
+    return int(lib().cmp_launch_count())
 
 
 def reset_launches():
-    global _launches
-    _launches = 0
+    lib().cmp_launch_count_reset()
 
 
 def ptr(t, dtype=None):
@@ -110,11 +112,41 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name, *args):
-    """Invoke an int-returning entry point on the current stream; raise on a non-zero code."""
+class KernelTimer:
+    """Optional CUDA-event timing of selected entry points on the launching stream (bench.py uses it
+    to measure the dominant kernel live, inside the timed region)."""
+
+    def __init__(self, names):
+        self.names = set(names)
+        self.records = []   # (name, start_event, end_event, work)
+
+    def summary(self):
+        """{name: (launches, total_ms, total_work)} - call after a device synchronise."""
+        out = {}
+        for name, e0, e1, work in self.records:
+            n, ms, w = out.get(name, (0, 0.0, 0.0))
+            out[name] = (n + 1, ms + e0.elapsed_time(e1), w + float(work))
+        return out
+
+
+timer: "KernelTimer | None" = None
+
+
+def call(name, *args, work=0.0):
+    """Invoke an int-returning entry point on the current stream; raise on a non-zero code.
+    ``work`` = algorithmic FLOPs (or bytes) of this launch, recorded when a KernelTimer is active."""
     global _launches
     fn = getattr(lib(), name)
-    rc = fn(*args, stream())
+    t = timer
+    if t is not None and name in t.names:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args, stream())
+        e1.record()
+        t.records.append((name, e0, e1, work))
+    else:
+        rc = fn(*args, stream())
     _launches += 1
     if rc != 0:
         msg = lib().cmp_last_error_string().decode("utf-8", "replace")

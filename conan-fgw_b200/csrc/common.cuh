@@ -10,6 +10,7 @@
 namespace cmp {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define CMP_REQUIRE(cond, code, ...)  \
   do {                                \
@@ -28,6 +29,7 @@ void set_error(const char* fmt, ...);
       (void)cudaGetLastError();                                                        \
       return CMP_ECUDA;                                                                \
     }                                                                                  \
+    ::cmp::count_launch();                                                             \
   } while (0)
 
 inline cudaStream_t as_stream(cmp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -3,6 +3,8 @@
 // generic-shape path; the fused tcgen05 kernels (cfconv_tc.cu) take over for the hot shapes.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace cmp {
@@ -15,6 +17,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached = 0;
@@ -249,6 +254,8 @@ using namespace cmp;
 
 extern "C" const char* cmp_last_error_string(void) { return g_err; }
 extern "C" int cmp_version(void) { return 100; }
+extern "C" long long cmp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" void cmp_launch_count_reset(void) { g_launches.store(0, std::memory_order_relaxed); }
 
 extern "C" int cmp_device_is_sm100(void) {
   int dev = 0, major = 0;

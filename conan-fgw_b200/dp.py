@@ -1,0 +1,103 @@
+"""Data-parallel training step for the backbone: shard molecules, flat gradient all-reduce, fused Adam.
+
+What it mirrors in the reference: Lightning DDP (``conan_fgw/src/trainer.py:308-325``,
+strategy ``ddp_find_unused_parameters_false``) with ``DistributedSampler(shuffle=False)``
+(``conan_fgw/src/data/datamodules.py:40-41``) and Adam (``model/common.py:368-370``).
+The forward path needs no inter-GPU traffic (conformer graphs are independent); the only
+collective is one all-reduce of a single flat fp32 gradient buffer per step.
+"""
+
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def shard_molecules(num_molecules: int, rank: int, world_size: int) -> List[int]:
+    """Indices of the molecules rank ``rank`` owns: ``rank, rank+W, ...`` padded by wrap-around to equal
+    length on every rank - the rule of ``DistributedSampler(shuffle=False, drop_last=False)``."""
+    if num_molecules == 0:
+        return []
+    per = -(-num_molecules // world_size)
+    total = per * world_size
+    idx = list(range(num_molecules))
+    while len(idx) < total:
+        idx += idx[: total - len(idx)]
+    return idx[rank:total:world_size]
+
+
+class FlatParameters:
+    """Re-homes a module's parameters (and gradients) as views of one contiguous fp32 buffer so the
+    gradient all-reduce is a single collective and Adam a single kernel."""
+
+    def __init__(self, modules):
+        params, seen = [], set()
+        for m in modules:
+            for p in m.parameters():
+                if id(p) not in seen and p.requires_grad:
+                    seen.add(id(p))
+                    params.append(p)
+        if not params:
+            raise ValueError("no trainable parameters")
+        dev = params[0].device
+        n = sum(p.numel() for p in params)
+        self.params = params
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.grad[off:off + k].view_as(p)
+            off += k
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.step_count = 0
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def all_reduce(self, group=None):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+            return dist.get_world_size(group)
+        return 1
+
+    def adam(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
+        self.step_count += 1
+        ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, lr, betas, eps,
+                      weight_decay, grad_scale)
+
+
+class RegressionStep:
+    """One ConAN-style regression training step around the backbone:
+    backbone -> [G, H/2] -> mean over the K conformers of a molecule (``schnet_based_models.py:242``)
+    -> linear head -> MSE (``model/common.py:288``) -> backward -> [all-reduce] -> Adam."""
+
+    def __init__(self, backbone, hidden_half: int, num_conformers: int, lr: float = 1e-3, group=None):
+        self.backbone = backbone
+        dev = next(backbone.parameters()).device
+        self.head = torch.nn.Linear(hidden_half, 1).to(dev)
+        self.K = int(num_conformers)
+        self.flat = FlatParameters([backbone, self.head])
+        self.lr = lr
+        self.group = group
+
+    def loss(self, z, pos, batch, targets, num_graphs):
+        emb = self.backbone(z, pos, batch, num_graphs=num_graphs)          # [G, H/2]
+        mol = emb.view(-1, self.K, emb.size(1)).mean(dim=1)                  # conformers of a molecule are consecutive
+        pred = self.head(mol)
+        return torch.nn.functional.mse_loss(pred, targets)
+
+    def step(self, z, pos, batch, targets, num_graphs):
+        self.flat.zero_grad()
+        loss = self.loss(z, pos, batch, targets, num_graphs)
+        loss.backward()
+        world = self.flat.all_reduce(self.group)
+        self.flat.adam(lr=self.lr, grad_scale=1.0 / world)
+        return loss.detach()

@@ -28,6 +28,13 @@ class Linear(nn.Linear):
         return ops.linear(x, self.weight, self.bias, act, residual)
 
 
+class Embedding(nn.Embedding):
+    """``torch.nn.Embedding`` parameters and init, lookup / weight gradient through the C ABI."""
+
+    def forward(self, z, status=None):
+        return ops.embedding(z, self.weight, self.padding_idx, status)
+
+
 class ShiftedSoftplus(nn.Module):
     def __init__(self):
         super().__init__()
@@ -168,7 +175,7 @@ class SchNet(nn.Module):
         self.mean, self.std, self.scale = mean, std, None
         self.sum_aggr = SumAggregation()
         self.readout = SumAggregation()
-        self.embedding = nn.Embedding(100, hidden_channels, padding_idx=0)
+        self.embedding = Embedding(100, hidden_channels, padding_idx=0)
         self.interaction_graph = interaction_graph if interaction_graph is not None else \
             RadiusInteractionGraph(cutoff, max_num_neighbors)
         self.distance_expansion = GaussianSmearing(0.0, cutoff, num_gaussians)
@@ -192,7 +199,7 @@ class SchNet(nn.Module):
 
     # -- trunk shared by every forward variant ------------------------------------------------
     def embed(self, z, status=None):
-        return ops.embedding(z, self.embedding.weight, self.embedding.padding_idx, status)
+        return self.embedding(z, status)
 
     def trunk(self, z, pos, batch, num_graphs=None):
         """Embedding + T interaction blocks.  Returns ``(h[N,H], graph)``."""

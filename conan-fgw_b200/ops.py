@@ -46,7 +46,7 @@ def gemm(a, b, trans_a=False, trans_b=True, bias=None, act=ACT_NONE, residual=No
     ws = _lib.workspace(ws_bytes, a.device) if ws_bytes else None
     call("cmp_gemm_f32", int(trans_a), int(trans_b), M, N, K, ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out),
          out.stride(0), ptr(bias), int(act), ptr(residual), residual.stride(0) if residual is not None else 0,
-         ptr(ws), ws.numel() if ws is not None else 0)
+         ptr(ws), ws.numel() if ws is not None else 0, work=2.0 * M * N * K)
     return out
 
 

@@ -57,6 +57,9 @@ typedef void* cmp_stream_t; /* a cudaStream_t */
 
 const char* cmp_last_error_string(void);
 int cmp_version(void);
+/* number of kernels this library has launched in this process (bench.py reports it) */
+long long cmp_launch_count(void);
+void cmp_launch_count_reset(void);
 /* 1 when the running device is compute capability 10.x (tcgen05 kernels usable) */
 int cmp_device_is_sm100(void);
 
