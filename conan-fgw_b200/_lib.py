@@ -44,6 +44,15 @@ SIGNATURES = {
     "cmp_segment_sum_fwd": (I, [P, P, L, I, P, P]),
     "cmp_segment_sum_bwd": (I, [P, P, L, I, P, P]),
     "cmp_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, I, F, P]),
+    "cmp_build_tiles_workspace": (S, [L]),
+    "cmp_build_tiles": (I, [P, P, L, I, P, L, P, P, S, P, P]),
+    "cmp_gather_f32": (I, [P, P, P, L, P, P]),
+    "cmp_cfconv_tc_supported": (I, [I, I]),
+    "cmp_cfconv_tc_weights_bytes": (S, []),
+    "cmp_cfconv_tc_tile_edges": (I, []),
+    "cmp_cfconv_tc_pack_weights": (I, [P, P, P, P, I, I, P, P]),
+    "cmp_cfconv_fused_fwd": (I, [P, P, P, P, P, P, P, P, I, F, F, L, I, P, P]),
+    "cmp_debug_umma_gemm": (I, [P, L, P, L, P, I, I, I, I, I, I, I, I, I, I, I, P]),
 }
 
 ACT_NONE, ACT_SSP, ACT_SILU = 0, 1, 2

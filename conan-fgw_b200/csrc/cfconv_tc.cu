@@ -1,0 +1,393 @@
+// Fused CFConv for sm_100a: one pass per interaction block, the E x F filter never leaves the SM.
+//
+// Replaces PyG CFConv.forward / message for num_filters = 128:
+//   agg[i,:] = sum_{j->i} x'[j,:] * ( W2 * ssp(W1 * rbf(d_ij) + b1) + b2 ) * C(d_ij)
+//
+// Work unit = an edge tile: up to 128 edges = a run of whole target rows of one conformer (built by
+// cmp_build_tiles).  Orientation: filter channels live on the 128 TMEM lanes, edges on the columns,
+//   D1[128 hid, e] = W1aug[128, 64]  * rbf_aug[64, e]     (A, B K-major;   bias b1 rides in column Ng)
+//   D2[128 out, e] = W2aug[128, 144] * a'[144, e]         (A K-major, B MN-major)
+// with a'[k, e] = C_e * ssp(D1[k, e]) and the extra row a'[128, e] = C_e carrying b2 * C_e, so the
+// epilogue thread that owns channel f walks the tile's edges in CSR order doing one FMA per edge,
+//   acc += D2[f, e] * x'[src_e, f],
+// and stores agg[dst, f] when a target row ends: deterministic, no shuffles, no atomics, same
+// summation order as the oracle's index_add_.
+//
+// CTA = NG independent pipelines ("groups": 4 compute warps + 1 MMA-issuing warp each) that alternate
+// between SIMT phases and tensor phases so one group's epilogue overlaps the other's MMAs.  x' rows of
+// the tile's conformer are staged in shared memory by 1-D TMA bulk copies (re-used by consecutive
+// tiles of the same conformer); weights arrive as ready-made UMMA shared-memory images.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cmp {
+namespace {
+
+constexpr int F = 128;           // filter channels = UMMA M
+constexpr int TILE_E = 128;      // edges per tile   = max UMMA N
+constexpr int K1 = 64;           // Gaussians padded (+ bias column)
+constexpr int K2 = 144;          // hidden channels + (cutoff, bias) row, padded to 16
+constexpr int XP_CAP = 80;       // atoms of a conformer staged in shared memory
+constexpr int NG = 2;            // pipelines per CTA
+constexpr int CTA_THREADS = NG * 128 + NG * 32;
+
+constexpr uint32_t W1_BYTES = F * K1 * 2;         // 16384
+constexpr uint32_t W2_BYTES = F * K2 * 2;         // 36864
+constexpr uint32_t B1_SBO = (K1 / 8) * 128;       // 1024: 8-row group stride of a K-major [rows, 64] image
+constexpr uint32_t A2_SBO = (K2 / 8) * 128;       // 2304: 8-row group stride of a K-major [rows, 144] image
+constexpr uint32_t B2_BYTES = K2 * TILE_E * 2;    // 36864 (the rbf image, 16384 B, aliases its head)
+constexpr uint32_t XP_BYTES = XP_CAP * F * 4;     // 40960
+constexpr uint32_t META_BYTES = TILE_E * 8 + TILE_E * 4;  // int2 {src, dst-if-row-end} + C
+constexpr uint32_t GROUP_BYTES = B2_BYTES + XP_BYTES + META_BYTES;
+constexpr uint32_t SMEM_BYTES = W1_BYTES + W2_BYTES + NG * GROUP_BYTES + 1024;  // + alignment slack
+
+struct FwdParams {
+  const float* xprime;
+  const float* dist;
+  const int32_t* rowptr;
+  const int32_t* col;
+  const int4* tiles;
+  const int32_t* num_tiles;
+  const uint8_t* weights;  // W1 image followed by W2 image
+  const float* offset;     // Gaussian centres [Ng]
+  float* agg;
+  float coeff;
+  float cutoff;
+  int Ng;
+};
+
+__device__ __forceinline__ float ssp_fast(float x) {
+  float t = __expf(-fabsf(x));
+  return fmaxf(x, 0.0f) + __logf(1.0f + t) - kLn2;
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[1 + NG * 5];  // wbar | per group: b1ready, d1ready, b2ready, d2ready, xbar
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_offset[K1];
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW1 = smem;
+  uint8_t* sW2 = smem + W1_BYTES;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1);
+    for (int g = 0; g < NG; ++g) {
+      tc::mbar_init(&bars[1 + g * 5 + 0], 128);  // b1ready: every compute thread arrives
+      tc::mbar_init(&bars[1 + g * 5 + 1], 1);    // d1ready: tcgen05.commit
+      tc::mbar_init(&bars[1 + g * 5 + 2], 128);  // b2ready
+      tc::mbar_init(&bars[1 + g * 5 + 3], 1);    // d2ready
+      tc::mbar_init(&bars[1 + g * 5 + 4], 1);    // xbar: TMA bulk copy of x'
+    }
+    tc::mbar_fence_init();
+  }
+  if (tid < K1) s_offset[tid] = (tid < p.Ng) ? p.offset[tid] : 0.0f;
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int64_t T = *p.num_tiles;
+  const int64_t U = (int64_t)gridDim.x * NG;
+
+  if (warp >= NG * 4) {
+    // ======================= MMA-issuing warp of group g =======================
+    const int g = warp - NG * 4;
+    if (lane == 0) {
+      uint64_t* wbar = &bars[0];
+      uint64_t* b1ready = &bars[1 + g * 5 + 0];
+      uint64_t* d1ready = &bars[1 + g * 5 + 1];
+      uint64_t* b2ready = &bars[1 + g * 5 + 2];
+      uint64_t* d2ready = &bars[1 + g * 5 + 3];
+      if (g == 0) {
+        tc::mbar_arrive_expect_tx(wbar, W1_BYTES + W2_BYTES);
+        tc::bulk_g2s(sW1, p.weights, W1_BYTES, wbar);
+        tc::bulk_g2s(sW2, p.weights + W1_BYTES, W2_BYTES, wbar);
+      }
+      uint8_t* sB = smem + W1_BYTES + W2_BYTES + g * GROUP_BYTES;
+      const uint32_t d1 = tmem_base + g * 256, d2 = d1 + 128;
+      const uint32_t aW1 = tc::smem_u32(sW1), aW2 = tc::smem_u32(sW2), aB = tc::smem_u32(sB);
+      const int64_t u = (int64_t)blockIdx.x * NG + g;
+      const int64_t t0 = u * T / U, t1 = (u + 1) * T / U;
+      tc::mbar_wait(wbar, 0);
+      uint32_t it = 0;
+      for (int64_t ti = t0; ti < t1; ++ti, ++it) {
+        const int4 tile = p.tiles[ti];
+        const int ne = p.rowptr[tile.y] - p.rowptr[tile.x];
+        const int npad = (ne + 15) & ~15;
+        const uint32_t par = it & 1;
+        tc::mbar_wait(b1ready, par);
+        tc::tc_fence_after();
+        const uint32_t idesc1 = tc::umma_idesc_f16(F, npad, 1, 0, 0);
+#pragma unroll
+        for (int ks = 0; ks < K1 / 16; ++ks)
+          tc::umma_f16(d1, tc::umma_smem_desc(aW1 + ks * 256, 128, B1_SBO), tc::umma_smem_desc(aB + ks * 256, 128, B1_SBO),
+                       idesc1, ks > 0);
+        tc::umma_commit(d1ready);
+        tc::mbar_wait(b2ready, par);
+        tc::tc_fence_after();
+        const uint32_t idesc2 = tc::umma_idesc_f16(F, npad, 1, 0, 1);
+#pragma unroll
+        for (int ks = 0; ks < K2 / 16; ++ks)
+          tc::umma_f16(d2, tc::umma_smem_desc(aW2 + ks * 256, 128, A2_SBO), tc::umma_smem_desc(aB + ks * 256, 128, A2_SBO),
+                       idesc2, ks > 0);
+        tc::umma_commit(d2ready);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= compute warps of group g =======================
+    const int g = warp >> 2;
+    const int t = tid & 127;               // thread within the group = edge slot (rbf) = channel (epilogues)
+    const int wq = warp & 3;               // TMEM lane quarter this warp may touch
+    uint64_t* b1ready = &bars[1 + g * 5 + 0];
+    uint64_t* d1ready = &bars[1 + g * 5 + 1];
+    uint64_t* b2ready = &bars[1 + g * 5 + 2];
+    uint64_t* d2ready = &bars[1 + g * 5 + 3];
+    uint64_t* xbar = &bars[1 + g * 5 + 4];
+    uint8_t* sB = smem + W1_BYTES + W2_BYTES + g * GROUP_BYTES;
+    float* sX = reinterpret_cast<float*>(sB + B2_BYTES);
+    int2* sMeta = reinterpret_cast<int2*>(sB + B2_BYTES + XP_BYTES);
+    float* sC = reinterpret_cast<float*>(sB + B2_BYTES + XP_BYTES + TILE_E * 8);
+    const uint32_t d1 = tmem_base + g * 256 + ((uint32_t)(wq * 32) << 16);
+    const uint32_t d2 = d1 + 128;
+    const int64_t u = (int64_t)blockIdx.x * NG + g;
+    const int64_t t0 = u * T / U, t1 = (u + 1) * T / U;
+    const float coeff = p.coeff, cutoff = p.cutoff;
+    const int Ng = p.Ng;
+
+    int staged_conf = -1;
+    uint32_t xloads = 0;
+    uint32_t it = 0;
+    for (int64_t ti = t0; ti < t1; ++ti, ++it) {
+      const int4 tile = p.tiles[ti];
+      const int e0 = p.rowptr[tile.x];
+      const int ne = p.rowptr[tile.y] - e0;
+      const int npad = (ne + 15) & ~15;
+      const uint32_t par = it & 1;
+      const int cs = tile.z, cn = tile.w;
+      const bool staged = cn <= XP_CAP;
+
+      tc::named_bar_sync(1 + g, 128);  // previous tile of this group fully consumed (sB, sX, sMeta, TMEM)
+
+      bool x_wait = false;
+      if (staged && cs != staged_conf) {
+        if (t == 0) {
+          const uint32_t bytes = (uint32_t)cn * F * 4;
+          tc::mbar_arrive_expect_tx(xbar, bytes);
+          tc::bulk_g2s(sX, p.xprime + (int64_t)cs * F, bytes, xbar);
+        }
+        staged_conf = cs;
+        x_wait = true;
+      }
+
+      // ---- per-edge metadata + Gaussian expansion -> B1 (K-major [edge, 64]) ----
+      for (int r = tile.x + t; r < tile.y; r += 128) {
+        const int b = p.rowptr[r] - e0, e = p.rowptr[r + 1] - e0;
+        for (int k = b; k < e; ++k) sMeta[k].y = (k == e - 1) ? r : -1;
+      }
+      if (t < npad) {
+        float d = 0.0f;
+        const bool live = t < ne;
+        if (live) {
+          d = p.dist[e0 + t];
+          const int src = p.col[e0 + t];
+          sMeta[t].x = staged ? (src - cs) : src;
+          sC[t] = 0.5f * (__cosf(d * kPi / cutoff) + 1.0f);
+        } else {
+          sMeta[t] = make_int2(0, -1);
+          sC[t] = 0.0f;
+        }
+        uint8_t* rowp = sB + (t >> 3) * B1_SBO + (t & 7) * 16;
+#pragma unroll
+        for (int jc = 0; jc < K1 / 8; ++jc) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int k = jc * 8 + j;
+            float x = d - s_offset[k];
+            float rv = __expf(coeff * x * x);
+            v[j] = !live ? 0.0f : (k < Ng ? rv : (k == Ng ? 1.0f : 0.0f));
+          }
+          uint4 q = make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
+                               tc::pack_bf16x2(v[6], v[7]));
+          *reinterpret_cast<uint4*>(rowp + jc * 128) = q;
+        }
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(b1ready);
+
+      // ---- epilogue 1: a' = C * ssp(D1) -> B2 (MN-major [144, edge]) ----
+      tc::mbar_wait(d1ready, par);
+      tc::tc_fence_after();
+      {
+        uint8_t* colp = sB + t * 16;  // k = t: (k/8)*128 + (k%8)*16 = k*16
+        for (int c0 = 0; c0 < npad; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(d1 + c0, v);
+          tc::tmem_wait_ld();
+          const float4* cp = reinterpret_cast<const float4*>(sC + c0);
+          float c[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 cc = cp[q];
+            c[q * 4 + 0] = cc.x; c[q * 4 + 1] = cc.y; c[q * 4 + 2] = cc.z; c[q * 4 + 3] = cc.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = ssp_fast(v[j]) * c[j];
+          uint4 q0 = make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
+                                tc::pack_bf16x2(v[6], v[7]));
+          uint4 q1 = make_uint4(tc::pack_bf16x2(v[8], v[9]), tc::pack_bf16x2(v[10], v[11]),
+                                tc::pack_bf16x2(v[12], v[13]), tc::pack_bf16x2(v[14], v[15]));
+          *reinterpret_cast<uint4*>(colp + (c0 >> 3) * A2_SBO) = q0;
+          *reinterpret_cast<uint4*>(colp + ((c0 >> 3) + 1) * A2_SBO) = q1;
+        }
+        // rows 128..143: row 128 = C_e (multiplies the b2 column of W2aug), rows 129..143 = 0
+        for (int item = t; item < (npad >> 3) * 16; item += 128) {
+          const int ec = item >> 4, kr = item & 15;
+          uint4 q = make_uint4(0, 0, 0, 0);
+          if (kr == 0) {
+            const float* c = sC + ec * 8;
+            q = make_uint4(tc::pack_bf16x2(c[0], c[1]), tc::pack_bf16x2(c[2], c[3]), tc::pack_bf16x2(c[4], c[5]),
+                           tc::pack_bf16x2(c[6], c[7]));
+          }
+          *reinterpret_cast<uint4*>(sB + ec * A2_SBO + (128 + kr) * 16) = q;
+        }
+      }
+      tc::tc_fence_before();
+      tc::fence_proxy_async();
+      tc::mbar_arrive(b2ready);
+
+      // ---- epilogue 2: gather x'_src, multiply, reduce per target row (CSR order) ----
+      tc::mbar_wait(d2ready, par);
+      tc::tc_fence_after();
+      if (x_wait) {
+        tc::mbar_wait(xbar, xloads & 1);
+        ++xloads;
+      }
+      {
+        const int f = wq * 32 + lane;
+        const float* xsrc = staged ? (sX + f) : (p.xprime + f);
+        float acc = 0.0f;
+        for (int c0 = 0; c0 < npad; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(d2 + c0, v);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int e = c0 + j;
+            if (e < ne) {
+              const int2 m = sMeta[e];
+              acc = fmaf(v[j], xsrc[(int64_t)m.x * F], acc);
+              if (m.y >= 0) {
+                p.agg[(int64_t)m.y * F + f] = acc;
+                acc = 0.0f;
+              }
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
+}
+
+// ---- weight images ----------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
+                                    const float* __restrict__ W2, const float* __restrict__ b2, int Ng,
+                                    uint8_t* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < F * K1) {
+    const int m = idx / K1, k = idx % K1;
+    float v = (k < Ng) ? W1[m * Ng + k] : (k == Ng ? b1[m] : 0.0f);
+    uint32_t off = (m & 7) * 16 + (k & 7) * 2 + (m >> 3) * B1_SBO + (k >> 3) * 128;
+    *reinterpret_cast<__nv_bfloat16*>(out + off) = __float2bfloat16_rn(v);
+  } else if (idx < F * K1 + F * K2) {
+    const int j = idx - F * K1;
+    const int m = j / K2, k = j % K2;
+    float v = (k < F) ? W2[m * F + k] : (k == F ? b2[m] : 0.0f);
+    uint32_t off = (m & 7) * 16 + (k & 7) * 2 + (m >> 3) * A2_SBO + (k >> 3) * 128;
+    *reinterpret_cast<__nv_bfloat16*>(out + W1_BYTES + off) = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace
+}  // namespace cmp
+
+using namespace cmp;
+
+extern "C" int cmp_cfconv_tc_supported(int num_filters, int num_gaussians) {
+  return num_filters == F && num_gaussians >= 1 && num_gaussians < K1;
+}
+
+extern "C" size_t cmp_cfconv_tc_weights_bytes(void) { return W1_BYTES + W2_BYTES; }
+
+extern "C" int cmp_cfconv_tc_tile_edges(void) { return TILE_E; }
+
+extern "C" int cmp_cfconv_tc_pack_weights(const float* W1, const float* b1, const float* W2, const float* b2,
+                                          int num_filters, int num_gaussians, void* packed, cmp_stream_t stream) {
+  CMP_REQUIRE(cmp_cfconv_tc_supported(num_filters, num_gaussians), CMP_EUNSUPPORTED,
+              "cmp_cfconv_tc_pack_weights: needs num_filters == 128 and num_gaussians < 64 (got %d, %d)", num_filters,
+              num_gaussians);
+  CMP_REQUIRE(W1 && b1 && W2 && b2 && packed, CMP_EINVAL, "cmp_cfconv_tc_pack_weights: null pointer");
+  const int total = F * K1 + F * K2;
+  pack_weights_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(W1, b1, W2, b2, num_gaussians,
+                                                                         reinterpret_cast<uint8_t*>(packed));
+  CMP_LAUNCH_CHECK("cmp_cfconv_tc_pack_weights");
+  return CMP_OK;
+}
+
+extern "C" int cmp_cfconv_fused_fwd(const float* xprime, const float* dist, const int32_t* rowptr, const int32_t* col,
+                                    const void* tiles, const int32_t* num_tiles, const void* packed_weights,
+                                    const float* offset, int num_gaussians, float coeff, float cutoff, int64_t N,
+                                    int num_filters, float* agg, cmp_stream_t stream) {
+  CMP_REQUIRE(cmp_cfconv_tc_supported(num_filters, num_gaussians), CMP_EUNSUPPORTED,
+              "cmp_cfconv_fused_fwd: needs num_filters == 128 and num_gaussians < 64 (got %d, %d)", num_filters,
+              num_gaussians);
+  CMP_REQUIRE(N >= 0 && cutoff > 0.0f, CMP_EINVAL, "cmp_cfconv_fused_fwd: bad size");
+  if (N == 0) return CMP_OK;
+  CMP_REQUIRE(xprime && dist && rowptr && col && tiles && num_tiles && packed_weights && offset && agg, CMP_EINVAL,
+              "cmp_cfconv_fused_fwd: null pointer");
+  CMP_REQUIRE(((uintptr_t)xprime % 16 == 0) && ((uintptr_t)packed_weights % 16 == 0), CMP_EINVAL,
+              "cmp_cfconv_fused_fwd: xprime / packed_weights must be 16-byte aligned (TMA bulk copy)");
+  CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED, "cmp_cfconv_fused_fwd: needs an sm_100 device (tcgen05)");
+  cudaStream_t st = as_stream(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(cfconv_fused_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) !=
+        cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("cmp_cfconv_fused_fwd: cannot opt in to %u bytes of shared memory", SMEM_BYTES);
+      return CMP_ECUDA;
+    }
+    attr_set = true;
+  }
+  // rows without edges are never visited by a tile: their aggregate is zero
+  CMP_REQUIRE(cudaMemsetAsync(agg, 0, (size_t)N * F * sizeof(float), st) == cudaSuccess, CMP_ECUDA,
+              "cmp_cfconv_fused_fwd: memset failed");
+  FwdParams p;
+  p.xprime = xprime;
+  p.dist = dist;
+  p.rowptr = rowptr;
+  p.col = col;
+  p.tiles = reinterpret_cast<const int4*>(tiles);
+  p.num_tiles = num_tiles;
+  p.weights = reinterpret_cast<const uint8_t*>(packed_weights);
+  p.offset = offset;
+  p.agg = agg;
+  p.coeff = coeff;
+  p.cutoff = cutoff;
+  p.Ng = num_gaussians;
+  cfconv_fused_fwd_kernel<<<sm_count(), CTA_THREADS, SMEM_BYTES, st>>>(p);
+  CMP_LAUNCH_CHECK("cmp_cfconv_fused_fwd");
+  return CMP_OK;
+}

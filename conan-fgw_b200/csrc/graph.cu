@@ -264,6 +264,60 @@ __global__ void csr_to_edge_index_kernel(const int32_t* __restrict__ rowptr, con
   }
 }
 
+// ---- edge tiles: runs of whole target rows of ONE conformer holding <= tile_edges edges ----------
+// (the unit of work of the fused tensor-core kernels: a tile is one UMMA N-extent)
+__device__ __forceinline__ int walk_tiles(const int32_t* __restrict__ rowptr, int s, int e, int tile_edges,
+                                          int4* __restrict__ out, int* status) {
+  int count = 0, first = s, cur = 0;
+  for (int r = s; r < e; ++r) {
+    int d = rowptr[r + 1] - rowptr[r];
+    if (d > tile_edges) {
+      atomicOr(status, CMP_STATUS_EDGE_OVERFLOW);
+      d = 0;
+    }
+    if (cur + d > tile_edges && cur > 0) {
+      if (out) out[count] = make_int4(first, r, s, e - s);
+      ++count;
+      first = r;
+      cur = 0;
+    }
+    cur += d;
+  }
+  if (cur > 0) {
+    if (out) out[count] = make_int4(first, e, s, e - s);
+    ++count;
+  }
+  return count;
+}
+
+__global__ void tiles_count_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ seg_ptr, int64_t G,
+                                   int tile_edges, int32_t* __restrict__ counts, int* status) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  counts[g] = walk_tiles(rowptr, seg_ptr[g], seg_ptr[g + 1], tile_edges, nullptr, status);
+}
+
+__global__ void tiles_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ seg_ptr, int64_t G,
+                                  int tile_edges, const int32_t* __restrict__ tile_ptr, int64_t cap,
+                                  int4* __restrict__ tiles, int32_t* __restrict__ num_tiles, int* status) {
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g == 0) *num_tiles = (tile_ptr[G] <= cap) ? tile_ptr[G] : 0;
+  if (g >= G) return;
+  if ((int64_t)tile_ptr[G] > cap) {
+    if (g == 0) atomicOr(status, CMP_STATUS_EDGE_OVERFLOW);
+    return;
+  }
+  walk_tiles(rowptr, seg_ptr[g], seg_ptr[g + 1], tile_edges, tiles + tile_ptr[g], status);
+}
+
+__global__ void gather_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
+                                  const int32_t* __restrict__ count_ptr, float* __restrict__ dst) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t n = *count_ptr;
+  for (; i < n; i += stride) dst[i] = src[idx[i]];
+}
+
 __global__ void set_i32_kernel(int32_t* p, int64_t n, int32_t v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -337,5 +391,47 @@ extern "C" int cmp_csr_to_edge_index(const int32_t* rowptr, const int32_t* col, 
   CMP_REQUIRE(rowptr && col && edge_index, CMP_EINVAL, "cmp_csr_to_edge_index: null pointer");
   csr_to_edge_index_kernel<<<(int)ceil_div(N, 256), 256, 0, as_stream(stream)>>>(rowptr, col, N, E, edge_index);
   CMP_LAUNCH_CHECK("cmp_csr_to_edge_index");
+  return CMP_OK;
+}
+
+extern "C" size_t cmp_build_tiles_workspace(int64_t G) {
+  return align_up((size_t)(2 * G + 8) * sizeof(int32_t), 256);  // counts[G] + tile_ptr[G+1]
+}
+
+extern "C" int cmp_build_tiles(const int32_t* rowptr, const int32_t* seg_ptr, int64_t G, int tile_edges, void* tiles,
+                               int64_t cap_tiles, int32_t* num_tiles, void* workspace, size_t workspace_bytes,
+                               int* status, cmp_stream_t stream) {
+  CMP_REQUIRE(G >= 0 && tile_edges >= 16 && cap_tiles >= 0, CMP_EINVAL, "cmp_build_tiles: bad size");
+  CMP_REQUIRE(num_tiles && status, CMP_EINVAL, "cmp_build_tiles: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (G == 0) {
+    set_i32_kernel<<<1, 32, 0, st>>>(num_tiles, 1, 0);
+    CMP_LAUNCH_CHECK("cmp_build_tiles(empty)");
+    return CMP_OK;
+  }
+  CMP_REQUIRE(rowptr && seg_ptr && tiles, CMP_EINVAL, "cmp_build_tiles: null pointer");
+  CMP_REQUIRE(workspace && workspace_bytes >= cmp_build_tiles_workspace(G), CMP_EWORKSPACE,
+              "cmp_build_tiles: workspace too small");
+  int32_t* counts = reinterpret_cast<int32_t*>(workspace);
+  int32_t* tile_ptr = counts + G;
+  tiles_count_kernel<<<(unsigned)ceil_div(G, 128), 128, 0, st>>>(rowptr, seg_ptr, G, tile_edges, counts, status);
+  CMP_LAUNCH_CHECK("cmp_build_tiles(count)");
+  scan_conformers_kernel<<<1, 1024, 0, st>>>(counts, G, tile_ptr);
+  CMP_LAUNCH_CHECK("cmp_build_tiles(scan)");
+  tiles_fill_kernel<<<(unsigned)ceil_div(G, 128), 128, 0, st>>>(rowptr, seg_ptr, G, tile_edges, tile_ptr, cap_tiles,
+                                                               reinterpret_cast<int4*>(tiles), num_tiles, status);
+  CMP_LAUNCH_CHECK("cmp_build_tiles(fill)");
+  return CMP_OK;
+}
+
+extern "C" int cmp_gather_f32(const float* src, const int32_t* idx, const int32_t* count_ptr, int64_t max_count,
+                              float* dst, cmp_stream_t stream) {
+  CMP_REQUIRE(max_count >= 0, CMP_EINVAL, "cmp_gather_f32: negative size");
+  if (max_count == 0) return CMP_OK;
+  CMP_REQUIRE(src && idx && count_ptr && dst, CMP_EINVAL, "cmp_gather_f32: null pointer");
+  int64_t blocks = ceil_div(max_count, 256);
+  if (blocks > 4096) blocks = 4096;
+  gather_f32_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, idx, count_ptr, dst);
+  CMP_LAUNCH_CHECK("cmp_gather_f32");
   return CMP_OK;
 }

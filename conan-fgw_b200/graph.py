@@ -73,6 +73,38 @@ class NeighborList:
             self._edge_index = ei
         return self._edge_index
 
+    # ---- edge tiles for the fused tensor-core kernels (built on first use, no host sync) ----------
+    def _build_tiles(self, rowptr):
+        dev = rowptr.device
+        tile_e = _lib.size_query("cmp_cfconv_tc_tile_edges")
+        cap = self.cap_E // 64 + self.G + 1
+        tiles = torch.empty(max(cap, 1), 4, dtype=torch.int32, device=dev)
+        num = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = _lib.workspace(_lib.size_query("cmp_build_tiles_workspace", self.G), dev)
+        _lib.call("cmp_build_tiles", _lib.ptr(rowptr), _lib.ptr(self.seg_ptr), self.G, tile_e, _lib.ptr(tiles), cap,
+                  _lib.ptr(num), _lib.ptr(ws), ws.numel(), _lib.ptr(self.status))
+        return tiles, num
+
+    def tiles(self):
+        """(tiles int32[cap,4], num_tiles int32[1]) over the target-sorted CSR."""
+        if getattr(self, "_tiles", None) is None:
+            if self.G == 0 and self.N > 0:
+                raise _lib.ConanMPError("edge tiles need conformer segments (graph was built from a raw edge_index)")
+            self._tiles = self._build_tiles(self.rowptr)
+        return self._tiles
+
+    def tiles_t(self):
+        """Same for the source-sorted transpose, plus ``dist_t`` (distances in transposed edge order)."""
+        if getattr(self, "_tiles_t", None) is None:
+            if self.rowptr_t is None:
+                raise _lib.ConanMPError("the transposed neighbour list was not built")
+            tiles, num = self._build_tiles(self.rowptr_t)
+            dist_t = torch.empty_like(self.dist)
+            _lib.call("cmp_gather_f32", _lib.ptr(self.dist), _lib.ptr(self.eid_t), _lib.ptr(self.rowptr[self.N:]),
+                      self.cap_E, _lib.ptr(dist_t))
+            self._tiles_t = (tiles, num, dist_t)
+        return self._tiles_t
+
     def edge_weight(self) -> torch.Tensor:
         w = self.dist[: self.E]
         w._cmp_graph = self

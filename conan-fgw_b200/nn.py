@@ -98,12 +98,34 @@ class CFConv(nn.Module):
         self.lin2 = Linear(num_filters, out_channels)
         self.nn = nn
         self.cutoff = cutoff
+        self.precision = "fp32"     # "fp32": exact kernels;  "bf16": fused tcgen05 kernel (bf16 filter MLP)
         self.reset_parameters()
 
     def reset_parameters(self):
         torch.nn.init.xavier_uniform_(self.lin1.weight)
         torch.nn.init.xavier_uniform_(self.lin2.weight)
         self.lin2.bias.data.fill_(0)
+
+    def _standard_mlp(self):
+        net = self.nn
+        return (isinstance(net, torch.nn.Sequential) and len(net) == 3 and isinstance(net[0], torch.nn.Linear)
+                and isinstance(net[1], ShiftedSoftplus) and isinstance(net[2], torch.nn.Linear)
+                and net[0].bias is not None and net[2].bias is not None)
+
+    def fused_ok(self, graph, smearing) -> bool:
+        """The fused geometric kernel applies: bf16 mode, radius-built graph, Gaussian expansion of its
+        distances, standard filter MLP, supported (num_filters, num_gaussians), sm_100 device."""
+        return (self.precision == "bf16" and graph is not None and graph.G > 0 and graph.cutoff is not None
+                and isinstance(smearing, GaussianSmearing) and self._standard_mlp()
+                and ops.fused_supported(self.lin1.out_features, smearing.offset.numel())
+                and self.nn[0].in_features == smearing.offset.numel())
+
+    def forward_fused(self, x, graph, smearing, act=_lib.ACT_NONE):
+        xp = self.lin1(x)
+        net = self.nn
+        agg = ops.cfconv_fused(xp, net[0].weight, net[0].bias, net[2].weight, net[2].bias, graph, smearing.offset,
+                               smearing.coeff, self.cutoff)
+        return self.lin2(agg, act=act)
 
     def filter(self, edge_attr):
         """``self.nn(edge_attr)``: Linear -> ShiftedSoftplus -> Linear with the activation fused."""
@@ -119,6 +141,10 @@ class CFConv(nn.Module):
             graph, perm = graph_from_edge_index(edge_index, edge_weight, x.size(0))
             if perm is not None:
                 edge_attr = edge_attr[perm]
+        tag = getattr(edge_attr, "_cmp_rbf_of", None)
+        if tag is not None and getattr(tag[0], "_cmp_graph", None) is graph and self.fused_ok(graph, tag[1]):
+            # edge_attr is the Gaussian expansion of this graph's own distances: run the fused kernel
+            return self.forward_fused(x, graph, tag[1], act=act)
         W = self.filter(edge_attr)
         xp = self.lin1(x)
         agg = ops.cfconv_message(xp, W, graph, self.cutoff)
@@ -151,6 +177,10 @@ class InteractionBlock(nn.Module):
                 residual=None):
         # conv -> ssp (fused into conv.lin2's epilogue) -> lin (+ residual fused when the caller passes it)
         y = self.conv(x, edge_index, edge_weight, edge_attr, graph=graph, act=_lib.ACT_SSP)
+        return self.lin(y, residual=residual)
+
+    def forward_fused(self, x, graph, smearing, residual=None):
+        y = self.conv.forward_fused(x, graph, smearing, act=_lib.ACT_SSP)
         return self.lin(y, residual=residual)
 
 
@@ -186,7 +216,19 @@ class SchNet(nn.Module):
         self.lin2 = Linear(hidden_channels // 2, 1)
         self.register_buffer("initial_atomref", None)
         self.atomref = None
+        self.precision = "fp32"
         self.reset_parameters()
+
+    def set_precision(self, precision: str):
+        """"fp32": exact-fp32 kernels (1e-5 parity mode).  "bf16": fused tcgen05 CFConv with a bf16
+        filter MLP (fp32 accumulation, fp32 node features); tolerance stated in DESIGN.md."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        for m in self.modules():
+            if isinstance(m, CFConv):
+                m.precision = precision
+        return self
 
     def reset_parameters(self):
         self.embedding.reset_parameters()
@@ -207,6 +249,11 @@ class SchNet(nn.Module):
         if isinstance(ig, RadiusInteractionGraph):
             graph = ig.neighbor_list(pos, batch, num_graphs)
             h = self.embed(z, graph.status)
+            if all(blk.conv.fused_ok(graph, self.distance_expansion) for blk in self.interactions):
+                # fused path: no edge_index / rbf[E, Ng] / filter[E, F] is ever materialised, no host sync
+                for blk in self.interactions:
+                    h = blk.forward_fused(h, graph, self.distance_expansion, residual=h)
+                return h, graph
             edge_index = None
             edge_weight = graph.edge_weight()      # first host sync: also surfaces device-side input errors
         else:  # user supplied interaction graph: generic path

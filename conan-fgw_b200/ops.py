@@ -213,6 +213,80 @@ def cfconv_message(xprime, filt, graph, cutoff):
     return _CFConvMessageFn.apply(xprime, filt, graph, cutoff)
 
 
+def _fused_fwd_launch(xin, dist, rowptr, col, tiles, num_tiles, packed, offset, coeff, cutoff, n_edges_hint):
+    N, F = xin.shape
+    Ng = offset.numel()
+    out = torch.empty(N, F, dtype=torch.float32, device=xin.device)
+    # algorithmic FLOPs of this launch: 2*(Ng*F + F*F) per edge
+    work = 2.0 * (Ng * F + F * F) * float(n_edges_hint)
+    call("cmp_cfconv_fused_fwd", ptr(xin), ptr(dist), ptr(rowptr), ptr(col), ptr(tiles), ptr(num_tiles), ptr(packed),
+         ptr(offset), Ng, float(coeff), float(cutoff), N, F, ptr(out), work=work)
+    return out
+
+
+def pack_filter_weights(W1, b1, W2, b2):
+    F, Ng = W1.shape
+    nbytes = _lib.size_query("cmp_cfconv_tc_weights_bytes")
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=W1.device)
+    call("cmp_cfconv_tc_pack_weights", ptr(_f32c(W1)), ptr(_f32c(b1)), ptr(_f32c(W2)), ptr(_f32c(b2)), F, Ng,
+         ptr(packed))
+    return packed
+
+
+class _CFConvFusedFn(Function):
+    """Geometric CFConv in one tcgen05 kernel (bf16 filter MLP):  agg = sum_j x'_j * W(d_ij) * C(d_ij).
+
+    backward: d x' runs the SAME fused kernel over the transposed neighbour list with the upstream
+    gradient as its input (W depends on the edge only through d_ij); the filter-MLP weight gradients
+    are recomputed on the exact-fp32 kernels (rbf -> Linear+ssp -> Linear, then GEMMs with K = E)."""
+
+    @staticmethod
+    def forward(ctx, xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff):
+        xprime = _f32c(xprime)
+        packed = pack_filter_weights(W1, b1, W2, b2)
+        tiles, num = graph.tiles()
+        e_hint = graph._E if graph._E is not None else graph.cap_E
+        agg = _fused_fwd_launch(xprime, graph.dist, graph.rowptr, graph.col, tiles, num, packed, offset, coeff,
+                                cutoff, e_hint)
+        ctx.graph, ctx.coeff, ctx.cutoff = graph, float(coeff), float(cutoff)
+        ctx.save_for_backward(xprime, W1, b1, W2, b2, offset, packed)
+        return agg
+
+    @staticmethod
+    def backward(ctx, g):
+        xprime, W1, b1, W2, b2, offset, packed = ctx.saved_tensors
+        graph = ctx.graph
+        g = _f32c(g)
+        N, F = xprime.shape
+        dx = None
+        if ctx.needs_input_grad[0]:
+            tiles_t, num_t, dist_t = graph.tiles_t()
+            e_hint = graph._E if graph._E is not None else graph.cap_E
+            dx = _fused_fwd_launch(g, dist_t, graph.rowptr_t, graph.col_t, tiles_t, num_t, packed, offset, ctx.coeff,
+                                   ctx.cutoff, e_hint)
+        grads = [None, None, None, None]
+        if any(ctx.needs_input_grad[1:5]):
+            E = graph.E
+            dfilt = torch.empty(E, F, dtype=torch.float32, device=g.device)
+            call("cmp_cfconv_message_bwd", ptr(g), ptr(xprime), None, ptr(graph.dist), ptr(graph.rowptr),
+                 ptr(graph.col), None, None, None, N, F, ctx.cutoff, ptr(dfilt), None)
+            with torch.enable_grad():
+                ps = [t.detach().requires_grad_(True) for t in (W1, b1, W2, b2)]
+                rbf = gaussian_rbf(graph.dist[:E], offset, ctx.coeff)
+                filt = linear(linear(rbf, ps[0], ps[1], ACT_SSP), ps[2], ps[3])
+                grads = list(torch.autograd.grad(filt, ps, dfilt))
+        return (dx, *grads, None, None, None, None)
+
+
+def cfconv_fused(xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff):
+    return _CFConvFusedFn.apply(xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff)
+
+
+def fused_supported(num_filters, num_gaussians) -> bool:
+    return bool(_lib.lib().cmp_cfconv_tc_supported(int(num_filters), int(num_gaussians))) and \
+        bool(_lib.lib().cmp_device_is_sm100())
+
+
 class _SegmentSumFn(Function):
     @staticmethod
     def forward(ctx, x, seg_ptr, G):

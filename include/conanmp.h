@@ -172,6 +172,47 @@ int cmp_segment_sum_fwd(const float* x, const int32_t* seg_ptr, int64_t G, int C
 int cmp_segment_sum_bwd(const float* dout, const int32_t* seg_ptr, int64_t G, int C, float* dx,
                         cmp_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * Fused tensor-core CFConv (tcgen05 / TMEM / TMA bulk copies), num_filters = 128
+ * ------------------------------------------------------------------------- */
+
+/* Edge tiles = the work units of the fused kernels: runs of whole target rows of ONE conformer
+ * holding <= tile_edges edges.  tiles is an int4 array {first_row, end_row, conformer_first_atom,
+ * conformer_atom_count}; *num_tiles receives the count (device memory, no host sync).
+ * Works on either orientation of the CSR (rowptr or rowptr_t). */
+size_t cmp_build_tiles_workspace(int64_t G);
+int cmp_build_tiles(const int32_t* rowptr, const int32_t* seg_ptr, int64_t G, int tile_edges,
+                    void* tiles, int64_t cap_tiles, int32_t* num_tiles, void* workspace,
+                    size_t workspace_bytes, int* status, cmp_stream_t stream);
+
+/* dst[i] = src[idx[i]] for i < *count_ptr (per-edge data in transposed order, no host sync). */
+int cmp_gather_f32(const float* src, const int32_t* idx, const int32_t* count_ptr,
+                   int64_t max_count, float* dst, cmp_stream_t stream);
+
+/* 1 when (num_filters, num_gaussians) is served by the fused kernels (128, < 64). */
+int cmp_cfconv_tc_supported(int num_filters, int num_gaussians);
+size_t cmp_cfconv_tc_weights_bytes(void);
+int cmp_cfconv_tc_tile_edges(void);
+/* Filter-MLP weights (PyG InteractionBlock.mlp: Linear(Ng,F), ssp, Linear(F,F)) -> bf16 UMMA
+ * shared-memory images with the biases folded in as an extra K column. */
+int cmp_cfconv_tc_pack_weights(const float* W1, const float* b1, const float* W2, const float* b2,
+                               int num_filters, int num_gaussians, void* packed,
+                               cmp_stream_t stream);
+/* agg[i,:] = sum_{j->i} xprime[j,:] * (W2 ssp(W1 rbf(d_ij) + b1) + b2) * C(d_ij) in ONE kernel:
+ * Gaussian expansion, filter MLP (tcgen05, bf16 operands, fp32 accumulate), cosine cutoff,
+ * gather-multiply and the per-target reduction (CSR order, deterministic).  Replaces
+ * GaussianSmearing + CFConv.nn + CFConv.propagate (sns.py:161-164 through PyG CFConv.forward). */
+int cmp_cfconv_fused_fwd(const float* xprime, const float* dist, const int32_t* rowptr,
+                         const int32_t* col, const void* tiles, const int32_t* num_tiles,
+                         const void* packed_weights, const float* offset, int num_gaussians,
+                         float coeff, float cutoff, int64_t N, int num_filters, float* agg,
+                         cmp_stream_t stream);
+
+/* Single-tile UMMA probe used by the tests to pin descriptor / TMEM conventions. */
+int cmp_debug_umma_gemm(const void* a_img, int64_t a_bytes, const void* b_img, int64_t b_bytes,
+                        float* D, int N, int K, int fmt, int a_mn, int b_mn, int a_lbo, int a_sbo,
+                        int a_kstep, int b_lbo, int b_sbo, int b_kstep, cmp_stream_t stream);
+
 /* Fused Adam step on flat fp32 buffers (the optimiser of model/common.py:368-370). */
 int cmp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, float weight_decay, int step,
