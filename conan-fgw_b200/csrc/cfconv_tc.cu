@@ -28,8 +28,9 @@ constexpr int TILE_E = 128;      // edges per tile   = max UMMA N
 constexpr int K1 = 64;           // Gaussians padded (+ bias column)
 constexpr int K2 = 144;          // hidden channels + (cutoff, bias) row, padded to 16
 constexpr int XP_CAP = 80;       // atoms of a conformer staged in shared memory
-constexpr int NG = 2;            // pipelines per CTA
-constexpr int CTA_THREADS = NG * 128 + NG * 32;
+constexpr int NG = 2;            // pipelines ("groups") per CTA
+constexpr int GT = 256;          // compute threads per group (8 warps: 2 per TMEM lane quarter)
+constexpr int CTA_THREADS = NG * GT + NG * 32;
 
 constexpr uint32_t W1_BYTES = F * K1 * 2;         // 16384
 constexpr uint32_t W2_BYTES = F * K2 * 2;         // 36864
@@ -37,37 +38,56 @@ constexpr uint32_t B1_SBO = (K1 / 8) * 128;       // 1024: 8-row group stride of
 constexpr uint32_t A2_SBO = (K2 / 8) * 128;       // 2304: 8-row group stride of a K-major [rows, 144] image
 constexpr uint32_t B2_BYTES = K2 * TILE_E * 2;    // 36864 (the rbf image, 16384 B, aliases its head)
 constexpr uint32_t XP_BYTES = XP_CAP * F * 4;     // 40960
-constexpr uint32_t META_BYTES = TILE_E * 8 + TILE_E * 4;  // int2 {src, dst-if-row-end} + C
-constexpr uint32_t GROUP_BYTES = B2_BYTES + XP_BYTES + META_BYTES;
-constexpr uint32_t SMEM_BYTES = W1_BYTES + W2_BYTES + NG * GROUP_BYTES + 1024;  // + alignment slack
+constexpr uint32_t OFF_X = B2_BYTES;
+constexpr uint32_t OFF_META = OFF_X + XP_BYTES;          // int2[128] {src, dst if the edge ends its row else -1}
+constexpr uint32_t OFF_C = OFF_META + TILE_E * 8;        // float[128] cosine cutoff
+constexpr uint32_t OFF_ROW = OFF_C + TILE_E * 4;         // int[136]  row offsets of the tile (relative)
+constexpr uint32_t GROUP_BYTES = OFF_ROW + 544;
+constexpr uint32_t SMEM_BYTES = W1_BYTES + W2_BYTES + NG * GROUP_BYTES;
 
 struct FwdParams {
   const float* xprime;
   const float* dist;
   const int32_t* rowptr;
   const int32_t* col;
-  const int4* tiles;
+  const int4* tiles;       // 2 x int4 per tile
   const int32_t* num_tiles;
   const uint8_t* weights;  // W1 image followed by W2 image
   const float* offset;     // Gaussian centres [Ng]
   float* agg;
-  float coeff;
+  float coeff_log2e;       // coeff * log2(e)
   float cutoff;
   int Ng;
 };
 
+struct TileInfo {
+  int row_begin, row_end, cs, cn, e0, ne;
+};
+
+__device__ __forceinline__ TileInfo load_tile(const int4* __restrict__ tiles, int64_t ti) {
+  const int4 a = __ldg(tiles + 2 * ti), b = __ldg(tiles + 2 * ti + 1);
+  TileInfo t;
+  t.row_begin = a.x; t.row_end = a.y; t.cs = a.z; t.cn = a.w; t.e0 = b.x; t.ne = b.y;
+  return t;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float ssp_fast(float x) {
-  float t = __expf(-fabsf(x));
+  float t = ex2_approx(-1.4426950408889634f * fabsf(x));
   return fmaxf(x, 0.0f) + __logf(1.0f + t) - kLn2;
 }
 
 __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const FwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bars[1 + NG * 5];  // wbar | per group: b1ready, d1ready, b2ready, d2ready, xbar
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_offset[K1];
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW1 = smem;
   uint8_t* sW2 = smem + W1_BYTES;
   const int tid = threadIdx.x;
@@ -76,11 +96,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
     for (int g = 0; g < NG; ++g) {
-      tc::mbar_init(&bars[1 + g * 5 + 0], 128);  // b1ready: every compute thread arrives
-      tc::mbar_init(&bars[1 + g * 5 + 1], 1);    // d1ready: tcgen05.commit
-      tc::mbar_init(&bars[1 + g * 5 + 2], 128);  // b2ready
-      tc::mbar_init(&bars[1 + g * 5 + 3], 1);    // d2ready
-      tc::mbar_init(&bars[1 + g * 5 + 4], 1);    // xbar: TMA bulk copy of x'
+      tc::mbar_init(&bars[1 + g * 5 + 0], GT);  // b1ready: every compute thread arrives
+      tc::mbar_init(&bars[1 + g * 5 + 1], 1);   // d1ready: tcgen05.commit
+      tc::mbar_init(&bars[1 + g * 5 + 2], GT);  // b2ready
+      tc::mbar_init(&bars[1 + g * 5 + 3], 1);   // d2ready
+      tc::mbar_init(&bars[1 + g * 5 + 4], 1);   // xbar: TMA bulk copy of x'
     }
     tc::mbar_fence_init();
   }
@@ -94,10 +114,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
 
   const int64_t T = *p.num_tiles;
   const int64_t U = (int64_t)gridDim.x * NG;
+  const int k1steps = (p.Ng + 1 + 15) >> 4;   // UMMA K-steps that hold Gaussians + the bias column
 
-  if (warp >= NG * 4) {
+  if (warp >= NG * (GT / 32)) {
     // ======================= MMA-issuing warp of group g =======================
-    const int g = warp - NG * 4;
+    const int g = warp - NG * (GT / 32);
     if (lane == 0) {
       uint64_t* wbar = &bars[0];
       uint64_t* b1ready = &bars[1 + g * 5 + 0];
@@ -116,16 +137,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
       const int64_t t0 = u * T / U, t1 = (u + 1) * T / U;
       tc::mbar_wait(wbar, 0);
       uint32_t it = 0;
+      int ne = (t0 < t1) ? load_tile(p.tiles, t0).ne : 0;
       for (int64_t ti = t0; ti < t1; ++ti, ++it) {
-        const int4 tile = p.tiles[ti];
-        const int ne = p.rowptr[tile.y] - p.rowptr[tile.x];
         const int npad = (ne + 15) & ~15;
+        if (ti + 1 < t1) ne = load_tile(p.tiles, ti + 1).ne;
         const uint32_t par = it & 1;
         tc::mbar_wait(b1ready, par);
         tc::tc_fence_after();
         const uint32_t idesc1 = tc::umma_idesc_f16(F, npad, 1, 0, 0);
-#pragma unroll
-        for (int ks = 0; ks < K1 / 16; ++ks)
+        for (int ks = 0; ks < k1steps; ++ks)
           tc::umma_f16(d1, tc::umma_smem_desc(aW1 + ks * 256, 128, B1_SBO), tc::umma_smem_desc(aB + ks * 256, 128, B1_SBO),
                        idesc1, ks > 0);
         tc::umma_commit(d1ready);
@@ -142,8 +162,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
     __syncwarp();
   } else {
     // ======================= compute warps of group g =======================
-    const int g = warp >> 2;
-    const int t = tid & 127;               // thread within the group = edge slot (rbf) = channel (epilogues)
+    const int g = warp / (GT / 32);
+    const int tt = tid - g * GT;           // 0..255 within the group
+    const int e = tt & 127;                // edge slot of this thread in the rbf phase
+    const int h = tt >> 7;                 // which half of the work this thread takes
     const int wq = warp & 3;               // TMEM lane quarter this warp may touch
     uint64_t* b1ready = &bars[1 + g * 5 + 0];
     uint64_t* d1ready = &bars[1 + g * 5 + 1];
@@ -151,33 +173,52 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
     uint64_t* d2ready = &bars[1 + g * 5 + 3];
     uint64_t* xbar = &bars[1 + g * 5 + 4];
     uint8_t* sB = smem + W1_BYTES + W2_BYTES + g * GROUP_BYTES;
-    float* sX = reinterpret_cast<float*>(sB + B2_BYTES);
-    int2* sMeta = reinterpret_cast<int2*>(sB + B2_BYTES + XP_BYTES);
-    float* sC = reinterpret_cast<float*>(sB + B2_BYTES + XP_BYTES + TILE_E * 8);
+    float* sX = reinterpret_cast<float*>(sB + OFF_X);
+    int2* sMeta = reinterpret_cast<int2*>(sB + OFF_META);
+    float* sC = reinterpret_cast<float*>(sB + OFF_C);
+    int* sRow = reinterpret_cast<int*>(sB + OFF_ROW);
     const uint32_t d1 = tmem_base + g * 256 + ((uint32_t)(wq * 32) << 16);
     const uint32_t d2 = d1 + 128;
     const int64_t u = (int64_t)blockIdx.x * NG + g;
     const int64_t t0 = u * T / U, t1 = (u + 1) * T / U;
-    const float coeff = p.coeff, cutoff = p.cutoff;
+    const float c2 = p.coeff_log2e, cutoff = p.cutoff;
     const int Ng = p.Ng;
+    const int chan = wq * 32 + lane;       // channel owned in the epilogues (TMEM lane)
 
     int staged_conf = -1;
     uint32_t xloads = 0;
     uint32_t it = 0;
+
+    // software prefetch of everything the next tile needs from global memory
+    TileInfo cur;
+    int pre_row = 0, pre_src = 0;
+    float pre_d = 0.0f;
+    if (t0 < t1) {
+      cur = load_tile(p.tiles, t0);
+      if (tt <= cur.row_end - cur.row_begin) pre_row = __ldg(p.rowptr + cur.row_begin + tt);
+      if (e < cur.ne) {
+        pre_d = __ldg(p.dist + cur.e0 + e);
+        pre_src = __ldg(p.col + cur.e0 + e);
+      }
+    }
+
     for (int64_t ti = t0; ti < t1; ++ti, ++it) {
-      const int4 tile = p.tiles[ti];
-      const int e0 = p.rowptr[tile.x];
-      const int ne = p.rowptr[tile.y] - e0;
+      const TileInfo tile = cur;
+      const bool have_next = ti + 1 < t1;
+      TileInfo nxt = tile;
+      if (have_next) nxt = load_tile(p.tiles, ti + 1);
+      const int ne = tile.ne;
       const int npad = (ne + 15) & ~15;
+      const int nrows = tile.row_end - tile.row_begin;
       const uint32_t par = it & 1;
-      const int cs = tile.z, cn = tile.w;
+      const int cs = tile.cs, cn = tile.cn;
       const bool staged = cn <= XP_CAP;
 
-      tc::named_bar_sync(1 + g, 128);  // previous tile of this group fully consumed (sB, sX, sMeta, TMEM)
+      tc::named_bar_sync(1 + g, GT);  // previous tile of this group fully consumed (sB, sX, sMeta, TMEM)
 
       bool x_wait = false;
       if (staged && cs != staged_conf) {
-        if (t == 0) {
+        if (tt == 0) {
           const uint32_t bytes = (uint32_t)cn * F * 4;
           tc::mbar_arrive_expect_tx(xbar, bytes);
           tc::bulk_g2s(sX, p.xprime + (int64_t)cs * F, bytes, xbar);
@@ -185,70 +226,84 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
         staged_conf = cs;
         x_wait = true;
       }
+      if (tt <= nrows) sRow[tt] = pre_row - tile.e0;
+      tc::named_bar_sync(1 + g, GT);
 
       // ---- per-edge metadata + Gaussian expansion -> B1 (K-major [edge, 64]) ----
-      for (int r = tile.x + t; r < tile.y; r += 128) {
-        const int b = p.rowptr[r] - e0, e = p.rowptr[r + 1] - e0;
-        for (int k = b; k < e; ++k) sMeta[k].y = (k == e - 1) ? r : -1;
-      }
-      if (t < npad) {
-        float d = 0.0f;
-        const bool live = t < ne;
-        if (live) {
-          d = p.dist[e0 + t];
-          const int src = p.col[e0 + t];
-          sMeta[t].x = staged ? (src - cs) : src;
-          sC[t] = 0.5f * (__cosf(d * kPi / cutoff) + 1.0f);
-        } else {
-          sMeta[t] = make_int2(0, -1);
-          sC[t] = 0.0f;
+      if (e < npad) {
+        const bool live = e < ne;
+        const float d = pre_d;
+        if (h == 0) {
+          if (live) {
+            int r = 0;
+            while (sRow[r + 1] <= e) ++r;
+            const bool last = (e + 1 == sRow[r + 1]);
+            sMeta[e] = make_int2(staged ? (pre_src - cs) : pre_src, last ? (tile.row_begin + r) : -1);
+            sC[e] = 0.5f * (__cosf(d * kPi / cutoff) + 1.0f);
+          } else {
+            sMeta[e] = make_int2(0, -1);
+            sC[e] = 0.0f;
+          }
         }
-        uint8_t* rowp = sB + (t >> 3) * B1_SBO + (t & 7) * 16;
-#pragma unroll
-        for (int jc = 0; jc < K1 / 8; ++jc) {
+        uint8_t* rowp = sB + (e >> 3) * B1_SBO + (e & 7) * 16;
+        const int jc0 = h * k1steps, jc1 = jc0 + k1steps;   // each half writes k1steps of the 2*k1steps chunks
+        for (int jc = jc0; jc < jc1; ++jc) {
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int k = jc * 8 + j;
-            float x = d - s_offset[k];
-            float rv = __expf(coeff * x * x);
+            const float x = d - s_offset[k];
+            const float rv = ex2_approx(c2 * x * x);
             v[j] = !live ? 0.0f : (k < Ng ? rv : (k == Ng ? 1.0f : 0.0f));
           }
-          uint4 q = make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
-                               tc::pack_bf16x2(v[6], v[7]));
-          *reinterpret_cast<uint4*>(rowp + jc * 128) = q;
+          *reinterpret_cast<uint4*>(rowp + jc * 128) =
+              make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
+                         tc::pack_bf16x2(v[6], v[7]));
         }
       }
       tc::fence_proxy_async();
       tc::mbar_arrive(b1ready);
 
+      // prefetch the next tile's global data while the tensor core and the epilogues run
+      if (have_next) {
+        if (tt <= nxt.row_end - nxt.row_begin) pre_row = __ldg(p.rowptr + nxt.row_begin + tt);
+        if (e < nxt.ne) {
+          pre_d = __ldg(p.dist + nxt.e0 + e);
+          pre_src = __ldg(p.col + nxt.e0 + e);
+        }
+      }
+      const int rsplit = (nrows + 1) >> 1;
+      const int esplit = sRow[rsplit];                     // rows [0, rsplit) -> half 0, the rest -> half 1
+      const int csplit = (((npad >> 4) + 1) >> 1) << 4;    // ep1 column split (multiple of 16)
+
       // ---- epilogue 1: a' = C * ssp(D1) -> B2 (MN-major [144, edge]) ----
       tc::mbar_wait(d1ready, par);
       tc::tc_fence_after();
       {
-        uint8_t* colp = sB + t * 16;  // k = t: (k/8)*128 + (k%8)*16 = k*16
-        for (int c0 = 0; c0 < npad; c0 += 16) {
+        uint8_t* colp = sB + chan * 16;  // k = chan: (k/8)*128 + (k%8)*16 = k*16
+        const int cb = h ? csplit : 0, ce = h ? npad : csplit;
+        for (int c0 = cb; c0 < ce; c0 += 16) {
           float v[16];
           tc::tmem_ld16(d1 + c0, v);
-          tc::tmem_wait_ld();
           const float4* cp = reinterpret_cast<const float4*>(sC + c0);
           float c[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float4 cc = cp[q];
+            const float4 cc = cp[q];
             c[q * 4 + 0] = cc.x; c[q * 4 + 1] = cc.y; c[q * 4 + 2] = cc.z; c[q * 4 + 3] = cc.w;
           }
+          tc::tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = ssp_fast(v[j]) * c[j];
-          uint4 q0 = make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
-                                tc::pack_bf16x2(v[6], v[7]));
-          uint4 q1 = make_uint4(tc::pack_bf16x2(v[8], v[9]), tc::pack_bf16x2(v[10], v[11]),
-                                tc::pack_bf16x2(v[12], v[13]), tc::pack_bf16x2(v[14], v[15]));
-          *reinterpret_cast<uint4*>(colp + (c0 >> 3) * A2_SBO) = q0;
-          *reinterpret_cast<uint4*>(colp + ((c0 >> 3) + 1) * A2_SBO) = q1;
+          *reinterpret_cast<uint4*>(colp + (c0 >> 3) * A2_SBO) =
+              make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
+                         tc::pack_bf16x2(v[6], v[7]));
+          *reinterpret_cast<uint4*>(colp + ((c0 >> 3) + 1) * A2_SBO) =
+              make_uint4(tc::pack_bf16x2(v[8], v[9]), tc::pack_bf16x2(v[10], v[11]), tc::pack_bf16x2(v[12], v[13]),
+                         tc::pack_bf16x2(v[14], v[15]));
         }
         // rows 128..143: row 128 = C_e (multiplies the b2 column of W2aug), rows 129..143 = 0
-        for (int item = t; item < (npad >> 3) * 16; item += 128) {
+        for (int item = tt; item < (npad >> 3) * 16; item += GT) {
           const int ec = item >> 4, kr = item & 15;
           uint4 q = make_uint4(0, 0, 0, 0);
           if (kr == 0) {
@@ -271,28 +326,63 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
         ++xloads;
       }
       {
-        const int f = wq * 32 + lane;
-        const float* xsrc = staged ? (sX + f) : (p.xprime + f);
+        const int lo = h ? esplit : 0, hi = h ? ne : esplit;
         float acc = 0.0f;
-        for (int c0 = 0; c0 < npad; c0 += 16) {
-          float v[16];
-          tc::tmem_ld16(d2 + c0, v);
-          tc::tmem_wait_ld();
+        float* aggc = p.agg + chan;
+        if (staged) {
+          const float* xs_base = sX + chan;
+          for (int c0 = lo & ~15; c0 < hi; c0 += 16) {
+            float v[16];
+            tc::tmem_ld16(d2 + c0, v);
+            int2 m[16];
+            float xs[16];
+            const int4* mp = reinterpret_cast<const int4*>(sMeta + c0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int e = c0 + j;
-            if (e < ne) {
-              const int2 m = sMeta[e];
-              acc = fmaf(v[j], xsrc[(int64_t)m.x * F], acc);
-              if (m.y >= 0) {
-                p.agg[(int64_t)m.y * F + f] = acc;
-                acc = 0.0f;
+            for (int q = 0; q < 8; ++q) {
+              const int4 mm = mp[q];
+              m[2 * q] = make_int2(mm.x, mm.y);
+              m[2 * q + 1] = make_int2(mm.z, mm.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xs[j] = xs_base[m[j].x * F];
+            tc::tmem_wait_ld();
+            const bool full = (c0 >= lo) && (c0 + 16 <= hi);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (full || (c0 + j >= lo && c0 + j < hi)) {
+                acc = fmaf(v[j], xs[j], acc);
+                if (m[j].y >= 0) {
+                  aggc[(int64_t)m[j].y * F] = acc;
+                  acc = 0.0f;
+                }
+              }
+            }
+          }
+        } else {
+          const float* xs_base = p.xprime + chan;
+          for (int c0 = lo & ~15; c0 < hi; c0 += 16) {
+            float v[16];
+            tc::tmem_ld16(d2 + c0, v);
+            float xs[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xs[j] = __ldg(xs_base + (int64_t)sMeta[c0 + j].x * F);
+            tc::tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (c0 + j >= lo && c0 + j < hi) {
+                acc = fmaf(v[j], xs[j], acc);
+                const int dst = sMeta[c0 + j].y;
+                if (dst >= 0) {
+                  aggc[(int64_t)dst * F] = acc;
+                  acc = 0.0f;
+                }
               }
             }
           }
         }
       }
       tc::tc_fence_before();
+      cur = nxt;
     }
   }
 
@@ -384,7 +474,7 @@ extern "C" int cmp_cfconv_fused_fwd(const float* xprime, const float* dist, cons
   p.weights = reinterpret_cast<const uint8_t*>(packed_weights);
   p.offset = offset;
   p.agg = agg;
-  p.coeff = coeff;
+  p.coeff_log2e = coeff * 1.4426950408889634f;
   p.cutoff = cutoff;
   p.Ng = num_gaussians;
   cfconv_fused_fwd_kernel<<<sm_count(), CTA_THREADS, SMEM_BYTES, st>>>(p);

@@ -266,6 +266,7 @@ __global__ void csr_to_edge_index_kernel(const int32_t* __restrict__ rowptr, con
 
 // ---- edge tiles: runs of whole target rows of ONE conformer holding <= tile_edges edges ----------
 // (the unit of work of the fused tensor-core kernels: a tile is one UMMA N-extent)
+// descriptor = 2 x int4: {first_row, end_row, conformer_first_atom, conformer_atoms}, {first_edge, num_edges, 0, 0}
 __device__ __forceinline__ int walk_tiles(const int32_t* __restrict__ rowptr, int s, int e, int tile_edges,
                                           int4* __restrict__ out, int* status) {
   int count = 0, first = s, cur = 0;
@@ -276,7 +277,10 @@ __device__ __forceinline__ int walk_tiles(const int32_t* __restrict__ rowptr, in
       d = 0;
     }
     if (cur + d > tile_edges && cur > 0) {
-      if (out) out[count] = make_int4(first, r, s, e - s);
+      if (out) {
+        out[2 * count] = make_int4(first, r, s, e - s);
+        out[2 * count + 1] = make_int4(rowptr[first], rowptr[r] - rowptr[first], 0, 0);
+      }
       ++count;
       first = r;
       cur = 0;
@@ -284,7 +288,10 @@ __device__ __forceinline__ int walk_tiles(const int32_t* __restrict__ rowptr, in
     cur += d;
   }
   if (cur > 0) {
-    if (out) out[count] = make_int4(first, e, s, e - s);
+    if (out) {
+      out[2 * count] = make_int4(first, e, s, e - s);
+      out[2 * count + 1] = make_int4(rowptr[first], rowptr[e] - rowptr[first], 0, 0);
+    }
     ++count;
   }
   return count;
@@ -307,7 +314,7 @@ __global__ void tiles_fill_kernel(const int32_t* __restrict__ rowptr, const int3
     if (g == 0) atomicOr(status, CMP_STATUS_EDGE_OVERFLOW);
     return;
   }
-  walk_tiles(rowptr, seg_ptr[g], seg_ptr[g + 1], tile_edges, tiles + tile_ptr[g], status);
+  walk_tiles(rowptr, seg_ptr[g], seg_ptr[g + 1], tile_edges, tiles + 2 * (int64_t)tile_ptr[g], status);
 }
 
 __global__ void gather_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,

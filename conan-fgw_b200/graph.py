@@ -78,7 +78,7 @@ class NeighborList:
         dev = rowptr.device
         tile_e = _lib.size_query("cmp_cfconv_tc_tile_edges")
         cap = self.cap_E // 64 + self.G + 1
-        tiles = torch.empty(max(cap, 1), 4, dtype=torch.int32, device=dev)
+        tiles = torch.empty(max(cap, 1), 8, dtype=torch.int32, device=dev)
         num = torch.zeros(1, dtype=torch.int32, device=dev)
         ws = _lib.workspace(_lib.size_query("cmp_build_tiles_workspace", self.G), dev)
         _lib.call("cmp_build_tiles", _lib.ptr(rowptr), _lib.ptr(self.seg_ptr), self.G, tile_e, _lib.ptr(tiles), cap,
@@ -86,7 +86,7 @@ class NeighborList:
         return tiles, num
 
     def tiles(self):
-        """(tiles int32[cap,4], num_tiles int32[1]) over the target-sorted CSR."""
+        """(tiles int32[cap,8], num_tiles int32[1]) over the target-sorted CSR."""
         if getattr(self, "_tiles", None) is None:
             if self.G == 0 and self.N > 0:
                 raise _lib.ConanMPError("edge tiles need conformer segments (graph was built from a raw edge_index)")

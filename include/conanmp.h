@@ -177,8 +177,9 @@ int cmp_segment_sum_bwd(const float* dout, const int32_t* seg_ptr, int64_t G, in
  * ------------------------------------------------------------------------- */
 
 /* Edge tiles = the work units of the fused kernels: runs of whole target rows of ONE conformer
- * holding <= tile_edges edges.  tiles is an int4 array {first_row, end_row, conformer_first_atom,
- * conformer_atom_count}; *num_tiles receives the count (device memory, no host sync).
+ * holding <= tile_edges edges.  tiles is an array of 8 x int32 descriptors {first_row, end_row,
+ * conformer_first_atom, conformer_atom_count, first_edge, num_edges, 0, 0}; *num_tiles receives the
+ * count (device memory, no host sync).
  * Works on either orientation of the CSR (rowptr or rowptr_t). */
 size_t cmp_build_tiles_workspace(int64_t G);
 int cmp_build_tiles(const int32_t* rowptr, const int32_t* seg_ptr, int64_t G, int tile_edges,

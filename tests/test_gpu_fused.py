@@ -43,8 +43,9 @@ def test_tiles_cover_every_edge_once():
         tl = tiles[:T].cpu()
         rp = nl.rowptr.cpu()
         covered = 0
-        for fr, er, cs, cn in tl.tolist():
+        for fr, er, cs, cn, e0, ne_d, _, _ in tl.tolist():
             ne = int(rp[er] - rp[fr])
+            assert e0 == int(rp[fr]) and ne_d == ne
             assert 0 < ne <= 128 and cs <= fr < er <= cs + cn
             covered += ne
         assert covered == nl.E
