@@ -53,6 +53,15 @@ SIGNATURES = {
     "cmp_cfconv_tc_pack_weights": (I, [P, P, P, P, I, I, P, P]),
     "cmp_cfconv_fused_fwd": (I, [P, P, P, P, P, P, P, P, I, F, F, L, I, P, P]),
     "cmp_debug_umma_gemm": (I, [P, L, P, L, P, I, I, I, I, I, I, I, I, I, I, I, P]),
+    "cmp_csr_expand_rows": (I, [P, L, P, P]),
+    "cmp_cfconv_tc_bwd_tile_edges": (I, []),
+    "cmp_build_flat_tiles_workspace": (S, [L]),
+    "cmp_build_flat_tiles": (I, [P, P, P, L, I, P, L, P, P, S, P, P]),
+    "cmp_f32_to_bf16": (I, [P, L, P, P]),
+    "cmp_cfconv_tc_bwd_weights_bytes": (S, []),
+    "cmp_cfconv_fused_bwd_workspace": (S, []),
+    "cmp_cfconv_tc_pack_bwd_weights": (I, [P, P, P, I, I, P, P]),
+    "cmp_cfconv_fused_bwd_weights": (I, [P, P, P, P, P, P, P, P, P, I, F, F, I, P, P, P, P, P, S, P]),
 }
 
 ACT_NONE, ACT_SSP, ACT_SILU = 0, 1, 2

@@ -105,6 +105,26 @@ class NeighborList:
             self._tiles_t = (tiles, num, dist_t)
         return self._tiles_t
 
+    def flat_tiles(self):
+        """(erow int32[cap_E], tiles int32[cap,8], num_tiles int32[1]): 64-edge chunks per conformer for the
+        fused weight-gradient kernel (edges are independent there, so no row alignment)."""
+        if getattr(self, "_flat_tiles", None) is None:
+            if self.G == 0 and self.N > 0:
+                raise _lib.ConanMPError("edge tiles need conformer segments (graph was built from a raw edge_index)")
+            dev = self.rowptr.device
+            erow = torch.empty_like(self.col)
+            _lib.call("cmp_csr_expand_rows", _lib.ptr(self.rowptr), self.N, _lib.ptr(erow))
+            tile_e = _lib.size_query("cmp_cfconv_tc_bwd_tile_edges")
+            cap = self.cap_E // tile_e + self.G + 1
+            tiles = torch.empty(max(cap, 1), 8, dtype=torch.int32, device=dev)
+            num = torch.zeros(1, dtype=torch.int32, device=dev)
+            ws = _lib.workspace(_lib.size_query("cmp_build_flat_tiles_workspace", self.G), dev)
+            _lib.call("cmp_build_flat_tiles", _lib.ptr(self.conf_edge_ptr), _lib.ptr(self.seg_ptr), _lib.ptr(erow),
+                      self.G, tile_e, _lib.ptr(tiles), cap, _lib.ptr(num), _lib.ptr(ws), ws.numel(),
+                      _lib.ptr(self.status))
+            self._flat_tiles = (erow, tiles, num)
+        return self._flat_tiles
+
     def edge_weight(self) -> torch.Tensor:
         w = self.dist[: self.E]
         w._cmp_graph = self

@@ -266,16 +266,45 @@ class _CFConvFusedFn(Function):
                                    ctx.cutoff, e_hint)
         grads = [None, None, None, None]
         if any(ctx.needs_input_grad[1:5]):
-            E = graph.E
-            dfilt = torch.empty(E, F, dtype=torch.float32, device=g.device)
-            call("cmp_cfconv_message_bwd", ptr(g), ptr(xprime), None, ptr(graph.dist), ptr(graph.rowptr),
-                 ptr(graph.col), None, None, None, N, F, ctx.cutoff, ptr(dfilt), None)
-            with torch.enable_grad():
-                ps = [t.detach().requires_grad_(True) for t in (W1, b1, W2, b2)]
-                rbf = gaussian_rbf(graph.dist[:E], offset, ctx.coeff)
-                filt = linear(linear(rbf, ps[0], ps[1], ACT_SSP), ps[2], ps[3])
-                grads = list(torch.autograd.grad(filt, ps, dfilt))
+            if FUSED_WEIGHT_GRADS:
+                grads = list(_fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, ctx.coeff, ctx.cutoff))
+            else:   # exact-fp32 recompute of the filter MLP (kept for cross-checking the fused kernel)
+                E = graph.E
+                dfilt = torch.empty(E, F, dtype=torch.float32, device=g.device)
+                call("cmp_cfconv_message_bwd", ptr(g), ptr(xprime), None, ptr(graph.dist), ptr(graph.rowptr),
+                     ptr(graph.col), None, None, None, N, F, ctx.cutoff, ptr(dfilt), None)
+                with torch.enable_grad():
+                    ps = [t.detach().requires_grad_(True) for t in (W1, b1, W2, b2)]
+                    rbf = gaussian_rbf(graph.dist[:E], offset, ctx.coeff)
+                    filt = linear(linear(rbf, ps[0], ps[1], ACT_SSP), ps[2], ps[3])
+                    grads = list(torch.autograd.grad(filt, ps, dfilt))
         return (dx, *grads, None, None, None, None)
+
+
+FUSED_WEIGHT_GRADS = True
+
+
+def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff):
+    """dW1, db1, dW2, db2 of the filter MLP through cmp_cfconv_fused_bwd_weights (tcgen05, K = edges)."""
+    N, F = xprime.shape
+    Ng = offset.numel()
+    dev = g.device
+    xb = torch.empty(N, F, dtype=torch.bfloat16, device=dev)
+    call("cmp_f32_to_bf16", ptr(xprime), N * F, ptr(xb))
+    packed = torch.empty(_lib.size_query("cmp_cfconv_tc_bwd_weights_bytes"), dtype=torch.uint8, device=dev)
+    call("cmp_cfconv_tc_pack_bwd_weights", ptr(_f32c(W1)), ptr(_f32c(b1)), ptr(_f32c(W2)), F, Ng, ptr(packed))
+    erow, tiles, num = graph.flat_tiles()
+    dW1 = torch.empty(F, Ng, dtype=torch.float32, device=dev)
+    db1 = torch.empty(F, dtype=torch.float32, device=dev)
+    dW2 = torch.empty(F, F, dtype=torch.float32, device=dev)
+    db2 = torch.empty(F, dtype=torch.float32, device=dev)
+    ws = _lib.workspace(_lib.size_query("cmp_cfconv_fused_bwd_workspace"), dev)
+    e_hint = graph._E if graph._E is not None else graph.cap_E
+    # algorithmic FLOPs (SURVEY.md 8d): the weight-gradient half of "bwd = 2 x fwd" = 2*(Ng*F + F*F) per edge
+    call("cmp_cfconv_fused_bwd_weights", ptr(g), ptr(xb), ptr(graph.dist), ptr(graph.col), ptr(erow), ptr(tiles),
+         ptr(num), ptr(packed), ptr(offset), Ng, float(coeff), float(cutoff), F, ptr(dW1), ptr(db1), ptr(dW2),
+         ptr(db2), ptr(ws), ws.numel(), work=2.0 * (Ng * F + F * F) * float(e_hint))
+    return dW1, db1, dW2, db2
 
 
 def cfconv_fused(xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff):

@@ -209,6 +209,33 @@ int cmp_cfconv_fused_fwd(const float* xprime, const float* dist, const int32_t* 
                          float coeff, float cutoff, int64_t N, int num_filters, float* agg,
                          cmp_stream_t stream);
 
+/* Filter-MLP weight gradients of the fused CFConv in ONE kernel (+ a fixed-order reduction of the
+ * per-pipeline partial sums): recomputes rbf / hidden / a' per 64-edge tile on chip and accumulates
+ * dW2 = sum_e dF_e a'_e^T and dW1 = sum_e dh_e rbf_e^T in TMEM (tcgen05, bf16 operands, fp32
+ * accumulate).  g = dL/dagg [N,F]; xprime_bf16 = bf16 copy of x' [N,F]; erow = target row per edge;
+ * flat_tiles from cmp_build_flat_tiles.  Replaces autograd through CFConv.nn (PyG) - the GEMMs with
+ * K = E that dominate the reference's backward pass.  d x' is cmp_cfconv_fused_fwd over the
+ * transposed neighbour list with g as its input. */
+int cmp_csr_expand_rows(const int32_t* rowptr, int64_t N, int32_t* erow, cmp_stream_t stream);
+int cmp_cfconv_tc_bwd_tile_edges(void);
+size_t cmp_build_flat_tiles_workspace(int64_t G);
+int cmp_build_flat_tiles(const int32_t* conf_edge_ptr, const int32_t* seg_ptr, const int32_t* erow,
+                         int64_t G, int tile_edges, void* tiles, int64_t cap_tiles,
+                         int32_t* num_tiles, void* workspace, size_t workspace_bytes, int* status,
+                         cmp_stream_t stream);
+int cmp_f32_to_bf16(const float* src, int64_t n, void* dst, cmp_stream_t stream);
+size_t cmp_cfconv_tc_bwd_weights_bytes(void);
+size_t cmp_cfconv_fused_bwd_workspace(void);
+int cmp_cfconv_tc_pack_bwd_weights(const float* W1, const float* b1, const float* W2,
+                                   int num_filters, int num_gaussians, void* packed,
+                                   cmp_stream_t stream);
+int cmp_cfconv_fused_bwd_weights(const float* g, const void* xprime_bf16, const float* dist,
+                                 const int32_t* col, const int32_t* erow, const void* flat_tiles,
+                                 const int32_t* num_tiles, const void* packed_bwd_weights,
+                                 const float* offset, int num_gaussians, float coeff, float cutoff,
+                                 int num_filters, float* dW1, float* db1, float* dW2, float* db2,
+                                 void* workspace, size_t workspace_bytes, cmp_stream_t stream);
+
 /* Single-tile UMMA probe used by the tests to pin descriptor / TMEM conventions. */
 int cmp_debug_umma_gemm(const void* a_img, int64_t a_bytes, const void* b_img, int64_t b_bytes,
                         float* D, int N, int K, int fmt, int a_mn, int b_mn, int a_lbo, int a_sbo,

@@ -113,3 +113,43 @@ def test_module_api_picks_fused_kernel():
     out = c.readout(c.act(c.lin2(c.lin1(h))), batch, dim=0)
     assert rel_err(out, o(b.z, b.pos, b.batch)) < TOL_BF16
     assert cmp._lib.launches() - before < 40
+
+
+@pytest.mark.parametrize("n,B", [(27, 8), (65, 2), (9, 4)])
+def test_fused_weight_gradients_match_exact_recompute(n, B):
+    """cmp_cfconv_fused_bwd_weights (TMEM-accumulated dW) vs the exact-fp32 recompute path."""
+    _need_sm100()
+    torch.manual_seed(n)
+    b = syn.make_batch(B, 3, n, seed=n + 1).to(DEV)
+    nl = cmp.build_neighbor_list(b.pos, b.batch, 10.0)
+    F, Ng = 128, 50
+    blk = cmp.InteractionBlock(128, Ng, F, 10.0).to(DEV)
+    with torch.no_grad():
+        blk.mlp[0].bias.add_(0.1 * torch.randn(F, device=DEV))
+        blk.mlp[2].bias.add_(0.1 * torch.randn(F, device=DEV))
+    gs = cmp.GaussianSmearing(0.0, 10.0, Ng).to(DEV)
+    xp = torch.randn(b.z.numel(), F, device=DEV, requires_grad=True)
+    go = torch.randn(b.z.numel(), F, device=DEV)
+    params = [blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight, blk.mlp[2].bias]
+    res = {}
+    for fused in (False, True):
+        ops.FUSED_WEIGHT_GRADS = fused
+        try:
+            out = ops.cfconv_fused(xp, *params, nl, gs.offset, gs.coeff, 10.0)
+            res[fused] = torch.autograd.grad(out, [xp] + params, go)
+        finally:
+            ops.FUSED_WEIGHT_GRADS = True
+    names = ["dx'", "dW1", "db1", "dW2", "db2"]
+    for name, a, r in zip(names, res[True], res[False]):
+        assert rel_err(a, r) < 1e-2, name
+    # and the exact (non-fused forward) autograd as ground truth
+    rbf = gs(nl.edge_weight())
+    out_ref = ops.cfconv_message(xp, blk.conv.filter(rbf), nl, 10.0)
+    ref = torch.autograd.grad(out_ref, [xp] + params, go)
+    for name, a, r in zip(names, res[True], ref):
+        assert rel_err(a, r) < 2e-2, name
+    # deterministic
+    out = ops.cfconv_fused(xp, *params, nl, gs.offset, gs.coeff, 10.0)
+    again = torch.autograd.grad(out, [xp] + params, go)
+    for a, r in zip(again, res[True]):
+        assert torch.equal(a, r)
