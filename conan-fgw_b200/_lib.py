@@ -53,6 +53,12 @@ SIGNATURES = {
     "cmp_cfconv_tc_pack_weights": (I, [P, P, P, P, I, I, P, P]),
     "cmp_cfconv_fused_fwd": (I, [P, P, P, P, P, P, P, P, I, F, F, L, I, P, P]),
     "cmp_debug_umma_gemm": (I, [P, L, P, L, P, I, I, I, I, I, I, I, I, I, I, I, P]),
+    "cmp_node_gemm_tc_supported": (I, [I, I]),
+    "cmp_node_gemm_weight_bytes": (S, [I]),
+    "cmp_node_gemm_pack_weight": (I, [P, I, I, I, P, P]),
+    "cmp_node_gemm_fwd": (I, [P, L, P, L, P, P, I, P, L, P, L, L, I, I, P]),
+    "cmp_node_gemm_dw_workspace": (S, [I]),
+    "cmp_node_gemm_dw": (I, [P, L, P, L, P, L, L, I, I, P, P, P, S, P]),
     "cmp_csr_expand_rows": (I, [P, L, P, P]),
     "cmp_cfconv_tc_bwd_tile_edges": (I, []),
     "cmp_build_flat_tiles_workspace": (S, [L]),

@@ -1,0 +1,404 @@
+// Node-level linears on tcgen05 with split-bf16 operands (hi + lo, three MMA passes: hi*hi + hi*lo +
+// lo*hi, fp32 accumulation in TMEM), i.e. ~16 mantissa bits per operand: the node features stay
+// fp32-grade while the GEMMs run on the tensor pipe.  Replaces the torch.nn.Linear calls around the
+// message passing (PyG CFConv.lin1/lin2, InteractionBlock.lin, ConAN heads sns.py:177-179,225-231)
+// and their autograd GEMMs in the bf16 mode; the exact-fp32 mode keeps cmp_gemm_f32.
+//
+//   forward / dX:  Y[M, Nout] = act(X'[M, K] * W[Nout, K]^T + b) + R      (dX: W := W^T image)
+//                  orientation D[out channel (TMEM lane), atom (column)] so the epilogue thread that
+//                  owns a channel writes coalesced rows and holds its bias in a register;
+//   dW / db:       D[Nout, K (+ ones column)] += dY'^T X over 128-atom tiles (K of the MMA = atoms), both
+//                  operand images are re-read as MN-major views (LBO/SBO exchanged), per-CTA partial sums
+//                  are reduced in a fixed order.
+//   X' / dY' = input * (1 - exp(-y)/2) when saved_y is given: the ShiftedSoftplus backward fused into the
+//   operand load.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cmp {
+namespace {
+
+constexpr int TM = 128;            // atoms per tile
+constexpr int CW = 8;              // compute warps
+constexpr int NT = CW * 32 + 32;   // + 1 MMA warp
+constexpr int MAXC = 128;          // max channels (K or Nout)
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// fp32 tile [TM atoms, C channels] -> bf16 hi / lo K-major images (rows = atoms):
+//   byte(a, c) = (a%8)*16 + (c%8)*2 + (a/8)*sbo + (c/8)*128
+// when ones_chunk >= 0 that 16-byte chunk of every row is set to {1, 0, 0, ...} (hi) / 0 (lo).
+__device__ __forceinline__ void convert_tile(const float* __restrict__ X, int64_t ld, const float* __restrict__ Ysaved,
+                                             int64_t ldys, int64_t m0, int64_t M, int C, uint32_t sbo, uint8_t* hi,
+                                             uint8_t* lo, int ones_chunk, int warp, int lane) {
+  const int nchunk = C >> 3;
+  const int cbs = (nchunk + 3) >> 2;
+  const int al = lane & 7, cl = lane >> 3;
+  for (int wi = warp; wi < 16 * cbs; wi += CW) {
+    const int ab = wi / cbs, cb = wi - ab * cbs;
+    const int a = ab * 8 + al, chunk = cb * 4 + cl;
+    if (chunk >= nchunk) continue;
+    float v[8];
+    const int64_t row = m0 + a;
+    if (row < M) {
+      const float4* src = reinterpret_cast<const float4*>(X + row * ld + chunk * 8);
+      const float4 p0 = __ldg(src), p1 = __ldg(src + 1);
+      v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+      if (Ysaved) {
+        const float4* ys = reinterpret_cast<const float4*>(Ysaved + row * ldys + chunk * 8);
+        const float4 y0 = __ldg(ys), y1 = __ldg(ys + 1);
+        const float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= 1.0f - 0.5f * ex2_approx(-1.4426950408889634f * y[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    }
+    float l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float h = __bfloat162float(__float2bfloat16_rn(v[j]));
+      l[j] = v[j] - h;
+      v[j] = h;
+    }
+    const uint32_t off = (a & 7) * 16 + (a >> 3) * sbo + chunk * 128;
+    *reinterpret_cast<uint4*>(hi + off) = make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]),
+                                                      tc::pack_bf16x2(v[4], v[5]), tc::pack_bf16x2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(lo + off) = make_uint4(tc::pack_bf16x2(l[0], l[1]), tc::pack_bf16x2(l[2], l[3]),
+                                                      tc::pack_bf16x2(l[4], l[5]), tc::pack_bf16x2(l[6], l[7]));
+  }
+  if (ones_chunk >= 0) {
+    // two extra chunks (16 channels): chunk ones_chunk = {1,0,...}, ones_chunk + 1 = 0
+    const int t = warp * 32 + lane;
+    for (int item = t; item < TM * 2; item += CW * 32) {
+      const int a = item >> 1, which = item & 1;
+      const uint32_t off = (a & 7) * 16 + (a >> 3) * sbo + (ones_chunk + which) * 128;
+      const bool live = (m0 + a) < M && which == 0;
+      *reinterpret_cast<uint4*>(hi + off) = make_uint4(live ? 0x00003F80u : 0u, 0u, 0u, 0u);   // bf16(1.0) = 0x3F80
+      *reinterpret_cast<uint4*>(lo + off) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
+
+struct FwdParams {
+  const float* X;
+  int64_t ldx;
+  const float* saved_y;   // optional, same shape as X
+  int64_t ldys;
+  const uint8_t* w_img;   // hi image | lo image, each TM*K*2 bytes (rows = Nout padded to 128)
+  const float* bias;
+  const float* residual;
+  int64_t ldr;
+  float* Y;
+  int64_t ldy;
+  int64_t M;
+  int K, Nout, act;
+};
+
+__global__ void __launch_bounds__(NT, 1) node_gemm_fwd_kernel(const FwdParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bars[3];   // wbar, xready, dready
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.K;
+  const uint32_t img_bytes = TM * K * 2;
+  const uint32_t sbo = (K >> 3) * 128;
+  uint8_t* sWh = smem;
+  uint8_t* sWl = smem + img_bytes;
+  uint8_t* sXh = smem + 2 * img_bytes;
+  uint8_t* sXl = smem + 3 * img_bytes;
+
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], CW * 32);
+    tc::mbar_init(&bars[2], 1);
+    tc::mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int64_t ntiles = (p.M + TM - 1) / TM;
+
+  if (warp == CW) {
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(&bars[0], 2 * img_bytes);
+      tc::bulk_g2s(sWh, p.w_img, 2 * img_bytes, &bars[0]);
+      tc::mbar_wait(&bars[0], 0);
+      const uint32_t aWh = tc::smem_u32(sWh), aWl = tc::smem_u32(sWl), aXh = tc::smem_u32(sXh), aXl = tc::smem_u32(sXl);
+      const uint32_t idesc = tc::umma_idesc_f16(128, TM, 1, 0, 0);
+      uint32_t it = 0;
+      for (int64_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
+        tc::mbar_wait(&bars[1], it & 1);
+        tc::tc_fence_after();
+        const int ks_n = K >> 4;
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a = (pass == 2) ? aWl : aWh;
+          const uint32_t b = (pass == 1) ? aXl : aXh;
+          for (int ks = 0; ks < ks_n; ++ks)
+            tc::umma_f16(tmem_base, tc::umma_smem_desc(a + ks * 256, 128, sbo), tc::umma_smem_desc(b + ks * 256, 128, sbo),
+                         idesc, (pass | ks) != 0);
+        }
+        tc::umma_commit(&bars[2]);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int wq = warp & 3, h = warp >> 2;
+    const int chan = wq * 32 + lane;
+    const float bias = (p.bias && chan < p.Nout) ? p.bias[chan] : 0.0f;
+    const uint32_t tD = tmem_base + ((uint32_t)(wq * 32) << 16);
+    uint32_t it = 0;
+    for (int64_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
+      const int64_t m0 = ti * TM;
+      if (it > 0) tc::named_bar_sync(1, CW * 32);   // everyone finished reading TMEM / previous images consumed
+      convert_tile(p.X, p.ldx, p.saved_y, p.ldys, m0, p.M, K, sbo, sXh, sXl, -1, warp, lane);
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&bars[1]);
+      tc::mbar_wait(&bars[2], it & 1);
+      tc::tc_fence_after();
+      for (int c0 = h * 64; c0 < h * 64 + 64; c0 += 16) {
+        if (m0 + c0 >= p.M) break;
+        float v[16];
+        tc::tmem_ld16(tD + c0, v);
+        tc::tmem_wait_ld();
+        if (chan < p.Nout) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int64_t row = m0 + c0 + j;
+            if (row < p.M) {
+              float y = apply_act(v[j] + bias, p.act);
+              if (p.residual) y += p.residual[row * p.ldr + chan];
+              p.Y[row * p.ldy + chan] = y;
+            }
+          }
+        }
+      }
+      tc::tc_fence_before();
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 128);
+}
+
+struct DwParams {
+  const float* dY;      // [M, Nout]
+  int64_t lddy;
+  const float* saved_y; // optional [M, Nout]
+  int64_t ldys;
+  const float* X;       // [M, K]
+  int64_t ldx;
+  float* partial;       // [gridDim.x][128][K + 16]
+  int64_t M;
+  int K, Nout;
+};
+
+__global__ void __launch_bounds__(NT, 1) node_gemm_dw_kernel(const DwParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bars[2];   // ready (images written), done (MMAs finished)
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.K, Nout = p.Nout;
+  const int KX = K + 16;                             // + ones column block (bias gradient)
+  const uint32_t sbo_y = (Nout >> 3) * 128, sbo_x = (KX >> 3) * 128;
+  const uint32_t y_bytes = 16 * sbo_y + 2048, x_bytes = 16 * sbo_x;   // slack: M = 128 view of a 64-channel image
+  uint8_t* sYh = smem;
+  uint8_t* sYl = sYh + y_bytes;
+  uint8_t* sXh = sYl + y_bytes;
+  uint8_t* sXl = sXh + x_bytes;
+
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], CW * 32);
+    tc::mbar_init(&bars[1], 1);
+    tc::mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int64_t ntiles = (p.M + TM - 1) / TM;
+  // contiguous tile range per CTA
+  const int64_t t0 = (int64_t)blockIdx.x * ntiles / gridDim.x, t1 = (int64_t)(blockIdx.x + 1) * ntiles / gridDim.x;
+
+  if (warp == CW) {
+    if (lane == 0) {
+      const uint32_t aYh = tc::smem_u32(sYh), aYl = tc::smem_u32(sYl), aXh = tc::smem_u32(sXh), aXl = tc::smem_u32(sXl);
+      const uint32_t idesc = tc::umma_idesc_f16(128, KX, 1, 1, 1);
+      uint32_t it = 0;
+      for (int64_t ti = t0; ti < t1; ++ti, ++it) {
+        tc::mbar_wait(&bars[0], it & 1);
+        tc::tc_fence_after();
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a = (pass == 2) ? aYl : aYh;
+          const uint32_t b = (pass == 1) ? aXl : aXh;
+          for (int ks = 0; ks < TM / 16; ++ks)
+            // MN-major views: LBO = stride between 8-atom groups, SBO = stride between 8-channel groups
+            tc::umma_f16(tmem_base, tc::umma_smem_desc(a + ks * 2 * sbo_y, sbo_y, 128),
+                         tc::umma_smem_desc(b + ks * 2 * sbo_x, sbo_x, 128), idesc, (it | pass | ks) != 0);
+        }
+        tc::umma_commit(&bars[1]);
+      }
+    }
+    __syncwarp();
+  } else {
+    uint32_t it = 0;
+    for (int64_t ti = t0; ti < t1; ++ti, ++it) {
+      const int64_t m0 = ti * TM;
+      if (it > 0) tc::mbar_wait(&bars[1], (it - 1) & 1);   // previous MMAs done reading the images
+      convert_tile(p.dY, p.lddy, p.saved_y, p.ldys, m0, p.M, Nout, sbo_y, sYh, sYl, -1, warp, lane);
+      convert_tile(p.X, p.ldx, nullptr, 0, m0, p.M, K, sbo_x, sXh, sXl, K >> 3, warp, lane);
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&bars[0]);
+    }
+    const int wq = warp & 3, h = warp >> 2;
+    const int chan = wq * 32 + lane;
+    const uint32_t tD = tmem_base + ((uint32_t)(wq * 32) << 16);
+    float* part = p.partial + (int64_t)blockIdx.x * 128 * KX;
+    const bool any = t0 < t1;
+    if (any) {
+      tc::mbar_wait(&bars[1], (it - 1) & 1);
+      tc::tc_fence_after();
+    }
+    // columns [0, KX) split between the two warp halves in 16-column blocks
+    const int nblk = KX >> 4;
+    for (int blk = h; blk < nblk; blk += 2) {
+      float v[16];
+      if (any) {
+        tc::tmem_ld16(tD + blk * 16, v);
+        tc::tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(part + chan * KX + blk * 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+}
+
+__global__ void node_dw_reduce_kernel(const float* __restrict__ partial, int P, int K, int Nout, float* __restrict__ dW,
+                                      float* __restrict__ db) {
+  const int KX = K + 16;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over Nout * (K + 1)
+  if (i >= Nout * (K + 1)) return;
+  const int n = i / (K + 1), k = i % (K + 1);
+  float s = 0.0f;
+  for (int c = 0; c < P; ++c) s += partial[((int64_t)c * 128 + n) * KX + k];
+  if (k < K) dW[n * K + k] = s;
+  else if (db) db[n] = s;
+}
+
+// W[rows, cols] (ld) fp32 -> hi | lo K-major images with 128 rows (zero padded): rows = MMA M.
+// transpose = 1 packs W^T (rows of the image = columns of W).
+__global__ void node_pack_weight_kernel(const float* __restrict__ W, int rows, int cols, int transpose,
+                                        uint8_t* __restrict__ out) {
+  const int R = transpose ? cols : rows;   // image rows that carry data
+  const int C = transpose ? rows : cols;   // image K extent
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128 * C) return;
+  const int r = idx / C, c = idx % C;
+  float v = 0.0f;
+  if (r < R) v = transpose ? W[c * cols + r] : W[r * cols + c];
+  const float h = __bfloat162float(__float2bfloat16_rn(v));
+  const uint32_t off = (r & 7) * 16 + (c & 7) * 2 + (r >> 3) * ((C >> 3) * 128) + (c >> 3) * 128;
+  *reinterpret_cast<__nv_bfloat16*>(out + off) = __float2bfloat16_rn(h);
+  *reinterpret_cast<__nv_bfloat16*>(out + 128 * C * 2 + off) = __float2bfloat16_rn(v - h);
+}
+
+bool dims_ok(int K, int Nout) {
+  return K >= 16 && K <= MAXC && K % 16 == 0 && Nout >= 16 && Nout <= MAXC && Nout % 16 == 0;
+}
+
+}  // namespace
+}  // namespace cmp
+
+using namespace cmp;
+
+extern "C" int cmp_node_gemm_tc_supported(int K, int Nout) { return dims_ok(K, Nout) ? 1 : 0; }
+
+extern "C" size_t cmp_node_gemm_weight_bytes(int image_K) { return (size_t)2 * 128 * image_K * 2; }
+
+extern "C" int cmp_node_gemm_pack_weight(const float* W, int rows, int cols, int transpose, void* packed,
+                                         cmp_stream_t stream) {
+  CMP_REQUIRE(W && packed, CMP_EINVAL, "cmp_node_gemm_pack_weight: null pointer");
+  CMP_REQUIRE(dims_ok(cols, rows), CMP_EUNSUPPORTED, "cmp_node_gemm_pack_weight: dims must be multiples of 16 in [16,128]");
+  const int C = transpose ? rows : cols;
+  node_pack_weight_kernel<<<(128 * C + 255) / 256, 256, 0, as_stream(stream)>>>(W, rows, cols, transpose,
+                                                                                reinterpret_cast<uint8_t*>(packed));
+  CMP_LAUNCH_CHECK("cmp_node_gemm_pack_weight");
+  return CMP_OK;
+}
+
+extern "C" int cmp_node_gemm_fwd(const float* X, int64_t ldx, const float* saved_y, int64_t ldys, const void* w_img,
+                                 const float* bias, int act, const float* residual, int64_t ldr, float* Y, int64_t ldy,
+                                 int64_t M, int K, int Nout, cmp_stream_t stream) {
+  CMP_REQUIRE(M >= 0, CMP_EINVAL, "cmp_node_gemm_fwd: negative size");
+  if (M == 0) return CMP_OK;
+  CMP_REQUIRE(dims_ok(K, Nout), CMP_EUNSUPPORTED, "cmp_node_gemm_fwd: K / Nout must be multiples of 16 in [16,128]");
+  CMP_REQUIRE(X && w_img && Y, CMP_EINVAL, "cmp_node_gemm_fwd: null pointer");
+  CMP_REQUIRE(ldx % 4 == 0 && (uintptr_t)X % 16 == 0 && (uintptr_t)w_img % 16 == 0 &&
+                  (!saved_y || (ldys % 4 == 0 && (uintptr_t)saved_y % 16 == 0)),
+              CMP_EINVAL, "cmp_node_gemm_fwd: operands must be 16-byte aligned with ld % 4 == 0");
+  CMP_REQUIRE(act == CMP_ACT_NONE || act == CMP_ACT_SSP || act == CMP_ACT_SILU, CMP_EINVAL, "cmp_node_gemm_fwd: bad act");
+  CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED, "cmp_node_gemm_fwd: needs an sm_100 device (tcgen05)");
+  const size_t smem = (size_t)4 * TM * K * 2;
+  if (cudaFuncSetAttribute(node_gemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TM * MAXC * 2) !=
+      cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("cmp_node_gemm_fwd: cannot opt in to shared memory");
+    return CMP_ECUDA;
+  }
+  FwdParams p{X, ldx, saved_y, ldys, reinterpret_cast<const uint8_t*>(w_img), bias, residual, ldr, Y, ldy, M, K, Nout, act};
+  const int64_t ntiles = ceil_div(M, TM);
+  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  node_gemm_fwd_kernel<<<grid, NT, smem, as_stream(stream)>>>(p);
+  CMP_LAUNCH_CHECK("cmp_node_gemm_fwd");
+  return CMP_OK;
+}
+
+extern "C" size_t cmp_node_gemm_dw_workspace(int K) { return align_up((size_t)sm_count() * 128 * (K + 16) * sizeof(float), 256); }
+
+extern "C" int cmp_node_gemm_dw(const float* dY, int64_t lddy, const float* saved_y, int64_t ldys, const float* X,
+                                int64_t ldx, int64_t M, int K, int Nout, float* dW, float* db, void* workspace,
+                                size_t workspace_bytes, cmp_stream_t stream) {
+  CMP_REQUIRE(M >= 0, CMP_EINVAL, "cmp_node_gemm_dw: negative size");
+  CMP_REQUIRE(dims_ok(K, Nout), CMP_EUNSUPPORTED, "cmp_node_gemm_dw: K / Nout must be multiples of 16 in [16,128]");
+  CMP_REQUIRE(dW && (M == 0 || (dY && X)), CMP_EINVAL, "cmp_node_gemm_dw: null pointer");
+  CMP_REQUIRE(lddy % 4 == 0 && ldx % 4 == 0 && (uintptr_t)dY % 16 == 0 && (uintptr_t)X % 16 == 0 &&
+                  (!saved_y || (ldys % 4 == 0 && (uintptr_t)saved_y % 16 == 0)),
+              CMP_EINVAL, "cmp_node_gemm_dw: operands must be 16-byte aligned with ld % 4 == 0");
+  CMP_REQUIRE(workspace && workspace_bytes >= cmp_node_gemm_dw_workspace(K), CMP_EWORKSPACE,
+              "cmp_node_gemm_dw: workspace too small");
+  CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED, "cmp_node_gemm_dw: needs an sm_100 device (tcgen05)");
+  const int KX = K + 16;
+  const size_t smem = (size_t)2 * (16 * (Nout / 8) * 128 + 2048) + (size_t)2 * 16 * (KX / 8) * 128;
+  if (cudaFuncSetAttribute(node_gemm_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           2 * (16 * (MAXC / 8) * 128 + 2048) + 2 * 16 * ((MAXC + 16) / 8) * 128) != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("cmp_node_gemm_dw: cannot opt in to shared memory");
+    return CMP_ECUDA;
+  }
+  DwParams p{dY, lddy, saved_y, ldys, X, ldx, reinterpret_cast<float*>(workspace), M, K, Nout};
+  const int64_t ntiles = ceil_div(M, TM);
+  int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  if (grid < 1) grid = 1;
+  node_gemm_dw_kernel<<<grid, NT, smem, as_stream(stream)>>>(p);
+  CMP_LAUNCH_CHECK("cmp_node_gemm_dw");
+  node_dw_reduce_kernel<<<(Nout * (K + 1) + 255) / 256, 256, 0, as_stream(stream)>>>(p.partial, grid, K, Nout, dW, db);
+  CMP_LAUNCH_CHECK("cmp_node_gemm_dw(reduce)");
+  return CMP_OK;
+}

@@ -69,8 +69,8 @@ __global__ void embedding_bwd_stage2(const float* __restrict__ partial, int chun
 }
 
 int embedding_chunk(int64_t N) {
-  int64_t c = ceil_div(N, 512);
-  return (int)(c < 1024 ? 1024 : c);
+  int64_t c = ceil_div(N, 1024);   // at most 1024 chunks; short chunks keep the sequential loops short
+  return (int)(c < 128 ? 128 : c);
 }
 
 // One warp per target row; lanes stride the channel axis (float4 when F % 4 == 0).

@@ -24,8 +24,10 @@ from .graph import NeighborList, build_neighbor_list, graph_from_edge_index, rad
 class Linear(nn.Linear):
     """``torch.nn.Linear`` parameters and init, forward through ``cmp_gemm_f32``."""
 
+    tc = False   # True (set by SchNet.set_precision("bf16")): split-bf16 tcgen05 node GEMMs
+
     def forward(self, x, act=_lib.ACT_NONE, residual=None):
-        return ops.linear(x, self.weight, self.bias, act, residual)
+        return ops.linear(x, self.weight, self.bias, act, residual, tc=self.tc)
 
 
 class Embedding(nn.Embedding):
@@ -228,6 +230,8 @@ class SchNet(nn.Module):
         for m in self.modules():
             if isinstance(m, CFConv):
                 m.precision = precision
+            if isinstance(m, Linear):
+                m.tc = precision == "bf16"
         return self
 
     def reset_parameters(self):

@@ -104,8 +104,74 @@ class _LinearFn(Function):
         return dx, dw, db, None, dres
 
 
-def linear(x, weight, bias=None, act=ACT_NONE, residual=None):
+def linear(x, weight, bias=None, act=ACT_NONE, residual=None, tc=False):
+    """``tc=True``: split-bf16 tcgen05 kernels (bf16 mode); else the exact-fp32 SIMT GEMM."""
+    if tc and node_tc_supported(weight.shape[1], weight.shape[0]):
+        return _LinearTCFn.apply(x, weight, bias, act, residual)
     return _LinearFn.apply(x, weight, bias, act, residual)
+
+
+def node_tc_supported(K, Nout) -> bool:
+    return bool(_lib.lib().cmp_node_gemm_tc_supported(int(K), int(Nout))) and bool(_lib.lib().cmp_device_is_sm100())
+
+
+def _pack_node_weight(weight, transpose):
+    rows, cols = weight.shape
+    image_k = rows if transpose else cols
+    packed = torch.empty(_lib.size_query("cmp_node_gemm_weight_bytes", image_k), dtype=torch.uint8,
+                         device=weight.device)
+    call("cmp_node_gemm_pack_weight", ptr(_f32c(weight)), rows, cols, int(transpose), ptr(packed))
+    return packed
+
+
+def _node_gemm(x2, w_img, K, Nout, bias=None, act=ACT_NONE, residual=None, saved_y=None):
+    M = x2.shape[0]
+    y = torch.empty(M, Nout, dtype=torch.float32, device=x2.device)
+    call("cmp_node_gemm_fwd", ptr(x2), x2.stride(0), ptr(saved_y), saved_y.stride(0) if saved_y is not None else 0,
+         ptr(w_img), ptr(bias), int(act), ptr(residual), residual.stride(0) if residual is not None else 0, ptr(y),
+         y.stride(0), M, K, Nout, work=2.0 * M * K * Nout)
+    return y
+
+
+class _LinearTCFn(Function):
+    """Same contract as _LinearFn on the tcgen05 split-bf16 node GEMM kernels (node_gemm_tc.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, residual):
+        if act not in (ACT_NONE, ACT_SSP):
+            raise ValueError("linear(tc): only NONE / SSP epilogues are provided")
+        if act != ACT_NONE and residual is not None:
+            raise ValueError("linear: an activation and a residual cannot be fused in the same call")
+        Nout, K = weight.shape
+        lead = x.shape[:-1]
+        x2 = _f32c(x.reshape(-1, K))
+        res2 = _f32c(residual.reshape(-1, Nout)) if residual is not None else None
+        y = _node_gemm(x2, _pack_node_weight(weight, False), K, Nout, _f32c(bias) if bias is not None else None, act,
+                       res2)
+        ctx.act, ctx.lead = act, lead
+        ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        ctx.save_for_backward(x2, weight, y if act != ACT_NONE else None)
+        return y.reshape(*lead, Nout)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, y = ctx.saved_tensors
+        Nout, K = weight.shape
+        dy2 = _f32c(dy.reshape(-1, Nout))
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            # dX = (dY * ssp') W : the forward kernel with the transposed weight image
+            dx = _node_gemm(dy2, _pack_node_weight(weight, True), Nout, K, saved_y=y).reshape(*ctx.lead, K)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            M = x2.shape[0]
+            dw = torch.empty(Nout, K, dtype=torch.float32, device=dy2.device)
+            db = torch.empty(Nout, dtype=torch.float32, device=dy2.device) if ctx.has_bias else None
+            ws = _lib.workspace(_lib.size_query("cmp_node_gemm_dw_workspace", K), dy2.device)
+            call("cmp_node_gemm_dw", ptr(dy2), dy2.stride(0), ptr(y), y.stride(0) if y is not None else 0, ptr(x2),
+                 x2.stride(0), M, K, Nout, ptr(dw), ptr(db), ptr(ws), ws.numel(), work=2.0 * M * K * Nout)
+        if ctx.has_res and ctx.needs_input_grad[4]:
+            dres = dy
+        return dx, dw, db, None, dres
 
 
 class _ActFn(Function):

@@ -236,6 +236,26 @@ int cmp_cfconv_fused_bwd_weights(const float* g, const void* xprime_bf16, const 
                                  int num_filters, float* dW1, float* db1, float* dW2, float* db2,
                                  void* workspace, size_t workspace_bytes, cmp_stream_t stream);
 
+/* Node-level linears on tcgen05 with split-bf16 operands (hi + lo images, three MMA passes, fp32
+ * accumulate): Y = act(X' W^T + b) + R with X' = X * (1 - exp(-saved_y)/2) when saved_y is given (the
+ * ShiftedSoftplus backward fused into the operand load).  K, Nout multiples of 16 in [16, 128].
+ * dX is the same kernel with the weight packed transposed; cmp_node_gemm_dw returns dW = dY'^T X
+ * and db = column sums of dY' (tile partials reduced in a fixed order).  Replaces torch.nn.Linear and
+ * its autograd GEMMs around the message passing (PyG CFConv.lin1/lin2, InteractionBlock.lin, ConAN
+ * heads sns.py:177-179,225-231) in the bf16 mode. */
+int cmp_node_gemm_tc_supported(int K, int Nout);
+size_t cmp_node_gemm_weight_bytes(int image_K);
+int cmp_node_gemm_pack_weight(const float* W, int rows, int cols, int transpose, void* packed,
+                              cmp_stream_t stream);
+int cmp_node_gemm_fwd(const float* X, int64_t ldx, const float* saved_y, int64_t ldys,
+                      const void* w_img, const float* bias, int act, const float* residual,
+                      int64_t ldr, float* Y, int64_t ldy, int64_t M, int K, int Nout,
+                      cmp_stream_t stream);
+size_t cmp_node_gemm_dw_workspace(int K);
+int cmp_node_gemm_dw(const float* dY, int64_t lddy, const float* saved_y, int64_t ldys,
+                     const float* X, int64_t ldx, int64_t M, int K, int Nout, float* dW, float* db,
+                     void* workspace, size_t workspace_bytes, cmp_stream_t stream);
+
 /* Single-tile UMMA probe used by the tests to pin descriptor / TMEM conventions. */
 int cmp_debug_umma_gemm(const void* a_img, int64_t a_bytes, const void* b_img, int64_t b_bytes,
                         float* D, int N, int K, int fmt, int a_mn, int b_mn, int a_lbo, int a_sbo,

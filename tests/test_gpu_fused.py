@@ -153,3 +153,31 @@ def test_fused_weight_gradients_match_exact_recompute(n, B):
     again = torch.autograd.grad(out, [xp] + params, go)
     for a, r in zip(again, res[True]):
         assert torch.equal(a, r)
+
+
+@pytest.mark.parametrize("M,K,Nout", [(1000, 128, 128), (17280, 128, 128), (300, 128, 64), (77, 64, 64), (128, 64, 128)])
+def test_node_gemm_tc_forward_and_gradients(M, K, Nout):
+    """Split-bf16 tcgen05 node GEMMs (fwd, dX with fused ssp', dW/db with TMEM accumulation) vs fp64."""
+    _need_sm100()
+    import math
+    torch.manual_seed(M + K)
+    x = torch.randn(M, K, device=DEV, requires_grad=True)
+    w = (torch.randn(Nout, K, device=DEV) / math.sqrt(K)).requires_grad_(True)
+    bias = torch.randn(Nout, device=DEV, requires_grad=True)
+    res = torch.randn(M, Nout, device=DEV, requires_grad=True)
+    for act, use_res in ((cmp._lib.ACT_NONE, True), (cmp._lib.ACT_SSP, False)):
+        y = ops.linear(x, w, bias, act, res if use_res else None, tc=True)
+        yr = x.double() @ w.double().t() + bias.double()
+        if act == cmp._lib.ACT_SSP:
+            yr = torch.nn.functional.softplus(yr) - math.log(2.0)
+        if use_res:
+            yr = yr + res.double()
+        assert rel_err(y, yr) < 2e-5
+        go = torch.randn_like(y)
+        ins = [x, w, bias] + ([res] if use_res else [])
+        got = torch.autograd.grad(y, ins, go)
+        want = torch.autograd.grad(yr, ins, go.double())
+        for a, b in zip(got, want):
+            assert rel_err(a, b) < 5e-5
+        again = torch.autograd.grad(ops.linear(x, w, bias, act, res if use_res else None, tc=True), [w], go)[0]
+        assert torch.equal(again, got[1])

@@ -100,3 +100,21 @@ def test_same_bytes_serve_as_transposed_operand():
               128, 1, 0, 1, 128, sbo, 256, sbo, 128, 2 * sbo)
     torch.cuda.synchronize()
     assert rel(D.cpu(), A @ Y) < 1e-5
+
+
+def test_mnmajor_a_and_b():
+    """Both operands as MN-major views of K-major [rows = atoms, K = channel] images (weight-gradient GEMMs)."""
+    g = torch.Generator().manual_seed(9)
+    Y = torch.randn(128, 64, generator=g).bfloat16().float()     # [atoms, Nout]
+    X = torch.randn(128, 144, generator=g).bfloat16().float()    # [atoms, K + 16]
+    sy, sx = (64 // 8) * 128, (144 // 8) * 128
+    y_img = torch.cat([image_kmajor(Y, 128, sy), torch.zeros(2048, dtype=torch.uint8)])   # slack: M = 128 view
+    x_img = image_kmajor(X, 128, sx)
+    a_img, b_img = y_img.to(DEV), x_img.to(DEV)
+    D = torch.zeros(128, 144, device=DEV)
+    # D[m = out channel, n = in channel] = sum_atoms Y[a, m] X[a, n]; K step (16 atoms) = 2 atom groups
+    _lib.call("cmp_debug_umma_gemm", _lib.ptr(a_img), a_img.numel(), _lib.ptr(b_img), b_img.numel(), _lib.ptr(D), 144,
+              128, 1, 1, 1, sy, 128, 2 * sy, sx, 128, 2 * sx)
+    torch.cuda.synchronize()
+    want = Y.t() @ X
+    assert rel(D.cpu()[:64], want) < 1e-5
