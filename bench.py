@@ -255,6 +255,15 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         resident_step()
     e2e_step()
+    if args.profile:      # ncu launch-list mode: only the timed steps follow, then exit
+        total_ms, launches, _ = timed(resident_step, args.steps)
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps({"profile_only": True, "ms_per_step": total_ms / args.steps,
+                              "launches_per_step": launches / args.steps}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     t_spin = time.perf_counter()
     while time.perf_counter() - t_spin < 0.5:      # keep the GPU under the same load until the sampler is running
         resident_step()
@@ -353,6 +362,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="fp32: exact kernels (1e-5 parity mode); bf16: fused tcgen05 CFConv, bf16 filter MLP")
+    ap.add_argument("--profile", action="store_true", help="warm-up + timed steps only (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
