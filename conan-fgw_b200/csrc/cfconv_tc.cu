@@ -39,10 +39,11 @@ constexpr uint32_t A2_SBO = (K2 / 8) * 128;       // 2304: 8-row group stride of
 constexpr uint32_t B2_BYTES = K2 * TILE_E * 2;    // 36864 (the rbf image, 16384 B, aliases its head)
 constexpr uint32_t XP_BYTES = XP_CAP * F * 4;     // 40960
 constexpr uint32_t OFF_X = B2_BYTES;
-constexpr uint32_t OFF_META = OFF_X + XP_BYTES;          // int2[128] {src, dst if the edge ends its row else -1}
+constexpr uint32_t OFF_META = OFF_X + XP_BYTES;          // int[128] x' row offset (floats) | int[128] target row
 constexpr uint32_t OFF_C = OFF_META + TILE_E * 8;        // float[128] cosine cutoff
 constexpr uint32_t OFF_ROW = OFF_C + TILE_E * 4;         // int[136]  row offsets of the tile (relative)
-constexpr uint32_t GROUP_BYTES = OFF_ROW + 544;
+constexpr uint32_t OFF_END = OFF_ROW + 544;              // uint32[8] row-end bit mask of each 16-edge chunk
+constexpr uint32_t GROUP_BYTES = OFF_END + 32;
 constexpr uint32_t SMEM_BYTES = W1_BYTES + W2_BYTES + NG * GROUP_BYTES;
 
 struct FwdParams {
@@ -77,9 +78,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-__device__ __forceinline__ float ssp_fast(float x) {
-  float t = ex2_approx(-1.4426950408889634f * fabsf(x));
-  return fmaxf(x, 0.0f) + __logf(1.0f + t) - kLn2;
+// softplus(x) = max(x, 0) + ln2 * log2(1 + 2^(-|x| log2 e)); the "- ln 2" of ShiftedSoftplus lives in the bias column
+__device__ __forceinline__ float softplus_fast(float x) {
+  const float t = ex2_approx(-1.4426950408889634f * fabsf(x));
+  return fmaf(__log2f(1.0f + t), kLn2, fmaxf(x, 0.0f));
 }
 
 __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const FwdParams p) {
@@ -174,9 +176,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
     uint64_t* xbar = &bars[1 + g * 5 + 4];
     uint8_t* sB = smem + W1_BYTES + W2_BYTES + g * GROUP_BYTES;
     float* sX = reinterpret_cast<float*>(sB + OFF_X);
-    int2* sMeta = reinterpret_cast<int2*>(sB + OFF_META);
+    int* sSrc = reinterpret_cast<int*>(sB + OFF_META);
+    int* sDst = sSrc + TILE_E;
     float* sC = reinterpret_cast<float*>(sB + OFF_C);
     int* sRow = reinterpret_cast<int*>(sB + OFF_ROW);
+    uint32_t* sEnd = reinterpret_cast<uint32_t*>(sB + OFF_END);
     const uint32_t d1 = tmem_base + g * 256 + ((uint32_t)(wq * 32) << 16);
     const uint32_t d2 = d1 + 128;
     const int64_t u = (int64_t)blockIdx.x * NG + g;
@@ -230,21 +234,30 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
       tc::named_bar_sync(1 + g, GT);
 
       // ---- per-edge metadata + Gaussian expansion -> B1 (K-major [edge, 64]) ----
+      if (h == 0) {   // warps 0..3 of the group: one edge slot per thread
+        bool last = false;
+        int srcoff = 0, dst = tile.row_begin;
+        float cval = 0.0f;
+        if (e < ne) {
+          int r = 0;
+          while (sRow[r + 1] <= e) ++r;
+          last = (e + 1 == sRow[r + 1]);
+          srcoff = (staged ? (pre_src - cs) : pre_src) * F;
+          dst = tile.row_begin + r;
+          cval = 0.5f * (__cosf(pre_d * kPi / cutoff) + 1.0f);
+        }
+        sSrc[e] = srcoff;
+        sDst[e] = dst;
+        sC[e] = cval;
+        const unsigned ends = __ballot_sync(0xffffffffu, last);
+        if (lane == 0) {
+          sEnd[e >> 4] = ends & 0xffffu;
+          sEnd[(e >> 4) + 1] = ends >> 16;
+        }
+      }
       if (e < npad) {
         const bool live = e < ne;
         const float d = pre_d;
-        if (h == 0) {
-          if (live) {
-            int r = 0;
-            while (sRow[r + 1] <= e) ++r;
-            const bool last = (e + 1 == sRow[r + 1]);
-            sMeta[e] = make_int2(staged ? (pre_src - cs) : pre_src, last ? (tile.row_begin + r) : -1);
-            sC[e] = 0.5f * (__cosf(d * kPi / cutoff) + 1.0f);
-          } else {
-            sMeta[e] = make_int2(0, -1);
-            sC[e] = 0.0f;
-          }
-        }
         uint8_t* rowp = sB + (e >> 3) * B1_SBO + (e & 7) * 16;
         const int jc0 = h * k1steps, jc1 = jc0 + k1steps;   // each half writes k1steps of the 2*k1steps chunks
         for (int jc = jc0; jc < jc1; ++jc) {
@@ -272,8 +285,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
           pre_src = __ldg(p.col + nxt.e0 + e);
         }
       }
-      const int rsplit = (nrows + 1) >> 1;
-      const int esplit = sRow[rsplit];                     // rows [0, rsplit) -> half 0, the rest -> half 1
       const int csplit = (((npad >> 4) + 1) >> 1) << 4;    // ep1 column split (multiple of 16)
 
       // ---- epilogue 1: a' = C * ssp(D1) -> B2 (MN-major [144, edge]) ----
@@ -294,7 +305,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
           }
           tc::tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = ssp_fast(v[j]) * c[j];
+          for (int j = 0; j < 16; ++j) v[j] = softplus_fast(v[j]) * c[j];
           *reinterpret_cast<uint4*>(colp + (c0 >> 3) * A2_SBO) =
               make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
                          tc::pack_bf16x2(v[6], v[7]));
@@ -326,60 +337,55 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
         ++xloads;
       }
       {
-        const int lo = h ? esplit : 0, hi = h ? ne : esplit;
+        // each warp half takes a 16-aligned half of the columns; a target row cut by the split is completed by two
+        // atomic adds onto the pre-zeroed output (two addends: commutative, hence still bitwise deterministic)
+        const int cb = h ? csplit : 0, ce = h ? npad : csplit;
         float acc = 0.0f;
         float* aggc = p.agg + chan;
-        if (staged) {
-          const float* xs_base = sX + chan;
-          for (int c0 = lo & ~15; c0 < hi; c0 += 16) {
-            float v[16];
-            tc::tmem_ld16(d2 + c0, v);
-            int2 m[16];
-            float xs[16];
-            const int4* mp = reinterpret_cast<const int4*>(sMeta + c0);
+        bool cont = h && cb < ne && !((sEnd[(cb - 1) >> 4] >> ((cb - 1) & 15)) & 1u);
+        const float* xs_smem = sX + chan;
+        const float* xs_gmem = p.xprime + chan;
+        for (int c0 = cb; c0 < ce; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(d2 + c0, v);
+          const uint32_t ends = sEnd[c0 >> 4];
+          float xs[16];
+          const int4* sp = reinterpret_cast<const int4*>(sSrc + c0);
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int4 mm = mp[q];
-              m[2 * q] = make_int2(mm.x, mm.y);
-              m[2 * q + 1] = make_int2(mm.z, mm.w);
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) xs[j] = xs_base[m[j].x * F];
-            tc::tmem_wait_ld();
-            const bool full = (c0 >= lo) && (c0 + 16 <= hi);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (full || (c0 + j >= lo && c0 + j < hi)) {
-                acc = fmaf(v[j], xs[j], acc);
-                if (m[j].y >= 0) {
-                  aggc[(int64_t)m[j].y * F] = acc;
-                  acc = 0.0f;
-                }
-              }
+          for (int q = 0; q < 4; ++q) {
+            const int4 o = sp[q];
+            if (staged) {
+              xs[4 * q + 0] = xs_smem[o.x]; xs[4 * q + 1] = xs_smem[o.y];
+              xs[4 * q + 2] = xs_smem[o.z]; xs[4 * q + 3] = xs_smem[o.w];
+            } else {
+              xs[4 * q + 0] = __ldg(xs_gmem + o.x); xs[4 * q + 1] = __ldg(xs_gmem + o.y);
+              xs[4 * q + 2] = __ldg(xs_gmem + o.z); xs[4 * q + 3] = __ldg(xs_gmem + o.w);
             }
           }
-        } else {
-          const float* xs_base = p.xprime + chan;
-          for (int c0 = lo & ~15; c0 < hi; c0 += 16) {
-            float v[16];
-            tc::tmem_ld16(d2 + c0, v);
-            float xs[16];
+          tc::tmem_wait_ld();
+          if (ends == 0u) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) xs[j] = __ldg(xs_base + (int64_t)sMeta[c0 + j].x * F);
-            tc::tmem_wait_ld();
+            for (int j = 0; j < 16; ++j) acc = fmaf(v[j], xs[j], acc);
+          } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              if (c0 + j >= lo && c0 + j < hi) {
-                acc = fmaf(v[j], xs[j], acc);
-                const int dst = sMeta[c0 + j].y;
-                if (dst >= 0) {
-                  aggc[(int64_t)dst * F] = acc;
-                  acc = 0.0f;
+              acc = fmaf(v[j], xs[j], acc);
+              if ((ends >> j) & 1u) {
+                float* dstp = aggc + (int64_t)sDst[c0 + j] * F;
+                if (cont) {
+                  atomicAdd(dstp, acc);
+                  cont = false;
+                } else {
+                  *dstp = acc;
                 }
+                acc = 0.0f;
               }
             }
           }
         }
+        // half 0 ends inside a target row: hand its partial sum over
+        if (!h && ce > 0 && ce <= ne && ce < npad + 1 && !((sEnd[(ce - 1) >> 4] >> ((ce - 1) & 15)) & 1u) && (ce - 1) < ne)
+          atomicAdd(aggc + (int64_t)sDst[ce - 1] * F, acc);
       }
       tc::tc_fence_before();
       cur = nxt;
@@ -404,7 +410,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ W1, const float* _
   } else if (idx < F * K1 + F * K2) {
     const int j = idx - F * K1;
     const int m = j / K2, k = j % K2;
-    float v = (k < F) ? W2[m * F + k] : (k == F ? b2[m] : 0.0f);
+    float v = 0.0f;
+    if (k < F) {
+      v = W2[m * F + k];
+    } else if (k == F) {
+      // the kernel feeds a' = C * softplus(h) (without the "- ln 2" of ShiftedSoftplus); the shift is folded into the
+      // bias column: W2q (C sp - C ln2) + b2 C = W2q (C sp) + C (b2 - ln2 * rowsum(W2q)), W2q = the bf16 weights
+      float rs = 0.0f;
+      for (int kk = 0; kk < F; ++kk) rs += __bfloat162float(__float2bfloat16_rn(W2[m * F + kk]));
+      v = b2[m] - kLn2 * rs;
+    }
     uint32_t off = (m & 7) * 16 + (k & 7) * 2 + (m >> 3) * A2_SBO + (k >> 3) * 128;
     *reinterpret_cast<__nv_bfloat16*>(out + W1_BYTES + off) = __float2bfloat16_rn(v);
   }
