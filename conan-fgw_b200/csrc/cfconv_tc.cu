@@ -78,10 +78,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// softplus(x) = max(x, 0) + ln2 * log2(1 + 2^(-|x| log2 e)); the "- ln 2" of ShiftedSoftplus lives in the bias column
+// ssp(x) = max(x, 0) + ln2 * (log2(1 + 2^(-|x| log2 e)) - 1).  (Folding the "- ln 2" into the bias column would save
+// an instruction but costs accuracy: ssp is small near 0, softplus is not, and a' is rounded to bf16.)
 __device__ __forceinline__ float softplus_fast(float x) {
   const float t = ex2_approx(-1.4426950408889634f * fabsf(x));
-  return fmaf(__log2f(1.0f + t), kLn2, fmaxf(x, 0.0f));
+  return fmaf(__log2f(1.0f + t) - 1.0f, kLn2, fmaxf(x, 0.0f));
 }
 
 __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const FwdParams p) {
@@ -414,11 +415,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ W1, const float* _
     if (k < F) {
       v = W2[m * F + k];
     } else if (k == F) {
-      // the kernel feeds a' = C * softplus(h) (without the "- ln 2" of ShiftedSoftplus); the shift is folded into the
-      // bias column: W2q (C sp - C ln2) + b2 C = W2q (C sp) + C (b2 - ln2 * rowsum(W2q)), W2q = the bf16 weights
-      float rs = 0.0f;
-      for (int kk = 0; kk < F; ++kk) rs += __bfloat162float(__float2bfloat16_rn(W2[m * F + kk]));
-      v = b2[m] - kLn2 * rs;
+      v = b2[m];
     }
     uint32_t off = (m & 7) * 16 + (k & 7) * 2 + (m >> 3) * A2_SBO + (k >> 3) * 128;
     *reinterpret_cast<__nv_bfloat16*>(out + W1_BYTES + off) = __float2bfloat16_rn(v);
