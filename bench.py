@@ -264,9 +264,8 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    t_spin = time.perf_counter()
-    while time.perf_counter() - t_spin < 0.5:      # keep the GPU under the same load until the sampler is running
-        resident_step()
+    for _ in range(60):      # keep the GPU under the same load until the clock sampler is running; a FIXED count,
+        resident_step()      # identical on every rank (each step holds a collective)
     torch.cuda.synchronize()
     dominant = ["cmp_gemm_f32", "cmp_cfconv_fused_fwd", "cmp_cfconv_fused_bwd_weights"]
     total_ms, launches, kt = timed(resident_step, args.steps, dominant)
