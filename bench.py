@@ -215,15 +215,30 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    use_graph = args.precision == "bf16" and not args.no_graph   # the exact mode syncs once per step (edge count)
+
     def resident_step():
         return trainer.step(d.z, d.pos, d.batch, targets, G)
 
+    def eager_step():
+        graph, trainer._graph = getattr(trainer, "_graph", None), None
+        try:
+            return trainer.step(d.z, d.pos, d.batch, targets, G)
+        finally:
+            trainer._graph = graph
+
     def e2e_step():
-        z = host.z.to(dev, non_blocking=True)
-        pos = host.pos.to(dev, non_blocking=True)
-        bt = host.batch.to(dev, non_blocking=True)
-        tg_ = targets_h.to(dev, non_blocking=True)
-        loss = trainer.step(z, pos, bt, tg_, G)
+        if getattr(trainer, "_graph", None) is not None:
+            # H2D straight into the captured graph's input buffers, replay, D2H of the loss
+            for dst, src in zip(trainer._static, (host.z, host.pos, host.batch, targets_h)):
+                dst.copy_(src, non_blocking=True)
+            loss = trainer.step(*trainer._static, G)
+        else:
+            z = host.z.to(dev, non_blocking=True)
+            pos = host.pos.to(dev, non_blocking=True)
+            bt = host.batch.to(dev, non_blocking=True)
+            tg_ = targets_h.to(dev, non_blocking=True)
+            loss = trainer.step(z, pos, bt, tg_, G)
         return float(loss.item())          # D2H read of the step's result
 
     def timed(step_fn, steps, timer_names=None):
@@ -254,6 +269,9 @@ def run_ours(args):
         sampler.start()          # nvidia-smi needs ~100 ms to start: sample across warm-up + timed region
     for _ in range(max(args.warmup, 3)):
         resident_step()
+    if use_graph and not args.profile:
+        trainer.capture(d.z, d.pos, d.batch, targets, G)    # whole fwd+bwd in one CUDA graph; Adam/all-reduce eager
+        resident_step()
     e2e_step()
     if args.profile:      # ncu launch-list mode: only the timed steps follow, then exit
         total_ms, launches, _ = timed(resident_step, args.steps)
@@ -267,10 +285,16 @@ def run_ours(args):
     for _ in range(60):      # keep the GPU under the same load until the clock sampler is running; a FIXED count,
         resident_step()      # identical on every rank (each step holds a collective)
     torch.cuda.synchronize()
-    dominant = ["cmp_gemm_f32", "cmp_cfconv_fused_fwd", "cmp_cfconv_fused_bwd_weights"]
-    total_ms, launches, kt = timed(resident_step, args.steps, dominant)
+    dominant = ["cmp_gemm_f32", "cmp_cfconv_fused_fwd", "cmp_cfconv_fused_bwd_weights", "cmp_node_gemm_fwd",
+                "cmp_node_gemm_dw"]
+    total_ms, launches, kt = timed(resident_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, _, _ = timed(e2e_step, args.steps)
+    # per-kernel durations (roofline) need the eager launches: same step, same inputs, CUDA events around each call
+    ksteps = max(3, min(args.steps, 10))
+    eager_ms, eager_launches, kt = timed(eager_step, ksteps, dominant)
+    launches_per_step = eager_launches / ksteps
+    launches = int(round(launches_per_step * args.steps))
 
     # the other numerics mode of the same step, for the record (exact-fp32 kernels <-> fused bf16 filter MLP)
     other = "fp32" if args.precision == "bf16" else "bf16"
@@ -311,6 +335,8 @@ def run_ours(args):
         "cmp_gemm_f32": "gemm_f32_kernel (exact-fp32 SIMT GEMM: filter MLP on E rows + node linears + their gradients)",
         "cmp_cfconv_fused_fwd": "cfconv_fused_fwd_kernel (tcgen05: rbf + filter MLP + cutoff + gather + segmented reduce)",
         "cmp_cfconv_fused_bwd_weights": "cfconv_fused_bwd_kernel (tcgen05: recompute + dW accumulated in TMEM, K = edges)",
+        "cmp_node_gemm_fwd": "node_gemm_fwd_kernel (tcgen05 split-bf16 node linears)",
+        "cmp_node_gemm_dw": "node_gemm_dw_kernel (tcgen05 split-bf16 weight gradients of the node linears)",
     }
     roofline = {
         "kernel": kernel_names[top],
@@ -319,8 +345,11 @@ def run_ours(args):
         "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"],
         "unit": "TFLOP/s", "frac": (achieved / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])) if achieved else None,
         "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
-        "launches_timed": n_l, "kernel_ms_per_step": k_ms / args.steps if args.steps else None,
-        "step_share": (k_ms / total_ms) if total_ms else None,
+        "launches_timed": n_l, "kernel_ms_per_step": k_ms / ksteps, "avg_launch_us": 1e3 * k_ms / max(n_l, 1),
+        "step_share": (k_ms / eager_ms) if eager_ms else None,
+        "timed_in": f"{ksteps} eager steps ({eager_ms / ksteps:.3f} ms/step) with CUDA events around every launch of the "
+                    f"listed kernels; `value` itself replays the same step from a CUDA graph" if use_graph else
+                    f"{ksteps} steps with CUDA events around every launch of the listed kernels",
         "algorithmic_flops_per_step": algorithmic_flops(N, E),
         "step_tflops": algorithmic_flops(N, E) * args.steps / (total_ms * 1e-3) / 1e12,
     }
@@ -339,6 +368,7 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "precision": args.precision, "molecules_per_gpu": B, "conformers_per_molecule": K, "atoms_per_conformer": n,
                    "conformers_per_gpu": G, "atoms": N, "edges": E, **MODEL_CFG, "max_num_neighbors": 32,
                    "step": "radius graph + fwd + MSE + bwd + grad all-reduce (N>1) + Adam",
+                   "cuda_graph": bool(use_graph),
                    "l2": "256 MiB buffer written between timed iterations (L2 flush, untimed)",
                    "parallelism": f"dp{world}"},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d,
@@ -361,6 +391,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="fp32: exact kernels (1e-5 parity mode); bf16: fused tcgen05 CFConv, bf16 filter MLP")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile", action="store_true", help="warm-up + timed steps only (for ncu launch lists)")
     args = ap.parse_args()
     if args.impl == "reference":
