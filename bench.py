@@ -340,7 +340,7 @@ def run_ours(args):
     }
     roofline = {
         "kernel": kernel_names[top],
-        "all_timed": {k: {"launches": v[0], "ms_per_step": v[1] / args.steps,
+        "all_timed": {k: {"launches": v[0], "ms_per_step": v[1] / ksteps, "avg_launch_us": 1e3 * v[1] / max(v[0], 1),
                           "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in summ.items()},
         "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"],
         "unit": "TFLOP/s", "frac": (achieved / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])) if achieved else None,

@@ -14,10 +14,12 @@ from .graph import NeighborList, build_neighbor_list, radius_graph  # noqa: F401
 from .nn import (CFConv, GaussianSmearing, InteractionBlock, Linear, RadiusInteractionGraph,  # noqa: F401
                  SchNet, ShiftedSoftplus, SumAggregation)
 from .schnet_no_sum import SchNetNoSum  # noqa: F401
+from . import visnet  # noqa: F401
+from .visnet import ViSNet, ViS_MP, ViSNetBlock, TorchGeometricViSNet  # noqa: F401
 from . import synthetic  # noqa: F401
 
 __all__ = [
     "radius_graph", "build_neighbor_list", "NeighborList", "RadiusInteractionGraph", "GaussianSmearing",
     "ShiftedSoftplus", "CFConv", "InteractionBlock", "SchNet", "SchNetNoSum", "Linear", "SumAggregation",
-    "build_library", "library_is_built", "synthetic",
+    "build_library", "library_is_built", "synthetic", "visnet", "ViSNet", "ViS_MP", "ViSNetBlock", "TorchGeometricViSNet",
 ]

@@ -59,6 +59,21 @@ SIGNATURES = {
     "cmp_node_gemm_fwd": (I, [P, L, P, L, P, P, I, P, L, P, L, L, I, I, P]),
     "cmp_node_gemm_dw_workspace": (S, [I]),
     "cmp_node_gemm_dw": (I, [P, L, P, L, P, L, L, I, I, P, P, P, S, P]),
+    "cmp_edge_message_fwd": (I, [P, P, P, P, P, L, I, P, P]),
+    "cmp_edge_message_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, P, P, P]),
+    "cmp_vis_edge_geometry": (I, [P, P, P, P, L, F, F, P, P, I, P, P, P, P]),
+    "cmp_layernorm_fwd": (I, [P, P, P, L, I, F, P, P, P, P]),
+    "cmp_layernorm_bwd": (I, [P, P, P, P, P, L, I, P, P, P]),
+    "cmp_csr_segment_sum": (I, [P, P, P, L, I, P, P]),
+    "cmp_gather_rows": (I, [P, P, L, I, P, P]),
+    "cmp_vis_edge_embed_fwd": (I, [P, P, P, P, L, I, P, P]),
+    "cmp_vis_edge_embed_bwd": (I, [P, P, P, P, P, L, I, P, P, P]),
+    "cmp_vis_message_fwd": (I, [P, P, P, P, P, P, P, P, L, I, I, P, P, P]),
+    "cmp_vis_message_bwd": (I, [P, P, P, P, P, P, P, P, P, P, L, I, I, P, P, P, P, P, P]),
+    "cmp_vis_vecagg_fwd": (I, [P, P, P, P, P, L, I, P, P]),
+    "cmp_vis_vecagg_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, P, P, P]),
+    "cmp_vis_edge_update_fwd": (I, [P, P, P, P, P, P, L, I, P, P, P]),
+    "cmp_vis_edge_update_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, P, P, P]),
     "cmp_csr_expand_rows": (I, [P, L, P, P]),
     "cmp_cfconv_tc_bwd_tile_edges": (I, []),
     "cmp_build_flat_tiles_workspace": (S, [L]),

@@ -78,7 +78,8 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 cfconv_message_fwd_kernel(const float* __restrict__ xprime, const float* __restrict__ filt,
                           const float* __restrict__ dist, const int32_t* __restrict__ rowptr,
-                          const int32_t* __restrict__ col, int64_t N, int F, float cutoff, float* __restrict__ agg) {
+                          const int32_t* __restrict__ col, int64_t N, int F, float cutoff, float* __restrict__ agg,
+                          const float* __restrict__ scale) {
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (row >= N) return;
@@ -89,7 +90,7 @@ cfconv_message_fwd_kernel(const float* __restrict__ xprime, const float* __restr
     for (int v = 0; v < VEC; ++v) acc[v] = 0.0f;
     for (int k = b; k < e; ++k) {
       int j = col[k];
-      float C = 0.5f * (cosf(dist[k] * kPi / cutoff) + 1.0f);
+      float C = scale ? scale[k] : 0.5f * (cosf(dist[k] * kPi / cutoff) + 1.0f);
       if (VEC == 4) {
         float4 x = *reinterpret_cast<const float4*>(xprime + (int64_t)j * F + c);
         float4 w = *reinterpret_cast<const float4*>(filt + (int64_t)k * F + c);
@@ -113,14 +114,14 @@ cfconv_message_fwd_kernel(const float* __restrict__ xprime, const float* __restr
 __global__ void __launch_bounds__(256)
 cfconv_dfilt_kernel(const float* __restrict__ g, const float* __restrict__ xprime, const float* __restrict__ dist,
                     const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N, int F,
-                    float cutoff, float* __restrict__ dfilt) {
+                    float cutoff, float* __restrict__ dfilt, const float* __restrict__ scale) {
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (row >= N) return;
   int b = rowptr[row], e = rowptr[row + 1];
   for (int k = b; k < e; ++k) {
     int j = col[k];
-    float C = 0.5f * (cosf(dist[k] * kPi / cutoff) + 1.0f);
+    float C = scale ? scale[k] : 0.5f * (cosf(dist[k] * kPi / cutoff) + 1.0f);
     for (int c = lane; c < F; c += 32)
       dfilt[(int64_t)k * F + c] = g[row * F + c] * xprime[(int64_t)j * F + c] * C;
   }
@@ -130,7 +131,8 @@ cfconv_dfilt_kernel(const float* __restrict__ g, const float* __restrict__ xprim
 __global__ void __launch_bounds__(256)
 cfconv_dx_kernel(const float* __restrict__ g, const float* __restrict__ filt, const float* __restrict__ dist,
                  const int32_t* __restrict__ rowptr_t, const int32_t* __restrict__ col_t,
-                 const int32_t* __restrict__ eid_t, int64_t N, int F, float cutoff, float* __restrict__ dx) {
+                 const int32_t* __restrict__ eid_t, int64_t N, int F, float cutoff, float* __restrict__ dx,
+                 const float* __restrict__ scale) {
   int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (row >= N) return;
@@ -140,7 +142,7 @@ cfconv_dx_kernel(const float* __restrict__ g, const float* __restrict__ filt, co
     for (int k = b; k < e; ++k) {
       int i = col_t[k];
       int eid = eid_t[k];
-      float C = 0.5f * (cosf(dist[eid] * kPi / cutoff) + 1.0f);
+      float C = scale ? scale[eid] : 0.5f * (cosf(dist[eid] * kPi / cutoff) + 1.0f);
       acc += g[(int64_t)i * F + c] * (filt[(int64_t)eid * F + c] * C);
     }
     dx[row * F + c] = acc;
@@ -249,10 +251,10 @@ extern "C" int cmp_cfconv_message_fwd(const float* xprime, const float* filt, co
   bool vec = (F % 4 == 0) && (((uintptr_t)xprime | (uintptr_t)filt | (uintptr_t)agg) % 16 == 0);
   if (vec)
     cfconv_message_fwd_kernel<4><<<blocks, 256, 0, as_stream(stream)>>>(xprime, filt, dist, rowptr, col, N, F, cutoff,
-                                                                        agg);
+                                                                        agg, nullptr);
   else
     cfconv_message_fwd_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(xprime, filt, dist, rowptr, col, N, F, cutoff,
-                                                                        agg);
+                                                                        agg, nullptr);
   CMP_LAUNCH_CHECK("cmp_cfconv_message_fwd");
   return CMP_OK;
 }
@@ -267,14 +269,15 @@ extern "C" int cmp_cfconv_message_bwd(const float* g, const float* xprime, const
   unsigned blocks = (unsigned)ceil_div(N * 32, 256);
   if (dfilt) {
     CMP_REQUIRE(xprime && col && dist, CMP_EINVAL, "cmp_cfconv_message_bwd: null pointer (dfilt inputs)");
-    cfconv_dfilt_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, xprime, dist, rowptr, col, N, F, cutoff, dfilt);
+    cfconv_dfilt_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, xprime, dist, rowptr, col, N, F, cutoff, dfilt,
+                                                               nullptr);
     CMP_LAUNCH_CHECK("cmp_cfconv_message_bwd(dfilt)");
   }
   if (dxprime) {
     CMP_REQUIRE(rowptr_t && col_t && eid_t && filt && dist, CMP_EINVAL,
                 "cmp_cfconv_message_bwd: null pointer (dxprime inputs)");
     cfconv_dx_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, filt, dist, rowptr_t, col_t, eid_t, N, F, cutoff,
-                                                            dxprime);
+                                                            dxprime, nullptr);
     CMP_LAUNCH_CHECK("cmp_cfconv_message_bwd(dx)");
   }
   return CMP_OK;
@@ -298,5 +301,42 @@ extern "C" int cmp_segment_sum_bwd(const float* dout, const int32_t* seg_ptr, in
   CMP_REQUIRE(dout && seg_ptr, CMP_EINVAL, "cmp_segment_sum_bwd: null pointer");
   segment_sum_bwd_kernel<<<(unsigned)G, 256, 0, as_stream(stream)>>>(dout, seg_ptr, C, dx);
   CMP_LAUNCH_CHECK("cmp_segment_sum_bwd");
+  return CMP_OK;
+}
+
+// Same gather-multiply-reduce with an explicit per-edge scale instead of the SchNet cosine cutoff:
+//   out[i] = sum_{e in row i} x[col[e]] * filt[e] * scale[e]
+// (ViSNet NeighborEmbedding, tgv.py:408-423: scale = masked cosine cutoff, 0 on self loops.)
+extern "C" int cmp_edge_message_fwd(const float* x, const float* filt, const float* scale, const int32_t* rowptr,
+                                    const int32_t* col, int64_t N, int F, float* out, cmp_stream_t stream) {
+  CMP_REQUIRE(N >= 0 && F >= 1, CMP_EINVAL, "cmp_edge_message_fwd: bad size");
+  if (N == 0) return CMP_OK;
+  CMP_REQUIRE(x && rowptr && out && scale, CMP_EINVAL, "cmp_edge_message_fwd: null pointer");
+  unsigned blocks = (unsigned)ceil_div(N * 32, 256);
+  cfconv_message_fwd_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(x, filt, nullptr, rowptr, col, N, F, 1.0f, out,
+                                                                      scale);
+  CMP_LAUNCH_CHECK("cmp_edge_message_fwd");
+  return CMP_OK;
+}
+
+extern "C" int cmp_edge_message_bwd(const float* g, const float* x, const float* filt, const float* scale,
+                                    const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t,
+                                    const int32_t* col_t, const int32_t* eid_t, int64_t N, int F, float* dfilt, float* dx,
+                                    cmp_stream_t stream) {
+  CMP_REQUIRE(N >= 0 && F >= 1, CMP_EINVAL, "cmp_edge_message_bwd: bad size");
+  if (N == 0) return CMP_OK;
+  CMP_REQUIRE(g && rowptr && scale, CMP_EINVAL, "cmp_edge_message_bwd: null pointer");
+  unsigned blocks = (unsigned)ceil_div(N * 32, 256);
+  if (dfilt) {
+    CMP_REQUIRE(x && col, CMP_EINVAL, "cmp_edge_message_bwd: null pointer (dfilt inputs)");
+    cfconv_dfilt_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, x, nullptr, rowptr, col, N, F, 1.0f, dfilt, scale);
+    CMP_LAUNCH_CHECK("cmp_edge_message_bwd(dfilt)");
+  }
+  if (dx) {
+    CMP_REQUIRE(rowptr_t && col_t && eid_t && filt, CMP_EINVAL, "cmp_edge_message_bwd: null pointer (dx inputs)");
+    cfconv_dx_kernel<<<blocks, 256, 0, as_stream(stream)>>>(g, filt, nullptr, rowptr_t, col_t, eid_t, N, F, 1.0f, dx,
+                                                            scale);
+    CMP_LAUNCH_CHECK("cmp_edge_message_bwd(dx)");
+  }
   return CMP_OK;
 }

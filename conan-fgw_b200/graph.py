@@ -105,6 +105,14 @@ class NeighborList:
             self._tiles_t = (tiles, num, dist_t)
         return self._tiles_t
 
+    def erow(self) -> torch.Tensor:
+        """Target atom of every edge (``edge_index[1]`` as int32), built once."""
+        if getattr(self, "_erow", None) is None:
+            erow = torch.empty_like(self.col)
+            _lib.call("cmp_csr_expand_rows", _lib.ptr(self.rowptr), self.N, _lib.ptr(erow))
+            self._erow = erow
+        return self._erow
+
     def flat_tiles(self):
         """(erow int32[cap_E], tiles int32[cap,8], num_tiles int32[1]): 64-edge chunks per conformer for the
         fused weight-gradient kernel (edges are independent there, so no row alignment)."""
@@ -112,8 +120,7 @@ class NeighborList:
             if self.G == 0 and self.N > 0:
                 raise _lib.ConanMPError("edge tiles need conformer segments (graph was built from a raw edge_index)")
             dev = self.rowptr.device
-            erow = torch.empty_like(self.col)
-            _lib.call("cmp_csr_expand_rows", _lib.ptr(self.rowptr), self.N, _lib.ptr(erow))
+            erow = self.erow()
             tile_e = _lib.size_query("cmp_cfconv_tc_bwd_tile_edges")
             cap = self.cap_E // tile_e + self.G + 1
             tiles = torch.empty(max(cap, 1), 8, dtype=torch.int32, device=dev)

@@ -256,6 +256,74 @@ int cmp_node_gemm_dw(const float* dY, int64_t lddy, const float* saved_y, int64_
                      const float* X, int64_t ldx, int64_t M, int K, int Nout, float* dW, float* db,
                      void* workspace, size_t workspace_bytes, cmp_stream_t stream);
 
+/* ------------------------------------------------------------------------- *
+ * ViSNet edge-level kernels (exact fp32; tgv.py = torch_geometric_visnet.py)
+ * Every reduction runs over the CSR (or its transpose) in a fixed order.
+ * ------------------------------------------------------------------------- */
+
+/* out[i] = sum_{e in row i} x[col[e]] * filt[e] * scale[e]  and its backward: the CFConv message
+ * kernels with an explicit per-edge scale (NeighborEmbedding.forward/message, tgv.py:408-423:
+ * scale = masked cosine cutoff, 0 on self loops). */
+int cmp_edge_message_fwd(const float* x, const float* filt, const float* scale,
+                         const int32_t* rowptr, const int32_t* col, int64_t N, int F, float* out,
+                         cmp_stream_t stream);
+int cmp_edge_message_bwd(const float* g, const float* x, const float* filt, const float* scale,
+                         const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t,
+                         const int32_t* col_t, const int32_t* eid_t, int64_t N, int F, float* dfilt,
+                         float* dx, cmp_stream_t stream);
+/* ExpNormalSmearing (tgv.py:100-111), CosineCutoff with the d < cutoff mask (tgv.py:44-46) and the
+ * unit edge vectors of ViSNetBlock.forward (tgv.py:864-866; self loops keep their zero vector). */
+int cmp_vis_edge_geometry(const float* evec, const float* dist, const int32_t* col,
+                          const int32_t* erow, int64_t E, float cutoff, float alpha,
+                          const float* means, const float* betas, int num_rbf, float* rbf,
+                          float* dhat, float* C, cmp_stream_t stream);
+/* torch.nn.LayerNorm over the last axis (tgv.py:605,883).  bwd returns dx and dy*xhat (its column
+ * sums and those of dy are dweight / dbias). */
+int cmp_layernorm_fwd(const float* x, const float* w, const float* b, int64_t M, int H, float eps,
+                      float* y, float* mean, float* rstd, cmp_stream_t stream);
+int cmp_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean,
+                      const float* rstd, int64_t M, int H, float* dx, float* dyxhat,
+                      cmp_stream_t stream);
+/* out[i] = sum_{e in row i} x[perm ? perm[e] : e] (scatter(..., reduce='sum') of tgv.py:671; with
+ * rowptr_t / eid_t the reduction at the SOURCE atoms), and out[e] = x[idx[e]] (the `_i` / `_j`
+ * gathers of MessagePassing). */
+int cmp_csr_segment_sum(const float* x, const int32_t* rowptr, const int32_t* perm, int64_t N, int C,
+                        float* out, cmp_stream_t stream);
+int cmp_gather_rows(const float* x, const int32_t* idx, int64_t E, int C, float* out,
+                    cmp_stream_t stream);
+/* EdgeEmbedding.forward (tgv.py:463-465): f[e] = (x_i + x_j) * ep[e]; bwd gives d ep and t = g*ep. */
+int cmp_vis_edge_embed_fwd(const float* x, const float* ep, const int32_t* col, const int32_t* erow,
+                           int64_t E, int H, float* f, cmp_stream_t stream);
+int cmp_vis_edge_embed_bwd(const float* g, const float* x, const float* ep, const int32_t* col,
+                           const int32_t* erow, int64_t E, int H, float* gep, float* t_out,
+                           cmp_stream_t stream);
+/* ViS_MP.message scalar part (tgv.py:644-648): attn = silu(sum_d q_i k_j dk) * C, m = v_j dv attn. */
+int cmp_vis_message_fwd(const float* q, const float* k, const float* v, const float* dk,
+                        const float* dv, const float* C, const int32_t* col, const int32_t* erow,
+                        int64_t E, int H, int heads, float* m, float* attn_pre, cmp_stream_t stream);
+int cmp_vis_message_bwd(const float* gm, const float* q, const float* k, const float* v,
+                        const float* dk, const float* dv, const float* C, const float* attn_pre,
+                        const int32_t* col, const int32_t* erow, int64_t E, int H, int heads,
+                        float* g_dk, float* g_dv, float* geq, float* gek, float* gev,
+                        cmp_stream_t stream);
+/* ViS_MP vector message + aggregation (tgv.py:650-651,672):
+ * vagg[i] = sum_e vec[j] * s1[e] + s2[e] * dhat[e], s12 = [s1 | s2] per edge. */
+int cmp_vis_vecagg_fwd(const float* vec, const float* s12, const float* dhat, const int32_t* rowptr,
+                       const int32_t* col, int64_t N, int H, float* vagg, cmp_stream_t stream);
+int cmp_vis_vecagg_bwd(const float* g, const float* vec, const float* s12, const float* dhat,
+                       const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t,
+                       const int32_t* col_t, const int32_t* eid_t, int64_t N, int H, float* g_s12,
+                       float* g_vec, cmp_stream_t stream);
+/* ViS_MP.edge_update (tgv.py:655-661) with w_trg / w_src applied at the nodes (bias-free linears):
+ * wdot = wt_i . ws_j - (wt_i . dhat)(ws_j . dhat);  df = fpa * wdot. */
+int cmp_vis_edge_update_fwd(const float* wt, const float* ws, const float* dhat, const float* fpa,
+                            const int32_t* col, const int32_t* erow, int64_t E, int H, float* df,
+                            float* wdot, cmp_stream_t stream);
+int cmp_vis_edge_update_bwd(const float* gw, const float* wt, const float* ws, const float* dhat,
+                            const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t,
+                            const int32_t* col_t, const int32_t* eid_t, int64_t N, int H, float* g_wt,
+                            float* g_ws, cmp_stream_t stream);
+
 /* Single-tile UMMA probe used by the tests to pin descriptor / TMEM conventions. */
 int cmp_debug_umma_gemm(const void* a_img, int64_t a_bytes, const void* b_img, int64_t b_bytes,
                         float* D, int N, int K, int fmt, int a_mn, int b_mn, int a_lbo, int a_sbo,

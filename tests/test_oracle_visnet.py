@@ -62,3 +62,15 @@ def test_live_against_reference_file():
     x, v = ref.representation_model(b.z, b.pos.clone(), b.batch)
     want = pyg_shim.scatter(ref.prior_model(ref.output_model.pre_reduce(x, v) * ref.std, b.z), b.batch, dim=0)
     assert rel_err(m(b.z, b.pos, b.batch), want) < 1e-6
+
+
+def test_cuda_modules_expose_the_reference_state_dict():
+    import conan_fgw_b200 as cmp
+
+    o = ov.ViSNet(None, hidden_channels=128)
+    c = cmp.ViSNet(None, hidden_channels=128)
+    so, sc = o.state_dict(), c.state_dict()
+    assert set(so) == set(sc) and len(sc) == 171
+    assert {k: tuple(v.shape) for k, v in so.items()} == {k: tuple(v.shape) for k, v in sc.items()}
+    c.load_state_dict(so, strict=True)
+    assert sum(p.numel() for p in c.parameters()) == 1798472
