@@ -22,3 +22,22 @@ for cfgname in ("cfg2_lipo_train", "cfg4_bace_cls"):
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 5
             print(f"{cfgname} {prec} {name}: {ms:.3f} ms  {G/ms*1e3:.0f} conformers/s", flush=True)
+
+# ViSNet, BASELINE.json configs[2]: FreeSolv-shaped, 32 x 5 conformers x 18 atoms, hidden 128, 6 layers
+b = cmp.synthetic.make_config_batch("cfg3_freesolv_visnet").to(dev)
+torch.manual_seed(0)
+m = cmp.ViSNet(None, hidden_channels=128).to(dev)
+G = b.num_graphs
+def vfwd():
+    with torch.no_grad():
+        return m(b.z, b.pos, b.batch, num_graphs=G)
+def vfb():
+    m.zero_grad(); m(b.z, b.pos, b.batch, num_graphs=G).pow(2).mean().backward()
+for name, fn in (("fwd", vfwd), ("fwd+bwd", vfb)):
+    for _ in range(3): fn()
+    torch.cuda.synchronize(); e0 = torch.cuda.Event(True); e1 = torch.cuda.Event(True)
+    e0.record()
+    for _ in range(5): fn()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"cfg3_freesolv_visnet fp32 {name}: {ms:.3f} ms  {G/ms*1e3:.0f} conformers/s", flush=True)
