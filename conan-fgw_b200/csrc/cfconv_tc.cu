@@ -82,14 +82,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // an instruction but costs accuracy: ssp is small near 0, softplus is not, and a' is rounded to bf16.)
 __device__ __forceinline__ float softplus_fast(float x) {
   const float t = ex2_approx(-1.4426950408889634f * fabsf(x));
-  return fmaf(__log2f(1.0f + t) - 1.0f, kLn2, fmaxf(x, 0.0f));
+  return fmaf(tc::fast_lg2(1.0f + t) - 1.0f, kLn2, fmaxf(x, 0.0f));
 }
 
 __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const FwdParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bars[1 + NG * 5];  // wbar | per group: b1ready, d1ready, b2ready, d2ready, xbar
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_offset[K1];
+  __shared__ __align__(16) float s_offset[K1];
+  __shared__ __align__(16) float s_c2[K1];   // coeff*log2(e) for the Gaussians, 0 for the bias column and the padding
 
   uint8_t* sW1 = smem;
   uint8_t* sW2 = smem + W1_BYTES;
@@ -107,7 +108,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
     }
     tc::mbar_fence_init();
   }
-  if (tid < K1) s_offset[tid] = (tid < p.Ng) ? p.offset[tid] : 0.0f;
+  if (tid < K1) {
+    s_offset[tid] = (tid < p.Ng) ? p.offset[tid] : 0.0f;
+    s_c2[tid] = (tid < p.Ng) ? p.coeff_log2e : 0.0f;
+  }
   __syncwarp();
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   tc::tc_fence_before();
@@ -257,18 +261,22 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
         }
       }
       if (e < npad) {
-        const bool live = e < ne;
-        const float d = pre_d;
+        const float d = (e < ne) ? pre_d : 0.0f;
         uint8_t* rowp = sB + (e >> 3) * B1_SBO + (e & 7) * 16;
         const int jc0 = h * k1steps, jc1 = jc0 + k1steps;   // each half writes k1steps of the 2*k1steps chunks
+        // exp2(c2_k (d - mu_k)^2) with c2_k = 0 beyond the Gaussians: the bias column (k = Ng) becomes exactly 1, the
+        // padding columns meet zero weights, and rows of padded edges only have to be finite (their C is 0)
         for (int jc = jc0; jc < jc1; ++jc) {
           float v[8];
+          const float4* op = reinterpret_cast<const float4*>(s_offset + jc * 8);
+          const float4* cp2 = reinterpret_cast<const float4*>(s_c2 + jc * 8);
+          const float4 o0 = op[0], o1 = op[1], k0 = cp2[0], k1 = cp2[1];
+          const float off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+          const float ck[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int k = jc * 8 + j;
-            const float x = d - s_offset[k];
-            const float rv = ex2_approx(c2 * x * x);
-            v[j] = !live ? 0.0f : (k < Ng ? rv : (k == Ng ? 1.0f : 0.0f));
+            const float x = d - off[j];
+            v[j] = tc::fast_ex2(ck[j] * (x * x));
           }
           *reinterpret_cast<uint4*>(rowp + jc * 128) =
               make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),

@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
   // wbar | per group: r_ready, d1_ready, f_ready, dda_ready, h_ready, w_done, xbar
   __shared__ uint64_t bars[1 + NG * 7];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_offset[K1];
+  __shared__ __align__(16) float s_offset[K1];
+  __shared__ __align__(16) float s_c2[K1];
 
   uint8_t* sW1 = smem;
   uint8_t* sW2T = smem + W1_BYTES;
@@ -123,7 +124,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
     }
     tc::mbar_fence_init();
   }
-  if (tid < K1) s_offset[tid] = (tid < p.Ng) ? p.offset[tid] : 0.0f;
+  if (tid < K1) {
+    s_offset[tid] = (tid < p.Ng) ? p.offset[tid] : 0.0f;
+    s_c2[tid] = (tid < p.Ng) ? p.coeff_log2e : 0.0f;
+  }
   __syncwarp();
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   tc::tc_fence_before();
@@ -277,23 +281,29 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
         const bool live = e < ne;
         const float d = pre_d;
         if (q == 0) {
+          // pre-multiplied element offsets of the x' row and the g row this edge reads
           if (live) {
-            sMeta[e] = make_int2(staged ? (pre_src - cs) : pre_src, pre_dst);
+            sMeta[e] = make_int2((staged ? (pre_src - cs) : pre_src) * F, (g_staged ? (pre_dst - r0) : pre_dst) * F);
             sC[e] = 0.5f * (__cosf(d * kPi / cutoff) + 1.0f);
           } else {
-            sMeta[e] = make_int2(staged ? 0 : cs, r0);
+            sMeta[e] = make_int2((staged ? 0 : cs) * F, (g_staged ? 0 : r0) * F);
             sC[e] = 0.0f;
           }
         }
         uint8_t* rowp = sR + (e >> 3) * 1024 + (e & 7) * 16;
+        // exp2(c2_k (d - mu_k)^2), c2_k = 0 beyond the Gaussians (bias column = 1; padding columns meet zero weights
+        // in h and are discarded in dW1).  Rows of padded edges must be ZERO here: they enter dW1 through K = edges.
         for (int jc = q; jc < 2 * k1steps; jc += 4) {
           float v[8];
+          const float4* op = reinterpret_cast<const float4*>(s_offset + jc * 8);
+          const float4* cp2 = reinterpret_cast<const float4*>(s_c2 + jc * 8);
+          const float4 o0 = op[0], o1 = op[1], k0 = cp2[0], k1 = cp2[1];
+          const float off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+          const float ck[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int k = jc * 8 + j;
-            const float x = d - s_offset[k];
-            const float rv = ex2_approx(c2 * x * x);
-            v[j] = !live ? 0.0f : (k < Ng ? rv : (k == Ng ? 1.0f : 0.0f));
+            const float x = d - off[j];
+            v[j] = live ? tc::fast_ex2(ck[j] * (x * x)) : 0.0f;
           }
           *reinterpret_cast<uint4*>(rowp + jc * 128) = pack_bf16x8(v);
         }
@@ -315,9 +325,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int2 m = sMeta[c0 + j];
-            const float xv = staged ? __bfloat162float(sXb[m.x * F + chan])
-                                    : __bfloat162float(p.xprime[(int64_t)m.x * F + chan]);
-            const float gv = g_staged ? sGr[(m.y - r0) * F + chan] : __ldg(p.g + (int64_t)m.y * F + chan);
+            const float xv = staged ? __bfloat162float(sXb[m.x + chan]) : __bfloat162float(p.xprime[(int64_t)m.x + chan]);
+            const float gv = g_staged ? sGr[m.y + chan] : __ldg(p.g + (int64_t)m.y + chan);
             const float df = (c0 + j < ne) ? gv * xv : 0.0f;
             db2 = fmaf(df, sC[c0 + j], db2);
             v[j] = df;
@@ -346,9 +355,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float x = v[j];
-            const float t = ex2_approx(-1.4426950408889634f * fabsf(x));
+            const float t = tc::fast_ex2(-1.4426950408889634f * fabsf(x));
             const float inv = __fdividef(1.0f, 1.0f + t);
-            a[j] = c[j] * (fmaxf(x, 0.0f) + __logf(1.0f + t) - kLn2);
+            a[j] = c[j] * fmaf(tc::fast_lg2(1.0f + t) - 1.0f, kLn2, fmaxf(x, 0.0f));
             s[j] = c[j] * (x >= 0.0f ? inv : t * inv);
           }
           *reinterpret_cast<uint4*>(sA + chan * 16 + (c0 >> 3) * 2048) = pack_bf16x8(a);

@@ -34,8 +34,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
+  // back off between polls: a spinning warp otherwise steals issue slots from the warps it is waiting for
+  while (!mbar_try_wait(bar, parity)) __nanosleep(64);
+}
+
+// MUFU.EX2 / MUFU.LG2 without the denormal fix-up code the non-ftz intrinsics carry
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // generic-proxy writes to shared memory -> visible to the async proxy (UMMA / TMA reads)
