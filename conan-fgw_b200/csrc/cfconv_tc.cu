@@ -59,6 +59,7 @@ struct FwdParams {
   float coeff_log2e;       // coeff * log2(e)
   float cutoff;
   int Ng;
+  long long* dbg;          // optional phase timestamps (CTA 0, pipeline 0): 8 x clock64 per tile
 };
 
 struct TileInfo {
@@ -223,6 +224,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
       const int cs = tile.cs, cn = tile.cn;
       const bool staged = cn <= XP_CAP;
 
+      const bool rec = p.dbg && blockIdx.x == 0 && g == 0 && tt == 0 && it < 32;
+      if (rec) p.dbg[it * 8 + 0] = clock64();
       tc::named_bar_sync(1 + g, GT);  // previous tile of this group fully consumed (sB, sX, sMeta, TMEM)
 
       bool x_wait = false;
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
       if (tt <= nrows) sRow[tt] = pre_row - tile.e0;
       tc::named_bar_sync(1 + g, GT);
 
+      if (rec) p.dbg[it * 8 + 1] = clock64();
       // ---- per-edge metadata + Gaussian expansion -> B1 (K-major [edge, 64]) ----
       if (h == 0) {   // warps 0..3 of the group: one edge slot per thread
         bool last = false;
@@ -283,6 +287,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
                          tc::pack_bf16x2(v[6], v[7]));
         }
       }
+      if (rec) p.dbg[it * 8 + 2] = clock64();
       tc::fence_proxy_async();
       tc::mbar_arrive(b1ready);
 
@@ -299,6 +304,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
       // ---- epilogue 1: a' = C * ssp(D1) -> B2 (MN-major [144, edge]) ----
       tc::mbar_wait(d1ready, par);
       tc::tc_fence_after();
+      if (rec) p.dbg[it * 8 + 3] = clock64();
       {
         uint8_t* colp = sB + chan * 16;  // k = chan: (k/8)*128 + (k%8)*16 = k*16
         const int cb = h ? csplit : 0, ce = h ? npad : csplit;
@@ -334,6 +340,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
           *reinterpret_cast<uint4*>(sB + ec * A2_SBO + (128 + kr) * 16) = q;
         }
       }
+      if (rec) p.dbg[it * 8 + 4] = clock64();
       tc::tc_fence_before();
       tc::fence_proxy_async();
       tc::mbar_arrive(b2ready);
@@ -341,6 +348,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
       // ---- epilogue 2: gather x'_src, multiply, reduce per target row (CSR order) ----
       tc::mbar_wait(d2ready, par);
       tc::tc_fence_after();
+      if (rec) p.dbg[it * 8 + 5] = clock64();
       if (x_wait) {
         tc::mbar_wait(xbar, xloads & 1);
         ++xloads;
@@ -396,6 +404,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
         if (!h && ce > 0 && ce <= ne && ce < npad + 1 && !((sEnd[(ce - 1) >> 4] >> ((ce - 1) & 15)) & 1u) && (ce - 1) < ne)
           atomicAdd(aggc + (int64_t)sDst[ce - 1] * F, acc);
       }
+      if (rec) p.dbg[it * 8 + 6] = clock64();
       tc::tc_fence_before();
       cur = nxt;
     }
@@ -434,6 +443,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ W1, const float* _
 }  // namespace cmp
 
 using namespace cmp;
+
+// debug hook: device buffer of 32 x 8 int64 phase timestamps filled by CTA 0 / pipeline 0 of the next launches
+static long long* g_fwd_dbg = nullptr;
+extern "C" void cmp_debug_set_fwd_timestamps(void* buf) { g_fwd_dbg = reinterpret_cast<long long*>(buf); }
 
 extern "C" int cmp_cfconv_tc_supported(int num_filters, int num_gaussians) {
   return num_filters == F && num_gaussians >= 1 && num_gaussians < K1;
@@ -497,6 +510,7 @@ extern "C" int cmp_cfconv_fused_fwd(const float* xprime, const float* dist, cons
   p.coeff_log2e = coeff * 1.4426950408889634f;
   p.cutoff = cutoff;
   p.Ng = num_gaussians;
+  p.dbg = g_fwd_dbg;
   cfconv_fused_fwd_kernel<<<sm_count(), CTA_THREADS, SMEM_BYTES, st>>>(p);
   CMP_LAUNCH_CHECK("cmp_cfconv_fused_fwd");
   return CMP_OK;

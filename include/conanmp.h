@@ -324,6 +324,10 @@ int cmp_vis_edge_update_bwd(const float* gw, const float* wt, const float* ws, c
                             const int32_t* col_t, const int32_t* eid_t, int64_t N, int H, float* g_wt,
                             float* g_ws, cmp_stream_t stream);
 
+/* Debug hook: when non-NULL, CTA 0 / pipeline 0 of cmp_cfconv_fused_fwd stores 8 clock64() phase
+ * timestamps per tile (first 32 tiles) into this device buffer of 256 int64. */
+void cmp_debug_set_fwd_timestamps(void* buf);
+
 /* Single-tile UMMA probe used by the tests to pin descriptor / TMEM conventions. */
 int cmp_debug_umma_gemm(const void* a_img, int64_t a_bytes, const void* b_img, int64_t b_bytes,
                         float* D, int N, int K, int fmt, int a_mn, int b_mn, int a_lbo, int a_sbo,
