@@ -82,7 +82,9 @@ class RegressionStep:
     def __init__(self, backbone, hidden_half: int, num_conformers: int, lr: float = 1e-3, group=None):
         self.backbone = backbone
         dev = next(backbone.parameters()).device
-        self.head = torch.nn.Linear(hidden_half, 1).to(dev)
+        from .nn import Linear
+
+        self.head = Linear(hidden_half, 1).to(dev)     # regression head (schnet_based_models.py:17-29) on cmp_gemm_f32
         self.K = int(num_conformers)
         self.flat = FlatParameters([backbone, self.head])
         self.lr = lr
@@ -90,7 +92,7 @@ class RegressionStep:
 
     def loss(self, z, pos, batch, targets, num_graphs):
         emb = self.backbone(z, pos, batch, num_graphs=num_graphs)          # [G, H/2]
-        mol = emb.view(-1, self.K, emb.size(1)).mean(dim=1)                  # conformers of a molecule are consecutive
+        mol = ops.conformers_mean(emb, self.K)                               # conformers of a molecule are consecutive
         pred = self.head(mol)
         return torch.nn.functional.mse_loss(pred, targets)
 

@@ -407,6 +407,27 @@ def segment_sum(x, seg_ptr, G):
     return _SegmentSumFn.apply(x, seg_ptr, int(G))
 
 
+_uniform_seg_cache = {}
+
+
+def conformers_mean(x, num_conformers: int):
+    """Mean over the K consecutive conformers of each molecule: [B*K, C] -> [B, C].
+
+    Replaces ``create_aggregation_index`` (a Python loop + host->device copy every step,
+    ``conan_fgw/src/model/common.py:414-423``) and ``conformers_mean_aggr``
+    (``schnet_based_models.py:242``): the index is implicit because conformers of a molecule are consecutive."""
+    G = x.shape[0]
+    K = int(num_conformers)
+    if G % K != 0:
+        raise ValueError("conformers_mean: the number of conformers must be a multiple of K")
+    key = (G, K, x.device)
+    seg = _uniform_seg_cache.get(key)
+    if seg is None:
+        seg = torch.arange(0, G + 1, K, dtype=torch.int32, device=x.device)
+        _uniform_seg_cache[key] = seg
+    return segment_sum(x, seg, G // K) * (1.0 / K)
+
+
 def segments_from_batch(batch, num_graphs=None):
     from .graph import num_graphs_of
 

@@ -147,3 +147,16 @@ def test_padding_atom_and_bad_atomic_number():
     z[1] = 100
     with pytest.raises(ValueError):
         c(z.to(DEV), b.pos.to(DEV), b.batch.to(DEV))
+
+
+def test_conformer_mean_and_regression_step_glue():
+    """Row (f)-1 of SURVEY.md 8: the K-conformer mean (common.py:414-423, schnet_based_models.py:242)."""
+    from conan_fgw_b200 import ops
+    x = torch.randn(12, 7, device=DEV, requires_grad=True)
+    y = ops.conformers_mean(x, 3)
+    want = x.view(4, 3, 7).mean(dim=1)
+    assert rel_err(y, want) < 1e-6
+    (g,) = torch.autograd.grad(y.sum(), x)
+    assert torch.allclose(g, torch.full_like(g, 1.0 / 3))
+    with pytest.raises(ValueError):
+        ops.conformers_mean(x, 5)
