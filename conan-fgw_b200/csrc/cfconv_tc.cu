@@ -27,8 +27,8 @@ constexpr int F = 128;           // filter channels = UMMA M
 constexpr int TILE_E = 128;      // edges per tile   = max UMMA N
 constexpr int K1 = 64;           // Gaussians padded (+ bias column)
 constexpr int K2 = 144;          // hidden channels + (cutoff, bias) row, padded to 16
-constexpr int XP_CAP = 80;       // atoms of a conformer staged in shared memory
-constexpr int NG = 2;            // pipelines ("groups") per CTA
+constexpr int XP_CAP = 40;       // atoms of a conformer staged in shared memory
+constexpr int NG = 3;            // pipelines ("groups") per CTA
 constexpr int GT = 256;          // compute threads per group (8 warps: 2 per TMEM lane quarter)
 constexpr int CTA_THREADS = NG * GT + NG * 32;
 
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
         tc::bulk_g2s(sW2, p.weights + W1_BYTES, W2_BYTES, wbar);
       }
       uint8_t* sB = smem + W1_BYTES + W2_BYTES + g * GROUP_BYTES;
-      const uint32_t d1 = tmem_base + g * 256, d2 = d1 + 128;
+      const uint32_t d1 = tmem_base + g * 128, d2 = d1;
       const uint32_t aW1 = tc::smem_u32(sW1), aW2 = tc::smem_u32(sW2), aB = tc::smem_u32(sB);
       const int64_t u = (int64_t)blockIdx.x * NG + g;
       const int64_t t0 = u * T / U, t1 = (u + 1) * T / U;
@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
     float* sC = reinterpret_cast<float*>(sB + OFF_C);
     int* sRow = reinterpret_cast<int*>(sB + OFF_ROW);
     uint32_t* sEnd = reinterpret_cast<uint32_t*>(sB + OFF_END);
-    const uint32_t d1 = tmem_base + g * 256 + ((uint32_t)(wq * 32) << 16);
-    const uint32_t d2 = d1 + 128;
+    const uint32_t d1 = tmem_base + g * 128 + ((uint32_t)(wq * 32) << 16);
+    const uint32_t d2 = d1;
     const int64_t u = (int64_t)blockIdx.x * NG + g;
     const int64_t t0 = u * T / U, t1 = (u + 1) * T / U;
     const float c2 = p.coeff_log2e, cutoff = p.cutoff;
