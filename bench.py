@@ -170,6 +170,49 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def visnet_secondary(cmp, dev, threads):
+    """BASELINE.json configs[2] for the record: ConAN-ViSNet (hidden 128, 6 layers, lmax 1), FreeSolv-shaped batch
+    (32 molecules x 5 conformers x 18 atoms), fwd+bwd, exact-fp32 CUDA kernels vs the CPU oracle (= a restatement of
+    the reference's own vendored file, pinned to it by tests/golden/visnet_ref.pt)."""
+    from oracle import visnet as ovis
+
+    b = cmp.synthetic.make_config_batch("cfg3_freesolv_visnet")
+    G = b.num_graphs
+    torch.manual_seed(0)
+    model = cmp.ViSNet(None, hidden_channels=128).to(dev)
+    d = b.to(dev)
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        model(d.z, d.pos, d.batch, num_graphs=G).pow(2).mean().backward()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    torch.set_num_threads(threads)
+    ref = ovis.ViSNet(None, hidden_channels=128)
+
+    def cpu_step():
+        ref.zero_grad(set_to_none=True)
+        ref(b.z, b.pos, b.batch).pow(2).mean().backward()
+
+    cpu_step()
+    t0 = time.perf_counter()
+    cpu_step()
+    cpu_s = time.perf_counter() - t0
+    return {"workload": "cfg3_freesolv_visnet", "metric": "ConAN-ViSNet conformers/sec fwd+bwd", "value": G / (ms * 1e-3),
+            "unit": UNIT, "ms_per_step": ms, "dtype": "f32", "cuda_graph": False,
+            "cpu_baseline": {"value": G / cpu_s, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "the full 160-conformer batch, 1 warm-up + 1 timed fwd+bwd of oracle.visnet.ViSNet"}}
+
+
 # -----------------------------------------------------------------------------------------------
 # GPU path
 # -----------------------------------------------------------------------------------------------
@@ -361,6 +404,8 @@ def run_ours(args):
                     "sample": f"{CPU_SAMPLE_MOLECULES} of 128 molecules x 5 conformers x 27 atoms, 1 warm-up + 2 timed "
                               f"fwd+bwd+Adam steps of oracle.schnet.SchNetNoSum ({cpu_step:.2f} s/step)"}
 
+    visnet = visnet_secondary(cmp, dev, threads) if world == 1 else None
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -374,7 +419,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
-        "other_mode": other_mode,
+        "other_mode": other_mode, "visnet": visnet,
         "tolerance": {"fp32": "1e-5 relative vs oracle (tests/test_gpu_schnet.py)",
                       "bf16": "5e-3 relative on embeddings, 2e-2 on gradients vs oracle (tests/test_gpu_fused.py)"},
     }

@@ -38,26 +38,41 @@ __device__ __forceinline__ void convert_tile(const float* __restrict__ X, int64_
   const int nchunk = C >> 3;
   const int cbs = (nchunk + 3) >> 2;
   const int al = lane & 7, cl = lane >> 3;
-  for (int wi = warp; wi < 16 * cbs; wi += CW) {
+  constexpr int UN = 4;   // warp-iterations whose global loads are issued back to back (memory-level parallelism)
+  const int total = 16 * cbs;
+  for (int base = warp; base < total; base += CW * UN) {
+   float4 P0[UN], P1[UN], Y0[UN], Y1[UN];
+   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+   for (int u = 0; u < UN; ++u) {
+     const int wi = base + u * CW;
+     const int ab = wi / cbs, cb = wi - ab * cbs;
+     const int a = ab * 8 + al, chunk = cb * 4 + cl;
+     const int64_t row = m0 + a;
+     P0[u] = P1[u] = zero4;
+     Y0[u] = Y1[u] = make_float4(1e30f, 1e30f, 1e30f, 1e30f);   // exp(-y) = 0: factor 1
+     if (wi < total && chunk < nchunk && row < M) {
+       const float4* src = reinterpret_cast<const float4*>(X + row * ld + chunk * 8);
+       P0[u] = __ldg(src);
+       P1[u] = __ldg(src + 1);
+       if (Ysaved) {
+         const float4* ys = reinterpret_cast<const float4*>(Ysaved + row * ldys + chunk * 8);
+         Y0[u] = __ldg(ys);
+         Y1[u] = __ldg(ys + 1);
+       }
+     }
+   }
+#pragma unroll
+   for (int u = 0; u < UN; ++u) {
+    const int wi = base + u * CW;
     const int ab = wi / cbs, cb = wi - ab * cbs;
     const int a = ab * 8 + al, chunk = cb * 4 + cl;
-    if (chunk >= nchunk) continue;
-    float v[8];
-    const int64_t row = m0 + a;
-    if (row < M) {
-      const float4* src = reinterpret_cast<const float4*>(X + row * ld + chunk * 8);
-      const float4 p0 = __ldg(src), p1 = __ldg(src + 1);
-      v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
-      if (Ysaved) {
-        const float4* ys = reinterpret_cast<const float4*>(Ysaved + row * ldys + chunk * 8);
-        const float4 y0 = __ldg(ys), y1 = __ldg(ys + 1);
-        const float y[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    if (wi >= total || chunk >= nchunk) continue;
+    float v[8] = {P0[u].x, P0[u].y, P0[u].z, P0[u].w, P1[u].x, P1[u].y, P1[u].z, P1[u].w};
+    if (Ysaved) {
+      const float y[8] = {Y0[u].x, Y0[u].y, Y0[u].z, Y0[u].w, Y1[u].x, Y1[u].y, Y1[u].z, Y1[u].w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] *= 1.0f - 0.5f * ex2_approx(-1.4426950408889634f * y[j]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+      for (int j = 0; j < 8; ++j) v[j] *= 1.0f - 0.5f * ex2_approx(-1.4426950408889634f * y[j]);
     }
     float l[8];
 #pragma unroll
@@ -71,6 +86,7 @@ __device__ __forceinline__ void convert_tile(const float* __restrict__ X, int64_
                                                       tc::pack_bf16x2(v[4], v[5]), tc::pack_bf16x2(v[6], v[7]));
     *reinterpret_cast<uint4*>(lo + off) = make_uint4(tc::pack_bf16x2(l[0], l[1]), tc::pack_bf16x2(l[2], l[3]),
                                                       tc::pack_bf16x2(l[4], l[5]), tc::pack_bf16x2(l[6], l[7]));
+   }
   }
   if (ones_chunk >= 0) {
     // two extra chunks (16 channels): chunk ones_chunk = {1,0,...}, ones_chunk + 1 = 0
@@ -166,18 +182,20 @@ __global__ void __launch_bounds__(NT, 1) node_gemm_fwd_kernel(const FwdParams p)
       tc::tc_fence_after();
       for (int c0 = h * 64; c0 < h * 64 + 64; c0 += 16) {
         if (m0 + c0 >= p.M) break;
-        float v[16];
+        float v[16], r[16];
         tc::tmem_ld16(tD + c0, v);
+        const bool live = chan < p.Nout;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {   // residual rows are fetched while the TMEM load is in flight
+          const int64_t row = m0 + c0 + j;
+          r[j] = (p.residual && live && row < p.M) ? __ldg(p.residual + row * p.ldr + chan) : 0.0f;
+        }
         tc::tmem_wait_ld();
-        if (chan < p.Nout) {
+        if (live) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int64_t row = m0 + c0 + j;
-            if (row < p.M) {
-              float y = apply_act(v[j] + bias, p.act);
-              if (p.residual) y += p.residual[row * p.ldr + chan];
-              p.Y[row * p.ldy + chan] = y;
-            }
+            if (row < p.M) p.Y[row * p.ldy + chan] = apply_act(v[j] + bias, p.act) + r[j];
           }
         }
       }
