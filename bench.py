@@ -397,14 +397,15 @@ def run_ours(args):
         "step_tflops": algorithmic_flops(N, E) * args.steps / (total_ms * 1e-3) / 1e12,
     }
 
-    # CPU baseline: bounded sample of the same workload on this host's cores
+    # ViSNet secondary line first: the CPU legs below leave OpenMP workers spinning, which slows kernel launching
     threads = os.cpu_count() or 1
+    visnet = visnet_secondary(cmp, dev, threads) if world == 1 else None
+
+    # CPU baseline: bounded sample of the same workload on this host's cores
     cpu_value, cpu_step = time_cpu(CPU_SAMPLE_MOLECULES, 2, 1, threads)
     cpu_baseline = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
                     "sample": f"{CPU_SAMPLE_MOLECULES} of 128 molecules x 5 conformers x 27 atoms, 1 warm-up + 2 timed "
                               f"fwd+bwd+Adam steps of oracle.schnet.SchNetNoSum ({cpu_step:.2f} s/step)"}
-
-    visnet = visnet_secondary(cmp, dev, threads) if world == 1 else None
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
