@@ -18,7 +18,8 @@
 namespace cmp {
 namespace {
 
-constexpr int TM = 128;            // atoms per tile
+constexpr int TM = 128;            // atoms per tile of the weight-gradient kernel (UMMA K runs over atoms)
+constexpr int TMF = 64;            // atoms per tile of the forward / dX kernel: 2 CTAs per SM hide each other's loads
 constexpr int CW = 8;              // compute warps
 constexpr int NT = CW * 32 + 32;   // + 1 MMA warp
 constexpr int MAXC = 128;          // max channels (K or Nout)
@@ -32,6 +33,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // fp32 tile [TM atoms, C channels] -> bf16 hi / lo K-major images (rows = atoms):
 //   byte(a, c) = (a%8)*16 + (c%8)*2 + (a/8)*sbo + (c/8)*128
 // when ones_chunk >= 0 that 16-byte chunk of every row is set to {1, 0, 0, ...} (hi) / 0 (lo).
+template <int ROWS>
 __device__ __forceinline__ void convert_tile(const float* __restrict__ X, int64_t ld, const float* __restrict__ Ysaved,
                                              int64_t ldys, int64_t m0, int64_t M, int C, uint32_t sbo, uint8_t* hi,
                                              uint8_t* lo, int ones_chunk, int warp, int lane) {
@@ -39,7 +41,7 @@ __device__ __forceinline__ void convert_tile(const float* __restrict__ X, int64_
   const int cbs = (nchunk + 3) >> 2;
   const int al = lane & 7, cl = lane >> 3;
   constexpr int UN = 4;   // warp-iterations whose global loads are issued back to back (memory-level parallelism)
-  const int total = 16 * cbs;
+  const int total = (ROWS / 8) * cbs;
   for (int base = warp; base < total; base += CW * UN) {
    float4 P0[UN], P1[UN], Y0[UN], Y1[UN];
    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -91,7 +93,7 @@ __device__ __forceinline__ void convert_tile(const float* __restrict__ X, int64_
   if (ones_chunk >= 0) {
     // two extra chunks (16 channels): chunk ones_chunk = {1,0,...}, ones_chunk + 1 = 0
     const int t = warp * 32 + lane;
-    for (int item = t; item < TM * 2; item += CW * 32) {
+    for (int item = t; item < ROWS * 2; item += CW * 32) {
       const int a = item >> 1, which = item & 1;
       const uint32_t off = (a & 7) * 16 + (a >> 3) * sbo + (ones_chunk + which) * 128;
       const bool live = (m0 + a) < M && which == 0;
@@ -116,18 +118,18 @@ struct FwdParams {
   int K, Nout, act;
 };
 
-__global__ void __launch_bounds__(NT, 1) node_gemm_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(NT, 2) node_gemm_fwd_kernel(const FwdParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bars[3];   // wbar, xready, dready
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int K = p.K;
-  const uint32_t img_bytes = TM * K * 2;
+  const uint32_t w_bytes = 128 * K * 2, x_bytes = TMF * K * 2;
   const uint32_t sbo = (K >> 3) * 128;
   uint8_t* sWh = smem;
-  uint8_t* sWl = smem + img_bytes;
-  uint8_t* sXh = smem + 2 * img_bytes;
-  uint8_t* sXl = smem + 3 * img_bytes;
+  uint8_t* sWl = smem + w_bytes;
+  uint8_t* sXh = smem + 2 * w_bytes;
+  uint8_t* sXl = sXh + x_bytes;
 
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
@@ -136,20 +138,20 @@ __global__ void __launch_bounds__(NT, 1) node_gemm_fwd_kernel(const FwdParams p)
     tc::mbar_fence_init();
   }
   __syncwarp();
-  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 128);
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const int64_t ntiles = (p.M + TM - 1) / TM;
+  const int64_t ntiles = (p.M + TMF - 1) / TMF;
 
   if (warp == CW) {
     if (lane == 0) {
-      tc::mbar_arrive_expect_tx(&bars[0], 2 * img_bytes);
-      tc::bulk_g2s(sWh, p.w_img, 2 * img_bytes, &bars[0]);
+      tc::mbar_arrive_expect_tx(&bars[0], 2 * w_bytes);
+      tc::bulk_g2s(sWh, p.w_img, 2 * w_bytes, &bars[0]);
       tc::mbar_wait(&bars[0], 0);
       const uint32_t aWh = tc::smem_u32(sWh), aWl = tc::smem_u32(sWl), aXh = tc::smem_u32(sXh), aXl = tc::smem_u32(sXl);
-      const uint32_t idesc = tc::umma_idesc_f16(128, TM, 1, 0, 0);
+      const uint32_t idesc = tc::umma_idesc_f16(128, TMF, 1, 0, 0);
       uint32_t it = 0;
       for (int64_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
         tc::mbar_wait(&bars[1], it & 1);
@@ -173,14 +175,14 @@ __global__ void __launch_bounds__(NT, 1) node_gemm_fwd_kernel(const FwdParams p)
     const uint32_t tD = tmem_base + ((uint32_t)(wq * 32) << 16);
     uint32_t it = 0;
     for (int64_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
-      const int64_t m0 = ti * TM;
+      const int64_t m0 = ti * TMF;
       if (it > 0) tc::named_bar_sync(1, CW * 32);   // everyone finished reading TMEM / previous images consumed
-      convert_tile(p.X, p.ldx, p.saved_y, p.ldys, m0, p.M, K, sbo, sXh, sXl, -1, warp, lane);
+      convert_tile<TMF>(p.X, p.ldx, p.saved_y, p.ldys, m0, p.M, K, sbo, sXh, sXl, -1, warp, lane);
       tc::fence_proxy_async();
       tc::mbar_arrive(&bars[1]);
       tc::mbar_wait(&bars[2], it & 1);
       tc::tc_fence_after();
-      for (int c0 = h * 64; c0 < h * 64 + 64; c0 += 16) {
+      for (int c0 = h * (TMF / 2); c0 < (h + 1) * (TMF / 2); c0 += 16) {
         if (m0 + c0 >= p.M) break;
         float v[16], r[16];
         tc::tmem_ld16(tD + c0, v);
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(NT, 1) node_gemm_fwd_kernel(const FwdParams p)
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base, 128);
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 64);
 }
 
 struct DwParams {
@@ -273,8 +275,8 @@ __global__ void __launch_bounds__(NT, 1) node_gemm_dw_kernel(const DwParams p) {
     for (int64_t ti = t0; ti < t1; ++ti, ++it) {
       const int64_t m0 = ti * TM;
       if (it > 0) tc::mbar_wait(&bars[1], (it - 1) & 1);   // previous MMAs done reading the images
-      convert_tile(p.dY, p.lddy, p.saved_y, p.ldys, m0, p.M, Nout, sbo_y, sYh, sYl, -1, warp, lane);
-      convert_tile(p.X, p.ldx, nullptr, 0, m0, p.M, K, sbo_x, sXh, sXl, K >> 3, warp, lane);
+      convert_tile<TM>(p.dY, p.lddy, p.saved_y, p.ldys, m0, p.M, Nout, sbo_y, sYh, sYl, -1, warp, lane);
+      convert_tile<TM>(p.X, p.ldx, nullptr, 0, m0, p.M, K, sbo_x, sXh, sXl, K >> 3, warp, lane);
       tc::fence_proxy_async();
       tc::mbar_arrive(&bars[0]);
     }
@@ -373,16 +375,17 @@ extern "C" int cmp_node_gemm_fwd(const float* X, int64_t ldx, const float* saved
               CMP_EINVAL, "cmp_node_gemm_fwd: operands must be 16-byte aligned with ld % 4 == 0");
   CMP_REQUIRE(act == CMP_ACT_NONE || act == CMP_ACT_SSP || act == CMP_ACT_SILU, CMP_EINVAL, "cmp_node_gemm_fwd: bad act");
   CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED, "cmp_node_gemm_fwd: needs an sm_100 device (tcgen05)");
-  const size_t smem = (size_t)4 * TM * K * 2;
-  if (cudaFuncSetAttribute(node_gemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * TM * MAXC * 2) !=
+  const size_t smem = (size_t)2 * 128 * K * 2 + (size_t)2 * TMF * K * 2;
+  if (cudaFuncSetAttribute(node_gemm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           2 * 128 * MAXC * 2 + 2 * TMF * MAXC * 2) !=
       cudaSuccess) {
     (void)cudaGetLastError();
     set_error("cmp_node_gemm_fwd: cannot opt in to shared memory");
     return CMP_ECUDA;
   }
   FwdParams p{X, ldx, saved_y, ldys, reinterpret_cast<const uint8_t*>(w_img), bias, residual, ldr, Y, ldy, M, K, Nout, act};
-  const int64_t ntiles = ceil_div(M, TM);
-  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  const int64_t ntiles = ceil_div(M, TMF);
+  const int grid = (int)(ntiles < 2 * sm_count() ? ntiles : 2 * sm_count());
   node_gemm_fwd_kernel<<<grid, NT, smem, as_stream(stream)>>>(p);
   CMP_LAUNCH_CHECK("cmp_node_gemm_fwd");
   return CMP_OK;
