@@ -150,14 +150,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
         const int npad = (ne + 15) & ~15;
         if (ti + 1 < t1) ne = load_tile(p.tiles, ti + 1).ne;
         const uint32_t par = it & 1;
-        tc::mbar_wait(b1ready, par);
+        tc::mbar_wait_spin(b1ready, par);
         tc::tc_fence_after();
         const uint32_t idesc1 = tc::umma_idesc_f16(F, npad, 1, 0, 0);
         for (int ks = 0; ks < k1steps; ++ks)
           tc::umma_f16(d1, tc::umma_smem_desc(aW1 + ks * 256, 128, B1_SBO), tc::umma_smem_desc(aB + ks * 256, 128, B1_SBO),
                        idesc1, ks > 0);
         tc::umma_commit(d1ready);
-        tc::mbar_wait(b2ready, par);
+        tc::mbar_wait_spin(b2ready, par);
         tc::tc_fence_after();
         const uint32_t idesc2 = tc::umma_idesc_f16(F, npad, 1, 0, 1);
 #pragma unroll

@@ -64,6 +64,7 @@ struct BwdParams {
   float coeff_log2e;
   float cutoff;
   int Ng;
+  long long* dbg;                 // optional phase timestamps (CTA 0, pipeline 0): 12 x clock64 per tile
 };
 
 struct TileInfo {
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
         if (ti + 1 < t1) ne = load_tile(p.tiles, ti + 1).ne;
         const uint32_t par = it & 1;
         // h = W1aug * rbf^T
-        tc::mbar_wait(b + 0, par);
+        tc::mbar_wait_spin(b + 0, par);
         tc::tc_fence_after();
         const uint32_t id1 = tc::umma_idesc_f16(F, npad, 1, 0, 0);
         for (int ks = 0; ks < k1steps; ++ks)
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
                        ks > 0);
         tc::umma_commit(b + 1);
         // da' = W2^T * dF      (dF image read as MN-major [K=f, N=e]: LBO 128, SBO 2048)
-        tc::mbar_wait(b + 2, par);
+        tc::mbar_wait_spin(b + 2, par);
         tc::tc_fence_after();
         const uint32_t id2 = tc::umma_idesc_f16(F, npad, 1, 0, 1);
 #pragma unroll
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
                        ks > 0);
         tc::umma_commit(b + 3);
         // weight gradients, K = edges of the tile (images read as K-major [rows=channel, K=e]: SBO 128, LBO 2048)
-        tc::mbar_wait(b + 4, par);
+        tc::mbar_wait_spin(b + 4, par);
         tc::tc_fence_after();
         const uint32_t id3 = tc::umma_idesc_f16(F, F, 1, 0, 0);
         const uint32_t id4 = tc::umma_idesc_f16(F, K1, 1, 0, 1);
@@ -260,8 +261,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
       const int r0 = tile.row_begin;
       const bool g_staged = (tile.row_end - tile.row_begin) <= GROWS;
 
+      const bool rec = p.dbg && blockIdx.x == 0 && g == 0 && tt == 0 && it < 20;
+      if (rec) p.dbg[it * 12 + 0] = clock64();
       // the previous tile's weight-gradient MMAs must be done reading the images before they are rewritten
       if (it > 0) tc::mbar_wait(b + 5, (it - 1) & 1);
+      if (rec) p.dbg[it * 12 + 1] = clock64();
 
       bool x_wait = false;
       if (staged && cs != staged_conf) {
@@ -308,6 +312,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
           *reinterpret_cast<uint4*>(rowp + jc * 128) = pack_bf16x8(v);
         }
       }
+      if (rec) p.dbg[it * 12 + 2] = clock64();
       tc::fence_proxy_async();
       tc::mbar_arrive(b + 0);
       if (have_next) prefetch(nxt);
@@ -317,27 +322,58 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
         ++xloads;
       }
 
+      if (rec) p.dbg[it * 12 + 3] = clock64();
       // ---- dF[f, e] = g[dst_e, f] * x'[src_e, f]  ->  dF image (runs while the tensor core computes h) ----
       {
+        // all shared-memory operands of 8 edges are fetched before any arithmetic (no dependent-load chains), and the
+        // staged / fallback decision is hoisted out of the loop
         const int cb = h * 32, ce = min(npad, h * 32 + 32);
+        const __nv_bfloat16* xs_s = sXb + chan;
+        const float* gs_s = sGr + chan;
+        const __nv_bfloat16* xs_g = p.xprime + chan;
+        const float* gs_g = p.g + chan;
         for (int c0 = cb; c0 < ce; c0 += 8) {
+          int2 m[8];
+          const int4* mp = reinterpret_cast<const int4*>(sMeta + c0);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const int4 mm = mp[k4];
+            m[2 * k4] = make_int2(mm.x, mm.y);
+            m[2 * k4 + 1] = make_int2(mm.z, mm.w);
+          }
+          const float4 c0v = *reinterpret_cast<const float4*>(sC + c0), c1v = *reinterpret_cast<const float4*>(sC + c0 + 4);
+          const float cc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+          float xv[8], gv[8];
+          if (staged) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xv[j] = __bfloat162float(xs_s[m[j].x]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xv[j] = __bfloat162float(xs_g[m[j].x]);
+          }
+          if (g_staged) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gv[j] = gs_s[m[j].y];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gv[j] = __ldg(gs_g + m[j].y);
+          }
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int2 m = sMeta[c0 + j];
-            const float xv = staged ? __bfloat162float(sXb[m.x + chan]) : __bfloat162float(p.xprime[(int64_t)m.x + chan]);
-            const float gv = g_staged ? sGr[m.y + chan] : __ldg(p.g + (int64_t)m.y + chan);
-            const float df = (c0 + j < ne) ? gv * xv : 0.0f;
-            db2 = fmaf(df, sC[c0 + j], db2);
-            v[j] = df;
+            // padded edges carry C = 0 and valid (row 0) offsets; their dF must still be exactly 0 (K = edges)
+            v[j] = (c0 + j < ne) ? gv[j] * xv[j] : 0.0f;
+            db2 = fmaf(v[j], cc[j], db2);
           }
           *reinterpret_cast<uint4*>(sF + chan * 16 + (c0 >> 3) * 2048) = pack_bf16x8(v);
         }
       }
 
+      if (rec) p.dbg[it * 12 + 4] = clock64();
       // ---- epilogue 1: a' = C ssp(h), S = C sigmoid(h) -> images ----
       tc::mbar_wait(b + 1, par);
       tc::tc_fence_after();
+      if (rec) p.dbg[it * 12 + 5] = clock64();
       {
         const int cb = h * 32, ce = min(npad, h * 32 + 32);
         for (int c0 = cb; c0 < ce; c0 += 16) {
@@ -366,6 +402,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
           *reinterpret_cast<uint4*>(sS + chan * 16 + ((c0 >> 3) + 1) * 2048) = pack_bf16x8(s + 8);
         }
       }
+      if (rec) p.dbg[it * 12 + 6] = clock64();
       tc::tc_fence_before();
       tc::fence_proxy_async();
       tc::mbar_arrive(b + 2);
@@ -373,6 +410,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
       // ---- epilogue 3: dh = da' * S -> dh image (in place over S) ----
       tc::mbar_wait(b + 3, par);
       tc::tc_fence_after();
+      if (rec) p.dbg[it * 12 + 7] = clock64();
       {
         const int cb = h * 32, ce = min(npad, h * 32 + 32);
         for (int c0 = cb; c0 < ce; c0 += 16) {
@@ -393,6 +431,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
           *sp1 = pack_bf16x8(v + 8);
         }
       }
+      if (rec) p.dbg[it * 12 + 8] = clock64();
       tc::tc_fence_before();
       tc::fence_proxy_async();
       tc::mbar_arrive(b + 4);
@@ -561,6 +600,9 @@ __global__ void flat_tiles_fill_kernel(const int32_t* __restrict__ conf_edge_ptr
 
 using namespace cmp;
 
+static long long* g_bwd_dbg = nullptr;
+extern "C" void cmp_debug_set_bwd_timestamps(void* buf) { g_bwd_dbg = reinterpret_cast<long long*>(buf); }
+
 extern "C" int cmp_csr_expand_rows(const int32_t* rowptr, int64_t N, int32_t* erow, cmp_stream_t stream) {
   CMP_REQUIRE(N >= 0, CMP_EINVAL, "cmp_csr_expand_rows: negative size");
   if (N == 0) return CMP_OK;
@@ -674,6 +716,7 @@ extern "C" int cmp_cfconv_fused_bwd_weights(const float* g, const void* xprime_b
   p.coeff_log2e = coeff * 1.4426950408889634f;
   p.cutoff = cutoff;
   p.Ng = num_gaussians;
+  p.dbg = g_bwd_dbg;
   const int grid = sm_count();
   cfconv_fused_bwd_kernel<<<grid, CTA_THREADS, SMEM_BYTES, st>>>(p);
   CMP_LAUNCH_CHECK("cmp_cfconv_fused_bwd_weights");

@@ -38,6 +38,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 
+// latency-critical single-thread wait (the MMA-issuing lane): poll without backing off
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
 // MUFU.EX2 / MUFU.LG2 without the denormal fix-up code the non-ftz intrinsics carry
 __device__ __forceinline__ float fast_ex2(float x) {
   float y;

@@ -327,6 +327,8 @@ int cmp_vis_edge_update_bwd(const float* gw, const float* wt, const float* ws, c
 /* Debug hook: when non-NULL, CTA 0 / pipeline 0 of cmp_cfconv_fused_fwd stores 8 clock64() phase
  * timestamps per tile (first 32 tiles) into this device buffer of 256 int64. */
 void cmp_debug_set_fwd_timestamps(void* buf);
+/* Same for cmp_cfconv_fused_bwd_weights: 12 timestamps per tile (first 20 tiles), 240 int64. */
+void cmp_debug_set_bwd_timestamps(void* buf);
 
 /* Single-tile UMMA probe used by the tests to pin descriptor / TMEM conventions. */
 int cmp_debug_umma_gemm(const void* a_img, int64_t a_bytes, const void* b_img, int64_t b_bytes,
