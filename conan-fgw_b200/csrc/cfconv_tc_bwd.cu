@@ -489,7 +489,14 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int U,
   if (i >= F * F + F * K1 + 2 * F) return;
   float s = 0.0f;
   if (i < F * F + F * K1) {
-    for (int u = 0; u < U; ++u) s += partial[(int64_t)u * PART_FLOATS + i];
+    // loads of 8 partials are issued together, the additions keep the fixed pipeline order (deterministic)
+    for (int u0 = 0; u0 < U; u0 += 8) {
+      float t[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t[k] = (u0 + k < U) ? __ldg(partial + (int64_t)(u0 + k) * PART_FLOATS + i) : 0.0f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += t[k];
+    }
     if (i < F * F) {
       dW2[i] = s;
     } else {

@@ -317,7 +317,14 @@ __global__ void node_dw_reduce_kernel(const float* __restrict__ partial, int P, 
   if (i >= Nout * (K + 1)) return;
   const int n = i / (K + 1), k = i % (K + 1);
   float s = 0.0f;
-  for (int c = 0; c < P; ++c) s += partial[((int64_t)c * 128 + n) * KX + k];
+  // loads of 8 partials are issued together, the additions keep the fixed CTA order (deterministic)
+  for (int c0 = 0; c0 < P; c0 += 8) {
+    float t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = (c0 + u < P) ? __ldg(partial + ((int64_t)(c0 + u) * 128 + n) * KX + k) : 0.0f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += t[u];
+  }
   if (k < K) dW[n * K + k] = s;
   else if (db) db[n] = s;
 }
