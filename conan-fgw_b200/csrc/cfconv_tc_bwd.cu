@@ -482,34 +482,42 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
   if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
-// out = sum over pipelines (fixed order) of the partial blocks, scattered into the parameter layouts
+// out = sum over pipelines of the partial blocks, scattered into the parameter layouts.  block = 32 outputs x 8
+// segments of the pipeline list: each thread sums its contiguous segment in order, the segment sums are combined in
+// segment order (a fixed summation tree: deterministic)
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int U, int Ng, float* __restrict__ dW1,
                                        float* __restrict__ db1, float* __restrict__ dW2, float* __restrict__ db2) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= F * F + F * K1 + 2 * F) return;
+  __shared__ float seg[8][33];
+  const int total = F * F + F * K1 + 2 * F;
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const bool live = i < total;
+  const int per = (U + 7) / 8;
+  const int u_lo = threadIdx.y * per, u_hi = min(U, u_lo + per);
   float s = 0.0f;
-  if (i < F * F + F * K1) {
-    // loads of 8 partials are issued together, the additions keep the fixed pipeline order (deterministic)
-    for (int u0 = 0; u0 < U; u0 += 8) {
-      float t[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) t[k] = (u0 + k < U) ? __ldg(partial + (int64_t)(u0 + k) * PART_FLOATS + i) : 0.0f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s += t[k];
-    }
-    if (i < F * F) {
-      dW2[i] = s;
+  if (live) {
+    if (i < F * F + F * K1) {
+      for (int u = u_lo; u < u_hi; ++u) s += partial[(int64_t)u * PART_FLOATS + i];
     } else {
-      const int k = (i - F * F) / K1, j = (i - F * F) % K1;
-      if (j < Ng) dW1[k * Ng + j] = s;
+      const int r = i - (F * F + F * K1);      // [0,128): db2, [128,256): db1; two warp halves each
+      const int base = F * F + F * K1 + (r / F) * 2 * F + (r % F);
+      for (int u = u_lo; u < u_hi; ++u)
+        s += partial[(int64_t)u * PART_FLOATS + base] + partial[(int64_t)u * PART_FLOATS + base + F];
     }
+  }
+  seg[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y != 0 || !live) return;
+  s = 0.0f;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) s += seg[y][threadIdx.x];
+  if (i < F * F) {
+    dW2[i] = s;
+  } else if (i < F * F + F * K1) {
+    const int k = (i - F * F) / K1, j = (i - F * F) % K1;
+    if (j < Ng) dW1[k * Ng + j] = s;
   } else {
-    const int r = i - (F * F + F * K1);      // [0,128): db2, [128,256): db1
-    const int which = r / F, c = r % F;
-    const int base = F * F + F * K1 + which * 2 * F;
-    for (int u = 0; u < U; ++u)
-      s += partial[(int64_t)u * PART_FLOATS + base + c] + partial[(int64_t)u * PART_FLOATS + base + F + c];
-    (which == 0 ? db2 : db1)[c] = s;
+    const int r = i - (F * F + F * K1);
+    (r / F == 0 ? db2 : db1)[r % F] = s;
   }
 }
 
@@ -728,7 +736,8 @@ extern "C" int cmp_cfconv_fused_bwd_weights(const float* g, const void* xprime_b
   cfconv_fused_bwd_kernel<<<grid, CTA_THREADS, SMEM_BYTES, st>>>(p);
   CMP_LAUNCH_CHECK("cmp_cfconv_fused_bwd_weights");
   const int total = F * F + F * K1 + 2 * F;
-  reduce_partials_kernel<<<(total + 255) / 256, 256, 0, st>>>(p.partial, grid * NG, num_gaussians, dW1, db1, dW2, db2);
+  reduce_partials_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(p.partial, grid * NG, num_gaussians, dW1, db1, dW2,
+                                                                    db2);
   CMP_LAUNCH_CHECK("cmp_cfconv_fused_bwd_weights(reduce)");
   return CMP_OK;
 }

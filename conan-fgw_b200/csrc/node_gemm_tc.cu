@@ -312,19 +312,24 @@ __global__ void __launch_bounds__(NT, 1) node_gemm_dw_kernel(const DwParams p) {
 
 __global__ void node_dw_reduce_kernel(const float* __restrict__ partial, int P, int K, int Nout, float* __restrict__ dW,
                                       float* __restrict__ db) {
+  // block = 32 outputs x 8 segments of the partial list: each thread sums its contiguous segment in order, the 8
+  // segment sums are combined in segment order (fixed summation tree: deterministic)
+  __shared__ float seg[8][33];
   const int KX = K + 16;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over Nout * (K + 1)
-  if (i >= Nout * (K + 1)) return;
-  const int n = i / (K + 1), k = i % (K + 1);
+  const int i = blockIdx.x * 32 + threadIdx.x;   // over Nout * (K + 1)
+  const bool live = i < Nout * (K + 1);
+  const int n = live ? i / (K + 1) : 0, k = live ? i % (K + 1) : 0;
+  const int per = (P + 7) / 8;
+  const int c_lo = threadIdx.y * per, c_hi = min(P, c_lo + per);
   float s = 0.0f;
-  // loads of 8 partials are issued together, the additions keep the fixed CTA order (deterministic)
-  for (int c0 = 0; c0 < P; c0 += 8) {
-    float t[8];
+  if (live)
+    for (int c = c_lo; c < c_hi; ++c) s += partial[((int64_t)c * 128 + n) * KX + k];
+  seg[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y != 0 || !live) return;
+  s = 0.0f;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) t[u] = (c0 + u < P) ? __ldg(partial + ((int64_t)(c0 + u) * 128 + n) * KX + k) : 0.0f;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) s += t[u];
-  }
+  for (int y = 0; y < 8; ++y) s += seg[y][threadIdx.x];
   if (k < K) dW[n * K + k] = s;
   else if (db) db[n] = s;
 }
@@ -426,7 +431,8 @@ extern "C" int cmp_node_gemm_dw(const float* dY, int64_t lddy, const float* save
   if (grid < 1) grid = 1;
   node_gemm_dw_kernel<<<grid, NT, smem, as_stream(stream)>>>(p);
   CMP_LAUNCH_CHECK("cmp_node_gemm_dw");
-  node_dw_reduce_kernel<<<(Nout * (K + 1) + 255) / 256, 256, 0, as_stream(stream)>>>(p.partial, grid, K, Nout, dW, db);
+  node_dw_reduce_kernel<<<(Nout * (K + 1) + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(p.partial, grid, K, Nout, dW,
+                                                                                          db);
   CMP_LAUNCH_CHECK("cmp_node_gemm_dw(reduce)");
   return CMP_OK;
 }
