@@ -338,9 +338,19 @@ __global__ void node_dw_reduce_kernel(const float* __restrict__ partial, int P, 
 // transpose = 1 packs W^T (rows of the image = columns of W).
 __global__ void node_pack_weight_kernel(const float* __restrict__ W, int rows, int cols, int transpose,
                                         uint8_t* __restrict__ out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (transpose == 2) {   // both images in one launch: [hi|lo of W] followed by [hi|lo of W^T]
+    const int n_norm = 128 * cols;
+    if (idx < n_norm) {
+      transpose = 0;
+    } else {
+      transpose = 1;
+      idx -= n_norm;
+      out += (size_t)2 * n_norm * 2;
+    }
+  }
   const int R = transpose ? cols : rows;   // image rows that carry data
   const int C = transpose ? rows : cols;   // image K extent
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 128 * C) return;
   const int r = idx / C, c = idx % C;
   float v = 0.0f;
@@ -368,7 +378,8 @@ extern "C" int cmp_node_gemm_pack_weight(const float* W, int rows, int cols, int
                                          cmp_stream_t stream) {
   CMP_REQUIRE(W && packed, CMP_EINVAL, "cmp_node_gemm_pack_weight: null pointer");
   CMP_REQUIRE(dims_ok(cols, rows), CMP_EUNSUPPORTED, "cmp_node_gemm_pack_weight: dims must be multiples of 16 in [16,128]");
-  const int C = transpose ? rows : cols;
+  CMP_REQUIRE(transpose >= 0 && transpose <= 2, CMP_EINVAL, "cmp_node_gemm_pack_weight: transpose must be 0, 1 or 2 (both)");
+  const int C = transpose == 2 ? rows + cols : (transpose ? rows : cols);
   node_pack_weight_kernel<<<(128 * C + 255) / 256, 256, 0, as_stream(stream)>>>(W, rows, cols, transpose,
                                                                                 reinterpret_cast<uint8_t*>(packed));
   CMP_LAUNCH_CHECK("cmp_node_gemm_pack_weight");

@@ -48,9 +48,19 @@ __global__ void embedding_bwd_stage1(const int64_t* __restrict__ z, int64_t N, c
   int64_t i1 = i0 + chunk;
   if (i1 > N) i1 = N;
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    for (int64_t i = i0; i < i1; ++i) {
-      int64_t zi = z[i];
-      if (zi >= 0 && zi < V) acc[zi * H + c] += dout[i * H + c];
+    // global loads of 8 atoms are issued together; the shared-memory accumulation keeps the atom order
+    for (int64_t i = i0; i < i1; i += 8) {
+      int64_t zz[8];
+      float dd[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const bool ok = i + u < i1;
+        zz[u] = ok ? z[i + u] : -1;
+        dd[u] = ok ? dout[(i + u) * H + c] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (zz[u] >= 0 && zz[u] < V) acc[zz[u] * H + c] += dd[u];
     }
   }
   __syncthreads();

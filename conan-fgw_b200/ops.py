@@ -124,6 +124,16 @@ def _pack_node_weight(weight, transpose):
     return packed
 
 
+def _pack_node_weight_both(weight):
+    """(image of W, image of W^T) from ONE launch: the forward uses the first, the dX backward the second."""
+    rows, cols = weight.shape
+    n_norm = _lib.size_query("cmp_node_gemm_weight_bytes", cols)
+    n_tr = _lib.size_query("cmp_node_gemm_weight_bytes", rows)
+    packed = torch.empty(n_norm + n_tr, dtype=torch.uint8, device=weight.device)
+    call("cmp_node_gemm_pack_weight", ptr(_f32c(weight)), rows, cols, 2, ptr(packed))
+    return packed[:n_norm], packed[n_norm:]
+
+
 def _node_gemm(x2, w_img, K, Nout, bias=None, act=ACT_NONE, residual=None, saved_y=None):
     M = x2.shape[0]
     y = torch.empty(M, Nout, dtype=torch.float32, device=x2.device)
@@ -146,8 +156,11 @@ class _LinearTCFn(Function):
         lead = x.shape[:-1]
         x2 = _f32c(x.reshape(-1, K))
         res2 = _f32c(residual.reshape(-1, Nout)) if residual is not None else None
-        y = _node_gemm(x2, _pack_node_weight(weight, False), K, Nout, _f32c(bias) if bias is not None else None, act,
-                       res2)
+        if ctx.needs_input_grad[0]:
+            w_img, ctx.w_img_t = _pack_node_weight_both(weight)
+        else:
+            w_img, ctx.w_img_t = _pack_node_weight(weight, False), None
+        y = _node_gemm(x2, w_img, K, Nout, _f32c(bias) if bias is not None else None, act, res2)
         ctx.act, ctx.lead = act, lead
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
         ctx.save_for_backward(x2, weight, y if act != ACT_NONE else None)
@@ -161,7 +174,8 @@ class _LinearTCFn(Function):
         dx = dw = db = dres = None
         if ctx.needs_input_grad[0]:
             # dX = (dY * ssp') W : the forward kernel with the transposed weight image
-            dx = _node_gemm(dy2, _pack_node_weight(weight, True), Nout, K, saved_y=y).reshape(*ctx.lead, K)
+            w_t = ctx.w_img_t if ctx.w_img_t is not None else _pack_node_weight(weight, True)
+            dx = _node_gemm(dy2, w_t, Nout, K, saved_y=y).reshape(*ctx.lead, K)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             M = x2.shape[0]
             dw = torch.empty(Nout, K, dtype=torch.float32, device=dy2.device)
