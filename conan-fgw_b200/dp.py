@@ -49,18 +49,33 @@ class FlatParameters:
         self.flat = torch.empty(n, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
+        self._grad_views = []
         for p in params:
             k = p.numel()
             self.flat[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat[off:off + k].view_as(p)
-            p.grad = self.grad[off:off + k].view_as(p)
+            self._grad_views.append(self.grad[off:off + k].view_as(p))
             off += k
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.step_count = 0
 
     def zero_grad(self):
-        self.grad.zero_()
+        """Gradients are produced as fresh tensors by the backward kernels (``p.grad = None`` lets autograd adopt them
+        without an accumulation kernel per parameter); ``collect_grads`` then moves them into the flat buffer with one
+        multi-tensor copy."""
+        for p in self.params:
+            p.grad = None
+
+    def collect_grads(self):
+        self.grad.zero_()          # parameters that received no gradient (e.g. an unused head) contribute zeros
+        dst, src = [], []
+        for p, view in zip(self.params, self._grad_views):
+            if p.grad is not None:
+                dst.append(view)
+                src.append(p.grad)
+        if dst:
+            torch._foreach_copy_(dst, src)
 
     def all_reduce(self, group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -100,6 +115,7 @@ class RegressionStep:
         self.flat.zero_grad()
         loss = self.loss(z, pos, batch, targets, num_graphs)
         loss.backward()
+        self.flat.collect_grads()
         return loss.detach()
 
     def capture(self, z, pos, batch, targets, num_graphs):

@@ -47,6 +47,7 @@ def _worker(rank, world, port, out):
         flat.zero_grad()
         loss = torch.nn.functional.mse_loss(net(x_all[idx]), y_all[idx], reduction="sum")
         loss.backward()
+        flat.collect_grads()
         local = flat.grad.clone()
         w = flat.all_reduce()
         assert w == world
