@@ -179,7 +179,7 @@ def visnet_secondary(cmp, dev, threads):
     b = cmp.synthetic.make_config_batch("cfg3_freesolv_visnet")
     G = b.num_graphs
     torch.manual_seed(0)
-    model = cmp.ViSNet(None, hidden_channels=128).to(dev)
+    model = cmp.ViSNet(None, hidden_channels=128).to(dev).set_precision("bf16")   # Linears on tcgen05 (split bf16)
     d = b.to(dev)
 
     E = model.representation_model.distance.neighbor_list(d.pos, d.batch, G).E    # fixed geometry: E is known
@@ -231,7 +231,8 @@ def visnet_secondary(cmp, dev, threads):
     cpu_step()
     cpu_s = time.perf_counter() - t0
     return {"workload": "cfg3_freesolv_visnet", "metric": "ConAN-ViSNet conformers/sec fwd+bwd", "value": G / (ms * 1e-3),
-            "unit": UNIT, "ms_per_step": ms, "eager_ms_per_step": eager_ms, "dtype": "f32", "cuda_graph": graphed,
+            "unit": UNIT, "ms_per_step": ms, "eager_ms_per_step": eager_ms,
+            "dtype": "f32 (Linears: split-bf16 tcgen05, ~2e-5)", "cuda_graph": graphed,
             "edges": E,
             "cpu_baseline": {"value": G / cpu_s, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "the full 160-conformer batch, 1 warm-up + 1 timed fwd+bwd of oracle.visnet.ViSNet"}}

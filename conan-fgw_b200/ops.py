@@ -108,6 +108,9 @@ def linear(x, weight, bias=None, act=ACT_NONE, residual=None, tc=False):
     """``tc=True``: split-bf16 tcgen05 kernels (bf16 mode); else the exact-fp32 SIMT GEMM."""
     if tc and node_tc_supported(weight.shape[1], weight.shape[0]):
         return _LinearTCFn.apply(x, weight, bias, act, residual)
+    if (tc and act == ACT_NONE and weight.shape[0] % 16 == 0 and weight.shape[1] % 16 == 0
+            and bool(_lib.lib().cmp_device_is_sm100())):
+        return _LinearTCBlockedFn.apply(x, weight, bias, residual)
     return _LinearFn.apply(x, weight, bias, act, residual)
 
 
@@ -141,6 +144,86 @@ def _node_gemm(x2, w_img, K, Nout, bias=None, act=ACT_NONE, residual=None, saved
          ptr(w_img), ptr(bias), int(act), ptr(residual), residual.stride(0) if residual is not None else 0, ptr(y),
          y.stride(0), M, K, Nout, work=2.0 * M * K * Nout)
     return y
+
+
+def _tc_matmul_blocked(x2, W, bias=None, residual=None, saved_y=None):
+    """y[M, Nout] = x2'[M, K] @ W[Nout, K]^T + bias + residual for any K, Nout that are multiples of 16, as a sequence
+    of <=128 x <=128 blocks of the tcgen05 node kernel: column blocks of the output are independent launches, K blocks
+    are chained through the kernel's residual input (no activation: callers apply it separately)."""
+    M, K = x2.shape
+    Nout = W.shape[0]
+    y = torch.empty(M, Nout, dtype=torch.float32, device=x2.device)
+    f4 = 4
+    for n0 in range(0, Nout, 128):
+        nb = min(128, Nout - n0)
+        for bi, k0 in enumerate(range(0, K, 128)):
+            kb = min(128, K - k0)
+            img = _pack_node_weight(W[n0:n0 + nb, k0:k0 + kb].contiguous(), False)
+            first = bi == 0
+            if first:
+                res_ptr = residual.data_ptr() + n0 * f4 if residual is not None else None
+                ldr = residual.stride(0) if residual is not None else 0
+            else:
+                res_ptr, ldr = y.data_ptr() + n0 * f4, Nout
+            b_ptr = bias.data_ptr() + n0 * f4 if (bias is not None and first) else None
+            sy_ptr = saved_y.data_ptr() + k0 * f4 if saved_y is not None else None
+            call("cmp_node_gemm_fwd", x2.data_ptr() + k0 * f4, K, sy_ptr, K if saved_y is not None else 0, ptr(img),
+                 b_ptr, ACT_NONE, res_ptr, ldr, y.data_ptr() + n0 * f4, Nout, M, kb, nb, work=2.0 * M * kb * nb)
+    return y
+
+
+def _tc_dw_blocked(dy2, saved_y, x2, want_db):
+    """dW[Nout, K] = dY'^T X (+ db = column sums of dY') in <=128 x <=128 blocks of cmp_node_gemm_dw."""
+    M, Nout = dy2.shape
+    K = x2.shape[1]
+    dev = dy2.device
+    dw = torch.empty(Nout, K, dtype=torch.float32, device=dev)
+    db = torch.empty(Nout, dtype=torch.float32, device=dev) if want_db else None
+    f4 = 4
+    for n0 in range(0, Nout, 128):
+        nb = min(128, Nout - n0)
+        for k0 in range(0, K, 128):
+            kb = min(128, K - k0)
+            blk = torch.empty(nb, kb, dtype=torch.float32, device=dev)
+            ws = _lib.workspace(_lib.size_query("cmp_node_gemm_dw_workspace", kb), dev)
+            db_ptr = db.data_ptr() + n0 * f4 if (want_db and k0 == 0) else None
+            sy_ptr = saved_y.data_ptr() + n0 * f4 if saved_y is not None else None
+            call("cmp_node_gemm_dw", dy2.data_ptr() + n0 * f4, Nout, sy_ptr, Nout if saved_y is not None else 0,
+                 x2.data_ptr() + k0 * f4, K, M, kb, nb, ptr(blk), db_ptr, ptr(ws), ws.numel(), work=2.0 * M * kb * nb)
+            if nb == Nout and kb == K:
+                dw = blk
+            else:
+                dw[n0:n0 + nb, k0:k0 + kb].copy_(blk)
+    return dw, db
+
+
+class _LinearTCBlockedFn(Function):
+    """linear(tc) for layers wider than 128 (ViSNet: H -> 2H / 3H, 2H -> H): blocked over the 128-wide kernel."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual):
+        Nout, K = weight.shape
+        lead = x.shape[:-1]
+        x2 = _f32c(x.reshape(-1, K))
+        res2 = _f32c(residual.reshape(-1, Nout)) if residual is not None else None
+        y = _tc_matmul_blocked(x2, weight, _f32c(bias) if bias is not None else None, res2)
+        ctx.lead, ctx.has_bias, ctx.has_res = lead, bias is not None, residual is not None
+        ctx.save_for_backward(x2, weight)
+        return y.reshape(*lead, Nout)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        Nout, K = weight.shape
+        dy2 = _f32c(dy.reshape(-1, Nout))
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = _tc_matmul_blocked(dy2, weight.t().contiguous()).reshape(*ctx.lead, K)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = _tc_dw_blocked(dy2, None, x2, ctx.has_bias)
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            dres = dy
+        return dx, dw, db, dres
 
 
 class _LinearTCFn(Function):

@@ -632,6 +632,17 @@ class TorchGeometricViSNet(nn.Module):
         if self.prior_model is not None:
             self.prior_model.reset_parameters()
 
+    def set_precision(self, precision: str):
+        """"fp32": every Linear on the exact SIMT GEMM (1e-5 parity).  "bf16": Linears on the tcgen05 kernels with
+        split-bf16 operands (hi + lo, three passes: ~2e-5 per GEMM); everything else stays exact fp32."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.precision = precision
+        for m in self.modules():
+            if isinstance(m, Linear):
+                m.tc = precision == "bf16"
+        return self
+
     def _per_atom(self, z, pos, batch, bary=False, num_graphs=None, num_edges=None):
         x, v = self.representation_model(z, pos, batch, num_graphs, num_edges)
         out = self.output_model.pre_reduce(x, v) * self.std

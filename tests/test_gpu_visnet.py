@@ -85,3 +85,40 @@ def test_deterministic_and_module_signatures():
     assert int((ei[0] == ei[1]).sum()) == b.z.numel()            # loop=True: one self loop per atom
     rbf = rm.distance_expansion(ew)
     assert rbf.shape == (ei.shape[1], 32)
+
+
+def test_tensor_core_linears_mode():
+    """set_precision("bf16"): every Linear (incl. the 2H / 3H wide ones, blocked) on the split-bf16 tcgen05 kernels.
+    Stated tolerance 2e-4 on embeddings / 2e-3 on gradients (each GEMM is good to ~2e-5)."""
+    if not cmp._lib.lib().cmp_device_is_sm100():
+        pytest.skip("tcgen05 kernels need an sm_100 device")
+    torch.manual_seed(5)
+    o = ov.ViSNet(None, hidden_channels=128)
+    with torch.no_grad():
+        for name, p in o.named_parameters():
+            if p.dim() <= 1 or "atomref" in name:
+                p.add_(0.1 * torch.randn_like(p))
+    c = cmp.ViSNet(None, hidden_channels=128).to(DEV)
+    c.load_state_dict(o.state_dict(), strict=True)
+    c.set_precision("bf16")
+    b = syn.make_batch(6, 2, 18, seed=3)
+    out_o = o(b.z, b.pos, b.batch)
+    out_c = c(b.z.to(DEV), b.pos.to(DEV), b.batch.to(DEV))
+    assert rel_err(out_c, out_o) < 2e-4
+    out_o.pow(2).mean().backward()
+    out_c.pow(2).mean().backward()
+    po, pc = dict(o.named_parameters()), dict(c.named_parameters())
+    for k in po:
+        if po[k].grad is not None:
+            assert rel_err(pc[k].grad, po[k].grad) < 2e-3, k
+    # wide / blocked linear against fp64 directly
+    from conan_fgw_b200 import ops
+    x = torch.randn(500, 256, device=DEV, requires_grad=True)
+    w = (torch.randn(384, 256, device=DEV) / 16).requires_grad_(True)
+    bias = torch.randn(384, device=DEV, requires_grad=True)
+    y = ops.linear(x, w, bias, tc=True)
+    yr = x.double() @ w.double().t() + bias.double()
+    assert rel_err(y, yr) < 3e-5
+    go = torch.randn_like(y)
+    for a, r in zip(torch.autograd.grad(y, [x, w, bias], go), torch.autograd.grad(yr, [x, w, bias], go.double())):
+        assert rel_err(a, r) < 6e-5
