@@ -262,7 +262,7 @@ def run_ours(args):
     cmp.build_library()
 
     c = cmp.synthetic.CONFIGS[WORKLOAD]
-    B, K, n = c["num_molecules"], c["num_conformers"], c["atoms"]
+    B, K, n = args.molecules or c["num_molecules"], c["num_conformers"], c["atoms"]
     # weak scaling: every rank owns its own B molecules (different seed per rank)
     host = cmp.synthetic.make_batch(B, K, n, seed=1234 + rank).pin()
     tg = torch.Generator().manual_seed(99 + rank)
@@ -365,16 +365,19 @@ def run_ours(args):
     launches = int(round(launches_per_step * args.steps))
 
     # the other numerics mode of the same step, for the record (exact-fp32 kernels <-> fused bf16 filter MLP)
-    other = "fp32" if args.precision == "bf16" else "bf16"
-    torch.manual_seed(0)
-    model_o = cmp.SchNetNoSum(None, **MODEL_CFG).to(dev).set_precision(other)
-    trainer_o = RegressionStep(model_o, MODEL_CFG["hidden_channels"] // 2, K, lr=1e-3)
-    for _ in range(3):
-        trainer_o.step(d.z, d.pos, d.batch, targets, G)
-    other_steps = max(3, min(args.steps, 10))
-    other_ms, _, _ = timed(lambda: trainer_o.step(d.z, d.pos, d.batch, targets, G), other_steps)
-    other_mode = {"precision": other, "value": world * G * other_steps / (other_ms * 1e-3), "unit": UNIT,
-                  "ms_per_step": other_ms / other_steps, "steps": other_steps}
+    other_mode = None
+    if not args.lean:
+        other = "fp32" if args.precision == "bf16" else "bf16"
+        torch.manual_seed(0)
+        model_o = cmp.SchNetNoSum(None, **MODEL_CFG).to(dev).set_precision(other)
+        trainer_o = RegressionStep(model_o, MODEL_CFG["hidden_channels"] // 2, K, lr=1e-3)
+        for _ in range(3):
+            trainer_o.step(d.z, d.pos, d.batch, targets, G)
+        other_steps = max(3, min(args.steps, 10))
+        other_ms, _, _ = timed(lambda: trainer_o.step(d.z, d.pos, d.batch, targets, G), other_steps)
+        other_mode = {"precision": other, "value": world * G * other_steps / (other_ms * 1e-3), "unit": UNIT,
+                      "ms_per_step": other_ms / other_steps, "steps": other_steps}
+        del model_o, trainer_o
 
     value = world * G * args.steps / (total_ms * 1e-3)
     e2e_value = world * G * args.steps / (e2e_ms * 1e-3)
@@ -426,13 +429,15 @@ def run_ours(args):
 
     # ViSNet secondary line first: the CPU legs below leave OpenMP workers spinning, which slows kernel launching
     threads = os.cpu_count() or 1
-    visnet = visnet_secondary(cmp, dev, threads) if world == 1 else None
+    visnet = visnet_secondary(cmp, dev, threads) if world == 1 and not args.lean else None
 
     # CPU baseline: bounded sample of the same workload on this host's cores
-    cpu_value, cpu_step = time_cpu(CPU_SAMPLE_MOLECULES, 2, 1, threads)
-    cpu_baseline = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
-                    "sample": f"{CPU_SAMPLE_MOLECULES} of 128 molecules x 5 conformers x 27 atoms, 1 warm-up + 2 timed "
-                              f"fwd+bwd+Adam steps of oracle.schnet.SchNetNoSum ({cpu_step:.2f} s/step)"}
+    cpu_baseline = None
+    if not args.lean:
+        cpu_value, cpu_step = time_cpu(CPU_SAMPLE_MOLECULES, 2, 1, threads)
+        cpu_baseline = {"value": cpu_value, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{CPU_SAMPLE_MOLECULES} of {B} molecules x {K} conformers x {n} atoms, 1 warm-up + 2 timed "
+                                  f"fwd+bwd+Adam steps of oracle.schnet.SchNetNoSum ({cpu_step:.2f} s/step)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -457,6 +462,7 @@ def run_ours(args):
 
 
 def main():
+    global WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
@@ -466,7 +472,15 @@ def main():
                     help="fp32: exact kernels (1e-5 parity mode); bf16: fused tcgen05 CFConv, bf16 filter MLP")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile", action="store_true", help="warm-up + timed steps only (for ncu launch lists)")
+    ap.add_argument("--workload", default=WORKLOAD, help="SchNet workload shape (synthetic.CONFIGS); the default is the "
+                    "configuration the metric is quoted on, the others are for sweeps")
+    ap.add_argument("--molecules", type=int, default=0, help="molecules per GPU (default: the workload's batch)")
+    ap.add_argument("--cutoff", type=float, default=0.0, help="override the cutoff radius (cfg 5 sweeps 5 / 10 A)")
+    ap.add_argument("--lean", action="store_true", help="skip the secondary lines (other precision, ViSNet, CPU baseline)")
     args = ap.parse_args()
+    WORKLOAD = args.workload
+    if args.cutoff > 0:
+        MODEL_CFG["cutoff"] = args.cutoff
     if args.impl == "reference":
         run_reference(args)
     else:
