@@ -353,7 +353,8 @@ def run_ours(args):
     for _ in range(60):      # keep the GPU under the same load until the clock sampler is running; a FIXED count,
         resident_step()      # identical on every rank (each step holds a collective)
     torch.cuda.synchronize()
-    dominant = ["cmp_gemm_f32", "cmp_cfconv_fused_fwd", "cmp_cfconv_fused_bwd_weights", "cmp_node_gemm_fwd",
+    dominant = ["cmp_gemm_f32", "cmp_cfconv_fused_fwd", "cmp_cfconv_fused_bwd_weights",
+                "cmp_cfconv_fused_bwd_weights_pairs", "cmp_node_gemm_fwd",
                 "cmp_node_gemm_dw"]
     total_ms, launches, kt = timed(resident_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
@@ -396,7 +397,7 @@ def run_ours(args):
     # algorithmic work of the fused kernels is known exactly from E (2*(Ng*F + F*F) FLOP per edge per
     # launch, for the forward / d x' pass and for the weight-gradient pass alike)
     per_edge = 2.0 * (MODEL_CFG["num_gaussians"] * MODEL_CFG["num_filters"] + MODEL_CFG["num_filters"] ** 2)
-    for k in ("cmp_cfconv_fused_fwd", "cmp_cfconv_fused_bwd_weights"):
+    for k in ("cmp_cfconv_fused_fwd", "cmp_cfconv_fused_bwd_weights", "cmp_cfconv_fused_bwd_weights_pairs"):
         if k in summ:
             summ[k] = (summ[k][0], summ[k][1], summ[k][0] * per_edge * E)
     top = max(summ, key=lambda k: summ[k][1]) if summ else dominant[0]
@@ -406,6 +407,8 @@ def run_ours(args):
         "cmp_gemm_f32": "gemm_f32_kernel (exact-fp32 SIMT GEMM: filter MLP on E rows + node linears + their gradients)",
         "cmp_cfconv_fused_fwd": "cfconv_fused_fwd_kernel (tcgen05: rbf + filter MLP + cutoff + gather + segmented reduce)",
         "cmp_cfconv_fused_bwd_weights": "cfconv_fused_bwd_kernel (tcgen05: recompute + dW accumulated in TMEM, K = edges)",
+        "cmp_cfconv_fused_bwd_weights_pairs": "cfconv_fused_bwd_kernel<pairs> (tcgen05: one column per undirected pair, "
+                                              "dW accumulated in TMEM; algorithmic FLOPs counted per directed edge)",
         "cmp_node_gemm_fwd": "node_gemm_fwd_kernel (tcgen05 split-bf16 node linears)",
         "cmp_node_gemm_dw": "node_gemm_dw_kernel (tcgen05 split-bf16 weight gradients of the node linears)",
     }

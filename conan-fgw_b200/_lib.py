@@ -85,6 +85,9 @@ SIGNATURES = {
     "cmp_cfconv_fused_bwd_workspace": (S, []),
     "cmp_cfconv_tc_pack_bwd_weights": (I, [P, P, P, I, I, P, P]),
     "cmp_cfconv_fused_bwd_weights": (I, [P, P, P, P, P, P, P, P, P, I, F, F, I, P, P, P, P, P, S, P]),
+    "cmp_build_pair_list_workspace": (S, [L, L]),
+    "cmp_build_pair_list": (I, [P, P, P, P, L, L, L, P, P, P, P, P, P, S, P, P]),
+    "cmp_cfconv_fused_bwd_weights_pairs": (I, [P, P, P, P, P, P, P, P, P, P, I, F, F, I, P, P, P, P, P, S, P]),
 }
 
 ACT_NONE, ACT_SSP, ACT_SILU = 0, 1, 2

@@ -45,13 +45,19 @@ constexpr uint32_t XB_BYTES = XP_CAP * F * 2;               // 20480
 constexpr uint32_t OFF_G = OFF_X + XB_BYTES;                // fp32 g rows [GROWS][128]
 constexpr uint32_t OFF_META = OFF_G + GROWS * F * 4;        // int2[64] {src (local or global), dst}
 constexpr uint32_t OFF_C = OFF_META + TE * 8;               // float[64]
-constexpr uint32_t GROUP_BYTES = OFF_C + TE * 4;
+constexpr uint32_t OFF_REV = OFF_C + TE * 4;                // float[64]  (pair mode: 1 when the reverse edge exists)
+constexpr uint32_t GROUP_BYTES = OFF_REV + TE * 4;
+// pair mode stages bf16 x' AND bf16 g of the conformer in the x' + g-row area: 2 x XP_PAIR rows
+constexpr int XP_PAIR = 48;
+static_assert(2u * XP_PAIR * F * 2 <= XB_BYTES + GROWS * F * 4, "pair-mode staging must fit the x' + g-row area");
 constexpr uint32_t SMEM_BYTES = W1_BYTES + W2T_BYTES + NG * GROUP_BYTES;
 
 constexpr int PART_FLOATS = F * F + F * K1 + 2 * F + 2 * F;   // dW2 | dW1 | db2[2 halves] | db1[2 halves]
 
 struct BwdParams {
-  const float* g;                 // [N, F] dL/dagg
+  const float* g;                 // [N, F] dL/dagg                      (edge mode)
+  const __nv_bfloat16* gb;        // [N, F] bf16 copy of dL/dagg          (pair mode)
+  const int32_t* rev;             // [P] reverse-edge flags               (pair mode)
   const __nv_bfloat16* xprime;    // [N, F] bf16 copy of x'
   const float* dist;
   const int32_t* col;
@@ -98,6 +104,10 @@ __device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
                     tc::pack_bf16x2(v[6], v[7]));
 }
 
+// PAIR = false: one column per directed edge, dF = g[dst] x'[src].
+// PAIR = true : one column per primary edge (graph.cu: one representative of {j->i, i->j}); both directions share the
+//               filter, so dF = g[dst] x'[src] + rev * g[src] x'[dst] and the tile count halves.
+template <bool PAIR>
 __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const BwdParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   // wbar | per group: r_ready, d1_ready, f_ready, dda_ready, h_ready, w_done, xbar
@@ -217,6 +227,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
     float* sGr = reinterpret_cast<float*>(sR + OFF_G);
     int2* sMeta = reinterpret_cast<int2*>(sR + OFF_META);
     float* sC = reinterpret_cast<float*>(sR + OFF_C);
+    float* sRev = reinterpret_cast<float*>(sR + OFF_REV);
+    const __nv_bfloat16* sGb = sXb + XP_PAIR * F;            // pair mode: bf16 g rows of the conformer
     const uint32_t tD = tmem_base + g * 256 + ((uint32_t)(wq * 32) << 16);
     const uint32_t tW2 = tD + 64, tW1 = tD + 192;
     const int64_t u = (int64_t)blockIdx.x * NG + g;
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
     uint32_t it = 0;
 
     TileInfo cur;
-    int pre_src = 0, pre_dst = 0;
+    int pre_src = 0, pre_dst = 0, pre_rev = 0;
     float pre_d = 0.0f;
     float4 pre_g = make_float4(0.f, 0.f, 0.f, 0.f);
     auto prefetch = [&](const TileInfo& t) {
@@ -238,10 +250,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
         pre_d = __ldg(p.dist + t.e0 + e);
         pre_src = __ldg(p.col + t.e0 + e);
         pre_dst = __ldg(p.erow + t.e0 + e);
+        if (PAIR) pre_rev = __ldg(p.rev + t.e0 + e);
       }
-      const int r = t.row_begin + (tt >> 5);
-      if (t.row_end - t.row_begin <= GROWS && r < t.row_end)
-        pre_g = __ldg(reinterpret_cast<const float4*>(p.g + (int64_t)r * F) + (tt & 31));
+      if (!PAIR) {
+        const int r = t.row_begin + (tt >> 5);
+        if (t.row_end - t.row_begin <= GROWS && r < t.row_end)
+          pre_g = __ldg(reinterpret_cast<const float4*>(p.g + (int64_t)r * F) + (tt & 31));
+      }
     };
     if (t0 < t1) {
       cur = load_tile(p.tiles, t0);
@@ -257,9 +272,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
       const int npad = (ne + 15) & ~15;
       const uint32_t par = it & 1;
       const int cs = tile.cs, cn = tile.cn;
-      const bool staged = cn <= XP_CAP;
+      const bool staged = cn <= (PAIR ? XP_PAIR : XP_CAP);
       const int r0 = tile.row_begin;
-      const bool g_staged = (tile.row_end - tile.row_begin) <= GROWS;
+      const bool g_staged = !PAIR && (tile.row_end - tile.row_begin) <= GROWS;
 
       const bool rec = p.dbg && blockIdx.x == 0 && g == 0 && tt == 0 && it < 20;
       if (rec) p.dbg[it * 12 + 0] = clock64();
@@ -271,8 +286,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
       if (staged && cs != staged_conf) {
         if (tt == 0) {
           const uint32_t bytes = (uint32_t)cn * F * 2;
-          tc::mbar_arrive_expect_tx(xbar, bytes);
+          tc::mbar_arrive_expect_tx(xbar, PAIR ? 2 * bytes : bytes);
           tc::bulk_g2s(sR + OFF_X, p.xprime + (int64_t)cs * F, bytes, xbar);
+          if (PAIR) tc::bulk_g2s(sR + OFF_X + XP_PAIR * F * 2, p.gb + (int64_t)cs * F, bytes, xbar);
         }
         staged_conf = cs;
         x_wait = true;
@@ -287,12 +303,16 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
         if (q == 0) {
           // pre-multiplied element offsets of the x' row and the g row this edge reads
           if (live) {
-            sMeta[e] = make_int2((staged ? (pre_src - cs) : pre_src) * F, (g_staged ? (pre_dst - r0) : pre_dst) * F);
+            if (PAIR)
+              sMeta[e] = make_int2((staged ? (pre_src - cs) : pre_src) * F, (staged ? (pre_dst - cs) : pre_dst) * F);
+            else
+              sMeta[e] = make_int2((staged ? (pre_src - cs) : pre_src) * F, (g_staged ? (pre_dst - r0) : pre_dst) * F);
             sC[e] = 0.5f * (__cosf(d * kPi / cutoff) + 1.0f);
           } else {
-            sMeta[e] = make_int2((staged ? 0 : cs) * F, (g_staged ? 0 : r0) * F);
+            sMeta[e] = make_int2((staged ? 0 : cs) * F, ((PAIR ? staged : g_staged) ? 0 : (PAIR ? cs : r0)) * F);
             sC[e] = 0.0f;
           }
+          if (PAIR) sRev[e] = (live && pre_rev) ? 1.0f : 0.0f;
         }
         uint8_t* rowp = sR + (e >> 3) * 1024 + (e & 7) * 16;
         // exp2(c2_k (d - mu_k)^2), c2_k = 0 beyond the Gaussians (bias column = 1; padding columns meet zero weights
@@ -343,27 +363,48 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_bwd_kernel(const 
           }
           const float4 c0v = *reinterpret_cast<const float4*>(sC + c0), c1v = *reinterpret_cast<const float4*>(sC + c0 + 4);
           const float cc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
-          float xv[8], gv[8];
-          if (staged) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) xv[j] = __bfloat162float(xs_s[m[j].x]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) xv[j] = __bfloat162float(xs_g[m[j].x]);
-          }
-          if (g_staged) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) gv[j] = gs_s[m[j].y];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) gv[j] = __ldg(gs_g + m[j].y);
-          }
           float v[8];
+          if (PAIR) {
+            // both directions of the pair: g[dst] x'[src] + rev * g[src] x'[dst]  (all four rows from the bf16 copies)
+            const float4 r0v = *reinterpret_cast<const float4*>(sRev + c0), r1v = *reinterpret_cast<const float4*>(sRev + c0 + 4);
+            const float rv[8] = {r0v.x, r0v.y, r0v.z, r0v.w, r1v.x, r1v.y, r1v.z, r1v.w};
+            const __nv_bfloat16* xs = staged ? xs_s : xs_g;
+            const __nv_bfloat16* gs = staged ? (sGb + chan) : (p.gb + chan);
+            float xs_[8], gd_[8], xd_[8], gs_[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            // padded edges carry C = 0 and valid (row 0) offsets; their dF must still be exactly 0 (K = edges)
-            v[j] = (c0 + j < ne) ? gv[j] * xv[j] : 0.0f;
-            db2 = fmaf(v[j], cc[j], db2);
+            for (int j = 0; j < 8; ++j) {
+              xs_[j] = __bfloat162float(xs[m[j].x]);
+              gd_[j] = __bfloat162float(gs[m[j].y]);
+              xd_[j] = __bfloat162float(xs[m[j].y]);
+              gs_[j] = __bfloat162float(gs[m[j].x]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[j] = (c0 + j < ne) ? fmaf(rv[j] * gs_[j], xd_[j], gd_[j] * xs_[j]) : 0.0f;
+              db2 = fmaf(v[j], cc[j], db2);
+            }
+          } else {
+            float xv[8], gv[8];
+            if (staged) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) xv[j] = __bfloat162float(xs_s[m[j].x]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) xv[j] = __bfloat162float(xs_g[m[j].x]);
+            }
+            if (g_staged) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) gv[j] = gs_s[m[j].y];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) gv[j] = __ldg(gs_g + m[j].y);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              // padded edges carry C = 0 and valid (row 0) offsets; their dF must still be exactly 0 (K = edges)
+              v[j] = (c0 + j < ne) ? gv[j] * xv[j] : 0.0f;
+              db2 = fmaf(v[j], cc[j], db2);
+            }
           }
           *reinterpret_cast<uint4*>(sF + chan * 16 + (c0 >> 3) * 2048) = pack_bf16x8(v);
         }
@@ -690,6 +731,29 @@ extern "C" int cmp_cfconv_tc_pack_bwd_weights(const float* W1, const float* b1, 
   return CMP_OK;
 }
 
+template <bool PAIR>
+static int launch_fused_bwd(BwdParams p, int num_gaussians, float* dW1, float* db1, float* dW2, float* db2,
+                            cudaStream_t st, const char* what) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(cfconv_fused_bwd_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)SMEM_BYTES) != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("%s: cannot opt in to %u bytes of shared memory", what, SMEM_BYTES);
+      return CMP_ECUDA;
+    }
+    attr_set = true;
+  }
+  const int grid = sm_count();
+  cfconv_fused_bwd_kernel<PAIR><<<grid, CTA_THREADS, SMEM_BYTES, st>>>(p);
+  CMP_LAUNCH_CHECK(what);
+  const int total = F * F + F * K1 + 2 * F;
+  reduce_partials_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(p.partial, grid * NG, num_gaussians, dW1, db1, dW2,
+                                                                    db2);
+  CMP_LAUNCH_CHECK(what);
+  return CMP_OK;
+}
+
 extern "C" int cmp_cfconv_fused_bwd_weights(const float* g, const void* xprime_bf16, const float* dist,
                                             const int32_t* col, const int32_t* erow, const void* flat_tiles,
                                             const int32_t* num_tiles, const void* packed_bwd_weights,
@@ -706,19 +770,10 @@ extern "C" int cmp_cfconv_fused_bwd_weights(const float* g, const void* xprime_b
   CMP_REQUIRE(workspace && workspace_bytes >= cmp_cfconv_fused_bwd_workspace(), CMP_EWORKSPACE,
               "cmp_cfconv_fused_bwd_weights: workspace too small");
   CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED, "cmp_cfconv_fused_bwd_weights: needs an sm_100 device (tcgen05)");
-  cudaStream_t st = as_stream(stream);
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(cfconv_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) !=
-        cudaSuccess) {
-      (void)cudaGetLastError();
-      set_error("cmp_cfconv_fused_bwd_weights: cannot opt in to %u bytes of shared memory", SMEM_BYTES);
-      return CMP_ECUDA;
-    }
-    attr_set = true;
-  }
   BwdParams p;
   p.g = g;
+  p.gb = nullptr;
+  p.rev = nullptr;
   p.xprime = reinterpret_cast<const __nv_bfloat16*>(xprime_bf16);
   p.dist = dist;
   p.col = col;
@@ -732,12 +787,45 @@ extern "C" int cmp_cfconv_fused_bwd_weights(const float* g, const void* xprime_b
   p.cutoff = cutoff;
   p.Ng = num_gaussians;
   p.dbg = g_bwd_dbg;
-  const int grid = sm_count();
-  cfconv_fused_bwd_kernel<<<grid, CTA_THREADS, SMEM_BYTES, st>>>(p);
-  CMP_LAUNCH_CHECK("cmp_cfconv_fused_bwd_weights");
-  const int total = F * F + F * K1 + 2 * F;
-  reduce_partials_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(p.partial, grid * NG, num_gaussians, dW1, db1, dW2,
-                                                                    db2);
-  CMP_LAUNCH_CHECK("cmp_cfconv_fused_bwd_weights(reduce)");
-  return CMP_OK;
+  return launch_fused_bwd<false>(p, num_gaussians, dW1, db1, dW2, db2, as_stream(stream), "cmp_cfconv_fused_bwd_weights");
+}
+
+extern "C" int cmp_cfconv_fused_bwd_weights_pairs(const void* g_bf16, const void* xprime_bf16, const float* pair_dist,
+                                                  const int32_t* pair_src, const int32_t* pair_dst,
+                                                  const int32_t* pair_rev, const void* pair_tiles,
+                                                  const int32_t* num_tiles, const void* packed_bwd_weights,
+                                                  const float* offset, int num_gaussians, float coeff, float cutoff,
+                                                  int num_filters, float* dW1, float* db1, float* dW2, float* db2,
+                                                  void* workspace, size_t workspace_bytes, cmp_stream_t stream) {
+  CMP_REQUIRE(num_filters == F && num_gaussians >= 1 && num_gaussians < K1, CMP_EUNSUPPORTED,
+              "cmp_cfconv_fused_bwd_weights_pairs: needs num_filters == 128 and num_gaussians < 64");
+  CMP_REQUIRE(g_bf16 && xprime_bf16 && pair_dist && pair_src && pair_dst && pair_rev && pair_tiles && num_tiles &&
+                  packed_bwd_weights && offset && dW1 && db1 && dW2 && db2,
+              CMP_EINVAL, "cmp_cfconv_fused_bwd_weights_pairs: null pointer");
+  CMP_REQUIRE(((uintptr_t)xprime_bf16 % 16 == 0) && ((uintptr_t)packed_bwd_weights % 16 == 0) &&
+                  ((uintptr_t)g_bf16 % 16 == 0),
+              CMP_EINVAL, "cmp_cfconv_fused_bwd_weights_pairs: pointers must be 16-byte aligned");
+  CMP_REQUIRE(workspace && workspace_bytes >= cmp_cfconv_fused_bwd_workspace(), CMP_EWORKSPACE,
+              "cmp_cfconv_fused_bwd_weights_pairs: workspace too small");
+  CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED,
+              "cmp_cfconv_fused_bwd_weights_pairs: needs an sm_100 device (tcgen05)");
+  BwdParams p;
+  p.g = nullptr;
+  p.gb = reinterpret_cast<const __nv_bfloat16*>(g_bf16);
+  p.rev = pair_rev;
+  p.xprime = reinterpret_cast<const __nv_bfloat16*>(xprime_bf16);
+  p.dist = pair_dist;
+  p.col = pair_src;
+  p.erow = pair_dst;
+  p.tiles = reinterpret_cast<const int4*>(pair_tiles);
+  p.num_tiles = num_tiles;
+  p.weights = reinterpret_cast<const uint8_t*>(packed_bwd_weights);
+  p.offset = offset;
+  p.partial = reinterpret_cast<float*>(workspace);
+  p.coeff_log2e = coeff * 1.4426950408889634f;
+  p.cutoff = cutoff;
+  p.Ng = num_gaussians;
+  p.dbg = g_bwd_dbg;
+  return launch_fused_bwd<true>(p, num_gaussians, dW1, db1, dW2, db2, as_stream(stream),
+                                "cmp_cfconv_fused_bwd_weights_pairs");
 }

@@ -317,6 +317,78 @@ __global__ void tiles_fill_kernel(const int32_t* __restrict__ rowptr, const int3
   walk_tiles(rowptr, seg_ptr[g], seg_ptr[g + 1], tile_edges, tiles + 2 * (int64_t)tile_ptr[g], status);
 }
 
+// ---- primary edges: one representative per undirected pair -----------------------------------------
+// The filter of an edge depends on the distance only, so (j -> i) and (i -> j) share it.  Edge (j -> i) (row i,
+// column j) is PRIMARY when j > i, or when j < i and the reverse edge is missing (the neighbour cap may keep one
+// direction only); rev = 1 when a primary edge's reverse exists.  Order: rows ascending, columns ascending.
+__device__ __forceinline__ bool csr_has(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int row,
+                                        int target) {
+  int lo = rowptr[row], hi = rowptr[row + 1];
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int c = col[mid];
+    if (c == target) return true;
+    if (c < target) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(kGraphThreads)
+pair_count_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                  const int32_t* __restrict__ seg_ptr, int32_t* __restrict__ pcount, int32_t* __restrict__ conf_pairs) {
+  __shared__ int warp_sums[kGraphThreads / 32];
+  const int g = blockIdx.x;
+  const int s = seg_ptr[g], n = seg_ptr[g + 1] - s;
+  int local = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int row = s + i;
+    int c = 0;
+    for (int k = rowptr[row]; k < rowptr[row + 1]; ++k) {
+      const int j = col[k];
+      if (j >= row || !csr_has(rowptr, col, j, row)) ++c;   // a self loop is its own (unpaired) representative
+    }
+    pcount[row] = c;
+    local += c;
+  }
+  for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < kGraphThreads / 32; ++w) t += warp_sums[w];
+    conf_pairs[g] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kGraphThreads)
+pair_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dist,
+                 const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ pcount,
+                 const int32_t* __restrict__ conf_pair_ptr, int64_t cap_P, int32_t* __restrict__ p_src,
+                 int32_t* __restrict__ p_dst, float* __restrict__ p_dist, int32_t* __restrict__ p_rev, int* status) {
+  const int g = blockIdx.x;
+  const int s = seg_ptr[g], n = seg_ptr[g + 1] - s;
+  if ((int64_t)conf_pair_ptr[g + 1] > cap_P) {
+    if (threadIdx.x == 0) atomicOr(status, CMP_STATUS_EDGE_OVERFLOW);
+    return;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int row = s + i;
+    int w = conf_pair_ptr[g];
+    for (int r = 0; r < i; ++r) w += pcount[s + r];
+    for (int k = rowptr[row]; k < rowptr[row + 1]; ++k) {
+      const int j = col[k];
+      const bool has = (j != row) && csr_has(rowptr, col, j, row);
+      if (j >= row || !has) {
+        p_src[w] = j;
+        p_dst[w] = row;
+        p_dist[w] = dist[k];
+        p_rev[w] = has ? 1 : 0;
+        ++w;
+      }
+    }
+  }
+}
+
 __global__ void gather_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
                                   const int32_t* __restrict__ count_ptr, float* __restrict__ dst) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -428,6 +500,38 @@ extern "C" int cmp_build_tiles(const int32_t* rowptr, const int32_t* seg_ptr, in
   tiles_fill_kernel<<<(unsigned)ceil_div(G, 128), 128, 0, st>>>(rowptr, seg_ptr, G, tile_edges, tile_ptr, cap_tiles,
                                                                reinterpret_cast<int4*>(tiles), num_tiles, status);
   CMP_LAUNCH_CHECK("cmp_build_tiles(fill)");
+  return CMP_OK;
+}
+
+extern "C" size_t cmp_build_pair_list_workspace(int64_t N, int64_t G) {
+  return align_up((size_t)(N + G + 8) * sizeof(int32_t), 256);   // pcount[N] + conf_pairs[G]
+}
+
+extern "C" int cmp_build_pair_list(const int32_t* rowptr, const int32_t* col, const float* dist, const int32_t* seg_ptr,
+                                   int64_t N, int64_t G, int64_t cap_P, int32_t* p_src, int32_t* p_dst, float* p_dist,
+                                   int32_t* p_rev, int32_t* conf_pair_ptr, void* workspace, size_t workspace_bytes,
+                                   int* status, cmp_stream_t stream) {
+  CMP_REQUIRE(N >= 0 && G >= 0 && cap_P >= 0, CMP_EINVAL, "cmp_build_pair_list: negative size");
+  CMP_REQUIRE(conf_pair_ptr && status, CMP_EINVAL, "cmp_build_pair_list: null pointer");
+  cudaStream_t st = as_stream(stream);
+  if (N == 0 || G == 0) {
+    set_i32_kernel<<<(int)ceil_div(G + 1, 256), 256, 0, st>>>(conf_pair_ptr, G + 1, 0);
+    CMP_LAUNCH_CHECK("cmp_build_pair_list(empty)");
+    return CMP_OK;
+  }
+  CMP_REQUIRE(rowptr && col && dist && seg_ptr && p_src && p_dst && p_dist && p_rev, CMP_EINVAL,
+              "cmp_build_pair_list: null pointer");
+  CMP_REQUIRE(workspace && workspace_bytes >= cmp_build_pair_list_workspace(N, G), CMP_EWORKSPACE,
+              "cmp_build_pair_list: workspace too small");
+  int32_t* pcount = reinterpret_cast<int32_t*>(workspace);
+  int32_t* conf_pairs = pcount + N;
+  pair_count_kernel<<<(unsigned)G, kGraphThreads, 0, st>>>(rowptr, col, seg_ptr, pcount, conf_pairs);
+  CMP_LAUNCH_CHECK("cmp_build_pair_list(count)");
+  scan_conformers_kernel<<<1, 1024, 0, st>>>(conf_pairs, G, conf_pair_ptr);
+  CMP_LAUNCH_CHECK("cmp_build_pair_list(scan)");
+  pair_fill_kernel<<<(unsigned)G, kGraphThreads, 0, st>>>(rowptr, col, dist, seg_ptr, pcount, conf_pair_ptr, cap_P, p_src,
+                                                          p_dst, p_dist, p_rev, status);
+  CMP_LAUNCH_CHECK("cmp_build_pair_list(fill)");
   return CMP_OK;
 }
 

@@ -132,6 +132,35 @@ class NeighborList:
             self._flat_tiles = (erow, tiles, num)
         return self._flat_tiles
 
+    def pair_tiles(self):
+        """(pair_src, pair_dst, pair_dist, pair_rev, tiles, num_tiles): one primary edge per undirected pair
+        (``cmp_build_pair_list``) cut into 64-column chunks per conformer - the work list of the pair mode of the
+        fused weight-gradient kernel (the filter is shared by both directions of a pair)."""
+        if getattr(self, "_pair_tiles", None) is None:
+            if self.G == 0 and self.N > 0:
+                raise _lib.ConanMPError("pair tiles need conformer segments (graph was built from a raw edge_index)")
+            dev = self.rowptr.device
+            cap = max(self.cap_E, 1)      # every edge may be unpaired
+            src = torch.empty(cap, dtype=torch.int32, device=dev)
+            dst = torch.empty(cap, dtype=torch.int32, device=dev)
+            dist = torch.empty(cap, dtype=torch.float32, device=dev)
+            rev = torch.empty(cap, dtype=torch.int32, device=dev)
+            conf_ptr = torch.empty(self.G + 1, dtype=torch.int32, device=dev)
+            ws = _lib.workspace(_lib.size_query("cmp_build_pair_list_workspace", self.N, self.G), dev)
+            _lib.call("cmp_build_pair_list", _lib.ptr(self.rowptr), _lib.ptr(self.col), _lib.ptr(self.dist),
+                      _lib.ptr(self.seg_ptr), self.N, self.G, cap, _lib.ptr(src), _lib.ptr(dst), _lib.ptr(dist),
+                      _lib.ptr(rev), _lib.ptr(conf_ptr), _lib.ptr(ws), ws.numel(), _lib.ptr(self.status))
+            tile_e = _lib.size_query("cmp_cfconv_tc_bwd_tile_edges")
+            cap_t = cap // tile_e + self.G + 1
+            tiles = torch.empty(max(cap_t, 1), 8, dtype=torch.int32, device=dev)
+            num = torch.zeros(1, dtype=torch.int32, device=dev)
+            ws = _lib.workspace(_lib.size_query("cmp_build_flat_tiles_workspace", self.G), dev)
+            _lib.call("cmp_build_flat_tiles", _lib.ptr(conf_ptr), _lib.ptr(self.seg_ptr), _lib.ptr(dst),
+                      self.G, tile_e, _lib.ptr(tiles), cap_t, _lib.ptr(num), _lib.ptr(ws), ws.numel(),
+                      _lib.ptr(self.status))
+            self._pair_tiles = (src, dst, dist, rev, tiles, num, conf_ptr)
+        return self._pair_tiles
+
     def edge_weight(self) -> torch.Tensor:
         w = self.dist[: self.E]
         w._cmp_graph = self

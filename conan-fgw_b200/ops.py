@@ -445,6 +445,9 @@ class _CFConvFusedFn(Function):
 
 
 FUSED_WEIGHT_GRADS = True
+# one column per undirected pair in the weight-gradient pass (both directions share the filter); False = one column
+# per directed edge with fp32 g (kept for cross-checking)
+FUSED_PAIR_GRADS = True
 
 
 def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff):
@@ -456,7 +459,6 @@ def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff):
     call("cmp_f32_to_bf16", ptr(xprime), N * F, ptr(xb))
     packed = torch.empty(_lib.size_query("cmp_cfconv_tc_bwd_weights_bytes"), dtype=torch.uint8, device=dev)
     call("cmp_cfconv_tc_pack_bwd_weights", ptr(_f32c(W1)), ptr(_f32c(b1)), ptr(_f32c(W2)), F, Ng, ptr(packed))
-    erow, tiles, num = graph.flat_tiles()
     dW1 = torch.empty(F, Ng, dtype=torch.float32, device=dev)
     db1 = torch.empty(F, dtype=torch.float32, device=dev)
     dW2 = torch.empty(F, F, dtype=torch.float32, device=dev)
@@ -464,6 +466,15 @@ def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff):
     ws = _lib.workspace(_lib.size_query("cmp_cfconv_fused_bwd_workspace"), dev)
     e_hint = graph._E if graph._E is not None else graph.cap_E
     # algorithmic FLOPs: the weight-gradient half of "bwd = 2 x fwd" = 2*(Ng*F + F*F) per edge
+    if FUSED_PAIR_GRADS:
+        gb = torch.empty(N, F, dtype=torch.bfloat16, device=dev)
+        call("cmp_f32_to_bf16", ptr(_f32c(g)), N * F, ptr(gb))
+        psrc, pdst, pdist, prev, tiles, num, _ = graph.pair_tiles()
+        call("cmp_cfconv_fused_bwd_weights_pairs", ptr(gb), ptr(xb), ptr(pdist), ptr(psrc), ptr(pdst), ptr(prev),
+             ptr(tiles), ptr(num), ptr(packed), ptr(offset), Ng, float(coeff), float(cutoff), F, ptr(dW1), ptr(db1),
+             ptr(dW2), ptr(db2), ptr(ws), ws.numel(), work=2.0 * (Ng * F + F * F) * float(e_hint))
+        return dW1, db1, dW2, db2
+    erow, tiles, num = graph.flat_tiles()
     call("cmp_cfconv_fused_bwd_weights", ptr(g), ptr(xb), ptr(graph.dist), ptr(graph.col), ptr(erow), ptr(tiles),
          ptr(num), ptr(packed), ptr(offset), Ng, float(coeff), float(cutoff), F, ptr(dW1), ptr(db1), ptr(dW2),
          ptr(db2), ptr(ws), ws.numel(), work=2.0 * (Ng * F + F * F) * float(e_hint))

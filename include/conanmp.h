@@ -236,6 +236,26 @@ int cmp_cfconv_fused_bwd_weights(const float* g, const void* xprime_bf16, const 
                                  int num_filters, float* dW1, float* db1, float* dW2, float* db2,
                                  void* workspace, size_t workspace_bytes, cmp_stream_t stream);
 
+/* Pair mode of the same pass.  The filter W(d_ij) of PyG CFConv (schnet.py CFConv.forward: W = nn(edge_attr) * C)
+ * depends on the distance only, so the two directions of an undirected pair share it and their weight-gradient
+ * terms add: dF = g[dst] x'[src] + rev * g[src] x'[dst].  cmp_build_pair_list emits one PRIMARY edge per pair
+ * (j -> i with j > i; or the surviving direction when the neighbour cap of radius_graph dropped the other one,
+ * rev = 0; rows and columns ascending) with per-conformer offsets conf_pair_ptr[G+1]; tiles for it come from
+ * cmp_build_flat_tiles(conf_pair_ptr, seg_ptr, pair_dst, ...).  Halves the filter-MLP recomputation of the backward. */
+size_t cmp_build_pair_list_workspace(int64_t N, int64_t G);
+int cmp_build_pair_list(const int32_t* rowptr, const int32_t* col, const float* dist,
+                        const int32_t* seg_ptr, int64_t N, int64_t G, int64_t cap_P, int32_t* pair_src,
+                        int32_t* pair_dst, float* pair_dist, int32_t* pair_rev, int32_t* conf_pair_ptr,
+                        void* workspace, size_t workspace_bytes, int* status, cmp_stream_t stream);
+int cmp_cfconv_fused_bwd_weights_pairs(const void* g_bf16, const void* xprime_bf16,
+                                       const float* pair_dist, const int32_t* pair_src,
+                                       const int32_t* pair_dst, const int32_t* pair_rev,
+                                       const void* pair_tiles, const int32_t* num_tiles,
+                                       const void* packed_bwd_weights, const float* offset,
+                                       int num_gaussians, float coeff, float cutoff, int num_filters,
+                                       float* dW1, float* db1, float* dW2, float* db2, void* workspace,
+                                       size_t workspace_bytes, cmp_stream_t stream);
+
 /* Node-level linears on tcgen05 with split-bf16 operands (hi + lo images, three MMA passes, fp32
  * accumulate): Y = act(X' W^T + b) + R with X' = X * (1 - exp(-saved_y)/2) when saved_y is given (the
  * ShiftedSoftplus backward fused into the operand load).  K, Nout multiples of 16 in [16, 128].

@@ -115,19 +115,59 @@ def test_module_api_picks_fused_kernel():
     assert cmp._lib.launches() - before < 40
 
 
-@pytest.mark.parametrize("n,B", [(27, 8), (65, 2), (9, 4)])
-def test_fused_weight_gradients_match_exact_recompute(n, B):
-    """cmp_cfconv_fused_bwd_weights (TMEM-accumulated dW) vs the exact-fp32 recompute path."""
+def test_pair_list_has_one_representative_per_undirected_pair():
+    """cmp_build_pair_list against a set-based restatement: every directed edge is covered exactly once, either as a
+    primary edge or as the reverse of one; unpaired edges (neighbour cap) are their own representative."""
+    b = syn.make_batch(3, 2, 50, seed=5).to(DEV)           # 50 atoms, cap 32: truncated, asymmetric graph
+    b2 = syn.make_batch(4, 3, 20, seed=6).to(DEV)          # complete graphs
+    for bb in (b, b2):
+        nl = cmp.build_neighbor_list(bb.pos, bb.batch, 10.0)
+        E = nl.E
+        src, dst, dist, rev, tiles, num, conf_ptr = nl.pair_tiles()
+        nl.check()
+        P = int(conf_ptr[-1])
+        ei = nl.edge_index().cpu()
+        edges = {(int(j), int(i)): k for k, (j, i) in enumerate(zip(ei[0], ei[1]))}
+        ps, pd, pr, pdist = src[:P].cpu(), dst[:P].cpu(), rev[:P].cpu(), dist[:P].cpu()
+        covered = set()
+        for j, i, r, d in zip(ps.tolist(), pd.tolist(), pr.tolist(), pdist.tolist()):
+            assert (j, i) in edges and (j, i) not in covered
+            assert d == float(nl.dist[edges[(j, i)]])
+            covered.add((j, i))
+            assert bool(r) == ((i, j) in edges)
+            if r:
+                assert j > i and (i, j) not in covered
+                covered.add((i, j))
+        assert covered == set(edges) and len(covered) == E
+        # sorted by (dst, src) inside a conformer, tiles cover [0, P) in 64-column chunks of one conformer
+        key = pd * (bb.z.numel() + 1) + ps
+        assert bool((key[1:] > key[:-1]).all())
+        t = tiles[: int(num)].cpu()
+        assert int(t[:, 5].sum()) == P and int(t[:, 5].max()) <= 64
+
+
+@pytest.mark.parametrize("pairs", [True, False])
+@pytest.mark.parametrize("n,B,cutoff", [(27, 8, 10.0), (65, 2, 10.0), (9, 4, 10.0), (45, 3, 5.0), (50, 2, 10.0)])
+def test_fused_weight_gradients_match_exact_recompute(n, B, cutoff, pairs):
+    """cmp_cfconv_fused_bwd_weights[_pairs] (TMEM-accumulated dW) vs the exact-fp32 recompute path."""
     _need_sm100()
+    ops.FUSED_PAIR_GRADS = pairs
+    try:
+        _check_fused_weight_gradients(n, B, cutoff)
+    finally:
+        ops.FUSED_PAIR_GRADS = True
+
+
+def _check_fused_weight_gradients(n, B, cutoff):
     torch.manual_seed(n)
     b = syn.make_batch(B, 3, n, seed=n + 1).to(DEV)
-    nl = cmp.build_neighbor_list(b.pos, b.batch, 10.0)
+    nl = cmp.build_neighbor_list(b.pos, b.batch, cutoff)
     F, Ng = 128, 50
-    blk = cmp.InteractionBlock(128, Ng, F, 10.0).to(DEV)
+    blk = cmp.InteractionBlock(128, Ng, F, cutoff).to(DEV)
     with torch.no_grad():
         blk.mlp[0].bias.add_(0.1 * torch.randn(F, device=DEV))
         blk.mlp[2].bias.add_(0.1 * torch.randn(F, device=DEV))
-    gs = cmp.GaussianSmearing(0.0, 10.0, Ng).to(DEV)
+    gs = cmp.GaussianSmearing(0.0, cutoff, Ng).to(DEV)
     xp = torch.randn(b.z.numel(), F, device=DEV, requires_grad=True)
     go = torch.randn(b.z.numel(), F, device=DEV)
     params = [blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight, blk.mlp[2].bias]
@@ -135,7 +175,7 @@ def test_fused_weight_gradients_match_exact_recompute(n, B):
     for fused in (False, True):
         ops.FUSED_WEIGHT_GRADS = fused
         try:
-            out = ops.cfconv_fused(xp, *params, nl, gs.offset, gs.coeff, 10.0)
+            out = ops.cfconv_fused(xp, *params, nl, gs.offset, gs.coeff, cutoff)
             res[fused] = torch.autograd.grad(out, [xp] + params, go)
         finally:
             ops.FUSED_WEIGHT_GRADS = True
@@ -144,12 +184,12 @@ def test_fused_weight_gradients_match_exact_recompute(n, B):
         assert rel_err(a, r) < 1e-2, name
     # and the exact (non-fused forward) autograd as ground truth
     rbf = gs(nl.edge_weight())
-    out_ref = ops.cfconv_message(xp, blk.conv.filter(rbf), nl, 10.0)
+    out_ref = ops.cfconv_message(xp, blk.conv.filter(rbf), nl, cutoff)
     ref = torch.autograd.grad(out_ref, [xp] + params, go)
     for name, a, r in zip(names, res[True], ref):
         assert rel_err(a, r) < 2e-2, name
     # deterministic
-    out = ops.cfconv_fused(xp, *params, nl, gs.offset, gs.coeff, 10.0)
+    out = ops.cfconv_fused(xp, *params, nl, gs.offset, gs.coeff, cutoff)
     again = torch.autograd.grad(out, [xp] + params, go)
     for a, r in zip(again, res[True]):
         assert torch.equal(a, r)
