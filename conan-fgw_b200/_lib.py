@@ -46,6 +46,7 @@ SIGNATURES = {
     "cmp_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, I, F, P]),
     "cmp_build_tiles_workspace": (S, [L]),
     "cmp_build_tiles": (I, [P, P, L, I, P, L, P, P, S, P, P]),
+    "cmp_build_tiles_min_atoms": (I, [P, P, L, I, I, P, L, P, P, S, P, P]),
     "cmp_gather_f32": (I, [P, P, P, L, P, P]),
     "cmp_cfconv_tc_supported": (I, [I, I]),
     "cmp_cfconv_tc_weights_bytes": (S, []),
@@ -85,6 +86,8 @@ SIGNATURES = {
     "cmp_cfconv_fused_bwd_workspace": (S, []),
     "cmp_cfconv_tc_pack_bwd_weights": (I, [P, P, P, I, I, P, P]),
     "cmp_cfconv_fused_bwd_weights": (I, [P, P, P, P, P, P, P, P, P, I, F, F, I, P, P, P, P, P, S, P]),
+    "cmp_cfconv_pair_max_atoms": (I, []),
+    "cmp_cfconv_pair_fwd": (I, [P, P, P, P, P, P, P, L, P, P, I, F, F, I, I, P, P]),
     "cmp_build_pair_list_workspace": (S, [L, L]),
     "cmp_build_pair_list": (I, [P, P, P, P, L, L, L, P, P, P, P, P, P, S, P, P]),
     "cmp_cfconv_fused_bwd_weights_pairs": (I, [P, P, P, P, P, P, P, P, P, P, I, F, F, I, P, P, P, P, P, S, P]),

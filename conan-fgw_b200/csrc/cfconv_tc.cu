@@ -97,6 +97,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
   uint8_t* sW2 = smem + W1_BYTES;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  // nothing to do (every conformer went to the pair kernel): leave before touching TMEM or the weight images
+  if (*p.num_tiles == 0) return;
 
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);

@@ -297,15 +297,17 @@ __device__ __forceinline__ int walk_tiles(const int32_t* __restrict__ rowptr, in
   return count;
 }
 
+// conformers with fewer than min_atoms atoms get no tiles (they belong to the pair kernel, cfconv_pair.cu)
 __global__ void tiles_count_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ seg_ptr, int64_t G,
-                                   int tile_edges, int32_t* __restrict__ counts, int* status) {
+                                   int tile_edges, int min_atoms, int32_t* __restrict__ counts, int* status) {
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
-  counts[g] = walk_tiles(rowptr, seg_ptr[g], seg_ptr[g + 1], tile_edges, nullptr, status);
+  const int s = seg_ptr[g], e = seg_ptr[g + 1];
+  counts[g] = (e - s < min_atoms) ? 0 : walk_tiles(rowptr, s, e, tile_edges, nullptr, status);
 }
 
 __global__ void tiles_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ seg_ptr, int64_t G,
-                                  int tile_edges, const int32_t* __restrict__ tile_ptr, int64_t cap,
+                                  int tile_edges, int min_atoms, const int32_t* __restrict__ tile_ptr, int64_t cap,
                                   int4* __restrict__ tiles, int32_t* __restrict__ num_tiles, int* status) {
   int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g == 0) *num_tiles = (tile_ptr[G] <= cap) ? tile_ptr[G] : 0;
@@ -314,6 +316,7 @@ __global__ void tiles_fill_kernel(const int32_t* __restrict__ rowptr, const int3
     if (g == 0) atomicOr(status, CMP_STATUS_EDGE_OVERFLOW);
     return;
   }
+  if (seg_ptr[g + 1] - seg_ptr[g] < min_atoms) return;
   walk_tiles(rowptr, seg_ptr[g], seg_ptr[g + 1], tile_edges, tiles + 2 * (int64_t)tile_ptr[g], status);
 }
 
@@ -477,9 +480,20 @@ extern "C" size_t cmp_build_tiles_workspace(int64_t G) {
   return align_up((size_t)(2 * G + 8) * sizeof(int32_t), 256);  // counts[G] + tile_ptr[G+1]
 }
 
+extern "C" int cmp_build_tiles_min_atoms(const int32_t* rowptr, const int32_t* seg_ptr, int64_t G, int tile_edges,
+                                         int min_atoms, void* tiles, int64_t cap_tiles, int32_t* num_tiles,
+                                         void* workspace, size_t workspace_bytes, int* status, cmp_stream_t stream);
+
 extern "C" int cmp_build_tiles(const int32_t* rowptr, const int32_t* seg_ptr, int64_t G, int tile_edges, void* tiles,
                                int64_t cap_tiles, int32_t* num_tiles, void* workspace, size_t workspace_bytes,
                                int* status, cmp_stream_t stream) {
+  return cmp_build_tiles_min_atoms(rowptr, seg_ptr, G, tile_edges, 0, tiles, cap_tiles, num_tiles, workspace,
+                                   workspace_bytes, status, stream);
+}
+
+extern "C" int cmp_build_tiles_min_atoms(const int32_t* rowptr, const int32_t* seg_ptr, int64_t G, int tile_edges,
+                                         int min_atoms, void* tiles, int64_t cap_tiles, int32_t* num_tiles,
+                                         void* workspace, size_t workspace_bytes, int* status, cmp_stream_t stream) {
   CMP_REQUIRE(G >= 0 && tile_edges >= 16 && cap_tiles >= 0, CMP_EINVAL, "cmp_build_tiles: bad size");
   CMP_REQUIRE(num_tiles && status, CMP_EINVAL, "cmp_build_tiles: null pointer");
   cudaStream_t st = as_stream(stream);
@@ -493,11 +507,13 @@ extern "C" int cmp_build_tiles(const int32_t* rowptr, const int32_t* seg_ptr, in
               "cmp_build_tiles: workspace too small");
   int32_t* counts = reinterpret_cast<int32_t*>(workspace);
   int32_t* tile_ptr = counts + G;
-  tiles_count_kernel<<<(unsigned)ceil_div(G, 128), 128, 0, st>>>(rowptr, seg_ptr, G, tile_edges, counts, status);
+  tiles_count_kernel<<<(unsigned)ceil_div(G, 128), 128, 0, st>>>(rowptr, seg_ptr, G, tile_edges, min_atoms, counts,
+                                                                status);
   CMP_LAUNCH_CHECK("cmp_build_tiles(count)");
   scan_conformers_kernel<<<1, 1024, 0, st>>>(counts, G, tile_ptr);
   CMP_LAUNCH_CHECK("cmp_build_tiles(scan)");
-  tiles_fill_kernel<<<(unsigned)ceil_div(G, 128), 128, 0, st>>>(rowptr, seg_ptr, G, tile_edges, tile_ptr, cap_tiles,
+  tiles_fill_kernel<<<(unsigned)ceil_div(G, 128), 128, 0, st>>>(rowptr, seg_ptr, G, tile_edges, min_atoms, tile_ptr,
+                                                               cap_tiles,
                                                                reinterpret_cast<int4*>(tiles), num_tiles, status);
   CMP_LAUNCH_CHECK("cmp_build_tiles(fill)");
   return CMP_OK;

@@ -74,36 +74,40 @@ class NeighborList:
         return self._edge_index
 
     # ---- edge tiles for the fused tensor-core kernels (built on first use, no host sync) ----------
-    def _build_tiles(self, rowptr):
+    def _build_tiles(self, rowptr, min_atoms=0):
         dev = rowptr.device
         tile_e = _lib.size_query("cmp_cfconv_tc_tile_edges")
         cap = self.cap_E // 64 + self.G + 1
         tiles = torch.empty(max(cap, 1), 8, dtype=torch.int32, device=dev)
         num = torch.zeros(1, dtype=torch.int32, device=dev)
         ws = _lib.workspace(_lib.size_query("cmp_build_tiles_workspace", self.G), dev)
-        _lib.call("cmp_build_tiles", _lib.ptr(rowptr), _lib.ptr(self.seg_ptr), self.G, tile_e, _lib.ptr(tiles), cap,
-                  _lib.ptr(num), _lib.ptr(ws), ws.numel(), _lib.ptr(self.status))
+        _lib.call("cmp_build_tiles_min_atoms", _lib.ptr(rowptr), _lib.ptr(self.seg_ptr), self.G, tile_e, int(min_atoms),
+                  _lib.ptr(tiles), cap, _lib.ptr(num), _lib.ptr(ws), ws.numel(), _lib.ptr(self.status))
         return tiles, num
 
-    def tiles(self):
-        """(tiles int32[cap,8], num_tiles int32[1]) over the target-sorted CSR."""
-        if getattr(self, "_tiles", None) is None:
+    def tiles(self, min_atoms=0):
+        """(tiles int32[cap,8], num_tiles int32[1]) over the target-sorted CSR; conformers with fewer than
+        ``min_atoms`` atoms are left out (they go to the pair kernel)."""
+        cache = self.__dict__.setdefault("_tiles", {})
+        if min_atoms not in cache:
             if self.G == 0 and self.N > 0:
                 raise _lib.ConanMPError("edge tiles need conformer segments (graph was built from a raw edge_index)")
-            self._tiles = self._build_tiles(self.rowptr)
-        return self._tiles
+            cache[min_atoms] = self._build_tiles(self.rowptr, min_atoms)
+        return cache[min_atoms]
 
-    def tiles_t(self):
+    def tiles_t(self, min_atoms=0):
         """Same for the source-sorted transpose, plus ``dist_t`` (distances in transposed edge order)."""
-        if getattr(self, "_tiles_t", None) is None:
+        cache = self.__dict__.setdefault("_tiles_t", {})
+        if min_atoms not in cache:
             if self.rowptr_t is None:
                 raise _lib.ConanMPError("the transposed neighbour list was not built")
-            tiles, num = self._build_tiles(self.rowptr_t)
-            dist_t = torch.empty_like(self.dist)
-            _lib.call("cmp_gather_f32", _lib.ptr(self.dist), _lib.ptr(self.eid_t), _lib.ptr(self.rowptr[self.N:]),
-                      self.cap_E, _lib.ptr(dist_t))
-            self._tiles_t = (tiles, num, dist_t)
-        return self._tiles_t
+            tiles, num = self._build_tiles(self.rowptr_t, min_atoms)
+            if getattr(self, "_dist_t", None) is None:
+                self._dist_t = torch.empty_like(self.dist)
+                _lib.call("cmp_gather_f32", _lib.ptr(self.dist), _lib.ptr(self.eid_t), _lib.ptr(self.rowptr[self.N:]),
+                          self.cap_E, _lib.ptr(self._dist_t))
+            cache[min_atoms] = (tiles, num, self._dist_t)
+        return cache[min_atoms]
 
     def erow(self) -> torch.Tensor:
         """Target atom of every edge (``edge_index[1]`` as int32), built once."""

@@ -387,6 +387,35 @@ def _fused_fwd_launch(xin, dist, rowptr, col, tiles, num_tiles, packed, offset, 
     return out
 
 
+# conformers of <= cmp_cfconv_pair_max_atoms() atoms: one filter evaluation per undirected pair (cfconv_pair.cu); larger
+# ones stay on the per-edge kernel.  False = per-edge kernel for everything (kept for cross-checking).
+FUSED_PAIR_FORWARD = True
+
+
+def _fused_aggregate(xin, graph, packed, offset, coeff, cutoff, transposed):
+    """agg = sum_j x_j * W(d_ij) C(d_ij) over the neighbour list (or its transpose) on the fused tcgen05 kernels."""
+    e_hint = graph._E if graph._E is not None else graph.cap_E
+    pairs = FUSED_PAIR_FORWARD and graph.G > 0
+    min_atoms = _lib.size_query("cmp_cfconv_pair_max_atoms") + 1 if pairs else 0
+    if transposed:
+        tiles, num, dist = graph.tiles_t(min_atoms)
+        rowptr, col = graph.rowptr_t, graph.col_t
+    else:
+        tiles, num = graph.tiles(min_atoms)
+        dist, rowptr, col = graph.dist, graph.rowptr, graph.col
+    # zero-fills the output and serves the conformers the pair kernel does not take (their share of the work is
+    # not known on the host without a sync: the algorithmic FLOPs are booked on the pair launch)
+    out = _fused_fwd_launch(xin, dist, rowptr, col, tiles, num, packed, offset, coeff, cutoff, 0 if pairs else e_hint)
+    if pairs:
+        N, F = xin.shape
+        Ng = offset.numel()
+        psrc, pdst, pdist, prev, _, _, conf_ptr = graph.pair_tiles()
+        call("cmp_cfconv_pair_fwd", ptr(xin), ptr(graph.seg_ptr), ptr(conf_ptr), ptr(psrc), ptr(pdst), ptr(pdist),
+             ptr(prev), graph.G, ptr(packed), ptr(offset), Ng, float(coeff), float(cutoff), F, int(bool(transposed)),
+             ptr(out), work=2.0 * (Ng * F + F * F) * float(e_hint))
+    return out
+
+
 def pack_filter_weights(W1, b1, W2, b2):
     F, Ng = W1.shape
     nbytes = _lib.size_query("cmp_cfconv_tc_weights_bytes")
@@ -407,10 +436,7 @@ class _CFConvFusedFn(Function):
     def forward(ctx, xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff):
         xprime = _f32c(xprime)
         packed = pack_filter_weights(W1, b1, W2, b2)
-        tiles, num = graph.tiles()
-        e_hint = graph._E if graph._E is not None else graph.cap_E
-        agg = _fused_fwd_launch(xprime, graph.dist, graph.rowptr, graph.col, tiles, num, packed, offset, coeff,
-                                cutoff, e_hint)
+        agg = _fused_aggregate(xprime, graph, packed, offset, coeff, cutoff, transposed=False)
         ctx.graph, ctx.coeff, ctx.cutoff = graph, float(coeff), float(cutoff)
         ctx.save_for_backward(xprime, W1, b1, W2, b2, offset, packed)
         return agg
@@ -423,10 +449,9 @@ class _CFConvFusedFn(Function):
         N, F = xprime.shape
         dx = None
         if ctx.needs_input_grad[0]:
-            tiles_t, num_t, dist_t = graph.tiles_t()
-            e_hint = graph._E if graph._E is not None else graph.cap_E
-            dx = _fused_fwd_launch(g, dist_t, graph.rowptr_t, graph.col_t, tiles_t, num_t, packed, offset, ctx.coeff,
-                                   ctx.cutoff, e_hint)
+            if graph.rowptr_t is None:
+                raise _lib.ConanMPError("cfconv backward needs the transposed neighbour list")
+            dx = _fused_aggregate(g, graph, packed, offset, ctx.coeff, ctx.cutoff, transposed=True)
         grads = [None, None, None, None]
         if any(ctx.needs_input_grad[1:5]):
             if FUSED_WEIGHT_GRADS:

@@ -185,6 +185,10 @@ size_t cmp_build_tiles_workspace(int64_t G);
 int cmp_build_tiles(const int32_t* rowptr, const int32_t* seg_ptr, int64_t G, int tile_edges,
                     void* tiles, int64_t cap_tiles, int32_t* num_tiles, void* workspace,
                     size_t workspace_bytes, int* status, cmp_stream_t stream);
+/* Same, skipping conformers with fewer than min_atoms atoms (those are served by cmp_cfconv_pair_fwd). */
+int cmp_build_tiles_min_atoms(const int32_t* rowptr, const int32_t* seg_ptr, int64_t G, int tile_edges,
+                              int min_atoms, void* tiles, int64_t cap_tiles, int32_t* num_tiles,
+                              void* workspace, size_t workspace_bytes, int* status, cmp_stream_t stream);
 
 /* dst[i] = src[idx[i]] for i < *count_ptr (per-edge data in transposed order, no host sync). */
 int cmp_gather_f32(const float* src, const int32_t* idx, const int32_t* count_ptr,
@@ -208,6 +212,20 @@ int cmp_cfconv_fused_fwd(const float* xprime, const float* dist, const int32_t* 
                          const void* packed_weights, const float* offset, int num_gaussians,
                          float coeff, float cutoff, int64_t N, int num_filters, float* agg,
                          cmp_stream_t stream);
+
+/* The same aggregation for conformers of at most cmp_cfconv_pair_max_atoms() (32) atoms, one filter evaluation per
+ * UNDIRECTED pair (cmp_build_pair_list): the filter depends on d_ij only, so j -> i and i -> j share it.  One CTA per
+ * conformer at a time (x rows staged in shared memory by a TMA bulk copy, per-pipeline [atoms, F] accumulators in
+ * shared memory, summed in a fixed order: deterministic, no atomics).  Rows of larger conformers (and of conformers
+ * without edges) are NOT written: run cmp_cfconv_fused_fwd first with tiles from
+ * cmp_build_tiles_min_atoms(min_atoms = 33) - it zero-fills `agg` and serves the large conformers.
+ * transposed = 1 exchanges the two directions of every pair (the d x' pass of the backward, x = dL/dagg). */
+int cmp_cfconv_pair_max_atoms(void);
+int cmp_cfconv_pair_fwd(const float* x, const int32_t* seg_ptr, const int32_t* conf_pair_ptr,
+                        const int32_t* pair_src, const int32_t* pair_dst, const float* pair_dist,
+                        const int32_t* pair_rev, int64_t G, const void* packed_weights,
+                        const float* offset, int num_gaussians, float coeff, float cutoff,
+                        int num_filters, int transposed, float* agg, cmp_stream_t stream);
 
 /* Filter-MLP weight gradients of the fused CFConv in ONE kernel (+ a fixed-order reduction of the
  * per-pipeline partial sums): recomputes rbf / hidden / a' per 64-edge tile on chip and accumulates

@@ -146,6 +146,68 @@ def test_pair_list_has_one_representative_per_undirected_pair():
         assert int(t[:, 5].sum()) == P and int(t[:, 5].max()) <= 64
 
 
+@pytest.mark.parametrize("case", ["complete27", "tiny", "capped", "mixed", "single_pair"])
+def test_pair_kernel_matches_per_edge_kernel_and_exact_path(case):
+    """cmp_cfconv_pair_fwd (one filter evaluation per undirected pair, small conformers) against the per-edge fused
+    kernel and the exact-fp32 message path, forward and d x' (transposed pass); unpaired edges (neighbour cap) and
+    batches that mix small and large conformers included."""
+    _need_sm100()
+    torch.manual_seed(3)
+    mnn = 32
+    if case == "complete27":
+        b = syn.make_batch(5, 3, 27, seed=11).to(DEV)
+        z, pos, batch, G = b.z, b.pos, b.batch, b.num_graphs
+    elif case == "tiny":
+        b = syn.make_batch(40, 2, 3, seed=12).to(DEV)
+        z, pos, batch, G = b.z, b.pos, b.batch, b.num_graphs
+    elif case == "capped":            # 24 atoms but only 6 neighbours kept: many edges lose their reverse
+        b = syn.make_batch(4, 3, 24, seed=13).to(DEV)
+        z, pos, batch, G = b.z, b.pos, b.batch, b.num_graphs
+        mnn = 6
+    elif case == "mixed":             # 20- and 32-atom conformers (pair kernel) next to 33- and 50-atom ones (per-edge)
+        parts = [syn.make_batch(3, 2, n, seed=20 + n).to(DEV) for n in (20, 50, 32, 33)]
+        z, pos, batch, G = parts[0].z, parts[0].pos, parts[0].batch, parts[0].num_graphs
+        for q in parts[1:]:
+            z, pos, batch, G = (torch.cat([z, q.z]), torch.cat([pos, q.pos]), torch.cat([batch, q.batch + G]),
+                                G + q.num_graphs)
+    else:                             # two atoms: one pair, one tile of a single column
+        pos = torch.tensor([[0.0, 0.0, 0.0], [1.2, 0.1, 0.0]], device=DEV)
+        batch = torch.zeros(2, dtype=torch.long, device=DEV)
+        G = 1
+    nl = cmp.build_neighbor_list(pos, batch, 10.0, max_num_neighbors=mnn, num_graphs=G)
+    N = pos.size(0)
+    F, Ng = 128, 50
+    blk = cmp.InteractionBlock(128, Ng, F, 10.0).to(DEV)
+    with torch.no_grad():
+        blk.mlp[0].bias.add_(0.1 * torch.randn(F, device=DEV))
+        blk.mlp[2].bias.add_(0.1 * torch.randn(F, device=DEV))
+    gs = cmp.GaussianSmearing(0.0, 10.0, Ng).to(DEV)
+    params = [blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight, blk.mlp[2].bias]
+    xp = torch.randn(N, F, device=DEV, requires_grad=True)
+    go = torch.randn(N, F, device=DEV)
+    res = {}
+    for pairs in (False, True):
+        ops.FUSED_PAIR_FORWARD = pairs
+        try:
+            out = ops.cfconv_fused(xp, *params, nl, gs.offset, gs.coeff, 10.0)
+            (dx,) = torch.autograd.grad(out, [xp], go)
+            out2 = ops.cfconv_fused(xp, *params, nl, gs.offset, gs.coeff, 10.0)
+            (dx2,) = torch.autograd.grad(out2, [xp], go)
+        finally:
+            ops.FUSED_PAIR_FORWARD = True
+        assert torch.equal(out, out2) and torch.equal(dx, dx2)          # bit-reproducible
+        res[pairs] = (out.detach(), dx)
+    nl.check()
+    # same bf16 filter, different summation order only
+    assert rel_err(res[True][0], res[False][0]) < 2e-5
+    assert rel_err(res[True][1], res[False][1]) < 2e-5
+    rbf = gs(nl.edge_weight())
+    ref = ops.cfconv_message(xp, blk.conv.filter(rbf), nl, 10.0)
+    (dref,) = torch.autograd.grad(ref, [xp], go)
+    assert rel_err(res[True][0], ref) < TOL_BF16
+    assert rel_err(res[True][1], dref) < TOL_BF16
+
+
 @pytest.mark.parametrize("pairs", [True, False])
 @pytest.mark.parametrize("n,B,cutoff", [(27, 8, 10.0), (65, 2, 10.0), (9, 4, 10.0), (45, 3, 5.0), (50, 2, 10.0)])
 def test_fused_weight_gradients_match_exact_recompute(n, B, cutoff, pairs):
