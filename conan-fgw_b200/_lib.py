@@ -77,6 +77,7 @@ SIGNATURES = {
     "cmp_vis_edge_update_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, P, P, P]),
     "cmp_debug_set_fwd_timestamps": (None, [P]),
     "cmp_debug_set_bwd_timestamps": (None, [P]),
+    "cmp_debug_set_pair_timestamps": (None, [P]),
     "cmp_csr_expand_rows": (I, [P, L, P, P]),
     "cmp_cfconv_tc_bwd_tile_edges": (I, []),
     "cmp_build_flat_tiles_workspace": (S, [L]),

@@ -69,6 +69,7 @@ struct PairParams {
   int Ng;
   int G;
   int transposed;
+  long long* dbg;                  // optional clock64 timeline of CTA 0, pipeline 0 (10 stamps per tile, 24 tiles)
 };
 
 __device__ __forceinline__ float softplus_fast(float x) {
@@ -194,6 +195,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
       const int ntiles = (np + TE - 1) / TE;
 
       // every pipeline is done with the previous conformer (x rows, accumulators)
+      const bool rec = p.dbg && blockIdx.x == 0 && tid == 0 && it < 24;
+      long long t_conf = 0;
+      if (rec) t_conf = clock64();
       tc::named_bar_sync(CTA_BAR, NCOMP);
       if (tid == 0) {
         tc::fence_proxy_async();
@@ -227,7 +231,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
         const int ne = min(TE, np - k * TE);
         const int npad = (ne + 15) & ~15;
         const uint32_t par = it & 1;
+        if (rec) { p.dbg[it * 10 + 0] = t_conf; p.dbg[it * 10 + 1] = clock64(); }
         tc::named_bar_sync(1 + g, GT);   // previous tile of this pipeline consumed (images, metadata); acc zeroed
+        if (rec) p.dbg[it * 10 + 2] = clock64();
 
         // ---- per-pair metadata (warps 0, 1 of the pipeline) ----
         if (tt < TE) {
@@ -268,6 +274,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
                            tc::pack_bf16x2(v[6], v[7]));
           }
         }
+        if (rec) p.dbg[it * 10 + 3] = clock64();
         tc::fence_proxy_async();
         tc::mbar_arrive(b1ready);
         if (k + NG < ntiles) prefetch(k + NG);
@@ -275,6 +282,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
         // ---- epilogue 1: a' = C * ssp(D1) -> B2 (MN-major [144, pair]) ----
         tc::mbar_wait(d1ready, par);
         tc::tc_fence_after();
+        if (rec) p.dbg[it * 10 + 4] = clock64();
         {
           uint8_t* colp = sB + chan * 16;
           for (int c0 = 0; c0 < npad; c0 += 16) {
@@ -309,6 +317,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
             *reinterpret_cast<uint4*>(sB + ec * A2_SBO + (128 + kr) * 16) = w;
           }
         }
+        if (rec) p.dbg[it * 10 + 5] = clock64();
         tc::tc_fence_before();
         tc::fence_proxy_async();
         tc::mbar_arrive(b2ready);
@@ -316,6 +325,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
         // ---- epilogue 2: both directions of every pair, accumulated in shared memory ----
         tc::mbar_wait(d2ready, par);
         tc::tc_fence_after();
+        if (rec) p.dbg[it * 10 + 6] = clock64();
         if (!x_ready) {
           tc::mbar_wait(xbar, xphase & 1);
           x_ready = true;
@@ -383,6 +393,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
             }
           }
         }
+        if (rec) p.dbg[it * 10 + 7] = clock64();
         tc::tc_fence_before();
       }
       ++xphase;
@@ -401,6 +412,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
           outp[item] = s;
         }
       }
+      if (rec && it > 0) p.dbg[(it - 1) * 10 + 8] = clock64();   // finalize of the conformer this tile belonged to
     }
   }
 
@@ -413,6 +425,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
 }  // namespace cmp
 
 using namespace cmp;
+
+static long long* g_pair_dbg = nullptr;
+extern "C" void cmp_debug_set_pair_timestamps(void* buf) { g_pair_dbg = reinterpret_cast<long long*>(buf); }
 
 extern "C" int cmp_cfconv_pair_max_atoms(void) { return NCAP; }
 
@@ -459,6 +474,7 @@ extern "C" int cmp_cfconv_pair_fwd(const float* x, const int32_t* seg_ptr, const
   p.Ng = num_gaussians;
   p.G = (int)G;
   p.transposed = transposed;
+  p.dbg = g_pair_dbg;
   const int grid = (int)std::min<int64_t>(G, sm_count());
   cfconv_pair_kernel<<<grid, CTA_THREADS, SMEM_BYTES, st>>>(p);
   CMP_LAUNCH_CHECK("cmp_cfconv_pair_fwd");

@@ -365,6 +365,8 @@ int cmp_vis_edge_update_bwd(const float* gw, const float* wt, const float* ws, c
 /* Debug hook: when non-NULL, CTA 0 / pipeline 0 of cmp_cfconv_fused_fwd stores 8 clock64() phase
  * timestamps per tile (first 32 tiles) into this device buffer of 256 int64. */
 void cmp_debug_set_fwd_timestamps(void* buf);
+/* Same for cmp_cfconv_pair_fwd: 10 timestamps per tile of pipeline 0 (first 24 tiles), 240 int64. */
+void cmp_debug_set_pair_timestamps(void* buf);
 /* Same for cmp_cfconv_fused_bwd_weights: 12 timestamps per tile (first 20 tiles), 240 int64. */
 void cmp_debug_set_bwd_timestamps(void* buf);
 
