@@ -354,7 +354,7 @@ def run_ours(args):
         resident_step()      # identical on every rank (each step holds a collective)
     torch.cuda.synchronize()
     dominant = ["cmp_gemm_f32", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd", "cmp_cfconv_fused_bwd_weights",
-                "cmp_cfconv_fused_bwd_weights_pairs", "cmp_node_gemm_fwd",
+                "cmp_cfconv_fused_bwd_weights_pairs", "cmp_node_gemm_dw_grouped", "cmp_node_gemm_fwd",
                 "cmp_node_gemm_dw"]
     total_ms, launches, kt = timed(resident_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
@@ -417,6 +417,7 @@ def run_ours(args):
                                               "dW accumulated in TMEM; algorithmic FLOPs counted per directed edge)",
         "cmp_node_gemm_fwd": "node_gemm_fwd_kernel (tcgen05 split-bf16 node linears)",
         "cmp_node_gemm_dw": "node_gemm_dw_kernel (tcgen05 split-bf16 weight gradients of the node linears)",
+        "cmp_node_gemm_dw_grouped": "node_gemm_dw_grouped_kernel (all node-linear weight gradients of the step in one launch)",
     }
     roofline = {
         "kernel": kernel_names[top],

@@ -87,6 +87,9 @@ SIGNATURES = {
     "cmp_cfconv_fused_bwd_workspace": (S, []),
     "cmp_cfconv_tc_pack_bwd_weights": (I, [P, P, P, I, I, P, P]),
     "cmp_cfconv_fused_bwd_weights": (I, [P, P, P, P, P, P, P, P, P, I, F, F, I, P, P, P, P, P, S, P]),
+    "cmp_node_gemm_dw_group_max": (I, []),
+    "cmp_node_gemm_dw_grouped_workspace": (S, []),
+    "cmp_node_gemm_dw_grouped": (I, [P, I, P, S, P]),
     "cmp_cfconv_pair_max_atoms": (I, []),
     "cmp_cfconv_pair_fwd": (I, [P, P, P, P, P, P, P, L, P, P, I, F, F, I, I, P, P]),
     "cmp_build_pair_list_workspace": (S, [L, L]),
@@ -104,6 +107,13 @@ _launches = 0  # number of C-ABI compute calls issued (bench.py reports it)
 
 class ConanMPError(RuntimeError):
     pass
+
+
+class DwProblem(ctypes.Structure):
+    """``cmp_dw_problem_t`` of include/conanmp.h (one weight-gradient problem of a grouped launch)."""
+    _fields_ = [("dY", ctypes.c_void_p), ("lddy", ctypes.c_int64), ("saved_y", ctypes.c_void_p),
+                ("ldys", ctypes.c_int64), ("X", ctypes.c_void_p), ("ldx", ctypes.c_int64), ("M", ctypes.c_int64),
+                ("K", ctypes.c_int32), ("Nout", ctypes.c_int32), ("dW", ctypes.c_void_p), ("db", ctypes.c_void_p)]
 
 
 def register(extra: dict):

@@ -18,7 +18,9 @@
 namespace cmp {
 namespace {
 
-constexpr int TM = 128;            // atoms per tile of the weight-gradient kernel (UMMA K runs over atoms)
+constexpr int TM = 64;             // atoms per tile of the weight-gradient kernels (UMMA K runs over atoms); two CTAs
+                                   // per SM overlap each other's operand loads, conversions and MMAs
+constexpr int TMG = TM / 8;        // 8-atom groups per tile
 constexpr int TMF = 64;            // atoms per tile of the forward / dX kernel: 2 CTAs per SM hide each other's loads
 constexpr int CW = 8;              // compute warps
 constexpr int NT = CW * 32 + 32;   // + 1 MMA warp
@@ -221,7 +223,9 @@ struct DwParams {
   int K, Nout;
 };
 
-__global__ void __launch_bounds__(NT, 1) node_gemm_dw_kernel(const DwParams p) {
+// One CTA's share of a weight-gradient problem: tiles [rank, rank+1) * ntiles / nranks, accumulated in TMEM, written
+// as a [128][K + 16] partial block to `part`.
+__device__ __forceinline__ void node_dw_body(const DwParams& p, int rank, int nranks, float* __restrict__ part) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bars[2];   // ready (images written), done (MMAs finished)
   __shared__ uint32_t tmem_base_s;
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(NT, 1) node_gemm_dw_kernel(const DwParams p) {
   const int K = p.K, Nout = p.Nout;
   const int KX = K + 16;                             // + ones column block (bias gradient)
   const uint32_t sbo_y = (Nout >> 3) * 128, sbo_x = (KX >> 3) * 128;
-  const uint32_t y_bytes = 16 * sbo_y + 2048, x_bytes = 16 * sbo_x;   // slack: M = 128 view of a 64-channel image
+  const uint32_t y_bytes = TMG * sbo_y + 2048, x_bytes = TMG * sbo_x;   // slack: M = 128 view of a 64-channel image
   uint8_t* sYh = smem;
   uint8_t* sYl = sYh + y_bytes;
   uint8_t* sXh = sYl + y_bytes;
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(NT, 1) node_gemm_dw_kernel(const DwParams p) {
   const uint32_t tmem_base = tmem_base_s;
   const int64_t ntiles = (p.M + TM - 1) / TM;
   // contiguous tile range per CTA
-  const int64_t t0 = (int64_t)blockIdx.x * ntiles / gridDim.x, t1 = (int64_t)(blockIdx.x + 1) * ntiles / gridDim.x;
+  const int64_t t0 = (int64_t)rank * ntiles / nranks, t1 = (int64_t)(rank + 1) * ntiles / nranks;
 
   if (warp == CW) {
     if (lane == 0) {
@@ -283,7 +287,6 @@ __global__ void __launch_bounds__(NT, 1) node_gemm_dw_kernel(const DwParams p) {
     const int wq = warp & 3, h = warp >> 2;
     const int chan = wq * 32 + lane;
     const uint32_t tD = tmem_base + ((uint32_t)(wq * 32) << 16);
-    float* part = p.partial + (int64_t)blockIdx.x * 128 * KX;
     const bool any = t0 < t1;
     if (any) {
       tc::mbar_wait(&bars[1], (it - 1) & 1);
@@ -308,6 +311,49 @@ __global__ void __launch_bounds__(NT, 1) node_gemm_dw_kernel(const DwParams p) {
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+}
+
+__global__ void __launch_bounds__(NT, 2) node_gemm_dw_kernel(const DwParams p) {
+  node_dw_body(p, blockIdx.x, gridDim.x, p.partial + (int64_t)blockIdx.x * 128 * (p.K + 16));
+}
+
+// ---- grouped launch: many weight-gradient problems share one grid (the node linears of a whole backward pass) ----
+constexpr int MAX_GROUP = 32;
+constexpr int PART_STRIDE = 128 * (MAXC + 16);      // floats per CTA in the grouped workspace
+
+struct DwGroupEntry {
+  DwParams p;        // p.partial unused
+  float* dW;
+  float* db;
+  int cta_begin, cta_count;
+};
+
+struct DwGroup {
+  DwGroupEntry e[MAX_GROUP];
+  float* partial;    // [gridDim.x][PART_STRIDE]
+  int count;
+};
+
+__global__ void __launch_bounds__(NT, 2) node_gemm_dw_grouped_kernel(const __grid_constant__ DwGroup g) {
+  int idx = 0;
+  for (int i = 1; i < g.count; ++i)
+    if ((int)blockIdx.x >= g.e[i].cta_begin) idx = i;
+  const DwGroupEntry& en = g.e[idx];
+  node_dw_body(en.p, (int)blockIdx.x - en.cta_begin, en.cta_count, g.partial + (int64_t)blockIdx.x * PART_STRIDE);
+}
+
+// dW / db of problem blockIdx.y = sum of its CTAs' partial blocks in CTA order (fixed order: deterministic)
+__global__ void node_dw_grouped_reduce_kernel(const __grid_constant__ DwGroup g) {
+  const DwGroupEntry& en = g.e[blockIdx.y];
+  const int K = en.p.K, Nout = en.p.Nout, KX = K + 16;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Nout * (K + 1)) return;
+  const int n = i / (K + 1), k = i % (K + 1);
+  const float* src = g.partial + (int64_t)en.cta_begin * PART_STRIDE + n * KX + k;
+  float s = 0.0f;
+  for (int c = 0; c < en.cta_count; ++c) s += src[(int64_t)c * PART_STRIDE];
+  if (k < K) en.dW[n * K + k] = s;
+  else if (en.db) en.db[n] = s;
 }
 
 __global__ void node_dw_reduce_kernel(const float* __restrict__ partial, int P, int K, int Nout, float* __restrict__ dW,
@@ -429,9 +475,9 @@ extern "C" int cmp_node_gemm_dw(const float* dY, int64_t lddy, const float* save
               "cmp_node_gemm_dw: workspace too small");
   CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED, "cmp_node_gemm_dw: needs an sm_100 device (tcgen05)");
   const int KX = K + 16;
-  const size_t smem = (size_t)2 * (16 * (Nout / 8) * 128 + 2048) + (size_t)2 * 16 * (KX / 8) * 128;
+  const size_t smem = (size_t)2 * (TMG * (Nout / 8) * 128 + 2048) + (size_t)2 * TMG * (KX / 8) * 128;
   if (cudaFuncSetAttribute(node_gemm_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           2 * (16 * (MAXC / 8) * 128 + 2048) + 2 * 16 * ((MAXC + 16) / 8) * 128) != cudaSuccess) {
+                           2 * (TMG * (MAXC / 8) * 128 + 2048) + 2 * TMG * ((MAXC + 16) / 8) * 128) != cudaSuccess) {
     (void)cudaGetLastError();
     set_error("cmp_node_gemm_dw: cannot opt in to shared memory");
     return CMP_ECUDA;
@@ -445,5 +491,115 @@ extern "C" int cmp_node_gemm_dw(const float* dY, int64_t lddy, const float* save
   node_dw_reduce_kernel<<<(Nout * (K + 1) + 31) / 32, dim3(32, 8), 0, as_stream(stream)>>>(p.partial, grid, K, Nout, dW,
                                                                                           db);
   CMP_LAUNCH_CHECK("cmp_node_gemm_dw(reduce)");
+  return CMP_OK;
+}
+
+// ---- grouped weight gradients ------------------------------------------------------------------------
+// Mirrors cmp_dw_problem_t of include/conanmp.h.
+struct cmp_dw_problem_host {
+  const float* dY;
+  int64_t lddy;
+  const float* saved_y;
+  int64_t ldys;
+  const float* X;
+  int64_t ldx;
+  int64_t M;
+  int32_t K;
+  int32_t Nout;
+  float* dW;
+  float* db;
+};
+
+extern "C" int cmp_node_gemm_dw_group_max(void) { return MAX_GROUP; }
+
+extern "C" size_t cmp_node_gemm_dw_grouped_workspace(void) {
+  return align_up((size_t)2 * sm_count() * PART_STRIDE * sizeof(float), 256);
+}
+
+extern "C" int cmp_node_gemm_dw_grouped(const void* problems, int count, void* workspace, size_t workspace_bytes,
+                                        cmp_stream_t stream) {
+  CMP_REQUIRE(count >= 0 && count <= MAX_GROUP, CMP_EINVAL, "cmp_node_gemm_dw_grouped: count must be in [0, %d]", MAX_GROUP);
+  if (count == 0) return CMP_OK;
+  CMP_REQUIRE(problems, CMP_EINVAL, "cmp_node_gemm_dw_grouped: null pointer");
+  CMP_REQUIRE(workspace && workspace_bytes >= cmp_node_gemm_dw_grouped_workspace(), CMP_EWORKSPACE,
+              "cmp_node_gemm_dw_grouped: workspace too small");
+  CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED, "cmp_node_gemm_dw_grouped: needs an sm_100 device (tcgen05)");
+  const cmp_dw_problem_host* pr = reinterpret_cast<const cmp_dw_problem_host*>(problems);
+  const int G = 2 * sm_count();   // two resident CTAs per SM
+  CMP_REQUIRE(count <= G, CMP_EUNSUPPORTED, "cmp_node_gemm_dw_grouped: more problems than CTA slots");
+  DwGroup g;
+  int64_t tiles[MAX_GROUP];
+  int64_t total = 0;
+  for (int i = 0; i < count; ++i) {
+    const cmp_dw_problem_host& q = pr[i];
+    CMP_REQUIRE(q.M >= 0, CMP_EINVAL, "cmp_node_gemm_dw_grouped: negative size");
+    CMP_REQUIRE(dims_ok(q.K, q.Nout), CMP_EUNSUPPORTED,
+                "cmp_node_gemm_dw_grouped: K / Nout must be multiples of 16 in [16,128]");
+    CMP_REQUIRE(q.dW && (q.M == 0 || (q.dY && q.X)), CMP_EINVAL, "cmp_node_gemm_dw_grouped: null pointer");
+    CMP_REQUIRE(q.lddy % 4 == 0 && q.ldx % 4 == 0 && (uintptr_t)q.dY % 16 == 0 && (uintptr_t)q.X % 16 == 0 &&
+                    (!q.saved_y || (q.ldys % 4 == 0 && (uintptr_t)q.saved_y % 16 == 0)),
+                CMP_EINVAL, "cmp_node_gemm_dw_grouped: operands must be 16-byte aligned with ld % 4 == 0");
+    tiles[i] = q.M > 0 ? ceil_div(q.M, (int64_t)TM) : 1;
+    total += tiles[i];
+    g.e[i].p = DwParams{q.dY, q.lddy, q.saved_y, q.ldys, q.X, q.ldx, nullptr, q.M, q.K, q.Nout};
+    g.e[i].dW = q.dW;
+    g.e[i].db = q.db;
+  }
+  // CTAs per problem: proportional to its tiles, at least one, never more than its tiles; spare CTAs go to the
+  // problems with the most tiles per CTA
+  int cta[MAX_GROUP];
+  int used = 0;
+  for (int i = 0; i < count; ++i) {
+    int64_t c = (int64_t)G * tiles[i] / total;
+    if (c < 1) c = 1;
+    if (c > tiles[i]) c = tiles[i];
+    cta[i] = (int)c;
+    used += cta[i];
+  }
+  while (used > G) {
+    int big = 0;
+    for (int i = 1; i < count; ++i)
+      if (cta[i] > cta[big]) big = i;
+    --cta[big];
+    --used;
+  }
+  while (used < G) {
+    int best = -1;
+    double load = 1.0;   // only problems with more than one tile per CTA can use another CTA
+    for (int i = 0; i < count; ++i) {
+      const double l = (double)tiles[i] / cta[i];
+      if (cta[i] < tiles[i] && l > load) {
+        load = l;
+        best = i;
+      }
+    }
+    if (best < 0) break;
+    ++cta[best];
+    ++used;
+  }
+  int begin = 0;
+  for (int i = 0; i < count; ++i) {
+    g.e[i].cta_begin = begin;
+    g.e[i].cta_count = cta[i];
+    begin += cta[i];
+  }
+  g.partial = reinterpret_cast<float*>(workspace);
+  g.count = count;
+  static bool attr_set = false;
+  const int smem = 2 * (TMG * (MAXC / 8) * 128 + 2048) + 2 * TMG * ((MAXC + 16) / 8) * 128;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(node_gemm_dw_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("cmp_node_gemm_dw_grouped: cannot opt in to shared memory");
+      return CMP_ECUDA;
+    }
+    attr_set = true;
+  }
+  cudaStream_t st = as_stream(stream);
+  node_gemm_dw_grouped_kernel<<<begin, NT, smem, st>>>(g);
+  CMP_LAUNCH_CHECK("cmp_node_gemm_dw_grouped");
+  node_dw_grouped_reduce_kernel<<<dim3((MAXC * (MAXC + 1) + 127) / 128, count), 128, 0, st>>>(g);
+  CMP_LAUNCH_CHECK("cmp_node_gemm_dw_grouped(reduce)");
   return CMP_OK;
 }

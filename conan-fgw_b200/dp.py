@@ -114,7 +114,10 @@ class RegressionStep:
     def _fwd_bwd(self, z, pos, batch, targets, num_graphs):
         self.flat.zero_grad()
         loss = self.loss(z, pos, batch, targets, num_graphs)
-        loss.backward()
+        # parameter gradients are None here and every parameter is used once: the node-linear weight gradients can be
+        # queued during backward and issued as ONE grouped launch at its end
+        with ops.deferred_weight_grads():
+            loss.backward()
         self.flat.collect_grads()
         return loss.detach()
 

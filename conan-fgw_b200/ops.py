@@ -6,6 +6,8 @@ the current stream.  Nothing here falls back to a PyTorch implementation.
 
 from __future__ import annotations
 
+import ctypes
+
 import torch
 from torch.autograd import Function
 
@@ -226,6 +228,48 @@ class _LinearTCBlockedFn(Function):
         return dx, dw, db, dres
 
 
+class deferred_weight_grads:
+    """Inside this context the tensor-core Linears do not launch their weight-gradient GEMMs one by one during
+    ``backward()``: they return (still unwritten) gradient tensors and queue the problem; leaving the context issues
+    ALL of them as one grouped launch (``cmp_node_gemm_dw_grouped``) that fills the SMs instead of 20 small launches
+    of ~17 us each.  Only valid when nothing reads or accumulates into the parameter gradients before the context
+    exits, i.e. every parameter is used once and ``p.grad`` was ``None`` (``dp.RegressionStep`` guarantees both)."""
+
+    active = None      # the queue while a context is open
+
+    def __enter__(self):
+        if deferred_weight_grads.active is not None:
+            raise RuntimeError("deferred_weight_grads does not nest")
+        deferred_weight_grads.active = []
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        queue, deferred_weight_grads.active = deferred_weight_grads.active, None
+        if exc_type is None:
+            _flush_deferred_dw(queue)
+        return False
+
+
+def _flush_deferred_dw(queue):
+    if not queue:
+        return
+    dev = queue[0][0].device
+    gmax = _lib.size_query("cmp_node_gemm_dw_group_max")
+    ws = _lib.workspace(_lib.size_query("cmp_node_gemm_dw_grouped_workspace"), dev)
+    for lo in range(0, len(queue), gmax):
+        chunk = queue[lo:lo + gmax]
+        arr = (_lib.DwProblem * len(chunk))()
+        work = 0.0
+        for slot, (dy2, y, x2, K, Nout, dw_ptr, db_ptr) in zip(arr, chunk):
+            slot.dY, slot.lddy = dy2.data_ptr(), dy2.stride(0)
+            slot.saved_y, slot.ldys = (y.data_ptr(), y.stride(0)) if y is not None else (None, 0)
+            slot.X, slot.ldx = x2.data_ptr(), x2.stride(0)
+            slot.M, slot.K, slot.Nout = x2.shape[0], K, Nout
+            slot.dW, slot.db = dw_ptr, db_ptr
+            work += 2.0 * x2.shape[0] * K * Nout
+        call("cmp_node_gemm_dw_grouped", ctypes.addressof(arr), len(chunk), ptr(ws), ws.numel(), work=work)
+
+
 class _LinearTCFn(Function):
     """Same contract as _LinearFn on the tcgen05 split-bf16 node GEMM kernels (node_gemm_tc.cu)."""
 
@@ -263,9 +307,15 @@ class _LinearTCFn(Function):
             M = x2.shape[0]
             dw = torch.empty(Nout, K, dtype=torch.float32, device=dy2.device)
             db = torch.empty(Nout, dtype=torch.float32, device=dy2.device) if ctx.has_bias else None
-            ws = _lib.workspace(_lib.size_query("cmp_node_gemm_dw_workspace", K), dy2.device)
-            call("cmp_node_gemm_dw", ptr(dy2), dy2.stride(0), ptr(y), y.stride(0) if y is not None else 0, ptr(x2),
-                 x2.stride(0), M, K, Nout, ptr(dw), ptr(db), ptr(ws), ws.numel(), work=2.0 * M * K * Nout)
+            if deferred_weight_grads.active is not None:
+                # queued: raw pointers only for the outputs (autograd must stay the sole owner of dw / db, or it
+                # would clone them - unwritten - instead of adopting them as .grad); inputs are kept alive here
+                deferred_weight_grads.active.append((dy2, y, x2, K, Nout, dw.data_ptr(),
+                                                     db.data_ptr() if db is not None else None))
+            else:
+                ws = _lib.workspace(_lib.size_query("cmp_node_gemm_dw_workspace", K), dy2.device)
+                call("cmp_node_gemm_dw", ptr(dy2), dy2.stride(0), ptr(y), y.stride(0) if y is not None else 0, ptr(x2),
+                     x2.stride(0), M, K, Nout, ptr(dw), ptr(db), ptr(ws), ws.numel(), work=2.0 * M * K * Nout)
         if ctx.has_res and ctx.needs_input_grad[4]:
             dres = dy
         return dx, dw, db, None, dres

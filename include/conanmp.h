@@ -294,6 +294,28 @@ int cmp_node_gemm_dw(const float* dY, int64_t lddy, const float* saved_y, int64_
                      const float* X, int64_t ldx, int64_t M, int K, int Nout, float* dW, float* db,
                      void* workspace, size_t workspace_bytes, cmp_stream_t stream);
 
+/* Grouped form: up to cmp_node_gemm_dw_group_max() weight-gradient problems in ONE launch (the node linears of a
+ * whole backward pass, issued once at its end).  The SMs are divided between the problems in proportion to their
+ * tile counts; every CTA accumulates its tiles in TMEM and writes one partial block; a second kernel sums the
+ * partial blocks of each problem in CTA order (deterministic).  `problems` is a HOST array. */
+typedef struct cmp_dw_problem {
+  const float* dY;      /* [M, Nout] upstream gradient */
+  int64_t lddy;
+  const float* saved_y; /* optional [M, Nout]: forward output of a fused ShiftedSoftplus */
+  int64_t ldys;
+  const float* X;       /* [M, K] forward input */
+  int64_t ldx;
+  int64_t M;
+  int32_t K;
+  int32_t Nout;
+  float* dW;            /* [Nout, K] */
+  float* db;            /* [Nout] or NULL */
+} cmp_dw_problem_t;
+int cmp_node_gemm_dw_group_max(void);
+size_t cmp_node_gemm_dw_grouped_workspace(void);
+int cmp_node_gemm_dw_grouped(const void* problems /* const cmp_dw_problem_t[count], host */, int count,
+                             void* workspace, size_t workspace_bytes, cmp_stream_t stream);
+
 /* ------------------------------------------------------------------------- *
  * ViSNet edge-level kernels (exact fp32; tgv.py = torch_geometric_visnet.py)
  * Every reduction runs over the CSR (or its transpose) in a fixed order.
