@@ -17,6 +17,8 @@ from .schnet_no_sum import SchNetNoSum  # noqa: F401
 from . import visnet  # noqa: F401
 from .visnet import ViSNet, ViS_MP, ViSNetBlock, TorchGeometricViSNet  # noqa: F401
 from . import synthetic  # noqa: F401
+from . import aggregation  # noqa: F401
+from .aggregation import ConformerAggregationHead, MeanAggregation, create_aggregation_index  # noqa: F401
 
 __all__ = [
     "radius_graph", "build_neighbor_list", "NeighborList", "RadiusInteractionGraph", "GaussianSmearing",

@@ -87,6 +87,8 @@ SIGNATURES = {
     "cmp_cfconv_fused_bwd_workspace": (S, []),
     "cmp_cfconv_tc_pack_bwd_weights": (I, [P, P, P, I, I, P, P]),
     "cmp_cfconv_fused_bwd_weights": (I, [P, P, P, P, P, P, P, P, P, I, F, F, I, P, P, P, P, P, S, P]),
+    "cmp_dense_batch": (I, [P, P, L, L, I, F, P, P, P]),
+    "cmp_dense_adj": (I, [P, L, P, P, L, L, P, P]),
     "cmp_node_gemm_dw_group_max": (I, []),
     "cmp_node_gemm_dw_grouped_workspace": (S, []),
     "cmp_node_gemm_dw_grouped": (I, [P, I, P, S, P]),

@@ -392,6 +392,37 @@ pair_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
   }
 }
 
+// ---- dense views for the FGW input preparation (to_dense_batch / to_dense_adj of PyG) ------------------------
+// out[g, a, :] = x[seg_ptr[g] + a, :] (fill beyond the conformer), mask[g, a] = a < atoms(g)
+__global__ void dense_batch_kernel(const float* __restrict__ x, const int32_t* __restrict__ seg_ptr, int64_t G,
+                                   int64_t n_max, int C, float fill, float* __restrict__ out,
+                                   uint8_t* __restrict__ mask) {
+  const int64_t row = blockIdx.x;            // g * n_max + a
+  const int64_t g = row / n_max, a = row - g * n_max;
+  const int s = seg_ptr[g], n = seg_ptr[g + 1] - s;
+  const bool live = a < n;
+  if (threadIdx.x == 0 && mask) mask[row] = live ? 1 : 0;
+  const float* src = x + (int64_t)(s + a) * C;
+  float* dst = out + row * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) dst[c] = live ? src[c] : fill;
+}
+
+// adj[g, src - s, dst - s] += 1 for every edge whose two ends lie inside conformer g and below n_max
+// (integer-valued sums: the order of the atomic adds does not change the result)
+__global__ void dense_adj_kernel(const int64_t* __restrict__ ei_src, const int64_t* __restrict__ ei_dst, int64_t E,
+                                 const int64_t* __restrict__ batch, const int32_t* __restrict__ seg_ptr, int64_t G,
+                                 int64_t n_max, float* __restrict__ adj) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int64_t j = ei_src[e], i = ei_dst[e];
+  const int64_t g = batch ? batch[j] : 0;
+  if (g < 0 || g >= G) return;
+  const int64_t s = seg_ptr[g];
+  const int64_t a = j - s, b = i - s;
+  if (a < 0 || b < 0 || a >= n_max || b >= n_max) return;
+  atomicAdd(adj + (g * n_max + a) * n_max + b, 1.0f);
+}
+
 __global__ void gather_f32_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
                                   const int32_t* __restrict__ count_ptr, float* __restrict__ dst) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -548,6 +579,32 @@ extern "C" int cmp_build_pair_list(const int32_t* rowptr, const int32_t* col, co
   pair_fill_kernel<<<(unsigned)G, kGraphThreads, 0, st>>>(rowptr, col, dist, seg_ptr, pcount, conf_pair_ptr, cap_P, p_src,
                                                           p_dst, p_dist, p_rev, status);
   CMP_LAUNCH_CHECK("cmp_build_pair_list(fill)");
+  return CMP_OK;
+}
+
+extern "C" int cmp_dense_batch(const float* x, const int32_t* seg_ptr, int64_t G, int64_t n_max, int C, float fill,
+                               float* out, uint8_t* mask, cmp_stream_t stream) {
+  CMP_REQUIRE(G >= 0 && n_max >= 0 && C >= 0, CMP_EINVAL, "cmp_dense_batch: negative size");
+  if (G == 0 || n_max == 0) return CMP_OK;
+  CMP_REQUIRE(seg_ptr && out && (x || C == 0), CMP_EINVAL, "cmp_dense_batch: null pointer");
+  CMP_REQUIRE(G * n_max < ((int64_t)1 << 31), CMP_EUNSUPPORTED, "cmp_dense_batch: G * n_max must fit int32");
+  dense_batch_kernel<<<(unsigned)(G * n_max), 128, 0, as_stream(stream)>>>(x, seg_ptr, G, n_max, C, fill, out, mask);
+  CMP_LAUNCH_CHECK("cmp_dense_batch");
+  return CMP_OK;
+}
+
+extern "C" int cmp_dense_adj(const int64_t* edge_index, int64_t E, const int64_t* batch, const int32_t* seg_ptr,
+                             int64_t G, int64_t n_max, float* adj, cmp_stream_t stream) {
+  CMP_REQUIRE(E >= 0 && G >= 0 && n_max >= 0, CMP_EINVAL, "cmp_dense_adj: negative size");
+  if (G == 0 || n_max == 0) return CMP_OK;
+  CMP_REQUIRE(seg_ptr && adj && (edge_index || E == 0), CMP_EINVAL, "cmp_dense_adj: null pointer");
+  cudaStream_t st = as_stream(stream);
+  CMP_REQUIRE(cudaMemsetAsync(adj, 0, (size_t)G * n_max * n_max * sizeof(float), st) == cudaSuccess, CMP_ECUDA,
+              "cmp_dense_adj: memset failed");
+  if (E == 0) return CMP_OK;
+  dense_adj_kernel<<<(unsigned)ceil_div(E, 256), 256, 0, st>>>(edge_index, edge_index + E, E, batch, seg_ptr, G, n_max,
+                                                                 adj);
+  CMP_LAUNCH_CHECK("cmp_dense_adj");
   return CMP_OK;
 }
 

@@ -190,6 +190,16 @@ int cmp_build_tiles_min_atoms(const int32_t* rowptr, const int32_t* seg_ptr, int
                               int min_atoms, void* tiles, int64_t cap_tiles, int32_t* num_tiles,
                               void* workspace, size_t workspace_bytes, int* status, cmp_stream_t stream);
 
+/* Dense views for the FGW input preparation: torch_geometric.utils.to_dense_batch /
+ * to_dense_adj as schnet_no_sum.py:242-253 and visnet.py:168-177 call them.
+ * cmp_dense_batch: out[g, a, :] = x[seg_ptr[g] + a, :] for a < atoms(g), `fill` beyond; mask[g, a] (uint8, may be NULL).
+ * cmp_dense_adj:  adj[g, src - first(g), dst - first(g)] += 1 per edge of edge_index (int64 [2, E], row 0 = source),
+ *                 g = batch[src]; adj is zero-filled first; ends at or beyond n_max are dropped. */
+int cmp_dense_batch(const float* x, const int32_t* seg_ptr, int64_t G, int64_t n_max, int C, float fill,
+                    float* out, uint8_t* mask, cmp_stream_t stream);
+int cmp_dense_adj(const int64_t* edge_index, int64_t E, const int64_t* batch, const int32_t* seg_ptr,
+                  int64_t G, int64_t n_max, float* adj, cmp_stream_t stream);
+
 /* dst[i] = src[idx[i]] for i < *count_ptr (per-edge data in transposed order, no host sync). */
 int cmp_gather_f32(const float* src, const int32_t* idx, const int32_t* count_ptr,
                    int64_t max_count, float* dst, cmp_stream_t stream);
