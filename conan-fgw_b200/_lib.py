@@ -95,7 +95,7 @@ SIGNATURES = {
     "cmp_cfconv_pair_max_atoms": (I, []),
     "cmp_cfconv_pair_fwd": (I, [P, P, P, P, P, P, P, L, P, P, I, F, F, I, I, P, P]),
     "cmp_build_pair_list_workspace": (S, [L, L]),
-    "cmp_build_pair_list": (I, [P, P, P, P, L, L, L, P, P, P, P, P, P, S, P, P]),
+    "cmp_build_pair_list": (I, [P, P, P, P, L, L, I, L, P, P, P, P, P, P, S, P, P]),
     "cmp_cfconv_fused_bwd_weights_pairs": (I, [P, P, P, P, P, P, P, P, P, P, I, F, F, I, P, P, P, P, P, S, P]),
 }
 

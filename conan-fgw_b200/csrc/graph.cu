@@ -218,6 +218,26 @@ radius_fill_kernel(const float* __restrict__ pos, const int32_t* __restrict__ se
     }
     return -1;
   };
+  // A conformer with at most `cap` atoms cannot have been truncated, so its neighbour list is symmetric: the transposed
+  // row of j holds the same atoms as row j, and only the edge ids need a search - one thread per EDGE instead of a
+  // serial sweep over all (i, j) per atom.
+  if (n <= cap) {
+    const int eend = conf_edge_ptr[g + 1];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) rowptr_t[s + i] = rowptr[s + i];
+    if (g == G - 1 && threadIdx.x == 0) rowptr_t[N] = conf_edge_ptr[G];
+    for (int e = ebase + threadIdx.x; e < eend; e += blockDim.x) {
+      // row j of edge e: the last row whose offset is <= e
+      int lo = 0, hi = n - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (rowptr[s + mid] <= e) lo = mid; else hi = mid - 1;
+      }
+      const int j = lo, i = col[e] - s;
+      col_t[e] = s + i;                    // target of the transposed edge j -> i
+      eid_t[e] = find_in_row(i, j);        // ... which is stored in row i of the target-sorted list
+    }
+    return;
+  }
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
     int c = 0;
     for (int i = 0; i < n; ++i) c += (find_in_row(i, j) >= 0);
@@ -338,17 +358,19 @@ __device__ __forceinline__ bool csr_has(const int32_t* __restrict__ rowptr, cons
 
 __global__ void __launch_bounds__(kGraphThreads)
 pair_count_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                  const int32_t* __restrict__ seg_ptr, int32_t* __restrict__ pcount, int32_t* __restrict__ conf_pairs) {
+                  const int32_t* __restrict__ seg_ptr, int sym_atoms, int32_t* __restrict__ pcount,
+                  int32_t* __restrict__ conf_pairs) {
   __shared__ int warp_sums[kGraphThreads / 32];
   const int g = blockIdx.x;
   const int s = seg_ptr[g], n = seg_ptr[g + 1] - s;
+  const bool sym = n <= sym_atoms;    // too small to have been truncated: every edge has its reverse
   int local = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const int row = s + i;
     int c = 0;
     for (int k = rowptr[row]; k < rowptr[row + 1]; ++k) {
       const int j = col[k];
-      if (j >= row || !csr_has(rowptr, col, j, row)) ++c;   // a self loop is its own (unpaired) representative
+      if (j >= row || (!sym && !csr_has(rowptr, col, j, row))) ++c;   // a self loop is its own (unpaired) representative
     }
     pcount[row] = c;
     local += c;
@@ -365,7 +387,7 @@ pair_count_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
 
 __global__ void __launch_bounds__(kGraphThreads)
 pair_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ dist,
-                 const int32_t* __restrict__ seg_ptr, const int32_t* __restrict__ pcount,
+                 const int32_t* __restrict__ seg_ptr, int sym_atoms, const int32_t* __restrict__ pcount,
                  const int32_t* __restrict__ conf_pair_ptr, int64_t cap_P, int32_t* __restrict__ p_src,
                  int32_t* __restrict__ p_dst, float* __restrict__ p_dist, int32_t* __restrict__ p_rev, int* status) {
   const int g = blockIdx.x;
@@ -380,7 +402,7 @@ pair_fill_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
     for (int r = 0; r < i; ++r) w += pcount[s + r];
     for (int k = rowptr[row]; k < rowptr[row + 1]; ++k) {
       const int j = col[k];
-      const bool has = (j != row) && csr_has(rowptr, col, j, row);
+      const bool has = (j != row) && (n <= sym_atoms || csr_has(rowptr, col, j, row));
       if (j >= row || !has) {
         p_src[w] = j;
         p_dst[w] = row;
@@ -555,7 +577,8 @@ extern "C" size_t cmp_build_pair_list_workspace(int64_t N, int64_t G) {
 }
 
 extern "C" int cmp_build_pair_list(const int32_t* rowptr, const int32_t* col, const float* dist, const int32_t* seg_ptr,
-                                   int64_t N, int64_t G, int64_t cap_P, int32_t* p_src, int32_t* p_dst, float* p_dist,
+                                   int64_t N, int64_t G, int sym_atoms, int64_t cap_P, int32_t* p_src, int32_t* p_dst,
+                                   float* p_dist,
                                    int32_t* p_rev, int32_t* conf_pair_ptr, void* workspace, size_t workspace_bytes,
                                    int* status, cmp_stream_t stream) {
   CMP_REQUIRE(N >= 0 && G >= 0 && cap_P >= 0, CMP_EINVAL, "cmp_build_pair_list: negative size");
@@ -572,11 +595,12 @@ extern "C" int cmp_build_pair_list(const int32_t* rowptr, const int32_t* col, co
               "cmp_build_pair_list: workspace too small");
   int32_t* pcount = reinterpret_cast<int32_t*>(workspace);
   int32_t* conf_pairs = pcount + N;
-  pair_count_kernel<<<(unsigned)G, kGraphThreads, 0, st>>>(rowptr, col, seg_ptr, pcount, conf_pairs);
+  pair_count_kernel<<<(unsigned)G, kGraphThreads, 0, st>>>(rowptr, col, seg_ptr, sym_atoms, pcount, conf_pairs);
   CMP_LAUNCH_CHECK("cmp_build_pair_list(count)");
   scan_conformers_kernel<<<1, 1024, 0, st>>>(conf_pairs, G, conf_pair_ptr);
   CMP_LAUNCH_CHECK("cmp_build_pair_list(scan)");
-  pair_fill_kernel<<<(unsigned)G, kGraphThreads, 0, st>>>(rowptr, col, dist, seg_ptr, pcount, conf_pair_ptr, cap_P, p_src,
+  pair_fill_kernel<<<(unsigned)G, kGraphThreads, 0, st>>>(rowptr, col, dist, seg_ptr, sym_atoms, pcount, conf_pair_ptr,
+                                                          cap_P, p_src,
                                                           p_dst, p_dist, p_rev, status);
   CMP_LAUNCH_CHECK("cmp_build_pair_list(fill)");
   return CMP_OK;

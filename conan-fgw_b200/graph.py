@@ -38,6 +38,7 @@ class NeighborList:
         self.status = torch.zeros(1, **i32)
         self.cutoff = None
         self.loop = False
+        self.sym_atoms = 0           # 0: nothing is known about symmetry (graph built from a raw edge_index)
         self._E = None
         self._edge_index = None
         self._checked = False
@@ -152,7 +153,8 @@ class NeighborList:
             conf_ptr = torch.empty(self.G + 1, dtype=torch.int32, device=dev)
             ws = _lib.workspace(_lib.size_query("cmp_build_pair_list_workspace", self.N, self.G), dev)
             _lib.call("cmp_build_pair_list", _lib.ptr(self.rowptr), _lib.ptr(self.col), _lib.ptr(self.dist),
-                      _lib.ptr(self.seg_ptr), self.N, self.G, cap, _lib.ptr(src), _lib.ptr(dst), _lib.ptr(dist),
+                      _lib.ptr(self.seg_ptr), self.N, self.G, int(self.sym_atoms), cap, _lib.ptr(src), _lib.ptr(dst),
+                      _lib.ptr(dist),
                       _lib.ptr(rev), _lib.ptr(conf_ptr), _lib.ptr(ws), ws.numel(), _lib.ptr(self.status))
             tile_e = _lib.size_query("cmp_cfconv_tc_bwd_tile_edges")
             cap_t = cap // tile_e + self.G + 1
@@ -201,6 +203,7 @@ def build_neighbor_list(pos: torch.Tensor, batch: Optional[torch.Tensor], r: flo
     cap = max_num_neighbors if loop else max_num_neighbors + 1
     nl = NeighborList(N, G, N * cap, dev)
     nl.cutoff, nl.loop = float(r), bool(loop)
+    nl.sym_atoms = int(cap)      # conformers of at most this many atoms cannot have been truncated: symmetric lists
     i32 = dict(dtype=torch.int32, device=dev)
     if want_evec:
         nl.evec = torch.empty(max(nl.cap_E, 1), 3, dtype=torch.float32, device=dev)

@@ -269,10 +269,13 @@ int cmp_cfconv_fused_bwd_weights(const float* g, const void* xprime_bf16, const 
  * terms add: dF = g[dst] x'[src] + rev * g[src] x'[dst].  cmp_build_pair_list emits one PRIMARY edge per pair
  * (j -> i with j > i; or the surviving direction when the neighbour cap of radius_graph dropped the other one,
  * rev = 0; rows and columns ascending) with per-conformer offsets conf_pair_ptr[G+1]; tiles for it come from
- * cmp_build_flat_tiles(conf_pair_ptr, seg_ptr, pair_dst, ...).  Halves the filter-MLP recomputation of the backward. */
+ * cmp_build_flat_tiles(conf_pair_ptr, seg_ptr, pair_dst, ...).  Halves the filter-MLP recomputation of the backward.
+ * sym_atoms: conformers of at most this many atoms are known to be untruncated (max_num_neighbors + 1 for a graph
+ * without self loops), hence symmetric - their reverse-edge searches are skipped; 0 = search always. */
 size_t cmp_build_pair_list_workspace(int64_t N, int64_t G);
 int cmp_build_pair_list(const int32_t* rowptr, const int32_t* col, const float* dist,
-                        const int32_t* seg_ptr, int64_t N, int64_t G, int64_t cap_P, int32_t* pair_src,
+                        const int32_t* seg_ptr, int64_t N, int64_t G, int sym_atoms, int64_t cap_P,
+                        int32_t* pair_src,
                         int32_t* pair_dst, float* pair_dist, int32_t* pair_rev, int32_t* conf_pair_ptr,
                         void* workspace, size_t workspace_bytes, int* status, cmp_stream_t stream);
 int cmp_cfconv_fused_bwd_weights_pairs(const void* g_bf16, const void* xprime_bf16,
