@@ -87,6 +87,9 @@ SIGNATURES = {
     "cmp_cfconv_fused_bwd_workspace": (S, []),
     "cmp_cfconv_tc_pack_bwd_weights": (I, [P, P, P, I, I, P, P]),
     "cmp_cfconv_fused_bwd_weights": (I, [P, P, P, P, P, P, P, P, P, I, F, F, I, P, P, P, P, P, S, P]),
+    "cmp_node_gemm_pack_weights_grouped": (I, [P, I, P]),
+    "cmp_cfconv_tc_pack_weights_grouped": (I, [P, I, I, I, P]),
+    "cmp_cfconv_tc_pack_bwd_weights_grouped": (I, [P, I, I, I, P]),
     "cmp_dense_batch": (I, [P, P, L, L, I, F, P, P, P]),
     "cmp_dense_adj": (I, [P, L, P, P, L, L, P, P]),
     "cmp_node_gemm_dw_group_max": (I, []),
@@ -109,6 +112,17 @@ _launches = 0  # number of C-ABI compute calls issued (bench.py reports it)
 
 class ConanMPError(RuntimeError):
     pass
+
+
+class PackNodeJob(ctypes.Structure):
+    """``cmp_pack_node_job_t``."""
+    _fields_ = [("W", ctypes.c_void_p), ("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("packed", ctypes.c_void_p)]
+
+
+class PackFilterJob(ctypes.Structure):
+    """``cmp_pack_filter_job_t``."""
+    _fields_ = [("W1", ctypes.c_void_p), ("b1", ctypes.c_void_p), ("W2", ctypes.c_void_p), ("b2", ctypes.c_void_p),
+                ("packed_fwd", ctypes.c_void_p), ("packed_bwd", ctypes.c_void_p)]
 
 
 class DwProblem(ctypes.Structure):

@@ -418,10 +418,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
 }
 
 // ---- weight images ----------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
-                                    const float* __restrict__ W2, const float* __restrict__ b2, int Ng,
-                                    uint8_t* __restrict__ out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pack_weights_body(const float* __restrict__ W1, const float* __restrict__ b1,
+                                                  const float* __restrict__ W2, const float* __restrict__ b2, int Ng,
+                                                  uint8_t* __restrict__ out, int idx) {
   if (idx < F * K1) {
     const int m = idx / K1, k = idx % K1;
     float v = (k < Ng) ? W1[m * Ng + k] : (k == Ng ? b1[m] : 0.0f);
@@ -439,6 +438,30 @@ __global__ void pack_weights_kernel(const float* __restrict__ W1, const float* _
     uint32_t off = (m & 7) * 16 + (k & 7) * 2 + (m >> 3) * A2_SBO + (k >> 3) * 128;
     *reinterpret_cast<__nv_bfloat16*>(out + W1_BYTES + off) = __float2bfloat16_rn(v);
   }
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
+                                    const float* __restrict__ W2, const float* __restrict__ b2, int Ng,
+                                    uint8_t* __restrict__ out) {
+  pack_weights_body(W1, b1, W2, b2, Ng, out, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// grouped: the filter MLPs of all interaction blocks in one launch (job = blockIdx.y)
+constexpr int MAX_PACK_JOBS = 32;
+struct PackFilterJob {
+  const float* W1;
+  const float* b1;
+  const float* W2;
+  const float* b2;
+  uint8_t* packed_fwd;
+  uint8_t* packed_bwd;
+};
+struct PackFilterGroup {
+  PackFilterJob j[MAX_PACK_JOBS];
+};
+__global__ void pack_weights_grouped_kernel(const __grid_constant__ PackFilterGroup g, int Ng) {
+  const PackFilterJob& j = g.j[blockIdx.y];
+  pack_weights_body(j.W1, j.b1, j.W2, j.b2, Ng, j.packed_fwd, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 }  // namespace
@@ -515,5 +538,26 @@ extern "C" int cmp_cfconv_fused_fwd(const float* xprime, const float* dist, cons
   p.dbg = g_fwd_dbg;
   cfconv_fused_fwd_kernel<<<sm_count(), CTA_THREADS, SMEM_BYTES, st>>>(p);
   CMP_LAUNCH_CHECK("cmp_cfconv_fused_fwd");
+  return CMP_OK;
+}
+
+extern "C" int cmp_cfconv_tc_pack_weights_grouped(const void* jobs, int count, int num_filters, int num_gaussians,
+                                                  cmp_stream_t stream) {
+  CMP_REQUIRE(cmp_cfconv_tc_supported(num_filters, num_gaussians), CMP_EUNSUPPORTED,
+              "cmp_cfconv_tc_pack_weights_grouped: needs num_filters == 128 and num_gaussians < 64");
+  CMP_REQUIRE(count >= 0 && count <= MAX_PACK_JOBS, CMP_EINVAL, "cmp_cfconv_tc_pack_weights_grouped: count must be in [0, %d]",
+              MAX_PACK_JOBS);
+  if (count == 0) return CMP_OK;
+  CMP_REQUIRE(jobs, CMP_EINVAL, "cmp_cfconv_tc_pack_weights_grouped: null pointer");
+  const PackFilterJob* in = reinterpret_cast<const PackFilterJob*>(jobs);
+  PackFilterGroup g;
+  for (int i = 0; i < count; ++i) {
+    CMP_REQUIRE(in[i].W1 && in[i].b1 && in[i].W2 && in[i].b2 && in[i].packed_fwd, CMP_EINVAL,
+                "cmp_cfconv_tc_pack_weights_grouped: null pointer");
+    g.j[i] = in[i];
+  }
+  const int total = F * K1 + F * K2;
+  pack_weights_grouped_kernel<<<dim3((total + 255) / 256, count), 256, 0, as_stream(stream)>>>(g, num_gaussians);
+  CMP_LAUNCH_CHECK("cmp_cfconv_tc_pack_weights_grouped");
   return CMP_OK;
 }

@@ -562,9 +562,9 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int U,
   }
 }
 
-__global__ void pack_bwd_weights_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
-                                        const float* __restrict__ W2, int Ng, uint8_t* __restrict__ out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pack_bwd_weights_body(const float* __restrict__ W1, const float* __restrict__ b1,
+                                                      const float* __restrict__ W2, int Ng, uint8_t* __restrict__ out,
+                                                      int idx) {
   if (idx < F * K1) {
     const int m = idx / K1, k = idx % K1;
     const float v = (k < Ng) ? W1[m * Ng + k] : (k == Ng ? b1[m] : 0.0f);
@@ -577,6 +577,29 @@ __global__ void pack_bwd_weights_kernel(const float* __restrict__ W1, const floa
     const uint32_t off = (k & 7) * 16 + (f & 7) * 2 + (k >> 3) * 2048 + (f >> 3) * 128;
     *reinterpret_cast<__nv_bfloat16*>(out + W1_BYTES + off) = __float2bfloat16_rn(v);
   }
+}
+
+__global__ void pack_bwd_weights_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
+                                        const float* __restrict__ W2, int Ng, uint8_t* __restrict__ out) {
+  pack_bwd_weights_body(W1, b1, W2, Ng, out, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// grouped: same job layout as cfconv_tc.cu's PackFilterJob (cmp_pack_filter_job_t of the header)
+constexpr int MAX_PACK_JOBS = 32;
+struct PackFilterJob {
+  const float* W1;
+  const float* b1;
+  const float* W2;
+  const float* b2;
+  uint8_t* packed_fwd;
+  uint8_t* packed_bwd;
+};
+struct PackFilterGroup {
+  PackFilterJob j[MAX_PACK_JOBS];
+};
+__global__ void pack_bwd_weights_grouped_kernel(const __grid_constant__ PackFilterGroup g, int Ng) {
+  const PackFilterJob& j = g.j[blockIdx.y];
+  pack_bwd_weights_body(j.W1, j.b1, j.W2, Ng, j.packed_bwd, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, int64_t n, __nv_bfloat16* __restrict__ dst) {
@@ -828,4 +851,25 @@ extern "C" int cmp_cfconv_fused_bwd_weights_pairs(const void* g_bf16, const void
   p.dbg = g_bwd_dbg;
   return launch_fused_bwd<true>(p, num_gaussians, dW1, db1, dW2, db2, as_stream(stream),
                                 "cmp_cfconv_fused_bwd_weights_pairs");
+}
+
+extern "C" int cmp_cfconv_tc_pack_bwd_weights_grouped(const void* jobs, int count, int num_filters, int num_gaussians,
+                                                      cmp_stream_t stream) {
+  CMP_REQUIRE(num_filters == F && num_gaussians >= 1 && num_gaussians < K1, CMP_EUNSUPPORTED,
+              "cmp_cfconv_tc_pack_bwd_weights_grouped: needs num_filters == 128 and num_gaussians < 64");
+  CMP_REQUIRE(count >= 0 && count <= MAX_PACK_JOBS, CMP_EINVAL,
+              "cmp_cfconv_tc_pack_bwd_weights_grouped: count must be in [0, %d]", MAX_PACK_JOBS);
+  if (count == 0) return CMP_OK;
+  CMP_REQUIRE(jobs, CMP_EINVAL, "cmp_cfconv_tc_pack_bwd_weights_grouped: null pointer");
+  const PackFilterJob* in = reinterpret_cast<const PackFilterJob*>(jobs);
+  PackFilterGroup g;
+  for (int i = 0; i < count; ++i) {
+    CMP_REQUIRE(in[i].W1 && in[i].b1 && in[i].W2 && in[i].packed_bwd, CMP_EINVAL,
+                "cmp_cfconv_tc_pack_bwd_weights_grouped: null pointer");
+    g.j[i] = in[i];
+  }
+  const int total = F * K1 + F * F;
+  pack_bwd_weights_grouped_kernel<<<dim3((total + 255) / 256, count), 256, 0, as_stream(stream)>>>(g, num_gaussians);
+  CMP_LAUNCH_CHECK("cmp_cfconv_tc_pack_bwd_weights_grouped");
+  return CMP_OK;
 }

@@ -382,9 +382,8 @@ __global__ void node_dw_reduce_kernel(const float* __restrict__ partial, int P, 
 
 // W[rows, cols] (ld) fp32 -> hi | lo K-major images with 128 rows (zero padded): rows = MMA M.
 // transpose = 1 packs W^T (rows of the image = columns of W).
-__global__ void node_pack_weight_kernel(const float* __restrict__ W, int rows, int cols, int transpose,
-                                        uint8_t* __restrict__ out) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void node_pack_weight_body(const float* __restrict__ W, int rows, int cols, int transpose,
+                                                      uint8_t* __restrict__ out, int idx) {
   if (transpose == 2) {   // both images in one launch: [hi|lo of W] followed by [hi|lo of W^T]
     const int n_norm = 128 * cols;
     if (idx < n_norm) {
@@ -405,6 +404,25 @@ __global__ void node_pack_weight_kernel(const float* __restrict__ W, int rows, i
   const uint32_t off = (r & 7) * 16 + (c & 7) * 2 + (r >> 3) * ((C >> 3) * 128) + (c >> 3) * 128;
   *reinterpret_cast<__nv_bfloat16*>(out + off) = __float2bfloat16_rn(h);
   *reinterpret_cast<__nv_bfloat16*>(out + 128 * C * 2 + off) = __float2bfloat16_rn(v - h);
+}
+
+__global__ void node_pack_weight_kernel(const float* __restrict__ W, int rows, int cols, int transpose,
+                                        uint8_t* __restrict__ out) {
+  node_pack_weight_body(W, rows, cols, transpose, out, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// grouped: job blockIdx.y, both images of every weight (the node linears of a model in one launch)
+struct PackNodeJob {
+  const float* W;
+  int32_t rows, cols;
+  uint8_t* packed;
+};
+struct PackNodeGroup {
+  PackNodeJob j[MAX_GROUP];
+};
+__global__ void node_pack_weight_grouped_kernel(const __grid_constant__ PackNodeGroup g) {
+  const PackNodeJob& j = g.j[blockIdx.y];
+  node_pack_weight_body(j.W, j.rows, j.cols, 2, j.packed, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 bool dims_ok(int K, int Nout) {
@@ -601,5 +619,23 @@ extern "C" int cmp_node_gemm_dw_grouped(const void* problems, int count, void* w
   CMP_LAUNCH_CHECK("cmp_node_gemm_dw_grouped");
   node_dw_grouped_reduce_kernel<<<dim3((MAXC * (MAXC + 1) + 127) / 128, count), 128, 0, st>>>(g);
   CMP_LAUNCH_CHECK("cmp_node_gemm_dw_grouped(reduce)");
+  return CMP_OK;
+}
+
+extern "C" int cmp_node_gemm_pack_weights_grouped(const void* jobs, int count, cmp_stream_t stream) {
+  CMP_REQUIRE(count >= 0 && count <= MAX_GROUP, CMP_EINVAL, "cmp_node_gemm_pack_weights_grouped: count must be in [0, %d]",
+              MAX_GROUP);
+  if (count == 0) return CMP_OK;
+  CMP_REQUIRE(jobs, CMP_EINVAL, "cmp_node_gemm_pack_weights_grouped: null pointer");
+  const PackNodeJob* in = reinterpret_cast<const PackNodeJob*>(jobs);
+  PackNodeGroup g;
+  for (int i = 0; i < count; ++i) {
+    CMP_REQUIRE(in[i].W && in[i].packed, CMP_EINVAL, "cmp_node_gemm_pack_weights_grouped: null pointer");
+    CMP_REQUIRE(dims_ok(in[i].cols, in[i].rows), CMP_EUNSUPPORTED,
+                "cmp_node_gemm_pack_weights_grouped: dims must be multiples of 16 in [16,128]");
+    g.j[i] = in[i];
+  }
+  node_pack_weight_grouped_kernel<<<dim3((128 * 2 * MAXC + 255) / 256, count), 256, 0, as_stream(stream)>>>(g);
+  CMP_LAUNCH_CHECK("cmp_node_gemm_pack_weights_grouped");
   return CMP_OK;
 }

@@ -113,11 +113,13 @@ class RegressionStep:
 
     def _fwd_bwd(self, z, pos, batch, targets, num_graphs):
         self.flat.zero_grad()
-        loss = self.loss(z, pos, batch, targets, num_graphs)
-        # parameter gradients are None here and every parameter is used once: the node-linear weight gradients can be
-        # queued during backward and issued as ONE grouped launch at its end
-        with ops.deferred_weight_grads():
-            loss.backward()
+        # weights only change in adam(): every tensor-core weight image of this step is packed up front, grouped
+        with ops.prepacked_weights([self.backbone, self.head]):
+            loss = self.loss(z, pos, batch, targets, num_graphs)
+            # parameter gradients are None here and every parameter is used once: the node-linear weight gradients
+            # can be queued during backward and issued as ONE grouped launch at its end
+            with ops.deferred_weight_grads():
+                loss.backward()
         self.flat.collect_grads()
         return loss.detach()
 

@@ -120,6 +120,85 @@ def node_tc_supported(K, Nout) -> bool:
     return bool(_lib.lib().cmp_node_gemm_tc_supported(int(K), int(Nout))) and bool(_lib.lib().cmp_device_is_sm100())
 
 
+class prepacked_weights:
+    """Pack every weight image the enclosed forward + backward will need in THREE grouped launches (node linears,
+    filter MLPs forward, filter MLPs backward) instead of one or two small launches per layer.  Weights only change
+    in the optimizer step, so a training step opens this context right after it (``dp.RegressionStep``); the cache is
+    dropped when the context closes, so a later weight update can never meet a stale image."""
+
+    cache = None       # {weight.data_ptr(): images} while a context is open
+
+    def __init__(self, modules):
+        self.modules = list(modules)
+
+    def __enter__(self):
+        if prepacked_weights.cache is not None:
+            raise RuntimeError("prepacked_weights does not nest")
+        prepacked_weights.cache = _prepack(self.modules)
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        prepacked_weights.cache = None
+        return False
+
+
+def _prepack(modules):
+    from .nn import InteractionBlock, Linear    # late import: nn imports ops
+
+    cache = {}
+    node, filt = [], []
+    gmax = 32
+    skip = set()     # filter-MLP Linears of fused blocks never run as node GEMMs
+    for root in modules:
+        for m in root.modules():
+            if isinstance(m, InteractionBlock) and m.conv.precision == "bf16" and m.mlp[0].weight.is_cuda:
+                W1, b1, W2, b2 = m.mlp[0].weight, m.mlp[0].bias, m.mlp[2].weight, m.mlp[2].bias
+                if fused_supported(W1.shape[0], W1.shape[1]):
+                    skip.update((W1.data_ptr(), W2.data_ptr()))
+                    if W1.data_ptr() not in cache:
+                        dev = W1.device
+                        pf = torch.empty(_lib.size_query("cmp_cfconv_tc_weights_bytes"), dtype=torch.uint8, device=dev)
+                        pb = torch.empty(_lib.size_query("cmp_cfconv_tc_bwd_weights_bytes"), dtype=torch.uint8,
+                                         device=dev)
+                        cache[W1.data_ptr()] = (pf, pb)
+                        filt.append(tuple(_f32c(t.detach()) for t in (W1, b1, W2, b2)) + (pf, pb))
+    for root in modules:
+        for m in root.modules():
+            if isinstance(m, Linear) and m.tc and m.weight.is_cuda and m.weight.data_ptr() not in skip and \
+                    m.weight.data_ptr() not in cache and \
+                    bool(_lib.lib().cmp_node_gemm_tc_supported(m.weight.shape[1], m.weight.shape[0])):
+                rows, cols = m.weight.shape
+                n_norm = _lib.size_query("cmp_node_gemm_weight_bytes", cols)
+                n_tr = _lib.size_query("cmp_node_gemm_weight_bytes", rows)
+                packed = torch.empty(n_norm + n_tr, dtype=torch.uint8, device=m.weight.device)
+                cache[m.weight.data_ptr()] = (packed[:n_norm], packed[n_norm:])
+                node.append((_f32c(m.weight.detach()), rows, cols, packed))
+    for lo in range(0, len(node), gmax):
+        chunk = node[lo:lo + gmax]
+        arr = (_lib.PackNodeJob * len(chunk))()
+        for slot, (w, rows, cols, packed) in zip(arr, chunk):
+            slot.W, slot.rows, slot.cols, slot.packed = w.data_ptr(), rows, cols, packed.data_ptr()
+        call("cmp_node_gemm_pack_weights_grouped", ctypes.addressof(arr), len(chunk))
+    for lo in range(0, len(filt), gmax):
+        chunk = filt[lo:lo + gmax]
+        F, Ng = chunk[0][0].shape
+        if any(c[0].shape != (F, Ng) for c in chunk):
+            raise _lib.ConanMPError("prepacked_weights: interaction blocks of different shapes in one model")
+        arr = (_lib.PackFilterJob * len(chunk))()
+        for slot, (W1, b1, W2, b2, pf, pb) in zip(arr, chunk):
+            slot.W1, slot.b1, slot.W2, slot.b2 = W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr()
+            slot.packed_fwd, slot.packed_bwd = pf.data_ptr(), pb.data_ptr()
+        call("cmp_cfconv_tc_pack_weights_grouped", ctypes.addressof(arr), len(chunk), F, Ng)
+        call("cmp_cfconv_tc_pack_bwd_weights_grouped", ctypes.addressof(arr), len(chunk), F, Ng)
+    cache["_keepalive"] = (node, filt)
+    return cache
+
+
+def _cached_images(weight):
+    c = prepacked_weights.cache
+    return None if c is None else c.get(weight.data_ptr())
+
+
 def _pack_node_weight(weight, transpose):
     rows, cols = weight.shape
     image_k = rows if transpose else cols
@@ -283,7 +362,10 @@ class _LinearTCFn(Function):
         lead = x.shape[:-1]
         x2 = _f32c(x.reshape(-1, K))
         res2 = _f32c(residual.reshape(-1, Nout)) if residual is not None else None
-        if ctx.needs_input_grad[0]:
+        cached = _cached_images(weight)
+        if cached is not None:
+            w_img, ctx.w_img_t = cached
+        elif ctx.needs_input_grad[0]:
             w_img, ctx.w_img_t = _pack_node_weight_both(weight)
         else:
             w_img, ctx.w_img_t = _pack_node_weight(weight, False), None
@@ -467,6 +549,9 @@ def _fused_aggregate(xin, graph, packed, offset, coeff, cutoff, transposed):
 
 
 def pack_filter_weights(W1, b1, W2, b2):
+    cached = _cached_images(W1)
+    if cached is not None:
+        return cached[0]
     F, Ng = W1.shape
     nbytes = _lib.size_query("cmp_cfconv_tc_weights_bytes")
     packed = torch.empty(nbytes, dtype=torch.uint8, device=W1.device)
@@ -532,8 +617,12 @@ def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff):
     dev = g.device
     xb = torch.empty(N, F, dtype=torch.bfloat16, device=dev)
     call("cmp_f32_to_bf16", ptr(xprime), N * F, ptr(xb))
-    packed = torch.empty(_lib.size_query("cmp_cfconv_tc_bwd_weights_bytes"), dtype=torch.uint8, device=dev)
-    call("cmp_cfconv_tc_pack_bwd_weights", ptr(_f32c(W1)), ptr(_f32c(b1)), ptr(_f32c(W2)), F, Ng, ptr(packed))
+    cached = _cached_images(W1)
+    if cached is not None:
+        packed = cached[1]
+    else:
+        packed = torch.empty(_lib.size_query("cmp_cfconv_tc_bwd_weights_bytes"), dtype=torch.uint8, device=dev)
+        call("cmp_cfconv_tc_pack_bwd_weights", ptr(_f32c(W1)), ptr(_f32c(b1)), ptr(_f32c(W2)), F, Ng, ptr(packed))
     dW1 = torch.empty(F, Ng, dtype=torch.float32, device=dev)
     db1 = torch.empty(F, dtype=torch.float32, device=dev)
     dW2 = torch.empty(F, F, dtype=torch.float32, device=dev)

@@ -329,6 +329,32 @@ size_t cmp_node_gemm_dw_grouped_workspace(void);
 int cmp_node_gemm_dw_grouped(const void* problems /* const cmp_dw_problem_t[count], host */, int count,
                              void* workspace, size_t workspace_bytes, cmp_stream_t stream);
 
+/* Grouped weight packing: every weight image a training step needs in three launches instead of one per layer
+ * (weights change once per step, in cmp_adam_step).  `jobs` are HOST arrays of at most 32 entries.
+ * node job: both images of W[rows, cols] (normal, then transposed) into `packed`
+ *           (cmp_node_gemm_weight_bytes(cols) + cmp_node_gemm_weight_bytes(rows) bytes);
+ * filter job: forward images (cmp_cfconv_tc_weights_bytes()) into packed_fwd and/or backward images
+ *           (cmp_cfconv_tc_bwd_weights_bytes()) into packed_bwd of one interaction block's filter MLP. */
+typedef struct cmp_pack_node_job {
+  const float* W;
+  int32_t rows, cols;
+  void* packed;
+} cmp_pack_node_job_t;
+typedef struct cmp_pack_filter_job {
+  const float* W1;
+  const float* b1;
+  const float* W2;
+  const float* b2;
+  void* packed_fwd;
+  void* packed_bwd;
+} cmp_pack_filter_job_t;
+int cmp_node_gemm_pack_weights_grouped(const void* jobs /* cmp_pack_node_job_t[count] */, int count,
+                                       cmp_stream_t stream);
+int cmp_cfconv_tc_pack_weights_grouped(const void* jobs /* cmp_pack_filter_job_t[count] */, int count,
+                                       int num_filters, int num_gaussians, cmp_stream_t stream);
+int cmp_cfconv_tc_pack_bwd_weights_grouped(const void* jobs /* cmp_pack_filter_job_t[count] */, int count,
+                                           int num_filters, int num_gaussians, cmp_stream_t stream);
+
 /* ------------------------------------------------------------------------- *
  * ViSNet edge-level kernels (exact fp32; tgv.py = torch_geometric_visnet.py)
  * Every reduction runs over the CSR (or its transpose) in a fixed order.
