@@ -351,18 +351,47 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
             const uint32_t ends = ((c0 < 32) ? (ends_lo >> c0) : (ends_hi >> (c0 - 32))) & 0xffffu;
             if (fast) {
               tc::tmem_wait_ld();
+              // Groups of four columns.  The sources of one target row are strictly ascending, so when no row ends
+              // INSIDE a group its four read-modify-write targets are distinct: their loads are issued together instead
+              // of a dependent LDS -> FFMA -> STS chain per column (the compiler cannot prove the stores do not alias).
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float xj = xsb[oj[j]];
-                float aj = accb[oj[j]];
-                accA = fmaf(v[j], xj, accA);
-                aj = fmaf(v[j], xi, aj);
-                accb[oj[j]] = aj;
-                if ((ends >> j) & 1u) {
-                  accb[offI] += accA;
-                  accA = 0.0f;
-                  offI = sOI[min(c0 + j + 1, TE - 1)];
-                  xi = xsb[offI];
+              for (int k = 0; k < 16; k += 4) {
+                if (((ends >> k) & 0x7u) == 0u) {
+                  const float x0 = xsb[oj[k]], x1 = xsb[oj[k + 1]], x2 = xsb[oj[k + 2]], x3 = xsb[oj[k + 3]];
+                  float a0 = accb[oj[k]], a1 = accb[oj[k + 1]], a2 = accb[oj[k + 2]], a3 = accb[oj[k + 3]];
+                  accA = fmaf(v[k], x0, accA);
+                  accA = fmaf(v[k + 1], x1, accA);
+                  accA = fmaf(v[k + 2], x2, accA);
+                  accA = fmaf(v[k + 3], x3, accA);
+                  a0 = fmaf(v[k], xi, a0);
+                  a1 = fmaf(v[k + 1], xi, a1);
+                  a2 = fmaf(v[k + 2], xi, a2);
+                  a3 = fmaf(v[k + 3], xi, a3);
+                  accb[oj[k]] = a0;
+                  accb[oj[k + 1]] = a1;
+                  accb[oj[k + 2]] = a2;
+                  accb[oj[k + 3]] = a3;
+                  if ((ends >> (k + 3)) & 1u) {
+                    accb[offI] += accA;
+                    accA = 0.0f;
+                    offI = sOI[min(c0 + k + 4, TE - 1)];
+                    xi = xsb[offI];
+                  }
+                } else {
+#pragma unroll
+                  for (int j = k; j < k + 4; ++j) {
+                    const float xj = xsb[oj[j]];
+                    float aj = accb[oj[j]];
+                    accA = fmaf(v[j], xj, accA);
+                    aj = fmaf(v[j], xi, aj);
+                    accb[oj[j]] = aj;
+                    if ((ends >> j) & 1u) {
+                      accb[offI] += accA;
+                      accA = 0.0f;
+                      offI = sOI[min(c0 + j + 1, TE - 1)];
+                      xi = xsb[offI];
+                    }
+                  }
                 }
               }
             } else {
