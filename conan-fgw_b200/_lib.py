@@ -129,7 +129,8 @@ class DwProblem(ctypes.Structure):
     """``cmp_dw_problem_t`` of include/conanmp.h (one weight-gradient problem of a grouped launch)."""
     _fields_ = [("dY", ctypes.c_void_p), ("lddy", ctypes.c_int64), ("saved_y", ctypes.c_void_p),
                 ("ldys", ctypes.c_int64), ("X", ctypes.c_void_p), ("ldx", ctypes.c_int64), ("M", ctypes.c_int64),
-                ("K", ctypes.c_int32), ("Nout", ctypes.c_int32), ("dW", ctypes.c_void_p), ("db", ctypes.c_void_p)]
+                ("K", ctypes.c_int32), ("Nout", ctypes.c_int32), ("dW", ctypes.c_void_p), ("lddw", ctypes.c_int64),
+                ("db", ctypes.c_void_p)]
 
 
 def register(extra: dict):

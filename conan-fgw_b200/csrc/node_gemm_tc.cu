@@ -325,6 +325,7 @@ struct DwGroupEntry {
   DwParams p;        // p.partial unused
   float* dW;
   float* db;
+  int64_t lddw;      // leading dimension of dW (a block of a wider weight gradient)
   int cta_begin, cta_count;
 };
 
@@ -352,7 +353,7 @@ __global__ void node_dw_grouped_reduce_kernel(const __grid_constant__ DwGroup g)
   const float* src = g.partial + (int64_t)en.cta_begin * PART_STRIDE + n * KX + k;
   float s = 0.0f;
   for (int c = 0; c < en.cta_count; ++c) s += src[(int64_t)c * PART_STRIDE];
-  if (k < K) en.dW[n * K + k] = s;
+  if (k < K) en.dW[(int64_t)n * en.lddw + k] = s;
   else if (en.db) en.db[n] = s;
 }
 
@@ -525,6 +526,7 @@ struct cmp_dw_problem_host {
   int32_t K;
   int32_t Nout;
   float* dW;
+  int64_t lddw;
   float* db;
 };
 
@@ -560,8 +562,10 @@ extern "C" int cmp_node_gemm_dw_grouped(const void* problems, int count, void* w
     tiles[i] = q.M > 0 ? ceil_div(q.M, (int64_t)TM) : 1;
     total += tiles[i];
     g.e[i].p = DwParams{q.dY, q.lddy, q.saved_y, q.ldys, q.X, q.ldx, nullptr, q.M, q.K, q.Nout};
+    CMP_REQUIRE(q.lddw >= q.K, CMP_EINVAL, "cmp_node_gemm_dw_grouped: lddw must be >= K");
     g.e[i].dW = q.dW;
     g.e[i].db = q.db;
+    g.e[i].lddw = q.lddw;
   }
   // CTAs per problem: proportional to its tiles, at least one, never more than its tiles; spare CTAs go to the
   // problems with the most tiles per CTA

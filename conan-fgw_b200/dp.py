@@ -94,8 +94,10 @@ class RegressionStep:
     backbone -> [G, H/2] -> mean over the K conformers of a molecule (``schnet_based_models.py:242``)
     -> linear head -> MSE (``model/common.py:288``) -> backward -> [all-reduce] -> Adam."""
 
-    def __init__(self, backbone, hidden_half: int, num_conformers: int, lr: float = 1e-3, group=None):
+    def __init__(self, backbone, hidden_half: int, num_conformers: int, lr: float = 1e-3, group=None,
+                 backbone_kwargs=None):
         self.backbone = backbone
+        self.backbone_kwargs = dict(backbone_kwargs or {})   # e.g. {"num_edges": E} for a sync-free ViSNet forward
         dev = next(backbone.parameters()).device
         from .nn import Linear
 
@@ -106,7 +108,7 @@ class RegressionStep:
         self.group = group
 
     def loss(self, z, pos, batch, targets, num_graphs):
-        emb = self.backbone(z, pos, batch, num_graphs=num_graphs)          # [G, H/2]
+        emb = self.backbone(z, pos, batch, num_graphs=num_graphs, **self.backbone_kwargs)          # [G, H/2]
         mol = ops.conformers_mean(emb, self.K)                               # conformers of a molecule are consecutive
         pred = self.head(mol)
         return torch.nn.functional.mse_loss(pred, targets)

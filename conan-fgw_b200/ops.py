@@ -261,6 +261,19 @@ def _tc_dw_blocked(dy2, saved_y, x2, want_db):
     dw = torch.empty(Nout, K, dtype=torch.float32, device=dev)
     db = torch.empty(Nout, dtype=torch.float32, device=dev) if want_db else None
     f4 = 4
+    if deferred_weight_grads.active is not None:
+        # queued for the grouped launch: every <=128 x <=128 block writes straight into dw (leading dimension K)
+        for n0 in range(0, Nout, 128):
+            nb = min(128, Nout - n0)
+            for k0 in range(0, K, 128):
+                kb = min(128, K - k0)
+                deferred_weight_grads.active.append(dict(
+                    dY=dy2.data_ptr() + n0 * f4, lddy=Nout,
+                    saved_y=saved_y.data_ptr() + n0 * f4 if saved_y is not None else None,
+                    ldys=Nout if saved_y is not None else 0, X=x2.data_ptr() + k0 * f4, ldx=K, M=M, K=kb, Nout=nb,
+                    dW=dw.data_ptr() + (n0 * K + k0) * f4, lddw=K,
+                    db=db.data_ptr() + n0 * f4 if (want_db and k0 == 0) else None, keep=(dy2, saved_y, x2)))
+        return dw, db
     for n0 in range(0, Nout, 128):
         nb = min(128, Nout - n0)
         for k0 in range(0, K, 128):
@@ -332,20 +345,18 @@ class deferred_weight_grads:
 def _flush_deferred_dw(queue):
     if not queue:
         return
-    dev = queue[0][0].device
+    dev = queue[0]["keep"][0].device
     gmax = _lib.size_query("cmp_node_gemm_dw_group_max")
     ws = _lib.workspace(_lib.size_query("cmp_node_gemm_dw_grouped_workspace"), dev)
     for lo in range(0, len(queue), gmax):
         chunk = queue[lo:lo + gmax]
         arr = (_lib.DwProblem * len(chunk))()
         work = 0.0
-        for slot, (dy2, y, x2, K, Nout, dw_ptr, db_ptr) in zip(arr, chunk):
-            slot.dY, slot.lddy = dy2.data_ptr(), dy2.stride(0)
-            slot.saved_y, slot.ldys = (y.data_ptr(), y.stride(0)) if y is not None else (None, 0)
-            slot.X, slot.ldx = x2.data_ptr(), x2.stride(0)
-            slot.M, slot.K, slot.Nout = x2.shape[0], K, Nout
-            slot.dW, slot.db = dw_ptr, db_ptr
-            work += 2.0 * x2.shape[0] * K * Nout
+        for slot, q in zip(arr, chunk):
+            slot.dY, slot.lddy, slot.saved_y, slot.ldys = q["dY"], q["lddy"], q["saved_y"], q["ldys"]
+            slot.X, slot.ldx, slot.M, slot.K, slot.Nout = q["X"], q["ldx"], q["M"], q["K"], q["Nout"]
+            slot.dW, slot.lddw, slot.db = q["dW"], q["lddw"], q["db"]
+            work += 2.0 * q["M"] * q["K"] * q["Nout"]
         call("cmp_node_gemm_dw_grouped", ctypes.addressof(arr), len(chunk), ptr(ws), ws.numel(), work=work)
 
 
@@ -392,8 +403,10 @@ class _LinearTCFn(Function):
             if deferred_weight_grads.active is not None:
                 # queued: raw pointers only for the outputs (autograd must stay the sole owner of dw / db, or it
                 # would clone them - unwritten - instead of adopting them as .grad); inputs are kept alive here
-                deferred_weight_grads.active.append((dy2, y, x2, K, Nout, dw.data_ptr(),
-                                                     db.data_ptr() if db is not None else None))
+                deferred_weight_grads.active.append(dict(
+                    dY=dy2.data_ptr(), lddy=dy2.stride(0), saved_y=y.data_ptr() if y is not None else None,
+                    ldys=y.stride(0) if y is not None else 0, X=x2.data_ptr(), ldx=x2.stride(0), M=M, K=K, Nout=Nout,
+                    dW=dw.data_ptr(), lddw=K, db=db.data_ptr() if db is not None else None, keep=(dy2, y, x2)))
             else:
                 ws = _lib.workspace(_lib.size_query("cmp_node_gemm_dw_workspace", K), dy2.device)
                 call("cmp_node_gemm_dw", ptr(dy2), dy2.stride(0), ptr(y), y.stride(0) if y is not None else 0, ptr(x2),

@@ -321,7 +321,8 @@ typedef struct cmp_dw_problem {
   int64_t M;
   int32_t K;
   int32_t Nout;
-  float* dW;            /* [Nout, K] */
+  float* dW;            /* [Nout, K] with leading dimension lddw (a block of a wider gradient when lddw > K) */
+  int64_t lddw;
   float* db;            /* [Nout] or NULL */
 } cmp_dw_problem_t;
 int cmp_node_gemm_dw_group_max(void);
