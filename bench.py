@@ -38,6 +38,9 @@ WORKLOAD = "cfg2_lipo_train"
 METRIC = "ConAN-SchNet conformers/sec fwd+bwd"
 UNIT = "conformers/s"
 CPU_SAMPLE_MOLECULES = 16
+# measured once per round under ncu (never a timing source): DRAM traffic per launch at the default workload
+NCU_DRAM_BYTES_PER_LAUNCH = {"cmp_cfconv_pair_fwd": 12547584, "cmp_cfconv_fused_bwd_weights_pairs": 13398784 + 764672,
+                             "cmp_cfconv_fused_fwd": 15000000}
 
 
 def peaks():
@@ -430,7 +433,12 @@ def run_ours(args):
                           "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in summ.items()},
         "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"],
         "unit": "TFLOP/s", "frac": (achieved / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])) if achieved else None,
-        "traffic": None, "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+        # DRAM bytes of ONE launch of the dominant kernel from the committed `ncu --set full` capture of this workload
+        # (dram__bytes_read.sum + dram__bytes_write.sum); null when the dominant kernel has no capture under profiles/
+        "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(top) if WORKLOAD == "cfg2_lipo_train" else None,
+        "traffic_source": "profiles/r01_pair_fwd_kernel.metrics.csv, profiles/r01_pair_bwd_kernel.metrics.csv "
+                          "(ncu --set full, cfg 2; algorithmic bytes of the pair forward: x 8.8 MB + pair list 3.6 MB)",
+        "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
         "launches_timed": n_l, "kernel_ms_per_step": k_ms / ksteps, "avg_launch_us": 1e3 * k_ms / max(n_l, 1),
         # share of the device-side step: the eager pass is launch-bound on the host, so the kernel's time per step is
         # set against the graph-replayed step (back-to-back kernels), which is what the ncu launch list also measures

@@ -359,3 +359,39 @@ def test_training_step_with_grouped_packs_and_deferred_gradients_matches_plain_a
         l_g = graphed.step(b.z, b.pos, b.batch, targets, b.num_graphs)
         assert torch.equal(l_e, l_g)
     assert torch.equal(eager.flat.flat, graphed.flat.flat)
+
+
+@pytest.mark.parametrize("case", ["single_atoms", "no_edges", "empty_batch", "ragged"])
+def test_bf16_mode_edge_cases_against_oracle(case):
+    """Degenerate inputs through the whole bf16 model (pair list, pair kernel, per-edge kernel, grouped launches):
+    conformers of one atom, a cutoff below every distance, an empty batch, ragged conformer sizes around the 32-atom
+    switch between the two forward kernels."""
+    _need_sm100()
+    cfg = dict(hidden_channels=128, num_filters=128, num_interactions=2, num_gaussians=50, cutoff=10.0)
+    torch.manual_seed(6)
+    if case == "single_atoms":
+        sizes = [1, 5, 1, 1, 12]
+    elif case == "ragged":
+        sizes = [31, 32, 33, 34, 2, 40]
+    elif case == "no_edges":
+        sizes = [6, 9]
+        cfg["cutoff"] = 0.05
+    else:
+        sizes = []
+    o, c = make(seed=7, **cfg)
+    c.set_precision("bf16")
+    batch = torch.cat([torch.full((n,), g, dtype=torch.long) for g, n in enumerate(sizes)]) if sizes \
+        else torch.zeros(0, dtype=torch.long)
+    N = batch.numel()
+    pos = torch.rand(N, 3) * 4.0
+    z = torch.randint(1, 10, (N,))
+    ref = o(z, pos, batch) if N else torch.zeros(0, 64)
+    out = c(z.to(DEV), pos.to(DEV), batch.to(DEV), num_graphs=len(sizes))
+    assert out.shape == (len(sizes), 64)
+    if N:
+        assert rel_err(out, ref) < TOL_BF16
+        ref.pow(2).sum().backward()
+        out.pow(2).sum().backward()
+        for (n_, po), (_, pc) in zip(o.named_parameters(), c.named_parameters()):
+            if po.grad is not None and po.grad.abs().max() > 0:
+                assert rel_err(pc.grad, po.grad) < 2e-2, n_
