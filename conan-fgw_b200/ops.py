@@ -253,7 +253,7 @@ def _tc_matmul_blocked(x2, W, bias=None, residual=None, saved_y=None):
     return y
 
 
-def _tc_dw_blocked(dy2, saved_y, x2, want_db):
+def _tc_dw_blocked(dy2, saved_y, x2, want_db, param=None):
     """dW[Nout, K] = dY'^T X (+ db = column sums of dY') in <=128 x <=128 blocks of cmp_node_gemm_dw."""
     M, Nout = dy2.shape
     K = x2.shape[1]
@@ -272,7 +272,8 @@ def _tc_dw_blocked(dy2, saved_y, x2, want_db):
                     saved_y=saved_y.data_ptr() + n0 * f4 if saved_y is not None else None,
                     ldys=Nout if saved_y is not None else 0, X=x2.data_ptr() + k0 * f4, ldx=K, M=M, K=kb, Nout=nb,
                     dW=dw.data_ptr() + (n0 * K + k0) * f4, lddw=K,
-                    db=db.data_ptr() + n0 * f4 if (want_db and k0 == 0) else None, keep=(dy2, saved_y, x2)))
+                    db=db.data_ptr() + n0 * f4 if (want_db and k0 == 0) else None, keep=(dy2, saved_y, x2),
+                    param=param, dW_base=dw.data_ptr(), first=(n0 == 0 and k0 == 0)))
         return dw, db
     for n0 in range(0, Nout, 128):
         nb = min(128, Nout - n0)
@@ -314,7 +315,7 @@ class _LinearTCBlockedFn(Function):
         if ctx.needs_input_grad[0]:
             dx = _tc_matmul_blocked(dy2, weight.t().contiguous()).reshape(*ctx.lead, K)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw, db = _tc_dw_blocked(dy2, None, x2, ctx.has_bias)
+            dw, db = _tc_dw_blocked(dy2, None, x2, ctx.has_bias, param=weight if ctx.needs_input_grad[1] else None)
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = dy
         return dx, dw, db, dres
@@ -358,6 +359,15 @@ def _flush_deferred_dw(queue):
             slot.dW, slot.lddw, slot.db = q["dW"], q["lddw"], q["db"]
             work += 2.0 * q["M"] * q["K"] * q["Nout"]
         call("cmp_node_gemm_dw_grouped", ctypes.addressof(arr), len(chunk), ptr(ws), ws.numel(), work=work)
+    # autograd must have ADOPTED the tensors that were returned unwritten (it does when .grad was None and nothing else
+    # references them); had it copied or accumulated them instead, the values written above would be lost: fail loudly
+    for q in queue:
+        w = q.get("param")
+        if w is not None and w.is_leaf and q.get("first", True):
+            if w.grad is None or w.grad.data_ptr() != q["dW_base"]:
+                raise _lib.ConanMPError(
+                    "deferred_weight_grads: a parameter gradient was copied or accumulated before the grouped launch "
+                    "wrote it (use it only with p.grad = None and parameters that are used once)")
 
 
 class _LinearTCFn(Function):
@@ -406,7 +416,8 @@ class _LinearTCFn(Function):
                 deferred_weight_grads.active.append(dict(
                     dY=dy2.data_ptr(), lddy=dy2.stride(0), saved_y=y.data_ptr() if y is not None else None,
                     ldys=y.stride(0) if y is not None else 0, X=x2.data_ptr(), ldx=x2.stride(0), M=M, K=K, Nout=Nout,
-                    dW=dw.data_ptr(), lddw=K, db=db.data_ptr() if db is not None else None, keep=(dy2, y, x2)))
+                    dW=dw.data_ptr(), lddw=K, db=db.data_ptr() if db is not None else None, keep=(dy2, y, x2),
+                    param=weight if ctx.needs_input_grad[1] else None, dW_base=dw.data_ptr()))
             else:
                 ws = _lib.workspace(_lib.size_query("cmp_node_gemm_dw_workspace", K), dy2.device)
                 call("cmp_node_gemm_dw", ptr(dy2), dy2.stride(0), ptr(y), y.stride(0) if y is not None else 0, ptr(x2),

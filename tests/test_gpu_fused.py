@@ -316,9 +316,15 @@ def test_deferred_grouped_weight_gradients_match_the_immediate_launches():
         if r is not None:
             assert rel_err(g, r) < 2e-6
             assert torch.equal(g, a)
-    # a head-sized problem (M = conformers, 64 -> 64) and an empty queue go through the same entry point
+    # an empty queue goes through the same exit path
     with ops.deferred_weight_grads():
         pass
+    # gradients that already exist would be ACCUMULATED by autograd before the grouped launch writes them: refused loudly
+    out = c(b.z, b.pos, b.batch, num_graphs=b.num_graphs).pow(2).mean()
+    with pytest.raises(cmp._lib.ConanMPError):
+        with ops.deferred_weight_grads():
+            out.backward()
+    assert ops.deferred_weight_grads.active is None
 
 
 def test_training_step_with_grouped_packs_and_deferred_gradients_matches_plain_autograd():
