@@ -48,7 +48,8 @@ constexpr uint32_t OFF_C = OFF_OI + TE * 4;       // float[64] cosine cutoff
 constexpr uint32_t OFF_FA = OFF_C + TE * 4;       // float[64] 1 when the direction into i is live
 constexpr uint32_t OFF_FB = OFF_FA + TE * 4;      // float[64] 1 when the direction into j is live
 constexpr uint32_t OFF_FLAGS = OFF_FB + TE * 4;   // uint32[4]: row-end masks (columns 0..31, 32..63), unpaired masks
-constexpr uint32_t GROUP_BYTES = OFF_FLAGS + 16;
+constexpr uint32_t OFF_CH = OFF_FLAGS + 16;       // half[64]  cosine cutoff again, as f16 (packed epilogue 1)
+constexpr uint32_t GROUP_BYTES = OFF_CH + TE * 2;
 constexpr uint32_t SMEM_BYTES = W1_BYTES + W2_BYTES + XS_BYTES + NG * GROUP_BYTES;
 static_assert(GROUP_BYTES % 16 == 0, "pipeline blocks must stay 16-byte aligned");
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -71,11 +72,6 @@ struct PairParams {
   int transposed;
   long long* dbg;                  // optional clock64 timeline of CTA 0, pipeline 0 (10 stamps per tile, 24 tiles)
 };
-
-__device__ __forceinline__ float softplus_fast(float x) {
-  const float t = tc::fast_ex2(-1.4426950408889634f * fabsf(x));
-  return fmaf(tc::fast_lg2(1.0f + t) - 1.0f, kLn2, fmaxf(x, 0.0f));
-}
 
 __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -151,7 +147,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
           tc::umma_commit(d1ready);
           tc::mbar_wait_spin(b2ready, par);
           tc::tc_fence_after();
-          const uint32_t idesc2 = tc::umma_idesc_f16(F, npad, 1, 0, 1);
+          const uint32_t idesc2 = tc::umma_idesc_f16(F, npad, 0, 0, 1);   // W2 image and a' are f16
 #pragma unroll
           for (int ks = 0; ks < K2 / 16; ++ks)
             tc::umma_f16(d, tc::umma_smem_desc(aW2 + ks * 256, 128, A2_SBO), tc::umma_smem_desc(aB + ks * 256, 128, A2_SBO),
@@ -181,6 +177,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
     float* sFa = reinterpret_cast<float*>(sB + OFF_FA);
     float* sFb = reinterpret_cast<float*>(sB + OFF_FB);
     uint32_t* sFlags = reinterpret_cast<uint32_t*>(sB + OFF_FLAGS);
+    __half* sCh = reinterpret_cast<__half*>(sB + OFF_CH);
     const uint32_t d = tmem_base + g * TE + ((uint32_t)((warp & 3) * 32) << 16);
     const float cutoff = p.cutoff;
     const bool transposed = p.transposed != 0;
@@ -241,7 +238,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
           const bool rev = live && pre_rev != 0;
           sOJ[e] = live ? (pre_src - cs) * F : 0;
           sOI[e] = live ? (pre_dst - cs) * F : 0;
-          sC[e] = live ? 0.5f * (__cosf(pre_d * kPi / cutoff) + 1.0f) : 0.0f;
+          const float cval = live ? 0.5f * (__cosf(pre_d * kPi / cutoff) + 1.0f) : 0.0f;
+          sC[e] = cval;
+          sCh[e] = __float2half_rn(cval);
           // direction into i (the primary edge j -> i) and into j (its reverse); exchanged in the transposed pass
           sFa[e] = (live && (!transposed || rev)) ? 1.0f : 0.0f;
           sFb[e] = (live && (transposed || rev)) ? 1.0f : 0.0f;
@@ -288,32 +287,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
           for (int c0 = 0; c0 < npad; c0 += 16) {
             float v[16];
             tc::tmem_ld16(d + c0, v);
-            const float4* cp = reinterpret_cast<const float4*>(sC + c0);
-            float c[16];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              const float4 cc = cp[r];
-              c[r * 4 + 0] = cc.x; c[r * 4 + 1] = cc.y; c[r * 4 + 2] = cc.z; c[r * 4 + 3] = cc.w;
-            }
+            const uint4 ca = *reinterpret_cast<const uint4*>(sCh + c0), cb4 = *reinterpret_cast<const uint4*>(sCh + c0 + 8);
+            const uint32_t cw[8] = {ca.x, ca.y, ca.z, ca.w, cb4.x, cb4.y, cb4.z, cb4.w};
             tc::tmem_wait_ld();
+            uint32_t o[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = softplus_fast(v[j]) * c[j];
-            *reinterpret_cast<uint4*>(colp + (c0 >> 3) * A2_SBO) =
-                make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
-                           tc::pack_bf16x2(v[6], v[7]));
-            *reinterpret_cast<uint4*>(colp + ((c0 >> 3) + 1) * A2_SBO) =
-                make_uint4(tc::pack_bf16x2(v[8], v[9]), tc::pack_bf16x2(v[10], v[11]), tc::pack_bf16x2(v[12], v[13]),
-                           tc::pack_bf16x2(v[14], v[15]));
+            for (int j = 0; j < 8; ++j)
+              o[j] = tc::ssp_cutoff_f16x2(v[2 * j], v[2 * j + 1], *reinterpret_cast<const __half2*>(&cw[j]));
+            *reinterpret_cast<uint4*>(colp + (c0 >> 3) * A2_SBO) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(colp + ((c0 >> 3) + 1) * A2_SBO) = make_uint4(o[4], o[5], o[6], o[7]);
           }
           // rows 128..143: row 128 = C_p (multiplies the b2 column of W2aug), rows 129..143 = 0
           for (int item = tt; item < (npad >> 3) * 16; item += GT) {
             const int ec = item >> 4, kr = item & 15;
             uint4 w = make_uint4(0, 0, 0, 0);
-            if (kr == 0) {
-              const float* c = sC + ec * 8;
-              w = make_uint4(tc::pack_bf16x2(c[0], c[1]), tc::pack_bf16x2(c[2], c[3]), tc::pack_bf16x2(c[4], c[5]),
-                             tc::pack_bf16x2(c[6], c[7]));
-            }
+            if (kr == 0) w = *reinterpret_cast<const uint4*>(sCh + ec * 8);
             *reinterpret_cast<uint4*>(sB + ec * A2_SBO + (128 + kr) * 16) = w;
           }
         }

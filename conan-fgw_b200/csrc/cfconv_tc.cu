@@ -6,7 +6,8 @@
 // Work unit = an edge tile: up to 128 edges = a run of whole target rows of one conformer (built by
 // cmp_build_tiles).  Orientation: filter channels live on the 128 TMEM lanes, edges on the columns,
 //   D1[128 hid, e] = W1aug[128, 64]  * rbf_aug[64, e]     (A, B K-major;   bias b1 rides in column Ng)
-//   D2[128 out, e] = W2aug[128, 144] * a'[144, e]         (A K-major, B MN-major)
+//   D2[128 out, e] = W2aug[128, 144] * a'[144, e]         (A K-major, B MN-major; both f16: the softplus epilogue
+//                                                          runs in packed f16x2, tc_common.cuh)
 // with a'[k, e] = C_e * ssp(D1[k, e]) and the extra row a'[128, e] = C_e carrying b2 * C_e, so the
 // epilogue thread that owns channel f walks the tile's edges in CSR order doing one FMA per edge,
 //   acc += D2[f, e] * x'[src_e, f],
@@ -27,7 +28,7 @@ constexpr int F = 128;           // filter channels = UMMA M
 constexpr int TILE_E = 128;      // edges per tile   = max UMMA N
 constexpr int K1 = 64;           // Gaussians padded (+ bias column)
 constexpr int K2 = 144;          // hidden channels + (cutoff, bias) row, padded to 16
-constexpr int XP_CAP = 40;       // atoms of a conformer staged in shared memory
+constexpr int XP_CAP = 39;       // atoms of a conformer staged in shared memory
 constexpr int NG = 3;            // pipelines ("groups") per CTA
 constexpr int GT = 256;          // compute threads per group (8 warps: 2 per TMEM lane quarter)
 constexpr int CTA_THREADS = NG * GT + NG * 32;
@@ -40,10 +41,11 @@ constexpr uint32_t B2_BYTES = K2 * TILE_E * 2;    // 36864 (the rbf image, 16384
 constexpr uint32_t XP_BYTES = XP_CAP * F * 4;     // 40960
 constexpr uint32_t OFF_X = B2_BYTES;
 constexpr uint32_t OFF_META = OFF_X + XP_BYTES;          // int[128] x' row offset (floats) | int[128] target row
-constexpr uint32_t OFF_C = OFF_META + TILE_E * 8;        // float[128] cosine cutoff
-constexpr uint32_t OFF_ROW = OFF_C + TILE_E * 4;         // int[136]  row offsets of the tile (relative)
+constexpr uint32_t OFF_ROW = OFF_META + TILE_E * 8;      // int[136]  row offsets of the tile (relative)
 constexpr uint32_t OFF_END = OFF_ROW + 544;              // uint32[8] row-end bit mask of each 16-edge chunk
-constexpr uint32_t GROUP_BYTES = OFF_END + 32;
+constexpr uint32_t OFF_CH = OFF_END + 32;                // half[128] cosine cutoff again, as f16 (packed epilogue 1)
+constexpr uint32_t GROUP_BYTES = OFF_CH + TILE_E * 2;
+static_assert(W1_BYTES + W2_BYTES + NG * GROUP_BYTES <= 232448 - 2048, "shared memory budget (dynamic + ~2 KB static)");
 constexpr uint32_t SMEM_BYTES = W1_BYTES + W2_BYTES + NG * GROUP_BYTES;
 
 struct FwdParams {
@@ -71,19 +73,6 @@ __device__ __forceinline__ TileInfo load_tile(const int4* __restrict__ tiles, in
   TileInfo t;
   t.row_begin = a.x; t.row_end = a.y; t.cs = a.z; t.cn = a.w; t.e0 = b.x; t.ne = b.y;
   return t;
-}
-
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// ssp(x) = max(x, 0) + ln2 * (log2(1 + 2^(-|x| log2 e)) - 1).  (Folding the "- ln 2" into the bias column would save
-// an instruction but costs accuracy: ssp is small near 0, softplus is not, and a' is rounded to bf16.)
-__device__ __forceinline__ float softplus_fast(float x) {
-  const float t = ex2_approx(-1.4426950408889634f * fabsf(x));
-  return fmaf(tc::fast_lg2(1.0f + t) - 1.0f, kLn2, fmaxf(x, 0.0f));
 }
 
 __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const FwdParams p) {
@@ -161,7 +150,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
         tc::umma_commit(d1ready);
         tc::mbar_wait_spin(b2ready, par);
         tc::tc_fence_after();
-        const uint32_t idesc2 = tc::umma_idesc_f16(F, npad, 1, 0, 1);
+        const uint32_t idesc2 = tc::umma_idesc_f16(F, npad, 0, 0, 1);   // W2 image and a' are f16
 #pragma unroll
         for (int ks = 0; ks < K2 / 16; ++ks)
           tc::umma_f16(d2, tc::umma_smem_desc(aW2 + ks * 256, 128, A2_SBO), tc::umma_smem_desc(aB + ks * 256, 128, A2_SBO),
@@ -186,9 +175,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
     float* sX = reinterpret_cast<float*>(sB + OFF_X);
     int* sSrc = reinterpret_cast<int*>(sB + OFF_META);
     int* sDst = sSrc + TILE_E;
-    float* sC = reinterpret_cast<float*>(sB + OFF_C);
     int* sRow = reinterpret_cast<int*>(sB + OFF_ROW);
     uint32_t* sEnd = reinterpret_cast<uint32_t*>(sB + OFF_END);
+    __half* sCh = reinterpret_cast<__half*>(sB + OFF_CH);
     const uint32_t d1 = tmem_base + g * 128 + ((uint32_t)(wq * 32) << 16);
     const uint32_t d2 = d1;
     const int64_t u = (int64_t)blockIdx.x * NG + g;
@@ -259,7 +248,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
         }
         sSrc[e] = srcoff;
         sDst[e] = dst;
-        sC[e] = cval;
+        sCh[e] = __float2half_rn(cval);
         const unsigned ends = __ballot_sync(0xffffffffu, last);
         if (lane == 0) {
           sEnd[e >> 4] = ends & 0xffffu;
@@ -313,32 +302,21 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
         for (int c0 = cb; c0 < ce; c0 += 16) {
           float v[16];
           tc::tmem_ld16(d1 + c0, v);
-          const float4* cp = reinterpret_cast<const float4*>(sC + c0);
-          float c[16];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 cc = cp[q];
-            c[q * 4 + 0] = cc.x; c[q * 4 + 1] = cc.y; c[q * 4 + 2] = cc.z; c[q * 4 + 3] = cc.w;
-          }
+          const uint4 ca = *reinterpret_cast<const uint4*>(sCh + c0), cb4 = *reinterpret_cast<const uint4*>(sCh + c0 + 8);
+          const uint32_t cw[8] = {ca.x, ca.y, ca.z, ca.w, cb4.x, cb4.y, cb4.z, cb4.w};
           tc::tmem_wait_ld();
+          uint32_t o[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = softplus_fast(v[j]) * c[j];
-          *reinterpret_cast<uint4*>(colp + (c0 >> 3) * A2_SBO) =
-              make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]),
-                         tc::pack_bf16x2(v[6], v[7]));
-          *reinterpret_cast<uint4*>(colp + ((c0 >> 3) + 1) * A2_SBO) =
-              make_uint4(tc::pack_bf16x2(v[8], v[9]), tc::pack_bf16x2(v[10], v[11]), tc::pack_bf16x2(v[12], v[13]),
-                         tc::pack_bf16x2(v[14], v[15]));
+          for (int j = 0; j < 8; ++j)
+            o[j] = tc::ssp_cutoff_f16x2(v[2 * j], v[2 * j + 1], *reinterpret_cast<const __half2*>(&cw[j]));
+          *reinterpret_cast<uint4*>(colp + (c0 >> 3) * A2_SBO) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(colp + ((c0 >> 3) + 1) * A2_SBO) = make_uint4(o[4], o[5], o[6], o[7]);
         }
         // rows 128..143: row 128 = C_e (multiplies the b2 column of W2aug), rows 129..143 = 0
         for (int item = tt; item < (npad >> 3) * 16; item += GT) {
           const int ec = item >> 4, kr = item & 15;
           uint4 q = make_uint4(0, 0, 0, 0);
-          if (kr == 0) {
-            const float* c = sC + ec * 8;
-            q = make_uint4(tc::pack_bf16x2(c[0], c[1]), tc::pack_bf16x2(c[2], c[3]), tc::pack_bf16x2(c[4], c[5]),
-                           tc::pack_bf16x2(c[6], c[7]));
-          }
+          if (kr == 0) q = *reinterpret_cast<const uint4*>(sCh + ec * 8);
           *reinterpret_cast<uint4*>(sB + ec * A2_SBO + (128 + kr) * 16) = q;
         }
       }
@@ -436,7 +414,7 @@ __device__ __forceinline__ void pack_weights_body(const float* __restrict__ W1, 
       v = b2[m];
     }
     uint32_t off = (m & 7) * 16 + (k & 7) * 2 + (m >> 3) * A2_SBO + (k >> 3) * 128;
-    *reinterpret_cast<__nv_bfloat16*>(out + W1_BYTES + off) = __float2bfloat16_rn(v);
+    *reinterpret_cast<__half*>(out + W1_BYTES + off) = __float2half_rn(v);   // f16: the operand of the f16 a' image
   }
 }
 
