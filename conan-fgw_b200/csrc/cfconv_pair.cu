@@ -25,11 +25,11 @@ namespace cmp {
 namespace {
 
 constexpr int F = 128;
-constexpr int TE = 64;            // pair columns per tile = UMMA N
+constexpr int TE = 128;           // pair columns per tile = UMMA N
 constexpr int K1 = 64;            // Gaussians padded (+ bias column)
 constexpr int K2 = 144;           // hidden channels + (cutoff, bias) row, padded to 16
-constexpr int NCAP = 32;          // atoms of a conformer held in shared memory
-constexpr int NG = 4;             // pipelines per CTA
+constexpr int NCAP = 30;          // atoms of a conformer held in shared memory
+constexpr int NG = 3;             // pipelines per CTA
 constexpr int GT = 128;           // compute threads per pipeline: one per filter channel (= TMEM lane)
 constexpr int NCOMP = NG * GT;
 constexpr int CTA_THREADS = NCOMP + NG * 32;
@@ -44,15 +44,13 @@ constexpr uint32_t XS_BYTES = NCAP * F * 4;       // 16384
 constexpr uint32_t OFF_ACC = B2_BYTES;
 constexpr uint32_t OFF_OJ = OFF_ACC + XS_BYTES;   // int[64]   x / accumulator offset (floats) of the pair's source j
 constexpr uint32_t OFF_OI = OFF_OJ + TE * 4;      // int[64]   ... of its target i
-constexpr uint32_t OFF_C = OFF_OI + TE * 4;       // float[64] cosine cutoff
-constexpr uint32_t OFF_FA = OFF_C + TE * 4;       // float[64] 1 when the direction into i is live
-constexpr uint32_t OFF_FB = OFF_FA + TE * 4;      // float[64] 1 when the direction into j is live
-constexpr uint32_t OFF_FLAGS = OFF_FB + TE * 4;   // uint32[4]: row-end masks (columns 0..31, 32..63), unpaired masks
-constexpr uint32_t OFF_CH = OFF_FLAGS + 16;       // half[64]  cosine cutoff again, as f16 (packed epilogue 1)
+constexpr uint32_t OFF_FLAGS = OFF_OI + TE * 4;   // uint32[8]: row-end masks (32 columns per word), then unpaired masks
+constexpr uint32_t OFF_CH = OFF_FLAGS + 32;       // half[64]  cosine cutoff again, as f16 (packed epilogue 1)
 constexpr uint32_t GROUP_BYTES = OFF_CH + TE * 2;
 constexpr uint32_t SMEM_BYTES = W1_BYTES + W2_BYTES + XS_BYTES + NG * GROUP_BYTES;
 static_assert(GROUP_BYTES % 16 == 0, "pipeline blocks must stay 16-byte aligned");
-static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(SMEM_BYTES <= 232448 - 2048, "shared memory budget (dynamic + ~2 KB static)");
+static_assert(GT % TE == 0 && TE % 32 == 0 && NG * TE <= 512, "tile geometry");
 
 struct PairParams {
   const float* x;                  // [N, F]  x' (forward) or dL/dagg (transposed pass)
@@ -103,7 +101,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
     s_c2[tid] = (tid < p.Ng) ? p.coeff_log2e : 0.0f;
   }
   __syncwarp();
-  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 256);
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -162,8 +160,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
     const int g = warp >> 2;
     const int tt = tid - g * GT;          // = filter channel owned in the epilogues (TMEM lane)
     const int chan = tt;
-    const int e = tt & 63;                // pair column of this thread in the metadata / rbf phase
-    const int q = tt >> 6;                // two threads share a column in the rbf phase
+    const int e = tt % TE;                // pair column of this thread in the metadata / rbf phase
+    const int q = tt / TE;                // GT / TE threads share a column in the rbf phase
     uint64_t* xbar = &bars[1];
     uint64_t* b1ready = &bars[2 + g * 4 + 0];
     uint64_t* d1ready = &bars[2 + g * 4 + 1];
@@ -173,9 +171,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
     float* acc = reinterpret_cast<float*>(sB + OFF_ACC);
     int* sOJ = reinterpret_cast<int*>(sB + OFF_OJ);
     int* sOI = reinterpret_cast<int*>(sB + OFF_OI);
-    float* sC = reinterpret_cast<float*>(sB + OFF_C);
-    float* sFa = reinterpret_cast<float*>(sB + OFF_FA);
-    float* sFb = reinterpret_cast<float*>(sB + OFF_FB);
     uint32_t* sFlags = reinterpret_cast<uint32_t*>(sB + OFF_FLAGS);
     __half* sCh = reinterpret_cast<__half*>(sB + OFF_CH);
     const uint32_t d = tmem_base + g * TE + ((uint32_t)((warp & 3) * 32) << 16);
@@ -239,24 +234,20 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
           sOJ[e] = live ? (pre_src - cs) * F : 0;
           sOI[e] = live ? (pre_dst - cs) * F : 0;
           const float cval = live ? 0.5f * (__cosf(pre_d * kPi / cutoff) + 1.0f) : 0.0f;
-          sC[e] = cval;
           sCh[e] = __float2half_rn(cval);
-          // direction into i (the primary edge j -> i) and into j (its reverse); exchanged in the transposed pass
-          sFa[e] = (live && (!transposed || rev)) ? 1.0f : 0.0f;
-          sFb[e] = (live && (transposed || rev)) ? 1.0f : 0.0f;
           const bool last = live && (pre_nd != pre_dst);
           const unsigned ends = __ballot_sync(0xffffffffu, last);
           const unsigned unp = __ballot_sync(0xffffffffu, live && !rev);
           if (lane == 0) {
             sFlags[e >> 5] = ends;
-            sFlags[2 + (e >> 5)] = unp;
+            sFlags[TE / 32 + (e >> 5)] = unp;
           }
         }
         // ---- Gaussian expansion -> B1 (K-major [pair, 64]); two threads per column ----
         if (e < npad) {
           const float dist = (e < ne) ? pre_d : 0.0f;
           uint8_t* rowp = sB + (e >> 3) * B1_SBO + (e & 7) * 16;
-          for (int jc = q; jc < 2 * k1steps; jc += 2) {
+          for (int jc = q; jc < 2 * k1steps; jc += GT / TE) {
             float v[8];
             const float4* op = reinterpret_cast<const float4*>(s_offset + jc * 8);
             const float4* cp2 = reinterpret_cast<const float4*>(s_c2 + jc * 8);
@@ -321,8 +312,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
         {
           const float* xsb = sXs + chan;
           float* accb = acc + chan;
-          const uint32_t ends_lo = sFlags[0], ends_hi = sFlags[1];
-          const bool fast = (sFlags[2] | sFlags[3]) == 0u;   // every live column has both directions
+          uint32_t unp_any = 0u;
+#pragma unroll
+          for (int w = 0; w < TE / 32; ++w) unp_any |= sFlags[TE / 32 + w];
+          const bool fast = unp_any == 0u;   // every live column has both directions
           int offI = sOI[0];
           float xi = xsb[offI];
           float accA = 0.0f;
@@ -336,7 +329,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
               const int4 o = jp[r];
               oj[4 * r + 0] = o.x; oj[4 * r + 1] = o.y; oj[4 * r + 2] = o.z; oj[4 * r + 3] = o.w;
             }
-            const uint32_t ends = ((c0 < 32) ? (ends_lo >> c0) : (ends_hi >> (c0 - 32))) & 0xffffu;
+            const uint32_t ends = (sFlags[c0 >> 5] >> (c0 & 31)) & 0xffffu;
             if (fast) {
               tc::tmem_wait_ld();
               // Groups of four columns.  The sources of one target row are strictly ascending, so when no row ends
@@ -383,14 +376,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
                 }
               }
             } else {
+              // direction into i (the primary edge j -> i) and into j (its reverse); an unpaired edge keeps only its
+              // own direction, which is the one into i - or into j in the transposed pass
+              const uint32_t unp = (sFlags[TE / 32 + (c0 >> 5)] >> (c0 & 31)) & 0xffffu;
               float fa[16], fb[16];
-              const float4* ap = reinterpret_cast<const float4*>(sFa + c0);
-              const float4* bp = reinterpret_cast<const float4*>(sFb + c0);
 #pragma unroll
-              for (int r = 0; r < 4; ++r) {
-                const float4 a4 = ap[r], b4 = bp[r];
-                fa[4 * r + 0] = a4.x; fa[4 * r + 1] = a4.y; fa[4 * r + 2] = a4.z; fa[4 * r + 3] = a4.w;
-                fb[4 * r + 0] = b4.x; fb[4 * r + 1] = b4.y; fb[4 * r + 2] = b4.z; fb[4 * r + 3] = b4.w;
+              for (int r = 0; r < 16; ++r) {
+                const float paired = ((unp >> r) & 1u) ? 0.0f : 1.0f;
+                fa[r] = transposed ? paired : 1.0f;
+                fb[r] = transposed ? 1.0f : paired;
               }
               tc::tmem_wait_ld();
 #pragma unroll
@@ -435,7 +429,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
 
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem_base, 256);
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
