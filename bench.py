@@ -409,8 +409,8 @@ def run_ours(args):
               "cmp_cfconv_fused_bwd_weights_pairs"):
         if k in summ:
             # with the pair kernel active the per-edge forward kernel only zero-fills and serves conformers of more
-            # than 32 atoms (none in this workload): no algorithmic work is booked on it
-            # the forward work is shared by the per-edge kernel (conformers above 32 atoms) and the pair kernel (the
+            # than 30 atoms (none in this workload): no algorithmic work is booked on it
+            # the forward work is shared by the per-edge kernel (conformers above 30 atoms) and the pair kernel (the
             # rest); the split is not known on the host, so the edges are booked on whichever of the two ran longer
             # (the workloads of BASELINE.json are uniform: one of the two is idle)
             idle = False

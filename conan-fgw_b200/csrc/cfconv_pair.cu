@@ -1,4 +1,4 @@
-// Fused CFConv over UNDIRECTED PAIRS for small conformers (<= 32 atoms), sm_100a.
+// Fused CFConv over UNDIRECTED PAIRS for small conformers (<= 30 atoms), sm_100a.
 //
 // The filter of PyG's CFConv (W_ij = (W2 ssp(W1 rbf(d_ij) + b1) + b2) C(d_ij)) depends on the distance
 // only, so both directions of a pair share it.  This kernel evaluates the filter MLP ONCE per pair on tcgen05 / TMEM
@@ -7,7 +7,8 @@
 //       agg[i] += W_p * x[j]          (the primary edge j -> i of cmp_build_pair_list)
 //       agg[j] += W_p * x[i]          (its reverse, when it exists)
 // Work unit of a CTA = one conformer: its x rows are staged in shared memory once (1-D TMA bulk copy), its pair list is
-// cut into 64-column tiles that the CTA's NG pipelines take round-robin, and every pipeline accumulates into its OWN
+// cut into 128-column tiles that the CTA's NG pipelines take round-robin (a 27-atom conformer = 351 pairs = one
+// full round of three tiles), and every pipeline accumulates into its OWN
 // [atoms, 128] fp32 accumulator in shared memory (the thread that owns channel f is the only one that touches column f:
 // no atomics).  When the conformer is finished the accumulators are summed in pipeline order and the rows written with
 // plain stores: deterministic.  Conformers with more than NCAP atoms are left to cfconv_tc.cu (tile list filtered by

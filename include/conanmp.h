@@ -223,12 +223,12 @@ int cmp_cfconv_fused_fwd(const float* xprime, const float* dist, const int32_t* 
                          float coeff, float cutoff, int64_t N, int num_filters, float* agg,
                          cmp_stream_t stream);
 
-/* The same aggregation for conformers of at most cmp_cfconv_pair_max_atoms() (32) atoms, one filter evaluation per
+/* The same aggregation for conformers of at most cmp_cfconv_pair_max_atoms() (30) atoms, one filter evaluation per
  * UNDIRECTED pair (cmp_build_pair_list): the filter depends on d_ij only, so j -> i and i -> j share it.  One CTA per
  * conformer at a time (x rows staged in shared memory by a TMA bulk copy, per-pipeline [atoms, F] accumulators in
  * shared memory, summed in a fixed order: deterministic, no atomics).  Rows of larger conformers (and of conformers
  * without edges) are NOT written: run cmp_cfconv_fused_fwd first with tiles from
- * cmp_build_tiles_min_atoms(min_atoms = 33) - it zero-fills `agg` and serves the large conformers.
+ * cmp_build_tiles_min_atoms(min_atoms = cmp_cfconv_pair_max_atoms() + 1) - it zero-fills `agg` and serves the large conformers.
  * transposed = 1 exchanges the two directions of every pair (the d x' pass of the backward, x = dL/dagg). */
 int cmp_cfconv_pair_max_atoms(void);
 int cmp_cfconv_pair_fwd(const float* x, const int32_t* seg_ptr, const int32_t* conf_pair_ptr,
