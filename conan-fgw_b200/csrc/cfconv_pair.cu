@@ -320,8 +320,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
           int offI = sOI[0];
           float xi = xsb[offI];
           float accA = 0.0f;
+          long long t_ld = 0;
           for (int c0 = 0; c0 < npad; c0 += 16) {
             float v[16];
+            const long long t_a = rec ? clock64() : 0;
             tc::tmem_ld16(d + c0, v);
             int oj[16];
             const int4* jp = reinterpret_cast<const int4*>(sOJ + c0);
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
             const uint32_t ends = (sFlags[c0 >> 5] >> (c0 & 31)) & 0xffffu;
             if (fast) {
               tc::tmem_wait_ld();
+              if (rec) t_ld += clock64() - t_a;
               // Groups of four columns.  The sources of one target row are strictly ascending, so when no row ends
               // INSIDE a group its four read-modify-write targets are distinct: their loads are issued together instead
               // of a dependent LDS -> FFMA -> STS chain per column (the compiler cannot prove the stores do not alias).
@@ -404,6 +407,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
               }
             }
           }
+          if (rec) p.dbg[it * 10 + 9] = t_ld;
         }
         if (rec) p.dbg[it * 10 + 7] = clock64();
         tc::tc_fence_before();

@@ -22,4 +22,4 @@ for i in range(12):
     if r[1] == 0: break
     d = [int(r[k+1]-r[k]) for k in range(7)]
     fin = int(r[8]-r[7]) if r[8] else 0
-    print(i, "t0=%d" % (int(r[1])-base), " ".join(f"{n}={v}" for n, v in zip(names, d)), "->finalize done", fin)
+    print(i, "t0=%d" % (int(r[1])-base), " ".join(f"{n}={v}" for n, v in zip(names, d)), "->finalize done", fin, "| ep2 cycles in TMEM ld+wait:", int(r[9]))
