@@ -311,14 +311,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
           x_ready = true;
         }
         {
-          const float* xsb = sXs + chan;
+          const uint32_t xs_addr = tc::smem_u32(sXs + chan);   // x rows are read-only here: explicit shared addresses
           float* accb = acc + chan;
           uint32_t unp_any = 0u;
 #pragma unroll
           for (int w = 0; w < TE / 32; ++w) unp_any |= sFlags[TE / 32 + w];
           const bool fast = unp_any == 0u;   // every live column has both directions
           int offI = sOI[0];
-          float xi = xsb[offI];
+          float xi = tc::lds_f32(xs_addr + 4u * (uint32_t)(offI));
           float accA = 0.0f;
           long long t_ld = 0;
           for (int c0 = 0; c0 < npad; c0 += 16) {
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
 #pragma unroll
               for (int k = 0; k < 16; k += 4) {
                 if (((ends >> k) & 0x7u) == 0u) {
-                  const float x0 = xsb[oj[k]], x1 = xsb[oj[k + 1]], x2 = xsb[oj[k + 2]], x3 = xsb[oj[k + 3]];
+                  const float x0 = tc::lds_f32(xs_addr + 4u * (uint32_t)oj[k]), x1 = tc::lds_f32(xs_addr + 4u * (uint32_t)oj[k + 1]), x2 = tc::lds_f32(xs_addr + 4u * (uint32_t)oj[k + 2]), x3 = tc::lds_f32(xs_addr + 4u * (uint32_t)oj[k + 3]);
                   float a0 = accb[oj[k]], a1 = accb[oj[k + 1]], a2 = accb[oj[k + 2]], a3 = accb[oj[k + 3]];
                   accA = fmaf(v[k], x0, accA);
                   accA = fmaf(v[k + 1], x1, accA);
@@ -360,12 +360,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
                     accb[offI] += accA;
                     accA = 0.0f;
                     offI = sOI[min(c0 + k + 4, TE - 1)];
-                    xi = xsb[offI];
+                    xi = tc::lds_f32(xs_addr + 4u * (uint32_t)(offI));
                   }
                 } else {
 #pragma unroll
                   for (int j = k; j < k + 4; ++j) {
-                    const float xj = xsb[oj[j]];
+                    const float xj = tc::lds_f32(xs_addr + 4u * (uint32_t)oj[j]);
                     float aj = accb[oj[j]];
                     accA = fmaf(v[j], xj, accA);
                     aj = fmaf(v[j], xi, aj);
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
                       accb[offI] += accA;
                       accA = 0.0f;
                       offI = sOI[min(c0 + j + 1, TE - 1)];
-                      xi = xsb[offI];
+                      xi = tc::lds_f32(xs_addr + 4u * (uint32_t)(offI));
                     }
                   }
                 }
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
               tc::tmem_wait_ld();
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const float xj = xsb[oj[j]];
+                const float xj = tc::lds_f32(xs_addr + 4u * (uint32_t)oj[j]);
                 float aj = accb[oj[j]];
                 accA = fmaf(v[j] * fa[j], xj, accA);
                 aj = fmaf(v[j] * fb[j], xi, aj);
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_pair_kernel(const PairP
                   accb[offI] += accA;
                   accA = 0.0f;
                   offI = sOI[min(c0 + j + 1, TE - 1)];
-                  xi = xsb[offI];
+                  xi = tc::lds_f32(xs_addr + 4u * (uint32_t)(offI));
                 }
               }
             }

@@ -159,6 +159,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 
+// Shared-memory loads through an explicit 32-bit shared-window address held in a register: keeps ptxas from
+// re-deriving the window base (S2UR SR_CgaCtaId + address arithmetic) in front of every access of a hot loop.
+// Read-only data only (not volatile: the compiler may hoist / reorder these loads).
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+
 // ---- packed half-precision ShiftedSoftplus for the filter-MLP epilogue ---------------------------------------
 // ssp(x) * c for two columns at once, entirely in f16x2 (one MUFU.EX2 and ten packed ALU operations per PAIR instead
 // of two MUFU and ~10 ALU per element):  ssp(x) = max(x, 0) + ln(1 + t) - ln 2,  t = 2^(-|x| log2 e) in (0, 1],
