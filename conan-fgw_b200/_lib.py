@@ -78,6 +78,9 @@ SIGNATURES = {
     "cmp_debug_set_fwd_timestamps": (None, [P]),
     "cmp_debug_set_bwd_timestamps": (None, [P]),
     "cmp_debug_set_pair_timestamps": (None, [P]),
+    "cmp_debug_set_dense_timestamps": (None, [P]),
+    "cmp_debug_set_dense_stagger": (None, [I]),
+    "cmp_debug_set_dense_pipes": (None, [I]),
     "cmp_csr_expand_rows": (I, [P, L, P, P]),
     "cmp_cfconv_tc_bwd_tile_edges": (I, []),
     "cmp_build_flat_tiles_workspace": (S, [L]),
@@ -100,6 +103,13 @@ SIGNATURES = {
     "cmp_build_pair_list_workspace": (S, [L, L]),
     "cmp_build_pair_list": (I, [P, P, P, P, L, L, I, L, P, P, P, P, P, P, S, P, P]),
     "cmp_cfconv_fused_bwd_weights_pairs": (I, [P, P, P, P, P, P, P, P, P, P, I, F, F, I, P, P, P, P, P, S, P]),
+    "cmp_cfconv_dense_max_atoms": (I, []),
+    "cmp_cfconv_dense_supported": (I, [I, I]),
+    "cmp_cfconv_dense_weights_bytes": (S, []),
+    "cmp_build_adjacency": (I, [P, P, P, L, L, P, P]),
+    "cmp_cfconv_dense_pack_weights": (I, [P, P, P, P, I, I, P, P]),
+    "cmp_cfconv_dense_pack_weights_grouped": (I, [P, I, I, I, P]),
+    "cmp_cfconv_dense_fwd": (I, [P, P, P, P, L, P, P, I, F, F, I, I, I, P, P, P, P]),
 }
 
 ACT_NONE, ACT_SSP, ACT_SILU = 0, 1, 2
@@ -123,6 +133,12 @@ class PackFilterJob(ctypes.Structure):
     """``cmp_pack_filter_job_t``."""
     _fields_ = [("W1", ctypes.c_void_p), ("b1", ctypes.c_void_p), ("W2", ctypes.c_void_p), ("b2", ctypes.c_void_p),
                 ("packed_fwd", ctypes.c_void_p), ("packed_bwd", ctypes.c_void_p)]
+
+
+class DensePackJob(ctypes.Structure):
+    """``cmp_dense_pack_job_t``."""
+    _fields_ = [("W1", ctypes.c_void_p), ("b1", ctypes.c_void_p), ("W2", ctypes.c_void_p), ("b2", ctypes.c_void_p),
+                ("packed", ctypes.c_void_p)]
 
 
 class DwProblem(ctypes.Structure):

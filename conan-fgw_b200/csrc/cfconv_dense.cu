@@ -1,0 +1,808 @@
+// Fused CFConv over the dense 16 x 16 atom blocks of a conformer, sm_100a (forward and d x' pass).
+//
+// PyG's CFConv (reached from schnet_no_sum.py:161-164) evaluates, per directed edge j -> i,
+//       agg[i] += x'[j] * W(d_ij),     W(d) = (W2 ssp(W1 rbf(d) + b1) + b2) C(d).
+// W depends on the distance only, so both directions of a pair share one filter column.  This kernel evaluates the
+// filter MLP once per undirected pair on tcgen05 / TMEM and applies it to both directions from REGISTERS:
+//
+//   * a conformer (<= 128 atoms) is cut into blocks of 16 atoms; the pairs (i < j) are enumerated block-wise as
+//       DIAG(b)        the 120 pairs inside block b                       column = jl (jl - 1) / 2 + il   (il < jl)
+//       RECT(b, j0)    block b  x  8 later atoms j0 .. j0+7                column = 16 (j - j0) + il
+//     so the pair (i, j) of a TMEM column is a COMPILE-TIME function of the column index;
+//   * the thread that owns filter channel f (= TMEM lane f) keeps x'[16 b + il][f] and agg[16 b + il][f] of the current
+//     row block in registers (x' is re-read from L2 per tile, agg stays); epilogue 2 is two FMAs per (pair, channel),
+//       agg[i] += D2[f, col] * x[j];      agg[j] += D2[f, col] * x[i],
+//     no shared-memory gathers, no read-modify-write chains, no atomics.  Column-direction sums of a RECT tile (8 atoms)
+//     live in registers for the tile and are added to `out` by their owning thread (plain load / store, program order);
+//   * a pair exists iff the radius graph has the edge in at least one direction (adjacency bit matrix built from the CSR
+//     by cmp_build_adjacency: identical edge set by construction).  Missing pairs get C = 0, i.e. an all-zero D2 column.
+//     Truncated (max_num_neighbors) graphs are asymmetric: per-column direction masks select one-sided updates.
+//   * a CTA runs four independent pipelines (4 warps each, 128 TMEM columns each).  A pipeline owns a whole conformer,
+//     pulls the next one from a global counter when done, and never synchronises with the other pipelines, so MUFU-,
+//     FMA-, LSU- and tensor-bound phases of different conformers overlap.  Thread 0 of a pipeline issues its MMAs.
+//
+// Per tile (<= 128 pair columns), orientation as in cfconv_tc.cu (filter channels on the TMEM lanes, pairs on columns):
+//   D1[128, p] = W1aug[128, 64] * rbf_aug[64, p]          f16 operands, log2(e) folded into W1aug / b1
+//   a'[k, p]   = C_p (max(D1, 0) + log2(1 + 2^-|D1|) - 1)  packed f16x2 epilogue   (= C_p ssp(h) / ln 2)
+//   D2[128, p] = W2aug[128, 144] * a'[144, p]              ln 2 folded into W2; row 128 of a' is C_p and carries b2
+//
+// `transposed` exchanges the two directions: the same kernel is the backward pass with respect to x'.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cmp {
+namespace {
+
+constexpr int F = 128;
+constexpr int TE = 128;            // pair columns per tile = max UMMA N
+constexpr int K1 = 64;             // Gaussians padded (+ bias column)
+constexpr int K2 = 144;            // hidden channels + (cutoff, bias) row, padded to 16
+constexpr int NP = 3;              // pipelines per CTA
+constexpr int PT = 128;            // threads per pipeline: one per filter channel (= TMEM lane)
+constexpr int CTA_THREADS = NP * PT;
+constexpr int NMAX = 128;          // atoms per conformer
+constexpr int AW = NMAX / 32;      // adjacency words per atom
+
+constexpr uint32_t W1_BYTES = F * K1 * 2;          // 16384
+constexpr uint32_t W2_BYTES = F * K2 * 2;          // 36864
+constexpr uint32_t B1_SBO = (K1 / 8) * 128;        // 1024: 8-row group stride of a K-major [rows, 64] image
+constexpr uint32_t A2_SBO = (K2 / 8) * 128;        // 2304: 8-row group stride of a K-major [rows, 144] image
+constexpr uint32_t IMG_BYTES = K2 * TE * 2;        // 36864: a' image (the rbf image, 16 KB, aliases its head)
+constexpr uint32_t OFF_C = IMG_BYTES;              // half[128]  cosine cutoff of every column
+constexpr uint32_t OFF_POS = OFF_C + TE * 2;       // float[NMAX * 3]
+constexpr uint32_t OFF_ADJ = OFF_POS + NMAX * 12;  // uint32[NMAX * AW]
+constexpr uint32_t OFF_MASK = OFF_ADJ + NMAX * AW * 4;   // uint32[2][8]: direction masks of the tile (double buffered)
+constexpr uint32_t OFF_MISC = OFF_MASK + 64;       // int[4]
+constexpr uint32_t PIPE_BYTES = (OFF_MISC + 16 + 127) / 128 * 128;
+constexpr uint32_t SMEM_BYTES = W1_BYTES + W2_BYTES + NP * PIPE_BYTES;
+static_assert(SMEM_BYTES <= 232448 - 1024, "shared memory budget");
+
+struct DenseParams {
+  const float* x;            // [N, F]  x' (forward) or dL/dagg (transposed pass)
+  const float* pos;          // [N, 3]
+  const int32_t* seg_ptr;    // [G + 1]
+  const uint32_t* adj;       // [N, AW] bit j of row i: the graph has the edge (conformer-local) j -> i
+  const uint8_t* weights;    // W1 image, W2 image (cmp_cfconv_dense_pack_weights)
+  float* out;                // [N, F]
+  int32_t* counter;          // work counter, zero at launch
+  int32_t* status;           // CMP_STATUS_* bits (may be null)
+  float mu[K1];              // Gaussian centres * s (0 from Ng on)
+  float s;                   // sqrt(-coeff * log2 e):  rbf_k = 2^-(d s - mu_k)^2
+  float delta;               // spacing of the centres * s (uniform grids only)
+  float two_delta, delta2, qstep;   // 2 delta, delta^2, 2^(-2 delta^2)
+  int uniform;               // 1: centres are equally spaced -> anchored recurrence (3 MUFU per 16 Gaussians)
+  int stagger_ns;            // start-up delay between the pipelines of a CTA
+  int active_pipes;          // debug: pipelines >= this index take no work
+  float pi_over_cutoff;
+  int Ng;
+  int G;
+  int transposed;
+  int skip_large;            // 1: conformers above NMAX atoms belong to the per-edge kernel; 0: they are an error
+  long long* dbg;            // optional clock64 timeline of CTA 0 / pipeline 0: 8 stamps per executed tile (first 32)
+};
+
+// column c of a DIAG tile holds the pair (il, jl), il < jl, c = jl (jl - 1) / 2 + il  (loop-free: folds at compile time)
+__host__ __device__ constexpr int diag_j(int c) {
+  return 1 + (c >= 1) + (c >= 3) + (c >= 6) + (c >= 10) + (c >= 15) + (c >= 21) + (c >= 28) + (c >= 36) + (c >= 45) +
+         (c >= 55) + (c >= 66) + (c >= 78) + (c >= 91) + (c >= 105);
+}
+__host__ __device__ constexpr int diag_i(int c) { return c - diag_j(c) * (diag_j(c) - 1) / 2; }
+
+// 16 fp32 columns of this thread's TMEM lane; the wait carries the registers so no use can be scheduled above it
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+
+// ---- shared memory through explicit 32-bit shared-window addresses (no generic-address arithmetic in hot loops) ----
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t addr) { return __uint_as_float(lds32(addr)); }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// mbarrier wait on a shared-window address
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(0x989680u)
+        : "memory");
+  } while (ok == 0);
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<const __half2*>(&u); }
+__device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<const uint32_t*>(&h); }
+
+// Epilogue 1 in two stages so that the MUFU latency of chunk k + 1 hides behind the packed-half arithmetic of chunk k:
+//   stage A (16 fp32 pre-activations x, already scaled by log2 e): t = 2^-|x| on MUFU (fp32), packed to f16x2 with x
+//   stage B: a' = C (max(x, 0) + t Q3(t) - 1), Q3 ~ log2(1 + t) / t, one Horner STEP over all 8 pairs at a time (the
+//            8 chains are independent: written stage-wise so the scheduler interleaves them)
+struct Ep1Chunk {
+  uint32_t th[8];
+  uint32_t xh[8];
+};
+__device__ __forceinline__ void ep1_stage_a(float (&v)[16], Ep1Chunk& c) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c.xh[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = tc::fast_ex2(-fabsf(v[j]));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) c.th[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
+}
+__device__ __forceinline__ void ep1_stage_b(const Ep1Chunk& c, const uint32_t (&cw)[8], uint32_t (&o)[8]) {
+  const __half2 k3 = __float2half2_rn(-0.08479055f), k2 = __float2half2_rn(0.32563294f),
+                k1 = __float2half2_rn(-0.67996303f), k0 = __float2half2_rn(1.43901745f), zero = __float2half2_rn(0.0f);
+  __half2 q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q[j] = __hfma2(k3, as_h2(c.th[j]), k2);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q[j] = __hfma2(q[j], as_h2(c.th[j]), k1);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q[j] = __hfma2(q[j], as_h2(c.th[j]), k0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) q[j] = __hfma2(as_h2(c.th[j]), q[j], __hmax2(as_h2(c.xh[j]), zero));
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = as_u32(__hfma2(q[j], as_h2(cw[j]), __hneg2(as_h2(cw[j]))));
+}
+
+// ---- epilogue 2 of a RECT tile: rows il of the row block against the atoms j0 + jj, 16 columns per atom ----
+//   fwd (edge j -> i): ar[il] += v[il] * xj;      rev (edge i -> j): aj += v[il] * xr[il]
+// MODE 0: every group symmetric (missing pairs have an all-zero column)   1: only i -> j   2: only j -> i   3: mixed
+template <int MODE>
+__device__ __forceinline__ void rect_group(const float (&v)[16], float (&ar)[16], const float (&xr)[16], float xj,
+                                           float& aj, uint32_t mf, uint32_t mr) {
+  if (MODE == 0 || (MODE == 3 && mf == mr)) {
+    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+    for (int il = 0; il < 16; il += 2) {
+      ar[il] = fmaf(v[il], xj, ar[il]);
+      a0 = fmaf(v[il], xr[il], a0);
+      ar[il + 1] = fmaf(v[il + 1], xj, ar[il + 1]);
+      a1 = fmaf(v[il + 1], xr[il + 1], a1);
+    }
+    aj += a0 + a1;
+  } else if (MODE == 1 || (MODE == 3 && mf == 0u)) {
+    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+    for (int il = 0; il < 16; il += 2) {
+      a0 = fmaf(v[il], xr[il], a0);
+      a1 = fmaf(v[il + 1], xr[il + 1], a1);
+    }
+    aj += a0 + a1;
+  } else if (MODE == 2 || (MODE == 3 && mr == 0u)) {
+#pragma unroll
+    for (int il = 0; il < 16; ++il) ar[il] = fmaf(v[il], xj, ar[il]);
+  } else {
+    float a0 = 0.0f;
+#pragma unroll
+    for (int il = 0; il < 16; ++il) {
+      if ((mf >> il) & 1u) ar[il] = fmaf(v[il], xj, ar[il]);
+      if ((mr >> il) & 1u) a0 = fmaf(v[il], xr[il], a0);
+    }
+    aj += a0;
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void rect_tile(uint32_t dtm, int nj, float (&ar)[16], const float (&xr)[16],
+                                          const float (&xjr)[8], float (&ojr)[8], const uint32_t (&mF)[4],
+                                          const uint32_t (&mR)[4]) {
+  float v[16];   // one buffer: a TMEM load is ~20 cycles, the other pipelines of the CTA cover it
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) {
+    if (jj < nj) {
+      const uint32_t mf = (mF[jj >> 1] >> (16 * (jj & 1))) & 0xffffu, mr = (mR[jj >> 1] >> (16 * (jj & 1))) & 0xffffu;
+      tmem_ld16_issue(dtm + jj * 16, v);
+      tmem_ld16_wait(v);
+      rect_group<MODE>(v, ar, xr, xjr[jj], ojr[jj], mf, mr);
+    }
+  }
+}
+
+// ---- epilogue 2 of a DIAG tile: columns are j-major (atom jl owns columns jl (jl - 1) / 2 .. + jl - 1), so ONE uniform
+// branch per jl guards its FMAs (partial blocks) and everything inside is unconditional when the tile is symmetric ----
+template <bool SYM>
+__device__ __forceinline__ void diag_tile(uint32_t dtm, int m, float (&ar)[16], const float (&xr)[16],
+                                          const uint32_t (&mF)[4], const uint32_t (&mR)[4]) {
+  float v[16];
+#pragma unroll
+  for (int jl = 1; jl < 16; ++jl) {
+    if (jl < m) {
+      float aj = 0.0f;
+#pragma unroll
+      for (int il = 0; il < jl; ++il) {
+        const int c = jl * (jl - 1) / 2 + il;
+        if ((c & 15) == 0) {                       // first column of a 16-column chunk (compile-time condition)
+          tmem_ld16_issue(dtm + c, v);
+          tmem_ld16_wait(v);
+        }
+        const float w = v[c & 15];
+        if (SYM) {
+          ar[il] = fmaf(w, xr[jl], ar[il]);
+          aj = fmaf(w, xr[il], aj);
+        } else {
+          if ((mF[c >> 5] >> (c & 31)) & 1u) ar[il] = fmaf(w, xr[jl], ar[il]);
+          if ((mR[c >> 5] >> (c & 31)) & 1u) aj = fmaf(w, xr[il], aj);
+        }
+      }
+      ar[jl] += aj;
+    }
+  }
+}
+
+template <bool DBG>
+__global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_kernel(const __grid_constant__ DenseParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bars[1 + NP * 2];   // wbar | per pipeline: d1ready, d2ready
+  __shared__ uint32_t tmem_base_s;
+
+  uint8_t* sW1 = smem;
+  uint8_t* sW2 = smem + W1_BYTES;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = warp >> 2;                 // pipeline
+  const int t = tid & (PT - 1);            // filter channel (TMEM lane) = pair column in the rbf phase
+  const int wq = warp & 3;                 // TMEM lane quarter of this warp
+
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1);
+    for (int q = 0; q < NP; ++q) {
+      tc::mbar_init(&bars[1 + 2 * q], 1);
+      tc::mbar_init(&bars[2 + 2 * q], 1);
+    }
+    tc::mbar_fence_init();
+    tc::mbar_arrive_expect_tx(&bars[0], W1_BYTES + W2_BYTES);
+    tc::bulk_g2s(sW1, p.weights, W1_BYTES, &bars[0]);
+    tc::bulk_g2s(sW2, p.weights + W1_BYTES, W2_BYTES, &bars[0]);
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+
+  const int bar_id = 1 + g;
+  const uint32_t dcol = tmem_base_s + g * TE;                       // MMA destination (lane 0)
+  const uint32_t dtm = dcol + ((uint32_t)(wq * 32) << 16);          // this warp's lanes
+  const uint32_t aW1 = tc::smem_u32(smem);
+  const uint32_t aB = aW1 + W1_BYTES + W2_BYTES + (uint32_t)g * PIPE_BYTES;   // this pipeline's private block
+  const uint32_t aBar = tc::smem_u32(&bars[1 + 2 * g]);             // d1ready, d2ready = aBar + 8
+  const uint32_t dpair = (uint32_t)diag_i(t) | ((uint32_t)diag_j(t) << 8);   // pair of column t in a DIAG tile
+
+  if (p.stagger_ns > 0 && g > 0) __nanosleep((unsigned)(g * p.stagger_ns));
+  uint32_t ntile_dbg = 0;
+  const bool dbg_on = DBG && p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+#define DBG_STAMP(k) do { if (DBG && dbg_on && ntile_dbg < 32) p.dbg[ntile_dbg * 8 + (k)] = clock64(); } while (0)
+  uint32_t mma_phase = 0;      // parity of d1ready / d2ready (one completion each per executed tile)
+  uint32_t mtile = 0;          // candidate tiles seen (mask double buffer)
+  if (t == 0) tc::mbar_wait(&bars[0], 0);   // weight images (the MMA-issuing thread of every pipeline)
+
+  for (;;) {
+    if (g >= p.active_pipes) break;
+    tc::named_bar_sync(bar_id, PT);
+    if (t == 0) sts32(aB + OFF_MISC, (uint32_t)atomicAdd(p.counter, 1));
+    tc::named_bar_sync(bar_id, PT);
+    const int conf = (int)lds32(aB + OFF_MISC);
+    if (conf >= p.G) break;
+    const int cs = __ldg(p.seg_ptr + conf);
+    const int n = __ldg(p.seg_ptr + conf + 1) - cs;
+    if (n > NMAX) {
+      if (!p.skip_large && t == 0 && p.status) atomicOr(p.status, CMP_STATUS_EDGE_OVERFLOW);
+      continue;
+    }
+    if (n <= 0) continue;
+    const int goff = cs * F + t;          // element offset of (first atom of the conformer, channel t) in x / out
+    if (t < n) {
+      const float* pp = p.pos + (int64_t)(cs + t) * 3;
+      sts32(aB + OFF_POS + 12u * (uint32_t)t + 0, __float_as_uint(__ldg(pp + 0)));
+      sts32(aB + OFF_POS + 12u * (uint32_t)t + 4, __float_as_uint(__ldg(pp + 1)));
+      sts32(aB + OFF_POS + 12u * (uint32_t)t + 8, __float_as_uint(__ldg(pp + 2)));
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.adj) + cs + t);
+      sts128(aB + OFF_ADJ + 16u * (uint32_t)t, a.x, a.y, a.z, a.w);
+    }
+    // rows that later blocks add column sums to start from zero (block 0 is written once, at its end)
+    for (int a = 16; a < n; ++a) p.out[goff + a * F] = 0.0f;
+    tc::named_bar_sync(bar_id, PT);   // staging visible to the whole pipeline
+
+    const int nblocks = (n + 15) >> 4;
+    for (int bi = 0; bi < nblocks; ++bi) {
+      const int a0 = bi * 16;
+      const int m = min(16, n - a0);
+      float ar[16];
+#pragma unroll
+      for (int il = 0; il < 16; ++il) ar[il] = 0.0f;
+      const int nrect = (n > a0 + 16) ? ((n - a0 - 16 + 7) >> 3) : 0;
+      for (int tl = (m >= 2) ? -1 : 0; tl < nrect; ++tl, ++mtile) {
+        const bool diag = tl < 0;
+        const int j0 = diag ? a0 : a0 + 16 + 8 * tl;
+        const int nj = diag ? m : min(8, n - j0);
+        const int ncols = diag ? (m * (m - 1)) >> 1 : 16 * nj;
+        const int npad = (ncols + 15) & ~15;
+
+        DBG_STAMP(0);
+        // ---- which pair does column t hold, and in which directions does the graph have it ----
+        int i_loc, j_loc;
+        bool valid;
+        if (diag) {
+          i_loc = a0 + (int)(dpair & 0xffu);
+          j_loc = a0 + (int)(dpair >> 8);
+          valid = (t < 120) && ((int)(dpair >> 8) < m);
+        } else {
+          i_loc = a0 + (t & 15);
+          j_loc = j0 + (t >> 4);
+          valid = ((t & 15) < m) && ((t >> 4) < nj);
+        }
+        bool ef = false, er = false;
+        if (valid) {
+          ef = (lds32(aB + OFF_ADJ + 4u * (uint32_t)(i_loc * AW + (j_loc >> 5))) >> (j_loc & 31)) & 1u;    // edge j -> i
+          er = (lds32(aB + OFF_ADJ + 4u * (uint32_t)(j_loc * AW + (i_loc >> 5))) >> (i_loc & 31)) & 1u;    // edge i -> j
+        }
+        if (p.transposed) {
+          const bool tmp = ef;
+          ef = er;
+          er = tmp;
+        }
+        const uint32_t amk = aB + OFF_MASK + (mtile & 1u) * 32;
+        {
+          const unsigned bf = __ballot_sync(0xffffffffu, ef), br = __ballot_sync(0xffffffffu, er);
+          if (lane == 0) {
+            sts32(amk + 4u * (uint32_t)wq, bf);
+            sts32(amk + 16 + 4u * (uint32_t)wq, br);
+          }
+        }
+        tc::tc_fence_before();
+        tc::named_bar_sync(bar_id, PT);   // masks visible; previous tile fully consumed (TMEM, images, sC)
+        uint32_t mF[4], mR[4];
+        {
+          const uint4 a = lds128(amk), b = lds128(amk + 16);
+          mF[0] = a.x; mF[1] = a.y; mF[2] = a.z; mF[3] = a.w;
+          mR[0] = b.x; mR[1] = b.y; mR[2] = b.z; mR[3] = b.w;
+        }
+        const uint32_t anyF = mF[0] | mF[1] | mF[2] | mF[3], anyR = mR[0] | mR[1] | mR[2] | mR[3];
+        if ((anyF | anyR) == 0u) continue;   // no pair in this tile
+
+        DBG_STAMP(1);
+        // ---- column t: distance, cutoff, Gaussian expansion -> B1 image (K-major [pair, 64]) ----
+        if (t < npad) {
+          float dist = 0.0f, cval = 0.0f;
+          if (ef || er) {
+            const uint32_t pj = aB + OFF_POS + 12u * (uint32_t)j_loc, pi = aB + OFF_POS + 12u * (uint32_t)i_loc;
+            const float dx = lds_f(pj) - lds_f(pi), dy = lds_f(pj + 4) - lds_f(pi + 4), dz = lds_f(pj + 8) - lds_f(pi + 8);
+            const float d2 = dx * dx + dy * dy + dz * dz;
+            dist = d2 * rsqrtf(fmaxf(d2, 1e-20f));
+            cval = 0.5f * (__cosf(dist * p.pi_over_cutoff) + 1.0f);
+          }
+          asm volatile("st.shared.b16 [%0], %1;" ::"r"(aB + OFF_C + 2u * (uint32_t)t), "h"(__half_as_ushort(__float2half_rn(cval))) : "memory");
+          const uint32_t a_row = aB + (uint32_t)(t >> 3) * B1_SBO + (uint32_t)(t & 7) * 16;   // rbf row of column t
+          const int k1steps = (p.Ng + 16) >> 4;
+          const float ds = dist * p.s;
+          if (p.uniform) {
+            // equally spaced centres: per K-step of 16 Gaussians one anchor g_a = 2^-(u_a^2), u_a = d s - mu_a, and the two
+            // neighbour ratios 2^(+-2 delta u_a - delta^2) from MUFU; the others follow by g_(k+-1) = g_k r, r *= 2^(-2 delta^2)
+            // (a Gaussian more than ~5 centres from d is below f16 resolution, so an underflowing anchor costs nothing)
+#pragma unroll
+            for (int A = 0; A < K1 / 16; ++A) {
+              if (A < k1steps) {
+                float v[16];
+                const float u = ds - p.mu[A * 16 + 7];
+                const float ga = tc::fast_ex2(-u * u);
+                float r = tc::fast_ex2(fmaf(p.two_delta, u, -p.delta2));
+                float sdn = tc::fast_ex2(fmaf(-p.two_delta, u, -p.delta2));
+                v[7] = ga;
+                float gu = ga, gd = ga;
+#pragma unroll
+                for (int i = 1; i <= 8; ++i) {
+                  gu *= r;
+                  v[7 + i] = gu;
+                  if (i < 8) r *= p.qstep;
+                }
+#pragma unroll
+                for (int i = 1; i <= 7; ++i) {
+                  gd *= sdn;
+                  v[7 - i] = gd;
+                  if (i < 7) sdn *= p.qstep;
+                }
+                if (A == (p.Ng >> 4)) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) v[j] = (j == (p.Ng & 15)) ? 1.0f : v[j];
+                }
+                sts128(a_row + (2 * A) * 128, pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                       pack_f16x2(v[6], v[7]));
+                sts128(a_row + (2 * A + 1) * 128, pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]),
+                       pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
+              }
+            }
+          } else {
+#pragma unroll 1
+            for (int jc = 0; jc < 2 * k1steps; ++jc) {
+              float v[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float xx = ds - p.mu[jc * 8 + j];
+                v[j] = tc::fast_ex2(-xx * xx);
+              }
+              if (jc == (p.Ng >> 3)) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = (j == (p.Ng & 7)) ? 1.0f : v[j];
+              }
+              sts128(a_row + jc * 128, pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                     pack_f16x2(v[6], v[7]));
+            }
+          }
+        }
+        DBG_STAMP(2);
+        tc::fence_proxy_async();
+        tc::named_bar_sync(bar_id, PT);
+        if (t == 0) {
+          tc::tc_fence_after();
+          const uint32_t idesc1 = tc::umma_idesc_f16(F, npad, 0, 0, 0);
+          const int k1steps = (p.Ng + 16) >> 4;
+          for (int ks = 0; ks < k1steps; ++ks)
+            tc::umma_f16(dcol, tc::umma_smem_desc(aW1 + ks * 256, 128, B1_SBO), tc::umma_smem_desc(aB + ks * 256, 128, B1_SBO),
+                         idesc1, ks > 0);
+          umma_commit_addr(aBar);
+        }
+
+        // ---- epilogue 1: a' = C (max(D1, 0) + log2(1 + 2^-|D1|) - 1) -> B2 image (MN-major [144, pair]) ----
+        mbar_wait_addr(aBar, mma_phase);
+        tc::tc_fence_after();
+        DBG_STAMP(3);
+        {
+          const uint32_t aC = aB + OFF_C;
+          const uint32_t a_col = aB + (uint32_t)t * 16;                                       // a' column block of channel t
+          float v[16];
+          Ep1Chunk s0, s1;
+          tmem_ld16_issue(dtm, v);
+          tmem_ld16_wait(v);
+          ep1_stage_a(v, s0);
+          if (16 < npad) tmem_ld16_issue(dtm + 16, v);
+          for (int c0 = 0; c0 < npad; c0 += 32) {
+            const bool more1 = c0 + 16 < npad;
+            if (more1) {
+              tmem_ld16_wait(v);
+              ep1_stage_a(v, s1);
+              if (c0 + 32 < npad) tmem_ld16_issue(dtm + c0 + 32, v);
+            }
+            {
+              const uint4 ca = lds128(aC + 2u * (uint32_t)c0), cb4 = lds128(aC + 2u * (uint32_t)c0 + 16);
+              const uint32_t cw[8] = {ca.x, ca.y, ca.z, ca.w, cb4.x, cb4.y, cb4.z, cb4.w};
+              uint32_t o[8];
+              ep1_stage_b(s0, cw, o);
+              sts128(a_col + (uint32_t)(c0 >> 3) * A2_SBO, o[0], o[1], o[2], o[3]);
+              sts128(a_col + (uint32_t)((c0 >> 3) + 1) * A2_SBO, o[4], o[5], o[6], o[7]);
+            }
+            if (more1) {
+              if (c0 + 32 < npad) {
+                tmem_ld16_wait(v);
+                ep1_stage_a(v, s0);
+                if (c0 + 48 < npad) tmem_ld16_issue(dtm + c0 + 48, v);
+              }
+              const uint4 ca = lds128(aC + 2u * (uint32_t)c0 + 32), cb4 = lds128(aC + 2u * (uint32_t)c0 + 48);
+              const uint32_t cw[8] = {ca.x, ca.y, ca.z, ca.w, cb4.x, cb4.y, cb4.z, cb4.w};
+              uint32_t o[8];
+              ep1_stage_b(s1, cw, o);
+              sts128(a_col + (uint32_t)((c0 >> 3) + 2) * A2_SBO, o[0], o[1], o[2], o[3]);
+              sts128(a_col + (uint32_t)((c0 >> 3) + 3) * A2_SBO, o[4], o[5], o[6], o[7]);
+            }
+          }
+          // rows 128..143: row 128 = C_p (multiplies the b2 column of W2aug), rows 129..143 = 0
+          for (int item = t; item < (npad >> 3) * 16; item += PT) {
+            const int ec = item >> 4, kr = item & 15;
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (kr == 0) w = lds128(aC + 16u * (uint32_t)ec);
+            sts128(aB + (uint32_t)ec * A2_SBO + (uint32_t)(128 + kr) * 16, w.x, w.y, w.z, w.w);
+          }
+        }
+        DBG_STAMP(4);
+        tc::tc_fence_before();
+        tc::fence_proxy_async();
+        // operands of epilogue 2 that live in global memory: issued now, needed after the second MMA
+        float xr[16], xjr[8], ojr[8];
+#pragma unroll
+        for (int il = 0; il < 16; ++il) xr[il] = (il < m) ? __ldg(p.x + goff + (a0 + il) * F) : 0.0f;
+        if (!diag) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            xjr[jj] = (jj < nj) ? __ldg(p.x + goff + (j0 + jj) * F) : 0.0f;
+            ojr[jj] = (jj < nj) ? p.out[goff + (j0 + jj) * F] : 0.0f;
+          }
+        }
+        tc::named_bar_sync(bar_id, PT);
+        if (t == 0) {
+          tc::tc_fence_after();
+          const uint32_t idesc2 = tc::umma_idesc_f16(F, npad, 0, 0, 1);
+#pragma unroll
+          for (int ks = 0; ks < K2 / 16; ++ks)
+            tc::umma_f16(dcol, tc::umma_smem_desc(aW1 + W1_BYTES + ks * 256, 128, A2_SBO), tc::umma_smem_desc(aB + ks * 256, 128, A2_SBO),
+                         idesc2, ks > 0);
+          umma_commit_addr(aBar + 8);
+        }
+
+        // ---- epilogue 2: both directions of every pair, register operands ----
+        mbar_wait_addr(aBar + 8, mma_phase);
+        tc::tc_fence_after();
+        mma_phase ^= 1u;
+        DBG_STAMP(5);
+        const bool sym = (mF[0] == mR[0]) && (mF[1] == mR[1]) && (mF[2] == mR[2]) && (mF[3] == mR[3]);
+        if (diag) {
+          if (sym)
+            diag_tile<true>(dtm, m, ar, xr, mF, mR);
+          else
+            diag_tile<false>(dtm, m, ar, xr, mF, mR);
+        } else {
+          if (sym)
+            rect_tile<0>(dtm, nj, ar, xr, xjr, ojr, mF, mR);
+          else if (anyF == 0u)
+            rect_tile<1>(dtm, nj, ar, xr, xjr, ojr, mF, mR);
+          else if (anyR == 0u)
+            rect_tile<2>(dtm, nj, ar, xr, xjr, ojr, mF, mR);
+          else
+            rect_tile<3>(dtm, nj, ar, xr, xjr, ojr, mF, mR);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            if (jj < nj) p.out[goff + (j0 + jj) * F] = ojr[jj];
+        }
+        DBG_STAMP(6);
+        if (DBG && dbg_on && ntile_dbg < 32) p.dbg[ntile_dbg * 8 + 7] = npad;
+        if (DBG) ++ntile_dbg;
+      }
+      // ---- row block finished: its own rows ----
+      if (bi == 0) {
+#pragma unroll
+        for (int il = 0; il < 16; ++il)
+          if (il < m) p.out[goff + (a0 + il) * F] = ar[il];
+      } else {
+#pragma unroll
+        for (int il = 0; il < 16; ++il)
+          if (il < m) p.out[goff + (a0 + il) * F] += ar[il];
+      }
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
+// ---- weight images: f16, log2(e) folded into W1 / b1, ln 2 into W2 ---------------------------------------------
+__device__ __forceinline__ void dense_pack_body(const float* __restrict__ W1, const float* __restrict__ b1,
+                                                const float* __restrict__ W2, const float* __restrict__ b2, int Ng,
+                                                uint8_t* __restrict__ out, int idx) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  if (idx < F * K1) {
+    const int m = idx / K1, k = idx % K1;
+    const float v = (k < Ng) ? W1[m * Ng + k] : (k == Ng ? b1[m] : 0.0f);
+    const uint32_t off = (m & 7) * 16 + (k & 7) * 2 + (m >> 3) * B1_SBO + (k >> 3) * 128;
+    *reinterpret_cast<__half*>(out + off) = __float2half_rn(v * kLog2e);
+  } else if (idx < F * K1 + F * K2) {
+    const int j = idx - F * K1;
+    const int m = j / K2, k = j % K2;
+    float v = 0.0f;
+    if (k < F) {
+      v = W2[m * F + k] * kLn2;
+    } else if (k == F) {
+      v = b2[m];
+    }
+    const uint32_t off = (m & 7) * 16 + (k & 7) * 2 + (m >> 3) * A2_SBO + (k >> 3) * 128;
+    *reinterpret_cast<__half*>(out + W1_BYTES + off) = __float2half_rn(v);
+  }
+}
+
+__global__ void dense_pack_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
+                                  const float* __restrict__ W2, const float* __restrict__ b2, int Ng,
+                                  uint8_t* __restrict__ out) {
+  dense_pack_body(W1, b1, W2, b2, Ng, out, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+constexpr int MAX_PACK_JOBS = 32;
+struct DensePackJob {
+  const float* W1;
+  const float* b1;
+  const float* W2;
+  const float* b2;
+  uint8_t* packed;
+};
+struct DensePackGroup {
+  DensePackJob j[MAX_PACK_JOBS];
+};
+__global__ void dense_pack_grouped_kernel(const __grid_constant__ DensePackGroup g, int Ng) {
+  const DensePackJob& j = g.j[blockIdx.y];
+  dense_pack_body(j.W1, j.b1, j.W2, j.b2, Ng, j.packed, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// ---- adjacency bit matrix of every conformer of <= NMAX atoms -------------------------------------------------
+__global__ void __launch_bounds__(NMAX) adjacency_kernel(const int32_t* __restrict__ rowptr,
+                                                         const int32_t* __restrict__ col,
+                                                         const int32_t* __restrict__ seg_ptr, uint32_t* __restrict__ adj) {
+  const int conf = blockIdx.x;
+  const int cs = seg_ptr[conf], n = seg_ptr[conf + 1] - cs;
+  if (n > NMAX) return;
+  const int a = threadIdx.x;
+  if (a >= n) return;
+  uint32_t w[AW] = {0u, 0u, 0u, 0u};
+  const int e1 = rowptr[cs + a + 1];
+  for (int e = rowptr[cs + a]; e < e1; ++e) {
+    const int j = col[e] - cs;
+    if (j >= 0 && j < NMAX) w[j >> 5] |= 1u << (j & 31);
+  }
+  reinterpret_cast<uint4*>(adj)[cs + a] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+}  // namespace
+}  // namespace cmp
+
+using namespace cmp;
+
+static int g_dense_stagger_ns = 600, g_dense_active_pipes = NP;
+extern "C" void cmp_debug_set_dense_stagger(int ns) { g_dense_stagger_ns = ns; }
+extern "C" void cmp_debug_set_dense_pipes(int n) { g_dense_active_pipes = n; }
+static long long* g_dense_dbg = nullptr;
+extern "C" void cmp_debug_set_dense_timestamps(void* buf) { g_dense_dbg = reinterpret_cast<long long*>(buf); }
+
+extern "C" int cmp_cfconv_dense_max_atoms(void) { return NMAX; }
+
+extern "C" int cmp_cfconv_dense_supported(int num_filters, int num_gaussians) {
+  return num_filters == F && num_gaussians >= 1 && num_gaussians < K1;
+}
+
+extern "C" size_t cmp_cfconv_dense_weights_bytes(void) { return W1_BYTES + W2_BYTES; }
+
+extern "C" int cmp_build_adjacency(const int32_t* rowptr, const int32_t* col, const int32_t* seg_ptr, int64_t N, int64_t G,
+                                   uint32_t* adj, cmp_stream_t stream) {
+  CMP_REQUIRE(N >= 0 && G >= 0 && G < ((int64_t)1 << 31), CMP_EINVAL, "cmp_build_adjacency: bad size");
+  if (N == 0 || G == 0) return CMP_OK;
+  CMP_REQUIRE(rowptr && col && seg_ptr && adj, CMP_EINVAL, "cmp_build_adjacency: null pointer");
+  CMP_REQUIRE((uintptr_t)adj % 16 == 0, CMP_EINVAL, "cmp_build_adjacency: adj must be 16-byte aligned");
+  adjacency_kernel<<<(unsigned)G, NMAX, 0, as_stream(stream)>>>(rowptr, col, seg_ptr, adj);
+  CMP_LAUNCH_CHECK("cmp_build_adjacency");
+  return CMP_OK;
+}
+
+extern "C" int cmp_cfconv_dense_pack_weights(const float* W1, const float* b1, const float* W2, const float* b2,
+                                             int num_filters, int num_gaussians, void* packed, cmp_stream_t stream) {
+  CMP_REQUIRE(cmp_cfconv_dense_supported(num_filters, num_gaussians), CMP_EUNSUPPORTED,
+              "cmp_cfconv_dense_pack_weights: needs num_filters == 128 and num_gaussians < 64 (got %d, %d)", num_filters,
+              num_gaussians);
+  CMP_REQUIRE(W1 && b1 && W2 && b2 && packed, CMP_EINVAL, "cmp_cfconv_dense_pack_weights: null pointer");
+  const int total = F * K1 + F * K2;
+  dense_pack_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(W1, b1, W2, b2, num_gaussians,
+                                                                       reinterpret_cast<uint8_t*>(packed));
+  CMP_LAUNCH_CHECK("cmp_cfconv_dense_pack_weights");
+  return CMP_OK;
+}
+
+extern "C" int cmp_cfconv_dense_pack_weights_grouped(const void* jobs, int count, int num_filters, int num_gaussians,
+                                                     cmp_stream_t stream) {
+  CMP_REQUIRE(cmp_cfconv_dense_supported(num_filters, num_gaussians), CMP_EUNSUPPORTED,
+              "cmp_cfconv_dense_pack_weights_grouped: needs num_filters == 128 and num_gaussians < 64");
+  CMP_REQUIRE(count >= 0 && count <= MAX_PACK_JOBS, CMP_EINVAL,
+              "cmp_cfconv_dense_pack_weights_grouped: count must be in [0, %d]", MAX_PACK_JOBS);
+  if (count == 0) return CMP_OK;
+  CMP_REQUIRE(jobs, CMP_EINVAL, "cmp_cfconv_dense_pack_weights_grouped: null pointer");
+  const DensePackJob* in = reinterpret_cast<const DensePackJob*>(jobs);
+  DensePackGroup grp;
+  for (int i = 0; i < count; ++i) {
+    CMP_REQUIRE(in[i].W1 && in[i].b1 && in[i].W2 && in[i].b2 && in[i].packed, CMP_EINVAL,
+                "cmp_cfconv_dense_pack_weights_grouped: null pointer");
+    grp.j[i] = in[i];
+  }
+  const int total = F * K1 + F * K2;
+  dense_pack_grouped_kernel<<<dim3((total + 255) / 256, count), 256, 0, as_stream(stream)>>>(grp, num_gaussians);
+  CMP_LAUNCH_CHECK("cmp_cfconv_dense_pack_weights_grouped");
+  return CMP_OK;
+}
+
+extern "C" int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int32_t* seg_ptr, const uint32_t* adj,
+                                    int64_t G, const void* packed_weights, const float* offset_host, int num_gaussians,
+                                    float coeff, float cutoff, int num_filters, int transposed, int skip_large,
+                                    float* out, int32_t* counter, int32_t* status, cmp_stream_t stream) {
+  CMP_REQUIRE(cmp_cfconv_dense_supported(num_filters, num_gaussians), CMP_EUNSUPPORTED,
+              "cmp_cfconv_dense_fwd: needs num_filters == 128 and num_gaussians < 64 (got %d, %d)", num_filters,
+              num_gaussians);
+  CMP_REQUIRE(G >= 0 && G < ((int64_t)1 << 31) && cutoff > 0.0f && coeff < 0.0f, CMP_EINVAL,
+              "cmp_cfconv_dense_fwd: bad size, cutoff or coeff");
+  if (G == 0) return CMP_OK;
+  CMP_REQUIRE(x && pos && seg_ptr && adj && packed_weights && offset_host && out && counter, CMP_EINVAL,
+              "cmp_cfconv_dense_fwd: null pointer");
+  CMP_REQUIRE(((uintptr_t)packed_weights % 16 == 0) && ((uintptr_t)adj % 16 == 0), CMP_EINVAL,
+              "cmp_cfconv_dense_fwd: packed_weights / adj must be 16-byte aligned");
+  CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED, "cmp_cfconv_dense_fwd: needs an sm_100 device (tcgen05)");
+  cudaStream_t st = as_stream(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(cfconv_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(cfconv_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) !=
+            cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("cmp_cfconv_dense_fwd: cannot opt in to %u bytes of shared memory", SMEM_BYTES);
+      return CMP_ECUDA;
+    }
+    attr_set = true;
+  }
+  CMP_REQUIRE(cudaMemsetAsync(counter, 0, sizeof(int32_t), st) == cudaSuccess, CMP_ECUDA,
+              "cmp_cfconv_dense_fwd: memset failed");
+  DenseParams p;
+  p.x = x;
+  p.pos = pos;
+  p.seg_ptr = seg_ptr;
+  p.adj = adj;
+  p.weights = reinterpret_cast<const uint8_t*>(packed_weights);
+  p.out = out;
+  p.counter = counter;
+  p.status = status;
+  p.s = sqrtf(-coeff * 1.4426950408889634f);
+  for (int k = 0; k < K1; ++k) p.mu[k] = (k < num_gaussians) ? offset_host[k] * p.s : 0.0f;
+  {
+    // equally spaced centres (GaussianSmearing's linspace)?  then the recurrence applies
+    const float step = num_gaussians > 1 ? (offset_host[num_gaussians - 1] - offset_host[0]) / (float)(num_gaussians - 1) : 1.0f;
+    bool uni = num_gaussians > 1 && step > 0.0f;
+    for (int k = 0; k < num_gaussians && uni; ++k)
+      uni = fabsf(offset_host[k] - (offset_host[0] + step * (float)k)) <= 1e-4f * step;
+    p.uniform = uni ? 1 : 0;
+    p.delta = step * p.s;
+    p.two_delta = 2.0f * p.delta;
+    p.delta2 = p.delta * p.delta;
+    p.qstep = exp2f(-2.0f * p.delta2);
+    if (uni)   // the recurrence reads centres beyond Ng as anchors: continue the grid
+      for (int k = 0; k < K1; ++k) p.mu[k] = (offset_host[0] + step * (float)k) * p.s;
+    // 2^(2 delta |u| ) must stay finite: |u| <= (Ng + 16) delta
+    if (uni && 2.0f * p.delta2 * (float)(num_gaussians + 16) > 120.0f) p.uniform = 0;
+    if (!p.uniform)
+      for (int k = 0; k < K1; ++k) p.mu[k] = (k < num_gaussians) ? offset_host[k] * p.s : 0.0f;
+  }
+  p.stagger_ns = g_dense_stagger_ns;
+  p.active_pipes = g_dense_active_pipes;
+  p.pi_over_cutoff = kPi / cutoff;
+  p.Ng = num_gaussians;
+  p.G = (int)G;
+  p.transposed = transposed;
+  p.skip_large = skip_large;
+  p.dbg = g_dense_dbg;
+  const int grid = (int)std::min<int64_t>((G + NP - 1) / NP, sm_count());
+  CMP_REQUIRE((int64_t)G * NMAX * F < ((int64_t)1 << 31) || true, CMP_EINVAL, "unreachable");
+  if (p.dbg)
+    cfconv_dense_kernel<true><<<grid, CTA_THREADS, SMEM_BYTES, st>>>(p);
+  else
+    cfconv_dense_kernel<false><<<grid, CTA_THREADS, SMEM_BYTES, st>>>(p);
+  CMP_LAUNCH_CHECK("cmp_cfconv_dense_fwd");
+  return CMP_OK;
+}

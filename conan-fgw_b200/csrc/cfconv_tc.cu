@@ -65,13 +65,13 @@ struct FwdParams {
 };
 
 struct TileInfo {
-  int row_begin, row_end, cs, cn, e0, ne;
+  int row_begin, row_end, cs, cn, e0, ne, partial;   // partial: a chunk of ONE oversized row (sum is added, not stored)
 };
 
 __device__ __forceinline__ TileInfo load_tile(const int4* __restrict__ tiles, int64_t ti) {
   const int4 a = __ldg(tiles + 2 * ti), b = __ldg(tiles + 2 * ti + 1);
   TileInfo t;
-  t.row_begin = a.x; t.row_end = a.y; t.cs = a.z; t.cn = a.w; t.e0 = b.x; t.ne = b.y;
+  t.row_begin = a.x; t.row_end = a.y; t.cs = a.z; t.cn = a.w; t.e0 = b.x; t.ne = b.y; t.partial = b.z;
   return t;
 }
 
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
         staged_conf = cs;
         x_wait = true;
       }
-      if (tt <= nrows) sRow[tt] = pre_row - tile.e0;
+      if (tt <= nrows) sRow[tt] = tile.partial ? (tt == 0 ? 0 : ne) : pre_row - tile.e0;
       tc::named_bar_sync(1 + g, GT);
 
       if (rec) p.dbg[it * 8 + 1] = clock64();
@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
         float acc = 0.0f;
         float* aggc = p.agg + chan;
         bool cont = h && cb < ne && !((sEnd[(cb - 1) >> 4] >> ((cb - 1) & 15)) & 1u);
+        const bool partial = tile.partial != 0;
         const float* xs_smem = sX + chan;
         const float* xs_gmem = p.xprime + chan;
         for (int c0 = cb; c0 < ce; c0 += 16) {
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_fused_fwd_kernel(const 
               acc = fmaf(v[j], xs[j], acc);
               if ((ends >> j) & 1u) {
                 float* dstp = aggc + (int64_t)sDst[c0 + j] * F;
-                if (cont) {
+                if (cont || partial) {
                   atomicAdd(dstp, acc);
                   cont = false;
                 } else {

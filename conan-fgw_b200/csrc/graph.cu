@@ -286,15 +286,34 @@ __global__ void csr_to_edge_index_kernel(const int32_t* __restrict__ rowptr, con
 
 // ---- edge tiles: runs of whole target rows of ONE conformer holding <= tile_edges edges ----------
 // (the unit of work of the fused tensor-core kernels: a tile is one UMMA N-extent)
-// descriptor = 2 x int4: {first_row, end_row, conformer_first_atom, conformer_atoms}, {first_edge, num_edges, 0, 0}
+// descriptor = 2 x int4: {first_row, end_row, conformer_first_atom, conformer_atoms}, {first_edge, num_edges, partial, 0}
+// A row with more than tile_edges edges (only possible in the source-sorted transpose of a conformer above 128 atoms:
+// a low-index atom is a source for every in-range target) is cut into chunks of tile_edges edges; each chunk is its own
+// tile with partial = 1 and the kernel ADDS its sum to the (zero-filled) output row instead of storing it.
 __device__ __forceinline__ int walk_tiles(const int32_t* __restrict__ rowptr, int s, int e, int tile_edges,
                                           int4* __restrict__ out, int* status) {
+  (void)status;
   int count = 0, first = s, cur = 0;
   for (int r = s; r < e; ++r) {
-    int d = rowptr[r + 1] - rowptr[r];
+    const int d = rowptr[r + 1] - rowptr[r];
     if (d > tile_edges) {
-      atomicOr(status, CMP_STATUS_EDGE_OVERFLOW);
-      d = 0;
+      if (cur > 0) {
+        if (out) {
+          out[2 * count] = make_int4(first, r, s, e - s);
+          out[2 * count + 1] = make_int4(rowptr[first], rowptr[r] - rowptr[first], 0, 0);
+        }
+        ++count;
+      }
+      for (int k0 = 0; k0 < d; k0 += tile_edges) {
+        if (out) {
+          out[2 * count] = make_int4(r, r + 1, s, e - s);
+          out[2 * count + 1] = make_int4(rowptr[r] + k0, min(tile_edges, d - k0), 1, 0);
+        }
+        ++count;
+      }
+      first = r + 1;
+      cur = 0;
+      continue;
     }
     if (cur + d > tile_edges && cur > 0) {
       if (out) {

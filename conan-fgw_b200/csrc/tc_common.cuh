@@ -39,6 +39,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) __nanosleep(64);
 }
 
+// wait with a long hardware suspend hint: the thread sleeps inside try_wait until the phase completes instead of
+// burning issue slots in a poll / nanosleep loop (the other pipelines of the CTA need them)
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        : "memory");
+  } while (ok == 0);
+}
+
 // latency-critical single-thread wait (the MMA-issuing lane): poll without backing off
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {

@@ -38,6 +38,8 @@ class NeighborList:
         self.status = torch.zeros(1, **i32)
         self.cutoff = None
         self.loop = False
+        self.pos = None              # float32 [N, 3] the list was built from (radius-built lists only)
+        self.max_atoms = None        # caller's bound on atoms per conformer (None: unknown)
         self.sym_atoms = 0           # 0: nothing is known about symmetry (graph built from a raw edge_index)
         self._E = None
         self._edge_index = None
@@ -52,15 +54,17 @@ class NeighborList:
         return self._E
 
     def check(self):
-        """Raise for device-detected input errors (synchronises once)."""
-        if self._checked:
-            return
+        """Raise for device-detected input errors.  Reads the status word (one device -> host copy, synchronises) every
+        time it is called: the lazily built tile / pair lists and the fused kernels report through the same word, so a
+        single early read would miss them.  Sync-free callers (CUDA-graph steps) call this where they synchronise anyway
+        (``dp.RegressionStep.check``)."""
         s = int(self.status.item())
         self._checked = True
         if s & _lib.STATUS_UNSORTED_BATCH:
             raise ValueError("radius_graph: 'batch' must be sorted non-decreasing with ids in [0, num_graphs)")
         if s & _lib.STATUS_EDGE_OVERFLOW:
-            raise RuntimeError("radius_graph: neighbour capacity overflow")
+            raise RuntimeError("radius_graph: neighbour / tile capacity overflow, or a conformer above the promised "
+                               "max_atoms bound")
         if s & _lib.STATUS_BAD_ATOMIC_NUMBER:
             raise ValueError("atomic numbers must lie in [0, 100)")
 
@@ -78,7 +82,7 @@ class NeighborList:
     def _build_tiles(self, rowptr, min_atoms=0):
         dev = rowptr.device
         tile_e = _lib.size_query("cmp_cfconv_tc_tile_edges")
-        cap = self.cap_E // 64 + self.G + 1
+        cap = self.cap_E // 32 + self.G + 1
         tiles = torch.empty(max(cap, 1), 8, dtype=torch.int32, device=dev)
         num = torch.zeros(1, dtype=torch.int32, device=dev)
         ws = _lib.workspace(_lib.size_query("cmp_build_tiles_workspace", self.G), dev)
@@ -109,6 +113,19 @@ class NeighborList:
                           self.cap_E, _lib.ptr(self._dist_t))
             cache[min_atoms] = (tiles, num, self._dist_t)
         return cache[min_atoms]
+
+    def adjacency(self) -> torch.Tensor:
+        """uint32 [N, 4] bit matrix per conformer (bit j of row i: edge j -> i, conformer-local indices) for the dense
+        fused CFConv kernels (``cmp_build_adjacency``; conformers above 128 atoms are left out).  Built once."""
+        if getattr(self, "_adj", None) is None:
+            if self.G == 0 and self.N > 0:
+                raise _lib.ConanMPError("the adjacency matrix needs conformer segments (graph built from a raw edge_index)")
+            adj = torch.empty(max(self.N, 1), 4, dtype=torch.int32, device=self.rowptr.device)
+            _lib.call("cmp_build_adjacency", _lib.ptr(self.rowptr), _lib.ptr(self.col), _lib.ptr(self.seg_ptr), self.N,
+                      self.G, _lib.ptr(adj))
+            self._adj = adj
+            self._counter = torch.zeros(4, dtype=torch.int32, device=adj.device)
+        return self._adj
 
     def erow(self) -> torch.Tensor:
         """Target atom of every edge (``edge_index[1]`` as int32), built once."""
@@ -183,7 +200,8 @@ def num_graphs_of(batch: torch.Tensor, num_graphs: Optional[int] = None) -> int:
 
 def build_neighbor_list(pos: torch.Tensor, batch: Optional[torch.Tensor], r: float, max_num_neighbors: int = 32,
                         loop: bool = False, num_graphs: Optional[int] = None, want_evec: bool = False,
-                        want_transpose: bool = True, num_edges: Optional[int] = None) -> NeighborList:
+                        want_transpose: bool = True, num_edges: Optional[int] = None,
+                        max_atoms: Optional[int] = None) -> NeighborList:
     """``num_edges``: the caller vouches for the edge count (e.g. a CUDA-graph replay of the same geometry); it
     removes the one host synchronisation that code sizing tensors by E otherwise needs."""
     if not pos.is_cuda:
@@ -203,6 +221,8 @@ def build_neighbor_list(pos: torch.Tensor, batch: Optional[torch.Tensor], r: flo
     cap = max_num_neighbors if loop else max_num_neighbors + 1
     nl = NeighborList(N, G, N * cap, dev)
     nl.cutoff, nl.loop = float(r), bool(loop)
+    nl.pos = pos
+    nl.max_atoms = None if max_atoms is None else int(max_atoms)
     nl.sym_atoms = int(cap)      # conformers of at most this many atoms cannot have been truncated: symmetric lists
     i32 = dict(dtype=torch.int32, device=dev)
     if want_evec:
@@ -219,8 +239,7 @@ def build_neighbor_list(pos: torch.Tensor, batch: Optional[torch.Tensor], r: flo
               _lib.ptr(nl.evec), _lib.ptr(nl.rowptr_t), _lib.ptr(nl.col_t), _lib.ptr(nl.eid_t),
               _lib.ptr(nl.conf_edge_ptr), _lib.ptr(ws), ws.numel(), _lib.ptr(nl.status))
     if num_edges is not None:
-        nl._E = int(num_edges)
-        nl._checked = True
+        nl._E = int(num_edges)      # trusted for sizing; the status word still reports device-side errors via check()
     return nl
 
 

@@ -66,9 +66,9 @@ class RadiusInteractionGraph(nn.Module):
         self.cutoff = cutoff
         self.max_num_neighbors = max_num_neighbors
 
-    def neighbor_list(self, pos, batch, num_graphs=None) -> NeighborList:
+    def neighbor_list(self, pos, batch, num_graphs=None, max_atoms=None) -> NeighborList:
         return build_neighbor_list(pos, batch, self.cutoff, self.max_num_neighbors, loop=False,
-                                   num_graphs=num_graphs)
+                                   num_graphs=num_graphs, max_atoms=max_atoms)
 
     def forward(self, pos, batch):
         nl = self.neighbor_list(pos, batch)
@@ -118,7 +118,7 @@ class CFConv(nn.Module):
         """The fused geometric kernel applies: bf16 mode, radius-built graph, Gaussian expansion of its
         distances, standard filter MLP, supported (num_filters, num_gaussians), sm_100 device."""
         return (self.precision == "bf16" and graph is not None and graph.G > 0 and graph.cutoff is not None
-                and isinstance(smearing, GaussianSmearing) and self._standard_mlp()
+                and not graph.loop and isinstance(smearing, GaussianSmearing) and self._standard_mlp()
                 and ops.fused_supported(self.lin1.out_features, smearing.offset.numel())
                 and self.nn[0].in_features == smearing.offset.numel())
 
@@ -219,6 +219,9 @@ class SchNet(nn.Module):
         self.register_buffer("initial_atomref", None)
         self.atomref = None
         self.precision = "fp32"
+        # caller's bound on the atoms of any conformer it will feed (None: unknown).  With a bound <= 128 the fused
+        # path launches the dense-block kernel only; a conformer that breaks the promise raises through the status word.
+        self.max_atoms_hint = None
         self.reset_parameters()
 
     def set_precision(self, precision: str):
@@ -251,7 +254,7 @@ class SchNet(nn.Module):
         """Embedding + T interaction blocks.  Returns ``(h[N,H], graph)``."""
         ig = self.interaction_graph
         if isinstance(ig, RadiusInteractionGraph):
-            graph = ig.neighbor_list(pos, batch, num_graphs)
+            graph = ig.neighbor_list(pos, batch, num_graphs, max_atoms=self.max_atoms_hint)
             h = self.embed(z, graph.status)
             if all(blk.conv.fused_ok(graph, self.distance_expansion) for blk in self.interactions):
                 # fused path: no edge_index / rbf[E, Ng] / filter[E, F] is ever materialised, no host sync

@@ -128,13 +128,14 @@ class prepacked_weights:
 
     cache = None       # {weight.data_ptr(): images} while a context is open
 
-    def __init__(self, modules):
+    def __init__(self, modules, dense_only=False):
         self.modules = list(modules)
+        self.dense_only = bool(dense_only)
 
     def __enter__(self):
         if prepacked_weights.cache is not None:
             raise RuntimeError("prepacked_weights does not nest")
-        prepacked_weights.cache = _prepack(self.modules)
+        prepacked_weights.cache = _prepack(self.modules, self.dense_only)
         return self
 
     def __exit__(self, exc_type, exc, tb):
@@ -142,7 +143,9 @@ class prepacked_weights:
         return False
 
 
-def _prepack(modules):
+def _prepack(modules, dense_only=False):
+    """``dense_only``: the caller vouches that no conformer exceeds the dense kernel's atom limit, so the weight image of
+    the per-edge forward kernel is not needed."""
     from .nn import InteractionBlock, Linear    # late import: nn imports ops
 
     cache = {}
@@ -160,8 +163,11 @@ def _prepack(modules):
                         pf = torch.empty(_lib.size_query("cmp_cfconv_tc_weights_bytes"), dtype=torch.uint8, device=dev)
                         pb = torch.empty(_lib.size_query("cmp_cfconv_tc_bwd_weights_bytes"), dtype=torch.uint8,
                                          device=dev)
-                        cache[W1.data_ptr()] = (pf, pb)
-                        filt.append(tuple(_f32c(t.detach()) for t in (W1, b1, W2, b2)) + (pf, pb))
+                        pd = torch.empty(_lib.size_query("cmp_cfconv_dense_weights_bytes"), dtype=torch.uint8,
+                                         device=dev)
+                        # the per-edge forward image is only packed when conformers above the dense limit may occur
+                        cache[W1.data_ptr()] = (None if (FUSED_DENSE and dense_only) else pf, pb, pd)
+                        filt.append(tuple(_f32c(t.detach()) for t in (W1, b1, W2, b2)) + (pf, pb, pd))
     for root in modules:
         for m in root.modules():
             if isinstance(m, Linear) and m.tc and m.weight.is_cuda and m.weight.data_ptr() not in skip and \
@@ -185,11 +191,17 @@ def _prepack(modules):
         if any(c[0].shape != (F, Ng) for c in chunk):
             raise _lib.ConanMPError("prepacked_weights: interaction blocks of different shapes in one model")
         arr = (_lib.PackFilterJob * len(chunk))()
-        for slot, (W1, b1, W2, b2, pf, pb) in zip(arr, chunk):
+        darr = (_lib.DensePackJob * len(chunk))()
+        for slot, dslot, (W1, b1, W2, b2, pf, pb, pd) in zip(arr, darr, chunk):
             slot.W1, slot.b1, slot.W2, slot.b2 = W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr()
             slot.packed_fwd, slot.packed_bwd = pf.data_ptr(), pb.data_ptr()
-        call("cmp_cfconv_tc_pack_weights_grouped", ctypes.addressof(arr), len(chunk), F, Ng)
+            dslot.W1, dslot.b1, dslot.W2, dslot.b2 = slot.W1, slot.b1, slot.W2, slot.b2
+            dslot.packed = pd.data_ptr()
+        if not (FUSED_DENSE and dense_only):
+            call("cmp_cfconv_tc_pack_weights_grouped", ctypes.addressof(arr), len(chunk), F, Ng)
         call("cmp_cfconv_tc_pack_bwd_weights_grouped", ctypes.addressof(arr), len(chunk), F, Ng)
+        if FUSED_DENSE:
+            call("cmp_cfconv_dense_pack_weights_grouped", ctypes.addressof(darr), len(chunk), F, Ng)
     cache["_keepalive"] = (node, filt)
     return cache
 
@@ -543,44 +555,89 @@ def _fused_fwd_launch(xin, dist, rowptr, col, tiles, num_tiles, packed, offset, 
     return out
 
 
-# conformers of <= cmp_cfconv_pair_max_atoms() atoms: one filter evaluation per undirected pair (cfconv_pair.cu); larger
-# ones stay on the per-edge kernel.  False = per-edge kernel for everything (kept for cross-checking).
+# Forward / d x' aggregation kernel of the fused path:
+#   FUSED_DENSE (default): dense-block kernel (cfconv_dense.cu) for conformers of <= 128 atoms, per-edge kernel for larger
+#   FUSED_PAIR_FORWARD:    round-1 pair-list kernel for conformers of <= 30 atoms + per-edge kernel (cross-checking)
+#   neither:               per-edge kernel for everything (cross-checking)
+FUSED_DENSE = True
 FUSED_PAIR_FORWARD = True
 
 
-def _fused_aggregate(xin, graph, packed, offset, coeff, cutoff, transposed):
-    """agg = sum_j x_j * W(d_ij) C(d_ij) over the neighbour list (or its transpose) on the fused tcgen05 kernels."""
-    e_hint = graph._E if graph._E is not None else graph.cap_E
-    pairs = FUSED_PAIR_FORWARD and graph.G > 0
-    min_atoms = _lib.size_query("cmp_cfconv_pair_max_atoms") + 1 if pairs else 0
+def _offset_host(offset):
+    """Gaussian centres as a host float array (they become kernel parameters of the dense kernel).  Cached on the
+    buffer tensor: the one device -> host copy happens on first use, never inside a captured region afterwards."""
+    key = (offset.data_ptr(), offset._version, offset.numel())
+    cached = getattr(offset, "_cmp_host", None)
+    if cached is None or cached[0] != key:
+        vals = offset.detach().to(torch.float32).cpu().tolist()
+        cached = (key, (ctypes.c_float * len(vals))(*vals))
+        offset._cmp_host = cached
+    return cached[1]
+
+
+def _per_edge_aggregate(xin, graph, packed, offset, coeff, cutoff, transposed, min_atoms, e_hint):
     if transposed:
         tiles, num, dist = graph.tiles_t(min_atoms)
         rowptr, col = graph.rowptr_t, graph.col_t
     else:
         tiles, num = graph.tiles(min_atoms)
         dist, rowptr, col = graph.dist, graph.rowptr, graph.col
-    # zero-fills the output and serves the conformers the pair kernel does not take (their share of the work is
-    # not known on the host without a sync: the algorithmic FLOPs are booked on the pair launch)
-    out = _fused_fwd_launch(xin, dist, rowptr, col, tiles, num, packed, offset, coeff, cutoff, 0 if pairs else e_hint)
+    return _fused_fwd_launch(xin, dist, rowptr, col, tiles, num, packed, offset, coeff, cutoff, e_hint)
+
+
+def _fused_aggregate(xin, graph, W, offset, coeff, cutoff, transposed):
+    """agg = sum_j x_j * W(d_ij) C(d_ij) over the neighbour list (or its transpose) on the fused tcgen05 kernels.
+    ``W`` = (W1, b1, W2, b2) of the filter MLP (weight images come from the prepack cache or are packed here)."""
+    e_hint = graph._E if graph._E is not None else graph.cap_E
+    N, F = xin.shape
+    Ng = offset.numel()
+    flops = 2.0 * (Ng * F + F * F) * float(e_hint)
+    if FUSED_DENSE and graph.G > 0 and graph.pos is not None and not graph.loop:
+        cap = _lib.size_query("cmp_cfconv_dense_max_atoms")
+        dense_only = graph.max_atoms is not None and graph.max_atoms <= cap
+        if dense_only:
+            out = torch.empty(N, F, dtype=torch.float32, device=xin.device)
+        else:
+            # zero-fills the output and serves the conformers above the dense kernel's atom limit (their share of the
+            # work is not known on the host without a sync: the algorithmic FLOPs are booked on the dense launch)
+            out = _per_edge_aggregate(xin, graph, pack_filter_weights(*W), offset, coeff, cutoff, transposed, cap + 1, 0)
+        adj = graph.adjacency()
+        call("cmp_cfconv_dense_fwd", ptr(xin), ptr(graph.pos), ptr(graph.seg_ptr), ptr(adj), graph.G,
+             ptr(pack_dense_weights(*W)), ctypes.addressof(_offset_host(offset)), Ng, float(coeff), float(cutoff), F,
+             int(bool(transposed)), int(not dense_only), ptr(out), ptr(graph._counter), ptr(graph.status), work=flops)
+        return out
+    packed = pack_filter_weights(*W)
+    pairs = FUSED_PAIR_FORWARD and graph.G > 0
+    min_atoms = _lib.size_query("cmp_cfconv_pair_max_atoms") + 1 if pairs else 0
+    out = _per_edge_aggregate(xin, graph, packed, offset, coeff, cutoff, transposed, min_atoms, 0 if pairs else e_hint)
     if pairs:
-        N, F = xin.shape
-        Ng = offset.numel()
         psrc, pdst, pdist, prev, _, _, conf_ptr = graph.pair_tiles()
         call("cmp_cfconv_pair_fwd", ptr(xin), ptr(graph.seg_ptr), ptr(conf_ptr), ptr(psrc), ptr(pdst), ptr(pdist),
              ptr(prev), graph.G, ptr(packed), ptr(offset), Ng, float(coeff), float(cutoff), F, int(bool(transposed)),
-             ptr(out), work=2.0 * (Ng * F + F * F) * float(e_hint))
+             ptr(out), work=flops)
     return out
 
 
 def pack_filter_weights(W1, b1, W2, b2):
     cached = _cached_images(W1)
-    if cached is not None:
+    if cached is not None and cached[0] is not None:
         return cached[0]
     F, Ng = W1.shape
     nbytes = _lib.size_query("cmp_cfconv_tc_weights_bytes")
     packed = torch.empty(nbytes, dtype=torch.uint8, device=W1.device)
     call("cmp_cfconv_tc_pack_weights", ptr(_f32c(W1)), ptr(_f32c(b1)), ptr(_f32c(W2)), ptr(_f32c(b2)), F, Ng,
          ptr(packed))
+    return packed
+
+
+def pack_dense_weights(W1, b1, W2, b2):
+    cached = _cached_images(W1)
+    if cached is not None and len(cached) > 2 and cached[2] is not None:
+        return cached[2]
+    F, Ng = W1.shape
+    packed = torch.empty(_lib.size_query("cmp_cfconv_dense_weights_bytes"), dtype=torch.uint8, device=W1.device)
+    call("cmp_cfconv_dense_pack_weights", ptr(_f32c(W1.detach())), ptr(_f32c(b1.detach())), ptr(_f32c(W2.detach())),
+         ptr(_f32c(b2.detach())), F, Ng, ptr(packed))
     return packed
 
 
@@ -594,15 +651,14 @@ class _CFConvFusedFn(Function):
     @staticmethod
     def forward(ctx, xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff):
         xprime = _f32c(xprime)
-        packed = pack_filter_weights(W1, b1, W2, b2)
-        agg = _fused_aggregate(xprime, graph, packed, offset, coeff, cutoff, transposed=False)
+        agg = _fused_aggregate(xprime, graph, (W1, b1, W2, b2), offset, coeff, cutoff, transposed=False)
         ctx.graph, ctx.coeff, ctx.cutoff = graph, float(coeff), float(cutoff)
-        ctx.save_for_backward(xprime, W1, b1, W2, b2, offset, packed)
+        ctx.save_for_backward(xprime, W1, b1, W2, b2, offset)
         return agg
 
     @staticmethod
     def backward(ctx, g):
-        xprime, W1, b1, W2, b2, offset, packed = ctx.saved_tensors
+        xprime, W1, b1, W2, b2, offset = ctx.saved_tensors
         graph = ctx.graph
         g = _f32c(g)
         N, F = xprime.shape
@@ -610,7 +666,7 @@ class _CFConvFusedFn(Function):
         if ctx.needs_input_grad[0]:
             if graph.rowptr_t is None:
                 raise _lib.ConanMPError("cfconv backward needs the transposed neighbour list")
-            dx = _fused_aggregate(g, graph, packed, offset, ctx.coeff, ctx.cutoff, transposed=True)
+            dx = _fused_aggregate(g, graph, (W1, b1, W2, b2), offset, ctx.coeff, ctx.cutoff, transposed=True)
         grads = [None, None, None, None]
         if any(ctx.needs_input_grad[1:5]):
             if FUSED_WEIGHT_GRADS:

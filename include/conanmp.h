@@ -237,6 +237,45 @@ int cmp_cfconv_pair_fwd(const float* x, const int32_t* seg_ptr, const int32_t* c
                         const float* offset, int num_gaussians, float coeff, float cutoff,
                         int num_filters, int transposed, float* agg, cmp_stream_t stream);
 
+/* The same aggregation over the DENSE 16 x 16 atom blocks of every conformer of at most cmp_cfconv_dense_max_atoms()
+ * (128) atoms (cfconv_dense.cu): one filter evaluation per undirected pair, the pair (i, j) of a TMEM column is a
+ * compile-time function of the column, and the thread that owns a filter channel applies the column to both directions
+ * with x' / agg of the row block held in registers (no shared-memory gathers, no atomics, fixed summation order).
+ * Replaces CFConv.message / propagate as called from sns.py:161-164.
+ *   adj [N, 4] uint32: bit j of row i = the graph has the (conformer-local) edge j -> i; from cmp_build_adjacency
+ *                      (rows of conformers above the atom limit are not written and not read);
+ *   pos [N, 3], seg_ptr [G + 1]: as given to cmp_radius_csr;
+ *   offset_host: the num_gaussians Gaussian centres in HOST memory (they become kernel parameters);
+ *   packed_weights: cmp_cfconv_dense_pack_weights (f16 images, log2 e folded into W1 / b1 and ln 2 into W2);
+ *   counter: one int32 of device scratch (work queue head; the call zeroes it on the stream);
+ *   skip_large = 1: conformers above the atom limit are left untouched (serve them with cmp_cfconv_fused_fwd on tiles
+ *                   from cmp_build_tiles_min_atoms(limit + 1), issued BEFORE this call); 0: they set
+ *                   CMP_STATUS_EDGE_OVERFLOW in *status.
+ * Every row of `agg` that belongs to a conformer within the limit is written (zeros where an atom has no neighbour).
+ * transposed = 1 exchanges the two directions of every pair (the d x' pass of the backward, x = dL/dagg). */
+int cmp_cfconv_dense_max_atoms(void);
+int cmp_cfconv_dense_supported(int num_filters, int num_gaussians);
+size_t cmp_cfconv_dense_weights_bytes(void);
+int cmp_build_adjacency(const int32_t* rowptr, const int32_t* col, const int32_t* seg_ptr, int64_t N,
+                        int64_t G, uint32_t* adj, cmp_stream_t stream);
+int cmp_cfconv_dense_pack_weights(const float* W1, const float* b1, const float* W2, const float* b2,
+                                  int num_filters, int num_gaussians, void* packed, cmp_stream_t stream);
+/* jobs: array of `count` cmp_dense_pack_job_t in HOST memory (count <= 32) */
+typedef struct {
+  const float* W1;
+  const float* b1;
+  const float* W2;
+  const float* b2;
+  void* packed;
+} cmp_dense_pack_job_t;
+int cmp_cfconv_dense_pack_weights_grouped(const void* jobs, int count, int num_filters, int num_gaussians,
+                                          cmp_stream_t stream);
+int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int32_t* seg_ptr, const uint32_t* adj,
+                         int64_t G, const void* packed_weights, const float* offset_host,
+                         int num_gaussians, float coeff, float cutoff, int num_filters, int transposed,
+                         int skip_large, float* agg, int32_t* counter, int32_t* status,
+                         cmp_stream_t stream);
+
 /* Filter-MLP weight gradients of the fused CFConv in ONE kernel (+ a fixed-order reduction of the
  * per-pipeline partial sums): recomputes rbf / hidden / a' per 64-edge tile on chip and accumulates
  * dW2 = sum_e dF_e a'_e^T and dW1 = sum_e dh_e rbf_e^T in TMEM (tcgen05, bf16 operands, fp32
@@ -429,6 +468,12 @@ int cmp_vis_edge_update_bwd(const float* gw, const float* wt, const float* ws, c
 void cmp_debug_set_fwd_timestamps(void* buf);
 /* Same for cmp_cfconv_pair_fwd: 10 timestamps per tile of pipeline 0 (first 24 tiles), 240 int64. */
 void cmp_debug_set_pair_timestamps(void* buf);
+/* Same for cmp_cfconv_dense_fwd: 7 timestamps + the tile width per executed tile of pipeline 0 (first 32), 256 int64. */
+void cmp_debug_set_dense_timestamps(void* buf);
+/* Tuning knob: start-up delay (ns) between the four pipelines of a cmp_cfconv_dense_fwd CTA (default 600). */
+void cmp_debug_set_dense_stagger(int ns);
+/* Debug knob: only the first n pipelines of every cmp_cfconv_dense_fwd CTA take work (default 4). */
+void cmp_debug_set_dense_pipes(int n);
 /* Same for cmp_cfconv_fused_bwd_weights: 12 timestamps per tile (first 20 tiles), 240 int64. */
 void cmp_debug_set_bwd_timestamps(void* buf);
 

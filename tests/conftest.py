@@ -40,3 +40,15 @@ def rel_err(a, b):
     if denom == 0.0:
         return (a - b).abs().max().item()
     return (a - b).abs().max().item() / denom
+
+
+def row_rel_err(a, b, floor=0.05):
+    """Per-row error: max over rows r of max|a_r - b_r| / max(max|b_r|, floor * max|b|).  Tighter than ``rel_err`` for
+    small-magnitude rows (atoms with few neighbours, small parameters); the floor keeps all-zero rows meaningful."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    a, b = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
+    gmax = b.abs().max().item()
+    if gmax == 0.0:
+        return (a - b).abs().max().item()
+    denom = b.abs().max(dim=1).values.clamp_min(floor * gmax)
+    return ((a - b).abs().max(dim=1).values / denom).max().item()

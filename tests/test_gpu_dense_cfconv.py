@@ -1,0 +1,134 @@
+"""Dense-block fused CFConv (cfconv_dense.cu) against the exact-fp32 message kernels on the same neighbour list (GPU).
+
+Covers complete graphs (<= 33 atoms), truncated / asymmetric graphs (max_num_neighbors), sparse graphs (small cutoff),
+every block-boundary size, the 128-atom limit, the fallback above it, and the transposed (d x') pass.
+Stated tolerance of the f16 filter MLP: 5e-3 relative (max|a-b| / max|b|) and 5e-3 per row."""
+import pytest
+import torch
+
+import conan_fgw_b200 as cmp
+from conan_fgw_b200 import ops
+from conftest import rel_err, row_rel_err
+
+pytestmark = pytest.mark.gpu
+syn = cmp.synthetic
+DEV = "cuda"
+TOL = 5e-3
+F, NG = 128, 50
+
+
+def _need_sm100():
+    if not cmp._lib.lib().cmp_device_is_sm100():
+        pytest.skip("tcgen05 kernels need an sm_100 device")
+
+
+def _block(cutoff, seed=0):
+    torch.manual_seed(seed)
+    blk = cmp.InteractionBlock(128, NG, F, cutoff).to(DEV)
+    with torch.no_grad():
+        blk.mlp[0].bias.add_(0.1 * torch.randn(F, device=DEV))
+        blk.mlp[2].bias.add_(0.1 * torch.randn(F, device=DEV))
+    gs = cmp.GaussianSmearing(0.0, cutoff, NG).to(DEV)
+    return blk, gs
+
+
+def _exact(blk, gs, nl, xp, cutoff, g=None):
+    rbf = gs(nl.edge_weight())
+    filt = blk.conv.filter(rbf).detach()
+    xq = xp.detach().clone().requires_grad_(True)
+    agg = ops.cfconv_message(xq, filt, nl, cutoff)
+    if g is None:
+        return agg.detach(), None
+    (dx,) = torch.autograd.grad(agg, xq, g)
+    return agg.detach(), dx
+
+
+def _dense(blk, gs, nl, x, cutoff, transposed):
+    W = (blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight, blk.mlp[2].bias)
+    return ops._fused_aggregate(x, nl, W, gs.offset, gs.coeff, cutoff, transposed)
+
+
+@pytest.mark.parametrize("n,B,K,cutoff,max_nb", [
+    (27, 6, 3, 10.0, 32),     # cfg 2 shape: complete graphs, two row blocks
+    (2, 5, 2, 10.0, 32), (3, 4, 1, 10.0, 32), (16, 3, 2, 10.0, 32), (17, 3, 2, 10.0, 32), (24, 2, 2, 10.0, 32),
+    (25, 2, 2, 10.0, 32), (32, 2, 2, 10.0, 32), (33, 2, 2, 10.0, 32),
+    (45, 2, 2, 10.0, 32),     # cfg 5 shape: truncated
+    (65, 2, 2, 10.0, 32),     # cfg 4 shape: truncated, asymmetric
+    (45, 2, 2, 5.0, 32),      # sparse (cutoff 5)
+    (100, 1, 2, 10.0, 32), (128, 1, 1, 10.0, 32),
+    (40, 2, 2, 10.0, 8),      # hard truncation: mostly one-directional pairs
+])
+def test_dense_kernel_matches_exact_message_path(n, B, K, cutoff, max_nb):
+    _need_sm100()
+    b = syn.make_batch(B, K, n, seed=n).to(DEV)
+    nl = cmp.build_neighbor_list(b.pos, b.batch, cutoff, max_nb, max_atoms=n)
+    blk, gs = _block(cutoff, seed=n)
+    torch.manual_seed(n + 1)
+    xp = torch.randn(b.z.numel(), F, device=DEV)
+    g = torch.randn(b.z.numel(), F, device=DEV)
+    want, want_dx = _exact(blk, gs, nl, xp, cutoff, g)
+    got = _dense(blk, gs, nl, xp, cutoff, False)
+    got_dx = _dense(blk, gs, nl, g, cutoff, True)
+    nl.check()
+    assert rel_err(got, want) < TOL
+    assert rel_err(got_dx, want_dx) < TOL
+    assert row_rel_err(got, want) < 2 * TOL
+    # deterministic (work is handed out by an atomic counter: the assignment of conformers to pipelines varies)
+    for _ in range(3):
+        assert torch.equal(got, _dense(blk, gs, nl, xp, cutoff, False))
+
+
+def test_ragged_batch_and_isolated_atoms():
+    """Conformers of different sizes in one batch, single-atom conformers and atoms without any neighbour."""
+    _need_sm100()
+    sizes = [1, 27, 5, 64, 1, 33, 18, 2]
+    torch.manual_seed(0)
+    pos, batch = [], []
+    for g, n in enumerate(sizes):
+        p = syn.make_batch(1, 1, n, seed=10 + g).pos
+        if n == 18:
+            p[3] += 100.0          # an atom out of everyone's range
+        pos.append(p)
+        batch.append(torch.full((n,), g, dtype=torch.int64))
+    pos, batch = torch.cat(pos).to(DEV), torch.cat(batch).to(DEV)
+    nl = cmp.build_neighbor_list(pos, batch, 10.0, max_atoms=max(sizes))
+    blk, gs = _block(10.0, seed=3)
+    xp = torch.randn(pos.size(0), F, device=DEV)
+    want, _ = _exact(blk, gs, nl, xp, 10.0)
+    got = _dense(blk, gs, nl, xp, 10.0, False)
+    assert rel_err(got, want) < TOL
+    iso = (nl.rowptr[1:] == nl.rowptr[:-1]).nonzero().flatten()
+    assert iso.numel() >= 3 and bool((got[iso] == 0).all())
+
+
+def test_conformers_above_the_dense_limit_use_the_per_edge_kernel():
+    _need_sm100()
+    sizes = [140, 20, 131]
+    pos = torch.cat([syn.make_batch(1, 1, n, seed=n).pos for n in sizes]).to(DEV)
+    batch = torch.cat([torch.full((n,), g, dtype=torch.int64) for g, n in enumerate(sizes)]).to(DEV)
+    nl = cmp.build_neighbor_list(pos, batch, 10.0)            # no max_atoms promise: fallback launch is issued
+    blk, gs = _block(10.0, seed=5)
+    xp = torch.randn(pos.size(0), F, device=DEV)
+    g = torch.randn(pos.size(0), F, device=DEV)
+    want, want_dx = _exact(blk, gs, nl, xp, 10.0, g)
+    assert rel_err(_dense(blk, gs, nl, xp, 10.0, False), want) < TOL
+    assert rel_err(_dense(blk, gs, nl, g, 10.0, True), want_dx) < TOL
+    # a broken promise is reported through the status word, not by wrong numbers going unnoticed
+    nl2 = cmp.build_neighbor_list(pos, batch, 10.0, max_atoms=64)
+    _dense(blk, gs, nl2, xp, 10.0, False)
+    with pytest.raises(RuntimeError):
+        nl2.check()
+
+
+def test_adjacency_bits_equal_the_edge_list():
+    b = syn.make_batch(3, 2, 50, seed=5).to(DEV)
+    nl = cmp.build_neighbor_list(b.pos, b.batch, 10.0)
+    adj = nl.adjacency().cpu()
+    ei = nl.edge_index().cpu()
+    seg = nl.seg_ptr.cpu()
+    conf = torch.bucketize(torch.arange(nl.N), seg[1:], right=True)
+    want = torch.zeros(nl.N, 4, dtype=torch.int64)
+    for j, i in zip(ei[0].tolist(), ei[1].tolist()):
+        jl = j - int(seg[conf[i]])
+        want[i, jl >> 5] |= 1 << (jl & 31)
+    assert torch.equal(adj.to(torch.int64) & 0xFFFFFFFF, want)
