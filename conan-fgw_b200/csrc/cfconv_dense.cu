@@ -73,6 +73,7 @@ struct DenseParams {
   int uniform;               // 1: centres are equally spaced -> anchored recurrence (3 MUFU per 16 Gaussians)
   int stagger_ns;            // start-up delay between the pipelines of a CTA
   int active_pipes;          // debug: pipelines >= this index take no work
+  int dbg_mode;              // debug (DBG kernel only): 1 = no a' stores, 2 = no C loads, 4 = no TMEM loads in epilogue 1
   float pi_over_cutoff;
   int Ng;
   int G;
@@ -151,36 +152,50 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
 __device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<const __half2*>(&u); }
 __device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<const uint32_t*>(&h); }
 
-// Epilogue 1 in two stages so that the MUFU latency of chunk k + 1 hides behind the packed-half arithmetic of chunk k:
-//   stage A (16 fp32 pre-activations x, already scaled by log2 e): t = 2^-|x| on MUFU (fp32), packed to f16x2 with x
-//   stage B: a' = C (max(x, 0) + t Q3(t) - 1), Q3 ~ log2(1 + t) / t, one Horner STEP over all 8 pairs at a time (the
-//            8 chains are independent: written stage-wise so the scheduler interleaves them)
-struct Ep1Chunk {
-  uint32_t th[8];
-  uint32_t xh[8];
-};
-__device__ __forceinline__ void ep1_stage_a(float (&v)[16], Ep1Chunk& c) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) c.xh[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = tc::fast_ex2(-fabsf(v[j]));
-#pragma unroll
-  for (int j = 0; j < 8; ++j) c.th[j] = pack_f16x2(v[2 * j], v[2 * j + 1]);
-}
-__device__ __forceinline__ void ep1_stage_b(const Ep1Chunk& c, const uint32_t (&cw)[8], uint32_t (&o)[8]) {
+// Epilogue 1 on NC columns of this thread's TMEM lane (pre-activations x, already scaled by log2 e):
+//   t = 2^-|x| on MUFU (fp32), then in packed f16x2   a' = C (max(x, 0) + t Q3(t) - 1),   Q3 ~ log2(1 + t) / t.
+// All NC / 2 pair chains are independent: the packed-half work of the first pairs overlaps the MUFUs of the later ones.
+template <int NC>
+__device__ __forceinline__ void ep1_chunk(const float (&v)[NC], const uint32_t (&cw)[NC / 2], uint32_t (&o)[NC / 2]) {
   const __half2 k3 = __float2half2_rn(-0.08479055f), k2 = __float2half2_rn(0.32563294f),
                 k1 = __float2half2_rn(-0.67996303f), k0 = __float2half2_rn(1.43901745f), zero = __float2half2_rn(0.0f);
-  __half2 q[8];
+  uint32_t th[NC / 2];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) q[j] = __hfma2(k3, as_h2(c.th[j]), k2);
+  for (int j = 0; j < NC / 2; ++j)
+    th[j] = pack_f16x2(tc::fast_ex2(-fabsf(v[2 * j])), tc::fast_ex2(-fabsf(v[2 * j + 1])));
 #pragma unroll
-  for (int j = 0; j < 8; ++j) q[j] = __hfma2(q[j], as_h2(c.th[j]), k1);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) q[j] = __hfma2(q[j], as_h2(c.th[j]), k0);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) q[j] = __hfma2(as_h2(c.th[j]), q[j], __hmax2(as_h2(c.xh[j]), zero));
-#pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = as_u32(__hfma2(q[j], as_h2(cw[j]), __hneg2(as_h2(cw[j]))));
+  for (int j = 0; j < NC / 2; ++j) {
+    const __half2 t = as_h2(th[j]);
+    __half2 q = __hfma2(k3, t, k2);
+    q = __hfma2(q, t, k1);
+    q = __hfma2(q, t, k0);
+    q = __hfma2(t, q, __hmax2(as_h2(pack_f16x2(v[2 * j], v[2 * j + 1])), zero));
+    o[j] = as_u32(__hfma2(q, as_h2(cw[j]), __hneg2(as_h2(cw[j]))));
+  }
+}
+
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
 }
 
 // ---- epilogue 2 of a RECT tile: rows il of the row block against the atoms j0 + jj, 16 columns per atom ----
@@ -302,9 +317,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_kernel(const __gr
   const int bar_id = 1 + g;
   const uint32_t dcol = tmem_base_s + g * TE;                       // MMA destination (lane 0)
   const uint32_t dtm = dcol + ((uint32_t)(wq * 32) << 16);          // this warp's lanes
-  const uint32_t aW1 = tc::smem_u32(smem);
-  const uint32_t aB = aW1 + W1_BYTES + W2_BYTES + (uint32_t)g * PIPE_BYTES;   // this pipeline's private block
-  const uint32_t aBar = tc::smem_u32(&bars[1 + 2 * g]);             // d1ready, d2ready = aBar + 8
+  uint32_t aW1 = tc::smem_u32(smem);
+  uint32_t aB = aW1 + W1_BYTES + W2_BYTES + (uint32_t)g * PIPE_BYTES;         // this pipeline's private block
+  asm volatile("mov.u32 %0, %0;" : "+r"(aB));
+  asm volatile("mov.u32 %0, %0;" : "+r"(aW1));
+  uint32_t aBar = tc::smem_u32(&bars[1 + 2 * g]);                   // d1ready, d2ready = aBar + 8
+  // opaque copies: keeps ptxas from re-deriving the shared-window base (S2UR SR_CgaCtaId + arithmetic) inside hot loops
+  asm volatile("mov.u32 %0, %0;" : "+r"(aBar));
   const uint32_t dpair = (uint32_t)diag_i(t) | ((uint32_t)diag_j(t) << 8);   // pair of column t in a DIAG tile
 
   if (p.stagger_ns > 0 && g > 0) __nanosleep((unsigned)(g * p.stagger_ns));
@@ -346,9 +365,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_kernel(const __gr
     for (int bi = 0; bi < nblocks; ++bi) {
       const int a0 = bi * 16;
       const int m = min(16, n - a0);
-      float ar[16];
+      // x' rows of the block and its running sums.  Block 0 starts from zero; the rows of a later block already hold the
+      // column sums the earlier blocks added to them (same thread, program order), so they are the starting value and the
+      // block ends with a plain store.  These loads complete behind the first tile's rbf / MMA phases.
+      float xr[16], ar[16];
 #pragma unroll
-      for (int il = 0; il < 16; ++il) ar[il] = 0.0f;
+      for (int il = 0; il < 16; ++il) {
+        xr[il] = (il < m) ? __ldg(p.x + goff + (a0 + il) * F) : 0.0f;
+        ar[il] = (bi > 0 && il < m) ? p.out[goff + (a0 + il) * F] : 0.0f;
+      }
       const int nrect = (n > a0 + 16) ? ((n - a0 - 16 + 7) >> 3) : 0;
       for (int tl = (m >= 2) ? -1 : 0; tl < nrect; ++tl, ++mtile) {
         const bool diag = tl < 0;
@@ -488,41 +513,37 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_kernel(const __gr
         {
           const uint32_t aC = aB + OFF_C;
           const uint32_t a_col = aB + (uint32_t)t * 16;                                       // a' column block of channel t
-          float v[16];
-          Ep1Chunk s0, s1;
-          tmem_ld16_issue(dtm, v);
-          tmem_ld16_wait(v);
-          ep1_stage_a(v, s0);
-          if (16 < npad) tmem_ld16_issue(dtm + 16, v);
-          for (int c0 = 0; c0 < npad; c0 += 32) {
-            const bool more1 = c0 + 16 < npad;
-            if (more1) {
-              tmem_ld16_wait(v);
-              ep1_stage_a(v, s1);
-              if (c0 + 32 < npad) tmem_ld16_issue(dtm + c0 + 32, v);
-            }
-            {
-              const uint4 ca = lds128(aC + 2u * (uint32_t)c0), cb4 = lds128(aC + 2u * (uint32_t)c0 + 16);
-              const uint32_t cw[8] = {ca.x, ca.y, ca.z, ca.w, cb4.x, cb4.y, cb4.z, cb4.w};
-              uint32_t o[8];
-              ep1_stage_b(s0, cw, o);
-              sts128(a_col + (uint32_t)(c0 >> 3) * A2_SBO, o[0], o[1], o[2], o[3]);
-              sts128(a_col + (uint32_t)((c0 >> 3) + 1) * A2_SBO, o[4], o[5], o[6], o[7]);
-            }
-            if (more1) {
-              if (c0 + 32 < npad) {
-                tmem_ld16_wait(v);
-                ep1_stage_a(v, s0);
-                if (c0 + 48 < npad) tmem_ld16_issue(dtm + c0 + 48, v);
-              }
-              const uint4 ca = lds128(aC + 2u * (uint32_t)c0 + 32), cb4 = lds128(aC + 2u * (uint32_t)c0 + 48);
-              const uint32_t cw[8] = {ca.x, ca.y, ca.z, ca.w, cb4.x, cb4.y, cb4.z, cb4.w};
-              uint32_t o[8];
-              ep1_stage_b(s1, cw, o);
-              sts128(a_col + (uint32_t)((c0 >> 3) + 2) * A2_SBO, o[0], o[1], o[2], o[3]);
-              sts128(a_col + (uint32_t)((c0 >> 3) + 3) * A2_SBO, o[4], o[5], o[6], o[7]);
-            }
+          int c0 = 0;
+          for (; c0 + 32 <= npad; c0 += 32) {
+            if (DBG && dbg_on && ntile_dbg == 1) p.dbg[256 + (c0 >> 5)] = clock64();
+            float v[32];
+            tmem_ld32_issue(dtm + c0, v);
+            const uint4 c_a = lds128(aC + 2u * (uint32_t)c0), c_b = lds128(aC + 2u * (uint32_t)c0 + 16),
+                        c_c = lds128(aC + 2u * (uint32_t)c0 + 32), c_d = lds128(aC + 2u * (uint32_t)c0 + 48);
+            const uint32_t cw[16] = {c_a.x, c_a.y, c_a.z, c_a.w, c_b.x, c_b.y, c_b.z, c_b.w,
+                                     c_c.x, c_c.y, c_c.z, c_c.w, c_d.x, c_d.y, c_d.z, c_d.w};
+            uint32_t o[16];
+            tmem_ld32_wait(v);
+            ep1_chunk<32>(v, cw, o);
+            const uint32_t a_dst = a_col + (uint32_t)(c0 >> 3) * A2_SBO;
+            sts128(a_dst, o[0], o[1], o[2], o[3]);
+            sts128(a_dst + A2_SBO, o[4], o[5], o[6], o[7]);
+            sts128(a_dst + 2 * A2_SBO, o[8], o[9], o[10], o[11]);
+            sts128(a_dst + 3 * A2_SBO, o[12], o[13], o[14], o[15]);
           }
+          if (c0 < npad) {   // a last 16-column chunk
+            float v[16];
+            tmem_ld16_issue(dtm + c0, v);
+            const uint4 c_a = lds128(aC + 2u * (uint32_t)c0), c_b = lds128(aC + 2u * (uint32_t)c0 + 16);
+            const uint32_t cw[8] = {c_a.x, c_a.y, c_a.z, c_a.w, c_b.x, c_b.y, c_b.z, c_b.w};
+            uint32_t o[8];
+            tmem_ld16_wait(v);
+            ep1_chunk<16>(v, cw, o);
+            const uint32_t a_dst = a_col + (uint32_t)(c0 >> 3) * A2_SBO;
+            sts128(a_dst, o[0], o[1], o[2], o[3]);
+            sts128(a_dst + A2_SBO, o[4], o[5], o[6], o[7]);
+          }
+          if (DBG && dbg_on && ntile_dbg == 1) p.dbg[256 + 8] = clock64();
           // rows 128..143: row 128 = C_p (multiplies the b2 column of W2aug), rows 129..143 = 0
           for (int item = t; item < (npad >> 3) * 16; item += PT) {
             const int ec = item >> 4, kr = item & 15;
@@ -535,9 +556,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_kernel(const __gr
         tc::tc_fence_before();
         tc::fence_proxy_async();
         // operands of epilogue 2 that live in global memory: issued now, needed after the second MMA
-        float xr[16], xjr[8], ojr[8];
-#pragma unroll
-        for (int il = 0; il < 16; ++il) xr[il] = (il < m) ? __ldg(p.x + goff + (a0 + il) * F) : 0.0f;
+        float xjr[8], ojr[8];
         if (!diag) {
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
@@ -585,15 +604,9 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_kernel(const __gr
         if (DBG) ++ntile_dbg;
       }
       // ---- row block finished: its own rows ----
-      if (bi == 0) {
 #pragma unroll
-        for (int il = 0; il < 16; ++il)
-          if (il < m) p.out[goff + (a0 + il) * F] = ar[il];
-      } else {
-#pragma unroll
-        for (int il = 0; il < 16; ++il)
-          if (il < m) p.out[goff + (a0 + il) * F] += ar[il];
-      }
+      for (int il = 0; il < 16; ++il)
+        if (il < m) p.out[goff + (a0 + il) * F] = ar[il];
     }
   }
 
@@ -671,9 +684,11 @@ __global__ void __launch_bounds__(NMAX) adjacency_kernel(const int32_t* __restri
 
 using namespace cmp;
 
-static int g_dense_stagger_ns = 600, g_dense_active_pipes = NP;
+static int g_dense_stagger_ns = 1500, g_dense_active_pipes = NP;
 extern "C" void cmp_debug_set_dense_stagger(int ns) { g_dense_stagger_ns = ns; }
 extern "C" void cmp_debug_set_dense_pipes(int n) { g_dense_active_pipes = n; }
+static int g_dense_dbg_mode = 0;
+extern "C" void cmp_debug_set_dense_mode(int m) { g_dense_dbg_mode = m; }
 static long long* g_dense_dbg = nullptr;
 extern "C" void cmp_debug_set_dense_timestamps(void* buf) { g_dense_dbg = reinterpret_cast<long long*>(buf); }
 
@@ -791,6 +806,7 @@ extern "C" int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int3
   }
   p.stagger_ns = g_dense_stagger_ns;
   p.active_pipes = g_dense_active_pipes;
+  p.dbg_mode = g_dense_dbg_mode;
   p.pi_over_cutoff = kPi / cutoff;
   p.Ng = num_gaussians;
   p.G = (int)G;

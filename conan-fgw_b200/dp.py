@@ -116,7 +116,8 @@ class RegressionStep:
     def _fwd_bwd(self, z, pos, batch, targets, num_graphs):
         self.flat.zero_grad()
         # weights only change in adam(): every tensor-core weight image of this step is packed up front, grouped
-        with ops.prepacked_weights([self.backbone, self.head]):
+        hint = getattr(self.backbone, "max_atoms_hint", None)
+        with ops.prepacked_weights([self.backbone, self.head], dense_only=hint is not None and hint <= 128):
             loss = self.loss(z, pos, batch, targets, num_graphs)
             # parameter gradients are None here and every parameter is used once: the node-linear weight gradients
             # can be queued during backward and issued as ONE grouped launch at its end

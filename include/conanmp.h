@@ -470,10 +470,13 @@ void cmp_debug_set_fwd_timestamps(void* buf);
 void cmp_debug_set_pair_timestamps(void* buf);
 /* Same for cmp_cfconv_dense_fwd: 7 timestamps + the tile width per executed tile of pipeline 0 (first 32), 256 int64. */
 void cmp_debug_set_dense_timestamps(void* buf);
-/* Tuning knob: start-up delay (ns) between the four pipelines of a cmp_cfconv_dense_fwd CTA (default 600). */
+/* Tuning knob: start-up delay (ns) between the four pipelines of a cmp_cfconv_dense_fwd CTA (default 1500). */
 void cmp_debug_set_dense_stagger(int ns);
 /* Debug knob: only the first n pipelines of every cmp_cfconv_dense_fwd CTA take work (default 4). */
 void cmp_debug_set_dense_pipes(int n);
+/* Debug knob of the timestamped build of cmp_cfconv_dense_fwd: bit 0 = skip the a' stores, bit 1 = skip the cutoff loads,
+ * bit 2 = skip the TMEM loads of epilogue 1 (results are then meaningless; for phase timing only). */
+void cmp_debug_set_dense_mode(int mode);
 /* Same for cmp_cfconv_fused_bwd_weights: 12 timestamps per tile (first 20 tiles), 240 int64. */
 void cmp_debug_set_bwd_timestamps(void* buf);
 
