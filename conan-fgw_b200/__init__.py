@@ -13,15 +13,16 @@ from .build import build_library, library_is_built  # noqa: F401
 from .graph import NeighborList, build_neighbor_list, radius_graph  # noqa: F401
 from .nn import (CFConv, GaussianSmearing, InteractionBlock, Linear, RadiusInteractionGraph,  # noqa: F401
                  SchNet, ShiftedSoftplus, SumAggregation)
-from .schnet_no_sum import SchNetNoSum  # noqa: F401
+from .schnet_no_sum import SchNetNoSum, SchNetWithMultipleReturns  # noqa: F401
 from . import visnet  # noqa: F401
 from .visnet import ViSNet, ViS_MP, ViSNetBlock, TorchGeometricViSNet  # noqa: F401
 from . import synthetic  # noqa: F401
 from . import aggregation  # noqa: F401
+from . import dp, utils  # noqa: F401  (loaded here so that the import alias covers them)
 from .aggregation import ConformerAggregationHead, MeanAggregation, create_aggregation_index  # noqa: F401
 
 __all__ = [
     "radius_graph", "build_neighbor_list", "NeighborList", "RadiusInteractionGraph", "GaussianSmearing",
-    "ShiftedSoftplus", "CFConv", "InteractionBlock", "SchNet", "SchNetNoSum", "Linear", "SumAggregation",
+    "ShiftedSoftplus", "CFConv", "InteractionBlock", "SchNet", "SchNetNoSum", "SchNetWithMultipleReturns", "Linear", "SumAggregation",
     "build_library", "library_is_built", "synthetic", "visnet", "ViSNet", "ViS_MP", "ViSNetBlock", "TorchGeometricViSNet",
 ]

@@ -29,6 +29,7 @@ SIGNATURES = {
     "cmp_radius_csr_workspace": (S, [L, L]),
     "cmp_radius_csr": (I, [P, P, L, L, D, I, I, L, P, P, P, P, P, P, P, P, P, S, P, P]),
     "cmp_csr_to_edge_index": (I, [P, P, L, L, P, P]),
+    "cmp_check_edge_count": (I, [P, L, L, P, P]),
     "cmp_gemm_workspace": (S, [L, L, L]),
     "cmp_gemm_f32": (I, [I, I, L, L, L, P, L, P, L, P, L, P, I, P, L, P, S, P]),
     "cmp_colsum_workspace": (S, [L, L]),

@@ -477,6 +477,11 @@ __global__ void set_i32_kernel(int32_t* p, int64_t n, int32_t v) {
   if (i < n) p[i] = v;
 }
 
+// the caller sized its [E, *] tensors by a promised edge count: report a geometry that breaks the promise
+__global__ void check_edge_count_kernel(const int32_t* __restrict__ rowptr, int64_t N, int64_t expected, int* status) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && (int64_t)rowptr[N] != expected) atomicOr(status, CMP_STATUS_EDGE_OVERFLOW);
+}
+
 }  // namespace
 }  // namespace cmp
 
@@ -660,5 +665,14 @@ extern "C" int cmp_gather_f32(const float* src, const int32_t* idx, const int32_
   if (blocks > 4096) blocks = 4096;
   gather_f32_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, idx, count_ptr, dst);
   CMP_LAUNCH_CHECK("cmp_gather_f32");
+  return CMP_OK;
+}
+
+extern "C" int cmp_check_edge_count(const int32_t* rowptr, int64_t N, int64_t expected_edges, int* status,
+                                    cmp_stream_t stream) {
+  CMP_REQUIRE(N >= 0 && expected_edges >= 0, CMP_EINVAL, "cmp_check_edge_count: negative size");
+  CMP_REQUIRE(rowptr && status, CMP_EINVAL, "cmp_check_edge_count: null pointer");
+  check_edge_count_kernel<<<1, 32, 0, as_stream(stream)>>>(rowptr, N, expected_edges, status);
+  CMP_LAUNCH_CHECK("cmp_check_edge_count");
   return CMP_OK;
 }

@@ -121,10 +121,17 @@ class RegressionStep:
             loss = self.loss(z, pos, batch, targets, num_graphs)
             # parameter gradients are None here and every parameter is used once: the node-linear weight gradients
             # can be queued during backward and issued as ONE grouped launch at its end
-            with ops.deferred_weight_grads():
+            with ops.deferred_weight_grads(self.flat.params):
                 loss.backward()
         self.flat.collect_grads()
         return loss.detach()
+
+    def check(self):
+        """Raise for device-side input errors reported since the last call (the captured / sync-free step never reads
+        the status word itself).  Call it where the host synchronises anyway, e.g. next to ``loss.item()``."""
+        chk = getattr(self.backbone, "check_status", None)
+        if chk is not None:
+            chk()
 
     def capture(self, z, pos, batch, targets, num_graphs):
         """Capture zero-grad + radius graph + forward + loss + backward into ONE CUDA graph (every entry point of

@@ -22,20 +22,42 @@ import torch
 from . import _lib
 
 
+def raise_for_status(status: torch.Tensor, reset: bool = False):
+    """Read a device-side status word (one device -> host copy: synchronises) and raise for the errors it reports.
+    The lazily built tile / pair lists and the fused kernels report through the same word as the radius search, so it is
+    read every time this is called; sync-free callers (CUDA-graph steps) call it where they synchronise anyway."""
+    s = int(status.item())
+    if reset and s:
+        status.zero_()
+    if s & _lib.STATUS_UNSORTED_BATCH:
+        raise ValueError("radius_graph: 'batch' must be sorted non-decreasing with ids in [0, num_graphs)")
+    if s & _lib.STATUS_EDGE_OVERFLOW:
+        raise RuntimeError("radius_graph: neighbour / tile capacity overflow, an edge count different from the promised "
+                           "num_edges, or a conformer above the promised max_atoms bound")
+    if s & _lib.STATUS_BAD_ATOMIC_NUMBER:
+        raise ValueError("atomic numbers must lie in [0, 100)")
+
+
 class NeighborList:
     """Device-resident CSR neighbour list of a batch of conformers."""
 
-    def __init__(self, N, G, cap_E, device):
+    def __init__(self, N, G, cap_E, device, status=None, zero_fill=False):
         i32 = dict(dtype=torch.int32, device=device)
+        self._alloc = torch.zeros if zero_fill else torch.empty
         self.N, self.G, self.cap_E = int(N), int(G), int(cap_E)
         self.seg_ptr = torch.empty(G + 1, **i32)
         self.conf_edge_ptr = torch.empty(G + 1, **i32)
         self.rowptr = torch.empty(N + 1, **i32)
-        self.col = torch.empty(max(cap_E, 1), **i32)
-        self.dist = torch.empty(max(cap_E, 1), dtype=torch.float32, device=device)
+        # zero_fill: with a promised edge count (num_edges) kernels run over the promised number of rows; if the real
+        # geometry has fewer edges the surplus rows must still hold valid atom indices (the mismatch itself is reported
+        # through the status word, never as an out-of-bounds access)
+        self.col = self._alloc(max(cap_E, 1), **i32)
+        self.dist = self._alloc(max(cap_E, 1), dtype=torch.float32, device=device)
         self.evec = None
         self.rowptr_t = self.col_t = self.eid_t = None
-        self.status = torch.zeros(1, **i32)
+        # device-side error word (CMP_STATUS_* bits); a model passes its own persistent word so that a sync-free training
+        # step can read it where it synchronises anyway (nn.SchNet.check_status / dp.RegressionStep.check)
+        self.status = status if status is not None else torch.zeros(1, **i32)
         self.cutoff = None
         self.loop = False
         self.pos = None              # float32 [N, 3] the list was built from (radius-built lists only)
@@ -54,19 +76,7 @@ class NeighborList:
         return self._E
 
     def check(self):
-        """Raise for device-detected input errors.  Reads the status word (one device -> host copy, synchronises) every
-        time it is called: the lazily built tile / pair lists and the fused kernels report through the same word, so a
-        single early read would miss them.  Sync-free callers (CUDA-graph steps) call this where they synchronise anyway
-        (``dp.RegressionStep.check``)."""
-        s = int(self.status.item())
-        self._checked = True
-        if s & _lib.STATUS_UNSORTED_BATCH:
-            raise ValueError("radius_graph: 'batch' must be sorted non-decreasing with ids in [0, num_graphs)")
-        if s & _lib.STATUS_EDGE_OVERFLOW:
-            raise RuntimeError("radius_graph: neighbour / tile capacity overflow, or a conformer above the promised "
-                               "max_atoms bound")
-        if s & _lib.STATUS_BAD_ATOMIC_NUMBER:
-            raise ValueError("atomic numbers must lie in [0, 100)")
+        raise_for_status(self.status)
 
     def edge_index(self) -> torch.Tensor:
         if self._edge_index is None:
@@ -130,7 +140,7 @@ class NeighborList:
     def erow(self) -> torch.Tensor:
         """Target atom of every edge (``edge_index[1]`` as int32), built once."""
         if getattr(self, "_erow", None) is None:
-            erow = torch.empty_like(self.col)
+            erow = self._alloc(self.col.shape, dtype=self.col.dtype, device=self.col.device)
             _lib.call("cmp_csr_expand_rows", _lib.ptr(self.rowptr), self.N, _lib.ptr(erow))
             self._erow = erow
         return self._erow
@@ -201,7 +211,7 @@ def num_graphs_of(batch: torch.Tensor, num_graphs: Optional[int] = None) -> int:
 def build_neighbor_list(pos: torch.Tensor, batch: Optional[torch.Tensor], r: float, max_num_neighbors: int = 32,
                         loop: bool = False, num_graphs: Optional[int] = None, want_evec: bool = False,
                         want_transpose: bool = True, num_edges: Optional[int] = None,
-                        max_atoms: Optional[int] = None) -> NeighborList:
+                        max_atoms: Optional[int] = None, status: Optional[torch.Tensor] = None) -> NeighborList:
     """``num_edges``: the caller vouches for the edge count (e.g. a CUDA-graph replay of the same geometry); it
     removes the one host synchronisation that code sizing tensors by E otherwise needs."""
     if not pos.is_cuda:
@@ -219,18 +229,18 @@ def build_neighbor_list(pos: torch.Tensor, batch: Optional[torch.Tensor], r: flo
     batch = batch.to(torch.int64).contiguous()
     G = num_graphs_of(batch, num_graphs)
     cap = max_num_neighbors if loop else max_num_neighbors + 1
-    nl = NeighborList(N, G, N * cap, dev)
+    nl = NeighborList(N, G, N * cap, dev, status=status, zero_fill=num_edges is not None)
     nl.cutoff, nl.loop = float(r), bool(loop)
     nl.pos = pos
     nl.max_atoms = None if max_atoms is None else int(max_atoms)
     nl.sym_atoms = int(cap)      # conformers of at most this many atoms cannot have been truncated: symmetric lists
     i32 = dict(dtype=torch.int32, device=dev)
     if want_evec:
-        nl.evec = torch.empty(max(nl.cap_E, 1), 3, dtype=torch.float32, device=dev)
+        nl.evec = nl._alloc(max(nl.cap_E, 1), 3, dtype=torch.float32, device=dev)
     if want_transpose:
         nl.rowptr_t = torch.empty(N + 1, **i32)
-        nl.col_t = torch.empty(max(nl.cap_E, 1), **i32)
-        nl.eid_t = torch.empty(max(nl.cap_E, 1), **i32)
+        nl.col_t = nl._alloc(max(nl.cap_E, 1), **i32)
+        nl.eid_t = nl._alloc(max(nl.cap_E, 1), **i32)
     _lib.call("cmp_batch_to_segments", _lib.ptr(batch), N, G, _lib.ptr(nl.seg_ptr), _lib.ptr(nl.status))
     ws_bytes = _lib.size_query("cmp_radius_csr_workspace", N, G)
     ws = _lib.workspace(ws_bytes, dev)
@@ -239,7 +249,9 @@ def build_neighbor_list(pos: torch.Tensor, batch: Optional[torch.Tensor], r: flo
               _lib.ptr(nl.evec), _lib.ptr(nl.rowptr_t), _lib.ptr(nl.col_t), _lib.ptr(nl.eid_t),
               _lib.ptr(nl.conf_edge_ptr), _lib.ptr(ws), ws.numel(), _lib.ptr(nl.status))
     if num_edges is not None:
-        nl._E = int(num_edges)      # trusted for sizing; the status word still reports device-side errors via check()
+        # trusted for sizing (no host sync); a geometry whose edge count differs sets CMP_STATUS_EDGE_OVERFLOW
+        nl._E = int(num_edges)
+        _lib.call("cmp_check_edge_count", _lib.ptr(nl.rowptr), N, int(num_edges), _lib.ptr(nl.status))
     return nl
 
 

@@ -66,9 +66,9 @@ class RadiusInteractionGraph(nn.Module):
         self.cutoff = cutoff
         self.max_num_neighbors = max_num_neighbors
 
-    def neighbor_list(self, pos, batch, num_graphs=None, max_atoms=None) -> NeighborList:
+    def neighbor_list(self, pos, batch, num_graphs=None, max_atoms=None, status=None) -> NeighborList:
         return build_neighbor_list(pos, batch, self.cutoff, self.max_num_neighbors, loop=False,
-                                   num_graphs=num_graphs, max_atoms=max_atoms)
+                                   num_graphs=num_graphs, max_atoms=max_atoms, status=status)
 
     def forward(self, pos, batch):
         nl = self.neighbor_list(pos, batch)
@@ -222,7 +222,16 @@ class SchNet(nn.Module):
         # caller's bound on the atoms of any conformer it will feed (None: unknown).  With a bound <= 128 the fused
         # path launches the dense-block kernel only; a conformer that breaks the promise raises through the status word.
         self.max_atoms_hint = None
+        # persistent device-side error word shared by every neighbour list this model builds (not part of the state_dict)
+        self.register_buffer("status", torch.zeros(1, dtype=torch.int32), persistent=False)
         self.reset_parameters()
+
+    def check_status(self):
+        """Raise for device-detected input errors of the forward passes since the last call (unsorted batch, atomic
+        number out of range, capacity overflow, broken ``max_atoms_hint`` promise).  One 4-byte device -> host read."""
+        from .graph import raise_for_status
+
+        raise_for_status(self.status, reset=True)
 
     def set_precision(self, precision: str):
         """"fp32": exact-fp32 kernels (1e-5 parity mode).  "bf16": fused tcgen05 CFConv with a bf16
@@ -254,7 +263,7 @@ class SchNet(nn.Module):
         """Embedding + T interaction blocks.  Returns ``(h[N,H], graph)``."""
         ig = self.interaction_graph
         if isinstance(ig, RadiusInteractionGraph):
-            graph = ig.neighbor_list(pos, batch, num_graphs, max_atoms=self.max_atoms_hint)
+            graph = ig.neighbor_list(pos, batch, num_graphs, max_atoms=self.max_atoms_hint, status=self.status)
             h = self.embed(z, graph.status)
             if all(blk.conv.fused_ok(graph, self.distance_expansion) for blk in self.interactions):
                 # fused path: no edge_index / rbf[E, Ng] / filter[E, F] is ever materialised, no host sync

@@ -7,6 +7,7 @@ the current stream.  Nothing here falls back to a PyTorch implementation.
 from __future__ import annotations
 
 import ctypes
+import threading
 
 import torch
 from torch.autograd import Function
@@ -120,26 +121,40 @@ def node_tc_supported(K, Nout) -> bool:
     return bool(_lib.lib().cmp_node_gemm_tc_supported(int(K), int(Nout))) and bool(_lib.lib().cmp_device_is_sm100())
 
 
-class prepacked_weights:
-    """Pack every weight image the enclosed forward + backward will need in THREE grouped launches (node linears,
-    filter MLPs forward, filter MLPs backward) instead of one or two small launches per layer.  Weights only change
-    in the optimizer step, so a training step opens this context right after it (``dp.RegressionStep``); the cache is
-    dropped when the context closes, so a later weight update can never meet a stale image."""
+# Open contexts (weight-image caches, deferred weight-gradient queues).  Process-wide on purpose: autograd runs
+# ``Function.backward`` on its own device thread, so a thread-local registry would be invisible exactly where the queue is
+# filled.  Isolation between models comes from ownership instead: weight images are keyed by the weight's storage
+# address, and a deferred-gradient context only accepts the parameters it was opened for.
+_registry = {"packs": [], "dw": []}
+_registry_lock = threading.Lock()
 
-    cache = None       # {weight.data_ptr(): images} while a context is open
+
+def _stack(name):
+    return _registry[name]
+
+
+class prepacked_weights:
+    """Pack every weight image the enclosed forward + backward will need in a few grouped launches (node linears,
+    filter MLPs forward / dense / backward) instead of one or two small launches per layer.  Weights only change in
+    the optimizer step, so a training step opens this context right after it (``dp.RegressionStep``); the images are
+    dropped when the context closes, so a later weight update can never meet a stale image.  Contexts nest (inner ones
+    are searched first); images are keyed by the weight's storage address, so two models never collide."""
 
     def __init__(self, modules, dense_only=False):
         self.modules = list(modules)
         self.dense_only = bool(dense_only)
+        self.cache = None
 
     def __enter__(self):
-        if prepacked_weights.cache is not None:
-            raise RuntimeError("prepacked_weights does not nest")
-        prepacked_weights.cache = _prepack(self.modules, self.dense_only)
+        self.cache = _prepack(self.modules, self.dense_only)
+        with _registry_lock:
+            _stack("packs").append(self)
         return self
 
     def __exit__(self, exc_type, exc, tb):
-        prepacked_weights.cache = None
+        with _registry_lock:
+            _stack("packs").remove(self)
+        self.cache = None
         return False
 
 
@@ -207,8 +222,14 @@ def _prepack(modules, dense_only=False):
 
 
 def _cached_images(weight):
-    c = prepacked_weights.cache
-    return None if c is None else c.get(weight.data_ptr())
+    key = weight.data_ptr()
+    with _registry_lock:
+        open_ctx = list(_stack("packs"))
+    for ctx in reversed(open_ctx):
+        hit = ctx.cache.get(key) if ctx.cache is not None else None
+        if hit is not None:
+            return hit
+    return None
 
 
 def _pack_node_weight(weight, transpose):
@@ -273,13 +294,14 @@ def _tc_dw_blocked(dy2, saved_y, x2, want_db, param=None):
     dw = torch.empty(Nout, K, dtype=torch.float32, device=dev)
     db = torch.empty(Nout, dtype=torch.float32, device=dev) if want_db else None
     f4 = 4
-    if deferred_weight_grads.active is not None:
+    dwq = _dw_queue(param)
+    if dwq is not None:
         # queued for the grouped launch: every <=128 x <=128 block writes straight into dw (leading dimension K)
         for n0 in range(0, Nout, 128):
             nb = min(128, Nout - n0)
             for k0 in range(0, K, 128):
                 kb = min(128, K - k0)
-                deferred_weight_grads.active.append(dict(
+                dwq.append(dict(
                     dY=dy2.data_ptr() + n0 * f4, lddy=Nout,
                     saved_y=saved_y.data_ptr() + n0 * f4 if saved_y is not None else None,
                     ldys=Nout if saved_y is not None else 0, X=x2.data_ptr() + k0 * f4, ldx=K, M=M, K=kb, Nout=nb,
@@ -338,21 +360,38 @@ class deferred_weight_grads:
     ``backward()``: they return (still unwritten) gradient tensors and queue the problem; leaving the context issues
     ALL of them as one grouped launch (``cmp_node_gemm_dw_grouped``) that fills the SMs instead of 20 small launches
     of ~17 us each.  Only valid when nothing reads or accumulates into the parameter gradients before the context
-    exits, i.e. every parameter is used once and ``p.grad`` was ``None`` (``dp.RegressionStep`` guarantees both)."""
+    exits, i.e. every parameter is used once, has no hooks and ``p.grad`` was ``None`` (``dp.RegressionStep``
+    guarantees all three; the flush verifies that autograd adopted every weight AND bias gradient tensor).
+    ``params``: the parameters this context owns (None = every parameter).  A Linear whose weight belongs to no open
+    context launches its gradient GEMM immediately, so two models stepping at the same time never share a queue."""
 
-    active = None      # the queue while a context is open
+    def __init__(self, params=None):
+        self.queue = None
+        self.owned = None if params is None else {p.data_ptr() for p in params}
 
     def __enter__(self):
-        if deferred_weight_grads.active is not None:
-            raise RuntimeError("deferred_weight_grads does not nest")
-        deferred_weight_grads.active = []
+        self.queue = []
+        with _registry_lock:
+            _stack("dw").append(self)
         return self
 
     def __exit__(self, exc_type, exc, tb):
-        queue, deferred_weight_grads.active = deferred_weight_grads.active, None
+        with _registry_lock:
+            _stack("dw").remove(self)
+        queue, self.queue = self.queue, None
         if exc_type is None:
             _flush_deferred_dw(queue)
         return False
+
+
+def _dw_queue(weight=None):
+    """The queue of the innermost open context that owns ``weight`` (called from autograd's backward thread)."""
+    key = None if weight is None else weight.data_ptr()
+    with _registry_lock:
+        for ctx in reversed(_stack("dw")):
+            if ctx.queue is not None and (ctx.owned is None or key is None or key in ctx.owned):
+                return ctx.queue
+    return None
 
 
 def _flush_deferred_dw(queue):
@@ -374,12 +413,13 @@ def _flush_deferred_dw(queue):
     # autograd must have ADOPTED the tensors that were returned unwritten (it does when .grad was None and nothing else
     # references them); had it copied or accumulated them instead, the values written above would be lost: fail loudly
     for q in queue:
-        w = q.get("param")
-        if w is not None and w.is_leaf and q.get("first", True):
-            if w.grad is None or w.grad.data_ptr() != q["dW_base"]:
-                raise _lib.ConanMPError(
-                    "deferred_weight_grads: a parameter gradient was copied or accumulated before the grouped launch "
-                    "wrote it (use it only with p.grad = None and parameters that are used once)")
+        for key, base in (("param", "dW_base"), ("bias_param", "db_base")):
+            w = q.get(key)
+            if w is not None and w.is_leaf and q.get("first", True):
+                if w.grad is None or w.grad.data_ptr() != q[base]:
+                    raise _lib.ConanMPError(
+                        "deferred_weight_grads: a parameter gradient was copied or accumulated before the grouped launch "
+                        "wrote it (use it only with p.grad = None, no hooks, and parameters that are used once)")
 
 
 class _LinearTCFn(Function):
@@ -405,6 +445,7 @@ class _LinearTCFn(Function):
         y = _node_gemm(x2, w_img, K, Nout, _f32c(bias) if bias is not None else None, act, res2)
         ctx.act, ctx.lead = act, lead
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        ctx.bias_ref = bias          # the Parameter itself: the deferred-gradient flush checks that autograd adopted db
         ctx.save_for_backward(x2, weight, y if act != ACT_NONE else None)
         return y.reshape(*lead, Nout)
 
@@ -422,14 +463,17 @@ class _LinearTCFn(Function):
             M = x2.shape[0]
             dw = torch.empty(Nout, K, dtype=torch.float32, device=dy2.device)
             db = torch.empty(Nout, dtype=torch.float32, device=dy2.device) if ctx.has_bias else None
-            if deferred_weight_grads.active is not None:
+            dwq = _dw_queue(weight)
+            if dwq is not None:
                 # queued: raw pointers only for the outputs (autograd must stay the sole owner of dw / db, or it
                 # would clone them - unwritten - instead of adopting them as .grad); inputs are kept alive here
-                deferred_weight_grads.active.append(dict(
+                dwq.append(dict(
                     dY=dy2.data_ptr(), lddy=dy2.stride(0), saved_y=y.data_ptr() if y is not None else None,
                     ldys=y.stride(0) if y is not None else 0, X=x2.data_ptr(), ldx=x2.stride(0), M=M, K=K, Nout=Nout,
                     dW=dw.data_ptr(), lddw=K, db=db.data_ptr() if db is not None else None, keep=(dy2, y, x2),
-                    param=weight if ctx.needs_input_grad[1] else None, dW_base=dw.data_ptr()))
+                    param=weight if ctx.needs_input_grad[1] else None, dW_base=dw.data_ptr(),
+                    bias_param=ctx.bias_ref if (db is not None and ctx.needs_input_grad[2]) else None,
+                    db_base=db.data_ptr() if db is not None else None))
             else:
                 ws = _lib.workspace(_lib.size_query("cmp_node_gemm_dw_workspace", K), dy2.device)
                 call("cmp_node_gemm_dw", ptr(dy2), dy2.stride(0), ptr(y), y.stride(0) if y is not None else 0, ptr(x2),
@@ -780,14 +824,21 @@ def conformers_mean(x, num_conformers: int):
     return segment_sum(x, seg, G // K) * (1.0 / K)
 
 
-def segments_from_batch(batch, num_graphs=None):
-    from .graph import num_graphs_of
+def segments_from_batch(batch, num_graphs=None, status=None):
+    """Segment pointers of a SORTED index vector.  An unsorted index cannot be served by the segment kernels (PyG's
+    scatter would accept it): it is reported - through ``status`` when the caller supplies its own word (sync-free
+    paths read it later), otherwise by one device -> host read here."""
+    from .graph import num_graphs_of, raise_for_status
 
     batch = batch.to(torch.int64).contiguous()
     G = num_graphs_of(batch, num_graphs)
     seg = torch.empty(G + 1, dtype=torch.int32, device=batch.device)
-    status = torch.zeros(1, dtype=torch.int32, device=batch.device)
+    own = status is None
+    if own:
+        status = torch.zeros(1, dtype=torch.int32, device=batch.device)
     call("cmp_batch_to_segments", ptr(batch), batch.numel(), G, ptr(seg), ptr(status))
+    if own and not torch.cuda.is_current_stream_capturing():
+        raise_for_status(status)
     return seg, G
 
 

@@ -338,9 +338,9 @@ class Distance(nn.Module):
         super().__init__()
         self.cutoff, self.max_num_neighbors, self.add_self_loops = cutoff, max_num_neighbors, add_self_loops
 
-    def neighbor_list(self, pos, batch, num_graphs=None, num_edges=None) -> NeighborList:
+    def neighbor_list(self, pos, batch, num_graphs=None, num_edges=None, status=None) -> NeighborList:
         return build_neighbor_list(pos, batch, self.cutoff, self.max_num_neighbors, loop=self.add_self_loops,
-                                   num_graphs=num_graphs, want_evec=True, num_edges=num_edges)
+                                   num_graphs=num_graphs, want_evec=True, num_edges=num_edges, status=status)
 
     def forward(self, pos, batch):
         nl = self.neighbor_list(pos, batch)
@@ -490,6 +490,8 @@ class ViSNetBlock(nn.Module):
         self.vis_mp_layers.append(ViS_MP(last_layer=True, **kw))
         self.out_norm = nn.LayerNorm(hidden_channels)
         self.vec_out_norm = VecLayerNorm(hidden_channels, trainable=trainable_vecnorm, norm_type=vecnorm_type)
+        # persistent device-side error word of every neighbour list this block builds (not part of the state_dict)
+        self.register_buffer("status", torch.zeros(1, dtype=torch.int32), persistent=False)
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -503,7 +505,7 @@ class ViSNetBlock(nn.Module):
         self.vec_out_norm.reset_parameters()
 
     def forward(self, z, pos, batch, num_graphs=None, num_edges=None):
-        nl = self.distance.neighbor_list(pos, batch, num_graphs, num_edges)
+        nl = self.distance.neighbor_list(pos, batch, num_graphs, num_edges, status=self.status)
         x = self.embedding(z, nl.status)
         edge_index, edge_weight = nl.edge_index(), nl.edge_weight()
         if self.trainable_rbf:
@@ -642,6 +644,13 @@ class TorchGeometricViSNet(nn.Module):
             if isinstance(m, Linear):
                 m.tc = precision == "bf16"
         return self
+
+    def check_status(self):
+        """Raise for device-detected input errors of the forward passes since the last call (unsorted batch, atomic
+        number out of range, capacity overflow, an edge count different from a promised ``num_edges``)."""
+        from .graph import raise_for_status
+
+        raise_for_status(self.representation_model.status, reset=True)
 
     def _per_atom(self, z, pos, batch, bary=False, num_graphs=None, num_edges=None):
         x, v = self.representation_model(z, pos, batch, num_graphs, num_edges)

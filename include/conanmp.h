@@ -100,6 +100,11 @@ int cmp_radius_csr(const float* pos, const int32_t* seg_ptr, int64_t N, int64_t 
                    int32_t* conf_edge_ptr, void* workspace, size_t workspace_bytes, int* status,
                    cmp_stream_t stream);
 
+/* Sync-free callers size their [E, *] tensors by an edge count they vouch for (a CUDA-graph replay of the same
+ * geometry): sets CMP_STATUS_EDGE_OVERFLOW in *status when rowptr[N] differs from expected_edges. */
+int cmp_check_edge_count(const int32_t* rowptr, int64_t N, int64_t expected_edges, int* status,
+                         cmp_stream_t stream);
+
 /* CSR -> PyG edge_index int64[2, E] (row 0 = source j, row 1 = target i). */
 int cmp_csr_to_edge_index(const int32_t* rowptr, const int32_t* col, int64_t N, int64_t E,
                           int64_t* edge_index, cmp_stream_t stream);

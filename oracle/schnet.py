@@ -192,8 +192,11 @@ class SchNet(nn.Module):
         return out
 
 
+COVALENT_BONDS_ATTRS_DIM = 3      # schnet_no_sum.py:23
+
+
 class SchNetNoSum(SchNet):
-    """ConAN's backbone, ``schnet_no_sum.py:90-232`` (``use_covalent=False`` branch)."""
+    """ConAN's backbone, ``schnet_no_sum.py:90-232`` (both the plain and the ``use_covalent`` trunk)."""
 
     def __init__(self, device=None, hidden_channels=128, num_filters=128, num_interactions=6,
                  num_gaussians=50, cutoff=10.0, interaction_graph=None, max_num_neighbors=32,
@@ -201,7 +204,6 @@ class SchNetNoSum(SchNet):
                  use_covalent=False, use_readout=True):
         super().__init__(hidden_channels, num_filters, num_interactions, num_gaussians, cutoff,
                          interaction_graph, max_num_neighbors, readout, dipole, mean, std, atomref)
-        assert not use_covalent, "covalent trunk is unreachable from the ConAN CLI (SURVEY.md 2.1 #1)"
         self.device = device
         self.use_readout = use_readout
         self.use_covalent = use_covalent
@@ -209,19 +211,72 @@ class SchNetNoSum(SchNet):
         self.lin1_bary = nn.Linear(hidden_channels, half)
         self.lin2_bary = nn.Linear(half, half)
         self.lin2 = nn.Linear(half, half)
+        if use_covalent:                                   # schnet_no_sum.py:131-142
+            self.interactions_cov = nn.ModuleList(
+                InteractionBlock(hidden_channels, COVALENT_BONDS_ATTRS_DIM, num_filters, cutoff)
+                for _ in range(num_interactions))
+            self.lin1 = nn.Linear(hidden_channels * 2, half)
+            self.lin1_bary = nn.Linear(hidden_channels * 2, half)
+
+    def full_trunk(self, z, pos, batch, data_batch):
+        h = self.trunk(z, pos, batch)
+        if self.use_covalent:                              # schnet_no_sum.py:166-175
+            h_cov = self.embedding(z)
+            ei = data_batch.edge_index
+            ew = torch.ones(ei.shape[1], dtype=torch.float32)
+            ea = data_batch.edge_attr.float()
+            for blk in self.interactions_cov:
+                h_cov = h_cov + blk(h_cov, ei, ew, ea)
+            h = torch.cat([h, h_cov], dim=1)
+        return h
 
     def forward(self, z, pos, batch=None, data_batch=None):
         batch = torch.zeros_like(z) if batch is None else batch
-        h = self.trunk(z, pos, batch)
+        h = self.full_trunk(z, pos, batch, data_batch)
         h = self.act(self.lin2(self.lin1(h)))          # ConAN head order: lin1 -> lin2 -> ssp
         return self.readout(h, batch, dim=0) if self.use_readout else h
 
     def forward_3d_bary(self, z, pos, batch=None, data_batch=None):
         batch = torch.zeros_like(z) if batch is None else batch
-        hs = self.trunk(z, pos, batch)
+        hs = self.full_trunk(z, pos, batch, data_batch)
         h = self.act(self.lin2(self.lin1(hs)))
         hb = self.act(self.lin2_bary(self.lin1_bary(hs)))
         return h, hb
+
+
+class SchNetWithMultipleReturns(SchNet):
+    """``schnet_no_sum.py:357-450``: per-atom ``ssp(lin1(h))`` plus the radius graph and its Gaussian expansion."""
+
+    def __init__(self, hidden_channels=128, num_filters=128, num_interactions=6, num_gaussians=50, cutoff=10.0,
+                 interaction_graph=None, max_num_neighbors=32, readout="add", dipole=False, mean=None, std=None,
+                 atomref=None, use_covalent=False, use_readout=True):
+        super().__init__(hidden_channels, num_filters, num_interactions, num_gaussians, cutoff,
+                         interaction_graph, max_num_neighbors, readout, dipole, mean, std, atomref)
+        self.use_readout = use_readout
+        self.use_covalent = use_covalent
+        if use_covalent:
+            self.interactions_cov = nn.ModuleList(
+                InteractionBlock(hidden_channels, COVALENT_BONDS_ATTRS_DIM, num_filters, cutoff)
+                for _ in range(num_interactions))
+            self.lin1 = nn.Linear(hidden_channels * 2, hidden_channels // 2)
+
+    def forward(self, z, pos, batch=None, data_batch=None, conformers_index=None):
+        batch = torch.zeros_like(z) if batch is None else batch
+        h = self.embedding(z)
+        edge_index, edge_weight = self.interaction_graph(pos, batch)
+        edge_attr = self.distance_expansion(edge_weight)
+        for blk in self.interactions:
+            h = h + blk(h, edge_index, edge_weight, edge_attr)
+        if self.use_covalent:
+            h_cov = self.embedding(z)
+            ei = data_batch.edge_index
+            ew = torch.ones(ei.shape[1], dtype=torch.float32)
+            ea = data_batch.edge_attr.float()
+            for blk in self.interactions_cov:
+                h_cov = h_cov + blk(h_cov, ei, ew, ea)
+            h = torch.cat([h, h_cov], dim=1)
+        h = self.act(self.lin1(h))
+        return h, edge_index, edge_attr
 
 
 def to_double(module: nn.Module) -> nn.Module:

@@ -50,3 +50,18 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_import_alias_shares_submodules():
+    """`conan_fgw_b200.<sub>` must be the very module objects the hyphen-named package uses (a second copy
+    of nn / dp under the alias name breaks isinstance checks such as the weight pre-packing's)."""
+    import sys
+
+    import conan_fgw_b200 as pkg
+    from conan_fgw_b200.dp import RegressionStep
+    from conan_fgw_b200.nn import Linear
+    from conan_fgw_b200.utils import to_dense_batch  # noqa: F401
+
+    assert sys.modules["conan_fgw_b200.nn"] is sys.modules["conan-fgw_b200.nn"]
+    assert sys.modules["conan_fgw_b200.dp"] is sys.modules["conan-fgw_b200.dp"]
+    assert Linear is pkg.Linear and RegressionStep is pkg.dp.RegressionStep

@@ -324,7 +324,17 @@ def test_deferred_grouped_weight_gradients_match_the_immediate_launches():
     with pytest.raises(cmp._lib.ConanMPError):
         with ops.deferred_weight_grads():
             out.backward()
-    assert ops.deferred_weight_grads.active is None
+    assert ops._dw_queue() is None
+    # a context only takes the parameters it owns: somebody else's Linear launches immediately
+    for p in params:
+        p.grad = None
+    out = c(b.z, b.pos, b.batch, num_graphs=b.num_graphs).pow(2).mean()
+    with ops.deferred_weight_grads([torch.nn.Parameter(torch.zeros(1, device=DEV))]) as ctx:
+        out.backward()
+        assert ctx.queue == []
+    for g, r in zip([p.grad for p in params], ref):
+        if r is not None:
+            assert rel_err(g, r) < 2e-6
 
 
 def test_training_step_with_grouped_packs_and_deferred_gradients_matches_plain_autograd():
@@ -354,7 +364,7 @@ def test_training_step_with_grouped_packs_and_deferred_gradients_matches_plain_a
     loss = step._fwd_bwd(b.z, b.pos, b.batch, targets, b.num_graphs)
     assert torch.equal(loss, loss_ref.detach())
     assert rel_err(step.flat.grad, g_ref) < 2e-6
-    assert ops.prepacked_weights.cache is None and ops.deferred_weight_grads.active is None
+    assert not ops._stack("packs") and ops._dw_queue() is None
 
     # two optimizer steps eagerly vs from the captured graph: same parameters afterwards
     eager, graphed = fresh(), fresh()

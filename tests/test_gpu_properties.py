@@ -105,3 +105,82 @@ def test_fused_mode_agrees_with_exact_mode_at_large_sizes(cfg, molecules, cutoff
         fused(b.z, b.pos, b.batch, num_graphs=b.num_graphs).pow(2).mean().backward()
         grads.append(torch.cat([p.grad.reshape(-1) for p in fused.parameters() if p.grad is not None]))
     assert torch.isfinite(grads[0]).all() and torch.equal(grads[0], grads[1])
+
+
+def test_status_word_is_read_on_the_sync_free_path():
+    """The fused (bf16) trunk never synchronises; device-side input errors accumulate in the model's persistent status
+    word and `check_status()` raises for them wherever the caller synchronises (silent garbage otherwise)."""
+    torch.manual_seed(0)
+    m = cmp.SchNetNoSum(None, num_interactions=1).to(DEV)
+    if cmp._lib.lib().cmp_device_is_sm100():
+        m.set_precision("bf16")
+    b = syn.make_batch(2, 2, 10, seed=1).to(DEV)
+    m(b.z, b.pos, b.batch, num_graphs=b.num_graphs)
+    m.check_status()                                            # clean input: nothing to report
+    bad = b.batch.flip(0).contiguous()
+    m(b.z, b.pos, bad, num_graphs=b.num_graphs)
+    with pytest.raises(ValueError):
+        m.check_status()
+    m.check_status()                                            # the word was reset by the failing read
+    z_bad = b.z.clone()
+    z_bad[3] = 100
+    m(z_bad, b.pos, b.batch, num_graphs=b.num_graphs)
+    with pytest.raises(ValueError):
+        m.check_status()
+    # a promised bound on the conformer size (it removes the fallback launches for conformers above the dense kernel's
+    # 128 atoms) that the data breaks
+    m.max_atoms_hint = 64
+    big = syn.make_batch(1, 1, 130, seed=2).to(DEV)
+    m(big.z, big.pos, big.batch, num_graphs=1)
+    if m.precision == "bf16":
+        with pytest.raises(RuntimeError):
+            m.check_status()
+
+
+def test_visnet_promised_edge_count_is_validated_on_device():
+    torch.manual_seed(0)
+    m = cmp.ViSNet(None, hidden_channels=32).to(DEV)
+    b = syn.make_batch(2, 2, 8, seed=2).to(DEV)
+    E = m.representation_model.distance.neighbor_list(b.pos, b.batch, b.num_graphs).E
+    m(b.z, b.pos, b.batch, num_graphs=b.num_graphs, num_edges=E)
+    m.check_status()
+    moved = b.pos.clone()
+    moved[0] += 50.0                                            # same shapes, different geometry: fewer edges
+    m(b.z, moved, b.batch, num_graphs=b.num_graphs, num_edges=E)
+    with pytest.raises(RuntimeError):
+        m.check_status()
+
+
+def test_unsorted_index_is_not_silently_mis_summed():
+    """SumAggregation over an unsorted index: PyG's scatter would give the right sums, the segment kernels cannot -
+    the call raises instead of returning wrong numbers."""
+    x = torch.randn(6, 4, device=DEV)
+    idx = torch.tensor([0, 1, 0, 1, 2, 2], device=DEV)
+    with pytest.raises(ValueError):
+        cmp.SumAggregation()(x, idx, dim=0)
+
+
+def test_fused_mode_gradients_at_the_bench_size():
+    """Every parameter gradient of the fused (f16 filter MLP) mode against the exact-fp32 GPU mode on the FULL cfg 2
+    batch (640 conformers, 449 K edges, T = 6): the weight gradients sum over all edges there, so a systematic rounding
+    bias would show up that the 8-molecule oracle comparison cannot see.  Stated tolerance: 5e-3 relative
+    (max|a-b| / max|b|) and 5e-3 per conformer row on the embeddings; 1e-2 per parameter on the gradients (measured
+    worst case 6.4e-3, the W2 gradient of block 4: the weight-gradient kernel still rounds g and x' to bf16)."""
+    if not cmp._lib.lib().cmp_device_is_sm100():
+        pytest.skip("tcgen05 kernels need an sm_100 device")
+    from conftest import row_rel_err
+
+    b = syn.make_config_batch("cfg2_lipo_train").to(DEV)
+    m = _model("fp32")
+    want = m(b.z, b.pos, b.batch, num_graphs=b.num_graphs)
+    want.pow(2).mean().backward()
+    ref = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.set_precision("bf16")
+    m.max_atoms_hint = 27
+    m.zero_grad()
+    got = m(b.z, b.pos, b.batch, num_graphs=b.num_graphs)
+    got.pow(2).mean().backward()
+    m.check_status()
+    assert rel_err(got, want) < 5e-3 and row_rel_err(got, want) < 5e-3
+    worst = max((rel_err(p.grad, ref[k]), k) for k, p in m.named_parameters() if k in ref)
+    assert worst[0] < 1e-2, worst

@@ -160,3 +160,57 @@ def test_conformer_mean_and_regression_step_glue():
     assert torch.allclose(g, torch.full_like(g, 1.0 / 3))
     with pytest.raises(ValueError):
         ops.conformers_mean(x, 5)
+
+
+def _bond_graph(batch, seed=0):
+    import types
+
+    g = torch.Generator().manual_seed(seed)
+    src, dst = [], []
+    b = batch.tolist()
+    for a in range(len(b) - 1):
+        if b[a] == b[a + 1]:
+            src += [a, a + 1]
+            dst += [a + 1, a]
+    ei = torch.tensor([src, dst], dtype=torch.int64)
+    ea = torch.rand(ei.shape[1], 3, generator=g)
+    return types.SimpleNamespace(edge_index=ei, edge_attr=ea)
+
+
+def test_covalent_trunk_matches_oracle():
+    """use_covalent=True (schnet_no_sum.py:131-142,166-175): forward, forward_3d_bary and every gradient, 1e-5."""
+    import types
+
+    torch.manual_seed(5)
+    cfg = dict(hidden_channels=64, num_filters=64, num_interactions=2, num_gaussians=20, cutoff=6.0, use_covalent=True)
+    o = osn.SchNetNoSum(None, **cfg)
+    c = cmp.SchNetNoSum(None, **cfg).to(DEV)
+    c.load_state_dict(o.state_dict(), strict=True)
+    b = syn.make_batch(3, 2, 14, seed=8)
+    db = _bond_graph(b.batch)
+    dbc = types.SimpleNamespace(edge_index=db.edge_index.to(DEV), edge_attr=db.edge_attr.to(DEV))
+    want = o(b.z, b.pos, b.batch, data_batch=db)
+    got = c(b.z.to(DEV), b.pos.to(DEV), b.batch.to(DEV), data_batch=dbc)
+    assert rel_err(got, want) < 1e-5
+    want.pow(2).mean().backward()
+    got.pow(2).mean().backward()
+    for (k, po), (_, pc) in zip(o.named_parameters(), c.named_parameters()):
+        if po.grad is not None:
+            assert rel_err(pc.grad, po.grad) < 1e-5, k
+    h, hb = c.forward_3d_bary(b.z.to(DEV), b.pos.to(DEV), b.batch.to(DEV), data_batch=dbc)
+    ho, hbo = o.forward_3d_bary(b.z, b.pos, b.batch, data_batch=db)
+    assert rel_err(h, ho) < 1e-5 and rel_err(hb, hbo) < 1e-5
+
+
+def test_schnet_with_multiple_returns_matches_oracle():
+    """schnet_no_sum.py:405-450: (ssp(lin1(h)), edge_index, rbf); edge_index bit-exact, the rest to 1e-5."""
+    torch.manual_seed(6)
+    cfg = dict(hidden_channels=64, num_filters=64, num_interactions=2, num_gaussians=20, cutoff=6.0)
+    o = osn.SchNetWithMultipleReturns(**cfg)
+    c = cmp.SchNetWithMultipleReturns(**cfg).to(DEV)
+    c.load_state_dict(o.state_dict(), strict=True)
+    b = syn.make_batch(3, 2, 14, seed=9)
+    ho, eio, eao = o(b.z, b.pos, b.batch)
+    hc, eic, eac = c(b.z.to(DEV), b.pos.to(DEV), b.batch.to(DEV))
+    assert torch.equal(eic.cpu(), eio)
+    assert rel_err(eac, eao) < 1e-5 and rel_err(hc, ho) < 1e-5

@@ -134,3 +134,49 @@ def test_self_golden_regression():
     for k, p in m.named_parameters():
         if k in g["grads"]:
             assert rel_err(p.grad, g["grads"][k]) < 1e-5, k
+
+
+def _bond_graph(batch, seed=0):
+    """A synthetic covalent graph: a chain inside every conformer, both directions, 3 bond attributes per edge
+    (the layout of ``data_batch.edge_index / edge_attr`` consumed at schnet_no_sum.py:166-175)."""
+    import types
+
+    g = torch.Generator().manual_seed(seed)
+    src, dst = [], []
+    b = batch.tolist()
+    for a in range(len(b) - 1):
+        if b[a] == b[a + 1]:
+            src += [a, a + 1]
+            dst += [a + 1, a]
+    ei = torch.tensor([src, dst], dtype=torch.int64)
+    ea = torch.rand(ei.shape[1], 3, generator=g)
+    return types.SimpleNamespace(edge_index=ei, edge_attr=ea)
+
+
+def test_covalent_trunk_and_multiple_returns_contract():
+    """use_covalent=True doubles the head input (schnet_no_sum.py:131-142) and adds one InteractionBlock stack on the
+    3 bond attributes; SchNetWithMultipleReturns returns (ssp(lin1(h)), edge_index, rbf) (schnet_no_sum.py:405-450)."""
+    from conan_fgw_b200 import synthetic as syn
+
+    torch.manual_seed(0)
+    b = syn.make_batch(2, 2, 9, seed=3)
+    db = _bond_graph(b.batch)
+    m = osn.SchNetNoSum(None, hidden_channels=32, num_filters=32, num_interactions=2, num_gaussians=10, cutoff=5.0,
+                        use_covalent=True)
+    sd = m.state_dict()
+    assert sd["lin1.weight"].shape == (16, 64) and sd["lin1_bary.weight"].shape == (16, 64)
+    assert sd["interactions_cov.1.mlp.0.weight"].shape == (32, 3)
+    out = m(b.z, b.pos, b.batch, data_batch=db)
+    assert out.shape == (4, 16) and torch.isfinite(out).all()
+    h, hb = m.forward_3d_bary(b.z, b.pos, b.batch, data_batch=db)
+    assert h.shape == hb.shape == (b.z.numel(), 16)
+    # the covalent stack matters: zeroing its filter MLP output changes the result
+    out.sum().backward()
+    assert m.interactions_cov[0].mlp[0].weight.grad.abs().sum() > 0
+
+    mr = osn.SchNetWithMultipleReturns(hidden_channels=32, num_filters=32, num_interactions=2, num_gaussians=10, cutoff=5.0)
+    h, ei, ea = mr(b.z, b.pos, b.batch)
+    assert h.shape == (b.z.numel(), 16) and ei.shape[0] == 2 and ea.shape == (ei.shape[1], 10)
+    from oracle.radius import radius_graph_ref
+
+    assert torch.equal(ei, radius_graph_ref(b.pos, 5.0, b.batch))
