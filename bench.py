@@ -364,7 +364,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     dominant = ["cmp_gemm_f32", "cmp_cfconv_dense_fwd", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd", "cmp_cfconv_fused_bwd_weights",
                 "cmp_cfconv_fused_bwd_weights_pairs", "cmp_node_gemm_dw_grouped", "cmp_node_gemm_fwd",
-                "cmp_node_gemm_dw"]
+                "cmp_node_gemm_dw", "cmp_node_chain_fwd"]
     total_ms, launches, kt = timed(resident_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, _, _ = timed(e2e_step, args.steps)
@@ -435,6 +435,8 @@ def run_ours(args):
         "cmp_cfconv_fused_bwd_weights_pairs": "cfconv_fused_bwd_kernel<pairs> (tcgen05: one column per undirected pair, "
                                               "dW accumulated in TMEM; algorithmic FLOPs counted per directed edge)",
         "cmp_node_gemm_fwd": "node_gemm_fwd_kernel (tcgen05 split-bf16 node linears)",
+        "cmp_node_chain_fwd": "node_chain_kernel (tcgen05 split-bf16: lin2 -> ssp -> lin (+ h) -> next lin1 of an interaction "
+                              "block chained on chip, and its backward)",
         "cmp_node_gemm_dw": "node_gemm_dw_kernel (tcgen05 split-bf16 weight gradients of the node linears)",
         "cmp_node_gemm_dw_grouped": "node_gemm_dw_grouped_kernel (all node-linear weight gradients of the step in one launch)",
     }

@@ -59,6 +59,8 @@ SIGNATURES = {
     "cmp_node_gemm_weight_bytes": (S, [I]),
     "cmp_node_gemm_pack_weight": (I, [P, I, I, I, P, P]),
     "cmp_node_gemm_fwd": (I, [P, L, P, L, P, P, I, P, L, P, L, L, I, I, P]),
+    "cmp_node_chain_max_stages": (I, []),
+    "cmp_node_chain_fwd": (I, [P, L, L, P, I, P]),
     "cmp_node_gemm_dw_workspace": (S, [I]),
     "cmp_node_gemm_dw": (I, [P, L, P, L, P, L, L, I, I, P, P, P, S, P]),
     "cmp_edge_message_fwd": (I, [P, P, P, P, P, L, I, P, P]),
@@ -141,6 +143,14 @@ class DensePackJob(ctypes.Structure):
     """``cmp_dense_pack_job_t``."""
     _fields_ = [("W1", ctypes.c_void_p), ("b1", ctypes.c_void_p), ("W2", ctypes.c_void_p), ("b2", ctypes.c_void_p),
                 ("packed", ctypes.c_void_p)]
+
+
+class ChainStage(ctypes.Structure):
+    """``cmp_chain_stage_t``."""
+    _fields_ = [("w_img", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("residual", ctypes.c_void_p),
+                ("scale_y", ctypes.c_void_p), ("out", ctypes.c_void_p), ("ldr", ctypes.c_int64),
+                ("lds", ctypes.c_int64), ("ldo", ctypes.c_int64), ("K", ctypes.c_int32), ("Nout", ctypes.c_int32),
+                ("act", ctypes.c_int32)]
 
 
 class DwProblem(ctypes.Structure):

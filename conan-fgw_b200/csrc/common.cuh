@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <utility>
 
 #include "conanmp.h"
 
@@ -33,6 +34,35 @@ void count_launch();
   } while (0)
 
 inline cudaStream_t as_stream(cmp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// A kernel launched through launch_pdl() may be scheduled while its predecessor in the stream is still draining: its
+// prologue (barrier init, TMEM allocation, TMA of weight images that were packed many launches earlier) overlaps the
+// predecessor's tail.  Contract of a PDL-aware kernel: pdl_wait() before the first access to anything the predecessor
+// may have written (it returns once the predecessor has completed and its writes are visible), nothing but private
+// set-up before it, and pdl_launch_dependents() once per CTA so that ITS successor can be scheduled early in turn.
+// Works under stream capture (the edge becomes a programmatic dependency of the CUDA graph).
+bool pdl_enabled();   // CMP_NO_PDL=1 in the environment turns every launch_pdl() into a plain launch
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -5,6 +5,8 @@
 
 #include <atomic>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cmp {
@@ -20,6 +22,15 @@ void set_error(const char* fmt, ...) {
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("CMP_NO_PDL");
+    cached = (e && e[0] && e[0] != '0') ? 0 : 1;
+  }
+  return cached != 0;
+}
 
 int sm_count() {
   static int cached = 0;

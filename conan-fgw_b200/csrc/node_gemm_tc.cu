@@ -35,7 +35,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // fp32 tile [TM atoms, C channels] -> bf16 hi / lo K-major images (rows = atoms):
 //   byte(a, c) = (a%8)*16 + (c%8)*2 + (a/8)*sbo + (c/8)*128
 // when ones_chunk >= 0 that 16-byte chunk of every row is set to {1, 0, 0, ...} (hi) / 0 (lo).
-template <int ROWS>
+template <int ROWS, int NW = CW>
 __device__ __forceinline__ void convert_tile(const float* __restrict__ X, int64_t ld, const float* __restrict__ Ysaved,
                                              int64_t ldys, int64_t m0, int64_t M, int C, uint32_t sbo, uint8_t* hi,
                                              uint8_t* lo, int ones_chunk, int warp, int lane) {
@@ -44,12 +44,12 @@ __device__ __forceinline__ void convert_tile(const float* __restrict__ X, int64_
   const int al = lane & 7, cl = lane >> 3;
   constexpr int UN = 4;   // warp-iterations whose global loads are issued back to back (memory-level parallelism)
   const int total = (ROWS / 8) * cbs;
-  for (int base = warp; base < total; base += CW * UN) {
+  for (int base = warp; base < total; base += NW * UN) {
    float4 P0[UN], P1[UN], Y0[UN], Y1[UN];
    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
    for (int u = 0; u < UN; ++u) {
-     const int wi = base + u * CW;
+     const int wi = base + u * NW;
      const int ab = wi / cbs, cb = wi - ab * cbs;
      const int a = ab * 8 + al, chunk = cb * 4 + cl;
      const int64_t row = m0 + a;
@@ -68,7 +68,7 @@ __device__ __forceinline__ void convert_tile(const float* __restrict__ X, int64_
    }
 #pragma unroll
    for (int u = 0; u < UN; ++u) {
-    const int wi = base + u * CW;
+    const int wi = base + u * NW;
     const int ab = wi / cbs, cb = wi - ab * cbs;
     const int a = ab * 8 + al, chunk = cb * 4 + cl;
     if (wi >= total || chunk >= nchunk) continue;
@@ -95,7 +95,7 @@ __device__ __forceinline__ void convert_tile(const float* __restrict__ X, int64_
   if (ones_chunk >= 0) {
     // two extra chunks (16 channels): chunk ones_chunk = {1,0,...}, ones_chunk + 1 = 0
     const int t = warp * 32 + lane;
-    for (int item = t; item < ROWS * 2; item += CW * 32) {
+    for (int item = t; item < ROWS * 2; item += NW * 32) {
       const int a = item >> 1, which = item & 1;
       const uint32_t off = (a & 7) * 16 + (a >> 3) * sbo + (ones_chunk + which) * 128;
       const bool live = (m0 + a) < M && which == 0;
@@ -146,9 +146,11 @@ __global__ void __launch_bounds__(NT, 2) node_gemm_fwd_kernel(const FwdParams p)
   tc::tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const int64_t ntiles = (p.M + TMF - 1) / TMF;
+  pdl_launch_dependents();
 
   if (warp == CW) {
     if (lane == 0) {
+      pdl_wait();   // the weight image may have been packed by the launch right before this one
       tc::mbar_arrive_expect_tx(&bars[0], 2 * w_bytes);
       tc::bulk_g2s(sWh, p.w_img, 2 * w_bytes, &bars[0]);
       tc::mbar_wait(&bars[0], 0);
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(NT, 2) node_gemm_fwd_kernel(const FwdParams p)
   } else {
     const int wq = warp & 3, h = warp >> 2;
     const int chan = wq * 32 + lane;
+    pdl_wait();
     const float bias = (p.bias && chan < p.Nout) ? p.bias[chan] : 0.0f;
     const uint32_t tD = tmem_base + ((uint32_t)(wq * 32) << 16);
     uint32_t it = 0;
@@ -315,6 +318,206 @@ __device__ __forceinline__ void node_dw_body(const DwParams& p, int rank, int nr
 
 __global__ void __launch_bounds__(NT, 2) node_gemm_dw_kernel(const DwParams p) {
   node_dw_body(p, blockIdx.x, gridDim.x, p.partial + (int64_t)blockIdx.x * 128 * (p.K + 16));
+}
+
+// ---- chained node linears: up to three Linear stages on one 64-atom tile without leaving the SM ---------------------
+// Stage s:  V_s = act_s(U_s W_s^T + b_s) * (1 - exp(-Ys)/2)  + R_s ,   U_0 = X (global),  U_(s+1) = V_s (on chip).
+//   forward  of an interaction-block tail (PyG CFConv.lin2 -> ssp -> InteractionBlock.lin (+ h) -> next block's CFConv.lin1,
+//            sns.py:163-164):  agg -> [lin2, ssp] -> y -> [lin, + h] -> h' -> [lin1'] -> x''
+//   backward of the same tail: dx'' -> [lin1'^T, + dh'] -> dh -> [lin^T, * ssp'(y)] -> dpre -> [lin2^T] -> dagg
+// Every stage is the split-bf16 GEMM of node_gemm_fwd_kernel (hi + lo images, three passes, fp32 accumulate).  The
+// epilogue thread that owns output channel k holds V_s[k, atoms] and writes 8 consecutive atoms as one 16-byte chunk of
+// the NEXT stage's operand, which is therefore read as an MN-major B operand (atoms contiguous): no transposition.
+// `out` of a stage may be null (value only feeds the next stage).  Weights of all stages stay in shared memory.
+constexpr int MAXS = 3;
+constexpr int CWC = 16;            // compute warps of the chain kernel: 4 per TMEM lane quarter, 16 atoms each
+constexpr int NTC = CWC * 32 + 32;
+struct ChainStage {
+  const uint8_t* w_img;    // hi | lo image, rows = Nout padded to 128, K columns
+  const float* bias;       // [Nout] or null
+  const float* residual;   // [M, Nout] or null (added last)
+  const float* scale_y;    // [M, Nout] or null: saved ShiftedSoftplus OUTPUT y, V *= 1 - exp(-y) / 2  (ssp' on the output side)
+  float* out;              // [M, Nout] or null
+  int64_t ldr, lds, ldo;
+  int K, Nout, act;
+};
+struct ChainParams {
+  const float* X;
+  int64_t ldx;
+  int64_t M;
+  int nstages;
+  ChainStage st[MAXS];
+};
+
+__global__ void __launch_bounds__(NTC, 1) node_chain_kernel(const __grid_constant__ ChainParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bars[MAXS + 2];   // wbar[s], xready, dready
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t w_off[MAXS + 1];
+  w_off[0] = 0;
+#pragma unroll
+  for (int s = 0; s < MAXS; ++s) w_off[s + 1] = w_off[s] + (s < p.nstages ? 2u * 128u * (uint32_t)p.st[s].K * 2u : 0u);
+  uint8_t* sXh = smem + w_off[MAXS];
+  uint8_t* sXl = sXh + TMF * MAXC * 2;
+
+  if (tid == 0) {
+    for (int s = 0; s < MAXS; ++s) tc::mbar_init(&bars[s], 1);
+    tc::mbar_init(&bars[MAXS], CWC * 32);
+    tc::mbar_init(&bars[MAXS + 1], 1);
+    tc::mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int64_t ntiles = (p.M + TMF - 1) / TMF;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == CWC) {
+    if (lane == 0) {
+      for (int s = 0; s < p.nstages; ++s) {
+        const uint32_t bytes = w_off[s + 1] - w_off[s];
+        tc::mbar_arrive_expect_tx(&bars[s], bytes);
+        tc::bulk_g2s(smem + w_off[s], p.st[s].w_img, bytes, &bars[s]);
+      }
+      const uint32_t aXh = tc::smem_u32(sXh), aXl = tc::smem_u32(sXl);
+      uint32_t n = 0;   // operand images consumed so far
+      for (int64_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        for (int s = 0; s < p.nstages; ++s, ++n) {
+          const int K = p.st[s].K;
+          const uint32_t sbo = (uint32_t)(K >> 3) * 128;
+          const uint32_t aWh = tc::smem_u32(smem + w_off[s]), aWl = aWh + 128u * (uint32_t)K * 2u;
+          if (ti == (int64_t)blockIdx.x) tc::mbar_wait(&bars[s], 0);
+          tc::mbar_wait(&bars[MAXS], n & 1);
+          tc::tc_fence_after();
+          // stage 0 reads the K-major image of convert_tile, later stages the MN-major image the previous epilogue wrote
+          const uint32_t idesc = tc::umma_idesc_f16(128, TMF, 1, 0, s == 0 ? 0 : 1);
+          const int ks_n = K >> 4;
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a = (pass == 2) ? aWl : aWh;
+            const uint32_t b = (pass == 1) ? aXl : aXh;
+            for (int ks = 0; ks < ks_n; ++ks)
+              tc::umma_f16(tmem_base, tc::umma_smem_desc(a + ks * 256, 128, sbo), tc::umma_smem_desc(b + ks * 256, 128, sbo),
+                           idesc, (pass | ks) != 0);
+          }
+          tc::umma_commit(&bars[MAXS + 1]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    const int wq = warp & 3, h = warp >> 2;
+    const int chan = wq * 32 + lane;
+    const uint32_t tD = tmem_base + ((uint32_t)(wq * 32) << 16);
+    uint32_t n = 0;
+    for (int64_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+      const int64_t m0 = ti * TMF;
+      // the last stage of the previous tile was read out of TMEM by every thread before anyone arrives on xready below;
+      // its MMAs (the only readers of the images) completed before that read-out
+      if (n > 0) tc::named_bar_sync(1, CWC * 32);
+      convert_tile<TMF, CWC>(p.X, p.ldx, nullptr, 0, m0, p.M, p.st[0].K, (uint32_t)(p.st[0].K >> 3) * 128, sXh, sXl, -1, warp, lane);
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&bars[MAXS]);
+      for (int s = 0; s < p.nstages; ++s, ++n) {
+        // stage parameters into registers (p.st[s] with a run-time s would otherwise be re-read from the parameter bank
+        // through local memory inside the element loops)
+        const int Nout = p.st[s].Nout, act = p.st[s].act;
+        const bool live = chan < Nout;
+        const float bias = (p.st[s].bias && live) ? __ldg(p.st[s].bias + chan) : 0.0f;
+        const bool feeds = s + 1 < p.nstages;
+        const uint32_t sbo_n = (uint32_t)(Nout >> 3) * 128;   // K of the next stage = Nout of this one
+        const int64_t ldr = p.st[s].ldr, lds = p.st[s].lds, ldo = p.st[s].ldo;
+        const float* res_p = p.st[s].residual ? p.st[s].residual + m0 * ldr + chan : nullptr;
+        const float* ys_p = p.st[s].scale_y ? p.st[s].scale_y + m0 * lds + chan : nullptr;
+        float* out_p = p.st[s].out ? p.st[s].out + m0 * ldo + chan : nullptr;
+        const int rows = (int)min((int64_t)TMF, p.M - m0);    // atoms of this tile that exist
+        const int c0 = h * 16;             // this warp's 16 atoms of the tile
+        // full tile and a real channel: no per-element predicates (the common case: one ragged tile per launch at most)
+        const bool full = live && rows == TMF;
+        const int ir = (int)ldr, is = (int)lds, io = (int)ldo;   // row strides fit 32 bits (a tile spans 64 rows)
+        float v[16], r[16], y[16];
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {   // residual / saved-activation rows are fetched while the MMAs of the stage run
+            r[j] = res_p ? __ldg(res_p + (c0 + j) * ir) : 0.0f;
+            y[j] = ys_p ? __ldg(ys_p + (c0 + j) * is) : 1e30f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const bool ok = live && (c0 + j) < rows;
+            r[j] = (res_p && ok) ? __ldg(res_p + (c0 + j) * ir) : 0.0f;
+            y[j] = (ys_p && ok) ? __ldg(ys_p + (c0 + j) * is) : 1e30f;
+          }
+        }
+        tc::mbar_wait(&bars[MAXS + 1], n & 1);
+        tc::tc_fence_after();
+        tc::tmem_ld16(tD + c0, v);
+        tc::tmem_wait_ld();
+        if (act == CMP_ACT_SSP) {
+          // softplus(x) - ln 2 = max(x, 0) + ln 2 (log2(1 + 2^(-|x| log2 e)) - 1): two MUFU ops, ~1e-6 relative
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = v[j] + bias;
+            const float t = ex2_approx(-1.4426950408889634f * fabsf(x));
+            v[j] = fmaf(tc::fast_lg2(1.0f + t) - 1.0f, kLn2, fmaxf(x, 0.0f));
+          }
+        } else if (act == CMP_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = silu(v[j] + bias);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += bias;
+        }
+        if (ys_p) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= 1.0f - 0.5f * ex2_approx(-1.4426950408889634f * y[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += r[j];
+        if (out_p && live) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) out_p[(c0 + j) * io] = v[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < rows) out_p[(c0 + j) * io] = v[j];
+          }
+        }
+        if (feeds && live) {
+          // this thread's channel is K row `chan` of the next operand: 8 atoms = one 16-byte chunk (MN-major)
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float x = (full || c0 + g8 * 8 + j < rows) ? v[g8 * 8 + j] : 0.0f;
+              hi[j] = __bfloat162float(__float2bfloat16_rn(x));
+              lo[j] = x - hi[j];
+            }
+            const uint32_t off = (uint32_t)chan * 16 + (uint32_t)((c0 >> 3) + g8) * sbo_n;
+            *reinterpret_cast<uint4*>(sXh + off) = make_uint4(tc::pack_bf16x2(hi[0], hi[1]), tc::pack_bf16x2(hi[2], hi[3]),
+                                                              tc::pack_bf16x2(hi[4], hi[5]), tc::pack_bf16x2(hi[6], hi[7]));
+            *reinterpret_cast<uint4*>(sXl + off) = make_uint4(tc::pack_bf16x2(lo[0], lo[1]), tc::pack_bf16x2(lo[2], lo[3]),
+                                                              tc::pack_bf16x2(lo[4], lo[5]), tc::pack_bf16x2(lo[6], lo[7]));
+          }
+        }
+        tc::tc_fence_before();
+        if (feeds) {
+          tc::fence_proxy_async();
+          tc::mbar_arrive(&bars[MAXS]);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 64);
 }
 
 // ---- grouped launch: many weight-gradient problems share one grid (the node linears of a whole backward pass) ----
@@ -474,8 +677,67 @@ extern "C" int cmp_node_gemm_fwd(const float* X, int64_t ldx, const float* saved
   FwdParams p{X, ldx, saved_y, ldys, reinterpret_cast<const uint8_t*>(w_img), bias, residual, ldr, Y, ldy, M, K, Nout, act};
   const int64_t ntiles = ceil_div(M, TMF);
   const int grid = (int)(ntiles < 2 * sm_count() ? ntiles : 2 * sm_count());
-  node_gemm_fwd_kernel<<<grid, NT, smem, as_stream(stream)>>>(p);
+  CMP_REQUIRE(launch_pdl(node_gemm_fwd_kernel, dim3(grid), dim3(NT), smem, as_stream(stream), p) == cudaSuccess, CMP_ECUDA,
+              "cmp_node_gemm_fwd: launch failed");
   CMP_LAUNCH_CHECK("cmp_node_gemm_fwd");
+  return CMP_OK;
+}
+
+extern "C" int cmp_node_chain_max_stages(void) { return MAXS; }
+
+extern "C" int cmp_node_chain_fwd(const float* X, int64_t ldx, int64_t M, const void* stages, int nstages,
+                                  cmp_stream_t stream) {
+  CMP_REQUIRE(M >= 0 && nstages >= 1 && nstages <= MAXS, CMP_EINVAL, "cmp_node_chain_fwd: bad size");
+  if (M == 0) return CMP_OK;
+  CMP_REQUIRE(X && stages, CMP_EINVAL, "cmp_node_chain_fwd: null pointer");
+  CMP_REQUIRE(ldx % 4 == 0 && (uintptr_t)X % 16 == 0, CMP_EINVAL, "cmp_node_chain_fwd: X must be 16-byte aligned, ldx % 4 == 0");
+  CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED, "cmp_node_chain_fwd: needs an sm_100 device (tcgen05)");
+  const cmp_chain_stage_t* in = reinterpret_cast<const cmp_chain_stage_t*>(stages);
+  ChainParams p;
+  p.X = X;
+  p.ldx = ldx;
+  p.M = M;
+  p.nstages = nstages;
+  size_t w_bytes = 0;
+  for (int s = 0; s < nstages; ++s) {
+    CMP_REQUIRE(dims_ok(in[s].K, in[s].Nout), CMP_EUNSUPPORTED,
+                "cmp_node_chain_fwd: K / Nout must be multiples of 16 in [16,128]");
+    CMP_REQUIRE(in[s].w_img && (uintptr_t)in[s].w_img % 16 == 0, CMP_EINVAL, "cmp_node_chain_fwd: weight image missing / misaligned");
+    CMP_REQUIRE(s == 0 || in[s].K == in[s - 1].Nout, CMP_EINVAL, "cmp_node_chain_fwd: stage K must equal the previous Nout");
+    CMP_REQUIRE(in[s].act == CMP_ACT_NONE || in[s].act == CMP_ACT_SSP || in[s].act == CMP_ACT_SILU, CMP_EINVAL,
+                "cmp_node_chain_fwd: bad act");
+    ChainStage& d = p.st[s];
+    d.w_img = reinterpret_cast<const uint8_t*>(in[s].w_img);
+    d.bias = in[s].bias;
+    d.residual = in[s].residual;
+    d.scale_y = in[s].scale_y;
+    d.out = in[s].out;
+    d.ldr = in[s].ldr;
+    d.lds = in[s].lds;
+    d.ldo = in[s].ldo;
+    d.K = in[s].K;
+    d.Nout = in[s].Nout;
+    d.act = in[s].act;
+    w_bytes += (size_t)2 * 128 * in[s].K * 2;
+  }
+  CMP_REQUIRE(p.st[nstages - 1].out != nullptr, CMP_EINVAL, "cmp_node_chain_fwd: the last stage needs an output");
+  for (int s = nstages; s < MAXS; ++s) p.st[s] = ChainStage{};
+  const size_t smem = w_bytes + (size_t)2 * TMF * MAXC * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(node_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             MAXS * 2 * 128 * MAXC * 2 + 2 * TMF * MAXC * 2) != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("cmp_node_chain_fwd: cannot opt in to shared memory");
+      return CMP_ECUDA;
+    }
+    attr_set = true;
+  }
+  const int64_t ntiles = ceil_div(M, TMF);
+  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+  CMP_REQUIRE(launch_pdl(node_chain_kernel, dim3(grid), dim3(NTC), smem, as_stream(stream), p) == cudaSuccess, CMP_ECUDA,
+              "cmp_node_chain_fwd: launch failed");
+  CMP_LAUNCH_CHECK("cmp_node_chain_fwd");
   return CMP_OK;
 }
 

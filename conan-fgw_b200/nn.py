@@ -21,6 +21,11 @@ from . import _lib, ops
 from .graph import NeighborList, build_neighbor_list, graph_from_edge_index, radius_graph  # noqa: F401
 
 
+# fused (bf16-mode) trunk: chain the node linears of a block tail in one kernel (cmp_node_chain_fwd); False = one launch
+# per Linear (kept for cross-checking)
+CHAIN_NODE_LINEARS = True
+
+
 class Linear(nn.Linear):
     """``torch.nn.Linear`` parameters and init, forward through ``cmp_gemm_f32``."""
 
@@ -267,8 +272,25 @@ class SchNet(nn.Module):
             h = self.embed(z, graph.status)
             if all(blk.conv.fused_ok(graph, self.distance_expansion) for blk in self.interactions):
                 # fused path: no edge_index / rbf[E, Ng] / filter[E, F] is ever materialised, no host sync
-                for blk in self.interactions:
-                    h = blk.forward_fused(h, graph, self.distance_expansion, residual=h)
+                blocks = list(self.interactions)
+                chained = CHAIN_NODE_LINEARS and all(
+                    ops.block_tail_supported(b.conv.lin2, b.lin, n.conv.lin1 if n is not None else None)
+                    for b, n in zip(blocks, blocks[1:] + [None]))
+                if not chained:
+                    for blk in blocks:
+                        h = blk.forward_fused(h, graph, self.distance_expansion, residual=h)
+                    return h, graph
+                # one kernel per block for the node linears: lin2 -> ssp -> lin (+ h) -> the NEXT block's lin1
+                sm = self.distance_expansion
+                x = blocks[0].conv.lin1(h)
+                for blk, nxt in zip(blocks, blocks[1:] + [None]):
+                    net = blk.conv.nn
+                    agg = ops.cfconv_fused(x, net[0].weight, net[0].bias, net[2].weight, net[2].bias, graph, sm.offset,
+                                           sm.coeff, blk.conv.cutoff)
+                    if nxt is not None:
+                        h, x = ops.block_tail(agg, h, blk.conv.lin2, blk.lin, nxt.conv.lin1)
+                    else:
+                        h = ops.block_tail(agg, h, blk.conv.lin2, blk.lin)
                 return h, graph
             edge_index = None
             edge_weight = graph.edge_weight()      # first host sync: also surfaces device-side input errors

@@ -460,27 +460,136 @@ class _LinearTCFn(Function):
             w_t = ctx.w_img_t if ctx.w_img_t is not None else _pack_node_weight(weight, True)
             dx = _node_gemm(dy2, w_t, Nout, K, saved_y=y).reshape(*ctx.lead, K)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            M = x2.shape[0]
-            dw = torch.empty(Nout, K, dtype=torch.float32, device=dy2.device)
-            db = torch.empty(Nout, dtype=torch.float32, device=dy2.device) if ctx.has_bias else None
-            dwq = _dw_queue(weight)
-            if dwq is not None:
-                # queued: raw pointers only for the outputs (autograd must stay the sole owner of dw / db, or it
-                # would clone them - unwritten - instead of adopting them as .grad); inputs are kept alive here
-                dwq.append(dict(
-                    dY=dy2.data_ptr(), lddy=dy2.stride(0), saved_y=y.data_ptr() if y is not None else None,
-                    ldys=y.stride(0) if y is not None else 0, X=x2.data_ptr(), ldx=x2.stride(0), M=M, K=K, Nout=Nout,
-                    dW=dw.data_ptr(), lddw=K, db=db.data_ptr() if db is not None else None, keep=(dy2, y, x2),
-                    param=weight if ctx.needs_input_grad[1] else None, dW_base=dw.data_ptr(),
-                    bias_param=ctx.bias_ref if (db is not None and ctx.needs_input_grad[2]) else None,
-                    db_base=db.data_ptr() if db is not None else None))
-            else:
-                ws = _lib.workspace(_lib.size_query("cmp_node_gemm_dw_workspace", K), dy2.device)
-                call("cmp_node_gemm_dw", ptr(dy2), dy2.stride(0), ptr(y), y.stride(0) if y is not None else 0, ptr(x2),
-                     x2.stride(0), M, K, Nout, ptr(dw), ptr(db), ptr(ws), ws.numel(), work=2.0 * M * K * Nout)
+            dw, db = _weight_grads(dy2, y, x2, weight, ctx.bias_ref if ctx.has_bias else None, ctx.needs_input_grad[1],
+                                   ctx.needs_input_grad[2])
         if ctx.has_res and ctx.needs_input_grad[4]:
             dres = dy
         return dx, dw, db, None, dres
+
+
+
+def _weight_grads(dy2, saved_y, x2, weight, bias, want_w=True, want_b=True):
+    """dW = dY'^T X and db = column sums of dY' of one tensor-core Linear (dY' = dY * ssp'(saved_y) when given):
+    queued for the grouped launch inside ``deferred_weight_grads`` (see there), launched immediately otherwise."""
+    Nout, K = weight.shape
+    M = x2.shape[0]
+    dev = dy2.device
+    dw = torch.empty(Nout, K, dtype=torch.float32, device=dev)
+    db = torch.empty(Nout, dtype=torch.float32, device=dev) if bias is not None else None
+    dwq = _dw_queue(weight)
+    if dwq is not None:
+        # queued: raw pointers only for the outputs (autograd must stay the sole owner of dw / db, or it would clone
+        # them - unwritten - instead of adopting them as .grad); inputs are kept alive here
+        dwq.append(dict(
+            dY=dy2.data_ptr(), lddy=dy2.stride(0), saved_y=saved_y.data_ptr() if saved_y is not None else None,
+            ldys=saved_y.stride(0) if saved_y is not None else 0, X=x2.data_ptr(), ldx=x2.stride(0), M=M, K=K, Nout=Nout,
+            dW=dw.data_ptr(), lddw=K, db=db.data_ptr() if db is not None else None, keep=(dy2, saved_y, x2),
+            param=weight if want_w else None, dW_base=dw.data_ptr(),
+            bias_param=bias if (db is not None and want_b) else None, db_base=db.data_ptr() if db is not None else None))
+    else:
+        ws = _lib.workspace(_lib.size_query("cmp_node_gemm_dw_workspace", K), dev)
+        call("cmp_node_gemm_dw", ptr(dy2), dy2.stride(0), ptr(saved_y), saved_y.stride(0) if saved_y is not None else 0,
+             ptr(x2), x2.stride(0), M, K, Nout, ptr(dw), ptr(db), ptr(ws), ws.numel(), work=2.0 * M * K * Nout)
+    return dw, db
+
+
+def _node_images(weight):
+    """(image of W, image of W^T) of a node Linear: from the prepack cache, else packed now."""
+    cached = _cached_images(weight)
+    return cached if cached is not None else _pack_node_weight_both(weight)
+
+
+def _chain(x2, stages):
+    """Run ``cmp_node_chain_fwd``.  stages: list of dicts {img, K, Nout, bias, act, residual, scale_y, out}."""
+    M = x2.shape[0]
+    arr = (_lib.ChainStage * len(stages))()
+    work = 0.0
+    for slot, st in zip(arr, stages):
+        slot.w_img = st["img"].data_ptr()
+        slot.bias = st["bias"].data_ptr() if st.get("bias") is not None else None
+        r, y, o = st.get("residual"), st.get("scale_y"), st.get("out")
+        slot.residual, slot.ldr = (r.data_ptr(), r.stride(0)) if r is not None else (None, 0)
+        slot.scale_y, slot.lds = (y.data_ptr(), y.stride(0)) if y is not None else (None, 0)
+        slot.out, slot.ldo = (o.data_ptr(), o.stride(0)) if o is not None else (None, 0)
+        slot.K, slot.Nout, slot.act = st["K"], st["Nout"], int(st.get("act", ACT_NONE))
+        work += 2.0 * M * st["K"] * st["Nout"]
+    call("cmp_node_chain_fwd", ptr(x2), x2.stride(0), M, ctypes.addressof(arr), len(stages), work=work)
+
+
+class _BlockTailFn(Function):
+    """The node-level tail of an interaction block and the head of the next one in ONE kernel per direction
+    (``cmp_node_chain_fwd``; PyG ``CFConv.lin2 -> ShiftedSoftplus -> InteractionBlock.lin``, the residual of
+    ``sns.py:164`` and the next block's ``CFConv.lin1``):
+
+        y = ssp(agg W2^T + b2);   h' = h + y Wl^T + bl;   x'' = h' W1n^T        (x'' only when W1n is given)
+
+    backward: ``dx'' -> [W1n, + dh'] -> dh -> [Wl, * ssp'(y)] -> dpre -> [W2] -> dagg`` on the same kernel with the
+    transposed weight images; the five weight / bias gradients go to the grouped weight-gradient launch."""
+
+    @staticmethod
+    def forward(ctx, agg, h, W2, b2, Wl, bl, W1n):
+        agg, h = _f32c(agg), _f32c(h)
+        N = agg.shape[0]
+        H, F = W2.shape
+        dev = agg.device
+        img2, img2_t = _node_images(W2)
+        imgl, imgl_t = _node_images(Wl)
+        y = torch.empty(N, H, dtype=torch.float32, device=dev)
+        hn = torch.empty(N, H, dtype=torch.float32, device=dev)
+        stages = [dict(img=img2, K=F, Nout=H, bias=b2, act=ACT_SSP, out=y),
+                  dict(img=imgl, K=H, Nout=H, bias=bl, residual=h, out=hn)]
+        xn = None
+        ctx.imgs_t = [img2_t, imgl_t, None]
+        if W1n is not None:
+            img1, img1_t = _node_images(W1n)
+            xn = torch.empty(N, W1n.shape[0], dtype=torch.float32, device=dev)
+            stages.append(dict(img=img1, K=H, Nout=W1n.shape[0], out=xn))
+            ctx.imgs_t[2] = img1_t
+        _chain(agg, stages)
+        ctx.has_next = W1n is not None
+        ctx.refs = (b2, bl)         # the Parameters themselves (bias-gradient adoption check of the deferred launch)
+        ctx.save_for_backward(agg, y, hn, W2, Wl, W1n)
+        if xn is None:
+            return hn
+        return hn, xn
+
+    @staticmethod
+    def backward(ctx, dhn, dxn=None):
+        agg, y, hn, W2, Wl, W1n = ctx.saved_tensors
+        b2, bl = ctx.refs
+        N = agg.shape[0]
+        H, F = W2.shape
+        dev = agg.device
+        img2_t, imgl_t, img1_t = ctx.imgs_t
+        dpre = torch.empty(N, H, dtype=torch.float32, device=dev)
+        dagg = torch.empty(N, F, dtype=torch.float32, device=dev)
+        tail = [dict(img=imgl_t, K=H, Nout=H, scale_y=y, out=dpre), dict(img=img2_t, K=H, Nout=F, out=dagg)]
+        if ctx.has_next and dxn is not None:
+            dxn = _f32c(dxn)
+            dh = torch.empty(N, H, dtype=torch.float32, device=dev)
+            res = _f32c(dhn) if dhn is not None else None
+            _chain(dxn, [dict(img=img1_t, K=W1n.shape[0], Nout=H, residual=res, out=dh)] + tail)
+        else:
+            dh = _f32c(dhn)
+            _chain(dh, tail)
+        dW2, db2 = _weight_grads(dpre, None, agg, W2, b2, ctx.needs_input_grad[2], ctx.needs_input_grad[3])
+        dWl, dbl = _weight_grads(dh, None, y, Wl, bl, ctx.needs_input_grad[4], ctx.needs_input_grad[5])
+        dW1n = None
+        if ctx.has_next and dxn is not None:
+            dW1n, _ = _weight_grads(dxn, None, hn, W1n, None, ctx.needs_input_grad[6], False)
+        return dagg, dh, dW2, db2, dWl, dbl, dW1n
+
+
+def block_tail(agg, h, lin2, lin, lin1_next=None):
+    """``(h', x'')`` (or ``h'`` alone) from the aggregate of an interaction block: see ``_BlockTailFn``."""
+    W1n = lin1_next.weight if lin1_next is not None else None
+    return _BlockTailFn.apply(agg, h, lin2.weight, lin2.bias, lin.weight, lin.bias, W1n)
+
+
+def block_tail_supported(lin2, lin, lin1_next=None) -> bool:
+    mods = [lin2, lin] + ([lin1_next] if lin1_next is not None else [])
+    return (all(m.tc and node_tc_supported(m.weight.shape[1], m.weight.shape[0]) for m in mods)
+            and lin2.bias is not None and lin.bias is not None and (lin1_next is None or lin1_next.bias is None))
 
 
 class _ActFn(Function):

@@ -339,6 +339,26 @@ int cmp_cfconv_fused_bwd_weights_pairs(const void* g_bf16, const void* xprime_bf
  * its autograd GEMMs around the message passing (PyG CFConv.lin1/lin2, InteractionBlock.lin, ConAN
  * heads sns.py:177-179,225-231) in the bf16 mode. */
 int cmp_node_gemm_tc_supported(int K, int Nout);
+
+/* Up to cmp_node_chain_max_stages() (3) of those linears CHAINED on one 64-atom tile, intermediates never leaving the SM:
+ *   V_s = act_s(U_s W_s^T + b_s) * (1 - exp(-scale_y_s) / 2) + R_s,   U_0 = X,  U_(s+1) = V_s.
+ * Forward of an interaction-block tail (PyG CFConv.lin2 -> ShiftedSoftplus -> InteractionBlock.lin (+ h) -> the next
+ * block's CFConv.lin1; sns.py:163-164) and, with transposed weight images, its backward
+ * (dx'' -> lin1'^T (+ dh') -> lin^T * ssp'(y) -> lin2^T).  scale_y is the saved ShiftedSoftplus OUTPUT.
+ * stages: array of nstages cmp_chain_stage_t in HOST memory; K of stage s must equal Nout of stage s - 1; `out` may be
+ * NULL for a stage whose value only feeds the next one (not for the last). */
+typedef struct {
+  const void* w_img;     /* cmp_node_gemm_pack_weight image (hi | lo) of W [Nout, K] */
+  const float* bias;     /* [Nout] or NULL */
+  const float* residual; /* [M, Nout] or NULL */
+  const float* scale_y;  /* [M, Nout] or NULL */
+  float* out;            /* [M, Nout] or NULL */
+  int64_t ldr, lds, ldo;
+  int32_t K, Nout, act;
+} cmp_chain_stage_t;
+int cmp_node_chain_max_stages(void);
+int cmp_node_chain_fwd(const float* X, int64_t ldx, int64_t M, const void* stages, int nstages,
+                       cmp_stream_t stream);
 size_t cmp_node_gemm_weight_bytes(int image_K);
 int cmp_node_gemm_pack_weight(const float* W, int rows, int cols, int transpose, void* packed,
                               cmp_stream_t stream);

@@ -411,3 +411,79 @@ def test_bf16_mode_edge_cases_against_oracle(case):
         for (n_, po), (_, pc) in zip(o.named_parameters(), c.named_parameters()):
             if po.grad is not None and po.grad.abs().max() > 0:
                 assert rel_err(pc.grad, po.grad) < 2e-2, n_
+
+
+def test_node_chain_kernel_matches_fp64_reference():
+    """cmp_node_chain_fwd: 1 - 3 chained split-bf16 linears with every epilogue option (bias, ssp, residual, ssp' scaling
+    by a saved activation), ragged tile (M not a multiple of 64), 64- and 128-wide stages; fp32-grade: 5e-5 vs fp64."""
+    _need_sm100()
+    torch.manual_seed(11)
+    M = 64 * 5 + 23
+
+    def ssp(t):
+        return torch.nn.functional.softplus(t) - 0.6931471805599453
+
+    def run(dims, opts):
+        X = torch.randn(M, dims[0], device=DEV)
+        stages, u = [], X.double()
+        keep = []
+        for s, (K, Nout) in enumerate(zip(dims[:-1], dims[1:])):
+            W = torch.randn(Nout, K, device=DEV) / K ** 0.5
+            o = opts[s]
+            bias = torch.randn(Nout, device=DEV) if o.get("bias") else None
+            res = torch.randn(M, Nout, device=DEV) if o.get("residual") else None
+            ysv = torch.randn(M, Nout, device=DEV) if o.get("scale_y") else None
+            out = torch.empty(M, Nout, device=DEV) if (o.get("out", True) or s == len(dims) - 2) else None
+            img = ops._pack_node_weight(W, False)
+            stages.append(dict(img=img, K=K, Nout=Nout, bias=bias, act=ops.ACT_SSP if o.get("ssp") else ops.ACT_NONE,
+                               residual=res, scale_y=ysv, out=out))
+            v = u @ W.double().t()
+            if bias is not None:
+                v = v + bias.double()
+            if o.get("ssp"):
+                v = ssp(v)
+            if ysv is not None:
+                v = v * (1.0 - 0.5 * torch.exp(-ysv.double()))
+            if res is not None:
+                v = v + res.double()
+            keep.append((out, v))
+            u = v
+        ops._chain(X, stages)
+        for out, v in keep:
+            if out is not None:
+                assert rel_err(out, v) < 5e-5
+
+    run([128, 128], [dict(bias=True, ssp=True)])
+    run([128, 128, 128], [dict(bias=True, ssp=True), dict(bias=True, residual=True)])
+    run([128, 128, 128, 128], [dict(bias=True, ssp=True), dict(bias=True, residual=True), dict()])
+    run([128, 128, 128, 128], [dict(residual=True), dict(scale_y=True), dict()])            # the backward chain
+    run([128, 128, 128, 128], [dict(bias=True, ssp=True, out=False), dict(bias=True, residual=True, out=False), dict()])
+    run([128, 64, 64], [dict(bias=True), dict(bias=True, ssp=True)])                        # head-shaped stages
+    run([64, 128, 32], [dict(bias=True, ssp=True), dict(residual=True)])
+
+
+def test_chained_trunk_equals_per_layer_launches():
+    """nn.CHAIN_NODE_LINEARS: the same split-bf16 arithmetic in one kernel per block tail - embeddings and every gradient
+    agree with the one-launch-per-Linear path to fp32 rounding."""
+    _need_sm100()
+    from conan_fgw_b200 import nn as cnn
+
+    _, c = make(seed=6, num_interactions=3)
+    c.set_precision("bf16")
+    b = syn.make_batch(5, 3, 23, seed=9).to(DEV)
+    res = {}
+    for chained in (False, True):
+        cnn.CHAIN_NODE_LINEARS = chained
+        try:
+            c.zero_grad()
+            before = cmp._lib.launches()
+            out = c(b.z, b.pos, b.batch, num_graphs=b.num_graphs)
+            out.pow(2).mean().backward()
+            res[chained] = (out.detach().clone(), {k: p.grad.clone() for k, p in c.named_parameters() if p.grad is not None},
+                            cmp._lib.launches() - before)
+        finally:
+            cnn.CHAIN_NODE_LINEARS = True
+    assert rel_err(res[True][0], res[False][0]) < 2e-5
+    for k, g in res[False][1].items():
+        assert rel_err(res[True][1][k], g) < 5e-5, k
+    assert res[True][2] < res[False][2]
