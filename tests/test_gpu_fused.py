@@ -485,5 +485,8 @@ def test_chained_trunk_equals_per_layer_launches():
             cnn.CHAIN_NODE_LINEARS = True
     assert rel_err(res[True][0], res[False][0]) < 2e-5
     for k, g in res[False][1].items():
-        assert rel_err(res[True][1][k], g) < 5e-5, k
+        # the filter-MLP weight gradients are accumulated from bf16-staged copies of g and x' (cfconv_tc_bwd.cu): an fp32-
+        # rounding difference of those inputs flips bf16 roundings, so these parameters agree to 2e-4, the rest to 5e-5
+        tol = 2e-4 if ".mlp." in k else 5e-5
+        assert rel_err(res[True][1][k], g) < tol, k
     assert res[True][2] < res[False][2]
