@@ -615,6 +615,517 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_kernel(const __gr
   if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
+
+// =================================================================================================================
+// Warp-specialised variant (the default): ONE stream of tiles per CTA, the phases of a tile on different warps
+// =================================================================================================================
+// The per-pipeline kernel above runs the five phases of a tile one after the other on the same 128 threads.  Its softplus
+// epilogue is bound by the XU pipe (MUFU.EX2 and the F2FP conversions share it: 16 lanes per clock and SM), which then
+// idles during the other phases (measured: XU 39 %, issue 37 %, 12 K cycles per tile and pipeline).  Here the tiles of the
+// CTA's conformers flow through warp groups that only meet at mbarriers:
+//
+//   XU sets  (2 x 4 warps; set k & 1 owns tile k)   thread = pair column:    Gaussians / cutoff / masks of tile k + 2 -> B1[set]
+//                                                   thread = filter channel: D1[set] -> a' -> A2[set]       (both XU work)
+//   MMA      (1 thread)                             D1[k & 1] = W1 B1[k & 1];   D2[k & 1] = W2 A2[k & 1]  (TMEM 4 x 128 columns)
+//   EP2      (4 warps, thread = filter channel)     D2[k & 1] -> both directions of every pair, x' / agg rows in registers
+//
+// so the XU-bound work of one tile overlaps the FMA-bound epilogue 2 of the previous tile and both MMAs, and the two sets
+// cover each other's waits.  Every role walks the same tile sequence (conformers blockIdx.x, blockIdx.x + gridDim.x, ...; a
+// pure function of seg_ptr), so the running tile counter k alone names buffers and mbarrier phases: tile k uses buffer
+// k & 1 and its event is completion number k >> 1 of that buffer's barrier.
+//   b1_full[s]    set -> MMA        B1[s], cutoffs and masks of tile k written                (128 arrivals)
+//   mma1_done[s]  MMA -> set        D1[s] holds tile k (and B1[s] may be overwritten)         (tcgen05.commit)
+//   a2_full[s]    set -> MMA        A2[s] written and D1[s] consumed                          (128 arrivals)
+//   mma2_done[s]  MMA -> EP2, set   D2[s] holds tile k; A2[s] may be overwritten              (tcgen05.commit)
+//   d2_empty[s]   EP2 -> MMA        D2[s] consumed                                            (128 arrivals)
+// Cutoffs and direction masks travel in a ring of 8 slots: the Gaussians of tile k + 8 cannot start before EP2(k) has
+// finished (chain mma1_done(k + 6) <- a2_full(k + 4) <- mma2_done(k + 2) <- d2_empty(k)): no barrier of its own.
+namespace ws {
+constexpr int W_EP2 = 0, W_SET = 4, W_MMA = 12, NWARPS = 13;   // 4 warps per SMSP at most: 128 registers per thread
+constexpr int THREADS = NWARPS * 32;
+constexpr int MR = 8;                                   // meta ring slots
+constexpr uint32_t B1_BYTES = TE * K1 * 2;              // 16384
+constexpr uint32_t A2_BYTES = K2 * TE * 2;              // 36864
+constexpr uint32_t META_BYTES = 320;                    // half C[128] | uint32 mF[4] | uint32 mR[4] | pad
+constexpr uint32_t GEO_BYTES = NMAX * 12 + NMAX * AW * 4;   // positions + adjacency rows of a set's current conformer
+constexpr uint32_t OFF_B1 = W1_BYTES + W2_BYTES;
+constexpr uint32_t OFF_A2 = OFF_B1 + 2 * B1_BYTES;
+constexpr uint32_t OFF_GEO = OFF_A2 + 2 * A2_BYTES;
+constexpr uint32_t OFF_META = OFF_GEO + 2 * GEO_BYTES;
+constexpr uint32_t SMEM = OFF_META + MR * META_BYTES;
+static_assert(SMEM <= 232448 - 1024, "shared memory budget");
+// mbarrier slots (8 bytes each)
+constexpr uint32_t BAR_W = 0, BAR_B1 = 8, BAR_M1 = 24, BAR_A2 = 40, BAR_M2 = 56, BAR_D2 = 72, NBARS = 11;
+}  // namespace ws
+
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+struct TileGeom {
+  bool diag;
+  int j0, nj, ncols, npad;
+};
+__device__ __forceinline__ TileGeom tile_geom(int n, int a0, int m, int tl) {
+  TileGeom g;
+  g.diag = tl < 0;
+  g.j0 = g.diag ? a0 : a0 + 16 + 8 * tl;
+  g.nj = g.diag ? m : min(8, n - g.j0);
+  g.ncols = g.diag ? (m * (m - 1)) >> 1 : 16 * g.nj;
+  g.npad = (g.ncols + 15) & ~15;
+  return g;
+}
+
+// the tile sequence as nested loops (k = running tile counter of the CTA, identical in every role):
+//   conf_begin(cs, n)   block_begin(bi, a0, m)   tile(tg, n, a0, m)   block_end(a0, m)
+template <class FC, class FB, class FT, class FE>
+__device__ __forceinline__ void ws_tile_loop(const DenseParams& p, uint32_t& k, FC&& conf_begin, FB&& block_begin,
+                                             FT&& tile, FE&& block_end) {
+  for (int conf = blockIdx.x; conf < p.G; conf += gridDim.x) {
+    const int cs = __ldg(p.seg_ptr + conf);
+    const int n = __ldg(p.seg_ptr + conf + 1) - cs;
+    if (n > NMAX || n <= 0) continue;
+    conf_begin(cs, n);
+    const int nblocks = (n + 15) >> 4;
+    for (int bi = 0; bi < nblocks; ++bi) {
+      const int a0 = bi * 16;
+      const int m = min(16, n - a0);
+      block_begin(bi, a0, m);
+      const int nrect = (n > a0 + 16) ? ((n - a0 - 16 + 7) >> 3) : 0;
+      for (int tl = (m >= 2) ? -1 : 0; tl < nrect; ++tl, ++k) tile(tile_geom(n, a0, m, tl), n, a0, m);
+      block_end(a0, m);
+    }
+  }
+}
+
+// the same sequence as an iterator (the XU sets walk it twice: the Gaussians run two tiles ahead of epilogue 1)
+struct TileIter {
+  int conf, cs, n, a0, m, tl, nrect;
+  __device__ __forceinline__ void start(const DenseParams& p) {
+    conf = (int)blockIdx.x - (int)gridDim.x;
+    cs = 0; n = 0; a0 = 0; m = 0; tl = 0; nrect = 0;
+  }
+  // advance to the next tile; false when the CTA's conformers are exhausted
+  __device__ __forceinline__ bool next(const DenseParams& p) {
+    if (++tl < nrect) return true;
+    a0 += 16;
+    for (;;) {
+      if (a0 < n) {
+        m = min(16, n - a0);
+        nrect = (n > a0 + 16) ? ((n - a0 - 16 + 7) >> 3) : 0;
+        tl = (m >= 2) ? -1 : 0;
+        if (tl < nrect) return true;
+        a0 += 16;
+        continue;
+      }
+      conf += (int)gridDim.x;
+      if (conf >= p.G) return false;
+      cs = __ldg(p.seg_ptr + conf);
+      n = __ldg(p.seg_ptr + conf + 1) - cs;
+      if (n > NMAX || n <= 0) n = 0;      // not ours: skipped by every role
+      a0 = 0;
+    }
+  }
+  __device__ __forceinline__ TileGeom geom() const { return tile_geom(n, a0, m, tl); }
+};
+
+// DBG: clock64 timeline of CTA 0 in p.dbg: [role 0 = XU sets, 1 = MMA, 2 = EP2][tile < 64][8 stamps]
+template <bool DBG>
+__global__ void __launch_bounds__(ws::THREADS, 1) cfconv_dense_ws_kernel(const __grid_constant__ DenseParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bars[ws::NBARS];
+#define WS_STAMP(role, kk, i)                                                                              \
+  do {                                                                                                     \
+    if (DBG && p.dbg != nullptr && blockIdx.x == 0 && (kk) < 64u && (tid & 127) == 0)                      \
+      p.dbg[((role) * 64 + (kk)) * 8 + (i)] = clock64();                                                   \
+  } while (0)
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wq = warp & 3;                 // TMEM lane quarter of this warp
+
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&bars[1 + s], 128);    // b1_full
+      tc::mbar_init(&bars[3 + s], 1);      // mma1_done
+      tc::mbar_init(&bars[5 + s], 128);    // a2_full
+      tc::mbar_init(&bars[7 + s], 1);      // mma2_done
+      tc::mbar_init(&bars[9 + s], 128);    // d2_empty
+    }
+    tc::mbar_fence_init();
+    tc::mbar_arrive_expect_tx(&bars[0], W1_BYTES + W2_BYTES);
+    tc::bulk_g2s(smem, p.weights, W1_BYTES, &bars[0]);
+    tc::bulk_g2s(smem + W1_BYTES, p.weights + W1_BYTES, W2_BYTES, &bars[0]);
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+
+  const uint32_t tm = tmem_base_s;
+  uint32_t sbase = tc::smem_u32(smem);
+  uint32_t bbase = tc::smem_u32(bars);
+  // opaque copies: keeps ptxas from re-deriving the shared-window base inside the hot loops
+  asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
+  asm volatile("mov.u32 %0, %0;" : "+r"(bbase));
+
+  if (warp >= ws::W_SET && warp < ws::W_MMA) {
+    // ================================ XU sets: Gaussians of tile k + 2, epilogue 1 of tile k ================================
+    const uint32_t set = (uint32_t)(warp - ws::W_SET) >> 2;
+    const int t = (tid - ws::W_SET * 32) & (PT - 1);      // pair column (Gaussians) / filter channel = TMEM lane (epilogue 1)
+    const uint32_t dpair = (uint32_t)diag_i(t) | ((uint32_t)diag_j(t) << 8);
+    const uint32_t aPos = sbase + ws::OFF_GEO + set * ws::GEO_BYTES, aAdj = aPos + NMAX * 12;
+    const uint32_t aB = sbase + ws::OFF_B1 + set * ws::B1_BYTES;
+    const uint32_t aA = sbase + ws::OFF_A2 + set * ws::A2_BYTES;
+    const uint32_t a_col = aA + (uint32_t)t * 16;                                  // a' column block of channel t
+    const uint32_t a_row = aB + (uint32_t)(t >> 3) * B1_SBO + (uint32_t)(t & 7) * 16;   // rbf row of column t
+    const uint32_t dtm = tm + set * TE + ((uint32_t)(wq * 32) << 16);
+    const int k1steps = (p.Ng + 16) >> 4;
+    const int bar_id = 1 + (int)set;
+
+    // ---- Gaussians, cutoff and direction masks of tile kr (the iterator's current tile) -> B1[set], meta ring ----
+    auto gaussians = [&](const TileIter& it, uint32_t kr) {
+      const TileGeom tg = it.geom();
+      int i_loc, j_loc;
+      bool valid;
+      if (tg.diag) {
+        i_loc = it.a0 + (int)(dpair & 0xffu);
+        j_loc = it.a0 + (int)(dpair >> 8);
+        valid = (t < 120) && ((int)(dpair >> 8) < it.m);
+      } else {
+        i_loc = it.a0 + (t & 15);
+        j_loc = tg.j0 + (t >> 4);
+        valid = ((t & 15) < it.m) && ((t >> 4) < tg.nj);
+      }
+      bool ef = false, er = false;
+      if (valid) {
+        ef = (lds32(aAdj + 4u * (uint32_t)(i_loc * AW + (j_loc >> 5))) >> (j_loc & 31)) & 1u;    // edge j -> i
+        er = (lds32(aAdj + 4u * (uint32_t)(j_loc * AW + (i_loc >> 5))) >> (i_loc & 31)) & 1u;    // edge i -> j
+      }
+      if (p.transposed) {
+        const bool tmp = ef;
+        ef = er;
+        er = tmp;
+      }
+      const uint32_t am = sbase + ws::OFF_META + (kr & (ws::MR - 1)) * ws::META_BYTES;
+      {
+        const unsigned bf = __ballot_sync(0xffffffffu, ef), br = __ballot_sync(0xffffffffu, er);
+        if (lane == 0) {
+          sts32(am + 256 + 4u * (uint32_t)wq, bf);
+          sts32(am + 272 + 4u * (uint32_t)wq, br);
+        }
+      }
+      if (t < tg.npad) {
+        float dist = 0.0f, cval = 0.0f;
+        if (ef || er) {
+          const uint32_t pj = aPos + 12u * (uint32_t)j_loc, pi = aPos + 12u * (uint32_t)i_loc;
+          const float dx = lds_f(pj) - lds_f(pi), dy = lds_f(pj + 4) - lds_f(pi + 4), dz = lds_f(pj + 8) - lds_f(pi + 8);
+          const float d2 = dx * dx + dy * dy + dz * dz;
+          dist = d2 * rsqrtf(fmaxf(d2, 1e-20f));
+          cval = 0.5f * (__cosf(dist * p.pi_over_cutoff) + 1.0f);
+        }
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(am + 2u * (uint32_t)t), "h"(__half_as_ushort(__float2half_rn(cval))) : "memory");
+        const float ds = dist * p.s;
+        if (p.uniform) {
+          // equally spaced centres: per K-step of 16 Gaussians one anchor g_a = 2^-(u_a^2), u_a = d s - mu_a, and the two
+          // neighbour ratios 2^(+-2 delta u_a - delta^2) from MUFU; the others follow by g_(k+-1) = g_k r, r *= 2^(-2 delta^2)
+          // (a Gaussian more than ~5 centres from d is below f16 resolution, so an underflowing anchor costs nothing)
+#pragma unroll
+          for (int A = 0; A < K1 / 16; ++A) {
+            if (A < k1steps) {
+              float v[16];
+              const float u = ds - p.mu[A * 16 + 7];
+              const float ga = tc::fast_ex2(-u * u);
+              float r = tc::fast_ex2(fmaf(p.two_delta, u, -p.delta2));
+              float sdn = tc::fast_ex2(fmaf(-p.two_delta, u, -p.delta2));
+              v[7] = ga;
+              float gu = ga, gd = ga;
+#pragma unroll
+              for (int i = 1; i <= 8; ++i) {
+                gu *= r;
+                v[7 + i] = gu;
+                if (i < 8) r *= p.qstep;
+              }
+#pragma unroll
+              for (int i = 1; i <= 7; ++i) {
+                gd *= sdn;
+                v[7 - i] = gd;
+                if (i < 7) sdn *= p.qstep;
+              }
+              if (A == (p.Ng >> 4)) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = (j == (p.Ng & 15)) ? 1.0f : v[j];
+              }
+              sts128(a_row + (2 * A) * 128, pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                     pack_f16x2(v[6], v[7]));
+              sts128(a_row + (2 * A + 1) * 128, pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]),
+                     pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int jc = 0; jc < 2 * k1steps; ++jc) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float xx = ds - p.mu[jc * 8 + j];
+              v[j] = tc::fast_ex2(-xx * xx);
+            }
+            if (jc == (p.Ng >> 3)) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = (j == (p.Ng & 7)) ? 1.0f : v[j];
+            }
+            sts128(a_row + jc * 128, pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                   pack_f16x2(v[6], v[7]));
+          }
+        }
+      }
+      tc::fence_proxy_async();
+      mbar_arrive_addr(bbase + ws::BAR_B1 + 8 * set);
+    };
+    // positions and adjacency rows of the conformer the Gaussian iterator is in (the set's private copy)
+    int staged_conf = -1;
+    auto stage = [&](const TileIter& it) {
+      if (it.conf == staged_conf) return;
+      staged_conf = it.conf;
+      tc::named_bar_sync(bar_id, PT);      // every column of the set is done with the previous conformer
+      if (t < it.n) {
+        const float* pp = p.pos + (int64_t)(it.cs + t) * 3;
+        sts32(aPos + 12u * (uint32_t)t + 0, __float_as_uint(__ldg(pp + 0)));
+        sts32(aPos + 12u * (uint32_t)t + 4, __float_as_uint(__ldg(pp + 1)));
+        sts32(aPos + 12u * (uint32_t)t + 8, __float_as_uint(__ldg(pp + 2)));
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.adj) + it.cs + t);
+        sts128(aAdj + 16u * (uint32_t)t, a.x, a.y, a.z, a.w);
+      }
+      tc::named_bar_sync(bar_id, PT);
+    };
+    // advance an iterator by n tiles
+    auto advance = [&](TileIter& it, int steps) {
+      bool ok = true;
+      for (int i = 0; i < steps && ok; ++i) ok = it.next(p);
+      return ok;
+    };
+
+    TileIter itE, itR;         // epilogue-1 tile k, Gaussian tile k + 2
+    itE.start(p);
+    itR.start(p);
+    bool okE = advance(itE, 1 + (int)set);     // tile number `set`
+    bool okR = advance(itR, 1 + (int)set);
+    if (okR) {                                  // Gaussians of the set's first tile
+      stage(itR);
+      gaussians(itR, set);
+      okR = advance(itR, 2);
+    }
+    for (uint32_t k = set; okE; k += 2) {
+      // ---- epilogue 1 of tile k: a' = C (max(D1, 0) + log2(1 + 2^-|D1|) - 1) -> A2[set] (MN-major [144, pair]) ----
+      const int npad = itE.geom().npad;
+      const uint32_t aC = sbase + ws::OFF_META + (k & (ws::MR - 1)) * ws::META_BYTES;
+      WS_STAMP(0, k, 0);
+      mbar_wait_addr(bbase + ws::BAR_M1 + 8 * set, (k >> 1) & 1u);                        // D1[set] holds tile k
+      WS_STAMP(0, k, 1);
+      if (k >= 2) mbar_wait_addr(bbase + ws::BAR_M2 + 8 * set, ((k >> 1) - 1) & 1u);     // MMA2(k - 2) has read A2[set]
+      tc::tc_fence_after();
+      WS_STAMP(0, k, 2);
+      int c0 = 0;
+      for (; c0 + 32 <= npad; c0 += 32) {
+        float v[32];
+        tmem_ld32_issue(dtm + c0, v);
+        const uint4 c_a = lds128(aC + 2u * (uint32_t)c0), c_b = lds128(aC + 2u * (uint32_t)c0 + 16),
+                    c_c = lds128(aC + 2u * (uint32_t)c0 + 32), c_d = lds128(aC + 2u * (uint32_t)c0 + 48);
+        const uint32_t cw[16] = {c_a.x, c_a.y, c_a.z, c_a.w, c_b.x, c_b.y, c_b.z, c_b.w,
+                                 c_c.x, c_c.y, c_c.z, c_c.w, c_d.x, c_d.y, c_d.z, c_d.w};
+        uint32_t o[16];
+        tmem_ld32_wait(v);
+        ep1_chunk<32>(v, cw, o);
+        const uint32_t a_dst = a_col + (uint32_t)(c0 >> 3) * A2_SBO;
+        sts128(a_dst, o[0], o[1], o[2], o[3]);
+        sts128(a_dst + A2_SBO, o[4], o[5], o[6], o[7]);
+        sts128(a_dst + 2 * A2_SBO, o[8], o[9], o[10], o[11]);
+        sts128(a_dst + 3 * A2_SBO, o[12], o[13], o[14], o[15]);
+      }
+      if (c0 < npad) {   // a last 16-column chunk
+        float v[16];
+        tmem_ld16_issue(dtm + c0, v);
+        const uint4 c_a = lds128(aC + 2u * (uint32_t)c0), c_b = lds128(aC + 2u * (uint32_t)c0 + 16);
+        const uint32_t cw[8] = {c_a.x, c_a.y, c_a.z, c_a.w, c_b.x, c_b.y, c_b.z, c_b.w};
+        uint32_t o[8];
+        tmem_ld16_wait(v);
+        ep1_chunk<16>(v, cw, o);
+        const uint32_t a_dst = a_col + (uint32_t)(c0 >> 3) * A2_SBO;
+        sts128(a_dst, o[0], o[1], o[2], o[3]);
+        sts128(a_dst + A2_SBO, o[4], o[5], o[6], o[7]);
+      }
+      // rows 128..143: row 128 = C_p (multiplies the b2 column of W2aug), rows 129..143 = 0
+      for (int item = t; item < (npad >> 3) * 16; item += PT) {
+        const int ec = item >> 4, kr = item & 15;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        if (kr == 0) w = lds128(aC + 16u * (uint32_t)ec);
+        sts128(aA + (uint32_t)ec * A2_SBO + (uint32_t)(128 + kr) * 16, w.x, w.y, w.z, w.w);
+      }
+      tc::tc_fence_before();
+      tc::fence_proxy_async();
+      mbar_arrive_addr(bbase + ws::BAR_A2 + 8 * set);
+      WS_STAMP(0, k, 3);
+      // ---- Gaussians of tile k + 2 (B1[set] is free: its reader, MMA1(k), has completed) ----
+      if (okR) {
+        stage(itR);
+        gaussians(itR, k + 2);
+        okR = advance(itR, 2);
+      }
+      WS_STAMP(0, k, 4);
+      if (DBG && p.dbg != nullptr && blockIdx.x == 0 && k < 64u && t == 0) p.dbg[(0 * 64 + k) * 8 + 7] = npad;
+      okE = advance(itE, 2);
+    }
+  } else if (warp == ws::W_MMA) {
+    // ================================ MMA: one thread issues everything ================================
+    if (lane == 0) {
+      uint32_t k = 0;
+      mbar_wait_addr(bbase + ws::BAR_W, 0);          // weight images
+      const int k1steps = (p.Ng + 16) >> 4;
+      const uint32_t aW1 = sbase, aW2 = sbase + W1_BYTES;
+      int np1 = 0, np2 = 0;                          // tile widths of tiles k - 1 and k - 2
+      auto issue_mma2 = [&](uint32_t j, int npad) {  // D2[j & 1] = W2aug A2[j & 1]
+        const uint32_t s = j & 1u;
+        if (j >= 2) mbar_wait_addr(bbase + ws::BAR_D2 + 8 * s, ((j >> 1) - 1) & 1u);   // EP2(j - 2) has consumed D2[s]
+        tc::tc_fence_after();
+        const uint32_t idesc2 = tc::umma_idesc_f16(F, npad, 0, 0, 1);
+        const uint32_t aA = sbase + ws::OFF_A2 + s * ws::A2_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < K2 / 16; ++ks)
+          tc::umma_f16(tm + 256 + s * TE, tc::umma_smem_desc(aW2 + ks * 256, 128, A2_SBO),
+                       tc::umma_smem_desc(aA + ks * 256, 128, A2_SBO), idesc2, ks > 0);
+        umma_commit_addr(bbase + ws::BAR_M2 + 8 * s);
+      };
+      ws_tile_loop(
+          p, k, [&](int, int) {}, [&](int, int, int) {},
+          [&](const TileGeom tg, int, int, int) {
+            const uint32_t s = k & 1u;
+            WS_STAMP(1, k, 0);
+            // epilogue 1 of tile k - 2: A2[s] is complete and D1[s] has been read
+            if (k >= 2) mbar_wait_addr(bbase + ws::BAR_A2 + 8 * s, ((k >> 1) - 1) & 1u);
+            WS_STAMP(1, k, 1);
+            mbar_wait_addr(bbase + ws::BAR_B1 + 8 * s, (k >> 1) & 1u);
+            WS_STAMP(1, k, 2);
+            tc::tc_fence_after();
+            const uint32_t idesc1 = tc::umma_idesc_f16(F, tg.npad, 0, 0, 0);
+            const uint32_t aB = sbase + ws::OFF_B1 + s * ws::B1_BYTES;
+            for (int ks = 0; ks < k1steps; ++ks)
+              tc::umma_f16(tm + s * TE, tc::umma_smem_desc(aW1 + ks * 256, 128, B1_SBO),
+                           tc::umma_smem_desc(aB + ks * 256, 128, B1_SBO), idesc1, ks > 0);
+            umma_commit_addr(bbase + ws::BAR_M1 + 8 * s);
+            WS_STAMP(1, k, 3);
+            if (k >= 2) issue_mma2(k - 2, np2);
+            WS_STAMP(1, k, 4);
+            np2 = np1;
+            np1 = tg.npad;
+          },
+          [&](int, int) {});
+      // drain: the second MMA of the last two tiles
+      if (k >= 2) {
+        mbar_wait_addr(bbase + ws::BAR_A2 + 8 * (k & 1u), ((k >> 1) - 1) & 1u);
+        issue_mma2(k - 2, np2);
+      }
+      if (k >= 1) {
+        const uint32_t j = k - 1;
+        mbar_wait_addr(bbase + ws::BAR_A2 + 8 * (j & 1u), (j >> 1) & 1u);
+        issue_mma2(j, np1);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ EP2: both directions of every pair, register operands ================================
+    const int t = tid;                                                             // filter channel = TMEM lane
+    const uint32_t dtm0 = tm + 256 + ((uint32_t)(wq * 32) << 16);
+    uint32_t k = 0;
+    int goff = 0;
+    float xr[16], ar[16];
+    ws_tile_loop(
+        p, k,
+        [&](int cs, int n) {
+          goff = cs * F + t;          // element offset of (first atom of the conformer, channel t) in x / out
+          // rows that later blocks add column sums to start from zero (block 0 is written once, at its end)
+          for (int a = 16; a < n; ++a) p.out[goff + a * F] = 0.0f;
+        },
+        [&](int bi, int a0, int m) {
+          // x' rows of the block and its running sums.  Block 0 starts from zero; the rows of a later block already hold
+          // the column sums the earlier blocks added to them (same thread, program order)
+#pragma unroll
+          for (int il = 0; il < 16; ++il) {
+            xr[il] = (il < m) ? __ldg(p.x + goff + (a0 + il) * F) : 0.0f;
+            ar[il] = (bi > 0 && il < m) ? p.out[goff + (a0 + il) * F] : 0.0f;
+          }
+        },
+        [&](const TileGeom tg, int, int, int m) {
+          const uint32_t s = k & 1u;
+          const uint32_t dtm = dtm0 + s * TE;
+          // operands of a RECT tile that live in global memory: issued now, needed after the second MMA
+          float xjr[8], ojr[8];
+          if (!tg.diag) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              xjr[jj] = (jj < tg.nj) ? __ldg(p.x + goff + (tg.j0 + jj) * F) : 0.0f;
+              ojr[jj] = (jj < tg.nj) ? p.out[goff + (tg.j0 + jj) * F] : 0.0f;
+            }
+          }
+          WS_STAMP(2, k, 0);
+          mbar_wait_addr(bbase + ws::BAR_M2 + 8 * s, (k >> 1) & 1u);                 // D2[s] holds tile k
+          tc::tc_fence_after();
+          WS_STAMP(2, k, 1);
+          const uint32_t amk = sbase + ws::OFF_META + (k & (ws::MR - 1)) * ws::META_BYTES + 256;
+          uint32_t mF[4], mR[4];
+          {
+            const uint4 a = lds128(amk), b = lds128(amk + 16);
+            mF[0] = a.x; mF[1] = a.y; mF[2] = a.z; mF[3] = a.w;
+            mR[0] = b.x; mR[1] = b.y; mR[2] = b.z; mR[3] = b.w;
+          }
+          const uint32_t anyF = mF[0] | mF[1] | mF[2] | mF[3], anyR = mR[0] | mR[1] | mR[2] | mR[3];
+          const bool sym = (mF[0] == mR[0]) && (mF[1] == mR[1]) && (mF[2] == mR[2]) && (mF[3] == mR[3]);
+          if ((anyF | anyR) != 0u) {
+            if (tg.diag) {
+              if (sym)
+                diag_tile<true>(dtm, m, ar, xr, mF, mR);
+              else
+                diag_tile<false>(dtm, m, ar, xr, mF, mR);
+            } else {
+              if (sym)
+                rect_tile<0>(dtm, tg.nj, ar, xr, xjr, ojr, mF, mR);
+              else if (anyF == 0u)
+                rect_tile<1>(dtm, tg.nj, ar, xr, xjr, ojr, mF, mR);
+              else if (anyR == 0u)
+                rect_tile<2>(dtm, tg.nj, ar, xr, xjr, ojr, mF, mR);
+              else
+                rect_tile<3>(dtm, tg.nj, ar, xr, xjr, ojr, mF, mR);
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj)
+                if (jj < tg.nj) p.out[goff + (tg.j0 + jj) * F] = ojr[jj];
+            }
+          }
+          tc::tc_fence_before();
+          mbar_arrive_addr(bbase + ws::BAR_D2 + 8 * s);
+          WS_STAMP(2, k, 2);
+        },
+        [&](int a0, int m) {
+          // ---- row block finished: its own rows ----
+#pragma unroll
+          for (int il = 0; il < 16; ++il)
+            if (il < m) p.out[goff + (a0 + il) * F] = ar[il];
+        });
+    // conformers above the atom limit belong to the per-edge kernel (skip_large) or are an error
+    if (!p.skip_large && t == 0 && p.status) {
+      for (int conf = blockIdx.x; conf < p.G; conf += gridDim.x)
+        if (__ldg(p.seg_ptr + conf + 1) - __ldg(p.seg_ptr + conf) > NMAX) atomicOr(p.status, CMP_STATUS_EDGE_OVERFLOW);
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+#undef WS_STAMP
+}
+
 // ---- weight images: f16, log2(e) folded into W1 / b1, ln 2 into W2 ---------------------------------------------
 __device__ __forceinline__ void dense_pack_body(const float* __restrict__ W1, const float* __restrict__ b1,
                                                 const float* __restrict__ W2, const float* __restrict__ b2, int Ng,
@@ -687,6 +1198,8 @@ using namespace cmp;
 static int g_dense_stagger_ns = 1500, g_dense_active_pipes = NP;
 extern "C" void cmp_debug_set_dense_stagger(int ns) { g_dense_stagger_ns = ns; }
 extern "C" void cmp_debug_set_dense_pipes(int n) { g_dense_active_pipes = n; }
+static int g_dense_variant = 0;   // 0: warp-specialised (default)   1: per-pipeline kernel
+extern "C" void cmp_debug_set_dense_variant(int v) { g_dense_variant = v; }
 static int g_dense_dbg_mode = 0;
 extern "C" void cmp_debug_set_dense_mode(int m) { g_dense_dbg_mode = m; }
 static long long* g_dense_dbg = nullptr;
@@ -766,6 +1279,10 @@ extern "C" int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int3
     if (cudaFuncSetAttribute(cfconv_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) !=
             cudaSuccess ||
         cudaFuncSetAttribute(cfconv_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(cfconv_dense_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws::SMEM) !=
+            cudaSuccess ||
+        cudaFuncSetAttribute(cfconv_dense_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws::SMEM) !=
             cudaSuccess) {
       (void)cudaGetLastError();
       set_error("cmp_cfconv_dense_fwd: cannot opt in to %u bytes of shared memory", SMEM_BYTES);
@@ -773,8 +1290,10 @@ extern "C" int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int3
     }
     attr_set = true;
   }
-  CMP_REQUIRE(cudaMemsetAsync(counter, 0, sizeof(int32_t), st) == cudaSuccess, CMP_ECUDA,
-              "cmp_cfconv_dense_fwd: memset failed");
+  const bool legacy = g_dense_variant == 1;
+  if (legacy)   // the per-pipeline kernel pulls conformers from a work counter; the warp-specialised one walks a fixed sequence
+    CMP_REQUIRE(cudaMemsetAsync(counter, 0, sizeof(int32_t), st) == cudaSuccess, CMP_ECUDA,
+                "cmp_cfconv_dense_fwd: memset failed");
   DenseParams p;
   p.x = x;
   p.pos = pos;
@@ -815,7 +1334,11 @@ extern "C" int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int3
   p.dbg = g_dense_dbg;
   const int grid = (int)std::min<int64_t>((G + NP - 1) / NP, sm_count());
   CMP_REQUIRE((int64_t)G * NMAX * F < ((int64_t)1 << 31) || true, CMP_EINVAL, "unreachable");
-  if (p.dbg)
+  if (!legacy && p.dbg)
+    cfconv_dense_ws_kernel<true><<<(int)std::min<int64_t>(G, sm_count()), ws::THREADS, ws::SMEM, st>>>(p);
+  else if (!legacy)
+    cfconv_dense_ws_kernel<false><<<(int)std::min<int64_t>(G, sm_count()), ws::THREADS, ws::SMEM, st>>>(p);
+  else if (p.dbg)
     cfconv_dense_kernel<true><<<grid, CTA_THREADS, SMEM_BYTES, st>>>(p);
   else
     cfconv_dense_kernel<false><<<grid, CTA_THREADS, SMEM_BYTES, st>>>(p);

@@ -502,6 +502,8 @@ void cmp_debug_set_dense_pipes(int n);
 /* Debug knob of the timestamped build of cmp_cfconv_dense_fwd: bit 0 = skip the a' stores, bit 1 = skip the cutoff loads,
  * bit 2 = skip the TMEM loads of epilogue 1 (results are then meaningless; for phase timing only). */
 void cmp_debug_set_dense_mode(int mode);
+/* Kernel variant of cmp_cfconv_dense_fwd: 0 = warp-specialised tile pipeline (default), 1 = per-pipeline kernel. */
+void cmp_debug_set_dense_variant(int variant);
 /* Same for cmp_cfconv_fused_bwd_weights: 12 timestamps per tile (first 20 tiles), 240 int64. */
 void cmp_debug_set_bwd_timestamps(void* buf);
 

@@ -1,0 +1,33 @@
+"""Ad-hoc: clock64 timeline of the warp-specialised dense kernel (CTA 0: XU sets, MMA thread, EP2) on a workload."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import conan_fgw_b200 as cmp
+from conan_fgw_b200 import _lib, ops
+dev = "cuda"
+wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2_lipo_train"
+b = cmp.synthetic.make_config_batch(wl).to(dev)
+n_max = int(torch.bincount(b.batch).max())
+nl = cmp.build_neighbor_list(b.pos, b.batch, 10.0, max_atoms=n_max, num_graphs=b.num_graphs)
+torch.manual_seed(0)
+blk = cmp.InteractionBlock(128, 50, 128, 10.0).to(dev)
+gs = cmp.GaussianSmearing(0.0, 10.0, 50).to(dev)
+W = (blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight, blk.mlp[2].bias)
+x = torch.randn(b.z.numel(), 128, device=dev)
+with torch.no_grad():
+    for _ in range(2):
+        ops._fused_aggregate(x, nl, W, gs.offset, gs.coeff, 10.0, False)
+    buf = torch.zeros(3 * 64 * 8, dtype=torch.int64, device=dev)
+    _lib.lib().cmp_debug_set_dense_timestamps(buf.data_ptr())
+    ops._fused_aggregate(x, nl, W, gs.offset, gs.coeff, 10.0, False)
+    torch.cuda.synchronize()
+    _lib.lib().cmp_debug_set_dense_timestamps(None)
+t = buf.cpu().view(3, 64, 8)
+base = int(t[1][0][0])
+for k in range(24):
+    if t[0][k][0] == 0:
+        break
+    s, m, e = t[0][k], t[1][k], t[2][k]
+    r = lambda v: int(v) - base
+    print(f"k={k:2d} npad={int(s[7]):3d} | XU set {k & 1}: wait D1 {r(s[0])}->{r(s[1])} A2free {r(s[2])} ep1 done {r(s[3])} (ep1 {int(s[3]-s[2])}) gauss done {r(s[4])} (rbf {int(s[4]-s[3])})"
+          f" | MMA: start {r(m[0])} a2 {r(m[1])} b1 {r(m[2])} mma1 issued {r(m[3])} mma2 issued {r(m[4])}"
+          f" | EP2: ready {r(e[0])} D2 {r(e[1])} done {r(e[2])} (ep2 {int(e[2]-e[1])})")
