@@ -114,7 +114,7 @@ SIGNATURES = {
     "cmp_build_adjacency": (I, [P, P, P, L, L, P, P]),
     "cmp_cfconv_dense_pack_weights": (I, [P, P, P, P, I, I, P, P]),
     "cmp_cfconv_dense_pack_weights_grouped": (I, [P, I, I, I, P]),
-    "cmp_cfconv_dense_fwd": (I, [P, P, P, P, L, P, P, I, F, F, I, I, I, P, P, P, P]),
+    "cmp_cfconv_dense_fwd": (I, [P, P, P, P, L, P, P, I, F, F, I, I, I, I, P, P, P, P]),
 }
 
 ACT_NONE, ACT_SSP, ACT_SILU = 0, 1, 2

@@ -141,6 +141,19 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
         : "memory");
   } while (ok == 0);
 }
+// poll without a suspend hint: the wake-up after a suspended try_wait costs far more than the issue slots of the poll
+__device__ __forceinline__ void mbar_spin_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (ok == 0);
+}
 __device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -641,7 +654,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_kernel(const __gr
 // Cutoffs and direction masks travel in a ring of 8 slots: the Gaussians of tile k + 8 cannot start before EP2(k) has
 // finished (chain mma1_done(k + 6) <- a2_full(k + 4) <- mma2_done(k + 2) <- d2_empty(k)): no barrier of its own.
 namespace ws {
-constexpr int W_EP2 = 0, W_SET = 4, W_MMA = 12, NWARPS = 13;   // 4 warps per SMSP at most: 128 registers per thread
+// warps 0-7: XU sets 0, 1 | 8-11: EP2 | 12: MMA (13-15 idle: setmaxnreg works on aligned groups of four warps).  The issue
+// arbiter prefers the higher warp id, so the MMA thread and EP2 go before the XU warps of their scheduler.
+constexpr int W_SET = 0, W_EP2 = 8, W_MMA = 12, NWARPS = 16;
+// registers: 128 per thread at launch (16 warps = the whole file); the MMA group shrinks to 56, EP2 grows to 176
+// (per scheduler: 2 x 128 + 176 + 56 = 488 of its 512 registers per lane)
+constexpr int REGS_EP2 = 176, REGS_MMA = 56;
 constexpr int THREADS = NWARPS * 32;
 constexpr int MR = 8;                                   // meta ring slots
 constexpr uint32_t B1_BYTES = TE * K1 * 2;              // 16384
@@ -649,13 +667,13 @@ constexpr uint32_t A2_BYTES = K2 * TE * 2;              // 36864
 constexpr uint32_t META_BYTES = 320;                    // half C[128] | uint32 mF[4] | uint32 mR[4] | pad
 constexpr uint32_t GEO_BYTES = NMAX * 12 + NMAX * AW * 4;   // positions + adjacency rows of a set's current conformer
 constexpr uint32_t OFF_B1 = W1_BYTES + W2_BYTES;
-constexpr uint32_t OFF_A2 = OFF_B1 + 2 * B1_BYTES;
+constexpr uint32_t OFF_A2 = OFF_B1 + 4 * B1_BYTES;     // B1[set + 2 * ((k >> 1) & 1)]
 constexpr uint32_t OFF_GEO = OFF_A2 + 2 * A2_BYTES;
 constexpr uint32_t OFF_META = OFF_GEO + 2 * GEO_BYTES;
 constexpr uint32_t SMEM = OFF_META + MR * META_BYTES;
 static_assert(SMEM <= 232448 - 1024, "shared memory budget");
 // mbarrier slots (8 bytes each)
-constexpr uint32_t BAR_W = 0, BAR_B1 = 8, BAR_M1 = 24, BAR_A2 = 40, BAR_M2 = 56, BAR_D2 = 72, NBARS = 11;
+constexpr uint32_t BAR_W = 0, BAR_B1 = 8, BAR_M1 = 40, BAR_A2 = 56, BAR_M2 = 72, BAR_D2 = 88, NBARS = 13;
 }  // namespace ws
 
 __device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
@@ -676,54 +694,71 @@ __device__ __forceinline__ TileGeom tile_geom(int n, int a0, int m, int tl) {
   return g;
 }
 
-// the tile sequence as nested loops (k = running tile counter of the CTA, identical in every role):
-//   conf_begin(cs, n)   block_begin(bi, a0, m)   tile(tg, n, a0, m)   block_end(a0, m)
-template <class FC, class FB, class FT, class FE>
-__device__ __forceinline__ void ws_tile_loop(const DenseParams& p, uint32_t& k, FC&& conf_begin, FB&& block_begin,
-                                             FT&& tile, FE&& block_end) {
-  for (int conf = blockIdx.x; conf < p.G; conf += gridDim.x) {
-    const int cs = __ldg(p.seg_ptr + conf);
-    const int n = __ldg(p.seg_ptr + conf + 1) - cs;
-    if (n > NMAX || n <= 0) continue;
-    conf_begin(cs, n);
-    const int nblocks = (n + 15) >> 4;
-    for (int bi = 0; bi < nblocks; ++bi) {
-      const int a0 = bi * 16;
-      const int m = min(16, n - a0);
-      block_begin(bi, a0, m);
-      const int nrect = (n > a0 + 16) ? ((n - a0 - 16 + 7) >> 3) : 0;
-      for (int tl = (m >= 2) ? -1 : 0; tl < nrect; ++tl, ++k) tile(tile_geom(n, a0, m, tl), n, a0, m);
-      block_end(a0, m);
-    }
-  }
-}
-
-// the same sequence as an iterator (the XU sets walk it twice: the Gaussians run two tiles ahead of epilogue 1)
-struct TileIter {
-  int conf, cs, n, a0, m, tl, nrect;
+// Conformer cursor of a role: seg_ptr is read two conformers ahead, so neither the bounds of the current conformer nor
+// those of the next one (whose inputs the roles prefetch) ever wait for a global load.
+struct ConfCursor {
+  int conf, cs0, ce0, cs1, ce1, cs2, ce2;     // current / next / next-next [start, end)
   __device__ __forceinline__ void start(const DenseParams& p) {
-    conf = (int)blockIdx.x - (int)gridDim.x;
-    cs = 0; n = 0; a0 = 0; m = 0; tl = 0; nrect = 0;
+    conf = (int)blockIdx.x;
+    const int c1 = conf + (int)gridDim.x, c2 = c1 + (int)gridDim.x;
+    cs0 = ce0 = cs1 = ce1 = cs2 = ce2 = 0;
+    if (conf < p.G) { cs0 = __ldg(p.seg_ptr + conf); ce0 = __ldg(p.seg_ptr + conf + 1); }
+    if (c1 < p.G) { cs1 = __ldg(p.seg_ptr + c1); ce1 = __ldg(p.seg_ptr + c1 + 1); }
+    if (c2 < p.G) { cs2 = __ldg(p.seg_ptr + c2); ce2 = __ldg(p.seg_ptr + c2 + 1); }
   }
-  // advance to the next tile; false when the CTA's conformers are exhausted
+  __device__ __forceinline__ bool valid(const DenseParams& p) const { return conf < p.G; }
+  __device__ __forceinline__ void advance(const DenseParams& p) {
+    conf += (int)gridDim.x;
+    cs0 = cs1; ce0 = ce1; cs1 = cs2; ce1 = ce2;
+    const int c2 = conf + 2 * (int)gridDim.x;
+    cs2 = ce2 = 0;
+    if (c2 < p.G) { cs2 = __ldg(p.seg_ptr + c2); ce2 = __ldg(p.seg_ptr + c2 + 1); }
+  }
+  // atoms of the current / next conformer as the roles treat them (0 = skipped by every role)
+  __device__ __forceinline__ int n0() const { const int n = ce0 - cs0; return (n > NMAX || n <= 0) ? 0 : n; }
+  __device__ __forceinline__ int n1() const { const int n = ce1 - cs1; return (n > NMAX || n <= 0) ? 0 : n; }
+};
+
+// Every role walks the same tile sequence with this iterator.  Code size matters here: the roles of a CTA execute
+// different code on the same schedulers, so each role's loop has ONE call site per phase (the first version of this kernel
+// inlined the phases at several sites: 255 KB of SASS, instruction-fetch stalls everywhere, conformer boundaries of ~5000
+// cycles) and the iterator costs a few instructions per tile.
+struct TileWalk {
+  ConfCursor cc;
+  int n, a0, m, tl, nrect;          // current tile: conformer size, row block, tile of the block (-1 = DIAG)
+  bool started, new_conf, new_block;
+  __device__ __forceinline__ void start(const DenseParams& p) {
+    cc.start(p);
+    n = 0; a0 = 0; m = 0; tl = 0; nrect = 0;
+    started = false; new_conf = false; new_block = false;
+  }
+  // advance to the next tile; false when the CTA's conformers are exhausted (and on every later call)
   __device__ __forceinline__ bool next(const DenseParams& p) {
+    new_conf = false;
+    new_block = false;
     if (++tl < nrect) return true;
-    a0 += 16;
     for (;;) {
+      a0 += 16;
       if (a0 < n) {
         m = min(16, n - a0);
         nrect = (n > a0 + 16) ? ((n - a0 - 16 + 7) >> 3) : 0;
         tl = (m >= 2) ? -1 : 0;
+        new_block = true;
         if (tl < nrect) return true;
-        a0 += 16;
         continue;
       }
-      conf += (int)gridDim.x;
-      if (conf >= p.G) return false;
-      cs = __ldg(p.seg_ptr + conf);
-      n = __ldg(p.seg_ptr + conf + 1) - cs;
-      if (n > NMAX || n <= 0) n = 0;      // not ours: skipped by every role
-      a0 = 0;
+      if (started) {
+        if (cc.valid(p)) cc.advance(p);
+      } else {
+        started = true;
+      }
+      if (!cc.valid(p)) {
+        n = 0; nrect = 0; tl = 0; a0 = 0;
+        return false;
+      }
+      n = cc.n0();
+      a0 = -16;
+      new_conf = true;
     }
   }
   __device__ __forceinline__ TileGeom geom() const { return tile_geom(n, a0, m, tl); }
@@ -744,15 +779,25 @@ __global__ void __launch_bounds__(ws::THREADS, 1) cfconv_dense_ws_kernel(const _
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int wq = warp & 3;                 // TMEM lane quarter of this warp
+  // DBG: [1536 + 4 c + {0, 1, 2}] = globaltimer (ns) at entry / after the set-up / at exit of CTA 0 (c = 0) and the last CTA
+#define WS_GSTAMP(i)                                                                                             \
+  do {                                                                                                           \
+    if (DBG && p.dbg != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {               \
+      unsigned long long gt;                                                                                     \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));                                                     \
+      p.dbg[1536 + 4 * (blockIdx.x == 0 ? 0 : 1) + (i)] = (long long)gt;                                         \
+    }                                                                                                            \
+  } while (0)
+  WS_GSTAMP(0);
 
   if (tid == 0) {
     tc::mbar_init(&bars[0], 1);
+    for (int s = 0; s < 4; ++s) tc::mbar_init(&bars[1 + s], 128);   // b1_full[set + 2 * ((k >> 1) & 1)]
     for (int s = 0; s < 2; ++s) {
-      tc::mbar_init(&bars[1 + s], 128);    // b1_full
-      tc::mbar_init(&bars[3 + s], 1);      // mma1_done
-      tc::mbar_init(&bars[5 + s], 128);    // a2_full
-      tc::mbar_init(&bars[7 + s], 1);      // mma2_done
-      tc::mbar_init(&bars[9 + s], 128);    // d2_empty
+      tc::mbar_init(&bars[5 + s], 1);      // mma1_done
+      tc::mbar_init(&bars[7 + s], 128);    // a2_full
+      tc::mbar_init(&bars[9 + s], 1);      // mma2_done
+      tc::mbar_init(&bars[11 + s], 128);   // d2_empty
     }
     tc::mbar_fence_init();
     tc::mbar_arrive_expect_tx(&bars[0], W1_BYTES + W2_BYTES);
@@ -771,34 +816,34 @@ __global__ void __launch_bounds__(ws::THREADS, 1) cfconv_dense_ws_kernel(const _
   // opaque copies: keeps ptxas from re-deriving the shared-window base inside the hot loops
   asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
   asm volatile("mov.u32 %0, %0;" : "+r"(bbase));
+  WS_GSTAMP(1);
 
-  if (warp >= ws::W_SET && warp < ws::W_MMA) {
-    // ================================ XU sets: Gaussians of tile k + 2, epilogue 1 of tile k ================================
+  if (warp < ws::W_EP2) {
+    // ================================ XU sets: Gaussians of tile k + 4, epilogue 1 of tile k ================================
     const uint32_t set = (uint32_t)(warp - ws::W_SET) >> 2;
     const int t = (tid - ws::W_SET * 32) & (PT - 1);      // pair column (Gaussians) / filter channel = TMEM lane (epilogue 1)
     const uint32_t dpair = (uint32_t)diag_i(t) | ((uint32_t)diag_j(t) << 8);
     const uint32_t aPos = sbase + ws::OFF_GEO + set * ws::GEO_BYTES, aAdj = aPos + NMAX * 12;
-    const uint32_t aB = sbase + ws::OFF_B1 + set * ws::B1_BYTES;
     const uint32_t aA = sbase + ws::OFF_A2 + set * ws::A2_BYTES;
     const uint32_t a_col = aA + (uint32_t)t * 16;                                  // a' column block of channel t
-    const uint32_t a_row = aB + (uint32_t)(t >> 3) * B1_SBO + (uint32_t)(t & 7) * 16;   // rbf row of column t
+    // rbf row of column t in B1 buffer `set` (the buffer of a tile is set + 2 * ((k >> 1) & 1))
+    const uint32_t a_row0 = sbase + ws::OFF_B1 + set * ws::B1_BYTES + (uint32_t)(t >> 3) * B1_SBO + (uint32_t)(t & 7) * 16;
     const uint32_t dtm = tm + set * TE + ((uint32_t)(wq * 32) << 16);
     const int k1steps = (p.Ng + 16) >> 4;
     const int bar_id = 1 + (int)set;
 
-    // ---- Gaussians, cutoff and direction masks of tile kr (the iterator's current tile) -> B1[set], meta ring ----
-    auto gaussians = [&](const TileIter& it, uint32_t kr) {
-      const TileGeom tg = it.geom();
+    // ---- Gaussians, cutoff and direction masks of tile kr -> its B1 buffer, meta ring ----
+    auto gaussians = [&](const TileGeom tg, int g_a0, int g_m, uint32_t kr) {
       int i_loc, j_loc;
       bool valid;
       if (tg.diag) {
-        i_loc = it.a0 + (int)(dpair & 0xffu);
-        j_loc = it.a0 + (int)(dpair >> 8);
-        valid = (t < 120) && ((int)(dpair >> 8) < it.m);
+        i_loc = g_a0 + (int)(dpair & 0xffu);
+        j_loc = g_a0 + (int)(dpair >> 8);
+        valid = (t < 120) && ((int)(dpair >> 8) < g_m);
       } else {
-        i_loc = it.a0 + (t & 15);
+        i_loc = g_a0 + (t & 15);
         j_loc = tg.j0 + (t >> 4);
-        valid = ((t & 15) < it.m) && ((t >> 4) < tg.nj);
+        valid = ((t & 15) < g_m) && ((t >> 4) < tg.nj);
       }
       bool ef = false, er = false;
       if (valid) {
@@ -811,6 +856,7 @@ __global__ void __launch_bounds__(ws::THREADS, 1) cfconv_dense_ws_kernel(const _
         er = tmp;
       }
       const uint32_t am = sbase + ws::OFF_META + (kr & (ws::MR - 1)) * ws::META_BYTES;
+      const uint32_t a_row = a_row0 + ((kr >> 1) & 1u) * (2 * ws::B1_BYTES);
       {
         const unsigned bf = __ballot_sync(0xffffffffu, ef), br = __ballot_sync(0xffffffffu, er);
         if (lane == 0) {
@@ -818,7 +864,7 @@ __global__ void __launch_bounds__(ws::THREADS, 1) cfconv_dense_ws_kernel(const _
           sts32(am + 272 + 4u * (uint32_t)wq, br);
         }
       }
-      if (t < tg.npad) {
+      if (t < tg.npad && !(DBG && (p.dbg_mode & 2))) {
         float dist = 0.0f, cval = 0.0f;
         if (ef || er) {
           const uint32_t pj = aPos + 12u * (uint32_t)j_loc, pi = aPos + 12u * (uint32_t)i_loc;
@@ -833,37 +879,35 @@ __global__ void __launch_bounds__(ws::THREADS, 1) cfconv_dense_ws_kernel(const _
           // equally spaced centres: per K-step of 16 Gaussians one anchor g_a = 2^-(u_a^2), u_a = d s - mu_a, and the two
           // neighbour ratios 2^(+-2 delta u_a - delta^2) from MUFU; the others follow by g_(k+-1) = g_k r, r *= 2^(-2 delta^2)
           // (a Gaussian more than ~5 centres from d is below f16 resolution, so an underflowing anchor costs nothing)
+#pragma unroll 1
+          for (int A = 0; A < k1steps; ++A) {
+            float v[16];
+            const float u = ds - p.mu[A * 16 + 7];
+            const float ga = tc::fast_ex2(-u * u);
+            float r = tc::fast_ex2(fmaf(p.two_delta, u, -p.delta2));
+            float sdn = tc::fast_ex2(fmaf(-p.two_delta, u, -p.delta2));
+            v[7] = ga;
+            float gu = ga, gd = ga;
 #pragma unroll
-          for (int A = 0; A < K1 / 16; ++A) {
-            if (A < k1steps) {
-              float v[16];
-              const float u = ds - p.mu[A * 16 + 7];
-              const float ga = tc::fast_ex2(-u * u);
-              float r = tc::fast_ex2(fmaf(p.two_delta, u, -p.delta2));
-              float sdn = tc::fast_ex2(fmaf(-p.two_delta, u, -p.delta2));
-              v[7] = ga;
-              float gu = ga, gd = ga;
-#pragma unroll
-              for (int i = 1; i <= 8; ++i) {
-                gu *= r;
-                v[7 + i] = gu;
-                if (i < 8) r *= p.qstep;
-              }
-#pragma unroll
-              for (int i = 1; i <= 7; ++i) {
-                gd *= sdn;
-                v[7 - i] = gd;
-                if (i < 7) sdn *= p.qstep;
-              }
-              if (A == (p.Ng >> 4)) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = (j == (p.Ng & 15)) ? 1.0f : v[j];
-              }
-              sts128(a_row + (2 * A) * 128, pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
-                     pack_f16x2(v[6], v[7]));
-              sts128(a_row + (2 * A + 1) * 128, pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]),
-                     pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
+            for (int i = 1; i <= 8; ++i) {
+              gu *= r;
+              v[7 + i] = gu;
+              if (i < 8) r *= p.qstep;
             }
+#pragma unroll
+            for (int i = 1; i <= 7; ++i) {
+              gd *= sdn;
+              v[7 - i] = gd;
+              if (i < 7) sdn *= p.qstep;
+            }
+            if (A == (p.Ng >> 4)) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = (j == (p.Ng & 15)) ? 1.0f : v[j];
+            }
+            sts128(a_row + (2 * A) * 128, pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                   pack_f16x2(v[6], v[7]));
+            sts128(a_row + (2 * A + 1) * 128, pack_f16x2(v[8], v[9]), pack_f16x2(v[10], v[11]),
+                   pack_f16x2(v[12], v[13]), pack_f16x2(v[14], v[15]));
           }
         } else {
 #pragma unroll 1
@@ -884,79 +928,60 @@ __global__ void __launch_bounds__(ws::THREADS, 1) cfconv_dense_ws_kernel(const _
         }
       }
       tc::fence_proxy_async();
-      mbar_arrive_addr(bbase + ws::BAR_B1 + 8 * set);
+      mbar_arrive_addr(bbase + ws::BAR_B1 + 8 * (set + 2 * ((kr >> 1) & 1u)));
     };
-    // positions and adjacency rows of the conformer the Gaussian iterator is in (the set's private copy)
-    int staged_conf = -1;
-    auto stage = [&](const TileIter& it) {
-      if (it.conf == staged_conf) return;
-      staged_conf = it.conf;
-      tc::named_bar_sync(bar_id, PT);      // every column of the set is done with the previous conformer
-      if (t < it.n) {
-        const float* pp = p.pos + (int64_t)(it.cs + t) * 3;
-        sts32(aPos + 12u * (uint32_t)t + 0, __float_as_uint(__ldg(pp + 0)));
-        sts32(aPos + 12u * (uint32_t)t + 4, __float_as_uint(__ldg(pp + 1)));
-        sts32(aPos + 12u * (uint32_t)t + 8, __float_as_uint(__ldg(pp + 2)));
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.adj) + it.cs + t);
-        sts128(aAdj + 16u * (uint32_t)t, a.x, a.y, a.z, a.w);
+    // positions and adjacency row of atom t of a conformer, global -> registers (issued one conformer ahead)
+    float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+    uint4 gadj = make_uint4(0u, 0u, 0u, 0u);
+    auto fetch_geometry = [&](int cs, int n) {
+      if (t < n && !(DBG && (p.dbg_mode & 8))) {
+        const float* pp = p.pos + (int64_t)(cs + t) * 3;
+        gx = __ldg(pp + 0);
+        gy = __ldg(pp + 1);
+        gz = __ldg(pp + 2);
+        gadj = __ldg(reinterpret_cast<const uint4*>(p.adj) + cs + t);
       }
-      tc::named_bar_sync(bar_id, PT);
     };
-    // advance an iterator by n tiles
-    auto advance = [&](TileIter& it, int steps) {
-      bool ok = true;
-      for (int i = 0; i < steps && ok; ++i) ok = it.next(p);
-      return ok;
-    };
-
-    TileIter itE, itR;         // epilogue-1 tile k, Gaussian tile k + 2
-    itE.start(p);
-    itR.start(p);
-    bool okE = advance(itE, 1 + (int)set);     // tile number `set`
-    bool okR = advance(itR, 1 + (int)set);
-    if (okR) {                                  // Gaussians of the set's first tile
-      stage(itR);
-      gaussians(itR, set);
-      okR = advance(itR, 2);
-    }
-    for (uint32_t k = set; okE; k += 2) {
-      // ---- epilogue 1 of tile k: a' = C (max(D1, 0) + log2(1 + 2^-|D1|) - 1) -> A2[set] (MN-major [144, pair]) ----
-      const int npad = itE.geom().npad;
+    // ---- epilogue 1 of tile k: a' = C (max(D1, 0) + log2(1 + 2^-|D1|) - 1) -> A2[set] (MN-major [144, pair]) ----
+    auto epilogue1 = [&](uint32_t k, int npad) {
       const uint32_t aC = sbase + ws::OFF_META + (k & (ws::MR - 1)) * ws::META_BYTES;
       WS_STAMP(0, k, 0);
-      mbar_wait_addr(bbase + ws::BAR_M1 + 8 * set, (k >> 1) & 1u);                        // D1[set] holds tile k
+      mbar_spin_addr(bbase + ws::BAR_M1 + 8 * set, (k >> 1) & 1u);                        // D1[set] holds tile k
       WS_STAMP(0, k, 1);
-      if (k >= 2) mbar_wait_addr(bbase + ws::BAR_M2 + 8 * set, ((k >> 1) - 1) & 1u);     // MMA2(k - 2) has read A2[set]
+      if (k >= 2) mbar_spin_addr(bbase + ws::BAR_M2 + 8 * set, ((k >> 1) - 1) & 1u);     // MMA2(k - 2) has read A2[set]
       tc::tc_fence_after();
       WS_STAMP(0, k, 2);
-      int c0 = 0;
-      for (; c0 + 32 <= npad; c0 += 32) {
-        float v[32];
-        tmem_ld32_issue(dtm + c0, v);
-        const uint4 c_a = lds128(aC + 2u * (uint32_t)c0), c_b = lds128(aC + 2u * (uint32_t)c0 + 16),
-                    c_c = lds128(aC + 2u * (uint32_t)c0 + 32), c_d = lds128(aC + 2u * (uint32_t)c0 + 48);
-        const uint32_t cw[16] = {c_a.x, c_a.y, c_a.z, c_a.w, c_b.x, c_b.y, c_b.z, c_b.w,
-                                 c_c.x, c_c.y, c_c.z, c_c.w, c_d.x, c_d.y, c_d.z, c_d.w};
-        uint32_t o[16];
-        tmem_ld32_wait(v);
-        ep1_chunk<32>(v, cw, o);
-        const uint32_t a_dst = a_col + (uint32_t)(c0 >> 3) * A2_SBO;
-        sts128(a_dst, o[0], o[1], o[2], o[3]);
-        sts128(a_dst + A2_SBO, o[4], o[5], o[6], o[7]);
-        sts128(a_dst + 2 * A2_SBO, o[8], o[9], o[10], o[11]);
-        sts128(a_dst + 3 * A2_SBO, o[12], o[13], o[14], o[15]);
-      }
-      if (c0 < npad) {   // a last 16-column chunk
-        float v[16];
-        tmem_ld16_issue(dtm + c0, v);
-        const uint4 c_a = lds128(aC + 2u * (uint32_t)c0), c_b = lds128(aC + 2u * (uint32_t)c0 + 16);
-        const uint32_t cw[8] = {c_a.x, c_a.y, c_a.z, c_a.w, c_b.x, c_b.y, c_b.z, c_b.w};
-        uint32_t o[8];
-        tmem_ld16_wait(v);
-        ep1_chunk<16>(v, cw, o);
-        const uint32_t a_dst = a_col + (uint32_t)(c0 >> 3) * A2_SBO;
-        sts128(a_dst, o[0], o[1], o[2], o[3]);
-        sts128(a_dst + A2_SBO, o[4], o[5], o[6], o[7]);
+      if (!(DBG && (p.dbg_mode & 1))) {
+        int c0 = 0;
+#pragma unroll 1
+        for (; c0 + 32 <= npad; c0 += 32) {
+          float v[32];
+          tmem_ld32_issue(dtm + c0, v);
+          const uint4 c_a = lds128(aC + 2u * (uint32_t)c0), c_b = lds128(aC + 2u * (uint32_t)c0 + 16),
+                      c_c = lds128(aC + 2u * (uint32_t)c0 + 32), c_d = lds128(aC + 2u * (uint32_t)c0 + 48);
+          const uint32_t cw[16] = {c_a.x, c_a.y, c_a.z, c_a.w, c_b.x, c_b.y, c_b.z, c_b.w,
+                                   c_c.x, c_c.y, c_c.z, c_c.w, c_d.x, c_d.y, c_d.z, c_d.w};
+          uint32_t o[16];
+          tmem_ld32_wait(v);
+          ep1_chunk<32>(v, cw, o);
+          const uint32_t a_dst = a_col + (uint32_t)(c0 >> 3) * A2_SBO;
+          sts128(a_dst, o[0], o[1], o[2], o[3]);
+          sts128(a_dst + A2_SBO, o[4], o[5], o[6], o[7]);
+          sts128(a_dst + 2 * A2_SBO, o[8], o[9], o[10], o[11]);
+          sts128(a_dst + 3 * A2_SBO, o[12], o[13], o[14], o[15]);
+        }
+        if (c0 < npad) {   // a last 16-column chunk
+          float v[16];
+          tmem_ld16_issue(dtm + c0, v);
+          const uint4 c_a = lds128(aC + 2u * (uint32_t)c0), c_b = lds128(aC + 2u * (uint32_t)c0 + 16);
+          const uint32_t cw[8] = {c_a.x, c_a.y, c_a.z, c_a.w, c_b.x, c_b.y, c_b.z, c_b.w};
+          uint32_t o[8];
+          tmem_ld16_wait(v);
+          ep1_chunk<16>(v, cw, o);
+          const uint32_t a_dst = a_col + (uint32_t)(c0 >> 3) * A2_SBO;
+          sts128(a_dst, o[0], o[1], o[2], o[3]);
+          sts128(a_dst + A2_SBO, o[4], o[5], o[6], o[7]);
+        }
       }
       // rows 128..143: row 128 = C_p (multiplies the b2 column of W2aug), rows 129..143 = 0
       for (int item = t; item < (npad >> 3) * 16; item += PT) {
@@ -969,161 +994,303 @@ __global__ void __launch_bounds__(ws::THREADS, 1) cfconv_dense_ws_kernel(const _
       tc::fence_proxy_async();
       mbar_arrive_addr(bbase + ws::BAR_A2 + 8 * set);
       WS_STAMP(0, k, 3);
-      // ---- Gaussians of tile k + 2 (B1[set] is free: its reader, MMA1(k), has completed) ----
-      if (okR) {
-        stage(itR);
-        gaussians(itR, k + 2);
-        okR = advance(itR, 2);
-      }
-      WS_STAMP(0, k, 4);
       if (DBG && p.dbg != nullptr && blockIdx.x == 0 && k < 64u && t == 0) p.dbg[(0 * 64 + k) * 8 + 7] = npad;
-      okE = advance(itE, 2);
+    };
+    // The set walks every tile of the CTA.  At its own tiles (k & 1 == set) it first runs epilogue 1 of tile k - 4 (its own
+    // tile before the previous one; that also frees the B1 buffer of tile k: MMA1(k - 4) has completed), then writes the
+    // Gaussians of tile k.  The Gaussians thus run two own tiles ahead of epilogue 1: MMA1 of the next tile is issued the
+    // moment an epilogue 1 hands D1[set] back and executes while the set is busy with Gaussians.  After the last tile the
+    // loop keeps turning until the queue of pending epilogues is empty.
+    TileWalk w;
+    w.start(p);
+    uint32_t k = 0, q0k = 0, q1k = 0;
+    int q0n = 0, q1n = 0, nq = 0;
+    int reg_conf = -1, smem_conf = -1;      // conformer whose geometry the registers / the set's shared copy hold
+    for (;;) {
+      const bool real = w.next(p);
+      if (real) {
+        if (w.new_conf && reg_conf != w.cc.conf) {      // first conformer, or the set owned no tile of the previous one
+          fetch_geometry(w.cc.cs0, w.n);
+          reg_conf = w.cc.conf;
+        }
+        if ((k & 1u) != set) {
+          ++k;
+          continue;
+        }
+      } else if (nq == 0) {
+        break;
+      }
+      if (nq == 2 || !real) {
+        epilogue1(q0k, q0n);
+        q0k = q1k;
+        q0n = q1n;
+        --nq;
+      }
+      if (real) {
+        if (smem_conf != w.cc.conf) {
+          // registers -> the set's private copy in shared memory, at the set's first own tile of the conformer
+          smem_conf = w.cc.conf;
+          tc::named_bar_sync(bar_id, PT);      // every column of the set is done with the previous conformer
+          sts32(aPos + 12u * (uint32_t)t + 0, __float_as_uint(gx));
+          sts32(aPos + 12u * (uint32_t)t + 4, __float_as_uint(gy));
+          sts32(aPos + 12u * (uint32_t)t + 8, __float_as_uint(gz));
+          sts128(aAdj + 16u * (uint32_t)t, gadj.x, gadj.y, gadj.z, gadj.w);
+          tc::named_bar_sync(bar_id, PT);
+          fetch_geometry(w.cc.cs1, w.cc.n1());      // in flight until the next conformer's first own tile
+          reg_conf = w.cc.conf + (int)gridDim.x;
+        }
+        const TileGeom tg = w.geom();
+        gaussians(tg, w.a0, w.m, k);
+        WS_STAMP(0, q0k, 4);
+        if (nq == 0) {
+          q0k = k;
+          q0n = tg.npad;
+        } else {
+          q1k = k;
+          q1n = tg.npad;
+        }
+        ++nq;
+        ++k;
+      }
     }
-  } else if (warp == ws::W_MMA) {
+  } else if (warp >= ws::W_MMA) {
     // ================================ MMA: one thread issues everything ================================
-    if (lane == 0) {
-      uint32_t k = 0;
-      mbar_wait_addr(bbase + ws::BAR_W, 0);          // weight images
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ws::REGS_MMA));
+    if (warp == ws::W_MMA && lane == 0) {
+      mbar_spin_addr(bbase + ws::BAR_W, 0);          // weight images
       const int k1steps = (p.Ng + 16) >> 4;
       const uint32_t aW1 = sbase, aW2 = sbase + W1_BYTES;
-      int np1 = 0, np2 = 0;                          // tile widths of tiles k - 1 and k - 2
-      auto issue_mma2 = [&](uint32_t j, int npad) {  // D2[j & 1] = W2aug A2[j & 1]
-        const uint32_t s = j & 1u;
-        if (j >= 2) mbar_wait_addr(bbase + ws::BAR_D2 + 8 * s, ((j >> 1) - 1) & 1u);   // EP2(j - 2) has consumed D2[s]
-        tc::tc_fence_after();
-        const uint32_t idesc2 = tc::umma_idesc_f16(F, npad, 0, 0, 1);
-        const uint32_t aA = sbase + ws::OFF_A2 + s * ws::A2_BYTES;
+      int np1 = 0, np2 = 0;                          // widths of tiles k - 1 and k - 2 (0: no such tile)
+      TileWalk w;
+      w.start(p);
+      for (uint32_t k = 0;; ++k) {
+        const bool real = w.next(p);
+        WS_STAMP(1, k, 0);
+        if (np2 > 0) {
+          // epilogue 1 of tile k - 2: A2 is complete and D1 has been read.  Its second MMA goes first: EP2 waits for D2,
+          // and the Gaussians of tile k were written long ago, so D1 of tile k follows at once
+          const uint32_t j = k - 2, s = j & 1u;
+          mbar_spin_addr(bbase + ws::BAR_A2 + 8 * s, (j >> 1) & 1u);
+          if (j >= 2) mbar_spin_addr(bbase + ws::BAR_D2 + 8 * s, ((j >> 1) - 1) & 1u);   // EP2(j - 2) has consumed D2[s]
+          tc::tc_fence_after();
+          const uint32_t idesc2 = tc::umma_idesc_f16(F, np2, 0, 0, 1);
+          const uint32_t aA = sbase + ws::OFF_A2 + s * ws::A2_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < K2 / 16; ++ks)
-          tc::umma_f16(tm + 256 + s * TE, tc::umma_smem_desc(aW2 + ks * 256, 128, A2_SBO),
-                       tc::umma_smem_desc(aA + ks * 256, 128, A2_SBO), idesc2, ks > 0);
-        umma_commit_addr(bbase + ws::BAR_M2 + 8 * s);
-      };
-      ws_tile_loop(
-          p, k, [&](int, int) {}, [&](int, int, int) {},
-          [&](const TileGeom tg, int, int, int) {
-            const uint32_t s = k & 1u;
-            WS_STAMP(1, k, 0);
-            // epilogue 1 of tile k - 2: A2[s] is complete and D1[s] has been read
-            if (k >= 2) mbar_wait_addr(bbase + ws::BAR_A2 + 8 * s, ((k >> 1) - 1) & 1u);
-            WS_STAMP(1, k, 1);
-            mbar_wait_addr(bbase + ws::BAR_B1 + 8 * s, (k >> 1) & 1u);
-            WS_STAMP(1, k, 2);
-            tc::tc_fence_after();
-            const uint32_t idesc1 = tc::umma_idesc_f16(F, tg.npad, 0, 0, 0);
-            const uint32_t aB = sbase + ws::OFF_B1 + s * ws::B1_BYTES;
-            for (int ks = 0; ks < k1steps; ++ks)
-              tc::umma_f16(tm + s * TE, tc::umma_smem_desc(aW1 + ks * 256, 128, B1_SBO),
-                           tc::umma_smem_desc(aB + ks * 256, 128, B1_SBO), idesc1, ks > 0);
-            umma_commit_addr(bbase + ws::BAR_M1 + 8 * s);
-            WS_STAMP(1, k, 3);
-            if (k >= 2) issue_mma2(k - 2, np2);
-            WS_STAMP(1, k, 4);
-            np2 = np1;
-            np1 = tg.npad;
-          },
-          [&](int, int) {});
-      // drain: the second MMA of the last two tiles
-      if (k >= 2) {
-        mbar_wait_addr(bbase + ws::BAR_A2 + 8 * (k & 1u), ((k >> 1) - 1) & 1u);
-        issue_mma2(k - 2, np2);
-      }
-      if (k >= 1) {
-        const uint32_t j = k - 1;
-        mbar_wait_addr(bbase + ws::BAR_A2 + 8 * (j & 1u), (j >> 1) & 1u);
-        issue_mma2(j, np1);
+          for (int ks = 0; ks < K2 / 16; ++ks)
+            tc::umma_f16(tm + 256 + s * TE, tc::umma_smem_desc(aW2 + ks * 256, 128, A2_SBO),
+                         tc::umma_smem_desc(aA + ks * 256, 128, A2_SBO), idesc2, ks > 0);
+          umma_commit_addr(bbase + ws::BAR_M2 + 8 * s);
+        }
+        WS_STAMP(1, k, 1);
+        int npad = 0;
+        if (real) {
+          npad = w.geom().npad;
+          const uint32_t s = k & 1u;
+          const uint32_t b = s + 2 * ((k >> 1) & 1u);       // B1 buffer of tile k: completion number k >> 2 of its barrier
+          mbar_spin_addr(bbase + ws::BAR_B1 + 8 * b, (k >> 2) & 1u);
+          WS_STAMP(1, k, 2);
+          tc::tc_fence_after();
+          const uint32_t idesc1 = tc::umma_idesc_f16(F, npad, 0, 0, 0);
+          const uint32_t aB = sbase + ws::OFF_B1 + b * ws::B1_BYTES;
+          for (int ks = 0; ks < k1steps; ++ks)
+            tc::umma_f16(tm + s * TE, tc::umma_smem_desc(aW1 + ks * 256, 128, B1_SBO),
+                         tc::umma_smem_desc(aB + ks * 256, 128, B1_SBO), idesc1, ks > 0);
+          umma_commit_addr(bbase + ws::BAR_M1 + 8 * s);
+          WS_STAMP(1, k, 3);
+        }
+        np2 = np1;
+        np1 = npad;
+        if (!real && np1 == 0 && np2 == 0) break;
       }
     }
     __syncwarp();
   } else {
     // ================================ EP2: both directions of every pair, register operands ================================
-    const int t = tid;                                                             // filter channel = TMEM lane
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ws::REGS_EP2));
+    const int t = tid - ws::W_EP2 * 32;                                            // filter channel = TMEM lane
     const uint32_t dtm0 = tm + 256 + ((uint32_t)(wq * 32) << 16);
+    const bool no_loads = DBG && (p.dbg_mode & 64);
+    // x' rows and running sums of this thread's channel.  [0..15]: the current row block; [16..23]: the atoms of the
+    // current RECT tile's columns.  Conformers of <= 32 atoms stay in these registers entirely (rows 16..31 in [16..31]):
+    // no read-modify-write of `out`, every row stored once; the second RECT tile and the second row block are brought
+    // into position with register swaps so that ONE copy of the tile code serves every case.
+    float xs[32], as[32];
+    float xn[32];                 // x' rows of the next conformer (<= 32 atoms), in flight while this one is processed
+    int xn_conf = -1;
+    int goff = 0, cn = 0, cur_a0 = 0, cur_m = 0;      // conformer in progress (cn = 0: none), row block held in [0..15]
+    bool small = false, halves_swapped = false;
     uint32_t k = 0;
-    int goff = 0;
-    float xr[16], ar[16];
-    ws_tile_loop(
-        p, k,
-        [&](int cs, int n) {
-          goff = cs * F + t;          // element offset of (first atom of the conformer, channel t) in x / out
-          // rows that later blocks add column sums to start from zero (block 0 is written once, at its end)
-          for (int a = 16; a < n; ++a) p.out[goff + a * F] = 0.0f;
-        },
-        [&](int bi, int a0, int m) {
-          // x' rows of the block and its running sums.  Block 0 starts from zero; the rows of a later block already hold
-          // the column sums the earlier blocks added to them (same thread, program order)
+    TileWalk w;
+    w.start(p);
+    for (;;) {
+      const bool real = w.next(p);
+      // ---- rows held in registers -> out: when the conformer ends, and per row block on the general path ----
+      if (cn > 0 && (!real || w.new_conf || (w.new_block && !small))) {
+        if (small) {
+          if (halves_swapped) {
 #pragma unroll
-          for (int il = 0; il < 16; ++il) {
-            xr[il] = (il < m) ? __ldg(p.x + goff + (a0 + il) * F) : 0.0f;
-            ar[il] = (bi > 0 && il < m) ? p.out[goff + (a0 + il) * F] : 0.0f;
-          }
-        },
-        [&](const TileGeom tg, int, int, int m) {
-          const uint32_t s = k & 1u;
-          const uint32_t dtm = dtm0 + s * TE;
-          // operands of a RECT tile that live in global memory: issued now, needed after the second MMA
-          float xjr[8], ojr[8];
-          if (!tg.diag) {
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              xjr[jj] = (jj < tg.nj) ? __ldg(p.x + goff + (tg.j0 + jj) * F) : 0.0f;
-              ojr[jj] = (jj < tg.nj) ? p.out[goff + (tg.j0 + jj) * F] : 0.0f;
+            for (int a = 0; a < 16; ++a) {
+              const float tmp = as[a];
+              as[a] = as[a + 16];
+              as[a + 16] = tmp;
             }
           }
-          WS_STAMP(2, k, 0);
-          mbar_wait_addr(bbase + ws::BAR_M2 + 8 * s, (k >> 1) & 1u);                 // D2[s] holds tile k
-          tc::tc_fence_after();
-          WS_STAMP(2, k, 1);
-          const uint32_t amk = sbase + ws::OFF_META + (k & (ws::MR - 1)) * ws::META_BYTES + 256;
-          uint32_t mF[4], mR[4];
-          {
-            const uint4 a = lds128(amk), b = lds128(amk + 16);
-            mF[0] = a.x; mF[1] = a.y; mF[2] = a.z; mF[3] = a.w;
-            mR[0] = b.x; mR[1] = b.y; mR[2] = b.z; mR[3] = b.w;
-          }
-          const uint32_t anyF = mF[0] | mF[1] | mF[2] | mF[3], anyR = mR[0] | mR[1] | mR[2] | mR[3];
-          const bool sym = (mF[0] == mR[0]) && (mF[1] == mR[1]) && (mF[2] == mR[2]) && (mF[3] == mR[3]);
-          if ((anyF | anyR) != 0u) {
-            if (tg.diag) {
-              if (sym)
-                diag_tile<true>(dtm, m, ar, xr, mF, mR);
-              else
-                diag_tile<false>(dtm, m, ar, xr, mF, mR);
-            } else {
-              if (sym)
-                rect_tile<0>(dtm, tg.nj, ar, xr, xjr, ojr, mF, mR);
-              else if (anyF == 0u)
-                rect_tile<1>(dtm, tg.nj, ar, xr, xjr, ojr, mF, mR);
-              else if (anyR == 0u)
-                rect_tile<2>(dtm, tg.nj, ar, xr, xjr, ojr, mF, mR);
-              else
-                rect_tile<3>(dtm, tg.nj, ar, xr, xjr, ojr, mF, mR);
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj)
-                if (jj < tg.nj) p.out[goff + (tg.j0 + jj) * F] = ojr[jj];
-            }
-          }
-          tc::tc_fence_before();
-          mbar_arrive_addr(bbase + ws::BAR_D2 + 8 * s);
-          WS_STAMP(2, k, 2);
-        },
-        [&](int a0, int m) {
-          // ---- row block finished: its own rows ----
+          for (int a = 0; a < 32; ++a)
+            if (a < cn) p.out[goff + a * F] = as[a];
+        } else {
 #pragma unroll
           for (int il = 0; il < 16; ++il)
-            if (il < m) p.out[goff + (a0 + il) * F] = ar[il];
-        });
-    // conformers above the atom limit belong to the per-edge kernel (skip_large) or are an error
-    if (!p.skip_large && t == 0 && p.status) {
-      for (int conf = blockIdx.x; conf < p.G; conf += gridDim.x)
-        if (__ldg(p.seg_ptr + conf + 1) - __ldg(p.seg_ptr + conf) > NMAX) atomicOr(p.status, CMP_STATUS_EDGE_OVERFLOW);
+            if (il < cur_m) p.out[goff + (cur_a0 + il) * F] = as[il];
+        }
+      }
+      if (!real) break;
+      const TileGeom tg = w.geom();
+      if (w.new_conf) {
+        cn = w.n;
+        goff = w.cc.cs0 * F + t;          // element offset of (first atom of the conformer, channel t) in x / out
+        small = cn <= 32;
+        halves_swapped = false;
+        if (small) {
+          if (xn_conf == w.cc.conf) {
+#pragma unroll
+            for (int a = 0; a < 32; ++a) xs[a] = xn[a];
+          } else {
+#pragma unroll
+            for (int a = 0; a < 32; ++a) xs[a] = (a < cn && !no_loads) ? __ldg(p.x + goff + a * F) : 0.0f;
+          }
+#pragma unroll
+          for (int a = 0; a < 32; ++a) as[a] = 0.0f;
+          const int nn = w.cc.n1();
+          if (nn > 0 && nn <= 32) {
+            const int goffn = w.cc.cs1 * F + t;
+#pragma unroll
+            for (int a = 0; a < 32; ++a) xn[a] = (a < nn && !no_loads) ? __ldg(p.x + goffn + a * F) : 0.0f;
+            xn_conf = w.cc.conf + (int)gridDim.x;
+          }
+        } else {
+          // rows that later blocks add column sums to start from zero (block 0 is written once, at its end)
+          for (int a = 16; a < cn; ++a) p.out[goff + a * F] = 0.0f;
+        }
+      }
+      if (w.new_block) {
+        cur_a0 = w.a0;
+        cur_m = w.m;
+        if (small) {
+          if (w.a0 == 16) {       // second row block of a small conformer: rows 16..31 -> [0..15]
+            halves_swapped = true;
+#pragma unroll
+            for (int a = 0; a < 16; ++a) {
+              float tmp = as[a];
+              as[a] = as[a + 16];
+              as[a + 16] = tmp;
+              tmp = xs[a];
+              xs[a] = xs[a + 16];
+              xs[a + 16] = tmp;
+            }
+          }
+        } else {
+          // x' rows of the block and its running sums.  Block 0 starts from zero; the rows of a later block already hold the
+          // column sums the earlier blocks added to them (same thread, program order)
+#pragma unroll
+          for (int il = 0; il < 16; ++il) {
+            xs[il] = (il < w.m && !no_loads) ? __ldg(p.x + goff + (w.a0 + il) * F) : 0.0f;
+            as[il] = (w.a0 > 0 && il < w.m && !no_loads) ? p.out[goff + (w.a0 + il) * F] : 0.0f;
+          }
+        }
+      }
+      const bool swap_cols = small && !tg.diag && w.tl == 1;      // atoms 24..31 of a small conformer -> [16..23]
+      if (swap_cols) {
+#pragma unroll
+        for (int a = 16; a < 24; ++a) {
+          float tmp = as[a];
+          as[a] = as[a + 8];
+          as[a + 8] = tmp;
+          tmp = xs[a];
+          xs[a] = xs[a + 8];
+          xs[a + 8] = tmp;
+        }
+      }
+      if (!small && !tg.diag) {
+        // operands of a RECT tile that live in global memory: issued now, needed after the second MMA
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          xs[16 + jj] = (jj < tg.nj && !no_loads) ? __ldg(p.x + goff + (tg.j0 + jj) * F) : 0.0f;
+          as[16 + jj] = (jj < tg.nj && !no_loads) ? p.out[goff + (tg.j0 + jj) * F] : 0.0f;
+        }
+      }
+      {
+        // ---- the tile: wait for D2[k & 1], read the direction masks, apply both directions, hand D2 back ----
+        float (&xr)[16] = reinterpret_cast<float (&)[16]>(xs[0]);
+        float (&ar)[16] = reinterpret_cast<float (&)[16]>(as[0]);
+        float (&xj)[8] = reinterpret_cast<float (&)[8]>(xs[16]);
+        float (&oj)[8] = reinterpret_cast<float (&)[8]>(as[16]);
+        const uint32_t s = k & 1u;
+        const uint32_t dtm = dtm0 + s * TE;
+        WS_STAMP(2, k, 0);
+        mbar_spin_addr(bbase + ws::BAR_M2 + 8 * s, (k >> 1) & 1u);                 // D2[s] holds tile k
+        tc::tc_fence_after();
+        WS_STAMP(2, k, 1);
+        const uint32_t amk = sbase + ws::OFF_META + (k & (ws::MR - 1)) * ws::META_BYTES + 256;
+        uint32_t mF[4], mR[4];
+        {
+          const uint4 a = lds128(amk), b = lds128(amk + 16);
+          mF[0] = a.x; mF[1] = a.y; mF[2] = a.z; mF[3] = a.w;
+          mR[0] = b.x; mR[1] = b.y; mR[2] = b.z; mR[3] = b.w;
+        }
+        const uint32_t anyF = mF[0] | mF[1] | mF[2] | mF[3], anyR = mR[0] | mR[1] | mR[2] | mR[3];
+        const bool sym = (mF[0] == mR[0]) && (mF[1] == mR[1]) && (mF[2] == mR[2]) && (mF[3] == mR[3]);
+        if ((anyF | anyR) != 0u && !(DBG && (p.dbg_mode & 4))) {
+          if (tg.diag) {
+            if (sym)
+              diag_tile<true>(dtm, w.m, ar, xr, mF, mR);
+            else
+              diag_tile<false>(dtm, w.m, ar, xr, mF, mR);
+          } else {
+            if (sym)
+              rect_tile<0>(dtm, tg.nj, ar, xr, xj, oj, mF, mR);
+            else
+              rect_tile<3>(dtm, tg.nj, ar, xr, xj, oj, mF, mR);
+          }
+        }
+        tc::tc_fence_before();
+        mbar_arrive_addr(bbase + ws::BAR_D2 + 8 * s);
+        WS_STAMP(2, k, 2);
+        ++k;
+      }
+      if (swap_cols) {
+#pragma unroll
+        for (int a = 16; a < 24; ++a) {
+          float tmp = as[a];
+          as[a] = as[a + 8];
+          as[a + 8] = tmp;
+          tmp = xs[a];
+          xs[a] = xs[a + 8];
+          xs[a + 8] = tmp;
+        }
+      }
+      if (!small && !tg.diag) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          if (jj < tg.nj) p.out[goff + (tg.j0 + jj) * F] = as[16 + jj];
+      }
+    }
+    // conformers without a tile: a single atom has no pair (its row is zero); above the atom limit they belong to the
+    // per-edge kernel (skip_large) or are an error
+    for (int conf = blockIdx.x; conf < p.G; conf += gridDim.x) {
+      const int cs = __ldg(p.seg_ptr + conf);
+      const int n = __ldg(p.seg_ptr + conf + 1) - cs;
+      if (n == 1) p.out[cs * F + t] = 0.0f;
+      if (n > NMAX && !p.skip_large && t == 0 && p.status) atomicOr(p.status, CMP_STATUS_EDGE_OVERFLOW);
     }
   }
 
   tc::tc_fence_before();
   __syncthreads();
+  WS_GSTAMP(2);
   if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 #undef WS_STAMP
+#undef WS_GSTAMP
 }
 
 // ---- weight images: f16, log2(e) folded into W1 / b1, ln 2 into W2 ---------------------------------------------
@@ -1198,7 +1365,7 @@ using namespace cmp;
 static int g_dense_stagger_ns = 1500, g_dense_active_pipes = NP;
 extern "C" void cmp_debug_set_dense_stagger(int ns) { g_dense_stagger_ns = ns; }
 extern "C" void cmp_debug_set_dense_pipes(int n) { g_dense_active_pipes = n; }
-static int g_dense_variant = 0;   // 0: warp-specialised (default)   1: per-pipeline kernel
+static int g_dense_variant = -1;   // -1: by max_atoms_hint (default)   0: warp-specialised   1: per-pipeline kernel
 extern "C" void cmp_debug_set_dense_variant(int v) { g_dense_variant = v; }
 static int g_dense_dbg_mode = 0;
 extern "C" void cmp_debug_set_dense_mode(int m) { g_dense_dbg_mode = m; }
@@ -1261,7 +1428,8 @@ extern "C" int cmp_cfconv_dense_pack_weights_grouped(const void* jobs, int count
 extern "C" int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int32_t* seg_ptr, const uint32_t* adj,
                                     int64_t G, const void* packed_weights, const float* offset_host, int num_gaussians,
                                     float coeff, float cutoff, int num_filters, int transposed, int skip_large,
-                                    float* out, int32_t* counter, int32_t* status, cmp_stream_t stream) {
+                                    int max_atoms_hint, float* out, int32_t* counter, int32_t* status,
+                                    cmp_stream_t stream) {
   CMP_REQUIRE(cmp_cfconv_dense_supported(num_filters, num_gaussians), CMP_EUNSUPPORTED,
               "cmp_cfconv_dense_fwd: needs num_filters == 128 and num_gaussians < 64 (got %d, %d)", num_filters,
               num_gaussians);
@@ -1290,7 +1458,9 @@ extern "C" int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int3
     }
     attr_set = true;
   }
-  const bool legacy = g_dense_variant == 1;
+  // conformers of <= 32 atoms stay in the registers of the warp-specialised kernel's EP2 group; above, its single EP2
+  // group (global read-modify-write of the column sums) is the bottleneck and the per-pipeline kernel is faster
+  const bool legacy = g_dense_variant == 1 || (g_dense_variant < 0 && !(max_atoms_hint > 0 && max_atoms_hint <= 32));
   if (legacy)   // the per-pipeline kernel pulls conformers from a work counter; the warp-specialised one walks a fixed sequence
     CMP_REQUIRE(cudaMemsetAsync(counter, 0, sizeof(int32_t), st) == cudaSuccess, CMP_ECUDA,
                 "cmp_cfconv_dense_fwd: memset failed");
@@ -1334,7 +1504,7 @@ extern "C" int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int3
   p.dbg = g_dense_dbg;
   const int grid = (int)std::min<int64_t>((G + NP - 1) / NP, sm_count());
   CMP_REQUIRE((int64_t)G * NMAX * F < ((int64_t)1 << 31) || true, CMP_EINVAL, "unreachable");
-  if (!legacy && p.dbg)
+  if (!legacy && (p.dbg || p.dbg_mode))
     cfconv_dense_ws_kernel<true><<<(int)std::min<int64_t>(G, sm_count()), ws::THREADS, ws::SMEM, st>>>(p);
   else if (!legacy)
     cfconv_dense_ws_kernel<false><<<(int)std::min<int64_t>(G, sm_count()), ws::THREADS, ws::SMEM, st>>>(p);

@@ -757,7 +757,8 @@ def _fused_aggregate(xin, graph, W, offset, coeff, cutoff, transposed):
         adj = graph.adjacency()
         call("cmp_cfconv_dense_fwd", ptr(xin), ptr(graph.pos), ptr(graph.seg_ptr), ptr(adj), graph.G,
              ptr(pack_dense_weights(*W)), ctypes.addressof(_offset_host(offset)), Ng, float(coeff), float(cutoff), F,
-             int(bool(transposed)), int(not dense_only), ptr(out), ptr(graph._counter), ptr(graph.status), work=flops)
+             int(bool(transposed)), int(not dense_only), int(graph.max_atoms or 0), ptr(out), ptr(graph._counter),
+             ptr(graph.status), work=flops)
         return out
     packed = pack_filter_weights(*W)
     pairs = FUSED_PAIR_FORWARD and graph.G > 0

@@ -256,6 +256,10 @@ int cmp_cfconv_pair_fwd(const float* x, const int32_t* seg_ptr, const int32_t* c
  *   skip_large = 1: conformers above the atom limit are left untouched (serve them with cmp_cfconv_fused_fwd on tiles
  *                   from cmp_build_tiles_min_atoms(limit + 1), issued BEFORE this call); 0: they set
  *                   CMP_STATUS_EDGE_OVERFLOW in *status.
+ *   max_atoms_hint: an upper bound of the atoms per conformer known to the caller (0 = unknown).  It only selects the
+ *                   kernel: up to 32 atoms the warp-specialised tile pipeline (cfconv_dense_ws_kernel: Gaussians + softplus
+ *                   epilogue, MMA issue and the two-direction epilogue on separate warp groups, the conformer's rows in
+ *                   registers), otherwise one pipeline of 128 threads per conformer.  Results are bit-identical.
  * Every row of `agg` that belongs to a conformer within the limit is written (zeros where an atom has no neighbour).
  * transposed = 1 exchanges the two directions of every pair (the d x' pass of the backward, x = dL/dagg). */
 int cmp_cfconv_dense_max_atoms(void);
@@ -278,7 +282,7 @@ int cmp_cfconv_dense_pack_weights_grouped(const void* jobs, int count, int num_f
 int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int32_t* seg_ptr, const uint32_t* adj,
                          int64_t G, const void* packed_weights, const float* offset_host,
                          int num_gaussians, float coeff, float cutoff, int num_filters, int transposed,
-                         int skip_large, float* agg, int32_t* counter, int32_t* status,
+                         int skip_large, int max_atoms_hint, float* agg, int32_t* counter, int32_t* status,
                          cmp_stream_t stream);
 
 /* Filter-MLP weight gradients of the fused CFConv in ONE kernel (+ a fixed-order reduction of the
@@ -502,7 +506,9 @@ void cmp_debug_set_dense_pipes(int n);
 /* Debug knob of the timestamped build of cmp_cfconv_dense_fwd: bit 0 = skip the a' stores, bit 1 = skip the cutoff loads,
  * bit 2 = skip the TMEM loads of epilogue 1 (results are then meaningless; for phase timing only). */
 void cmp_debug_set_dense_mode(int mode);
-/* Kernel variant of cmp_cfconv_dense_fwd: 0 = warp-specialised tile pipeline (default), 1 = per-pipeline kernel. */
+/* Kernel variant of cmp_cfconv_dense_fwd: -1 = by max_atoms_hint (default: the warp-specialised tile pipeline when no
+ * conformer exceeds 32 atoms - they then stay in registers -, the per-pipeline kernel otherwise), 0 = warp-specialised,
+ * 1 = per-pipeline. */
 void cmp_debug_set_dense_variant(int variant);
 /* Same for cmp_cfconv_fused_bwd_weights: 12 timestamps per tile (first 20 tiles), 240 int64. */
 void cmp_debug_set_bwd_timestamps(void* buf);

@@ -13,15 +13,22 @@ blk = cmp.InteractionBlock(128, 50, 128, 10.0).to(dev)
 gs = cmp.GaussianSmearing(0.0, 10.0, 50).to(dev)
 W = (blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight, blk.mlp[2].bias)
 x = torch.randn(b.z.numel(), 128, device=dev)
+_lib.lib().cmp_debug_set_dense_mode(int(os.environ.get("DENSE_MODE", "0")))
 with torch.no_grad():
     for _ in range(2):
         ops._fused_aggregate(x, nl, W, gs.offset, gs.coeff, 10.0, False)
-    buf = torch.zeros(3 * 64 * 8, dtype=torch.int64, device=dev)
+    buf = torch.zeros(3 * 64 * 8 + 8, dtype=torch.int64, device=dev)
     _lib.lib().cmp_debug_set_dense_timestamps(buf.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     ops._fused_aggregate(x, nl, W, gs.offset, gs.coeff, 10.0, False)
+    e1.record()
     torch.cuda.synchronize()
     _lib.lib().cmp_debug_set_dense_timestamps(None)
-t = buf.cpu().view(3, 64, 8)
+g = buf.cpu()[1536:].tolist()
+print(f"event-timed launch {e0.elapsed_time(e1) * 1e3:.1f} us | CTA 0: set-up {(g[1] - g[0]) / 1e3:.2f} us, body {(g[2] - g[1]) / 1e3:.2f} us | "
+      f"last CTA: entry +{(g[4] - g[0]) / 1e3:.2f} us, set-up {(g[5] - g[4]) / 1e3:.2f} us, body {(g[6] - g[5]) / 1e3:.2f} us, exit +{(g[6] - g[0]) / 1e3:.2f} us")
+t = buf.cpu()[:1536].view(3, 64, 8)
 base = int(t[1][0][0])
 for k in range(24):
     if t[0][k][0] == 0:
