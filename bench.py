@@ -37,10 +37,14 @@ MODEL_CFG = dict(hidden_channels=128, num_filters=128, num_interactions=6, num_g
 WORKLOAD = "cfg2_lipo_train"
 METRIC = "ConAN-SchNet conformers/sec fwd+bwd"
 UNIT = "conformers/s"
-CPU_SAMPLE_MOLECULES = 16
+CPU_SAMPLE_MOLECULES = 64            # cpu_baseline leg of our own arm: a bounded sample (about 10 s of CPU work)
+REFERENCE_BUDGET_S = 240.0           # --impl reference: the whole run (warm-up + timed steps) stays within this
 # measured once per round under ncu (never a timing source): DRAM traffic per launch at the default workload
-NCU_DRAM_BYTES_PER_LAUNCH = {"cmp_cfconv_pair_fwd": 12547584, "cmp_cfconv_fused_bwd_weights_pairs": 13398784 + 764672,
-                             "cmp_cfconv_fused_fwd": 15000000}
+# (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r02_dense_ws_kernel.metrics.csv, r01_pair_bwd_kernel.metrics.csv)
+NCU_DRAM_BYTES_PER_LAUNCH = {"cmp_cfconv_dense_fwd": 9481984, "cmp_cfconv_pair_fwd": 12547584,
+                             "cmp_cfconv_fused_bwd_weights_pairs": 13398784 + 764672, "cmp_cfconv_fused_fwd": 15000000}
+FWD_KERNELS = ("cmp_cfconv_dense_fwd", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd")
+DTYPE_FUSED = "f16 / bf16 filter-MLP operands with f32 accumulation (tcgen05), split-bf16 node linears (f32 grade), f32 elsewhere"
 
 
 def peaks():
@@ -51,6 +55,17 @@ def peaks():
                     source="measured (MEASURED_PEAKS.json)")
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0,
                 source="fallback (B200_PROFILING.md)")
+
+
+def tensor_peak(pk, clocks):
+    """The bf16 peak a kernel of this step is set against: the BURST figure when the sampled SM clock sat at its maximum
+    and the power draw stayed far below the 1 kW cap (these steps are milliseconds long and draw < 500 W; the sustained
+    figure was measured at a 1.34 GHz median under the cap), else the sustained one."""
+    burst, sus = pk["bf16_tflops"], pk["bf16_tflops_sustained"] or pk["bf16_tflops"]
+    if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks.get("power_w_max") is not None:
+        if clocks["sm_mhz"] >= 0.98 * clocks["sm_max_mhz"] and clocks["power_w_max"] < 700.0:
+            return burst, "burst bf16 (SM clock at max, %.0f W)" % clocks["power_w_max"]
+    return sus, "sustained bf16 (kernel timed inside a long step)"
 
 
 def algorithmic_flops(N, E, T=6, H=128, F=128, Ng=50, fwd_bwd=True):
@@ -156,16 +171,30 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import conan_fgw_b200 as cmp
+
     threads = os.cpu_count() or 1
-    c_mol = CPU_SAMPLE_MOLECULES
-    value, per_step = time_cpu(c_mol, max(1, args.steps), max(1, args.warmup), threads)
-    sample = (f"{c_mol} of the 128 molecules x 5 conformers x 27 atoms per step (same generator, same model); "
-              f"conformers/s scales linearly in molecules")
+    full = cmp.synthetic.CONFIGS[WORKLOAD]["num_molecules"]
+    steps, warmup = max(1, args.steps), max(1, args.warmup)
+    # the FULL batch of the workload when the whole run fits the budget (one probe step on a quarter batch decides),
+    # else the largest power-of-two fraction that does
+    probe_mol = max(1, full // 4)
+    step, _ = cpu_step_factory(probe_mol, threads)
+    step()
+    t0 = time.perf_counter()
+    step()
+    per_mol = (time.perf_counter() - t0) / probe_mol
+    c_mol = full
+    while c_mol > 8 and per_mol * c_mol * (steps + warmup) > REFERENCE_BUDGET_S:
+        c_mol //= 2
+    value, per_step = time_cpu(c_mol, steps, warmup, threads)
+    sample = (f"{c_mol} of the {full} molecules x 5 conformers x 27 atoms per step (same generator, same model)" +
+              ("" if c_mol == full else "; conformers/s scales linearly in molecules"))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_molecules": c_mol, **MODEL_CFG},
+        "config": {"workload": WORKLOAD, "sample_molecules": c_mol, "full_batch": c_mol == full, **MODEL_CFG},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -249,6 +278,86 @@ def visnet_secondary(cmp, dev, threads):
 # -----------------------------------------------------------------------------------------------
 # GPU path
 # -----------------------------------------------------------------------------------------------
+
+def measure_schnet_workload(workload, molecules, cutoff, steps, dev, world, rank, flush, pk, label, scaling=None):
+    """Another SchNet workload of BASELINE.json measured like the headline: `molecules` molecules on THIS rank, training
+    step replayed from a CUDA graph, CUDA events, max over ranks; then an eager pass with events around every launch
+    for the forward CFConv kernel's share of the tensor roofline.  Returns the entry on rank 0, None elsewhere."""
+    import torch.distributed as dist
+
+    import conan_fgw_b200 as cmp
+    from conan_fgw_b200 import _lib
+    from conan_fgw_b200.dp import RegressionStep
+
+    c = cmp.synthetic.CONFIGS[workload]
+    K, n = c["num_conformers"], c["atoms"]
+    cfg = dict(MODEL_CFG, cutoff=cutoff)
+    b = cmp.synthetic.make_batch(molecules, K, n, seed=4321 + rank).to(dev)
+    G = b.num_graphs
+    tg = torch.Generator().manual_seed(17 + rank)
+    targets = torch.randn(molecules, 1, generator=tg).to(dev)
+    torch.manual_seed(0)
+    model = cmp.SchNetNoSum(None, **cfg).to(dev).set_precision("bf16")
+    model.max_atoms_hint = n
+    trainer = RegressionStep(model, cfg["hidden_channels"] // 2, K, lr=1e-3)
+
+    def step():
+        return trainer.step(b.z, b.pos, b.batch, targets, G)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(3):
+        step()
+    trainer.capture(b.z, b.pos, b.batch, targets, G)
+    step()
+    sync_all()
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+    sync_all()
+    t = torch.tensor([sum(a.elapsed_time(z) for a, z in evs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    # forward CFConv kernel, timed per launch in an eager pass of the same step
+    graph, trainer._graph = trainer._graph, None
+    _lib.timer = _lib.KernelTimer(list(FWD_KERNELS))
+    ksteps = 3
+    for _ in range(ksteps):
+        step()
+    torch.cuda.synchronize()
+    summ = _lib.timer.summary()
+    _lib.timer = None
+    trainer._graph = graph
+    E = int(model.interaction_graph.neighbor_list(b.pos, b.batch, G).E)
+    sync_all()
+    del trainer, model
+    if rank != 0:
+        return None
+    per_edge = 2.0 * (cfg["num_gaussians"] * cfg["num_filters"] + cfg["num_filters"] ** 2)
+    top = max((k for k in FWD_KERNELS if k in summ), key=lambda k: summ[k][1], default=None)
+    fwd = None
+    if top is not None and summ[top][1] > 0:
+        n_l, k_ms, _ = summ[top]
+        ach = n_l * per_edge * E / (k_ms * 1e-3) / 1e12
+        fwd = {"kernel": top, "avg_launch_us": 1e3 * k_ms / n_l, "achieved": ach, "unit": "TFLOP/s",
+               "peak": pk["bf16_tflops"], "frac": ach / pk["bf16_tflops"], "peak_source": pk["source"] + ", burst bf16"}
+    entry = {"workload": label, "conformers_per_gpu": G, "atoms_per_conformer": n, "edges_per_gpu": E, "cutoff": cutoff,
+             "n_gpus": world, "value": world * G * steps / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / steps,
+             "steps": steps, "forward_cfconv_roofline": fwd}
+    if scaling:
+        entry["scaling"] = scaling
+    return entry
+
 
 def run_ours(args):
     import torch.distributed as dist
@@ -393,6 +502,35 @@ def run_ours(args):
     e2e_value = world * G * args.steps / (e2e_ms * 1e-3)
     h2d = sum(t.numel() * t.element_size() for t in (host.z, host.pos, host.batch, targets_h))
 
+    # BASELINE.json configs[3] / configs[4] beside the headline (same step, same measurement):
+    #   N = 1: cfg 4 full batch (256 molecules x 10 conformers x 65 atoms) and the cfg 5 per-GPU shard at both cutoffs;
+    #   N > 1: cfg 4 STRONG scaling - the 256 molecules split over the N ranks (DistributedSampler rule: 256 / N each)
+    E = int(model.interaction_graph.neighbor_list(d.pos, d.batch, G).E)
+    N = d.z.numel()
+    extra_configs = None
+    if not args.lean and WORKLOAD == "cfg2_lipo_train":
+        del trainer, model
+        pk0 = peaks()
+        extra_configs = []
+        xs = max(3, min(args.steps, 5))
+        if world == 1:
+            c4 = cmp.synthetic.CONFIGS["cfg4_bace_cls"]
+            c5 = cmp.synthetic.CONFIGS["cfg5_cov2_stress"]
+            jobs = [("cfg4_bace_cls", c4["num_molecules"], 10.0, "cfg4_bace_cls (full batch, SchNet defaults)", None),
+                    ("cfg5_cov2_stress", c5["num_molecules"] // 8, 10.0, "cfg5_cov2_stress (1/8 shard, cutoff 10 A)", None),
+                    ("cfg5_cov2_stress", c5["num_molecules"] // 8, 5.0, "cfg5_cov2_stress (1/8 shard, cutoff 5 A)", None)]
+        else:
+            c4 = cmp.synthetic.CONFIGS["cfg4_bace_cls"]
+            jobs = [("cfg4_bace_cls", c4["num_molecules"] // world, 10.0,
+                     f"cfg4_bace_cls strong scaling ({c4['num_molecules']} molecules over {world} GPUs)", "strong")]
+        for wl, mol, cut, label, sc in jobs:
+            try:
+                ent = measure_schnet_workload(wl, mol, cut, xs, dev, world, rank, flush, pk0, label, sc)
+            except Exception as exc:      # a sweep entry must never take the headline line down with it
+                ent = {"workload": label, "error": repr(exc)}
+            if rank == 0:
+                extra_configs.append(ent)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -400,9 +538,8 @@ def run_ours(args):
 
     # roofline of the dominant kernel (timed live above, on the launching stream)
     pk = peaks()
-    E = int(model.interaction_graph.neighbor_list(d.pos, d.batch, G).E)
-    N = d.z.numel()
     summ = kt.summary() if kt else {}
+    med = kt.medians() if kt else {}
     # algorithmic work of the fused kernels is known exactly from E (2*(Ng*F + F*F) FLOP per edge per
     # launch, for the forward / d x' pass and for the weight-gradient pass alike)
     per_edge = 2.0 * (MODEL_CFG["num_gaussians"] * MODEL_CFG["num_filters"] + MODEL_CFG["num_filters"] ** 2)
@@ -440,18 +577,31 @@ def run_ours(args):
         "cmp_node_gemm_dw": "node_gemm_dw_kernel (tcgen05 split-bf16 weight gradients of the node linears)",
         "cmp_node_gemm_dw_grouped": "node_gemm_dw_grouped_kernel (all node-linear weight gradients of the step in one launch)",
     }
+    peak_tf, peak_kind = tensor_peak(pk, clocks)
+    fwd_key = max((k for k in FWD_KERNELS if k in summ), key=lambda k: summ[k][1], default=None)
+    forward = None
+    if fwd_key is not None and summ[fwd_key][1] > 0 and summ[fwd_key][2] > 0:
+        f_ach = summ[fwd_key][2] / (summ[fwd_key][1] * 1e-3) / 1e12
+        forward = {"kernel": kernel_names[fwd_key], "avg_launch_us": 1e3 * summ[fwd_key][1] / summ[fwd_key][0],
+                   "achieved": f_ach, "unit": "TFLOP/s", "peak": peak_tf, "frac": f_ach / peak_tf,
+                   "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(fwd_key) if WORKLOAD == "cfg2_lipo_train" else None,
+                   "step_share": ((summ[fwd_key][1] / ksteps) / (total_ms / args.steps)) if total_ms else None}
     roofline = {
         "kernel": kernel_names[top],
         "all_timed": {k: {"launches": v[0], "ms_per_step": v[1] / ksteps, "avg_launch_us": 1e3 * v[1] / max(v[0], 1),
+                          "median_launch_us": 1e3 * med.get(k, 0.0),
                           "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None} for k, v in summ.items()},
-        "bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"],
-        "unit": "TFLOP/s", "frac": (achieved / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"])) if achieved else None,
+        "bound": "tensor", "achieved": achieved, "peak": peak_tf,
+        "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
+        # north_star's kernel (the fused CFConv forward / d x' pass), whichever kernel dominates the step
+        "forward_cfconv": forward,
         # DRAM bytes of ONE launch of the dominant kernel from the committed `ncu --set full` capture of this workload
         # (dram__bytes_read.sum + dram__bytes_write.sum); null when the dominant kernel has no capture under profiles/
         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(top) if WORKLOAD == "cfg2_lipo_train" else None,
-        "traffic_source": "profiles/r01_pair_fwd_kernel.metrics.csv, profiles/r01_pair_bwd_kernel.metrics.csv "
-                          "(ncu --set full, cfg 2; algorithmic bytes of the pair forward: x 8.8 MB + pair list 3.6 MB)",
-        "peak_source": pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+        "traffic_source": "profiles/r02_dense_ws_kernel.metrics.csv (forward), profiles/r01_pair_bwd_kernel.metrics.csv "
+                          "(weight gradients): ncu --set full, cfg 2; algorithmic bytes of the dense forward: x' 8.8 MB read "
+                          "+ positions / adjacency 0.5 MB (the 8.8 MB of agg stay in L2)",
+        "peak_source": pk["source"] + ", " + peak_kind,
         "launches_timed": n_l, "kernel_ms_per_step": k_ms / ksteps, "avg_launch_us": 1e3 * k_ms / max(n_l, 1),
         # share of the device-side step: the eager pass is launch-bound on the host, so the kernel's time per step is
         # set against the graph-replayed step (back-to-back kernels), which is what the ncu launch list also measures
@@ -478,7 +628,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.precision == "fp32" else "bf16 filter MLP / f32 elsewhere", "data": "synthetic",
+        "dtype": "f32" if args.precision == "fp32" else DTYPE_FUSED, "data": "synthetic",
         "config": {"workload": WORKLOAD, "precision": args.precision, "molecules_per_gpu": B, "conformers_per_molecule": K, "atoms_per_conformer": n,
                    "conformers_per_gpu": G, "atoms": N, "edges": E, **MODEL_CFG, "max_num_neighbors": 32,
                    "step": "radius graph + fwd + MSE + bwd + grad all-reduce (N>1) + Adam",
@@ -488,7 +638,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
-        "other_mode": other_mode, "visnet": visnet,
+        "other_mode": other_mode, "visnet": visnet, "configs": extra_configs,
         "tolerance": {"fp32": "1e-5 relative vs oracle (tests/test_gpu_schnet.py)",
                       "bf16": "5e-3 relative on embeddings, 2e-2 on gradients vs oracle (tests/test_gpu_fused.py)"},
     }

@@ -232,6 +232,13 @@ class KernelTimer:
             out[name] = (n + 1, ms + e0.elapsed_time(e1), w + float(work))
         return out
 
+    def medians(self):
+        """{name: median launch duration in ms} - call after a device synchronise."""
+        per = {}
+        for name, e0, e1, _ in self.records:
+            per.setdefault(name, []).append(e0.elapsed_time(e1))
+        return {k: sorted(v)[len(v) // 2] for k, v in per.items()}
+
 
 timer: "KernelTimer | None" = None
 
