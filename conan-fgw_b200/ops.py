@@ -194,6 +194,23 @@ def _prepack(modules, dense_only=False):
                 packed = torch.empty(n_norm + n_tr, dtype=torch.uint8, device=m.weight.device)
                 cache[m.weight.data_ptr()] = (packed[:n_norm], packed[n_norm:])
                 node.append((_f32c(m.weight.detach()), rows, cols, packed))
+            elif isinstance(m, Linear) and m.tc and m.weight.is_cuda and m.weight.data_ptr() not in skip and \
+                    m.weight.shape[0] > 128 and m.weight.shape[1] <= 128 and m.weight.is_contiguous() and \
+                    m.weight.dtype == torch.float32:
+                # a layer wider than the kernel (ViSNet: H -> 2H / 3H): its 128-row blocks are contiguous [nb, K]
+                # matrices, so every block gets the image of W_b (forward) and of W_b^T (dX) from the same grouped launch
+                rows, cols = m.weight.shape
+                w = m.weight.detach()
+                for n0 in range(0, rows, 128):
+                    nb = min(128, rows - n0)
+                    blk = w[n0:n0 + nb]
+                    if blk.data_ptr() in cache or not bool(_lib.lib().cmp_node_gemm_tc_supported(cols, nb)):
+                        continue
+                    n_norm = _lib.size_query("cmp_node_gemm_weight_bytes", cols)
+                    n_tr = _lib.size_query("cmp_node_gemm_weight_bytes", nb)
+                    packed = torch.empty(n_norm + n_tr, dtype=torch.uint8, device=w.device)
+                    cache[blk.data_ptr()] = (packed[:n_norm], packed[n_norm:])
+                    node.append((blk, nb, cols, packed))
     for lo in range(0, len(node), gmax):
         chunk = node[lo:lo + gmax]
         arr = (_lib.PackNodeJob * len(chunk))()
@@ -263,7 +280,8 @@ def _node_gemm(x2, w_img, K, Nout, bias=None, act=ACT_NONE, residual=None, saved
 def _tc_matmul_blocked(x2, W, bias=None, residual=None, saved_y=None):
     """y[M, Nout] = x2'[M, K] @ W[Nout, K]^T + bias + residual for any K, Nout that are multiples of 16, as a sequence
     of <=128 x <=128 blocks of the tcgen05 node kernel: column blocks of the output are independent launches, K blocks
-    are chained through the kernel's residual input (no activation: callers apply it separately)."""
+    are chained through the kernel's residual input (no activation: callers apply it separately).  Row blocks of a
+    contiguous W with K <= 128 take their image from the prepack cache when a training step opened one."""
     M, K = x2.shape
     Nout = W.shape[0]
     y = torch.empty(M, Nout, dtype=torch.float32, device=x2.device)
@@ -272,7 +290,9 @@ def _tc_matmul_blocked(x2, W, bias=None, residual=None, saved_y=None):
         nb = min(128, Nout - n0)
         for bi, k0 in enumerate(range(0, K, 128)):
             kb = min(128, K - k0)
-            img = _pack_node_weight(W[n0:n0 + nb, k0:k0 + kb].contiguous(), False)
+            blk = W[n0:n0 + nb, k0:k0 + kb]
+            hit = _cached_images(blk) if (K <= 128 and blk.is_contiguous()) else None
+            img = hit[0] if hit is not None else _pack_node_weight(blk.contiguous(), False)
             first = bi == 0
             if first:
                 res_ptr = residual.data_ptr() + n0 * f4 if residual is not None else None
@@ -284,6 +304,26 @@ def _tc_matmul_blocked(x2, W, bias=None, residual=None, saved_y=None):
             call("cmp_node_gemm_fwd", x2.data_ptr() + k0 * f4, K, sy_ptr, K if saved_y is not None else 0, ptr(img),
                  b_ptr, ACT_NONE, res_ptr, ldr, y.data_ptr() + n0 * f4, Nout, M, kb, nb, work=2.0 * M * kb * nb)
     return y
+
+
+def _tc_dx_blocked(dy2, W):
+    """dX[M, K] = dY[M, Nout] @ W[Nout, K] for a wide layer: the row blocks W_b of W are the K blocks of this product,
+    chained through the kernel's residual input; their W_b^T images come from the prepack cache when there is one
+    (else the transposed weight is materialised and packed block by block as before)."""
+    M, Nout = dy2.shape
+    K = W.shape[1]
+    if not (K <= 128 and W.is_contiguous() and _cached_images(W[0:min(128, Nout)]) is not None):
+        return _tc_matmul_blocked(dy2, W.t().contiguous())
+    dx = torch.empty(M, K, dtype=torch.float32, device=dy2.device)
+    f4 = 4
+    for bi, n0 in enumerate(range(0, Nout, 128)):
+        nb = min(128, Nout - n0)
+        hit = _cached_images(W[n0:n0 + nb])
+        img = hit[1] if hit is not None else _pack_node_weight(W[n0:n0 + nb].contiguous(), True)
+        res_ptr, ldr = (None, 0) if bi == 0 else (dx.data_ptr(), K)
+        call("cmp_node_gemm_fwd", dy2.data_ptr() + n0 * f4, Nout, None, 0, ptr(img), None, ACT_NONE, res_ptr, ldr,
+             dx.data_ptr(), K, M, nb, K, work=2.0 * M * nb * K)
+    return dx
 
 
 def _tc_dw_blocked(dy2, saved_y, x2, want_db, param=None):
@@ -347,7 +387,7 @@ class _LinearTCBlockedFn(Function):
         dy2 = _f32c(dy.reshape(-1, Nout))
         dx = dw = db = dres = None
         if ctx.needs_input_grad[0]:
-            dx = _tc_matmul_blocked(dy2, weight.t().contiguous()).reshape(*ctx.lead, K)
+            dx = _tc_dx_blocked(dy2, weight).reshape(*ctx.lead, K)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw, db = _tc_dw_blocked(dy2, None, x2, ctx.has_bias, param=weight if ctx.needs_input_grad[1] else None)
         if ctx.has_res and ctx.needs_input_grad[3]:
