@@ -22,6 +22,15 @@ def _need_sm100():
         pytest.skip("tcgen05 kernels need an sm_100 device")
 
 
+@pytest.fixture(params=[-1, 0, 1], ids=["auto", "warp-specialised", "per-pipeline"])
+def variant(request):
+    """Both kernels behind cmp_cfconv_dense_fwd serve every conformer size (the default picks one by max_atoms_hint):
+    the warp-specialised tile pipeline (registers-only path up to 32 atoms, general path above) and the per-pipeline one."""
+    cmp._lib.lib().cmp_debug_set_dense_variant(request.param)
+    yield request.param
+    cmp._lib.lib().cmp_debug_set_dense_variant(-1)
+
+
 def _block(cutoff, seed=0):
     torch.manual_seed(seed)
     blk = cmp.InteractionBlock(128, NG, F, cutoff).to(DEV)
@@ -58,7 +67,7 @@ def _dense(blk, gs, nl, x, cutoff, transposed):
     (100, 1, 2, 10.0, 32), (128, 1, 1, 10.0, 32),
     (40, 2, 2, 10.0, 8),      # hard truncation: mostly one-directional pairs
 ])
-def test_dense_kernel_matches_exact_message_path(n, B, K, cutoff, max_nb):
+def test_dense_kernel_matches_exact_message_path(n, B, K, cutoff, max_nb, variant):
     _need_sm100()
     b = syn.make_batch(B, K, n, seed=n).to(DEV)
     nl = cmp.build_neighbor_list(b.pos, b.batch, cutoff, max_nb, max_atoms=n)
@@ -78,10 +87,10 @@ def test_dense_kernel_matches_exact_message_path(n, B, K, cutoff, max_nb):
         assert torch.equal(got, _dense(blk, gs, nl, xp, cutoff, False))
 
 
-def test_ragged_batch_and_isolated_atoms():
+def test_ragged_batch_and_isolated_atoms(variant):
     """Conformers of different sizes in one batch, single-atom conformers and atoms without any neighbour."""
     _need_sm100()
-    sizes = [1, 27, 5, 64, 1, 33, 18, 2]
+    sizes = [1, 27, 5, 64, 1, 33, 18, 2, 17, 32, 1]
     torch.manual_seed(0)
     pos, batch = [], []
     for g, n in enumerate(sizes):
@@ -98,10 +107,13 @@ def test_ragged_batch_and_isolated_atoms():
     got = _dense(blk, gs, nl, xp, 10.0, False)
     assert rel_err(got, want) < TOL
     iso = (nl.rowptr[1:] == nl.rowptr[:-1]).nonzero().flatten()
-    assert iso.numel() >= 3 and bool((got[iso] == 0).all())
+    assert iso.numel() >= 4 and bool((got[iso] == 0).all())
+    # both kernels produce the same bits
+    cmp._lib.lib().cmp_debug_set_dense_variant(1 if variant != 1 else 0)
+    assert torch.equal(got, _dense(blk, gs, nl, xp, 10.0, False))
 
 
-def test_conformers_above_the_dense_limit_use_the_per_edge_kernel():
+def test_conformers_above_the_dense_limit_use_the_per_edge_kernel(variant):
     _need_sm100()
     sizes = [140, 20, 131]
     pos = torch.cat([syn.make_batch(1, 1, n, seed=n).pos for n in sizes]).to(DEV)
