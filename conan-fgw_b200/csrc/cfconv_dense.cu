@@ -765,6 +765,9 @@ struct TileWalk {
 };
 
 // DBG: clock64 timeline of CTA 0 in p.dbg: [role 0 = XU sets, 1 = MMA, 2 = EP2][tile < 64][8 stamps]
+//   XU set:  0 epilogue 1 starts waiting for D1, 1 D1 there, 2 A2 free, 3 a2_full signalled, 6 staging, 5 Gaussians start,
+//            4 b1_full signalled, 7 = tile width;   MMA: 0 iteration start, 1 second MMA of tile k - 2 issued, 2 B1 of tile k
+//            there, 3 first MMA issued;   EP2: 0 waiting for D2, 1 D2 there, 2 d2_empty signalled
 template <bool DBG>
 __global__ void __launch_bounds__(ws::THREADS, 1) cfconv_dense_ws_kernel(const __grid_constant__ DenseParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -1027,6 +1030,7 @@ __global__ void __launch_bounds__(ws::THREADS, 1) cfconv_dense_ws_kernel(const _
         --nq;
       }
       if (real) {
+        WS_STAMP(0, k, 6);
         if (smem_conf != w.cc.conf) {
           // registers -> the set's private copy in shared memory, at the set's first own tile of the conformer
           smem_conf = w.cc.conf;
@@ -1040,8 +1044,9 @@ __global__ void __launch_bounds__(ws::THREADS, 1) cfconv_dense_ws_kernel(const _
           reg_conf = w.cc.conf + (int)gridDim.x;
         }
         const TileGeom tg = w.geom();
+        WS_STAMP(0, k, 5);
         gaussians(tg, w.a0, w.m, k);
-        WS_STAMP(0, q0k, 4);
+        WS_STAMP(0, k, 4);
         if (nq == 0) {
           q0k = k;
           q0n = tg.npad;

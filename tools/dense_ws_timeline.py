@@ -30,11 +30,13 @@ print(f"event-timed launch {e0.elapsed_time(e1) * 1e3:.1f} us | CTA 0: set-up {(
       f"last CTA: entry +{(g[4] - g[0]) / 1e3:.2f} us, set-up {(g[5] - g[4]) / 1e3:.2f} us, body {(g[6] - g[5]) / 1e3:.2f} us, exit +{(g[6] - g[0]) / 1e3:.2f} us")
 t = buf.cpu()[:1536].view(3, 64, 8)
 base = int(t[1][0][0])
-for k in range(24):
-    if t[0][k][0] == 0:
+r = lambda v: int(v) - base
+print("cycles relative to the MMA thread's start; tile k is served by XU set k & 1")
+for k in range(40):
+    if t[0][k][5] == 0:
         break
     s, m, e = t[0][k], t[1][k], t[2][k]
-    r = lambda v: int(v) - base
-    print(f"k={k:2d} npad={int(s[7]):3d} | XU set {k & 1}: wait D1 {r(s[0])}->{r(s[1])} A2free {r(s[2])} ep1 done {r(s[3])} (ep1 {int(s[3]-s[2])}) gauss done {r(s[4])} (rbf {int(s[4]-s[3])})"
-          f" | MMA: start {r(m[0])} a2 {r(m[1])} b1 {r(m[2])} mma1 issued {r(m[3])} mma2 issued {r(m[4])}"
-          f" | EP2: ready {r(e[0])} D2 {r(e[1])} done {r(e[2])} (ep2 {int(e[2]-e[1])})")
+    print(f"k={k:2d} npad={int(s[7]):3d} | Gaussians {r(s[6])} (stage) {r(s[5])} -> {r(s[4])} ({int(s[4] - s[5])}) | MMA1 issued {r(m[3])} | "
+          f"epilogue 1: waits from {r(s[0])}, D1 at {r(s[1])}, A2 free {r(s[2])}, done {r(s[3])} ({int(s[3] - s[2])}) | "
+          f"MMA2 issued {r(t[1][k + 2][1]) if k + 2 < 64 and t[1][k + 2][1] else '-'} | "
+          f"EP2: waits from {r(e[0])}, D2 at {r(e[1])}, done {r(e[2])} ({int(e[2] - e[1])})")
