@@ -267,7 +267,17 @@ def visnet_secondary(cmp, dev, threads):
     t0 = time.perf_counter()
     cpu_step()
     cpu_s = time.perf_counter() - t0
+    # HBM roofline of the step (per layer at least 2 H 4 bytes per edge for f_ij read + write and 2 x 4H x 4
+    # bytes per atom for x / vec; backward = 2 x forward): this workload (2 880 atoms, 42 K edges) is launch-latency bound
+    Hh, T = 128, 6
+    alg_bytes = 3.0 * T * (E * 2 * Hh * 4 + d.z.numel() * 8 * Hh * 4)
+    pk = peaks()
+    vis_roofline = {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": alg_bytes / (ms * 1e-3) / 1e9 / pk["hbm_gbs"], "algorithmic_bytes_per_step": alg_bytes,
+                    "traffic": None, "peak_source": pk["source"],
+                    "note": "whole step, CUDA-graph replay; ~900 small launches per step: latency bound, not HBM bound"}
     return {"workload": "cfg3_freesolv_visnet", "metric": "ConAN-ViSNet conformers/sec fwd+bwd", "value": G / (ms * 1e-3),
+            "roofline": vis_roofline,
             "unit": UNIT, "ms_per_step": ms, "eager_ms_per_step": eager_ms,
             "dtype": "f32 (Linears: split-bf16 tcgen05, ~2e-5)", "cuda_graph": graphed,
             "edges": E,

@@ -242,6 +242,26 @@ class KernelTimer:
 
 timer: "KernelTimer | None" = None
 
+# NVTX ranges around the phases of a step (radius graph + forward, backward, gradient all-reduce, Adam) and around every
+# interaction block: off by default (a range costs a few hundred ns on the launching thread); CMP_NVTX=1 turns them on
+# for nsys / ncu --nvtx timelines.
+NVTX = os.environ.get("CMP_NVTX", "0") not in ("", "0")
+
+
+class nvtx_range:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
+
 
 def call(name, *args, work=0.0):
     """Invoke an int-returning entry point on the current stream; raise on a non-zero code.

@@ -14,7 +14,7 @@ from typing import List, Optional
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import _lib, ops
 
 
 def shard_molecules(num_molecules: int, rank: int, world_size: int) -> List[int]:
@@ -118,10 +118,11 @@ class RegressionStep:
         # weights only change in adam(): every tensor-core weight image of this step is packed up front, grouped
         hint = getattr(self.backbone, "max_atoms_hint", None)
         with ops.prepacked_weights([self.backbone, self.head], dense_only=hint is not None and hint <= 128):
-            loss = self.loss(z, pos, batch, targets, num_graphs)
+            with _lib.nvtx_range("cmp/forward"):
+                loss = self.loss(z, pos, batch, targets, num_graphs)
             # parameter gradients are None here and every parameter is used once: the node-linear weight gradients
             # can be queued during backward and issued as ONE grouped launch at its end
-            with ops.deferred_weight_grads(self.flat.params):
+            with _lib.nvtx_range("cmp/backward"), ops.deferred_weight_grads(self.flat.params):
                 loss.backward()
         self.flat.collect_grads()
         return loss.detach()
@@ -162,6 +163,8 @@ class RegressionStep:
             loss = self._static_loss
         else:
             loss = self._fwd_bwd(z, pos, batch, targets, num_graphs)
-        world = self.flat.all_reduce(self.group)
-        self.flat.adam(lr=self.lr, grad_scale=1.0 / world)
+        with _lib.nvtx_range("cmp/grad_allreduce"):
+            world = self.flat.all_reduce(self.group)
+        with _lib.nvtx_range("cmp/adam"):
+            self.flat.adam(lr=self.lr, grad_scale=1.0 / world)
         return loss

@@ -17,10 +17,14 @@ for n, B, K in ((9, 2, 2), (27, 2, 1), (40, 1, 2)):
         if prec == "bf16" and not cmp._lib.lib().cmp_device_is_sm100():
             continue
         m.set_precision(prec)
-        m.zero_grad()
-        out = m(b.z, b.pos, b.batch, num_graphs=b.num_graphs)
-        out.pow(2).mean().backward()
-        m.check_status()
+        # both kernels behind cmp_cfconv_dense_fwd: 0 = warp-specialised tile pipeline, 1 = per-pipeline
+        for variant in ((0, 1) if prec == "bf16" else (-1,)):
+            cmp._lib.lib().cmp_debug_set_dense_variant(variant)
+            m.zero_grad()
+            out = m(b.z, b.pos, b.batch, num_graphs=b.num_graphs)
+            out.pow(2).mean().backward()
+            m.check_status()
+        cmp._lib.lib().cmp_debug_set_dense_variant(-1)
     print(f"schnet n={n}: ok", flush=True)
 v = cmp.ViSNet(None, hidden_channels=32).to(dev)
 b = syn.make_batch(2, 2, 8, seed=3).to(dev)
