@@ -56,6 +56,16 @@ def test_baseline_shape_cfg1_forward_and_gradients():
     compare(o, c, syn.make_config_batch("cfg1_esol_fwd", scale=0.25))
 
 
+def test_baseline_shape_cfg1_full_size_forward():
+    # the whole cfg 1 batch (160 conformers, 4 160 atoms, 104 K edges) forward against the CPU oracle
+    o, c = pair(2)
+    b = syn.make_config_batch("cfg1_esol_fwd")
+    with torch.no_grad():
+        want = o(b.z, b.pos, b.batch)
+        got = c(b.z.to(DEV), b.pos.to(DEV), b.batch.to(DEV))
+    assert got.shape == want.shape and rel_err(got, want) < 1e-5
+
+
 def test_conan_regression_shape_and_truncated_graph():
     # ConAN's own instantiation (common.py:524-529): T=3; 65-atom conformers truncate at 32/33 neighbours
     o, c = pair(3, num_interactions=3)

@@ -36,7 +36,8 @@ def test_golden_from_reference_file_forward_and_gradients():
         assert rel_err(params[k].grad, ref) < 5e-5, k
 
 
-@pytest.mark.parametrize("B,K,n,H,L", [(4, 2, 18, 128, 6), (2, 2, 40, 64, 3), (3, 1, 5, 32, 2)])
+@pytest.mark.parametrize("B,K,n,H,L", [(4, 2, 18, 128, 6), (2, 2, 40, 64, 3), (3, 1, 5, 32, 2),
+                                        (2, 2, 14, 512, 2)])       # the classification width (common.py:513-522)
 def test_conan_wrapper_vs_oracle(B, K, n, H, L):
     torch.manual_seed(B + n)
     o = ov.ViSNet(None, hidden_channels=H, num_layers=L)
@@ -111,8 +112,18 @@ def test_tensor_core_linears_mode():
     for k in po:
         if po[k].grad is not None:
             assert rel_err(pc[k].grad, po[k].grad) < 2e-3, k
-    # wide / blocked linear against fp64 directly
+    # the same step inside prepacked_weights (what dp.RegressionStep does): the block images of the wide Linears come from
+    # the grouped pack, dX is chained over the row blocks with the cached transposed images - identical numbers
     from conan_fgw_b200 import ops
+    ref_grads = {k: p.grad.clone() for k, p in pc.items() if p.grad is not None}
+    c.zero_grad()
+    with ops.prepacked_weights([c]):
+        out_p = c(b.z.to(DEV), b.pos.to(DEV), b.batch.to(DEV))
+        out_p.pow(2).mean().backward()
+    assert torch.equal(out_p, out_c)
+    for k, g_ref in ref_grads.items():
+        assert rel_err(pc[k].grad, g_ref) < 1e-6, k
+    # wide / blocked linear against fp64 directly
     x = torch.randn(500, 256, device=DEV, requires_grad=True)
     w = (torch.randn(384, 256, device=DEV) / 16).requires_grad_(True)
     bias = torch.randn(384, device=DEV, requires_grad=True)
