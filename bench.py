@@ -41,7 +41,7 @@ CPU_SAMPLE_MOLECULES = 64            # cpu_baseline leg of our own arm: a bounde
 REFERENCE_BUDGET_S = 240.0           # --impl reference: the whole run (warm-up + timed steps) stays within this
 # measured once per round under ncu (never a timing source): DRAM traffic per launch at the default workload
 # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r02_dense_ws_kernel.metrics.csv, r01_pair_bwd_kernel.metrics.csv)
-NCU_DRAM_BYTES_PER_LAUNCH = {"cmp_cfconv_dense_fwd": 9481984, "cmp_cfconv_pair_fwd": 12547584,
+NCU_DRAM_BYTES_PER_LAUNCH = {"cmp_cfconv_dense_fwd": 9481984, "cmp_cfconv_dense_bwd_weights": None, "cmp_cfconv_pair_fwd": 12547584,
                              "cmp_cfconv_fused_bwd_weights_pairs": 13398784 + 764672, "cmp_cfconv_fused_fwd": 15000000}
 FWD_KERNELS = ("cmp_cfconv_dense_fwd", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd")
 DTYPE_FUSED = "f16 / bf16 filter-MLP operands with f32 accumulation (tcgen05), split-bf16 node linears (f32 grade), f32 elsewhere"
@@ -482,7 +482,7 @@ def run_ours(args):
         resident_step()      # identical on every rank (each step holds a collective)
     torch.cuda.synchronize()
     dominant = ["cmp_gemm_f32", "cmp_cfconv_dense_fwd", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd", "cmp_cfconv_fused_bwd_weights",
-                "cmp_cfconv_fused_bwd_weights_pairs", "cmp_node_gemm_dw_grouped", "cmp_node_gemm_fwd",
+                "cmp_cfconv_fused_bwd_weights_pairs", "cmp_cfconv_dense_bwd_weights", "cmp_node_gemm_dw_grouped", "cmp_node_gemm_fwd",
                 "cmp_node_gemm_dw", "cmp_node_chain_fwd"]
     total_ms, launches, kt = timed(resident_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
@@ -554,7 +554,7 @@ def run_ours(args):
     # launch, for the forward / d x' pass and for the weight-gradient pass alike)
     per_edge = 2.0 * (MODEL_CFG["num_gaussians"] * MODEL_CFG["num_filters"] + MODEL_CFG["num_filters"] ** 2)
     for k in ("cmp_cfconv_dense_fwd", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd", "cmp_cfconv_fused_bwd_weights",
-              "cmp_cfconv_fused_bwd_weights_pairs"):
+              "cmp_cfconv_fused_bwd_weights_pairs", "cmp_cfconv_dense_bwd_weights"):
         if k in summ:
             # with the pair kernel active the per-edge forward kernel only zero-fills and serves conformers of more
             # than 30 atoms (none in this workload): no algorithmic work is booked on it
@@ -581,6 +581,9 @@ def run_ours(args):
         "cmp_cfconv_fused_bwd_weights": "cfconv_fused_bwd_kernel (tcgen05: recompute + dW accumulated in TMEM, K = edges)",
         "cmp_cfconv_fused_bwd_weights_pairs": "cfconv_fused_bwd_kernel<pairs> (tcgen05: one column per undirected pair, "
                                               "dW accumulated in TMEM; algorithmic FLOPs counted per directed edge)",
+        "cmp_cfconv_dense_bwd_weights": "cfconv_dense_bwd_kernel (tcgen05: filter-MLP weight gradients over the dense atom blocks, "
+                                        "dF from fp32 rows of g and x' in registers, dW accumulated in TMEM; algorithmic FLOPs "
+                                        "counted per directed edge)",
         "cmp_node_gemm_fwd": "node_gemm_fwd_kernel (tcgen05 split-bf16 node linears)",
         "cmp_node_chain_fwd": "node_chain_kernel (tcgen05 split-bf16: lin2 -> ssp -> lin (+ h) -> next lin1 of an interaction "
                               "block chained on chip, and its backward)",

@@ -674,6 +674,578 @@ __global__ void flat_tiles_fill_kernel(const int32_t* __restrict__ conf_edge_ptr
   }
 }
 
+
+// =================================================================================================================
+// Dense-block weight gradients (conformers of <= 128 atoms): same phases, columns = the pairs of 16 x 16 atom blocks
+// =================================================================================================================
+// cfconv_fused_bwd_kernel<pairs> reads a pair list: per column and channel four gathers from bf16 copies of g and x'
+// staged per conformer (two extra conversion launches per layer), plus per-column metadata.  Here the columns of a tile
+// are the pairs of the dense blocks of cfconv_dense.cu, cut into tiles of 64: DIAG(b) columns [0, 64) and [64, 120),
+// RECT(b, j0) = block b x 4 later atoms.  The pair of a column is a compile-time function of its index, so the thread
+// that owns channel f keeps g[16 rows][f] and x'[16 rows][f] of the row block in fp32 registers and builds
+//     dF[f, (i, j)] = [j -> i] g[i] x'[j] + [i -> j] g[j] x'[i]
+// with two multiply-adds per column - no gathers, no staging, no bf16 copies (the products are rounded once, to the
+// bf16 dF image).  Distances come from the positions, the two directions of a pair from the adjacency bit matrix
+// (cmp_build_adjacency).  Everything after dF (the MMAs, epilogues 1 and 3, TMEM accumulators, partial sums) is the
+// pipeline of cfconv_fused_bwd_kernel.
+constexpr int DN_MAX = 128;        // atoms per conformer
+constexpr int DN_AW = 4;           // adjacency words per atom
+constexpr uint32_t D_OFF_A = R_BYTES;
+constexpr uint32_t D_OFF_F = D_OFF_A + CH_BYTES;
+constexpr uint32_t D_OFF_S = D_OFF_F + CH_BYTES;
+constexpr uint32_t D_OFF_POS = D_OFF_S + CH_BYTES;                 // float[128][3]
+constexpr uint32_t D_OFF_ADJ = D_OFF_POS + DN_MAX * 12;            // uint32[128][4]
+constexpr uint32_t D_OFF_C = D_OFF_ADJ + DN_MAX * DN_AW * 4;       // float[64]
+constexpr uint32_t D_OFF_MASK = D_OFF_C + TE * 4;                  // uint32[4]: [j -> i] of columns 0..31, 32..63; [i -> j] likewise
+constexpr uint32_t D_GROUP_BYTES = (D_OFF_MASK + 16 + 127) / 128 * 128;
+constexpr uint32_t D_SMEM_BYTES = W1_BYTES + W2T_BYTES + NG * D_GROUP_BYTES;
+
+// column c of the DIAG pairs of a block holds (il, jl), il < jl, c = jl (jl - 1) / 2 + il
+__host__ __device__ constexpr int dg_j(int c) {
+  return 1 + (c >= 1) + (c >= 3) + (c >= 6) + (c >= 10) + (c >= 15) + (c >= 21) + (c >= 28) + (c >= 36) + (c >= 45) +
+         (c >= 55) + (c >= 66) + (c >= 78) + (c >= 91) + (c >= 105);
+}
+__host__ __device__ constexpr int dg_i(int c) { return c - dg_j(c) * (dg_j(c) - 1) / 2; }
+
+__host__ __device__ inline int dense_block_tiles(int n, int a0) {
+  const int m = (n - a0) < 16 ? (n - a0) : 16;
+  const int nd = m * (m - 1) / 2;
+  const int rest = n - a0 - 16;
+  return (nd > 0) + (nd > 64) + (rest > 0 ? (rest + 3) / 4 : 0);
+}
+__host__ __device__ inline int dense_conf_tiles(int n) {
+  if (n > DN_MAX || n <= 0) return 0;
+  int t = 0;
+  for (int a0 = 0; a0 < n; a0 += 16) t += dense_block_tiles(n, a0);
+  return t;
+}
+
+// tile_ptr[g] = tiles of the conformers before g (single block; G is at most a few 10^4 conformers per GPU)
+__global__ void dense_tile_ptr_kernel(const int32_t* __restrict__ seg_ptr, int64_t G, int32_t* __restrict__ ptr,
+                                      int* status) {
+  __shared__ int carry;
+  __shared__ int buf[256];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < G; base += blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    int v = 0;
+    if (i < G) {
+      const int n = seg_ptr[i + 1] - seg_ptr[i];
+      if (n > DN_MAX && status) atomicOr(status, CMP_STATUS_EDGE_OVERFLOW);
+      v = dense_conf_tiles(n);
+    }
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+      const int t = (threadIdx.x >= o) ? buf[threadIdx.x - o] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < G) ptr[i] = carry + buf[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 255) carry += buf[255];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ptr[G] = carry;
+}
+
+struct DenseBwdParams {
+  const float* g;                 // [N, F] dL/dagg (fp32)
+  const float* xprime;            // [N, F] x' (fp32)
+  const float* pos;               // [N, 3]
+  const int32_t* seg_ptr;         // [G + 1]
+  const uint32_t* adj;            // [N, 4]
+  const int32_t* tile_ptr;        // [G + 1]
+  const uint8_t* weights;         // W1aug image | W2^T image (cmp_cfconv_tc_pack_bwd_weights)
+  const float* offset;
+  float* partial;                 // [gridDim.x * NG][PART_FLOATS]
+  float coeff_log2e;
+  float cutoff;
+  int Ng;
+  int G;
+};
+
+// position of a pipeline in its tile sequence
+struct DenseWalk {
+  int conf, cs, n, a0, lt, nt;    // conformer, first atom, atoms; row block; local tile and tiles of the block
+  __device__ __forceinline__ void load_conf(const DenseBwdParams& p) {
+    cs = __ldg(p.seg_ptr + conf);
+    n = __ldg(p.seg_ptr + conf + 1) - cs;
+    if (n > DN_MAX || n <= 0) n = 0;
+  }
+  // position at global tile t (t < total)
+  __device__ __forceinline__ void seek(const DenseBwdParams& p, int64_t t) {
+    int lo = 0, hi = p.G;            // last conformer with tile_ptr[conf] <= t
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((int64_t)__ldg(p.tile_ptr + mid) <= t) lo = mid; else hi = mid;
+    }
+    conf = lo;
+    load_conf(p);
+    int local = (int)(t - __ldg(p.tile_ptr + conf));
+    a0 = 0;
+    nt = dense_block_tiles(n, 0);
+    while (local >= nt) {
+      local -= nt;
+      a0 += 16;
+      nt = dense_block_tiles(n, a0);
+    }
+    lt = local;
+  }
+  __device__ __forceinline__ void next(const DenseBwdParams& p) {
+    if (++lt < nt) return;
+    lt = 0;
+    for (;;) {
+      a0 += 16;
+      if (a0 < n) {
+        nt = dense_block_tiles(n, a0);
+        if (nt > 0) return;
+        continue;
+      }
+      if (++conf >= p.G) {        // past the end: never used (callers count tiles)
+        n = 0; a0 = 0; nt = 1;
+        return;
+      }
+      load_conf(p);
+      a0 = -16;
+    }
+  }
+  // geometry of the current tile: kind 0..3 = DIAG columns [32 kind', ...) pairs of 64: c_base = 64 * (kind >> 1); 4 = RECT
+  __device__ __forceinline__ void tile(bool& diag, int& c_base, int& j0, int& ncols) const {
+    const int m = min(16, n - a0);
+    const int nd = m * (m - 1) / 2;
+    const int ndt = (nd > 0) + (nd > 64);
+    diag = lt < ndt;
+    if (diag) {
+      c_base = 64 * lt;
+      j0 = a0;
+      ncols = min(64, nd - c_base);
+    } else {
+      c_base = 0;
+      j0 = a0 + 16 + 4 * (lt - ndt);
+      ncols = 16 * min(4, n - j0);
+    }
+  }
+};
+
+// dF of 32 columns of a DIAG tile: columns C0 .. C0 + 31 of the block's pair list (compile-time pairs)
+template <int C0>
+__device__ __forceinline__ void dense_df_diag(const float (&gr)[16], const float (&xr)[16], uint32_t mf, uint32_t mr,
+                                              const float* __restrict__ sC32, uint8_t* __restrict__ dstF, float& db2) {
+#pragma unroll
+  for (int c8 = 0; c8 < 32; c8 += 8) {
+    float v[8];
+    const float4 ca = *reinterpret_cast<const float4*>(sC32 + c8), cb = *reinterpret_cast<const float4*>(sC32 + c8 + 4);
+    const float cc[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int c = C0 + c8 + j;                     // compile-time after unrolling
+      const int il = c < 120 ? dg_i(c) : 0, jl = c < 120 ? dg_j(c) : 0;
+      const float a = ((mf >> (c8 + j)) & 1u) ? gr[il] * xr[jl] : 0.0f;       // edge j -> i: g[i] x'[j]
+      v[j] = ((mr >> (c8 + j)) & 1u) ? fmaf(gr[jl], xr[il], a) : a;           // edge i -> j: g[j] x'[i]
+      db2 = fmaf(v[j], cc[j], db2);
+    }
+    *reinterpret_cast<uint4*>(dstF + (c8 >> 3) * 2048) = pack_bf16x8(v);
+  }
+}
+
+// dF of 32 columns of a RECT tile: rows il of the block x the two column atoms of this half (gj / xj)
+__device__ __forceinline__ void dense_df_rect(const float (&gr)[16], const float (&xr)[16], const float (&gj)[2],
+                                              const float (&xj)[2], uint32_t mf, uint32_t mr,
+                                              const float* __restrict__ sC32, uint8_t* __restrict__ dstF, float& db2) {
+#pragma unroll
+  for (int c8 = 0; c8 < 32; c8 += 8) {
+    float v[8];
+    const float4 ca = *reinterpret_cast<const float4*>(sC32 + c8), cb = *reinterpret_cast<const float4*>(sC32 + c8 + 4);
+    const float cc[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 + j, il = c & 15, jj = c >> 4;
+      const float a = ((mf >> c) & 1u) ? gr[il] * xj[jj] : 0.0f;              // edge j -> i
+      v[j] = ((mr >> c) & 1u) ? fmaf(gj[jj], xr[il], a) : a;                  // edge i -> j
+      db2 = fmaf(v[j], cc[j], db2);
+    }
+    *reinterpret_cast<uint4*>(dstF + (c8 >> 3) * 2048) = pack_bf16x8(v);
+  }
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_bwd_kernel(const __grid_constant__ DenseBwdParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // wbar | per group: r_ready, d1_ready, f_ready, dda_ready, h_ready, w_done
+  __shared__ uint64_t bars[1 + NG * 6];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_offset[K1];
+  __shared__ __align__(16) float s_c2[K1];
+
+  uint8_t* sW1 = smem;
+  uint8_t* sW2T = smem + W1_BYTES;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1);
+    for (int g = 0; g < NG; ++g) {
+      uint64_t* b = &bars[1 + g * 6];
+      tc::mbar_init(b + 0, GT);  // r_ready   (rbf image, cutoffs and masks written)
+      tc::mbar_init(b + 1, 1);   // d1_ready  (h in TMEM)
+      tc::mbar_init(b + 2, GT);  // f_ready   (a', S, dF images written; h consumed)
+      tc::mbar_init(b + 3, 1);   // dda_ready (da' in TMEM)
+      tc::mbar_init(b + 4, GT);  // h_ready   (dh image written)
+      tc::mbar_init(b + 5, 1);   // w_done    (weight-gradient MMAs finished reading the images)
+    }
+    tc::mbar_fence_init();
+  }
+  if (tid < K1) {
+    s_offset[tid] = (tid < p.Ng) ? p.offset[tid] : 0.0f;
+    s_c2[tid] = (tid < p.Ng) ? p.coeff_log2e : 0.0f;
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int64_t T = __ldg(p.tile_ptr + p.G);
+  const int64_t U = (int64_t)gridDim.x * NG;
+  const int k1steps = (p.Ng + 1 + 15) >> 4;
+
+  if (warp >= NG * (GT / 32)) {
+    // ======================= MMA-issuing warp of group g =======================
+    const int g = warp - NG * (GT / 32);
+    if (lane == 0) {
+      uint64_t* wbar = &bars[0];
+      uint64_t* b = &bars[1 + g * 6];
+      if (g == 0) {
+        tc::mbar_arrive_expect_tx(wbar, W1_BYTES + W2T_BYTES);
+        tc::bulk_g2s(sW1, p.weights, W1_BYTES, wbar);
+        tc::bulk_g2s(sW2T, p.weights + W1_BYTES, W2T_BYTES, wbar);
+      }
+      uint8_t* sG0 = smem + W1_BYTES + W2T_BYTES + g * D_GROUP_BYTES;
+      const uint32_t aW1 = tc::smem_u32(sW1), aW2T = tc::smem_u32(sW2T);
+      const uint32_t aR = tc::smem_u32(sG0), aA = aR + D_OFF_A, aF = aR + D_OFF_F, aS = aR + D_OFF_S;
+      const uint32_t tD = tmem_base + g * 256, tW2 = tD + 64, tW1 = tD + 192;
+      const int64_t u = (int64_t)blockIdx.x * NG + g;
+      const int64_t t0 = u * T / U, t1 = (u + 1) * T / U;
+      tc::mbar_wait(wbar, 0);
+      DenseWalk w;
+      if (t0 < t1) w.seek(p, t0);
+      uint32_t it = 0;
+      for (int64_t ti = t0; ti < t1; ++ti, ++it) {
+        bool diag;
+        int c_base, j0, ncols;
+        w.tile(diag, c_base, j0, ncols);
+        const int npad = (ncols + 15) & ~15;
+        if (ti + 1 < t1) w.next(p);
+        const uint32_t par = it & 1;
+        // h = W1aug * rbf^T
+        tc::mbar_wait_spin(b + 0, par);
+        tc::tc_fence_after();
+        const uint32_t id1 = tc::umma_idesc_f16(F, npad, 1, 0, 0);
+        for (int ks = 0; ks < k1steps; ++ks)
+          tc::umma_f16(tD, tc::umma_smem_desc(aW1 + ks * 256, 128, 1024), tc::umma_smem_desc(aR + ks * 256, 128, 1024), id1,
+                       ks > 0);
+        tc::umma_commit(b + 1);
+        // da' = W2^T * dF      (dF image read as MN-major [K=f, N=e]: LBO 128, SBO 2048)
+        tc::mbar_wait_spin(b + 2, par);
+        tc::tc_fence_after();
+        const uint32_t id2 = tc::umma_idesc_f16(F, npad, 1, 0, 1);
+#pragma unroll
+        for (int ks = 0; ks < F / 16; ++ks)
+          tc::umma_f16(tD, tc::umma_smem_desc(aW2T + ks * 256, 128, 2048), tc::umma_smem_desc(aF + ks * 256, 128, 2048), id2,
+                       ks > 0);
+        tc::umma_commit(b + 3);
+        // weight gradients, K = columns of the tile (images read as K-major [rows=channel, K=e]: SBO 128, LBO 2048)
+        tc::mbar_wait_spin(b + 4, par);
+        tc::tc_fence_after();
+        const uint32_t id3 = tc::umma_idesc_f16(F, F, 1, 0, 0);
+        const uint32_t id4 = tc::umma_idesc_f16(F, K1, 1, 0, 1);
+        for (int ks = 0; ks < (npad >> 4); ++ks) {
+          const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+          tc::umma_f16(tW2, tc::umma_smem_desc(aF + ks * 4096, 2048, 128), tc::umma_smem_desc(aA + ks * 4096, 2048, 128), id3,
+                       acc);
+          tc::umma_f16(tW1, tc::umma_smem_desc(aS + ks * 4096, 2048, 128), tc::umma_smem_desc(aR + ks * 2048, 1024, 128), id4,
+                       acc);
+        }
+        tc::umma_commit(b + 5);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= compute warps of group g =======================
+    const int g = warp / (GT / 32);
+    const int tt = tid - g * GT;
+    const int wq = warp & 3;                  // TMEM lane quarter
+    const int h = (warp >> 2) & 1;            // column half handled in the channel-major phases
+    const int chan = wq * 32 + lane;
+    const int e = tt & 63;                    // column in the rbf phase
+    const int q = tt >> 6;                    // 4 threads share a column in the rbf phase
+    uint64_t* b = &bars[1 + g * 6];
+    uint8_t* sR = smem + W1_BYTES + W2T_BYTES + g * D_GROUP_BYTES;
+    uint8_t* sA = sR + D_OFF_A;
+    uint8_t* sF = sR + D_OFF_F;
+    uint8_t* sS = sR + D_OFF_S;
+    float* sPos = reinterpret_cast<float*>(sR + D_OFF_POS);
+    uint32_t* sAdj = reinterpret_cast<uint32_t*>(sR + D_OFF_ADJ);
+    float* sC = reinterpret_cast<float*>(sR + D_OFF_C);
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sR + D_OFF_MASK);
+    const uint32_t tD = tmem_base + g * 256 + ((uint32_t)(wq * 32) << 16);
+    const uint32_t tW2 = tD + 64, tW1 = tD + 192;
+    const int64_t u = (int64_t)blockIdx.x * NG + g;
+    const int64_t t0 = u * T / U, t1 = (u + 1) * T / U;
+    const float c2 = p.coeff_log2e, cutoff = p.cutoff;
+    (void)c2;
+
+    float db1 = 0.0f, db2 = 0.0f;
+    float gr[16], xr[16];                     // g and x' rows of the current row block, this thread's channel
+#pragma unroll
+    for (int i = 0; i < 16; ++i) gr[i] = xr[i] = 0.0f;
+    int rows_conf = -1, rows_a0 = -1, staged_conf = -1;
+    uint32_t it = 0;
+    DenseWalk w;
+    if (t0 < t1) w.seek(p, t0);
+
+    for (int64_t ti = t0; ti < t1; ++ti, ++it) {
+      bool diag;
+      int c_base, j0, ncols;
+      w.tile(diag, c_base, j0, ncols);
+      const int cs = w.cs, n = w.n, a0 = w.a0, conf = w.conf;
+      const int m = min(16, n - a0);
+      const int npad = (ncols + 15) & ~15;
+      const uint32_t par = it & 1;
+      const int goff = (cs + a0) * F + chan;
+
+      // rows of a new row block (fp32, straight from global memory: coalesced over the channel)
+      if (conf != rows_conf || a0 != rows_a0) {
+        rows_conf = conf;
+        rows_a0 = a0;
+#pragma unroll
+        for (int il = 0; il < 16; ++il) {
+          gr[il] = (il < m) ? __ldg(p.g + goff + il * F) : 0.0f;
+          xr[il] = (il < m) ? __ldg(p.xprime + goff + il * F) : 0.0f;
+        }
+      }
+      // the two column atoms of this half of a RECT tile
+      float gj[2] = {0.0f, 0.0f}, xj[2] = {0.0f, 0.0f};
+      if (!diag) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int a = j0 + 2 * h + jj;
+          if (a < n) {
+            gj[jj] = __ldg(p.g + (cs + a) * F + chan);
+            xj[jj] = __ldg(p.xprime + (cs + a) * F + chan);
+          }
+        }
+      }
+
+      // the previous tile's weight-gradient MMAs must be done reading the images before they are rewritten
+      if (it > 0) tc::mbar_wait(b + 5, (it - 1) & 1);
+
+      // positions and adjacency rows of a new conformer (the group's private copy)
+      if (conf != staged_conf) {
+        staged_conf = conf;
+        tc::named_bar_sync(1 + g, GT);       // nobody still reads the previous conformer's copy
+        if (tt < n) {
+          const float* pp = p.pos + (int64_t)(cs + tt) * 3;
+          sPos[3 * tt + 0] = __ldg(pp + 0);
+          sPos[3 * tt + 1] = __ldg(pp + 1);
+          sPos[3 * tt + 2] = __ldg(pp + 2);
+          reinterpret_cast<uint4*>(sAdj)[tt] = __ldg(reinterpret_cast<const uint4*>(p.adj) + cs + tt);
+        }
+        tc::named_bar_sync(1 + g, GT);
+      }
+
+      // ---- column e: pair, directions, distance, cutoff, Gaussian expansion -> rbf image ----
+      {
+        int il, jl, i_loc, j_loc;
+        if (diag) {
+          const int c = min(c_base + e, 119);
+          // jl = floor((1 + sqrt(1 + 8 c)) / 2): exact for c < 120 with one correction step each way
+          jl = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)c)) * 0.5f);
+          if (jl * (jl - 1) / 2 > c) --jl;
+          if ((jl + 1) * jl / 2 <= c) ++jl;
+          il = c - jl * (jl - 1) / 2;
+          i_loc = a0 + il;
+          j_loc = a0 + jl;
+        } else {
+          il = e & 15;
+          i_loc = a0 + il;
+          j_loc = j0 + (e >> 4);
+        }
+        bool ef = false, er = false;
+        if (e < ncols) {
+          ef = (sAdj[i_loc * DN_AW + (j_loc >> 5)] >> (j_loc & 31)) & 1u;     // edge j -> i
+          er = (sAdj[j_loc * DN_AW + (i_loc >> 5)] >> (i_loc & 31)) & 1u;     // edge i -> j
+        }
+        const bool live = ef || er;
+        float d = 0.0f;
+        if (live) {
+          const float dx = sPos[3 * j_loc] - sPos[3 * i_loc], dy = sPos[3 * j_loc + 1] - sPos[3 * i_loc + 1],
+                      dz = sPos[3 * j_loc + 2] - sPos[3 * i_loc + 2];
+          const float d2 = dx * dx + dy * dy + dz * dz;
+          d = d2 * rsqrtf(fmaxf(d2, 1e-20f));
+        }
+        if (q == 0) {       // warps 0 and 1 of the group hold columns 0..31 and 32..63 (whole warps: the ballots are uniform)
+          sC[e] = live ? 0.5f * (__cosf(d * kPi / cutoff) + 1.0f) : 0.0f;
+          const unsigned bf = __ballot_sync(0xffffffffu, ef), br = __ballot_sync(0xffffffffu, er);
+          if (lane == 0) {
+            sMask[e >> 5] = bf;
+            sMask[2 + (e >> 5)] = br;
+          }
+        }
+        if (e < npad) {
+          uint8_t* rowp = sR + (e >> 3) * 1024 + (e & 7) * 16;
+          // exp2(c2_k (d - mu_k)^2), c2_k = 0 beyond the Gaussians (bias column = 1).  Rows of missing pairs and of padded
+          // columns must be ZERO: they enter dW1 through K = columns.
+          for (int jc = q; jc < 2 * k1steps; jc += 4) {
+            float v[8];
+            const float4* op = reinterpret_cast<const float4*>(s_offset + jc * 8);
+            const float4* cp2 = reinterpret_cast<const float4*>(s_c2 + jc * 8);
+            const float4 o0 = op[0], o1 = op[1], k0 = cp2[0], k1 = cp2[1];
+            const float off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+            const float ck[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float x = d - off[j];
+              v[j] = live ? tc::fast_ex2(ck[j] * (x * x)) : 0.0f;
+            }
+            *reinterpret_cast<uint4*>(rowp + jc * 128) = pack_bf16x8(v);
+          }
+        }
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(b + 0);
+      tc::named_bar_sync(1 + g, GT);   // sC / sMask visible to the whole group
+
+      // ---- dF image from the row registers (runs while the tensor core computes h) ----
+      {
+        const uint32_t mf = sMask[h], mr = sMask[2 + h];
+        uint8_t* dstF = sF + chan * 16 + (h * 4) * 2048;
+        const float* sC32 = sC + 32 * h;
+        if (32 * h < npad) {
+          if (!diag) {
+            dense_df_rect(gr, xr, gj, xj, mf, mr, sC32, dstF, db2);
+          } else {
+            switch ((c_base >> 5) + h) {
+              case 0: dense_df_diag<0>(gr, xr, mf, mr, sC32, dstF, db2); break;
+              case 1: dense_df_diag<32>(gr, xr, mf, mr, sC32, dstF, db2); break;
+              case 2: dense_df_diag<64>(gr, xr, mf, mr, sC32, dstF, db2); break;
+              default: dense_df_diag<96>(gr, xr, mf, mr, sC32, dstF, db2); break;
+            }
+          }
+        }
+      }
+
+      // ---- epilogue 1: a' = C ssp(h), S = C sigmoid(h) -> images ----
+      tc::mbar_wait(b + 1, par);
+      tc::tc_fence_after();
+      {
+        const int cb = h * 32, ce = min(npad, h * 32 + 32);
+        for (int c0 = cb; c0 < ce; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(tD + c0, v);
+          float c[16];
+          const float4* cp = reinterpret_cast<const float4*>(sC + c0);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const float4 cc = cp[k4];
+            c[k4 * 4 + 0] = cc.x; c[k4 * 4 + 1] = cc.y; c[k4 * 4 + 2] = cc.z; c[k4 * 4 + 3] = cc.w;
+          }
+          tc::tmem_wait_ld();
+          float a[16], s[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = v[j];
+            const float t = tc::fast_ex2(-1.4426950408889634f * fabsf(x));
+            const float inv = __fdividef(1.0f, 1.0f + t);
+            a[j] = c[j] * fmaf(tc::fast_lg2(1.0f + t) - 1.0f, kLn2, fmaxf(x, 0.0f));
+            s[j] = c[j] * (x >= 0.0f ? inv : t * inv);
+          }
+          *reinterpret_cast<uint4*>(sA + chan * 16 + (c0 >> 3) * 2048) = pack_bf16x8(a);
+          *reinterpret_cast<uint4*>(sA + chan * 16 + ((c0 >> 3) + 1) * 2048) = pack_bf16x8(a + 8);
+          *reinterpret_cast<uint4*>(sS + chan * 16 + (c0 >> 3) * 2048) = pack_bf16x8(s);
+          *reinterpret_cast<uint4*>(sS + chan * 16 + ((c0 >> 3) + 1) * 2048) = pack_bf16x8(s + 8);
+        }
+      }
+      tc::tc_fence_before();
+      tc::fence_proxy_async();
+      tc::mbar_arrive(b + 2);
+
+      // ---- epilogue 3: dh = da' * S -> dh image (in place over S) ----
+      tc::mbar_wait(b + 3, par);
+      tc::tc_fence_after();
+      {
+        const int cb = h * 32, ce = min(npad, h * 32 + 32);
+        for (int c0 = cb; c0 < ce; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(tD + c0, v);
+          float s[16];
+          uint4* sp0 = reinterpret_cast<uint4*>(sS + chan * 16 + (c0 >> 3) * 2048);
+          uint4* sp1 = reinterpret_cast<uint4*>(sS + chan * 16 + ((c0 >> 3) + 1) * 2048);
+          unpack_bf16x8(*sp0, s);
+          unpack_bf16x8(*sp1, s + 8);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            v[j] *= s[j];
+            db1 += v[j];
+          }
+          *sp0 = pack_bf16x8(v);
+          *sp1 = pack_bf16x8(v + 8);
+        }
+      }
+      tc::tc_fence_before();
+      tc::fence_proxy_async();
+      tc::mbar_arrive(b + 4);
+      if (ti + 1 < t1) w.next(p);
+    }
+
+    // ---- drain: accumulators -> this pipeline's partial block ----
+    float* part = p.partial + u * (int64_t)PART_FLOATS;
+    const bool any = t0 < t1;
+    if (any) {
+      tc::mbar_wait(b + 5, (it - 1) & 1);
+      tc::tc_fence_after();
+    }
+    for (int c0 = h * 64; c0 < h * 64 + 64; c0 += 16) {       // dW2[f = chan][k]: columns [h*64, h*64+64)
+      float v[16];
+      if (any) {
+        tc::tmem_ld16(tW2 + c0, v);
+        tc::tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(part + chan * F + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    for (int c0 = h * 32; c0 < h * 32 + 32; c0 += 16) {       // dW1[k = chan][j]: columns [h*32, h*32+32)
+      float v[16];
+      if (any) {
+        tc::tmem_ld16(tW1 + c0, v);
+        tc::tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(part + F * F + chan * K1 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    part[F * F + F * K1 + h * F + chan] = db2;
+    part[F * F + F * K1 + 2 * F + h * F + chan] = db1;
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 }  // namespace cmp
 
@@ -871,5 +1443,64 @@ extern "C" int cmp_cfconv_tc_pack_bwd_weights_grouped(const void* jobs, int coun
   const int total = F * K1 + F * F;
   pack_bwd_weights_grouped_kernel<<<dim3((total + 255) / 256, count), 256, 0, as_stream(stream)>>>(g, num_gaussians);
   CMP_LAUNCH_CHECK("cmp_cfconv_tc_pack_bwd_weights_grouped");
+  return CMP_OK;
+}
+
+extern "C" size_t cmp_cfconv_dense_bwd_workspace(int64_t G) {
+  return align_up(cmp_cfconv_fused_bwd_workspace(), 256) + (size_t)(G + 1) * sizeof(int32_t);
+}
+
+extern "C" int cmp_cfconv_dense_bwd_weights(const float* g, const float* xprime, const float* pos, const int32_t* seg_ptr,
+                                            const uint32_t* adj, int64_t G, const void* packed_bwd_weights,
+                                            const float* offset, int num_gaussians, float coeff, float cutoff,
+                                            int num_filters, float* dW1, float* db1, float* dW2, float* db2,
+                                            void* workspace, size_t workspace_bytes, int32_t* status,
+                                            cmp_stream_t stream) {
+  CMP_REQUIRE(num_filters == F && num_gaussians >= 1 && num_gaussians < K1, CMP_EUNSUPPORTED,
+              "cmp_cfconv_dense_bwd_weights: needs num_filters == 128 and num_gaussians < 64");
+  CMP_REQUIRE(G >= 1 && G < ((int64_t)1 << 31), CMP_EINVAL, "cmp_cfconv_dense_bwd_weights: bad number of conformers");
+  CMP_REQUIRE(g && xprime && pos && seg_ptr && adj && packed_bwd_weights && offset && dW1 && db1 && dW2 && db2, CMP_EINVAL,
+              "cmp_cfconv_dense_bwd_weights: null pointer");
+  CMP_REQUIRE(((uintptr_t)packed_bwd_weights % 16 == 0) && ((uintptr_t)adj % 16 == 0), CMP_EINVAL,
+              "cmp_cfconv_dense_bwd_weights: packed_bwd_weights / adj must be 16-byte aligned");
+  CMP_REQUIRE(workspace && workspace_bytes >= cmp_cfconv_dense_bwd_workspace(G), CMP_EWORKSPACE,
+              "cmp_cfconv_dense_bwd_weights: workspace too small");
+  CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED, "cmp_cfconv_dense_bwd_weights: needs an sm_100 device (tcgen05)");
+  cudaStream_t st = as_stream(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(cfconv_dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SMEM_BYTES) !=
+        cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("cmp_cfconv_dense_bwd_weights: cannot opt in to %u bytes of shared memory", D_SMEM_BYTES);
+      return CMP_ECUDA;
+    }
+    attr_set = true;
+  }
+  DenseBwdParams p;
+  p.g = g;
+  p.xprime = xprime;
+  p.pos = pos;
+  p.seg_ptr = seg_ptr;
+  p.adj = adj;
+  int32_t* tile_ptr = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) +
+                                                 align_up(cmp_cfconv_fused_bwd_workspace(), 256));
+  p.tile_ptr = tile_ptr;
+  p.weights = reinterpret_cast<const uint8_t*>(packed_bwd_weights);
+  p.offset = offset;
+  p.partial = reinterpret_cast<float*>(workspace);
+  p.coeff_log2e = coeff * 1.4426950408889634f;
+  p.cutoff = cutoff;
+  p.Ng = num_gaussians;
+  p.G = (int)G;
+  dense_tile_ptr_kernel<<<1, 256, 0, st>>>(seg_ptr, G, tile_ptr, status);
+  CMP_LAUNCH_CHECK("cmp_cfconv_dense_bwd_weights");
+  const int grid = sm_count();
+  cfconv_dense_bwd_kernel<<<grid, CTA_THREADS, D_SMEM_BYTES, st>>>(p);
+  CMP_LAUNCH_CHECK("cmp_cfconv_dense_bwd_weights");
+  const int total = F * F + F * K1 + 2 * F;
+  reduce_partials_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(p.partial, grid * NG, num_gaussians, dW1, db1, dW2,
+                                                                    db2);
+  CMP_LAUNCH_CHECK("cmp_cfconv_dense_bwd_weights");
   return CMP_OK;
 }

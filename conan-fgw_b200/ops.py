@@ -884,13 +884,16 @@ FUSED_WEIGHT_GRADS = True
 FUSED_PAIR_GRADS = True
 
 
+# weight gradients over the dense blocks of the forward kernel (conformers of <= 128 atoms, promised by max_atoms): fp32
+# rows of g and x' in registers instead of a pair list and bf16 copies; False = always the pair-list kernel
+FUSED_DENSE_GRADS = True
+
+
 def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff):
-    """dW1, db1, dW2, db2 of the filter MLP through cmp_cfconv_fused_bwd_weights (tcgen05, K = edges)."""
+    """dW1, db1, dW2, db2 of the filter MLP through the tcgen05 weight-gradient kernels (K = edges / pairs)."""
     N, F = xprime.shape
     Ng = offset.numel()
     dev = g.device
-    xb = torch.empty(N, F, dtype=torch.bfloat16, device=dev)
-    call("cmp_f32_to_bf16", ptr(xprime), N * F, ptr(xb))
     cached = _cached_images(W1)
     if cached is not None:
         packed = cached[1]
@@ -901,8 +904,18 @@ def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff):
     db1 = torch.empty(F, dtype=torch.float32, device=dev)
     dW2 = torch.empty(F, F, dtype=torch.float32, device=dev)
     db2 = torch.empty(F, dtype=torch.float32, device=dev)
-    ws = _lib.workspace(_lib.size_query("cmp_cfconv_fused_bwd_workspace"), dev)
     e_hint = graph._E if graph._E is not None else graph.cap_E
+    if (FUSED_DENSE_GRADS and FUSED_DENSE and graph.G > 0 and graph.pos is not None and not graph.loop
+            and graph.max_atoms is not None and graph.max_atoms <= _lib.size_query("cmp_cfconv_dense_max_atoms")):
+        ws = _lib.workspace(_lib.size_query("cmp_cfconv_dense_bwd_workspace", graph.G), dev)
+        call("cmp_cfconv_dense_bwd_weights", ptr(_f32c(g)), ptr(_f32c(xprime)), ptr(graph.pos), ptr(graph.seg_ptr),
+             ptr(graph.adjacency()), graph.G, ptr(packed), ptr(offset), Ng, float(coeff), float(cutoff), F, ptr(dW1),
+             ptr(db1), ptr(dW2), ptr(db2), ptr(ws), ws.numel(), ptr(graph.status),
+             work=2.0 * (Ng * F + F * F) * float(e_hint))
+        return dW1, db1, dW2, db2
+    xb = torch.empty(N, F, dtype=torch.bfloat16, device=dev)
+    call("cmp_f32_to_bf16", ptr(xprime), N * F, ptr(xb))
+    ws = _lib.workspace(_lib.size_query("cmp_cfconv_fused_bwd_workspace"), dev)
     # algorithmic FLOPs: the weight-gradient half of "bwd = 2 x fwd" = 2*(Ng*F + F*F) per edge
     if FUSED_PAIR_GRADS:
         gb = torch.empty(N, F, dtype=torch.bfloat16, device=dev)

@@ -285,6 +285,22 @@ int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int32_t* seg_pt
                          int skip_large, int max_atoms_hint, float* agg, int32_t* counter, int32_t* status,
                          cmp_stream_t stream);
 
+/* Filter-MLP weight gradients over the DENSE blocks of cmp_cfconv_dense_fwd (conformers of at most 128 atoms; larger
+ * ones set CMP_STATUS_EDGE_OVERFLOW in *status and contribute nothing - serve such batches with
+ * cmp_cfconv_fused_bwd_weights_pairs): one column per undirected pair in tiles of 64, the pair of a column is a
+ * compile-time function of its index, so dF[f, (i, j)] = [j -> i] g[i] x'[j] + [i -> j] g[j] x'[i] is built from fp32 rows
+ * of g = dL/dagg and x' held in registers (no pair list, no bf16 copies of g / x', no gathers); distances from `pos`, the
+ * directions of a pair from `adj` (cmp_build_adjacency).  Same MMAs, epilogues and TMEM accumulators as
+ * cmp_cfconv_fused_bwd_weights; packed_bwd_weights from cmp_cfconv_tc_pack_bwd_weights; offset in DEVICE memory.
+ * workspace: cmp_cfconv_dense_bwd_workspace(G) bytes.  Replaces the weight-gradient half of CFConv's backward
+ * (PyG autograd through CFConv.message / nn, sns.py:161-164). */
+size_t cmp_cfconv_dense_bwd_workspace(int64_t G);
+int cmp_cfconv_dense_bwd_weights(const float* g, const float* xprime, const float* pos, const int32_t* seg_ptr,
+                                 const uint32_t* adj, int64_t G, const void* packed_bwd_weights, const float* offset,
+                                 int num_gaussians, float coeff, float cutoff, int num_filters, float* dW1, float* db1,
+                                 float* dW2, float* db2, void* workspace, size_t workspace_bytes, int32_t* status,
+                                 cmp_stream_t stream);
+
 /* Filter-MLP weight gradients of the fused CFConv in ONE kernel (+ a fixed-order reduction of the
  * per-pipeline partial sums): recomputes rbf / hidden / a' per 64-edge tile on chip and accumulates
  * dW2 = sum_e dF_e a'_e^T and dW1 = sum_e dh_e rbf_e^T in TMEM (tcgen05, bf16 operands, fp32

@@ -144,3 +144,67 @@ def test_adjacency_bits_equal_the_edge_list():
         jl = j - int(seg[conf[i]])
         want[i, jl >> 5] |= 1 << (jl & 31)
     assert torch.equal(adj.to(torch.int64) & 0xFFFFFFFF, want)
+
+
+def _exact_weight_grads(blk, gs, nl, xp, g, cutoff):
+    """Filter-MLP gradients through the exact-fp32 message kernels + autograd over materialised [E, F] rows."""
+    ps = [t.detach().clone().requires_grad_(True) for t in (blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight,
+                                                              blk.mlp[2].bias)]
+    rbf = gs(nl.edge_weight())
+    filt = ops.linear(ops.linear(rbf, ps[0], ps[1], cmp._lib.ACT_SSP), ps[2], ps[3])
+    agg = ops.cfconv_message(xp.detach(), filt, nl, cutoff)
+    return torch.autograd.grad(agg, ps, g)
+
+
+@pytest.mark.parametrize("n,B,K,cutoff,max_nb", [
+    (27, 6, 3, 10.0, 32), (2, 5, 2, 10.0, 32), (12, 3, 2, 10.0, 32), (16, 3, 2, 10.0, 32), (17, 3, 2, 10.0, 32),
+    (33, 2, 2, 10.0, 32), (45, 2, 2, 10.0, 32), (65, 2, 2, 10.0, 32), (45, 2, 2, 5.0, 32), (128, 1, 1, 10.0, 32),
+    (40, 2, 2, 10.0, 8),
+])
+def test_dense_weight_gradients_match_the_exact_path(n, B, K, cutoff, max_nb):
+    """cmp_cfconv_dense_bwd_weights (fp32 rows of g / x' in registers, columns over the dense blocks) against the exact
+    gradients and against the pair-list kernel.  Stated tolerance of the bf16 operand images: 1e-2 relative."""
+    _need_sm100()
+    b = syn.make_batch(B, K, n, seed=n).to(DEV)
+    nl = cmp.build_neighbor_list(b.pos, b.batch, cutoff, max_nb, max_atoms=n)
+    blk, gs = _block(cutoff, seed=n)
+    torch.manual_seed(n + 2)
+    xp = torch.randn(b.z.numel(), F, device=DEV)
+    g = torch.randn(b.z.numel(), F, device=DEV)
+    want = _exact_weight_grads(blk, gs, nl, xp, g, cutoff)
+    W = (blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight)
+    res = {}
+    for dense in (True, False):
+        ops.FUSED_DENSE_GRADS = dense
+        try:
+            before = cmp._lib.launches()
+            res[dense] = ops._fused_weight_grads(g, xp, *W, nl, gs.offset, gs.coeff, cutoff)
+            res[dense] = tuple(t.clone() for t in res[dense]) + (cmp._lib.launches() - before,)
+        finally:
+            ops.FUSED_DENSE_GRADS = True
+    nl.check()
+    for name, got, pair, ref in zip(("dW1", "db1", "dW2", "db2"), res[True], res[False], want):
+        assert rel_err(got, ref) < 1e-2, name
+        assert rel_err(got, pair) < 1e-2, name
+    # deterministic, and no conversion launches
+    again = ops._fused_weight_grads(g, xp, *W, nl, gs.offset, gs.coeff, cutoff)
+    for a, c in zip(again, res[True]):
+        assert torch.equal(a, c)
+    assert res[True][4] < res[False][4]
+
+
+def test_dense_weight_gradients_on_a_ragged_batch():
+    _need_sm100()
+    sizes = [1, 27, 5, 64, 1, 33, 18, 2, 17, 32, 1, 128, 3]
+    pos = torch.cat([syn.make_batch(1, 1, n, seed=20 + i).pos for i, n in enumerate(sizes)]).to(DEV)
+    batch = torch.cat([torch.full((n,), i, dtype=torch.int64) for i, n in enumerate(sizes)]).to(DEV)
+    nl = cmp.build_neighbor_list(pos, batch, 10.0, max_atoms=max(sizes))
+    blk, gs = _block(10.0, seed=7)
+    xp = torch.randn(pos.size(0), F, device=DEV)
+    g = torch.randn(pos.size(0), F, device=DEV)
+    want = _exact_weight_grads(blk, gs, nl, xp, g, 10.0)
+    got = ops._fused_weight_grads(g, xp, blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight, nl, gs.offset, gs.coeff,
+                                  10.0)
+    nl.check()
+    for name, a, ref in zip(("dW1", "db1", "dW2", "db2"), got, want):
+        assert rel_err(a, ref) < 1e-2, name
