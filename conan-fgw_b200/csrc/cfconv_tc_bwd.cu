@@ -690,15 +690,18 @@ __global__ void flat_tiles_fill_kernel(const int32_t* __restrict__ conf_edge_ptr
 // pipeline of cfconv_fused_bwd_kernel.
 constexpr int DN_MAX = 128;        // atoms per conformer
 constexpr int DN_AW = 4;           // adjacency words per atom
-constexpr uint32_t D_OFF_A = R_BYTES;
+// the rbf image R and the dF image F are double buffered (tile parity): the Gaussians and dF of tile k + 1 are written
+// while the weight-gradient MMAs of tile k still read R / F of tile k
+constexpr uint32_t D_OFF_A = 2 * R_BYTES;
 constexpr uint32_t D_OFF_F = D_OFF_A + CH_BYTES;
-constexpr uint32_t D_OFF_S = D_OFF_F + CH_BYTES;
+constexpr uint32_t D_OFF_S = D_OFF_F + 2 * CH_BYTES;
 constexpr uint32_t D_OFF_POS = D_OFF_S + CH_BYTES;                 // float[128][3]
 constexpr uint32_t D_OFF_ADJ = D_OFF_POS + DN_MAX * 12;            // uint32[128][4]
 constexpr uint32_t D_OFF_C = D_OFF_ADJ + DN_MAX * DN_AW * 4;       // float[64]
 constexpr uint32_t D_OFF_MASK = D_OFF_C + TE * 4;                  // uint32[4]: [j -> i] of columns 0..31, 32..63; [i -> j] likewise
 constexpr uint32_t D_GROUP_BYTES = (D_OFF_MASK + 16 + 127) / 128 * 128;
 constexpr uint32_t D_SMEM_BYTES = W1_BYTES + W2T_BYTES + NG * D_GROUP_BYTES;
+static_assert(D_SMEM_BYTES <= 232448 - 1024, "shared memory budget of the dense weight-gradient kernel");
 
 // column c of the DIAG pairs of a block holds (il, jl), il < jl, c = jl (jl - 1) / 2 + il
 __host__ __device__ constexpr int dg_j(int c) {
@@ -749,6 +752,31 @@ __global__ void dense_tile_ptr_kernel(const int32_t* __restrict__ seg_ptr, int64
     __syncthreads();
   }
   if (threadIdx.x == 0) ptr[G] = carry;
+}
+
+// a' = c ssp(x) and S = c sigmoid(x) of two columns, in packed f16x2, returned as bf16x2 image words:
+//   t = 2^(-|x| log2 e);  ssp(x) = max(x, 0) + ln2 (log2(1 + t) - 1),  log2(1 + t) = t Q4(t) (8e-5 on [0, 1]);
+//   sigmoid(x) = 1/2 + tanh(x / 2) / 2.
+__device__ __forceinline__ void ssp_sigmoid_f16x2(float x0, float x1, float c0, float c1, uint32_t& a_bf, uint32_t& s_bf) {
+  const __half2 x = __floats2half2_rn(x0, x1);
+  const __half2 c = __floats2half2_rn(c0, c1);
+  uint32_t tu, au = *reinterpret_cast<const uint32_t*>(&x);
+  const __half2 arg = __hmul2(__habs2(x), __float2half2_rn(-1.4426950408889634f));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(*reinterpret_cast<const uint32_t*>(&arg)));
+  const __half2 t = *reinterpret_cast<const __half2*>(&tu);
+  __half2 q = __hfma2(__float2half2_rn(0.0599455865f), t, __float2half2_rn(-0.227712643f));
+  q = __hfma2(q, t, __float2half2_rn(0.442274178f));
+  q = __hfma2(q, t, __float2half2_rn(-0.717063932f));
+  q = __hfma2(q, t, __float2half2_rn(1.44261568f));
+  const __half2 l2m1 = __hfma2(q, t, __float2half2_rn(-1.0f));                         // log2(1 + t) - 1
+  const __half2 sp = __hfma2(l2m1, __float2half2_rn(0.6931471805599453f), __hmax2(x, __float2half2_rn(0.0f)));
+  const float2 af = __half22float2(__hmul2(sp, c));
+  a_bf = tc::pack_bf16x2(af.x, af.y);
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(au) : "r"(*reinterpret_cast<const uint32_t*>(&hx)));
+  const __half2 sg = __hfma2(*reinterpret_cast<const __half2*>(&au), __float2half2_rn(0.5f), __float2half2_rn(0.5f));
+  const float2 sf = __half22float2(__hmul2(sg, c));
+  s_bf = tc::pack_bf16x2(sf.x, sf.y);
 }
 
 struct DenseBwdParams {
@@ -927,7 +955,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_bwd_kernel(const 
       }
       uint8_t* sG0 = smem + W1_BYTES + W2T_BYTES + g * D_GROUP_BYTES;
       const uint32_t aW1 = tc::smem_u32(sW1), aW2T = tc::smem_u32(sW2T);
-      const uint32_t aR = tc::smem_u32(sG0), aA = aR + D_OFF_A, aF = aR + D_OFF_F, aS = aR + D_OFF_S;
+      const uint32_t aR0 = tc::smem_u32(sG0), aA = aR0 + D_OFF_A, aF0 = aR0 + D_OFF_F, aS = aR0 + D_OFF_S;
       const uint32_t tD = tmem_base + g * 256, tW2 = tD + 64, tW1 = tD + 192;
       const int64_t u = (int64_t)blockIdx.x * NG + g;
       const int64_t t0 = u * T / U, t1 = (u + 1) * T / U;
@@ -942,6 +970,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_bwd_kernel(const 
         const int npad = (ncols + 15) & ~15;
         if (ti + 1 < t1) w.next(p);
         const uint32_t par = it & 1;
+        const uint32_t aR = aR0 + par * R_BYTES, aF = aF0 + par * CH_BYTES;
         // h = W1aug * rbf^T
         tc::mbar_wait_spin(b + 0, par);
         tc::tc_fence_after();
@@ -985,14 +1014,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_bwd_kernel(const 
     const int e = tt & 63;                    // column in the rbf phase
     const int q = tt >> 6;                    // 4 threads share a column in the rbf phase
     uint64_t* b = &bars[1 + g * 6];
-    uint8_t* sR = smem + W1_BYTES + W2T_BYTES + g * D_GROUP_BYTES;
-    uint8_t* sA = sR + D_OFF_A;
-    uint8_t* sF = sR + D_OFF_F;
-    uint8_t* sS = sR + D_OFF_S;
-    float* sPos = reinterpret_cast<float*>(sR + D_OFF_POS);
-    uint32_t* sAdj = reinterpret_cast<uint32_t*>(sR + D_OFF_ADJ);
-    float* sC = reinterpret_cast<float*>(sR + D_OFF_C);
-    uint32_t* sMask = reinterpret_cast<uint32_t*>(sR + D_OFF_MASK);
+    uint8_t* sG = smem + W1_BYTES + W2T_BYTES + g * D_GROUP_BYTES;
+    uint8_t* sA = sG + D_OFF_A;
+    uint8_t* sS = sG + D_OFF_S;
+    float* sPos = reinterpret_cast<float*>(sG + D_OFF_POS);
+    uint32_t* sAdj = reinterpret_cast<uint32_t*>(sG + D_OFF_ADJ);
+    float* sC = reinterpret_cast<float*>(sG + D_OFF_C);
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sG + D_OFF_MASK);
     const uint32_t tD = tmem_base + g * 256 + ((uint32_t)(wq * 32) << 16);
     const uint32_t tW2 = tD + 64, tW1 = tD + 192;
     const int64_t u = (int64_t)blockIdx.x * NG + g;
@@ -1017,6 +1045,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_bwd_kernel(const 
       const int m = min(16, n - a0);
       const int npad = (ncols + 15) & ~15;
       const uint32_t par = it & 1;
+      uint8_t* sR = sG + par * R_BYTES;                  // this tile's rbf and dF images
+      uint8_t* sF = sG + D_OFF_F + par * CH_BYTES;
       const int goff = (cs + a0) * F + chan;
 
       // rows of a new row block (fp32, straight from global memory: coalesced over the channel)
@@ -1041,9 +1071,6 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_bwd_kernel(const 
           }
         }
       }
-
-      // the previous tile's weight-gradient MMAs must be done reading the images before they are rewritten
-      if (it > 0) tc::mbar_wait(b + 5, (it - 1) & 1);
 
       // positions and adjacency rows of a new conformer (the group's private copy)
       if (conf != staged_conf) {
@@ -1140,7 +1167,12 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_bwd_kernel(const 
         }
       }
 
-      // ---- epilogue 1: a' = C ssp(h), S = C sigmoid(h) -> images ----
+      // ---- epilogue 1: a' = C ssp(h), S = C sigmoid(h) -> images.  Packed f16x2 arithmetic, ONE special-function op per
+      // element instead of three (ex2.approx.f16x2 for the softplus tail, tanh.approx.f16x2 for the sigmoid): the images
+      // are bf16 (8 mantissa bits), so f16 intermediates (10 bits) cost no accuracy ----
+      // (the a' / S images are single: the previous tile's weight-gradient MMAs must be done reading them - by now they
+      // have had the whole Gaussian + dF phase of this tile to finish)
+      if (it > 0) tc::mbar_wait(b + 5, (it - 1) & 1);
       tc::mbar_wait(b + 1, par);
       tc::tc_fence_after();
       {
@@ -1156,19 +1188,13 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_bwd_kernel(const 
             c[k4 * 4 + 0] = cc.x; c[k4 * 4 + 1] = cc.y; c[k4 * 4 + 2] = cc.z; c[k4 * 4 + 3] = cc.w;
           }
           tc::tmem_wait_ld();
-          float a[16], s[16];
+          uint32_t a[8], sg[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float x = v[j];
-            const float t = tc::fast_ex2(-1.4426950408889634f * fabsf(x));
-            const float inv = __fdividef(1.0f, 1.0f + t);
-            a[j] = c[j] * fmaf(tc::fast_lg2(1.0f + t) - 1.0f, kLn2, fmaxf(x, 0.0f));
-            s[j] = c[j] * (x >= 0.0f ? inv : t * inv);
-          }
-          *reinterpret_cast<uint4*>(sA + chan * 16 + (c0 >> 3) * 2048) = pack_bf16x8(a);
-          *reinterpret_cast<uint4*>(sA + chan * 16 + ((c0 >> 3) + 1) * 2048) = pack_bf16x8(a + 8);
-          *reinterpret_cast<uint4*>(sS + chan * 16 + (c0 >> 3) * 2048) = pack_bf16x8(s);
-          *reinterpret_cast<uint4*>(sS + chan * 16 + ((c0 >> 3) + 1) * 2048) = pack_bf16x8(s + 8);
+          for (int j = 0; j < 8; ++j) ssp_sigmoid_f16x2(v[2 * j], v[2 * j + 1], c[2 * j], c[2 * j + 1], a[j], sg[j]);
+          *reinterpret_cast<uint4*>(sA + chan * 16 + (c0 >> 3) * 2048) = make_uint4(a[0], a[1], a[2], a[3]);
+          *reinterpret_cast<uint4*>(sA + chan * 16 + ((c0 >> 3) + 1) * 2048) = make_uint4(a[4], a[5], a[6], a[7]);
+          *reinterpret_cast<uint4*>(sS + chan * 16 + (c0 >> 3) * 2048) = make_uint4(sg[0], sg[1], sg[2], sg[3]);
+          *reinterpret_cast<uint4*>(sS + chan * 16 + ((c0 >> 3) + 1) * 2048) = make_uint4(sg[4], sg[5], sg[6], sg[7]);
         }
       }
       tc::tc_fence_before();
@@ -1446,24 +1472,31 @@ extern "C" int cmp_cfconv_tc_pack_bwd_weights_grouped(const void* jobs, int coun
   return CMP_OK;
 }
 
-extern "C" size_t cmp_cfconv_dense_bwd_workspace(int64_t G) {
-  return align_up(cmp_cfconv_fused_bwd_workspace(), 256) + (size_t)(G + 1) * sizeof(int32_t);
+extern "C" size_t cmp_cfconv_dense_bwd_workspace(void) { return cmp_cfconv_fused_bwd_workspace(); }
+
+extern "C" int cmp_build_dense_bwd_tiles(const int32_t* seg_ptr, int64_t G, int32_t* tile_ptr, int32_t* status,
+                                         cmp_stream_t stream) {
+  CMP_REQUIRE(G >= 0 && G < ((int64_t)1 << 31), CMP_EINVAL, "cmp_build_dense_bwd_tiles: bad number of conformers");
+  CMP_REQUIRE(seg_ptr && tile_ptr, CMP_EINVAL, "cmp_build_dense_bwd_tiles: null pointer");
+  dense_tile_ptr_kernel<<<1, 256, 0, as_stream(stream)>>>(seg_ptr, G, tile_ptr, status);
+  CMP_LAUNCH_CHECK("cmp_build_dense_bwd_tiles");
+  return CMP_OK;
 }
 
 extern "C" int cmp_cfconv_dense_bwd_weights(const float* g, const float* xprime, const float* pos, const int32_t* seg_ptr,
-                                            const uint32_t* adj, int64_t G, const void* packed_bwd_weights,
+                                            const uint32_t* adj, const int32_t* tile_ptr, int64_t G,
+                                            const void* packed_bwd_weights,
                                             const float* offset, int num_gaussians, float coeff, float cutoff,
                                             int num_filters, float* dW1, float* db1, float* dW2, float* db2,
-                                            void* workspace, size_t workspace_bytes, int32_t* status,
-                                            cmp_stream_t stream) {
+                                            void* workspace, size_t workspace_bytes, cmp_stream_t stream) {
   CMP_REQUIRE(num_filters == F && num_gaussians >= 1 && num_gaussians < K1, CMP_EUNSUPPORTED,
               "cmp_cfconv_dense_bwd_weights: needs num_filters == 128 and num_gaussians < 64");
   CMP_REQUIRE(G >= 1 && G < ((int64_t)1 << 31), CMP_EINVAL, "cmp_cfconv_dense_bwd_weights: bad number of conformers");
-  CMP_REQUIRE(g && xprime && pos && seg_ptr && adj && packed_bwd_weights && offset && dW1 && db1 && dW2 && db2, CMP_EINVAL,
-              "cmp_cfconv_dense_bwd_weights: null pointer");
+  CMP_REQUIRE(g && xprime && pos && seg_ptr && adj && tile_ptr && packed_bwd_weights && offset && dW1 && db1 && dW2 && db2,
+              CMP_EINVAL, "cmp_cfconv_dense_bwd_weights: null pointer");
   CMP_REQUIRE(((uintptr_t)packed_bwd_weights % 16 == 0) && ((uintptr_t)adj % 16 == 0), CMP_EINVAL,
               "cmp_cfconv_dense_bwd_weights: packed_bwd_weights / adj must be 16-byte aligned");
-  CMP_REQUIRE(workspace && workspace_bytes >= cmp_cfconv_dense_bwd_workspace(G), CMP_EWORKSPACE,
+  CMP_REQUIRE(workspace && workspace_bytes >= cmp_cfconv_dense_bwd_workspace(), CMP_EWORKSPACE,
               "cmp_cfconv_dense_bwd_weights: workspace too small");
   CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED, "cmp_cfconv_dense_bwd_weights: needs an sm_100 device (tcgen05)");
   cudaStream_t st = as_stream(stream);
@@ -1483,8 +1516,6 @@ extern "C" int cmp_cfconv_dense_bwd_weights(const float* g, const float* xprime,
   p.pos = pos;
   p.seg_ptr = seg_ptr;
   p.adj = adj;
-  int32_t* tile_ptr = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(workspace) +
-                                                 align_up(cmp_cfconv_fused_bwd_workspace(), 256));
   p.tile_ptr = tile_ptr;
   p.weights = reinterpret_cast<const uint8_t*>(packed_bwd_weights);
   p.offset = offset;
@@ -1493,8 +1524,6 @@ extern "C" int cmp_cfconv_dense_bwd_weights(const float* g, const float* xprime,
   p.cutoff = cutoff;
   p.Ng = num_gaussians;
   p.G = (int)G;
-  dense_tile_ptr_kernel<<<1, 256, 0, st>>>(seg_ptr, G, tile_ptr, status);
-  CMP_LAUNCH_CHECK("cmp_cfconv_dense_bwd_weights");
   const int grid = sm_count();
   cfconv_dense_bwd_kernel<<<grid, CTA_THREADS, D_SMEM_BYTES, st>>>(p);
   CMP_LAUNCH_CHECK("cmp_cfconv_dense_bwd_weights");

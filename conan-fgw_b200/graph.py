@@ -137,6 +137,15 @@ class NeighborList:
             self._counter = torch.zeros(4, dtype=torch.int32, device=adj.device)
         return self._adj
 
+    def dense_bwd_tiles(self) -> torch.Tensor:
+        """int32 [G + 1]: tiles of the dense weight-gradient kernel before every conformer (``cmp_build_dense_bwd_tiles``;
+        a conformer above 128 atoms raises the status bit).  Built once per neighbour list, shared by all blocks."""
+        if getattr(self, "_dense_bwd_tiles", None) is None:
+            tp = torch.empty(self.G + 1, dtype=torch.int32, device=self.rowptr.device)
+            _lib.call("cmp_build_dense_bwd_tiles", _lib.ptr(self.seg_ptr), self.G, _lib.ptr(tp), _lib.ptr(self.status))
+            self._dense_bwd_tiles = tp
+        return self._dense_bwd_tiles
+
     def erow(self) -> torch.Tensor:
         """Target atom of every edge (``edge_index[1]`` as int32), built once."""
         if getattr(self, "_erow", None) is None:

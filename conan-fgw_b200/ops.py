@@ -907,10 +907,10 @@ def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff):
     e_hint = graph._E if graph._E is not None else graph.cap_E
     if (FUSED_DENSE_GRADS and FUSED_DENSE and graph.G > 0 and graph.pos is not None and not graph.loop
             and graph.max_atoms is not None and graph.max_atoms <= _lib.size_query("cmp_cfconv_dense_max_atoms")):
-        ws = _lib.workspace(_lib.size_query("cmp_cfconv_dense_bwd_workspace", graph.G), dev)
+        ws = _lib.workspace(_lib.size_query("cmp_cfconv_dense_bwd_workspace"), dev)
         call("cmp_cfconv_dense_bwd_weights", ptr(_f32c(g)), ptr(_f32c(xprime)), ptr(graph.pos), ptr(graph.seg_ptr),
-             ptr(graph.adjacency()), graph.G, ptr(packed), ptr(offset), Ng, float(coeff), float(cutoff), F, ptr(dW1),
-             ptr(db1), ptr(dW2), ptr(db2), ptr(ws), ws.numel(), ptr(graph.status),
+             ptr(graph.adjacency()), ptr(graph.dense_bwd_tiles()), graph.G, ptr(packed), ptr(offset), Ng, float(coeff),
+             float(cutoff), F, ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws), ws.numel(),
              work=2.0 * (Ng * F + F * F) * float(e_hint))
         return dW1, db1, dW2, db2
     xb = torch.empty(N, F, dtype=torch.bfloat16, device=dev)

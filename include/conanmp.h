@@ -286,20 +286,23 @@ int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int32_t* seg_pt
                          cmp_stream_t stream);
 
 /* Filter-MLP weight gradients over the DENSE blocks of cmp_cfconv_dense_fwd (conformers of at most 128 atoms; larger
- * ones set CMP_STATUS_EDGE_OVERFLOW in *status and contribute nothing - serve such batches with
+ * ones contribute nothing (cmp_build_dense_bwd_tiles sets CMP_STATUS_EDGE_OVERFLOW) - serve such batches with
  * cmp_cfconv_fused_bwd_weights_pairs): one column per undirected pair in tiles of 64, the pair of a column is a
  * compile-time function of its index, so dF[f, (i, j)] = [j -> i] g[i] x'[j] + [i -> j] g[j] x'[i] is built from fp32 rows
  * of g = dL/dagg and x' held in registers (no pair list, no bf16 copies of g / x', no gathers); distances from `pos`, the
  * directions of a pair from `adj` (cmp_build_adjacency).  Same MMAs, epilogues and TMEM accumulators as
  * cmp_cfconv_fused_bwd_weights; packed_bwd_weights from cmp_cfconv_tc_pack_bwd_weights; offset in DEVICE memory.
- * workspace: cmp_cfconv_dense_bwd_workspace(G) bytes.  Replaces the weight-gradient half of CFConv's backward
- * (PyG autograd through CFConv.message / nn, sns.py:161-164). */
-size_t cmp_cfconv_dense_bwd_workspace(int64_t G);
+ * tile_ptr [G + 1]: tiles of the conformers before g, from cmp_build_dense_bwd_tiles (once per neighbour list; it also
+ * raises the status bit for conformers above the limit).  workspace: cmp_cfconv_dense_bwd_workspace() bytes.
+ * Replaces the weight-gradient half of CFConv's backward (PyG autograd through CFConv.message / nn, sns.py:161-164). */
+size_t cmp_cfconv_dense_bwd_workspace(void);
+int cmp_build_dense_bwd_tiles(const int32_t* seg_ptr, int64_t G, int32_t* tile_ptr, int32_t* status,
+                              cmp_stream_t stream);
 int cmp_cfconv_dense_bwd_weights(const float* g, const float* xprime, const float* pos, const int32_t* seg_ptr,
-                                 const uint32_t* adj, int64_t G, const void* packed_bwd_weights, const float* offset,
-                                 int num_gaussians, float coeff, float cutoff, int num_filters, float* dW1, float* db1,
-                                 float* dW2, float* db2, void* workspace, size_t workspace_bytes, int32_t* status,
-                                 cmp_stream_t stream);
+                                 const uint32_t* adj, const int32_t* tile_ptr, int64_t G,
+                                 const void* packed_bwd_weights, const float* offset, int num_gaussians, float coeff,
+                                 float cutoff, int num_filters, float* dW1, float* db1, float* dW2, float* db2,
+                                 void* workspace, size_t workspace_bytes, cmp_stream_t stream);
 
 /* Filter-MLP weight gradients of the fused CFConv in ONE kernel (+ a fixed-order reduction of the
  * per-pipeline partial sums): recomputes rbf / hidden / a' per 64-edge tile on chip and accumulates
