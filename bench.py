@@ -487,11 +487,38 @@ def run_ours(args):
     total_ms, launches, kt = timed(resident_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, _, _ = timed(e2e_step, args.steps)
-    # per-kernel durations (roofline) need the eager launches: same step, same inputs, CUDA events around each call
+    # per-kernel durations (roofline): the same step, same inputs, CUDA events around each listed launch.  Eager pass first
+    # (it also counts the launches) ...
     ksteps = max(3, min(args.steps, 10))
     eager_ms, eager_launches, kt = timed(eager_step, ksteps, dominant)
     launches_per_step = eager_launches / ksteps
     launches = int(round(launches_per_step * args.steps))
+    # ... then, when the step is replayed from a CUDA graph, the durations INSIDE the replay: the step is captured once more
+    # with external event-record nodes around the listed launches, so the kernels are timed back to back exactly as in the
+    # timed region (the eager pass is launch-bound on the host: every kernel there starts on an idle GPU and measures 10-30 %
+    # longer).  Falls back to the eager numbers if the capture with events is refused.
+    graph_timed = None
+    if use_graph and not args.profile:
+        try:
+            gkt = _lib.KernelTimer(dominant, external=True)
+            trainer.capture(d.z, d.pos, d.batch, targets, G, timer=gkt)
+            resident_step()
+            sync_all()
+            for _ in range(ksteps):
+                flush.zero_()
+                resident_step()
+                torch.cuda.synchronize()
+                gkt.accumulate()
+            graph_timed = gkt
+            trainer.capture(d.z, d.pos, d.batch, targets, G)      # back to the plain graph
+            resident_step()
+            sync_all()
+        except Exception as exc:
+            print(f"bench.py: per-kernel timing inside the CUDA graph failed ({exc!r}); using the eager pass", file=sys.stderr)
+            graph_timed = None
+            trainer.capture(d.z, d.pos, d.batch, targets, G)
+            resident_step()
+            sync_all()
 
     # the other numerics mode of the same step, for the record (exact-fp32 kernels <-> fused bf16 filter MLP)
     other_mode = None
@@ -550,6 +577,9 @@ def run_ours(args):
     pk = peaks()
     summ = kt.summary() if kt else {}
     med = kt.medians() if kt else {}
+    eager_summ = {k: {"avg_launch_us": 1e3 * v[1] / max(v[0], 1)} for k, v in summ.items()}
+    if graph_timed is not None and graph_timed.acc:
+        summ, med = graph_timed.summary_accumulated(), graph_timed.medians_accumulated()
     # algorithmic work of the fused kernels is known exactly from E (2*(Ng*F + F*F) FLOP per edge per
     # launch, for the forward / d x' pass and for the weight-gradient pass alike)
     per_edge = 2.0 * (MODEL_CFG["num_gaussians"] * MODEL_CFG["num_filters"] + MODEL_CFG["num_filters"] ** 2)
@@ -619,9 +649,13 @@ def run_ours(args):
         # share of the device-side step: the eager pass is launch-bound on the host, so the kernel's time per step is
         # set against the graph-replayed step (back-to-back kernels), which is what the ncu launch list also measures
         "step_share": ((k_ms / ksteps) / (total_ms / args.steps)) if total_ms else None,
-        "timed_in": f"{ksteps} eager steps ({eager_ms / ksteps:.3f} ms/step) with CUDA events around every launch of the "
-                    f"listed kernels; `value` itself replays the same step from a CUDA graph" if use_graph else
-                    f"{ksteps} steps with CUDA events around every launch of the listed kernels",
+        "timed_in": (f"{ksteps} replays of the step's CUDA graph captured with external event-record nodes around every launch "
+                     f"of the listed kernels (back to back, as in the timed region; L2 flushed between replays)"
+                     if graph_timed is not None and graph_timed.acc else
+                     f"{ksteps} eager steps ({eager_ms / ksteps:.3f} ms/step) with CUDA events around every launch of the "
+                     f"listed kernels; `value` itself replays the same step from a CUDA graph" if use_graph else
+                     f"{ksteps} steps with CUDA events around every launch of the listed kernels"),
+        "eager_pass_avg_launch_us": {k: v["avg_launch_us"] for k, v in eager_summ.items()},
         "algorithmic_flops_per_step": algorithmic_flops(N, E),
         "step_tflops": algorithmic_flops(N, E) * args.steps / (total_ms * 1e-3) / 1e12,
     }

@@ -223,9 +223,13 @@ class KernelTimer:
     """Optional CUDA-event timing of selected entry points on the launching stream (bench.py uses it
     to measure the dominant kernel live, inside the timed region)."""
 
-    def __init__(self, names):
+    def __init__(self, names, external=False):
         self.names = set(names)
         self.records = []   # (name, start_event, end_event, work)
+        # external=True: the events become event-record NODES when the calls are captured into a CUDA graph
+        # (cudaEventRecordExternal), so the same records time every replay: call accumulate() after each replay + sync
+        self.external = bool(external)
+        self.acc = {}       # name -> [launches, total_ms, total_work, [durations]]
 
     def summary(self):
         """{name: (launches, total_ms, total_work)} - call after a device synchronise."""
@@ -234,6 +238,22 @@ class KernelTimer:
             n, ms, w = out.get(name, (0, 0.0, 0.0))
             out[name] = (n + 1, ms + e0.elapsed_time(e1), w + float(work))
         return out
+
+    def accumulate(self):
+        """Add the durations of the last graph replay (external mode) - call after a device synchronise."""
+        for name, e0, e1, work in self.records:
+            slot = self.acc.setdefault(name, [0, 0.0, 0.0, []])
+            ms = e0.elapsed_time(e1)
+            slot[0] += 1
+            slot[1] += ms
+            slot[2] += float(work)
+            slot[3].append(ms)
+
+    def summary_accumulated(self):
+        return {k: (v[0], v[1], v[2]) for k, v in self.acc.items()}
+
+    def medians_accumulated(self):
+        return {k: sorted(v[3])[len(v[3]) // 2] for k, v in self.acc.items()}
 
     def medians(self):
         """{name: median launch duration in ms} - call after a device synchronise."""
@@ -273,8 +293,8 @@ def call(name, *args, work=0.0):
     fn = getattr(lib(), name)
     t = timer
     if t is not None and name in t.names:
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
+        e0 = torch.cuda.Event(enable_timing=True, external=t.external)
+        e1 = torch.cuda.Event(enable_timing=True, external=t.external)
         e0.record()
         rc = fn(*args, stream())
         e1.record()

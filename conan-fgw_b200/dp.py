@@ -134,7 +134,7 @@ class RegressionStep:
         if chk is not None:
             chk()
 
-    def capture(self, z, pos, batch, targets, num_graphs):
+    def capture(self, z, pos, batch, targets, num_graphs, timer=None):
         """Capture zero-grad + radius graph + forward + loss + backward into ONE CUDA graph (every entry point of
         the library is stream-ordered and sync-free on the bf16 path).  Later ``step`` calls with tensors of the same
         shapes copy their inputs into the static buffers and replay it; the gradient all-reduce and Adam follow
@@ -148,8 +148,14 @@ class RegressionStep:
                 self._fwd_bwd(*self._static, self._static_G)
         torch.cuda.current_stream().wait_stream(side)
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
-            self._static_loss = self._fwd_bwd(*self._static, self._static_G)
+        # timer: a _lib.KernelTimer(external=True) whose event records are captured as graph nodes around the selected
+        # launches (bench.py: per-kernel durations of the replayed step itself)
+        prev, _lib.timer = _lib.timer, timer
+        try:
+            with torch.cuda.graph(self._graph):
+                self._static_loss = self._fwd_bwd(*self._static, self._static_G)
+        finally:
+            _lib.timer = prev
         return self
 
     def step(self, z, pos, batch, targets, num_graphs):
