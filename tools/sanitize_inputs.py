@@ -17,9 +17,11 @@ for n, B, K in ((9, 2, 2), (27, 2, 1), (40, 1, 2)):
         if prec == "bf16" and not cmp._lib.lib().cmp_device_is_sm100():
             continue
         m.set_precision(prec)
-        # both kernels behind cmp_cfconv_dense_fwd: 0 = warp-specialised tile pipeline, 1 = per-pipeline
+        # both kernels behind cmp_cfconv_dense_fwd: 0 = warp-specialised tile pipeline, 1 = per-pipeline; with the atom
+        # bound promised (variant 0 pass) the weight gradients run on the dense-block kernel, without it on the pair list
         for variant in ((0, 1) if prec == "bf16" else (-1,)):
             cmp._lib.lib().cmp_debug_set_dense_variant(variant)
+            m.max_atoms_hint = n if variant == 0 else None
             m.zero_grad()
             out = m(b.z, b.pos, b.batch, num_graphs=b.num_graphs)
             out.pow(2).mean().backward()
