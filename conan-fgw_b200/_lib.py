@@ -86,6 +86,7 @@ SIGNATURES = {
     "cmp_debug_set_dense_pipes": (None, [I]),
     "cmp_debug_set_dense_mode": (None, [I]),
     "cmp_debug_set_dense_variant": (None, [I]),
+    "cmp_debug_set_dense_bwd_variant": (None, [I]),
     "cmp_csr_expand_rows": (I, [P, L, P, P]),
     "cmp_cfconv_tc_bwd_tile_edges": (I, []),
     "cmp_build_flat_tiles_workspace": (S, [L]),

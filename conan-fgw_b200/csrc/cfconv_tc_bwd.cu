@@ -1272,6 +1272,476 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_bwd_kernel(const 
   if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
 }
 
+
+// =================================================================================================================
+// Warp-specialised dense weight gradients: ONE stream of 64-column tiles per CTA, every phase on its own warps
+// =================================================================================================================
+// cfconv_dense_bwd_kernel runs the phases of a tile one after the other on the 256 threads of a group (two groups per
+// CTA): ~13 K cycles per tile and group, issue slots 49 % busy, the da' MMA round trip exposed in every tile.  Here the
+// tiles of a CTA flow through warp groups that only meet at mbarriers (the recipe of cfconv_dense_ws_kernel):
+//   XG  (4 warps, 2 threads per column)  pair -> adjacency bits, distance, cutoff, Gaussians -> R[k & 1], cutoffs / masks
+//   DF  (4 warps, thread = channel)      dF from the fp32 rows of g and x' in registers -> F[k & 1]; db2
+//   MMA (1 thread)                       h[k & 1] = W1 R;  da'[k & 1] = W2^T F;  dW2 += F A^T,  dW1 += H R^T
+//   EP1 (4 warps, thread = channel)      h -> a' = C ssp(h) -> A[k & 1]
+//   EP3 (4 warps, thread = channel)      h, da' -> dh = da' C sigmoid(h) -> H[k & 1]; db1   (sigmoid recomputed from h: no
+//                                        S image, which pays for double buffering every other image)
+// Every image, h and da' are double buffered (TMEM: 2 x 64 + 2 x 64 + 128 + 64 = 448 columns), so a tile's Gaussians, dF,
+// both epilogues and all three MMA groups overlap those of its neighbours.  All roles walk the same tile sequence; tile k
+// of the CTA uses buffer k & 1 and completion number k >> 1 of that buffer's barriers.
+// MEASURED SLOWER than cfconv_dense_bwd_kernel (cfg 2: 150 us against 89 us) and therefore NOT the default
+// (cmp_debug_set_dense_bwd_variant(1) selects it; the tests run both): with two tiles in flight the chain
+// XG -> DF -> da' MMA -> EP3 -> weight-gradient MMAs -> w_done -> XG(k + 2) is serial per buffer and every link runs on 4
+// warps instead of 8.  A third set of images would fit in shared memory (3 x 56 KB), a third h / da' pair not in TMEM.
+//   r_ready[s]  XG  -> MMA, DF         R[s], cutoffs, masks of tile k written                      (128 arrivals)
+//   df_ready[s] DF  -> MMA             F[s] written                                               (128)
+//   d1_ready[s] MMA -> EP1, EP3        h[s] holds tile k                                          (commit)
+//   dda_ready[s] MMA -> EP3            da'[s] holds tile k                                        (commit)
+//   a_ready[s]  EP1 -> MMA             A[s] written, h[s] read                                    (128)
+//   h_ready[s]  EP3 -> MMA             H[s] written, h[s] and da'[s] read                         (128)
+//   w_done[s]   MMA -> XG, DF, EP1, EP3  the weight-gradient MMAs of tile k have read R, F, A, H [s]   (commit)
+namespace bws {
+constexpr int W_XG = 0, W_DF = 4, W_EP1 = 8, W_EP3 = 12, W_MMA = 16, NWARPS = 17;
+constexpr int THREADS = NWARPS * 32;
+constexpr uint32_t OFF_R = 0;                              // 2 x R_BYTES
+constexpr uint32_t OFF_F = OFF_R + 2 * R_BYTES;            // 2 x CH_BYTES
+constexpr uint32_t OFF_A = OFF_F + 2 * CH_BYTES;           // 2 x CH_BYTES
+constexpr uint32_t OFF_H = OFF_A + 2 * CH_BYTES;           // 2 x CH_BYTES
+constexpr uint32_t OFF_POS = OFF_H + 2 * CH_BYTES;         // float[128][3]
+constexpr uint32_t OFF_ADJ = OFF_POS + DN_MAX * 12;        // uint32[128][4]
+constexpr uint32_t OFF_META = OFF_ADJ + DN_MAX * DN_AW * 4;   // 2 x { float C[64]; uint32 mask[4] }
+constexpr uint32_t META_BYTES = TE * 4 + 16;
+constexpr uint32_t BODY_BYTES = OFF_META + 2 * META_BYTES;
+constexpr uint32_t SMEM = W1_BYTES + W2T_BYTES + (BODY_BYTES + 127) / 128 * 128;
+static_assert(SMEM <= 232448 - 1024, "shared memory budget of the warp-specialised weight-gradient kernel");
+// barrier slots
+constexpr int B_W = 0, B_R = 1, B_DF = 3, B_D1 = 5, B_DDA = 7, B_A = 9, B_H = 11, B_WD = 13, NBARS = 15;
+}  // namespace bws
+
+// a' = c ssp(x) of two columns in packed f16x2 (see ssp_sigmoid_f16x2), returned as a bf16x2 image word
+__device__ __forceinline__ uint32_t ssp_f16x2_bf16(float x0, float x1, float c0, float c1) {
+  const __half2 x = __floats2half2_rn(x0, x1);
+  const __half2 c = __floats2half2_rn(c0, c1);
+  uint32_t tu;
+  const __half2 arg = __hmul2(__habs2(x), __float2half2_rn(-1.4426950408889634f));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(tu) : "r"(*reinterpret_cast<const uint32_t*>(&arg)));
+  const __half2 t = *reinterpret_cast<const __half2*>(&tu);
+  __half2 q = __hfma2(__float2half2_rn(0.0599455865f), t, __float2half2_rn(-0.227712643f));
+  q = __hfma2(q, t, __float2half2_rn(0.442274178f));
+  q = __hfma2(q, t, __float2half2_rn(-0.717063932f));
+  q = __hfma2(q, t, __float2half2_rn(1.44261568f));
+  const __half2 l2m1 = __hfma2(q, t, __float2half2_rn(-1.0f));                         // log2(1 + t) - 1
+  const __half2 sp = __hfma2(l2m1, __float2half2_rn(0.6931471805599453f), __hmax2(x, __float2half2_rn(0.0f)));
+  const float2 af = __half22float2(__hmul2(sp, c));
+  return tc::pack_bf16x2(af.x, af.y);
+}
+// c sigmoid(x) of two columns (sigmoid = 1/2 + tanh(x / 2) / 2, one tanh.approx.f16x2), as two floats
+__device__ __forceinline__ float2 csigmoid_f16x2(float x0, float x1, float c0, float c1) {
+  const __half2 hx = __hmul2(__floats2half2_rn(x0, x1), __float2half2_rn(0.5f));
+  uint32_t au;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(au) : "r"(*reinterpret_cast<const uint32_t*>(&hx)));
+  const __half2 sg = __hfma2(*reinterpret_cast<const __half2*>(&au), __float2half2_rn(0.5f), __float2half2_rn(0.5f));
+  const float2 sf = __half22float2(__hmul2(sg, __floats2half2_rn(c0, c1)));
+  return sf;
+}
+
+__global__ void __launch_bounds__(bws::THREADS, 1) cfconv_dense_bwd_ws_kernel(const __grid_constant__ DenseBwdParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bars[bws::NBARS];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_offset[K1];
+  __shared__ __align__(16) float s_c2[K1];
+
+  uint8_t* sW1 = smem;
+  uint8_t* sW2T = smem + W1_BYTES;
+  uint8_t* sB = smem + W1_BYTES + W2T_BYTES;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int wq = warp & 3;
+
+  if (tid == 0) {
+    tc::mbar_init(&bars[bws::B_W], 1);
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&bars[bws::B_R + s], 128);
+      tc::mbar_init(&bars[bws::B_DF + s], 128);
+      tc::mbar_init(&bars[bws::B_D1 + s], 1);
+      tc::mbar_init(&bars[bws::B_DDA + s], 1);
+      tc::mbar_init(&bars[bws::B_A + s], 128);
+      tc::mbar_init(&bars[bws::B_H + s], 128);
+      tc::mbar_init(&bars[bws::B_WD + s], 1);
+    }
+    tc::mbar_fence_init();
+  }
+  if (tid < K1) {
+    s_offset[tid] = (tid < p.Ng) ? p.offset[tid] : 0.0f;
+    s_c2[tid] = (tid < p.Ng) ? p.coeff_log2e : 0.0f;
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t tH0 = tmem_base, tDA0 = tmem_base + 128, tW2 = tmem_base + 256, tW1 = tmem_base + 384;
+
+  const int64_t T = __ldg(p.tile_ptr + p.G);
+  const int64_t U = gridDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * T / U, t1 = ((int64_t)blockIdx.x + 1) * T / U;
+  const uint32_t nt = (uint32_t)(t1 - t0);           // tiles of this CTA
+  const int k1steps = (p.Ng + 1 + 15) >> 4;
+  // parity of completion number (k >> 1) of a buffer-k&1 barrier, and of the one two tiles earlier
+  auto par_now = [](uint32_t k) { return (k >> 1) & 1u; };
+  auto par_prev = [](uint32_t k) { return ((k >> 1) - 1u) & 1u; };
+
+  if (warp < bws::W_DF) {
+    // ================================ XG: Gaussians, cutoff, direction masks ================================
+    const int t = tid;                       // 0..127
+    const int e = t & 63, q = t >> 6;        // column, and which half of the K chunks this thread writes
+    float* sPos = reinterpret_cast<float*>(sB + bws::OFF_POS);
+    uint32_t* sAdj = reinterpret_cast<uint32_t*>(sB + bws::OFF_ADJ);
+    const float cutoff = p.cutoff;
+    int staged_conf = -1;
+    DenseWalk w;
+    if (nt > 0) w.seek(p, t0);
+    for (uint32_t k = 0; k < nt; ++k) {
+      const uint32_t s = k & 1u;
+      bool diag;
+      int c_base, j0, ncols;
+      w.tile(diag, c_base, j0, ncols);
+      const int cs = w.cs, n = w.n, a0 = w.a0, conf = w.conf;
+      const int npad = (ncols + 15) & ~15;
+      uint8_t* sR = sB + bws::OFF_R + s * R_BYTES;
+      float* sC = reinterpret_cast<float*>(sB + bws::OFF_META + s * bws::META_BYTES);
+      uint32_t* sMask = reinterpret_cast<uint32_t*>(sC + TE);
+      if (conf != staged_conf) {
+        staged_conf = conf;
+        tc::named_bar_sync(1, 128);          // nobody still reads the previous conformer's copy
+        if (t < n) {
+          const float* pp = p.pos + (int64_t)(cs + t) * 3;
+          sPos[3 * t + 0] = __ldg(pp + 0);
+          sPos[3 * t + 1] = __ldg(pp + 1);
+          sPos[3 * t + 2] = __ldg(pp + 2);
+          reinterpret_cast<uint4*>(sAdj)[t] = __ldg(reinterpret_cast<const uint4*>(p.adj) + cs + t);
+        }
+        tc::named_bar_sync(1, 128);
+      }
+      int il, jl, i_loc, j_loc;
+      if (diag) {
+        const int c = min(c_base + e, 119);
+        jl = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)c)) * 0.5f);
+        if (jl * (jl - 1) / 2 > c) --jl;
+        if ((jl + 1) * jl / 2 <= c) ++jl;
+        il = c - jl * (jl - 1) / 2;
+        i_loc = a0 + il;
+        j_loc = a0 + jl;
+      } else {
+        il = e & 15;
+        i_loc = a0 + il;
+        j_loc = j0 + (e >> 4);
+      }
+      bool ef = false, er = false;
+      if (e < ncols) {
+        ef = (sAdj[i_loc * DN_AW + (j_loc >> 5)] >> (j_loc & 31)) & 1u;     // edge j -> i
+        er = (sAdj[j_loc * DN_AW + (i_loc >> 5)] >> (i_loc & 31)) & 1u;     // edge i -> j
+      }
+      const bool live = ef || er;
+      float d = 0.0f;
+      if (live) {
+        const float dx = sPos[3 * j_loc] - sPos[3 * i_loc], dy = sPos[3 * j_loc + 1] - sPos[3 * i_loc + 1],
+                    dz = sPos[3 * j_loc + 2] - sPos[3 * i_loc + 2];
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        d = d2 * rsqrtf(fmaxf(d2, 1e-20f));
+      }
+      // the weight-gradient MMAs of tile k - 2 have read R[s]; everybody has read its cutoffs and masks
+      if (k >= 2) tc::mbar_wait(&bars[bws::B_WD + s], par_prev(k));
+      if (q == 0) {       // warps 0 and 1 hold columns 0..31 and 32..63 (whole warps: the ballots are uniform)
+        sC[e] = live ? 0.5f * (__cosf(d * kPi / cutoff) + 1.0f) : 0.0f;
+        const unsigned bf = __ballot_sync(0xffffffffu, ef), br = __ballot_sync(0xffffffffu, er);
+        if (lane == 0) {
+          sMask[e >> 5] = bf;
+          sMask[2 + (e >> 5)] = br;
+        }
+      }
+      if (e < npad) {
+        uint8_t* rowp = sR + (e >> 3) * 1024 + (e & 7) * 16;
+        for (int jc = q; jc < 2 * k1steps; jc += 2) {
+          float v[8];
+          const float4* op = reinterpret_cast<const float4*>(s_offset + jc * 8);
+          const float4* cp2 = reinterpret_cast<const float4*>(s_c2 + jc * 8);
+          const float4 o0 = op[0], o1 = op[1], k0 = cp2[0], k1 = cp2[1];
+          const float off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+          const float ck[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float x = d - off[j];
+            v[j] = live ? tc::fast_ex2(ck[j] * (x * x)) : 0.0f;
+          }
+          *reinterpret_cast<uint4*>(rowp + jc * 128) = pack_bf16x8(v);
+        }
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&bars[bws::B_R + s]);
+      if (k + 1 < nt) w.next(p);
+    }
+  } else if (warp < bws::W_EP1) {
+    // ================================ DF: dF image from the row registers ================================
+    const int chan = tid - bws::W_DF * 32;
+    float gr[16], xr[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) gr[i] = xr[i] = 0.0f;
+    float db2 = 0.0f;
+    int rows_conf = -1, rows_a0 = -1;
+    DenseWalk w;
+    if (nt > 0) w.seek(p, t0);
+    for (uint32_t k = 0; k < nt; ++k) {
+      const uint32_t s = k & 1u;
+      bool diag;
+      int c_base, j0, ncols;
+      w.tile(diag, c_base, j0, ncols);
+      const int cs = w.cs, n = w.n, a0 = w.a0, conf = w.conf;
+      const int m = min(16, n - a0);
+      const int npad = (ncols + 15) & ~15;
+      const int goff = (cs + a0) * F + chan;
+      if (conf != rows_conf || a0 != rows_a0) {
+        rows_conf = conf;
+        rows_a0 = a0;
+#pragma unroll
+        for (int il = 0; il < 16; ++il) {
+          gr[il] = (il < m) ? __ldg(p.g + goff + il * F) : 0.0f;
+          xr[il] = (il < m) ? __ldg(p.xprime + goff + il * F) : 0.0f;
+        }
+      }
+      float gj[4] = {0.0f, 0.0f, 0.0f, 0.0f}, xj[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (!diag) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int a = j0 + jj;
+          if (a < n) {
+            gj[jj] = __ldg(p.g + (cs + a) * F + chan);
+            xj[jj] = __ldg(p.xprime + (cs + a) * F + chan);
+          }
+        }
+      }
+      const float* sC = reinterpret_cast<const float*>(sB + bws::OFF_META + s * bws::META_BYTES);
+      const uint32_t* sMask = reinterpret_cast<const uint32_t*>(sC + TE);
+      uint8_t* dstF = sB + bws::OFF_F + s * CH_BYTES + chan * 16;
+      tc::mbar_wait(&bars[bws::B_R + s], par_now(k));                    // cutoffs and masks of tile k
+      if (k >= 2) tc::mbar_wait(&bars[bws::B_WD + s], par_prev(k));      // F[s] free
+      const uint32_t mf0 = sMask[0], mf1 = sMask[1], mr0 = sMask[2], mr1 = sMask[3];
+      if (!diag) {
+        const float gj0[2] = {gj[0], gj[1]}, xj0[2] = {xj[0], xj[1]}, gj1[2] = {gj[2], gj[3]}, xj1[2] = {xj[2], xj[3]};
+        dense_df_rect(gr, xr, gj0, xj0, mf0, mr0, sC, dstF, db2);
+        if (npad > 32) dense_df_rect(gr, xr, gj1, xj1, mf1, mr1, sC + 32, dstF + 4 * 2048, db2);
+      } else if (c_base == 0) {
+        dense_df_diag<0>(gr, xr, mf0, mr0, sC, dstF, db2);
+        if (npad > 32) dense_df_diag<32>(gr, xr, mf1, mr1, sC + 32, dstF + 4 * 2048, db2);
+      } else {
+        dense_df_diag<64>(gr, xr, mf0, mr0, sC, dstF, db2);
+        if (npad > 32) dense_df_diag<96>(gr, xr, mf1, mr1, sC + 32, dstF + 4 * 2048, db2);
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&bars[bws::B_DF + s]);
+      if (k + 1 < nt) w.next(p);
+    }
+    float* part = p.partial + (int64_t)blockIdx.x * PART_FLOATS;
+    part[F * F + F * K1 + chan] = db2;
+    part[F * F + F * K1 + F + chan] = 0.0f;
+  } else if (warp < bws::W_EP3) {
+    // ================================ EP1: h -> a' image; drains dW2 ================================
+    const int chan = tid - bws::W_EP1 * 32;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    DenseWalk w;
+    if (nt > 0) w.seek(p, t0);
+    for (uint32_t k = 0; k < nt; ++k) {
+      const uint32_t s = k & 1u;
+      bool diag;
+      int c_base, j0, ncols;
+      w.tile(diag, c_base, j0, ncols);
+      const int npad = (ncols + 15) & ~15;
+      const float* sC = reinterpret_cast<const float*>(sB + bws::OFF_META + s * bws::META_BYTES);
+      uint8_t* sA = sB + bws::OFF_A + s * CH_BYTES + chan * 16;
+      const uint32_t tH = tH0 + s * 64 + lane_off;
+      tc::mbar_wait(&bars[bws::B_D1 + s], par_now(k));                   // h[s] holds tile k
+      if (k >= 2) tc::mbar_wait(&bars[bws::B_WD + s], par_prev(k));      // A[s] free
+      tc::tc_fence_after();
+      for (int c0 = 0; c0 < npad; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(tH + c0, v);
+        float c[16];
+        const float4* cp = reinterpret_cast<const float4*>(sC + c0);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const float4 cc = cp[k4];
+          c[k4 * 4 + 0] = cc.x; c[k4 * 4 + 1] = cc.y; c[k4 * 4 + 2] = cc.z; c[k4 * 4 + 3] = cc.w;
+        }
+        tc::tmem_wait_ld();
+        uint32_t a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = ssp_f16x2_bf16(v[2 * j], v[2 * j + 1], c[2 * j], c[2 * j + 1]);
+        *reinterpret_cast<uint4*>(sA + (c0 >> 3) * 2048) = make_uint4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<uint4*>(sA + ((c0 >> 3) + 1) * 2048) = make_uint4(a[4], a[5], a[6], a[7]);
+      }
+      tc::tc_fence_before();
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&bars[bws::B_A + s]);
+      if (k + 1 < nt) w.next(p);
+    }
+    // drain dW2[f = chan][k = 0..127]
+    float* part = p.partial + (int64_t)blockIdx.x * PART_FLOATS;
+    if (nt > 0) {
+      tc::mbar_wait(&bars[bws::B_WD + ((nt - 1) & 1u)], par_now(nt - 1));
+      tc::tc_fence_after();
+    }
+    for (int c0 = 0; c0 < F; c0 += 16) {
+      float v[16];
+      if (nt > 0) {
+        tc::tmem_ld16(tW2 + lane_off + c0, v);
+        tc::tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(part + chan * F + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+  } else if (warp < bws::W_MMA) {
+    // ================================ EP3: h, da' -> dh image; db1; drains dW1 ================================
+    const int chan = tid - bws::W_EP3 * 32;
+    const uint32_t lane_off = (uint32_t)(wq * 32) << 16;
+    float db1 = 0.0f;
+    DenseWalk w;
+    if (nt > 0) w.seek(p, t0);
+    for (uint32_t k = 0; k < nt; ++k) {
+      const uint32_t s = k & 1u;
+      bool diag;
+      int c_base, j0, ncols;
+      w.tile(diag, c_base, j0, ncols);
+      const int npad = (ncols + 15) & ~15;
+      const float* sC = reinterpret_cast<const float*>(sB + bws::OFF_META + s * bws::META_BYTES);
+      uint8_t* sH = sB + bws::OFF_H + s * CH_BYTES + chan * 16;
+      const uint32_t tH = tH0 + s * 64 + lane_off, tDA = tDA0 + s * 64 + lane_off;
+      tc::mbar_wait(&bars[bws::B_D1 + s], par_now(k));                   // h[s]
+      tc::mbar_wait(&bars[bws::B_DDA + s], par_now(k));                  // da'[s]
+      if (k >= 2) tc::mbar_wait(&bars[bws::B_WD + s], par_prev(k));      // H[s] free
+      tc::tc_fence_after();
+      for (int c0 = 0; c0 < npad; c0 += 16) {
+        float hv[16], dv[16];
+        tc::tmem_ld16(tH + c0, hv);
+        tc::tmem_ld16(tDA + c0, dv);
+        float c[16];
+        const float4* cp = reinterpret_cast<const float4*>(sC + c0);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const float4 cc = cp[k4];
+          c[k4 * 4 + 0] = cc.x; c[k4 * 4 + 1] = cc.y; c[k4 * 4 + 2] = cc.z; c[k4 * 4 + 3] = cc.w;
+        }
+        tc::tmem_wait_ld();
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 sg = csigmoid_f16x2(hv[2 * j], hv[2 * j + 1], c[2 * j], c[2 * j + 1]);
+          o[2 * j] = dv[2 * j] * sg.x;
+          o[2 * j + 1] = dv[2 * j + 1] * sg.y;
+          db1 += o[2 * j] + o[2 * j + 1];
+        }
+        *reinterpret_cast<uint4*>(sH + (c0 >> 3) * 2048) = pack_bf16x8(o);
+        *reinterpret_cast<uint4*>(sH + ((c0 >> 3) + 1) * 2048) = pack_bf16x8(o + 8);
+      }
+      tc::tc_fence_before();
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&bars[bws::B_H + s]);
+      if (k + 1 < nt) w.next(p);
+    }
+    // drain dW1[k = chan][j = 0..63]
+    float* part = p.partial + (int64_t)blockIdx.x * PART_FLOATS;
+    if (nt > 0) {
+      tc::mbar_wait(&bars[bws::B_WD + ((nt - 1) & 1u)], par_now(nt - 1));
+      tc::tc_fence_after();
+    }
+    for (int c0 = 0; c0 < K1; c0 += 16) {
+      float v[16];
+      if (nt > 0) {
+        tc::tmem_ld16(tW1 + lane_off + c0, v);
+        tc::tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(part + F * F + chan * K1 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    part[F * F + F * K1 + 2 * F + chan] = db1;
+    part[F * F + F * K1 + 3 * F + chan] = 0.0f;
+  } else {
+    // ================================ MMA: one thread issues everything ================================
+    if (lane == 0) {
+      tc::mbar_arrive_expect_tx(&bars[bws::B_W], W1_BYTES + W2T_BYTES);
+      tc::bulk_g2s(sW1, p.weights, W1_BYTES, &bars[bws::B_W]);
+      tc::bulk_g2s(sW2T, p.weights + W1_BYTES, W2T_BYTES, &bars[bws::B_W]);
+      const uint32_t aW1 = tc::smem_u32(sW1), aW2T = tc::smem_u32(sW2T), aB = tc::smem_u32(sB);
+      tc::mbar_wait(&bars[bws::B_W], 0);
+      DenseWalk w;
+      if (nt > 0) w.seek(p, t0);
+      int np_prev = 0;                       // width of tile k - 1
+      const uint32_t id3 = tc::umma_idesc_f16(F, F, 1, 0, 0);
+      const uint32_t id4 = tc::umma_idesc_f16(F, K1, 1, 0, 1);
+      auto weight_grads = [&](uint32_t j, int npad) {      // dW2 += F A^T, dW1 += H R^T of tile j
+        const uint32_t s = j & 1u;
+        tc::mbar_wait_spin(&bars[bws::B_A + s], par_now(j));
+        tc::mbar_wait_spin(&bars[bws::B_H + s], par_now(j));
+        tc::tc_fence_after();
+        const uint32_t aR = aB + bws::OFF_R + s * R_BYTES, aF = aB + bws::OFF_F + s * CH_BYTES,
+                       aA = aB + bws::OFF_A + s * CH_BYTES, aH = aB + bws::OFF_H + s * CH_BYTES;
+        for (int ks = 0; ks < (npad >> 4); ++ks) {
+          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+          tc::umma_f16(tW2, tc::umma_smem_desc(aF + ks * 4096, 2048, 128), tc::umma_smem_desc(aA + ks * 4096, 2048, 128), id3,
+                       acc);
+          tc::umma_f16(tW1, tc::umma_smem_desc(aH + ks * 4096, 2048, 128), tc::umma_smem_desc(aR + ks * 2048, 1024, 128), id4,
+                       acc);
+        }
+        tc::umma_commit(&bars[bws::B_WD + s]);
+      };
+      for (uint32_t k = 0; k < nt; ++k) {
+        const uint32_t s = k & 1u;
+        bool diag;
+        int c_base, j0, ncols;
+        w.tile(diag, c_base, j0, ncols);
+        const int npad = (ncols + 15) & ~15;
+        if (k + 1 < nt) w.next(p);
+        const uint32_t aR = aB + bws::OFF_R + s * R_BYTES, aF = aB + bws::OFF_F + s * CH_BYTES;
+        // h[s] = W1aug * rbf^T   (h[s] and da'[s] are free: the weight-gradient MMAs of tile k - 2, issued in the previous
+        // iteration, waited for both epilogues of that tile)
+        tc::mbar_wait_spin(&bars[bws::B_R + s], par_now(k));
+        tc::tc_fence_after();
+        const uint32_t id1 = tc::umma_idesc_f16(F, npad, 1, 0, 0);
+        for (int ks = 0; ks < k1steps; ++ks)
+          tc::umma_f16(tH0 + s * 64, tc::umma_smem_desc(aW1 + ks * 256, 128, 1024), tc::umma_smem_desc(aR + ks * 256, 128, 1024),
+                       id1, ks > 0);
+        tc::umma_commit(&bars[bws::B_D1 + s]);
+        // da'[s] = W2^T * dF
+        tc::mbar_wait_spin(&bars[bws::B_DF + s], par_now(k));
+        tc::tc_fence_after();
+        const uint32_t id2 = tc::umma_idesc_f16(F, npad, 1, 0, 1);
+#pragma unroll
+        for (int ks = 0; ks < F / 16; ++ks)
+          tc::umma_f16(tDA0 + s * 64, tc::umma_smem_desc(aW2T + ks * 256, 128, 2048),
+                       tc::umma_smem_desc(aF + ks * 256, 128, 2048), id2, ks > 0);
+        tc::umma_commit(&bars[bws::B_DDA + s]);
+        // weight gradients of the previous tile
+        if (k >= 1) weight_grads(k - 1, np_prev);
+        np_prev = npad;
+      }
+      if (nt >= 1) weight_grads(nt - 1, np_prev);
+    }
+    __syncwarp();
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 }  // namespace cmp
 
@@ -1472,6 +1942,9 @@ extern "C" int cmp_cfconv_tc_pack_bwd_weights_grouped(const void* jobs, int coun
   return CMP_OK;
 }
 
+static int g_dense_bwd_variant = 0;   // 0: two groups of 256 threads (default)   1: warp-specialised tile pipeline
+extern "C" void cmp_debug_set_dense_bwd_variant(int v) { g_dense_bwd_variant = v; }
+
 extern "C" size_t cmp_cfconv_dense_bwd_workspace(void) { return cmp_cfconv_fused_bwd_workspace(); }
 
 extern "C" int cmp_build_dense_bwd_tiles(const int32_t* seg_ptr, int64_t G, int32_t* tile_ptr, int32_t* status,
@@ -1503,7 +1976,9 @@ extern "C" int cmp_cfconv_dense_bwd_weights(const float* g, const float* xprime,
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(cfconv_dense_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D_SMEM_BYTES) !=
-        cudaSuccess) {
+            cudaSuccess ||
+        cudaFuncSetAttribute(cfconv_dense_bwd_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bws::SMEM) !=
+            cudaSuccess) {
       (void)cudaGetLastError();
       set_error("cmp_cfconv_dense_bwd_weights: cannot opt in to %u bytes of shared memory", D_SMEM_BYTES);
       return CMP_ECUDA;
@@ -1525,11 +2000,15 @@ extern "C" int cmp_cfconv_dense_bwd_weights(const float* g, const float* xprime,
   p.Ng = num_gaussians;
   p.G = (int)G;
   const int grid = sm_count();
-  cfconv_dense_bwd_kernel<<<grid, CTA_THREADS, D_SMEM_BYTES, st>>>(p);
+  const bool ws = g_dense_bwd_variant == 1;
+  if (ws)
+    cfconv_dense_bwd_ws_kernel<<<grid, bws::THREADS, bws::SMEM, st>>>(p);
+  else
+    cfconv_dense_bwd_kernel<<<grid, CTA_THREADS, D_SMEM_BYTES, st>>>(p);
   CMP_LAUNCH_CHECK("cmp_cfconv_dense_bwd_weights");
   const int total = F * F + F * K1 + 2 * F;
-  reduce_partials_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(p.partial, grid * NG, num_gaussians, dW1, db1, dW2,
-                                                                    db2);
+  reduce_partials_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(p.partial, ws ? grid : grid * NG, num_gaussians, dW1,
+                                                                    db1, dW2, db2);
   CMP_LAUNCH_CHECK("cmp_cfconv_dense_bwd_weights");
   return CMP_OK;
 }

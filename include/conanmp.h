@@ -529,6 +529,9 @@ void cmp_debug_set_dense_mode(int mode);
  * conformer exceeds 32 atoms - they then stay in registers -, the per-pipeline kernel otherwise), 0 = warp-specialised,
  * 1 = per-pipeline. */
 void cmp_debug_set_dense_variant(int variant);
+/* Kernel variant of cmp_cfconv_dense_bwd_weights: 0 = two groups of 256 threads that run the phases of a tile in sequence
+ * (default), 1 = warp-specialised tile pipeline (measured slower; kept for comparison). */
+void cmp_debug_set_dense_bwd_variant(int variant);
 /* Same for cmp_cfconv_fused_bwd_weights: 12 timestamps per tile (first 20 tiles), 240 int64. */
 void cmp_debug_set_bwd_timestamps(void* buf);
 

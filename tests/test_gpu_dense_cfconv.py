@@ -146,6 +146,14 @@ def test_adjacency_bits_equal_the_edge_list():
     assert torch.equal(adj.to(torch.int64) & 0xFFFFFFFF, want)
 
 
+@pytest.fixture(params=[0, 1], ids=["two-group", "warp-specialised"])
+def bwd_variant(request):
+    """Both kernels behind cmp_cfconv_dense_bwd_weights."""
+    cmp._lib.lib().cmp_debug_set_dense_bwd_variant(request.param)
+    yield request.param
+    cmp._lib.lib().cmp_debug_set_dense_bwd_variant(0)
+
+
 def _exact_weight_grads(blk, gs, nl, xp, g, cutoff):
     """Filter-MLP gradients through the exact-fp32 message kernels + autograd over materialised [E, F] rows."""
     ps = [t.detach().clone().requires_grad_(True) for t in (blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight,
@@ -161,7 +169,7 @@ def _exact_weight_grads(blk, gs, nl, xp, g, cutoff):
     (33, 2, 2, 10.0, 32), (45, 2, 2, 10.0, 32), (65, 2, 2, 10.0, 32), (45, 2, 2, 5.0, 32), (128, 1, 1, 10.0, 32),
     (40, 2, 2, 10.0, 8),
 ])
-def test_dense_weight_gradients_match_the_exact_path(n, B, K, cutoff, max_nb):
+def test_dense_weight_gradients_match_the_exact_path(n, B, K, cutoff, max_nb, bwd_variant):
     """cmp_cfconv_dense_bwd_weights (fp32 rows of g / x' in registers, columns over the dense blocks) against the exact
     gradients and against the pair-list kernel.  Stated tolerance of the bf16 operand images: 1e-2 relative."""
     _need_sm100()
@@ -193,7 +201,7 @@ def test_dense_weight_gradients_match_the_exact_path(n, B, K, cutoff, max_nb):
     assert res[True][4] < res[False][4]
 
 
-def test_dense_weight_gradients_on_a_ragged_batch():
+def test_dense_weight_gradients_on_a_ragged_batch(bwd_variant):
     _need_sm100()
     sizes = [1, 27, 5, 64, 1, 33, 18, 2, 17, 32, 1, 128, 3]
     pos = torch.cat([syn.make_batch(1, 1, n, seed=20 + i).pos for i, n in enumerate(sizes)]).to(DEV)
