@@ -40,7 +40,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc not found: cannot build libconanmp.so")
     os.makedirs(LIB_DIR, exist_ok=True)
     tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(_ROOT, "include"), "-I", CSRC, "-o", tmp, *sources()]
+    extra = os.environ.get("CMP_NVCC_EXTRA", "").split()      # e.g. -DEP1_VARIANT=1 for kernel experiments
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", os.path.join(_ROOT, "include"), "-I", CSRC, "-o", tmp, *sources()]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

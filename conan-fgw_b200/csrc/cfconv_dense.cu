@@ -166,12 +166,12 @@ __device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<
 __device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<const uint32_t*>(&h); }
 
 // Epilogue 1 on NC columns of this thread's TMEM lane (pre-activations x, already scaled by log2 e):
-//   t = 2^-|x| on MUFU (fp32), then in packed f16x2   a' = C (max(x, 0) + t Q3(t) - 1),   Q3 ~ log2(1 + t) / t.
+//   t = 2^-|x| on MUFU (fp32), then in packed f16x2   a' = C (max(x, 0) - 1 + t + t (Q3(t) - 1)),   Q3 ~ log2(1 + t) / t.
 // All NC / 2 pair chains are independent: the packed-half work of the first pairs overlaps the MUFUs of the later ones.
 template <int NC>
 __device__ __forceinline__ void ep1_chunk(const float (&v)[NC], const uint32_t (&cw)[NC / 2], uint32_t (&o)[NC / 2]) {
   const __half2 k3 = __float2half2_rn(-0.08479055f), k2 = __float2half2_rn(0.32563294f),
-                k1 = __float2half2_rn(-0.67996303f), k0 = __float2half2_rn(1.43901745f), zero = __float2half2_rn(0.0f);
+                k1 = __float2half2_rn(-0.67996303f), k0m1 = __float2half2_rn(0.43901745f), one = __float2half2_rn(1.0f);
   uint32_t th[NC / 2];
 #pragma unroll
   for (int j = 0; j < NC / 2; ++j)
@@ -179,11 +179,15 @@ __device__ __forceinline__ void ep1_chunk(const float (&v)[NC], const uint32_t (
 #pragma unroll
   for (int j = 0; j < NC / 2; ++j) {
     const __half2 t = as_h2(th[j]);
-    __half2 q = __hfma2(k3, t, k2);
-    q = __hfma2(q, t, k1);
-    q = __hfma2(q, t, k0);
-    q = __hfma2(t, q, __hmax2(as_h2(pack_f16x2(v[2 * j], v[2 * j + 1])), zero));
-    o[j] = as_u32(__hfma2(q, as_h2(cw[j]), __hneg2(as_h2(cw[j]))));
+    // log2(1 + t) - 1 = (t - 1) + t (k0 - 1 + t (k1 + t (k2 + t k3))): every intermediate stays below 1/2 in magnitude, so the
+    // f16 roundings of the polynomial stay near 1e-4 (evaluating t (k0 + ...) directly rounds at magnitude ~1.4 and cost a
+    // factor 2.4 in the error of the whole model: embeddings 1.25e-3 -> 5.4e-4, gradients 1.2e-2 -> 5.3e-3 vs the oracle)
+    __half2 u = __hfma2(k3, t, k2);
+    u = __hfma2(u, t, k1);
+    const __half2 w = __hfma2(u, t, k0m1);
+    const __half2 rm1 = __hmax2(__hsub2(as_h2(pack_f16x2(v[2 * j], v[2 * j + 1])), one), __hneg2(one));   // max(x, 0) - 1
+    const __half2 sp = __hfma2(t, w, __hadd2(rm1, t));
+    o[j] = as_u32(__hmul2(sp, as_h2(cw[j])));
   }
 }
 
