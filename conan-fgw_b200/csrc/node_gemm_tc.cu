@@ -35,10 +35,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // fp32 tile [TM atoms, C channels] -> bf16 hi / lo K-major images (rows = atoms):
 //   byte(a, c) = (a%8)*16 + (c%8)*2 + (a/8)*sbo + (c/8)*128
 // when ones_chunk >= 0 that 16-byte chunk of every row is set to {1, 0, 0, ...} (hi) / 0 (lo).
-template <int ROWS, int NW = CW>
+struct NoWait {
+  __device__ __forceinline__ void operator()() const {}
+};
+// `after_loads` runs once, after the first batch of global loads has been issued and before anything is written to the
+// images: the place to wait for the previous reader of the images, so that the loads overlap its tail.
+template <int ROWS, int NW = CW, class AfterLoads = NoWait>
 __device__ __forceinline__ void convert_tile(const float* __restrict__ X, int64_t ld, const float* __restrict__ Ysaved,
                                              int64_t ldys, int64_t m0, int64_t M, int C, uint32_t sbo, uint8_t* hi,
-                                             uint8_t* lo, int ones_chunk, int warp, int lane) {
+                                             uint8_t* lo, int ones_chunk, int warp, int lane,
+                                             AfterLoads after_loads = AfterLoads()) {
   const int nchunk = C >> 3;
   const int cbs = (nchunk + 3) >> 2;
   const int al = lane & 7, cl = lane >> 3;
@@ -66,6 +72,7 @@ __device__ __forceinline__ void convert_tile(const float* __restrict__ X, int64_
        }
      }
    }
+   if (base == warp) after_loads();
 #pragma unroll
    for (int u = 0; u < UN; ++u) {
     const int wi = base + u * NW;
@@ -181,8 +188,11 @@ __global__ void __launch_bounds__(NT, 2) node_gemm_fwd_kernel(const FwdParams p)
     uint32_t it = 0;
     for (int64_t ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
       const int64_t m0 = ti * TMF;
-      if (it > 0) tc::named_bar_sync(1, CW * 32);   // everyone finished reading TMEM / previous images consumed
-      convert_tile<TMF>(p.X, p.ldx, p.saved_y, p.ldys, m0, p.M, K, sbo, sXh, sXl, -1, warp, lane);
+      // everyone finished reading TMEM / previous images consumed - checked between this tile's loads and its image writes
+      auto images_free = [&]() {
+        if (it > 0) tc::named_bar_sync(1, CW * 32);
+      };
+      convert_tile<TMF, CW>(p.X, p.ldx, p.saved_y, p.ldys, m0, p.M, K, sbo, sXh, sXl, -1, warp, lane, images_free);
       tc::fence_proxy_async();
       tc::mbar_arrive(&bars[1]);
       tc::mbar_wait(&bars[2], it & 1);
@@ -281,8 +291,12 @@ __device__ __forceinline__ void node_dw_body(const DwParams& p, int rank, int nr
     uint32_t it = 0;
     for (int64_t ti = t0; ti < t1; ++ti, ++it) {
       const int64_t m0 = ti * TM;
-      if (it > 0) tc::mbar_wait(&bars[1], (it - 1) & 1);   // previous MMAs done reading the images
-      convert_tile<TM>(p.dY, p.lddy, p.saved_y, p.ldys, m0, p.M, Nout, sbo_y, sYh, sYl, -1, warp, lane);
+      // the previous tile's MMAs must be done reading the images before they are rewritten - but not before the loads of
+      // this tile are issued: they are in flight while those MMAs finish
+      auto images_free = [&]() {
+        if (it > 0) tc::mbar_wait(&bars[1], (it - 1) & 1);
+      };
+      convert_tile<TM, CW>(p.dY, p.lddy, p.saved_y, p.ldys, m0, p.M, Nout, sbo_y, sYh, sYl, -1, warp, lane, images_free);
       convert_tile<TM>(p.X, p.ldx, nullptr, 0, m0, p.M, K, sbo_x, sXh, sXl, K >> 3, warp, lane);
       tc::fence_proxy_async();
       tc::mbar_arrive(&bars[0]);
@@ -418,8 +432,12 @@ __global__ void __launch_bounds__(NTC, 1) node_chain_kernel(const __grid_constan
       const int64_t m0 = ti * TMF;
       // the last stage of the previous tile was read out of TMEM by every thread before anyone arrives on xready below;
       // its MMAs (the only readers of the images) completed before that read-out
-      if (n > 0) tc::named_bar_sync(1, CWC * 32);
-      convert_tile<TMF, CWC>(p.X, p.ldx, nullptr, 0, m0, p.M, p.st[0].K, (uint32_t)(p.st[0].K >> 3) * 128, sXh, sXl, -1, warp, lane);
+      // (the barrier sits between the global loads of this tile and the first write to the images)
+      auto images_free = [&]() {
+        if (n > 0) tc::named_bar_sync(1, CWC * 32);
+      };
+      convert_tile<TMF, CWC>(p.X, p.ldx, nullptr, 0, m0, p.M, p.st[0].K, (uint32_t)(p.st[0].K >> 3) * 128, sXh, sXl, -1, warp, lane,
+                             images_free);
       tc::fence_proxy_async();
       tc::mbar_arrive(&bars[MAXS]);
       for (int s = 0; s < p.nstages; ++s, ++n) {
