@@ -687,7 +687,9 @@ def run_ours(args):
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "other_mode": other_mode, "visnet": visnet, "configs": extra_configs,
         "tolerance": {"fp32": "1e-5 relative vs oracle (tests/test_gpu_schnet.py)",
-                      "bf16": "5e-3 relative on embeddings, 2e-2 on gradients vs oracle (tests/test_gpu_fused.py)"},
+                      "bf16": "fused mode: 5e-3 relative on embeddings, 2e-2 on gradients vs the oracle on small batches "
+                              "(tests/test_gpu_fused.py); at this workload's full size 7.5e-3 per parameter against the exact "
+                              "mode (measured: embeddings 1.7e-3, worst gradient 4.9e-3; profiles/r02_fused_gradient_errors.md)"},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

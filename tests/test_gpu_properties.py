@@ -164,8 +164,8 @@ def test_fused_mode_gradients_at_the_bench_size():
     """Every parameter gradient of the fused (f16 filter MLP) mode against the exact-fp32 GPU mode on the FULL cfg 2
     batch (640 conformers, 449 K edges, T = 6): the weight gradients sum over all edges there, so a systematic rounding
     bias would show up that the 8-molecule oracle comparison cannot see.  Stated tolerance: 5e-3 relative
-    (max|a-b| / max|b|) and 5e-3 per conformer row on the embeddings; 1e-2 per parameter on the gradients (measured
-    worst case 6.4e-3, the W2 gradient of block 4: the weight-gradient kernel still rounds g and x' to bf16)."""
+    (max|a-b| / max|b|) and 5e-3 per conformer row on the embeddings; 7.5e-3 per parameter on the gradients (measured:
+    embeddings 1.7e-3, worst gradient 4.9e-3 - `profiles/r02_fused_gradient_errors.md` has the per-parameter table)."""
     if not cmp._lib.lib().cmp_device_is_sm100():
         pytest.skip("tcgen05 kernels need an sm_100 device")
     from conftest import row_rel_err
@@ -183,4 +183,4 @@ def test_fused_mode_gradients_at_the_bench_size():
     m.check_status()
     assert rel_err(got, want) < 5e-3 and row_rel_err(got, want) < 5e-3
     worst = max((rel_err(p.grad, ref[k]), k) for k, p in m.named_parameters() if k in ref)
-    assert worst[0] < 1e-2, worst
+    assert worst[0] < 7.5e-3, worst
