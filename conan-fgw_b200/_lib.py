@@ -116,6 +116,10 @@ SIGNATURES = {
     "cmp_cfconv_dense_pack_weights": (I, [P, P, P, P, I, I, P, P]),
     "cmp_cfconv_dense_pack_weights_grouped": (I, [P, I, I, I, P]),
     "cmp_cfconv_dense_fwd": (I, [P, P, P, P, L, P, P, I, F, F, I, I, I, I, P, P, P, P]),
+    "cmp_cfconv_dense_x3_weights_bytes": (S, []),
+    "cmp_cfconv_dense_x3_pack_weights": (I, [P, P, P, P, I, I, P, P]),
+    "cmp_cfconv_dense_x3_pack_weights_grouped": (I, [P, I, I, I, P]),
+    "cmp_cfconv_dense_x3_fwd": (I, [P, P, P, P, L, P, P, I, F, F, I, I, I, P, P, P, P]),
     "cmp_cfconv_dense_bwd_workspace": (S, []),
     "cmp_build_dense_bwd_tiles": (I, [P, L, P, P, P]),
     "cmp_cfconv_dense_bwd_weights": (I, [P, P, P, P, P, P, L, P, P, I, F, F, I, P, P, P, P, P, S, P]),

@@ -634,6 +634,336 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_kernel(const __gr
 
 
 // =================================================================================================================
+// fp32-grade variant ("x3"): every MMA operand split into f16 hi + lo, three passes per product, fp32 epilogues
+// =================================================================================================================
+// cfconv_dense_kernel rounds the Gaussians, the hidden activations a' and both weight matrices to f16 (11 significant
+// bits) and evaluates the softplus in packed f16: 5e-4 on the embeddings.  This variant keeps the whole structure (tiles,
+// pair <-> column maps, three independent pipelines, register-resident epilogue 2) but is fp32-grade end to end:
+//   * every operand image exists twice, hi = f16(v) and lo = f16(v - hi) (22 significant bits together), and every
+//     product runs as three MMAs into the same TMEM accumulator:  A B ~ Ah Bh + Al Bh + Ah Bl  (the dropped Al Bl term is
+//     2^-22 relative); the tensor pipe of the f16 kernel idles 88 % of the time, so the two extra passes are cheap;
+//   * distances exactly as the neighbour search stores them (sqrtf of the same expression), the cosine cutoff with cosf,
+//     one MUFU.EX2 per Gaussian on (d - mu_k) formed BEFORE scaling (no recurrence);
+//   * epilogue 1 in fp32: a' = C (max(x, 0) + lg2(1 + 2^-|x|) - 1), then split.
+// Shared memory: the two W1 and two W2 images take 104 KB, so a pipeline keeps the a' images of HALF a tile (64 columns,
+// hi + lo = 36 KB; the rbf images alias them) and runs epilogue 1 / the second product in two halves: D2 of the first half
+// overwrites only the D1 columns epilogue 1 has already consumed.
+namespace x3 {
+constexpr int HC = 64;                                     // columns per a' half
+constexpr uint32_t OFF_W1L = W1_BYTES, OFF_W2H = 2 * W1_BYTES, OFF_W2L = 2 * W1_BYTES + W2_BYTES;
+constexpr uint32_t W_BYTES = 2 * (W1_BYTES + W2_BYTES);    // W1 hi | W1 lo | W2 hi | W2 lo
+constexpr uint32_t AH_BYTES = (HC / 8) * A2_SBO;           // 18432: a' image of 64 columns (MN-major [144, 64])
+constexpr uint32_t B1I_BYTES = TE * K1 * 2;                // 16384: rbf image (K-major [128, 64])
+constexpr uint32_t IMG = 2 * AH_BYTES;
+static_assert(2 * B1I_BYTES <= IMG, "the rbf images alias the a' images");
+constexpr uint32_t OFF_C = IMG;                            // float[128]  cosine cutoff of every column
+constexpr uint32_t OFF_POS = OFF_C + TE * 4;
+constexpr uint32_t OFF_ADJ = OFF_POS + NMAX * 12;
+constexpr uint32_t OFF_MASK = OFF_ADJ + NMAX * AW * 4;
+constexpr uint32_t OFF_MISC = OFF_MASK + 64;
+constexpr uint32_t PIPE = (OFF_MISC + 16 + 127) / 128 * 128;
+constexpr uint32_t SMEM = W_BYTES + NP * PIPE;
+static_assert(SMEM <= 232448 - 1024, "shared memory budget");
+}  // namespace x3
+
+// hi = f16(a), lo = f16(a - hi) of two values, as packed image words
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  hi = as_u32(h);
+  lo = as_u32(__floats2half2_rn(a - hf.x, b - hf.y));
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_x3_kernel(const __grid_constant__ DenseParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bars[1 + NP * 3];   // wbar | per pipeline: d1ready, d2ready, half_done
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = warp >> 2;                 // pipeline
+  const int t = tid & (PT - 1);            // filter channel (TMEM lane) = pair column in the rbf phase
+  const int wq = warp & 3;                 // TMEM lane quarter of this warp
+
+  if (tid == 0) {
+    for (int q = 0; q < 1 + NP * 3; ++q) tc::mbar_init(&bars[q], 1);
+    tc::mbar_fence_init();
+    tc::mbar_arrive_expect_tx(&bars[0], x3::W_BYTES);
+    tc::bulk_g2s(smem, p.weights, x3::W_BYTES / 2, &bars[0]);
+    tc::bulk_g2s(smem + x3::W_BYTES / 2, p.weights + x3::W_BYTES / 2, x3::W_BYTES / 2, &bars[0]);
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+
+  const int bar_id = 1 + g;
+  const uint32_t dcol = tmem_base_s + g * TE;                       // MMA destination (lane 0)
+  const uint32_t dtm = dcol + ((uint32_t)(wq * 32) << 16);          // this warp's lanes
+  uint32_t aW = tc::smem_u32(smem);
+  uint32_t aB = aW + x3::W_BYTES + (uint32_t)g * x3::PIPE;          // this pipeline's private block
+  asm volatile("mov.u32 %0, %0;" : "+r"(aB));
+  asm volatile("mov.u32 %0, %0;" : "+r"(aW));
+  uint32_t aBar = tc::smem_u32(&bars[1 + 3 * g]);                   // d1ready, d2ready = + 8, half_done = + 16
+  asm volatile("mov.u32 %0, %0;" : "+r"(aBar));
+  const uint32_t dpair = (uint32_t)diag_i(t) | ((uint32_t)diag_j(t) << 8);   // pair of column t in a DIAG tile
+
+  uint32_t mma_phase = 0;      // parity of d1ready / d2ready (one completion each per executed tile)
+  uint32_t half_phase = 0;     // parity of half_done (one completion per executed tile of more than 64 columns)
+  uint32_t mtile = 0;          // candidate tiles seen (mask double buffer)
+  if (t == 0) tc::mbar_wait(&bars[0], 0);   // weight images (the MMA-issuing thread of every pipeline)
+  const int k1steps = (p.Ng + 16) >> 4;
+
+  for (;;) {
+    tc::named_bar_sync(bar_id, PT);
+    if (t == 0) sts32(aB + x3::OFF_MISC, (uint32_t)atomicAdd(p.counter, 1));
+    tc::named_bar_sync(bar_id, PT);
+    const int conf = (int)lds32(aB + x3::OFF_MISC);
+    if (conf >= p.G) break;
+    const int cs = __ldg(p.seg_ptr + conf);
+    const int n = __ldg(p.seg_ptr + conf + 1) - cs;
+    if (n > NMAX) {
+      if (!p.skip_large && t == 0 && p.status) atomicOr(p.status, CMP_STATUS_EDGE_OVERFLOW);
+      continue;
+    }
+    if (n <= 0) continue;
+    const int goff = cs * F + t;          // element offset of (first atom of the conformer, channel t) in x / out
+    if (t < n) {
+      const float* pp = p.pos + (int64_t)(cs + t) * 3;
+      sts32(aB + x3::OFF_POS + 12u * (uint32_t)t + 0, __float_as_uint(__ldg(pp + 0)));
+      sts32(aB + x3::OFF_POS + 12u * (uint32_t)t + 4, __float_as_uint(__ldg(pp + 1)));
+      sts32(aB + x3::OFF_POS + 12u * (uint32_t)t + 8, __float_as_uint(__ldg(pp + 2)));
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.adj) + cs + t);
+      sts128(aB + x3::OFF_ADJ + 16u * (uint32_t)t, a.x, a.y, a.z, a.w);
+    }
+    for (int a = 16; a < n; ++a) p.out[goff + a * F] = 0.0f;
+    tc::named_bar_sync(bar_id, PT);
+
+    const int nblocks = (n + 15) >> 4;
+    for (int bi = 0; bi < nblocks; ++bi) {
+      const int a0 = bi * 16;
+      const int m = min(16, n - a0);
+      float xr[16], ar[16];
+#pragma unroll
+      for (int il = 0; il < 16; ++il) {
+        xr[il] = (il < m) ? __ldg(p.x + goff + (a0 + il) * F) : 0.0f;
+        ar[il] = (bi > 0 && il < m) ? p.out[goff + (a0 + il) * F] : 0.0f;
+      }
+      const int nrect = (n > a0 + 16) ? ((n - a0 - 16 + 7) >> 3) : 0;
+      for (int tl = (m >= 2) ? -1 : 0; tl < nrect; ++tl, ++mtile) {
+        const bool diag = tl < 0;
+        const int j0 = diag ? a0 : a0 + 16 + 8 * tl;
+        const int nj = diag ? m : min(8, n - j0);
+        const int ncols = diag ? (m * (m - 1)) >> 1 : 16 * nj;
+        const int npad = (ncols + 15) & ~15;
+
+        // ---- which pair does column t hold, and in which directions does the graph have it ----
+        int i_loc, j_loc;
+        bool valid;
+        if (diag) {
+          i_loc = a0 + (int)(dpair & 0xffu);
+          j_loc = a0 + (int)(dpair >> 8);
+          valid = (t < 120) && ((int)(dpair >> 8) < m);
+        } else {
+          i_loc = a0 + (t & 15);
+          j_loc = j0 + (t >> 4);
+          valid = ((t & 15) < m) && ((t >> 4) < nj);
+        }
+        bool ef = false, er = false;
+        if (valid) {
+          ef = (lds32(aB + x3::OFF_ADJ + 4u * (uint32_t)(i_loc * AW + (j_loc >> 5))) >> (j_loc & 31)) & 1u;    // edge j -> i
+          er = (lds32(aB + x3::OFF_ADJ + 4u * (uint32_t)(j_loc * AW + (i_loc >> 5))) >> (i_loc & 31)) & 1u;    // edge i -> j
+        }
+        if (p.transposed) {
+          const bool tmp = ef;
+          ef = er;
+          er = tmp;
+        }
+        const uint32_t amk = aB + x3::OFF_MASK + (mtile & 1u) * 32;
+        {
+          const unsigned bf = __ballot_sync(0xffffffffu, ef), br = __ballot_sync(0xffffffffu, er);
+          if (lane == 0) {
+            sts32(amk + 4u * (uint32_t)wq, bf);
+            sts32(amk + 16 + 4u * (uint32_t)wq, br);
+          }
+        }
+        tc::tc_fence_before();
+        tc::named_bar_sync(bar_id, PT);   // masks visible; previous tile fully consumed (TMEM, images, cutoffs)
+        uint32_t mF[4], mR[4];
+        {
+          const uint4 a = lds128(amk), b = lds128(amk + 16);
+          mF[0] = a.x; mF[1] = a.y; mF[2] = a.z; mF[3] = a.w;
+          mR[0] = b.x; mR[1] = b.y; mR[2] = b.z; mR[3] = b.w;
+        }
+        const uint32_t anyF = mF[0] | mF[1] | mF[2] | mF[3], anyR = mR[0] | mR[1] | mR[2] | mR[3];
+        if ((anyF | anyR) == 0u) continue;   // no pair in this tile
+
+        // ---- column t: distance, cutoff, Gaussian expansion -> rbf images hi / lo (K-major [pair, 64]) ----
+        if (t < npad) {
+          float dist = 0.0f, cval = 0.0f;
+          if (ef || er) {
+            const uint32_t pj = aB + x3::OFF_POS + 12u * (uint32_t)j_loc, pi = aB + x3::OFF_POS + 12u * (uint32_t)i_loc;
+            const float dx = lds_f(pj) - lds_f(pi), dy = lds_f(pj + 4) - lds_f(pi + 4), dz = lds_f(pj + 8) - lds_f(pi + 8);
+            dist = sqrtf(dx * dx + dy * dy + dz * dz);       // the expression of the neighbour search (graph.cu)
+            cval = cos_cutoff_nomask(dist, p.pi_over_cutoff);
+          }
+          sts32(aB + x3::OFF_C + 4u * (uint32_t)t, __float_as_uint(cval));
+          const uint32_t a_row = aB + (uint32_t)(t >> 3) * B1_SBO + (uint32_t)(t & 7) * 16;   // rbf row of column t
+#pragma unroll 1
+          for (int jc = 0; jc < 2 * k1steps; ++jc) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float xx = (dist - p.mu[jc * 8 + j]) * p.s;
+              v[j] = tc::fast_ex2(-xx * xx);
+            }
+            if (jc == (p.Ng >> 3)) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = (j == (p.Ng & 7)) ? 1.0f : v[j];
+            }
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_f16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+            sts128(a_row + jc * 128, hi[0], hi[1], hi[2], hi[3]);
+            sts128(a_row + x3::B1I_BYTES + jc * 128, lo[0], lo[1], lo[2], lo[3]);
+          }
+        }
+        tc::fence_proxy_async();
+        tc::named_bar_sync(bar_id, PT);
+        if (t == 0) {
+          tc::tc_fence_after();
+          const uint32_t idesc1 = tc::umma_idesc_f16(F, npad, 0, 0, 0);
+#pragma unroll 1
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t wa = aW + (pass == 1 ? x3::OFF_W1L : 0u), ba = aB + (pass == 2 ? x3::B1I_BYTES : 0u);
+            for (int ks = 0; ks < k1steps; ++ks)
+              tc::umma_f16(dcol, tc::umma_smem_desc(wa + ks * 256, 128, B1_SBO), tc::umma_smem_desc(ba + ks * 256, 128, B1_SBO),
+                           idesc1, (pass | ks) != 0);
+          }
+          umma_commit_addr(aBar);
+        }
+
+        // operands of epilogue 2 that live in global memory: issued now, needed after the second product
+        float xjr[8], ojr[8];
+        if (!diag) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            xjr[jj] = (jj < nj) ? __ldg(p.x + goff + (j0 + jj) * F) : 0.0f;
+            ojr[jj] = (jj < nj) ? p.out[goff + (j0 + jj) * F] : 0.0f;
+          }
+        }
+
+        // ---- epilogue 1 + second product, 64 columns at a time ----
+        mbar_wait_addr(aBar, mma_phase);
+        tc::tc_fence_after();
+        const int nhalves = npad > x3::HC ? 2 : 1;
+        for (int hf = 0; hf < nhalves; ++hf) {
+          const int cb = hf * x3::HC;
+          const int nh = min(x3::HC, npad - cb);
+          if (hf == 1) {     // the first half's MMAs must be done reading the a' images
+            mbar_wait_addr(aBar + 16, half_phase);
+            half_phase ^= 1u;
+          }
+          const uint32_t aC = aB + x3::OFF_C + 4u * (uint32_t)cb;
+          const uint32_t a_col = aB + (uint32_t)t * 16;                                       // a' column block of channel t
+          for (int c0 = 0; c0 < nh; c0 += 16) {
+            float v[16];
+            tmem_ld16_issue(dtm + cb + c0, v);
+            const uint4 c_a = lds128(aC + 4u * (uint32_t)c0), c_b = lds128(aC + 4u * (uint32_t)c0 + 16),
+                        c_c = lds128(aC + 4u * (uint32_t)c0 + 32), c_d = lds128(aC + 4u * (uint32_t)c0 + 48);
+            const uint32_t cw[16] = {c_a.x, c_a.y, c_a.z, c_a.w, c_b.x, c_b.y, c_b.z, c_b.w,
+                                     c_c.x, c_c.y, c_c.z, c_c.w, c_d.x, c_d.y, c_d.z, c_d.w};
+            tmem_ld16_wait(v);
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a2[2];
+#pragma unroll
+              for (int q = 0; q < 2; ++q) {
+                const float x = v[2 * j + q];
+                const float e = tc::fast_ex2(-fabsf(x));
+                a2[q] = __uint_as_float(cw[2 * j + q]) * (fmaxf(x, 0.0f) + (tc::fast_lg2(1.0f + e) - 1.0f));
+              }
+              split_f16x2(a2[0], a2[1], hi[j], lo[j]);
+            }
+            const uint32_t a_dst = a_col + (uint32_t)(c0 >> 3) * A2_SBO;
+            sts128(a_dst, hi[0], hi[1], hi[2], hi[3]);
+            sts128(a_dst + A2_SBO, hi[4], hi[5], hi[6], hi[7]);
+            sts128(a_dst + x3::AH_BYTES, lo[0], lo[1], lo[2], lo[3]);
+            sts128(a_dst + x3::AH_BYTES + A2_SBO, lo[4], lo[5], lo[6], lo[7]);
+          }
+          // rows 128..143: row 128 = C_p (multiplies the b2 column of W2aug), rows 129..143 = 0
+          for (int item = t; item < (nh >> 3) * 16; item += PT) {
+            const int ec = item >> 4, kr = item & 15;
+            uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+            if (kr == 0) {
+              const uint4 c_a = lds128(aC + 32u * (uint32_t)ec), c_b = lds128(aC + 32u * (uint32_t)ec + 16);
+              split_f16x2(__uint_as_float(c_a.x), __uint_as_float(c_a.y), hi[0], lo[0]);
+              split_f16x2(__uint_as_float(c_a.z), __uint_as_float(c_a.w), hi[1], lo[1]);
+              split_f16x2(__uint_as_float(c_b.x), __uint_as_float(c_b.y), hi[2], lo[2]);
+              split_f16x2(__uint_as_float(c_b.z), __uint_as_float(c_b.w), hi[3], lo[3]);
+            }
+            const uint32_t dst = aB + (uint32_t)ec * A2_SBO + (uint32_t)(128 + kr) * 16;
+            sts128(dst, hi[0], hi[1], hi[2], hi[3]);
+            sts128(dst + x3::AH_BYTES, lo[0], lo[1], lo[2], lo[3]);
+          }
+          tc::tc_fence_before();
+          tc::fence_proxy_async();
+          tc::named_bar_sync(bar_id, PT);
+          if (t == 0) {
+            tc::tc_fence_after();
+            const uint32_t idesc2 = tc::umma_idesc_f16(F, nh, 0, 0, 1);
+#pragma unroll 1
+            for (int pass = 0; pass < 3; ++pass) {
+              const uint32_t wa = aW + (pass == 1 ? x3::OFF_W2L : x3::OFF_W2H), ba = aB + (pass == 2 ? x3::AH_BYTES : 0u);
+#pragma unroll
+              for (int ks = 0; ks < K2 / 16; ++ks)
+                tc::umma_f16(dcol + cb, tc::umma_smem_desc(wa + ks * 256, 128, A2_SBO), tc::umma_smem_desc(ba + ks * 256, 128, A2_SBO),
+                             idesc2, (pass | ks) != 0);
+            }
+            umma_commit_addr((hf + 1 < nhalves) ? aBar + 16 : aBar + 8);
+          }
+        }
+
+        // ---- epilogue 2: both directions of every pair, register operands ----
+        mbar_wait_addr(aBar + 8, mma_phase);
+        tc::tc_fence_after();
+        mma_phase ^= 1u;
+        const bool sym = (mF[0] == mR[0]) && (mF[1] == mR[1]) && (mF[2] == mR[2]) && (mF[3] == mR[3]);
+        if (diag) {
+          if (sym)
+            diag_tile<true>(dtm, m, ar, xr, mF, mR);
+          else
+            diag_tile<false>(dtm, m, ar, xr, mF, mR);
+        } else {
+          if (sym)
+            rect_tile<0>(dtm, nj, ar, xr, xjr, ojr, mF, mR);
+          else if (anyF == 0u)
+            rect_tile<1>(dtm, nj, ar, xr, xjr, ojr, mF, mR);
+          else if (anyR == 0u)
+            rect_tile<2>(dtm, nj, ar, xr, xjr, ojr, mF, mR);
+          else
+            rect_tile<3>(dtm, nj, ar, xr, xjr, ojr, mF, mR);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            if (jj < nj) p.out[goff + (j0 + jj) * F] = ojr[jj];
+        }
+      }
+      // ---- row block finished: its own rows ----
+#pragma unroll
+      for (int il = 0; il < 16; ++il)
+        if (il < m) p.out[goff + (a0 + il) * F] = ar[il];
+    }
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
+
+// =================================================================================================================
 // Warp-specialised variant (the default): ONE stream of tiles per CTA, the phases of a tile on different warps
 // =================================================================================================================
 // The per-pipeline kernel above runs the five phases of a tile one after the other on the same 128 threads.  Its softplus
@@ -1326,10 +1656,39 @@ __device__ __forceinline__ void dense_pack_body(const float* __restrict__ W1, co
   }
 }
 
+// x3 images: W1 hi | W1 lo | W2 hi | W2 lo, each in the layout of dense_pack_body (hi = f16(v), lo = f16(v - hi))
+__device__ __forceinline__ void dense_pack_x3_body(const float* __restrict__ W1, const float* __restrict__ b1,
+                                                   const float* __restrict__ W2, const float* __restrict__ b2, int Ng,
+                                                   uint8_t* __restrict__ out, int idx) {
+  constexpr float kLog2e = 1.4426950408889634f;
+  float v;
+  uint32_t off_hi, off_lo;
+  if (idx < F * K1) {
+    const int m = idx / K1, k = idx % K1;
+    v = ((k < Ng) ? W1[m * Ng + k] : (k == Ng ? b1[m] : 0.0f)) * kLog2e;
+    off_hi = (m & 7) * 16 + (k & 7) * 2 + (m >> 3) * B1_SBO + (k >> 3) * 128;
+    off_lo = off_hi + x3::OFF_W1L;
+  } else if (idx < F * K1 + F * K2) {
+    const int j = idx - F * K1;
+    const int m = j / K2, k = j % K2;
+    v = (k < F) ? W2[m * F + k] * kLn2 : (k == F ? b2[m] : 0.0f);
+    off_hi = x3::OFF_W2H + (m & 7) * 16 + (k & 7) * 2 + (m >> 3) * A2_SBO + (k >> 3) * 128;
+    off_lo = off_hi + W2_BYTES;
+  } else {
+    return;
+  }
+  const __half h = __float2half_rn(v);
+  *reinterpret_cast<__half*>(out + off_hi) = h;
+  *reinterpret_cast<__half*>(out + off_lo) = __float2half_rn(v - __half2float(h));
+}
+
 __global__ void dense_pack_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
                                   const float* __restrict__ W2, const float* __restrict__ b2, int Ng,
-                                  uint8_t* __restrict__ out) {
-  dense_pack_body(W1, b1, W2, b2, Ng, out, blockIdx.x * blockDim.x + threadIdx.x);
+                                  uint8_t* __restrict__ out, int x3_images) {
+  if (x3_images)
+    dense_pack_x3_body(W1, b1, W2, b2, Ng, out, blockIdx.x * blockDim.x + threadIdx.x);
+  else
+    dense_pack_body(W1, b1, W2, b2, Ng, out, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 constexpr int MAX_PACK_JOBS = 32;
@@ -1343,9 +1702,12 @@ struct DensePackJob {
 struct DensePackGroup {
   DensePackJob j[MAX_PACK_JOBS];
 };
-__global__ void dense_pack_grouped_kernel(const __grid_constant__ DensePackGroup g, int Ng) {
+__global__ void dense_pack_grouped_kernel(const __grid_constant__ DensePackGroup g, int Ng, int x3_images) {
   const DensePackJob& j = g.j[blockIdx.y];
-  dense_pack_body(j.W1, j.b1, j.W2, j.b2, Ng, j.packed, blockIdx.x * blockDim.x + threadIdx.x);
+  if (x3_images)
+    dense_pack_x3_body(j.W1, j.b1, j.W2, j.b2, Ng, j.packed, blockIdx.x * blockDim.x + threadIdx.x);
+  else
+    dense_pack_body(j.W1, j.b1, j.W2, j.b2, Ng, j.packed, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // ---- adjacency bit matrix of every conformer of <= NMAX atoms -------------------------------------------------
@@ -1400,38 +1762,61 @@ extern "C" int cmp_build_adjacency(const int32_t* rowptr, const int32_t* col, co
   return CMP_OK;
 }
 
-extern "C" int cmp_cfconv_dense_pack_weights(const float* W1, const float* b1, const float* W2, const float* b2,
-                                             int num_filters, int num_gaussians, void* packed, cmp_stream_t stream) {
+static int dense_pack_impl(const char* who, const float* W1, const float* b1, const float* W2, const float* b2,
+                           int num_filters, int num_gaussians, void* packed, int x3_images, cmp_stream_t stream) {
   CMP_REQUIRE(cmp_cfconv_dense_supported(num_filters, num_gaussians), CMP_EUNSUPPORTED,
-              "cmp_cfconv_dense_pack_weights: needs num_filters == 128 and num_gaussians < 64 (got %d, %d)", num_filters,
-              num_gaussians);
-  CMP_REQUIRE(W1 && b1 && W2 && b2 && packed, CMP_EINVAL, "cmp_cfconv_dense_pack_weights: null pointer");
+              "%s: needs num_filters == 128 and num_gaussians < 64 (got %d, %d)", who, num_filters, num_gaussians);
+  CMP_REQUIRE(W1 && b1 && W2 && b2 && packed, CMP_EINVAL, "%s: null pointer", who);
   const int total = F * K1 + F * K2;
   dense_pack_kernel<<<(total + 255) / 256, 256, 0, as_stream(stream)>>>(W1, b1, W2, b2, num_gaussians,
-                                                                       reinterpret_cast<uint8_t*>(packed));
-  CMP_LAUNCH_CHECK("cmp_cfconv_dense_pack_weights");
+                                                                       reinterpret_cast<uint8_t*>(packed), x3_images);
+  CMP_LAUNCH_CHECK(who);
+  return CMP_OK;
+}
+
+extern "C" int cmp_cfconv_dense_pack_weights(const float* W1, const float* b1, const float* W2, const float* b2,
+                                             int num_filters, int num_gaussians, void* packed, cmp_stream_t stream) {
+  return dense_pack_impl("cmp_cfconv_dense_pack_weights", W1, b1, W2, b2, num_filters, num_gaussians, packed, 0, stream);
+}
+
+extern "C" size_t cmp_cfconv_dense_x3_weights_bytes(void) { return x3::W_BYTES; }
+
+extern "C" int cmp_cfconv_dense_x3_pack_weights(const float* W1, const float* b1, const float* W2, const float* b2,
+                                                int num_filters, int num_gaussians, void* packed, cmp_stream_t stream) {
+  return dense_pack_impl("cmp_cfconv_dense_x3_pack_weights", W1, b1, W2, b2, num_filters, num_gaussians, packed, 1,
+                         stream);
+}
+
+static int dense_pack_grouped_impl(const char* who, const void* jobs, int count, int num_filters, int num_gaussians,
+                                   int x3_images, cmp_stream_t stream) {
+  CMP_REQUIRE(cmp_cfconv_dense_supported(num_filters, num_gaussians), CMP_EUNSUPPORTED,
+              "%s: needs num_filters == 128 and num_gaussians < 64", who);
+  CMP_REQUIRE(count >= 0 && count <= MAX_PACK_JOBS, CMP_EINVAL, "%s: count must be in [0, %d]", who, MAX_PACK_JOBS);
+  if (count == 0) return CMP_OK;
+  CMP_REQUIRE(jobs, CMP_EINVAL, "%s: null pointer", who);
+  const DensePackJob* in = reinterpret_cast<const DensePackJob*>(jobs);
+  DensePackGroup grp;
+  for (int i = 0; i < count; ++i) {
+    CMP_REQUIRE(in[i].W1 && in[i].b1 && in[i].W2 && in[i].b2 && in[i].packed, CMP_EINVAL, "%s: null pointer", who);
+    grp.j[i] = in[i];
+  }
+  const int total = F * K1 + F * K2;
+  dense_pack_grouped_kernel<<<dim3((total + 255) / 256, count), 256, 0, as_stream(stream)>>>(grp, num_gaussians,
+                                                                                              x3_images);
+  CMP_LAUNCH_CHECK(who);
   return CMP_OK;
 }
 
 extern "C" int cmp_cfconv_dense_pack_weights_grouped(const void* jobs, int count, int num_filters, int num_gaussians,
                                                      cmp_stream_t stream) {
-  CMP_REQUIRE(cmp_cfconv_dense_supported(num_filters, num_gaussians), CMP_EUNSUPPORTED,
-              "cmp_cfconv_dense_pack_weights_grouped: needs num_filters == 128 and num_gaussians < 64");
-  CMP_REQUIRE(count >= 0 && count <= MAX_PACK_JOBS, CMP_EINVAL,
-              "cmp_cfconv_dense_pack_weights_grouped: count must be in [0, %d]", MAX_PACK_JOBS);
-  if (count == 0) return CMP_OK;
-  CMP_REQUIRE(jobs, CMP_EINVAL, "cmp_cfconv_dense_pack_weights_grouped: null pointer");
-  const DensePackJob* in = reinterpret_cast<const DensePackJob*>(jobs);
-  DensePackGroup grp;
-  for (int i = 0; i < count; ++i) {
-    CMP_REQUIRE(in[i].W1 && in[i].b1 && in[i].W2 && in[i].b2 && in[i].packed, CMP_EINVAL,
-                "cmp_cfconv_dense_pack_weights_grouped: null pointer");
-    grp.j[i] = in[i];
-  }
-  const int total = F * K1 + F * K2;
-  dense_pack_grouped_kernel<<<dim3((total + 255) / 256, count), 256, 0, as_stream(stream)>>>(grp, num_gaussians);
-  CMP_LAUNCH_CHECK("cmp_cfconv_dense_pack_weights_grouped");
-  return CMP_OK;
+  return dense_pack_grouped_impl("cmp_cfconv_dense_pack_weights_grouped", jobs, count, num_filters, num_gaussians, 0,
+                                 stream);
+}
+
+extern "C" int cmp_cfconv_dense_x3_pack_weights_grouped(const void* jobs, int count, int num_filters, int num_gaussians,
+                                                        cmp_stream_t stream) {
+  return dense_pack_grouped_impl("cmp_cfconv_dense_x3_pack_weights_grouped", jobs, count, num_filters, num_gaussians, 1,
+                                 stream);
 }
 
 extern "C" int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int32_t* seg_ptr, const uint32_t* adj,
@@ -1522,5 +1907,57 @@ extern "C" int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int3
   else
     cfconv_dense_kernel<false><<<grid, CTA_THREADS, SMEM_BYTES, st>>>(p);
   CMP_LAUNCH_CHECK("cmp_cfconv_dense_fwd");
+  return CMP_OK;
+}
+
+extern "C" int cmp_cfconv_dense_x3_fwd(const float* x, const float* pos, const int32_t* seg_ptr, const uint32_t* adj,
+                                       int64_t G, const void* packed_weights, const float* offset_host,
+                                       int num_gaussians, float coeff, float cutoff, int num_filters, int transposed,
+                                       int skip_large, float* out, int32_t* counter, int32_t* status,
+                                       cmp_stream_t stream) {
+  CMP_REQUIRE(cmp_cfconv_dense_supported(num_filters, num_gaussians), CMP_EUNSUPPORTED,
+              "cmp_cfconv_dense_x3_fwd: needs num_filters == 128 and num_gaussians < 64 (got %d, %d)", num_filters,
+              num_gaussians);
+  CMP_REQUIRE(G >= 0 && G < ((int64_t)1 << 31) && cutoff > 0.0f && coeff < 0.0f, CMP_EINVAL,
+              "cmp_cfconv_dense_x3_fwd: bad size, cutoff or coeff");
+  if (G == 0) return CMP_OK;
+  CMP_REQUIRE(x && pos && seg_ptr && adj && packed_weights && offset_host && out && counter, CMP_EINVAL,
+              "cmp_cfconv_dense_x3_fwd: null pointer");
+  CMP_REQUIRE(((uintptr_t)packed_weights % 16 == 0) && ((uintptr_t)adj % 16 == 0), CMP_EINVAL,
+              "cmp_cfconv_dense_x3_fwd: packed_weights / adj must be 16-byte aligned");
+  CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED, "cmp_cfconv_dense_x3_fwd: needs an sm_100 device (tcgen05)");
+  cudaStream_t st = as_stream(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(cfconv_dense_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)x3::SMEM) !=
+        cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("cmp_cfconv_dense_x3_fwd: cannot opt in to %u bytes of shared memory", x3::SMEM);
+      return CMP_ECUDA;
+    }
+    attr_set = true;
+  }
+  CMP_REQUIRE(cudaMemsetAsync(counter, 0, sizeof(int32_t), st) == cudaSuccess, CMP_ECUDA,
+              "cmp_cfconv_dense_x3_fwd: memset failed");
+  DenseParams p = {};
+  p.x = x;
+  p.pos = pos;
+  p.seg_ptr = seg_ptr;
+  p.adj = adj;
+  p.weights = reinterpret_cast<const uint8_t*>(packed_weights);
+  p.out = out;
+  p.counter = counter;
+  p.status = status;
+  p.s = sqrtf(-coeff * 1.4426950408889634f);
+  for (int k = 0; k < K1; ++k) p.mu[k] = (k < num_gaussians) ? offset_host[k] : 0.0f;   // UNSCALED centres
+  p.active_pipes = NP;
+  p.pi_over_cutoff = kPi / cutoff;
+  p.Ng = num_gaussians;
+  p.G = (int)G;
+  p.transposed = transposed;
+  p.skip_large = skip_large;
+  const int grid = (int)std::min<int64_t>((G + NP - 1) / NP, sm_count());
+  cfconv_dense_x3_kernel<<<grid, CTA_THREADS, x3::SMEM, st>>>(p);
+  CMP_LAUNCH_CHECK("cmp_cfconv_dense_x3_fwd");
   return CMP_OK;
 }

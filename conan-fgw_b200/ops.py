@@ -778,13 +778,28 @@ def _per_edge_aggregate(xin, graph, packed, offset, coeff, cutoff, transposed, m
     return _fused_fwd_launch(xin, dist, rowptr, col, tiles, num, packed, offset, coeff, cutoff, e_hint)
 
 
-def _fused_aggregate(xin, graph, W, offset, coeff, cutoff, transposed):
+def x3_graph_ok(graph) -> bool:
+    """The fp32-grade fused kernels serve radius-built graphs whose conformers all fit the dense kernels."""
+    return (graph is not None and graph.G > 0 and graph.pos is not None and not graph.loop
+            and graph.max_atoms is not None and graph.max_atoms <= _lib.size_query("cmp_cfconv_dense_max_atoms"))
+
+
+def _fused_aggregate(xin, graph, W, offset, coeff, cutoff, transposed, x3=False):
     """agg = sum_j x_j * W(d_ij) C(d_ij) over the neighbour list (or its transpose) on the fused tcgen05 kernels.
-    ``W`` = (W1, b1, W2, b2) of the filter MLP (weight images come from the prepack cache or are packed here)."""
+    ``W`` = (W1, b1, W2, b2) of the filter MLP (weight images come from the prepack cache or are packed here).
+    ``x3``: the fp32-grade kernel (f16 hi + lo operand images, three MMA passes, fp32 epilogues)."""
     e_hint = graph._E if graph._E is not None else graph.cap_E
     N, F = xin.shape
     Ng = offset.numel()
     flops = 2.0 * (Ng * F + F * F) * float(e_hint)
+    if x3:
+        if not x3_graph_ok(graph):
+            raise _lib.ConanMPError("fp32-grade fused CFConv: needs a radius-built graph with max_atoms <= 128")
+        out = torch.empty(N, F, dtype=torch.float32, device=xin.device)
+        call("cmp_cfconv_dense_x3_fwd", ptr(xin), ptr(graph.pos), ptr(graph.seg_ptr), ptr(graph.adjacency()), graph.G,
+             ptr(pack_dense_x3_weights(*W)), ctypes.addressof(_offset_host(offset)), Ng, float(coeff), float(cutoff), F,
+             int(bool(transposed)), 0, ptr(out), ptr(graph._counter), ptr(graph.status), work=flops)
+        return out
     if FUSED_DENSE and graph.G > 0 and graph.pos is not None and not graph.loop:
         cap = _lib.size_query("cmp_cfconv_dense_max_atoms")
         dense_only = graph.max_atoms is not None and graph.max_atoms <= cap
@@ -835,6 +850,17 @@ def pack_dense_weights(W1, b1, W2, b2):
     return packed
 
 
+def pack_dense_x3_weights(W1, b1, W2, b2):
+    cached = _cached_images(W1)
+    if cached is not None and len(cached) > 3 and cached[3] is not None:
+        return cached[3]
+    F, Ng = W1.shape
+    packed = torch.empty(_lib.size_query("cmp_cfconv_dense_x3_weights_bytes"), dtype=torch.uint8, device=W1.device)
+    call("cmp_cfconv_dense_x3_pack_weights", ptr(_f32c(W1.detach())), ptr(_f32c(b1.detach())), ptr(_f32c(W2.detach())),
+         ptr(_f32c(b2.detach())), F, Ng, ptr(packed))
+    return packed
+
+
 class _CFConvFusedFn(Function):
     """Geometric CFConv in one tcgen05 kernel (bf16 filter MLP):  agg = sum_j x'_j * W(d_ij) * C(d_ij).
 
@@ -843,10 +869,10 @@ class _CFConvFusedFn(Function):
     are recomputed on the exact-fp32 kernels (rbf -> Linear+ssp -> Linear, then GEMMs with K = E)."""
 
     @staticmethod
-    def forward(ctx, xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff):
+    def forward(ctx, xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff, x3=False):
         xprime = _f32c(xprime)
-        agg = _fused_aggregate(xprime, graph, (W1, b1, W2, b2), offset, coeff, cutoff, transposed=False)
-        ctx.graph, ctx.coeff, ctx.cutoff = graph, float(coeff), float(cutoff)
+        agg = _fused_aggregate(xprime, graph, (W1, b1, W2, b2), offset, coeff, cutoff, transposed=False, x3=x3)
+        ctx.graph, ctx.coeff, ctx.cutoff, ctx.x3 = graph, float(coeff), float(cutoff), bool(x3)
         ctx.save_for_backward(xprime, W1, b1, W2, b2, offset)
         return agg
 
@@ -860,11 +886,13 @@ class _CFConvFusedFn(Function):
         if ctx.needs_input_grad[0]:
             if graph.rowptr_t is None:
                 raise _lib.ConanMPError("cfconv backward needs the transposed neighbour list")
-            dx = _fused_aggregate(g, graph, (W1, b1, W2, b2), offset, ctx.coeff, ctx.cutoff, transposed=True)
+            dx = _fused_aggregate(g, graph, (W1, b1, W2, b2), offset, ctx.coeff, ctx.cutoff, transposed=True,
+                                  x3=ctx.x3)
         grads = [None, None, None, None]
         if any(ctx.needs_input_grad[1:5]):
-            if FUSED_WEIGHT_GRADS:
-                grads = list(_fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, ctx.coeff, ctx.cutoff))
+            if FUSED_WEIGHT_GRADS and (not ctx.x3 or X3_WEIGHT_GRADS):
+                grads = list(_fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, ctx.coeff, ctx.cutoff,
+                                                 x3=ctx.x3))
             else:   # exact-fp32 recompute of the filter MLP (kept for cross-checking the fused kernel)
                 E = graph.E
                 dfilt = torch.empty(E, F, dtype=torch.float32, device=g.device)
@@ -875,10 +903,12 @@ class _CFConvFusedFn(Function):
                     rbf = gaussian_rbf(graph.dist[:E], offset, ctx.coeff)
                     filt = linear(linear(rbf, ps[0], ps[1], ACT_SSP), ps[2], ps[3])
                     grads = list(torch.autograd.grad(filt, ps, dfilt))
-        return (dx, *grads, None, None, None, None)
+        return (dx, *grads, None, None, None, None, None)
 
 
 FUSED_WEIGHT_GRADS = True
+# fp32-grade mode: weight gradients on the three-pass tcgen05 kernel; False = exact-fp32 recompute on [E, *] tensors
+X3_WEIGHT_GRADS = False
 # one column per undirected pair in the weight-gradient pass (both directions share the filter); False = one column
 # per directed edge with fp32 g (kept for cross-checking)
 FUSED_PAIR_GRADS = True
@@ -889,7 +919,7 @@ FUSED_PAIR_GRADS = True
 FUSED_DENSE_GRADS = True
 
 
-def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff):
+def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff, x3=False):
     """dW1, db1, dW2, db2 of the filter MLP through the tcgen05 weight-gradient kernels (K = edges / pairs)."""
     N, F = xprime.shape
     Ng = offset.numel()
@@ -932,8 +962,8 @@ def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff):
     return dW1, db1, dW2, db2
 
 
-def cfconv_fused(xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff):
-    return _CFConvFusedFn.apply(xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff)
+def cfconv_fused(xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff, x3=False):
+    return _CFConvFusedFn.apply(xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff, x3)
 
 
 def fused_supported(num_filters, num_gaussians) -> bool:

@@ -285,6 +285,23 @@ int cmp_cfconv_dense_fwd(const float* x, const float* pos, const int32_t* seg_pt
                          int skip_large, int max_atoms_hint, float* agg, int32_t* counter, int32_t* status,
                          cmp_stream_t stream);
 
+/* fp32-grade variant of cmp_cfconv_dense_fwd ("x3", cfconv_dense_x3_kernel): same tiles, pair <-> column maps and
+ * register-resident two-direction epilogue, but every MMA operand (Gaussians, a', W1, W2) is split into f16 hi + lo
+ * images and every product runs as three tcgen05 passes (hi hi + lo hi + hi lo, 22 significant bits), the softplus
+ * epilogue is evaluated in fp32, distances / cutoffs exactly as the exact kernels compute them.  Meets the 1e-5 parity
+ * bar of the exact path (sns.py:161-164 semantics) without materialising any [E, *] tensor.
+ *   packed_weights: cmp_cfconv_dense_x3_pack_weights (cmp_cfconv_dense_x3_weights_bytes() bytes: W1 hi | W1 lo | W2 hi |
+ *   W2 lo).  Other arguments as cmp_cfconv_dense_fwd (one kernel for every conformer size up to the atom limit). */
+size_t cmp_cfconv_dense_x3_weights_bytes(void);
+int cmp_cfconv_dense_x3_pack_weights(const float* W1, const float* b1, const float* W2, const float* b2,
+                                     int num_filters, int num_gaussians, void* packed, cmp_stream_t stream);
+int cmp_cfconv_dense_x3_pack_weights_grouped(const void* jobs, int count, int num_filters, int num_gaussians,
+                                             cmp_stream_t stream);
+int cmp_cfconv_dense_x3_fwd(const float* x, const float* pos, const int32_t* seg_ptr, const uint32_t* adj,
+                            int64_t G, const void* packed_weights, const float* offset_host,
+                            int num_gaussians, float coeff, float cutoff, int num_filters, int transposed,
+                            int skip_large, float* agg, int32_t* counter, int32_t* status, cmp_stream_t stream);
+
 /* Filter-MLP weight gradients over the DENSE blocks of cmp_cfconv_dense_fwd (conformers of at most 128 atoms; larger
  * ones contribute nothing (cmp_build_dense_bwd_tiles sets CMP_STATUS_EDGE_OVERFLOW) - serve such batches with
  * cmp_cfconv_fused_bwd_weights_pairs): one column per undirected pair in tiles of 64, the pair of a column is a
