@@ -43,7 +43,8 @@ REFERENCE_BUDGET_S = 240.0           # --impl reference: the whole run (warm-up 
 # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r02_dense_ws_kernel.metrics.csv, r01_pair_bwd_kernel.metrics.csv)
 NCU_DRAM_BYTES_PER_LAUNCH = {"cmp_cfconv_dense_fwd": 9481984, "cmp_cfconv_dense_bwd_weights": None, "cmp_cfconv_pair_fwd": 12547584,
                              "cmp_cfconv_fused_bwd_weights_pairs": 13398784 + 764672, "cmp_cfconv_fused_fwd": 15000000}
-FWD_KERNELS = ("cmp_cfconv_dense_fwd", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd")
+FWD_KERNELS = ("cmp_cfconv_dense_fwd", "cmp_cfconv_dense_x3_fwd", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd")
+DTYPE_X3 = "f32-grade: f16 / bf16 hi + lo filter-MLP operands, three tcgen05 passes, f32 accumulation and epilogues; split-bf16 node linears; f32 elsewhere"
 DTYPE_FUSED = "f16 / bf16 filter-MLP operands with f32 accumulation (tcgen05), split-bf16 node linears (f32 grade), f32 elsewhere"
 
 
@@ -411,7 +412,7 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    use_graph = args.precision == "bf16" and not args.no_graph   # the exact mode syncs once per step (edge count)
+    use_graph = args.precision in ("bf16", "fp32") and not args.no_graph   # the exact mode syncs once per step (edge count)
 
     def resident_step():
         return trainer.step(d.z, d.pos, d.batch, targets, G)
@@ -481,7 +482,7 @@ def run_ours(args):
     for _ in range(60):      # keep the GPU under the same load until the clock sampler is running; a FIXED count,
         resident_step()      # identical on every rank (each step holds a collective)
     torch.cuda.synchronize()
-    dominant = ["cmp_gemm_f32", "cmp_cfconv_dense_fwd", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd", "cmp_cfconv_fused_bwd_weights",
+    dominant = ["cmp_gemm_f32", "cmp_cfconv_dense_fwd", "cmp_cfconv_dense_x3_fwd", "cmp_cfconv_dense_bwd_x3_weights", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd", "cmp_cfconv_fused_bwd_weights",
                 "cmp_cfconv_fused_bwd_weights_pairs", "cmp_cfconv_dense_bwd_weights", "cmp_node_gemm_dw_grouped", "cmp_node_gemm_fwd",
                 "cmp_node_gemm_dw", "cmp_node_chain_fwd"]
     total_ms, launches, kt = timed(resident_step, args.steps)
@@ -520,20 +521,33 @@ def run_ours(args):
             resident_step()
             sync_all()
 
-    # the other numerics mode of the same step, for the record (exact-fp32 kernels <-> fused bf16 filter MLP)
-    other_mode = None
-    if not args.lean:
-        other = "fp32" if args.precision == "bf16" else "bf16"
+    # the other numerics modes of the same step, for the record: "fp32" = the 1e-5 parity mode (fp32-grade fused tcgen05
+    # kernels: hi + lo operand images, three MMA passes, fp32 epilogues; CUDA graph), "exact" = exact-fp32 SIMT kernels on
+    # materialised [E, *] tensors (the reference's own op sequence; one host sync per step), "bf16" = f16 filter MLP
+    def time_mode(prec):
         torch.manual_seed(0)
-        model_o = cmp.SchNetNoSum(None, **MODEL_CFG).to(dev).set_precision(other)
+        model_o = cmp.SchNetNoSum(None, **MODEL_CFG).to(dev).set_precision(prec)
+        model_o.max_atoms_hint = n
         trainer_o = RegressionStep(model_o, MODEL_CFG["hidden_channels"] // 2, K, lr=1e-3)
         for _ in range(3):
             trainer_o.step(d.z, d.pos, d.batch, targets, G)
-        other_steps = max(3, min(args.steps, 10))
-        other_ms, _, _ = timed(lambda: trainer_o.step(d.z, d.pos, d.batch, targets, G), other_steps)
-        other_mode = {"precision": other, "value": world * G * other_steps / (other_ms * 1e-3), "unit": UNIT,
-                      "ms_per_step": other_ms / other_steps, "steps": other_steps}
-        del model_o, trainer_o
+        graphed = prec in ("bf16", "fp32") and not args.no_graph
+        if graphed:
+            trainer_o.capture(d.z, d.pos, d.batch, targets, G)
+            trainer_o.step(d.z, d.pos, d.batch, targets, G)
+        steps_o = max(3, min(args.steps, 10))
+        ms_o, _, _ = timed(lambda: trainer_o.step(d.z, d.pos, d.batch, targets, G), steps_o)
+        trainer_o.check()
+        return {"precision": prec, "value": world * G * steps_o / (ms_o * 1e-3), "unit": UNIT,
+                "ms_per_step": ms_o / steps_o, "steps": steps_o, "cuda_graph": graphed}
+
+    other_mode, exact_mode = None, None
+    if not args.lean:
+        other_mode = time_mode("fp32" if args.precision != "fp32" else "bf16")
+        other_mode["tolerance"] = "1e-5 vs the oracle (fp32-grade fused kernels)" if other_mode["precision"] == "fp32" \
+            else "5e-3 embeddings / 7.5e-3 gradients"
+        if args.precision != "exact":
+            exact_mode = time_mode("exact")
 
     value = world * G * args.steps / (total_ms * 1e-3)
     e2e_value = world * G * args.steps / (e2e_ms * 1e-3)
@@ -583,8 +597,9 @@ def run_ours(args):
     # algorithmic work of the fused kernels is known exactly from E (2*(Ng*F + F*F) FLOP per edge per
     # launch, for the forward / d x' pass and for the weight-gradient pass alike)
     per_edge = 2.0 * (MODEL_CFG["num_gaussians"] * MODEL_CFG["num_filters"] + MODEL_CFG["num_filters"] ** 2)
-    for k in ("cmp_cfconv_dense_fwd", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd", "cmp_cfconv_fused_bwd_weights",
-              "cmp_cfconv_fused_bwd_weights_pairs", "cmp_cfconv_dense_bwd_weights"):
+    for k in ("cmp_cfconv_dense_fwd", "cmp_cfconv_dense_x3_fwd", "cmp_cfconv_dense_bwd_x3_weights", "cmp_cfconv_fused_fwd",
+              "cmp_cfconv_pair_fwd", "cmp_cfconv_fused_bwd_weights", "cmp_cfconv_fused_bwd_weights_pairs",
+              "cmp_cfconv_dense_bwd_weights"):
         if k in summ:
             # with the pair kernel active the per-edge forward kernel only zero-fills and serves conformers of more
             # than 30 atoms (none in this workload): no algorithmic work is booked on it
@@ -604,6 +619,12 @@ def run_ours(args):
         "cmp_cfconv_dense_fwd": "cfconv_dense_kernel (tcgen05: distances + rbf + filter MLP once per undirected pair of the dense "
                                 "16 x 16 atom blocks + cutoff, both directions applied from registers; algorithmic FLOPs "
                                 "counted per directed edge)",
+        "cmp_cfconv_dense_x3_fwd": "cfconv_dense_x3_kernel (tcgen05, fp32-grade: the dense-block forward with f16 hi + lo operand "
+                                   "images and three MMA passes per product, fp32 epilogues; algorithmic FLOPs counted once "
+                                   "per directed edge - the tensor pipe executes 3 x that per undirected pair)",
+        "cmp_cfconv_dense_bwd_x3_weights": "cfconv_dense_bwd_x3_kernel (tcgen05, fp32-grade filter-MLP weight gradients: bf16 hi + "
+                                           "lo operand images, three MMA passes per product; algorithmic FLOPs counted once per "
+                                           "directed edge)",
         "cmp_gemm_f32": "gemm_f32_kernel (exact-fp32 SIMT GEMM: filter MLP on E rows + node linears + their gradients)",
         "cmp_cfconv_fused_fwd": "cfconv_fused_fwd_kernel (tcgen05: rbf + filter MLP + cutoff + gather + segmented reduce)",
         "cmp_cfconv_pair_fwd": "cfconv_pair_kernel (tcgen05: rbf + filter MLP once per undirected pair + cutoff + both "
@@ -675,7 +696,7 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.precision == "fp32" else DTYPE_FUSED, "data": "synthetic",
+        "dtype": {"exact": "f32", "fp32": DTYPE_X3}.get(args.precision, DTYPE_FUSED), "data": "synthetic",
         "config": {"workload": WORKLOAD, "precision": args.precision, "molecules_per_gpu": B, "conformers_per_molecule": K, "atoms_per_conformer": n,
                    "conformers_per_gpu": G, "atoms": N, "edges": E, **MODEL_CFG, "max_num_neighbors": 32,
                    "step": "radius graph + fwd + MSE + bwd + grad all-reduce (N>1) + Adam",
@@ -685,7 +706,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
-        "other_mode": other_mode, "visnet": visnet, "configs": extra_configs,
+        "other_mode": other_mode, "exact_mode": exact_mode, "visnet": visnet, "configs": extra_configs,
         "tolerance": {"fp32": "1e-5 relative vs oracle (tests/test_gpu_schnet.py)",
                       "bf16": "fused mode: 5e-3 relative on embeddings, 2e-2 on gradients vs the oracle on small batches "
                               "(tests/test_gpu_fused.py); at this workload's full size 7.5e-3 per parameter against the exact "
@@ -703,7 +724,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
+    ap.add_argument("--precision", default="bf16", choices=["exact", "fp32", "bf16"],
                     help="fp32: exact kernels (1e-5 parity mode); bf16: fused tcgen05 CFConv, bf16 filter MLP")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile", action="store_true", help="warm-up + timed steps only (for ncu launch lists)")

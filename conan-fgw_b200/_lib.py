@@ -120,6 +120,9 @@ SIGNATURES = {
     "cmp_cfconv_dense_x3_pack_weights": (I, [P, P, P, P, I, I, P, P]),
     "cmp_cfconv_dense_x3_pack_weights_grouped": (I, [P, I, I, I, P]),
     "cmp_cfconv_dense_x3_fwd": (I, [P, P, P, P, L, P, P, I, F, F, I, I, I, P, P, P, P]),
+    "cmp_cfconv_dense_bwd_x3_weights_bytes": (S, []),
+    "cmp_cfconv_dense_bwd_x3_pack_weights_grouped": (I, [P, I, I, I, P]),
+    "cmp_cfconv_dense_bwd_x3_weights": (I, [P, P, P, P, P, P, L, P, P, I, F, F, I, P, P, P, P, P, S, P]),
     "cmp_cfconv_dense_bwd_workspace": (S, []),
     "cmp_build_dense_bwd_tiles": (I, [P, L, P, P, P]),
     "cmp_cfconv_dense_bwd_weights": (I, [P, P, P, P, P, P, L, P, P, I, F, F, I, P, P, P, P, P, S, P]),
@@ -152,6 +155,11 @@ class DensePackJob(ctypes.Structure):
     """``cmp_dense_pack_job_t``."""
     _fields_ = [("W1", ctypes.c_void_p), ("b1", ctypes.c_void_p), ("W2", ctypes.c_void_p), ("b2", ctypes.c_void_p),
                 ("packed", ctypes.c_void_p)]
+
+
+class BwdX3PackJob(ctypes.Structure):
+    """``cmp_bwd_x3_pack_job_t``."""
+    _fields_ = [("W1", ctypes.c_void_p), ("b1", ctypes.c_void_p), ("W2", ctypes.c_void_p), ("packed", ctypes.c_void_p)]
 
 
 class ChainStage(ctypes.Structure):

@@ -650,6 +650,10 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_kernel(const __gr
 // overwrites only the D1 columns epilogue 1 has already consumed.
 namespace x3 {
 constexpr int HC = 64;                                     // columns per a' half
+// Both weight images are scaled by 2^6 before the split: |W| ~ 0.1 would put the lo halves (|lo| <= 2^-12 |W|) into the
+// f16 subnormals (spacing 6e-8, i.e. 3e-7 of such a weight instead of 2^-23).  Powers of two: epilogue 1 multiplies the
+// pre-activation by 2^-6 and epilogue 2 reads x' rows scaled by 2^-6, both exact.
+constexpr float WSCALE = 64.0f, WSCALE_INV = 1.0f / 64.0f;
 constexpr uint32_t OFF_W1L = W1_BYTES, OFF_W2H = 2 * W1_BYTES, OFF_W2L = 2 * W1_BYTES + W2_BYTES;
 constexpr uint32_t W_BYTES = 2 * (W1_BYTES + W2_BYTES);    // W1 hi | W1 lo | W2 hi | W2 lo
 constexpr uint32_t AH_BYTES = (HC / 8) * A2_SBO;           // 18432: a' image of 64 columns (MN-major [144, 64])
@@ -747,7 +751,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_x3_kernel(const _
       float xr[16], ar[16];
 #pragma unroll
       for (int il = 0; il < 16; ++il) {
-        xr[il] = (il < m) ? __ldg(p.x + goff + (a0 + il) * F) : 0.0f;
+        xr[il] = (il < m) ? __ldg(p.x + goff + (a0 + il) * F) * x3::WSCALE_INV : 0.0f;   // D2 carries 2^6 (x3::WSCALE)
         ar[il] = (bi > 0 && il < m) ? p.out[goff + (a0 + il) * F] : 0.0f;
       }
       const int nrect = (n > a0 + 16) ? ((n - a0 - 16 + 7) >> 3) : 0;
@@ -816,7 +820,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_x3_kernel(const _
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float xx = (dist - p.mu[jc * 8 + j]) * p.s;
+#ifdef CMP_X3_ACCURATE
+              v[j] = exp2f(-xx * xx);
+#else
               v[j] = tc::fast_ex2(-xx * xx);
+#endif
             }
             if (jc == (p.Ng >> 3)) {
 #pragma unroll
@@ -849,7 +857,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_x3_kernel(const _
         if (!diag) {
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
-            xjr[jj] = (jj < nj) ? __ldg(p.x + goff + (j0 + jj) * F) : 0.0f;
+            xjr[jj] = (jj < nj) ? __ldg(p.x + goff + (j0 + jj) * F) * x3::WSCALE_INV : 0.0f;
             ojr[jj] = (jj < nj) ? p.out[goff + (j0 + jj) * F] : 0.0f;
           }
         }
@@ -881,9 +889,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_x3_kernel(const _
               float a2[2];
 #pragma unroll
               for (int q = 0; q < 2; ++q) {
-                const float x = v[2 * j + q];
+                const float x = v[2 * j + q] * x3::WSCALE_INV;
+#ifdef CMP_X3_ACCURATE
+                const float e = exp2f(-fabsf(x));
+                a2[q] = __uint_as_float(cw[2 * j + q]) * (fmaxf(x, 0.0f) + (log2f(1.0f + e) - 1.0f));
+#else
                 const float e = tc::fast_ex2(-fabsf(x));
                 a2[q] = __uint_as_float(cw[2 * j + q]) * (fmaxf(x, 0.0f) + (tc::fast_lg2(1.0f + e) - 1.0f));
+#endif
               }
               split_f16x2(a2[0], a2[1], hi[j], lo[j]);
             }
@@ -1665,13 +1678,13 @@ __device__ __forceinline__ void dense_pack_x3_body(const float* __restrict__ W1,
   uint32_t off_hi, off_lo;
   if (idx < F * K1) {
     const int m = idx / K1, k = idx % K1;
-    v = ((k < Ng) ? W1[m * Ng + k] : (k == Ng ? b1[m] : 0.0f)) * kLog2e;
+    v = ((k < Ng) ? W1[m * Ng + k] : (k == Ng ? b1[m] : 0.0f)) * kLog2e * x3::WSCALE;
     off_hi = (m & 7) * 16 + (k & 7) * 2 + (m >> 3) * B1_SBO + (k >> 3) * 128;
     off_lo = off_hi + x3::OFF_W1L;
   } else if (idx < F * K1 + F * K2) {
     const int j = idx - F * K1;
     const int m = j / K2, k = j % K2;
-    v = (k < F) ? W2[m * F + k] * kLn2 : (k == F ? b2[m] : 0.0f);
+    v = ((k < F) ? W2[m * F + k] * kLn2 : (k == F ? b2[m] : 0.0f)) * x3::WSCALE;
     off_hi = x3::OFF_W2H + (m & 7) * 16 + (k & 7) * 2 + (m >> 3) * A2_SBO + (k >> 3) * 128;
     off_lo = off_hi + W2_BYTES;
   } else {

@@ -579,9 +579,48 @@ __device__ __forceinline__ void pack_bwd_weights_body(const float* __restrict__ 
   }
 }
 
+// fp32-grade images: W1 hi | W1 lo | W2^T hi | W2^T lo (lo = bf16(v - hi)), layouts of pack_bwd_weights_body
+__device__ __forceinline__ void pack_bwd_weights_x3_body(const float* __restrict__ W1, const float* __restrict__ b1,
+                                                         const float* __restrict__ W2, int Ng,
+                                                         uint8_t* __restrict__ out, int idx) {
+  float v;
+  uint32_t off_hi, off_lo;
+  if (idx < F * K1) {
+    const int m = idx / K1, k = idx % K1;
+    v = (k < Ng) ? W1[m * Ng + k] : (k == Ng ? b1[m] : 0.0f);
+    off_hi = (m & 7) * 16 + (k & 7) * 2 + (m >> 3) * 1024 + (k >> 3) * 128;
+    off_lo = off_hi + W1_BYTES;
+  } else if (idx < F * K1 + F * F) {
+    const int j = idx - F * K1;
+    const int k = j / F, f = j % F;
+    v = W2[f * F + k];
+    off_hi = 2 * W1_BYTES + (k & 7) * 16 + (f & 7) * 2 + (k >> 3) * 2048 + (f >> 3) * 128;
+    off_lo = off_hi + W2T_BYTES;
+  } else {
+    return;
+  }
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(out + off_hi) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(out + off_lo) = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
 __global__ void pack_bwd_weights_kernel(const float* __restrict__ W1, const float* __restrict__ b1,
                                         const float* __restrict__ W2, int Ng, uint8_t* __restrict__ out) {
   pack_bwd_weights_body(W1, b1, W2, Ng, out, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+struct PackBwdX3Job {
+  const float* W1;
+  const float* b1;
+  const float* W2;
+  uint8_t* packed;
+};
+struct PackBwdX3Group {
+  PackBwdX3Job j[32];
+};
+__global__ void pack_bwd_weights_x3_kernel(const __grid_constant__ PackBwdX3Group g, int Ng) {
+  const PackBwdX3Job& j = g.j[blockIdx.y];
+  pack_bwd_weights_x3_body(j.W1, j.b1, j.W2, Ng, j.packed, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // grouped: same job layout as cfconv_tc.cu's PackFilterJob (cmp_pack_filter_job_t of the header)
@@ -859,7 +898,29 @@ struct DenseWalk {
 };
 
 // dF of 32 columns of a DIAG tile: columns C0 .. C0 + 31 of the block's pair list (compile-time pairs)
-template <int C0>
+// bf16 hi + lo images of 8 values (lo = bf16(v - hi): 16 significant bits together)
+__device__ __forceinline__ void split_bf16x8(const float* v, uint4& hi, uint4& lo) {
+  hi = pack_bf16x8(v);
+  float hf[8], r[8];
+  unpack_bf16x8(hi, hf);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = v[j] - hf[j];
+  lo = pack_bf16x8(r);
+}
+// LO_OFF != 0: also write the lo image, LO_OFF bytes behind the hi image (fp32-grade kernel)
+template <uint32_t LO_OFF>
+__device__ __forceinline__ void store_df8(uint8_t* dst, const float* v) {
+  if (LO_OFF == 0) {
+    *reinterpret_cast<uint4*>(dst) = pack_bf16x8(v);
+  } else {
+    uint4 hi, lo;
+    split_bf16x8(v, hi, lo);
+    *reinterpret_cast<uint4*>(dst) = hi;
+    *reinterpret_cast<uint4*>(dst + LO_OFF) = lo;
+  }
+}
+
+template <int C0, uint32_t LO_OFF = 0>
 __device__ __forceinline__ void dense_df_diag(const float (&gr)[16], const float (&xr)[16], uint32_t mf, uint32_t mr,
                                               const float* __restrict__ sC32, uint8_t* __restrict__ dstF, float& db2) {
 #pragma unroll
@@ -877,11 +938,12 @@ __device__ __forceinline__ void dense_df_diag(const float (&gr)[16], const float
       v[j] = ((mr >> (c8 + j)) & 1u) ? fmaf(gr[jl], xr[il], a) : a;           // edge i -> j: g[j] x'[i]
       db2 = fmaf(v[j], cc[j], db2);
     }
-    *reinterpret_cast<uint4*>(dstF + (c8 >> 3) * 2048) = pack_bf16x8(v);
+    store_df8<LO_OFF>(dstF + (c8 >> 3) * 2048, v);
   }
 }
 
 // dF of 32 columns of a RECT tile: rows il of the block x the two column atoms of this half (gj / xj)
+template <uint32_t LO_OFF = 0>
 __device__ __forceinline__ void dense_df_rect(const float (&gr)[16], const float (&xr)[16], const float (&gj)[2],
                                               const float (&xj)[2], uint32_t mf, uint32_t mr,
                                               const float* __restrict__ sC32, uint8_t* __restrict__ dstF, float& db2) {
@@ -897,7 +959,7 @@ __device__ __forceinline__ void dense_df_rect(const float (&gr)[16], const float
       v[j] = ((mr >> c) & 1u) ? fmaf(gj[jj], xr[il], a) : a;                  // edge i -> j
       db2 = fmaf(v[j], cc[j], db2);
     }
-    *reinterpret_cast<uint4*>(dstF + (c8 >> 3) * 2048) = pack_bf16x8(v);
+    store_df8<LO_OFF>(dstF + (c8 >> 3) * 2048, v);
   }
 }
 
@@ -1236,6 +1298,421 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_bwd_kernel(const 
     }
 
     // ---- drain: accumulators -> this pipeline's partial block ----
+    float* part = p.partial + u * (int64_t)PART_FLOATS;
+    const bool any = t0 < t1;
+    if (any) {
+      tc::mbar_wait(b + 5, (it - 1) & 1);
+      tc::tc_fence_after();
+    }
+    for (int c0 = h * 64; c0 < h * 64 + 64; c0 += 16) {       // dW2[f = chan][k]: columns [h*64, h*64+64)
+      float v[16];
+      if (any) {
+        tc::tmem_ld16(tW2 + c0, v);
+        tc::tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(part + chan * F + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    for (int c0 = h * 32; c0 < h * 32 + 32; c0 += 16) {       // dW1[k = chan][j]: columns [h*32, h*32+32)
+      float v[16];
+      if (any) {
+        tc::tmem_ld16(tW1 + c0, v);
+        tc::tmem_wait_ld();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(part + F * F + chan * K1 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    part[F * F + F * K1 + h * F + chan] = db2;
+    part[F * F + F * K1 + 2 * F + h * F + chan] = db1;
+  }
+
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 512);
+}
+
+
+// =================================================================================================================
+// fp32-grade dense weight gradients ("x3"): bf16 hi + lo operand images, three MMA passes per product
+// =================================================================================================================
+// Same tiles, column <-> pair maps, register-resident dF and TMEM accumulators as cfconv_dense_bwd_kernel, but every
+// operand (Gaussians, W1, W2^T, a', dF, dh) exists as a bf16 hi and a bf16 lo image (lo = bf16(v - hi): 16 significant
+// bits together; bf16 rather than f16 because dF / dh carry the dynamic range of the loss gradient) and every product
+// runs as hi hi + lo hi + hi lo into the same accumulator.  The per-column rounding errors (2^-17 relative, unbiased)
+// average out over the hundreds of thousands of columns a weight gradient sums, so dW1 / dW2 meet the 1e-5 bar of the
+// exact path.  Epilogues in fp32; distances and cutoffs as the exact kernels compute them; the pre-activations h stay
+// in TMEM next to da', so epilogue 3 recomputes sigmoid(h) instead of reading a rounded image.
+// The doubled images leave room for ONE group of 256 threads per CTA, single buffered: the phases of a tile run in
+// sequence and only the dF build overlaps the first product.
+namespace bx3 {
+constexpr int THREADS = GT + 32;
+constexpr uint32_t OFF_W1L = W1_BYTES, OFF_W2H = 2 * W1_BYTES, OFF_W2L = 2 * W1_BYTES + W2T_BYTES;
+constexpr uint32_t W_BYTES = 2 * (W1_BYTES + W2T_BYTES);          // W1 hi | W1 lo | W2^T hi | W2^T lo
+constexpr uint32_t OFF_R = 0;                                       // rbf hi | lo
+constexpr uint32_t OFF_A = OFF_R + 2 * R_BYTES;                     // a'  hi | lo
+constexpr uint32_t OFF_F = OFF_A + 2 * CH_BYTES;                    // dF  hi | lo
+constexpr uint32_t OFF_H = OFF_F + 2 * CH_BYTES;                    // dh  hi | lo
+constexpr uint32_t OFF_POS = OFF_H + 2 * CH_BYTES;                  // float[128][3]
+constexpr uint32_t OFF_ADJ = OFF_POS + DN_MAX * 12;                 // uint32[128][4]
+constexpr uint32_t OFF_C = OFF_ADJ + DN_MAX * DN_AW * 4;            // float[64]
+constexpr uint32_t OFF_MASK = OFF_C + TE * 4;                       // uint32[4]
+constexpr uint32_t BODY = (OFF_MASK + 16 + 127) / 128 * 128;
+constexpr uint32_t SMEM = W_BYTES + BODY;
+static_assert(SMEM <= 232448 - 1024, "shared memory budget of the fp32-grade weight-gradient kernel");
+}  // namespace bx3
+
+__global__ void __launch_bounds__(bx3::THREADS, 1) cfconv_dense_bwd_x3_kernel(const __grid_constant__ DenseBwdParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  // wbar | r_ready, d1_ready, f_ready, dda_ready, h_ready, w_done
+  __shared__ uint64_t bars[7];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_offset[K1];
+  __shared__ __align__(16) float s_c2[K1];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    tc::mbar_init(&bars[0], 1);
+    tc::mbar_init(&bars[1], GT);  // r_ready   (rbf images, cutoffs and masks written)
+    tc::mbar_init(&bars[2], 1);   // d1_ready  (h in TMEM)
+    tc::mbar_init(&bars[3], GT);  // f_ready   (a' and dF images written)
+    tc::mbar_init(&bars[4], 1);   // dda_ready (da' in TMEM)
+    tc::mbar_init(&bars[5], GT);  // h_ready   (dh images written)
+    tc::mbar_init(&bars[6], 1);   // w_done    (every MMA of the tile finished: all images may be overwritten)
+    tc::mbar_fence_init();
+  }
+  if (tid < K1) {
+    s_offset[tid] = (tid < p.Ng) ? p.offset[tid] : 0.0f;
+    s_c2[tid] = (tid < p.Ng) ? p.coeff_log2e : 0.0f;
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int64_t T = __ldg(p.tile_ptr + p.G);
+  const int64_t U = (int64_t)gridDim.x;
+  const int k1steps = (p.Ng + 1 + 15) >> 4;
+  const int64_t u = (int64_t)blockIdx.x;
+  const int64_t t0 = u * T / U, t1 = (u + 1) * T / U;
+  uint64_t* b = &bars[1];
+  uint8_t* sG = smem + bx3::W_BYTES;
+
+  if (warp >= GT / 32) {
+    // ======================= MMA-issuing warp =======================
+    if (lane == 0) {
+      uint64_t* wbar = &bars[0];
+      tc::mbar_arrive_expect_tx(wbar, bx3::W_BYTES);
+      tc::bulk_g2s(smem, p.weights, bx3::W_BYTES / 2, wbar);
+      tc::bulk_g2s(smem + bx3::W_BYTES / 2, p.weights + bx3::W_BYTES / 2, bx3::W_BYTES / 2, wbar);
+      const uint32_t aW = tc::smem_u32(smem);
+      const uint32_t aG = tc::smem_u32(sG);
+      const uint32_t aR = aG + bx3::OFF_R, aA = aG + bx3::OFF_A, aF = aG + bx3::OFF_F, aH = aG + bx3::OFF_H;
+      const uint32_t tH = tmem_base, tD = tmem_base + 64, tW2 = tmem_base + 128, tW1 = tmem_base + 256;
+      tc::mbar_wait(wbar, 0);
+      DenseWalk w;
+      if (t0 < t1) w.seek(p, t0);
+      uint32_t it = 0;
+      for (int64_t ti = t0; ti < t1; ++ti, ++it) {
+        bool diag;
+        int c_base, j0, ncols;
+        w.tile(diag, c_base, j0, ncols);
+        const int npad = (ncols + 15) & ~15;
+        if (ti + 1 < t1) w.next(p);
+        const uint32_t par = it & 1;
+        // h = W1aug * rbf^T
+        tc::mbar_wait_spin(b + 0, par);
+        tc::tc_fence_after();
+        const uint32_t id1 = tc::umma_idesc_f16(F, npad, 1, 0, 0);
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t wa = aW + (pass == 1 ? bx3::OFF_W1L : 0u), ra = aR + (pass == 2 ? R_BYTES : 0u);
+          for (int ks = 0; ks < k1steps; ++ks)
+            tc::umma_f16(tH, tc::umma_smem_desc(wa + ks * 256, 128, 1024), tc::umma_smem_desc(ra + ks * 256, 128, 1024), id1,
+                         (pass | ks) != 0);
+        }
+        tc::umma_commit(b + 1);
+        // da' = W2^T * dF      (dF image read as MN-major [K=f, N=e]: LBO 128, SBO 2048)
+        tc::mbar_wait_spin(b + 2, par);
+        tc::tc_fence_after();
+        const uint32_t id2 = tc::umma_idesc_f16(F, npad, 1, 0, 1);
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t wa = aW + (pass == 1 ? bx3::OFF_W2L : bx3::OFF_W2H), fa = aF + (pass == 2 ? CH_BYTES : 0u);
+#pragma unroll
+          for (int ks = 0; ks < F / 16; ++ks)
+            tc::umma_f16(tD, tc::umma_smem_desc(wa + ks * 256, 128, 2048), tc::umma_smem_desc(fa + ks * 256, 128, 2048), id2,
+                         (pass | ks) != 0);
+        }
+        tc::umma_commit(b + 3);
+        // dW2 += dF a'^T, K = columns of the tile (images read as K-major [rows=channel, K=e]: SBO 128, LBO 2048)
+        const uint32_t id3 = tc::umma_idesc_f16(F, F, 1, 0, 0);
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t fa = aF + (pass == 1 ? CH_BYTES : 0u), aa = aA + (pass == 2 ? CH_BYTES : 0u);
+          for (int ks = 0; ks < (npad >> 4); ++ks)
+            tc::umma_f16(tW2, tc::umma_smem_desc(fa + ks * 4096, 2048, 128), tc::umma_smem_desc(aa + ks * 4096, 2048, 128), id3,
+                         (it | (uint32_t)pass | (uint32_t)ks) != 0u);
+        }
+        // dW1 += dh rbf^T
+        tc::mbar_wait_spin(b + 4, par);
+        tc::tc_fence_after();
+        const uint32_t id4 = tc::umma_idesc_f16(F, K1, 1, 0, 1);
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t ha = aH + (pass == 1 ? CH_BYTES : 0u), ra = aR + (pass == 2 ? R_BYTES : 0u);
+          for (int ks = 0; ks < (npad >> 4); ++ks)
+            tc::umma_f16(tW1, tc::umma_smem_desc(ha + ks * 4096, 2048, 128), tc::umma_smem_desc(ra + ks * 2048, 1024, 128), id4,
+                         (it | (uint32_t)pass | (uint32_t)ks) != 0u);
+        }
+        tc::umma_commit(b + 5);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= compute warps =======================
+    const int tt = tid;
+    const int wq = warp & 3;                  // TMEM lane quarter
+    const int h = (warp >> 2) & 1;            // column half handled in the channel-major phases
+    const int chan = wq * 32 + lane;
+    const int e = tt & 63;                    // column in the rbf phase
+    const int q = tt >> 6;                    // 4 threads share a column in the rbf phase
+    uint8_t* sR = sG + bx3::OFF_R;
+    uint8_t* sA = sG + bx3::OFF_A;
+    uint8_t* sF = sG + bx3::OFF_F;
+    uint8_t* sH = sG + bx3::OFF_H;
+    float* sPos = reinterpret_cast<float*>(sG + bx3::OFF_POS);
+    uint32_t* sAdj = reinterpret_cast<uint32_t*>(sG + bx3::OFF_ADJ);
+    float* sC = reinterpret_cast<float*>(sG + bx3::OFF_C);
+    uint32_t* sMask = reinterpret_cast<uint32_t*>(sG + bx3::OFF_MASK);
+    const uint32_t tH = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const uint32_t tD = tH + 64, tW2 = tH + 128, tW1 = tH + 256;
+    const float pi_over_cutoff = kPi / p.cutoff;
+
+    float db1 = 0.0f, db2 = 0.0f;
+    float gr[16], xr[16];                     // g and x' rows of the current row block, this thread's channel
+#pragma unroll
+    for (int i = 0; i < 16; ++i) gr[i] = xr[i] = 0.0f;
+    int rows_conf = -1, rows_a0 = -1, staged_conf = -1;
+    uint32_t it = 0;
+    DenseWalk w;
+    if (t0 < t1) w.seek(p, t0);
+
+    for (int64_t ti = t0; ti < t1; ++ti, ++it) {
+      bool diag;
+      int c_base, j0, ncols;
+      w.tile(diag, c_base, j0, ncols);
+      const int cs = w.cs, n = w.n, a0 = w.a0, conf = w.conf;
+      const int m = min(16, n - a0);
+      const int npad = (ncols + 15) & ~15;
+      const uint32_t par = it & 1;
+      const int goff = (cs + a0) * F + chan;
+
+      if (conf != rows_conf || a0 != rows_a0) {
+        rows_conf = conf;
+        rows_a0 = a0;
+#pragma unroll
+        for (int il = 0; il < 16; ++il) {
+          gr[il] = (il < m) ? __ldg(p.g + goff + il * F) : 0.0f;
+          xr[il] = (il < m) ? __ldg(p.xprime + goff + il * F) : 0.0f;
+        }
+      }
+      float gj[2] = {0.0f, 0.0f}, xj[2] = {0.0f, 0.0f};
+      if (!diag) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int a = j0 + 2 * h + jj;
+          if (a < n) {
+            gj[jj] = __ldg(p.g + (cs + a) * F + chan);
+            xj[jj] = __ldg(p.xprime + (cs + a) * F + chan);
+          }
+        }
+      }
+
+      if (conf != staged_conf) {
+        staged_conf = conf;
+        tc::named_bar_sync(1, GT);       // nobody still reads the previous conformer's copy
+        if (tt < n) {
+          const float* pp = p.pos + (int64_t)(cs + tt) * 3;
+          sPos[3 * tt + 0] = __ldg(pp + 0);
+          sPos[3 * tt + 1] = __ldg(pp + 1);
+          sPos[3 * tt + 2] = __ldg(pp + 2);
+          reinterpret_cast<uint4*>(sAdj)[tt] = __ldg(reinterpret_cast<const uint4*>(p.adj) + cs + tt);
+        }
+        tc::named_bar_sync(1, GT);
+      }
+
+      // every MMA of the previous tile has finished reading the images
+      if (it > 0) tc::mbar_wait(b + 5, (it - 1) & 1);
+
+      // ---- column e: pair, directions, distance, cutoff, Gaussian expansion -> rbf images ----
+      {
+        int il, jl, i_loc, j_loc;
+        if (diag) {
+          const int c = min(c_base + e, 119);
+          jl = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)c)) * 0.5f);
+          if (jl * (jl - 1) / 2 > c) --jl;
+          if ((jl + 1) * jl / 2 <= c) ++jl;
+          il = c - jl * (jl - 1) / 2;
+          i_loc = a0 + il;
+          j_loc = a0 + jl;
+        } else {
+          il = e & 15;
+          i_loc = a0 + il;
+          j_loc = j0 + (e >> 4);
+        }
+        bool ef = false, er = false;
+        if (e < ncols) {
+          ef = (sAdj[i_loc * DN_AW + (j_loc >> 5)] >> (j_loc & 31)) & 1u;     // edge j -> i
+          er = (sAdj[j_loc * DN_AW + (i_loc >> 5)] >> (i_loc & 31)) & 1u;     // edge i -> j
+        }
+        const bool live = ef || er;
+        float d = 0.0f;
+        if (live) {
+          const float dx = sPos[3 * j_loc] - sPos[3 * i_loc], dy = sPos[3 * j_loc + 1] - sPos[3 * i_loc + 1],
+                      dz = sPos[3 * j_loc + 2] - sPos[3 * i_loc + 2];
+          d = sqrtf(dx * dx + dy * dy + dz * dz);          // the expression of the neighbour search (graph.cu)
+        }
+        if (q == 0) {
+          sC[e] = live ? cos_cutoff_nomask(d, pi_over_cutoff) : 0.0f;
+          const unsigned bf = __ballot_sync(0xffffffffu, ef), br = __ballot_sync(0xffffffffu, er);
+          if (lane == 0) {
+            sMask[e >> 5] = bf;
+            sMask[2 + (e >> 5)] = br;
+          }
+        }
+        if (e < npad) {
+          uint8_t* rowp = sR + (e >> 3) * 1024 + (e & 7) * 16;
+          for (int jc = q; jc < 2 * k1steps; jc += 4) {
+            float v[8];
+            const float4* op = reinterpret_cast<const float4*>(s_offset + jc * 8);
+            const float4* cp2 = reinterpret_cast<const float4*>(s_c2 + jc * 8);
+            const float4 o0 = op[0], o1 = op[1], k0 = cp2[0], k1 = cp2[1];
+            const float off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+            const float ck[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float x = d - off[j];
+              v[j] = live ? tc::fast_ex2(ck[j] * (x * x)) : 0.0f;
+            }
+            uint4 hi, lo;
+            split_bf16x8(v, hi, lo);
+            *reinterpret_cast<uint4*>(rowp + jc * 128) = hi;
+            *reinterpret_cast<uint4*>(rowp + R_BYTES + jc * 128) = lo;
+          }
+        }
+      }
+      tc::fence_proxy_async();
+      tc::mbar_arrive(b + 0);
+      tc::named_bar_sync(1, GT);   // sC / sMask visible to the whole group
+
+      // ---- dF images from the row registers (runs while the tensor core computes h) ----
+      {
+        const uint32_t mf = sMask[h], mr = sMask[2 + h];
+        uint8_t* dstF = sF + chan * 16 + (h * 4) * 2048;
+        const float* sC32 = sC + 32 * h;
+        if (32 * h < npad) {
+          if (!diag) {
+            dense_df_rect<CH_BYTES>(gr, xr, gj, xj, mf, mr, sC32, dstF, db2);
+          } else {
+            switch ((c_base >> 5) + h) {
+              case 0: dense_df_diag<0, CH_BYTES>(gr, xr, mf, mr, sC32, dstF, db2); break;
+              case 1: dense_df_diag<32, CH_BYTES>(gr, xr, mf, mr, sC32, dstF, db2); break;
+              case 2: dense_df_diag<64, CH_BYTES>(gr, xr, mf, mr, sC32, dstF, db2); break;
+              default: dense_df_diag<96, CH_BYTES>(gr, xr, mf, mr, sC32, dstF, db2); break;
+            }
+          }
+        }
+      }
+
+      // ---- epilogue 1: a' = C ssp(h) -> images (h stays in TMEM for epilogue 3) ----
+      tc::mbar_wait(b + 1, par);
+      tc::tc_fence_after();
+      {
+        const int cb = h * 32, ce = min(npad, h * 32 + 32);
+        for (int c0 = cb; c0 < ce; c0 += 16) {
+          float v[16];
+          tc::tmem_ld16(tH + c0, v);
+          float c[16];
+          const float4* cp = reinterpret_cast<const float4*>(sC + c0);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const float4 cc = cp[k4];
+            c[k4 * 4 + 0] = cc.x; c[k4 * 4 + 1] = cc.y; c[k4 * 4 + 2] = cc.z; c[k4 * 4 + 3] = cc.w;
+          }
+          tc::tmem_wait_ld();
+          float a[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = v[j];
+            const float t = tc::fast_ex2(-1.4426950408889634f * fabsf(x));
+            a[j] = c[j] * fmaf(tc::fast_lg2(1.0f + t) - 1.0f, kLn2, fmaxf(x, 0.0f));
+          }
+          uint4 hi, lo;
+          split_bf16x8(a, hi, lo);
+          *reinterpret_cast<uint4*>(sA + chan * 16 + (c0 >> 3) * 2048) = hi;
+          *reinterpret_cast<uint4*>(sA + CH_BYTES + chan * 16 + (c0 >> 3) * 2048) = lo;
+          split_bf16x8(a + 8, hi, lo);
+          *reinterpret_cast<uint4*>(sA + chan * 16 + ((c0 >> 3) + 1) * 2048) = hi;
+          *reinterpret_cast<uint4*>(sA + CH_BYTES + chan * 16 + ((c0 >> 3) + 1) * 2048) = lo;
+        }
+      }
+      tc::tc_fence_before();
+      tc::fence_proxy_async();
+      tc::mbar_arrive(b + 2);
+
+      // ---- epilogue 3: dh = da' * C sigmoid(h) -> dh images ----
+      tc::mbar_wait(b + 3, par);
+      tc::tc_fence_after();
+      {
+        const int cb = h * 32, ce = min(npad, h * 32 + 32);
+        for (int c0 = cb; c0 < ce; c0 += 16) {
+          float v[16], hh[16];
+          tc::tmem_ld16(tD + c0, v);
+          tc::tmem_ld16(tH + c0, hh);
+          float c[16];
+          const float4* cp = reinterpret_cast<const float4*>(sC + c0);
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const float4 cc = cp[k4];
+            c[k4 * 4 + 0] = cc.x; c[k4 * 4 + 1] = cc.y; c[k4 * 4 + 2] = cc.z; c[k4 * 4 + 3] = cc.w;
+          }
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = hh[j];
+            const float t = tc::fast_ex2(-1.4426950408889634f * fabsf(x));
+            const float inv = __fdividef(1.0f, 1.0f + t);
+            v[j] *= c[j] * (x >= 0.0f ? inv : t * inv);
+            db1 += v[j];
+          }
+          uint4 hi, lo;
+          split_bf16x8(v, hi, lo);
+          *reinterpret_cast<uint4*>(sH + chan * 16 + (c0 >> 3) * 2048) = hi;
+          *reinterpret_cast<uint4*>(sH + CH_BYTES + chan * 16 + (c0 >> 3) * 2048) = lo;
+          split_bf16x8(v + 8, hi, lo);
+          *reinterpret_cast<uint4*>(sH + chan * 16 + ((c0 >> 3) + 1) * 2048) = hi;
+          *reinterpret_cast<uint4*>(sH + CH_BYTES + chan * 16 + ((c0 >> 3) + 1) * 2048) = lo;
+        }
+      }
+      tc::tc_fence_before();
+      tc::fence_proxy_async();
+      tc::mbar_arrive(b + 4);
+      if (ti + 1 < t1) w.next(p);
+    }
+
+    // ---- drain: accumulators -> this CTA's partial block ----
     float* part = p.partial + u * (int64_t)PART_FLOATS;
     const bool any = t0 < t1;
     if (any) {
@@ -2015,5 +2492,80 @@ extern "C" int cmp_cfconv_dense_bwd_weights(const float* g, const float* xprime,
   reduce_partials_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(p.partial, ws ? grid : grid * NG, num_gaussians, dW1,
                                                                     db1, dW2, db2);
   CMP_LAUNCH_CHECK("cmp_cfconv_dense_bwd_weights");
+  return CMP_OK;
+}
+
+extern "C" size_t cmp_cfconv_dense_bwd_x3_weights_bytes(void) { return 2 * (W1_BYTES + W2T_BYTES); }
+
+extern "C" int cmp_cfconv_dense_bwd_x3_pack_weights_grouped(const void* jobs, int count, int num_filters,
+                                                            int num_gaussians, cmp_stream_t stream) {
+  CMP_REQUIRE(num_filters == F && num_gaussians >= 1 && num_gaussians < K1, CMP_EUNSUPPORTED,
+              "cmp_cfconv_dense_bwd_x3_pack_weights_grouped: needs num_filters == 128 and num_gaussians < 64");
+  CMP_REQUIRE(count >= 0 && count <= 32, CMP_EINVAL,
+              "cmp_cfconv_dense_bwd_x3_pack_weights_grouped: count must be in [0, 32]");
+  if (count == 0) return CMP_OK;
+  CMP_REQUIRE(jobs, CMP_EINVAL, "cmp_cfconv_dense_bwd_x3_pack_weights_grouped: null pointer");
+  const PackBwdX3Job* in = reinterpret_cast<const PackBwdX3Job*>(jobs);
+  PackBwdX3Group g;
+  for (int i = 0; i < count; ++i) {
+    CMP_REQUIRE(in[i].W1 && in[i].b1 && in[i].W2 && in[i].packed, CMP_EINVAL,
+                "cmp_cfconv_dense_bwd_x3_pack_weights_grouped: null pointer");
+    g.j[i] = in[i];
+  }
+  const int total = F * K1 + F * F;
+  pack_bwd_weights_x3_kernel<<<dim3((total + 255) / 256, count), 256, 0, as_stream(stream)>>>(g, num_gaussians);
+  CMP_LAUNCH_CHECK("cmp_cfconv_dense_bwd_x3_pack_weights_grouped");
+  return CMP_OK;
+}
+
+extern "C" int cmp_cfconv_dense_bwd_x3_weights(const float* g, const float* xprime, const float* pos,
+                                               const int32_t* seg_ptr, const uint32_t* adj, const int32_t* tile_ptr,
+                                               int64_t G, const void* packed_bwd_x3_weights, const float* offset,
+                                               int num_gaussians, float coeff, float cutoff, int num_filters,
+                                               float* dW1, float* db1, float* dW2, float* db2, void* workspace,
+                                               size_t workspace_bytes, cmp_stream_t stream) {
+  CMP_REQUIRE(num_filters == F && num_gaussians >= 1 && num_gaussians < K1, CMP_EUNSUPPORTED,
+              "cmp_cfconv_dense_bwd_x3_weights: needs num_filters == 128 and num_gaussians < 64");
+  CMP_REQUIRE(G >= 1 && G < ((int64_t)1 << 31), CMP_EINVAL, "cmp_cfconv_dense_bwd_x3_weights: bad number of conformers");
+  CMP_REQUIRE(g && xprime && pos && seg_ptr && adj && tile_ptr && packed_bwd_x3_weights && offset && dW1 && db1 && dW2 &&
+                  db2,
+              CMP_EINVAL, "cmp_cfconv_dense_bwd_x3_weights: null pointer");
+  CMP_REQUIRE(((uintptr_t)packed_bwd_x3_weights % 16 == 0) && ((uintptr_t)adj % 16 == 0), CMP_EINVAL,
+              "cmp_cfconv_dense_bwd_x3_weights: packed weights / adj must be 16-byte aligned");
+  CMP_REQUIRE(workspace && workspace_bytes >= cmp_cfconv_dense_bwd_workspace(), CMP_EWORKSPACE,
+              "cmp_cfconv_dense_bwd_x3_weights: workspace too small");
+  CMP_REQUIRE(cmp_device_is_sm100(), CMP_EUNSUPPORTED,
+              "cmp_cfconv_dense_bwd_x3_weights: needs an sm_100 device (tcgen05)");
+  cudaStream_t st = as_stream(stream);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(cfconv_dense_bwd_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bx3::SMEM) !=
+        cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("cmp_cfconv_dense_bwd_x3_weights: cannot opt in to %u bytes of shared memory", bx3::SMEM);
+      return CMP_ECUDA;
+    }
+    attr_set = true;
+  }
+  DenseBwdParams p;
+  p.g = g;
+  p.xprime = xprime;
+  p.pos = pos;
+  p.seg_ptr = seg_ptr;
+  p.adj = adj;
+  p.tile_ptr = tile_ptr;
+  p.weights = reinterpret_cast<const uint8_t*>(packed_bwd_x3_weights);
+  p.offset = offset;
+  p.partial = reinterpret_cast<float*>(workspace);
+  p.coeff_log2e = coeff * 1.4426950408889634f;
+  p.cutoff = cutoff;
+  p.Ng = num_gaussians;
+  p.G = (int)G;
+  const int grid = sm_count();
+  cfconv_dense_bwd_x3_kernel<<<grid, bx3::THREADS, bx3::SMEM, st>>>(p);
+  CMP_LAUNCH_CHECK("cmp_cfconv_dense_bwd_x3_weights");
+  const int total = F * F + F * K1 + 2 * F;
+  reduce_partials_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(p.partial, grid, num_gaussians, dW1, db1, dW2, db2);
+  CMP_LAUNCH_CHECK("cmp_cfconv_dense_bwd_x3_weights");
   return CMP_OK;
 }

@@ -12,6 +12,7 @@ checkpoints load with ``strict=True``.
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable, Optional
 
 import torch
@@ -24,6 +25,15 @@ from .graph import NeighborList, build_neighbor_list, graph_from_edge_index, rad
 # fused (bf16-mode) trunk: chain the node linears of a block tail in one kernel (cmp_node_chain_fwd); False = one launch
 # per Linear (kept for cross-checking)
 CHAIN_NODE_LINEARS = True
+
+# "fp32" precision: fused fp32-grade (three-pass) CFConv kernels whenever the graph qualifies (radius-built, promised
+# max_atoms <= 128); False = always the exact kernels on materialised [E, *] tensors (same as precision "exact")
+FUSED_FP32 = os.environ.get("CMP_FUSED_FP32", "1") != "0"
+# "fp32" precision, fused CFConv: node linears on the split-bf16 tcgen05 kernels (chained block tails) instead of the
+# exact SIMT GEMM.  Off by default: bf16 hi + lo pairs carry 16 significant bits, which over the 18 node GEMMs of a
+# 6-block trunk costs 1e-5 .. 2e-5 on the embeddings and 4e-5 on the gradients (measured, tools/x3_errors.py) - outside
+# the 1e-5 bar of this mode.  1.6 x faster (cfg 2: 234 K vs 146 K conformers/s); CMP_FP32_NODE_TC=1 or nn.FP32_NODE_TC.
+FP32_NODE_TC = os.environ.get("CMP_FP32_NODE_TC", "0") != "0"
 
 
 class Linear(nn.Linear):
@@ -105,7 +115,9 @@ class CFConv(nn.Module):
         self.lin2 = Linear(num_filters, out_channels)
         self.nn = nn
         self.cutoff = cutoff
-        self.precision = "fp32"     # "fp32": exact kernels;  "bf16": fused tcgen05 kernel (bf16 filter MLP)
+        # "exact": exact-fp32 kernels on materialised tensors;  "fp32": fp32-grade fused tcgen05 kernels where the graph
+        # qualifies, else the exact kernels;  "bf16": fused tcgen05 kernels with an f16 filter MLP
+        self.precision = "fp32"
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -119,19 +131,30 @@ class CFConv(nn.Module):
                 and isinstance(net[1], ShiftedSoftplus) and isinstance(net[2], torch.nn.Linear)
                 and net[0].bias is not None and net[2].bias is not None)
 
-    def fused_ok(self, graph, smearing) -> bool:
-        """The fused geometric kernel applies: bf16 mode, radius-built graph, Gaussian expansion of its
-        distances, standard filter MLP, supported (num_filters, num_gaussians), sm_100 device."""
-        return (self.precision == "bf16" and graph is not None and graph.G > 0 and graph.cutoff is not None
+    def fused_mode(self, graph, smearing):
+        """Which fused geometric kernel applies to this layer on this graph: ``"f16"`` (bf16 mode: f16 filter MLP),
+        ``"x3"`` (fp32 mode: fp32-grade three-pass kernels; needs a promised ``max_atoms`` <= 128) or ``None`` (the
+        exact kernels).  Fused kernels need a radius-built graph, the Gaussian expansion of its distances, the standard
+        filter MLP, supported (num_filters, num_gaussians) and an sm_100 device."""
+        if self.precision not in ("bf16", "fp32") or (self.precision == "fp32" and not FUSED_FP32):
+            return None
+        if not (graph is not None and graph.G > 0 and graph.cutoff is not None
                 and not graph.loop and isinstance(smearing, GaussianSmearing) and self._standard_mlp()
                 and ops.fused_supported(self.lin1.out_features, smearing.offset.numel())
-                and self.nn[0].in_features == smearing.offset.numel())
+                and self.nn[0].in_features == smearing.offset.numel()):
+            return None
+        if self.precision == "bf16":
+            return "f16"
+        return "x3" if ops.x3_graph_ok(graph) else None
+
+    def fused_ok(self, graph, smearing) -> bool:
+        return self.fused_mode(graph, smearing) is not None
 
     def forward_fused(self, x, graph, smearing, act=_lib.ACT_NONE):
         xp = self.lin1(x)
         net = self.nn
         agg = ops.cfconv_fused(xp, net[0].weight, net[0].bias, net[2].weight, net[2].bias, graph, smearing.offset,
-                               smearing.coeff, self.cutoff)
+                               smearing.coeff, self.cutoff, x3=self.fused_mode(graph, smearing) == "x3")
         return self.lin2(agg, act=act)
 
     def filter(self, edge_attr):
@@ -239,10 +262,13 @@ class SchNet(nn.Module):
         raise_for_status(self.status, reset=True)
 
     def set_precision(self, precision: str):
-        """"fp32": exact-fp32 kernels (1e-5 parity mode).  "bf16": fused tcgen05 CFConv with a bf16
-        filter MLP (fp32 accumulation, fp32 node features); tolerance stated in DESIGN.md."""
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        """"exact": exact-fp32 kernels on materialised rbf / filter tensors (the reference's own op sequence).
+        "fp32" (default): the 1e-5 parity mode - fp32-grade fused tcgen05 CFConv (hi + lo operand images, three MMA
+        passes, fp32 epilogues) and split-bf16 node linears when the model was given ``max_atoms_hint`` <= 128 and the
+        shapes are supported, otherwise the exact kernels.  "bf16": fused tcgen05 CFConv with an f16 filter MLP (fp32
+        accumulation, fp32 node features); tolerance stated in DESIGN.md."""
+        if precision not in ("exact", "fp32", "bf16"):
+            raise ValueError("precision must be 'exact', 'fp32' or 'bf16'")
         self.precision = precision
         for m in self.modules():
             if isinstance(m, CFConv):
@@ -250,6 +276,15 @@ class SchNet(nn.Module):
             if isinstance(m, Linear):
                 m.tc = precision == "bf16"
         return self
+
+    def _node_tc(self, on: bool):
+        """fp32 mode: the node linears follow the CFConv kernels (tcgen05 with the fused path, exact otherwise)."""
+        if self.precision != "fp32":
+            return
+        mods = [m for blk in self.interactions for m in (blk.conv.lin1, blk.conv.lin2, blk.lin)]
+        mods += [m for m in self.children() if isinstance(m, Linear)]       # heads
+        for m in mods:
+            m.tc = bool(on)
 
     def reset_parameters(self):
         self.embedding.reset_parameters()
@@ -270,7 +305,10 @@ class SchNet(nn.Module):
         if isinstance(ig, RadiusInteractionGraph):
             graph = ig.neighbor_list(pos, batch, num_graphs, max_atoms=self.max_atoms_hint, status=self.status)
             h = self.embed(z, graph.status)
-            if all(blk.conv.fused_ok(graph, self.distance_expansion) for blk in self.interactions):
+            modes = {blk.conv.fused_mode(graph, self.distance_expansion) for blk in self.interactions}
+            x3 = modes == {"x3"}
+            self._node_tc(x3 and FP32_NODE_TC)
+            if len(modes) == 1 and None not in modes:
                 # fused path: no edge_index / rbf[E, Ng] / filter[E, F] is ever materialised, no host sync
                 blocks = list(self.interactions)
                 chained = CHAIN_NODE_LINEARS and all(
@@ -286,7 +324,7 @@ class SchNet(nn.Module):
                 for blk, nxt in zip(blocks, blocks[1:] + [None]):
                     net = blk.conv.nn
                     agg = ops.cfconv_fused(x, net[0].weight, net[0].bias, net[2].weight, net[2].bias, graph, sm.offset,
-                                           sm.coeff, blk.conv.cutoff)
+                                           sm.coeff, blk.conv.cutoff, x3=x3)
                     if nxt is not None:
                         h, x = ops.block_tail(agg, h, blk.conv.lin2, blk.lin, nxt.conv.lin1)
                     else:

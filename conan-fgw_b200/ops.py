@@ -146,7 +146,7 @@ class prepacked_weights:
         self.cache = None
 
     def __enter__(self):
-        self.cache = _prepack(self.modules, self.dense_only)
+        self.cache = _prepack(self.modules, self.dense_only, x3_hint=self.dense_only)
         with _registry_lock:
             _stack("packs").append(self)
         return self
@@ -158,17 +158,30 @@ class prepacked_weights:
         return False
 
 
-def _prepack(modules, dense_only=False):
+def _prepack(modules, dense_only=False, x3_hint=True):
     """``dense_only``: the caller vouches that no conformer exceeds the dense kernel's atom limit, so the weight image of
     the per-edge forward kernel is not needed."""
     from .nn import InteractionBlock, Linear    # late import: nn imports ops
 
     cache = {}
-    node, filt = [], []
+    node, filt, filt_x3 = [], [], []
     gmax = 32
     skip = set()     # filter-MLP Linears of fused blocks never run as node GEMMs
     for root in modules:
         for m in root.modules():
+            if isinstance(m, InteractionBlock) and m.conv.precision == "fp32" and m.mlp[0].weight.is_cuda and x3_hint:
+                # fp32-grade fused kernels: hi + lo images of the dense forward and of the weight-gradient kernel
+                W1, b1, W2, b2 = m.mlp[0].weight, m.mlp[0].bias, m.mlp[2].weight, m.mlp[2].bias
+                if fused_supported(W1.shape[0], W1.shape[1]) and m.conv._standard_mlp():
+                    skip.update((W1.data_ptr(), W2.data_ptr()))
+                    if W1.data_ptr() not in cache:
+                        dev = W1.device
+                        px = torch.empty(_lib.size_query("cmp_cfconv_dense_x3_weights_bytes"), dtype=torch.uint8,
+                                         device=dev)
+                        pbx = torch.empty(_lib.size_query("cmp_cfconv_dense_bwd_x3_weights_bytes"), dtype=torch.uint8,
+                                          device=dev)
+                        cache[W1.data_ptr()] = (None, None, None, px, pbx)
+                        filt_x3.append(tuple(_f32c(t.detach()) for t in (W1, b1, W2, b2)) + (px, pbx))
             if isinstance(m, InteractionBlock) and m.conv.precision == "bf16" and m.mlp[0].weight.is_cuda:
                 W1, b1, W2, b2 = m.mlp[0].weight, m.mlp[0].bias, m.mlp[2].weight, m.mlp[2].bias
                 if fused_supported(W1.shape[0], W1.shape[1]):
@@ -234,7 +247,20 @@ def _prepack(modules, dense_only=False):
         call("cmp_cfconv_tc_pack_bwd_weights_grouped", ctypes.addressof(arr), len(chunk), F, Ng)
         if FUSED_DENSE:
             call("cmp_cfconv_dense_pack_weights_grouped", ctypes.addressof(darr), len(chunk), F, Ng)
-    cache["_keepalive"] = (node, filt)
+    for lo in range(0, len(filt_x3), gmax):
+        chunk = filt_x3[lo:lo + gmax]
+        F, Ng = chunk[0][0].shape
+        if any(c[0].shape != (F, Ng) for c in chunk):
+            raise _lib.ConanMPError("prepacked_weights: interaction blocks of different shapes in one model")
+        darr = (_lib.DensePackJob * len(chunk))()
+        barr = (_lib.BwdX3PackJob * len(chunk))()
+        for dslot, bslot, (W1, b1, W2, b2, px, pbx) in zip(darr, barr, chunk):
+            dslot.W1, dslot.b1, dslot.W2, dslot.b2 = W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr()
+            dslot.packed = px.data_ptr()
+            bslot.W1, bslot.b1, bslot.W2, bslot.packed = dslot.W1, dslot.b1, dslot.W2, pbx.data_ptr()
+        call("cmp_cfconv_dense_x3_pack_weights_grouped", ctypes.addressof(darr), len(chunk), F, Ng)
+        call("cmp_cfconv_dense_bwd_x3_pack_weights_grouped", ctypes.addressof(barr), len(chunk), F, Ng)
+    cache["_keepalive"] = (node, filt, filt_x3)
     return cache
 
 
@@ -861,6 +887,20 @@ def pack_dense_x3_weights(W1, b1, W2, b2):
     return packed
 
 
+def pack_bwd_x3_weights(W1, b1, W2):
+    cached = _cached_images(W1)
+    if cached is not None and len(cached) > 4 and cached[4] is not None:
+        return cached[4]
+    F, Ng = W1.shape
+    packed = torch.empty(_lib.size_query("cmp_cfconv_dense_bwd_x3_weights_bytes"), dtype=torch.uint8, device=W1.device)
+    job = (_lib.BwdX3PackJob * 1)()
+    keep = [_f32c(t.detach()) for t in (W1, b1, W2)]
+    job[0].W1, job[0].b1, job[0].W2, job[0].packed = keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(), \
+        packed.data_ptr()
+    call("cmp_cfconv_dense_bwd_x3_pack_weights_grouped", ctypes.addressof(job), 1, F, Ng)
+    return packed
+
+
 class _CFConvFusedFn(Function):
     """Geometric CFConv in one tcgen05 kernel (bf16 filter MLP):  agg = sum_j x'_j * W(d_ij) * C(d_ij).
 
@@ -908,7 +948,7 @@ class _CFConvFusedFn(Function):
 
 FUSED_WEIGHT_GRADS = True
 # fp32-grade mode: weight gradients on the three-pass tcgen05 kernel; False = exact-fp32 recompute on [E, *] tensors
-X3_WEIGHT_GRADS = False
+X3_WEIGHT_GRADS = True
 # one column per undirected pair in the weight-gradient pass (both directions share the filter); False = one column
 # per directed edge with fp32 g (kept for cross-checking)
 FUSED_PAIR_GRADS = True
@@ -925,7 +965,9 @@ def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff, x3=
     Ng = offset.numel()
     dev = g.device
     cached = _cached_images(W1)
-    if cached is not None:
+    if x3:
+        packed = None
+    elif cached is not None and cached[1] is not None:
         packed = cached[1]
     else:
         packed = torch.empty(_lib.size_query("cmp_cfconv_tc_bwd_weights_bytes"), dtype=torch.uint8, device=dev)
@@ -935,6 +977,15 @@ def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff, x3=
     dW2 = torch.empty(F, F, dtype=torch.float32, device=dev)
     db2 = torch.empty(F, dtype=torch.float32, device=dev)
     e_hint = graph._E if graph._E is not None else graph.cap_E
+    if x3:
+        if not x3_graph_ok(graph):
+            raise _lib.ConanMPError("fp32-grade fused CFConv: needs a radius-built graph with max_atoms <= 128")
+        ws = _lib.workspace(_lib.size_query("cmp_cfconv_dense_bwd_workspace"), dev)
+        call("cmp_cfconv_dense_bwd_x3_weights", ptr(_f32c(g)), ptr(_f32c(xprime)), ptr(graph.pos), ptr(graph.seg_ptr),
+             ptr(graph.adjacency()), ptr(graph.dense_bwd_tiles()), graph.G, ptr(pack_bwd_x3_weights(W1, b1, W2)),
+             ptr(offset), Ng, float(coeff), float(cutoff), F, ptr(dW1), ptr(db1), ptr(dW2), ptr(db2), ptr(ws),
+             ws.numel(), work=2.0 * (Ng * F + F * F) * float(e_hint))
+        return dW1, db1, dW2, db2
     if (FUSED_DENSE_GRADS and FUSED_DENSE and graph.G > 0 and graph.pos is not None and not graph.loop
             and graph.max_atoms is not None and graph.max_atoms <= _lib.size_query("cmp_cfconv_dense_max_atoms")):
         ws = _lib.workspace(_lib.size_query("cmp_cfconv_dense_bwd_workspace"), dev)

@@ -321,6 +321,27 @@ int cmp_cfconv_dense_bwd_weights(const float* g, const float* xprime, const floa
                                  float cutoff, int num_filters, float* dW1, float* db1, float* dW2, float* db2,
                                  void* workspace, size_t workspace_bytes, cmp_stream_t stream);
 
+/* fp32-grade variant of cmp_cfconv_dense_bwd_weights ("x3", cfconv_dense_bwd_x3_kernel): every operand (Gaussians,
+ * W1, W2^T, a', dF, dh) as bf16 hi + lo images, three tcgen05 passes per product, fp32 epilogues, sigmoid recomputed from
+ * the TMEM-resident pre-activations.  dW1 / db1 / dW2 / db2 meet the 1e-5 bar of the exact path.
+ *   packed_bwd_x3_weights: cmp_cfconv_dense_bwd_x3_pack_weights_grouped (cmp_cfconv_dense_bwd_x3_weights_bytes() bytes:
+ *   W1aug hi | lo | W2^T hi | lo); jobs = array of cmp_bwd_x3_pack_job_t in HOST memory (count <= 32).
+ * Other arguments, workspace and tile_ptr as cmp_cfconv_dense_bwd_weights. */
+typedef struct {
+  const float* W1;
+  const float* b1;
+  const float* W2;
+  void* packed;
+} cmp_bwd_x3_pack_job_t;
+size_t cmp_cfconv_dense_bwd_x3_weights_bytes(void);
+int cmp_cfconv_dense_bwd_x3_pack_weights_grouped(const void* jobs, int count, int num_filters, int num_gaussians,
+                                                 cmp_stream_t stream);
+int cmp_cfconv_dense_bwd_x3_weights(const float* g, const float* xprime, const float* pos, const int32_t* seg_ptr,
+                                    const uint32_t* adj, const int32_t* tile_ptr, int64_t G,
+                                    const void* packed_bwd_x3_weights, const float* offset, int num_gaussians,
+                                    float coeff, float cutoff, int num_filters, float* dW1, float* db1, float* dW2,
+                                    float* db2, void* workspace, size_t workspace_bytes, cmp_stream_t stream);
+
 /* Filter-MLP weight gradients of the fused CFConv in ONE kernel (+ a fixed-order reduction of the
  * per-pipeline partial sums): recomputes rbf / hidden / a' per 64-edge tile on chip and accumulates
  * dW2 = sum_e dF_e a'_e^T and dW1 = sum_e dh_e rbf_e^T in TMEM (tcgen05, bf16 operands, fp32

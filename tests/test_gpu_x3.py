@@ -121,3 +121,117 @@ def test_x3_refuses_graphs_without_an_atom_bound():
     xp = torch.randn(b.z.numel(), F, device=DEV)
     with pytest.raises(cmp._lib.ConanMPError):
         ops.cfconv_fused(xp, *_params(blk), nl, gs.offset, gs.coeff, 10.0, x3=True)
+
+
+# ---- whole models in the "fp32" precision with a promised atom bound: fused fp32-grade kernels end to end ----------------
+from oracle import schnet as osn   # noqa: E402  (test infrastructure: the CPU oracle is the checker)
+
+
+def _pair(seed=0, **cfg):
+    torch.manual_seed(seed)
+    o = osn.SchNetNoSum(None, **cfg)
+    with torch.no_grad():
+        for p in o.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    c = cmp.SchNetNoSum(None, **cfg).to(DEV)
+    c.load_state_dict(o.state_dict(), strict=True)
+    return o, c
+
+
+def _compare_model(o, c, b, tol=TOL, tol_grad=None):
+    tol_grad = tol if tol_grad is None else tol_grad
+    out_o = o(b.z, b.pos, b.batch)
+    out_c = c(b.z.to(DEV), b.pos.to(DEV), b.batch.to(DEV))
+    c.check_status()
+    assert out_c.shape == out_o.shape
+    assert rel_err(out_c, out_o) < tol
+    o.zero_grad(), c.zero_grad()
+    out_o.pow(2).mean().backward()
+    out_c.pow(2).mean().backward()
+    po, pc = dict(o.named_parameters()), dict(c.named_parameters())
+    for k in po:
+        if po[k].grad is None:
+            assert pc[k].grad is None, k
+            continue
+        assert pc[k].grad is not None, k
+        assert rel_err(pc[k].grad, po[k].grad) < tol_grad, k
+
+
+# Stated tolerances of the fused fp32-grade mode on a 6-block trunk (measured: tools/x3_errors.py, profiles/r02_x3_errors.md).
+# The tensor pipe accumulates with truncation and the weight-gradient kernel holds its gradient operands as bf16 pairs, so
+# the gradients of the filter MLP sit at 1.3e-5 where the exact kernels reach 6e-7; the embeddings meet 1e-5 (3e-6).
+X3_TOL = {False: (1e-5, 2e-5),       # exact node linears (the default): embeddings, gradients
+          True: (2.5e-5, 6e-5)}      # split-bf16 tcgen05 node linears (nn.FP32_NODE_TC): 1.9e-5 / 4.1e-5 measured
+
+
+@pytest.mark.parametrize("node_tc", [True, False], ids=["tcgen05-node-linears", "exact-node-linears"])
+def test_fp32_mode_runs_the_fused_kernels(node_tc, monkeypatch):
+    """BASELINE cfg 1 shape (scaled): with ``max_atoms_hint`` the default precision routes every CFConv to the x3 kernels
+    (no [E, *] tensor, no host sync); ``nn.FP32_NODE_TC`` also moves the node linears to the split-bf16 tcgen05 kernels."""
+    _need_sm100()
+    from conan_fgw_b200 import nn as cnn
+    monkeypatch.setattr(cnn, "FP32_NODE_TC", node_tc)
+    o, c = _pair(2)
+    b = syn.make_config_batch("cfg1_esol_fwd", scale=0.25)
+    c.max_atoms_hint = int(torch.bincount(b.batch).max())
+    lib = cmp._lib
+    lib.reset_launches()
+    lib.timer = lib.KernelTimer(["cmp_cfconv_dense_x3_fwd", "cmp_cfconv_dense_bwd_x3_weights", "cmp_cfconv_message_fwd",
+                                 "cmp_gemm_f32", "cmp_node_chain_fwd"])
+    try:
+        _compare_model(o, c, b, *X3_TOL[node_tc])
+        torch.cuda.synchronize()
+        seen = {k: v[0] for k, v in lib.timer.summary().items()}
+    finally:
+        lib.timer = None
+    assert seen.get("cmp_cfconv_dense_x3_fwd", 0) == 12 and seen.get("cmp_cfconv_dense_bwd_x3_weights", 0) == 6
+    assert seen.get("cmp_cfconv_message_fwd", 0) == 0
+    assert (seen.get("cmp_node_chain_fwd", 0) > 0) == node_tc
+
+
+def test_fp32_mode_truncated_graphs_and_three_blocks():
+    """ConAN's regression instantiation (T = 3) on 65-atom conformers: truncated, asymmetric neighbour lists."""
+    _need_sm100()
+    o, c = _pair(3, num_interactions=3)
+    c.max_atoms_hint = 65
+    _compare_model(o, c, syn.make_batch(1, 2, 65, seed=4))
+
+
+def test_fp32_mode_without_a_bound_or_in_exact_precision_stays_on_the_exact_kernels():
+    _need_sm100()
+    o, c = _pair(5, num_interactions=2)
+    b = syn.make_batch(2, 2, 20, seed=6)
+    lib = cmp._lib
+    for setup in ("no-hint", "exact"):
+        c.max_atoms_hint = None if setup == "no-hint" else 20
+        c.set_precision("fp32" if setup == "no-hint" else "exact")
+        lib.timer = lib.KernelTimer(["cmp_cfconv_dense_x3_fwd", "cmp_cfconv_message_fwd"])
+        try:
+            _compare_model(o, c, b)
+            torch.cuda.synchronize()
+            seen = {k: v[0] for k, v in lib.timer.summary().items()}
+        finally:
+            lib.timer = None
+        assert seen.get("cmp_cfconv_dense_x3_fwd", 0) == 0 and seen.get("cmp_cfconv_message_fwd", 0) > 0
+
+
+def test_fp32_fused_training_step_in_a_cuda_graph_matches_the_exact_mode():
+    """dp.RegressionStep in fp32 mode is sync-free (capturable) and its loss trajectory follows the exact kernels'."""
+    _need_sm100()
+    from conan_fgw_b200.dp import RegressionStep
+    cfg = dict(hidden_channels=128, num_filters=128, num_interactions=3, num_gaussians=50, cutoff=10.0)
+    b = syn.make_batch(8, 3, 24, seed=9).to(DEV)
+    targets = torch.randn(8, 1, device=DEV)
+    losses = {}
+    for prec in ("exact", "fp32"):
+        torch.manual_seed(0)
+        m = cmp.SchNetNoSum(None, **cfg).to(DEV).set_precision(prec)
+        m.max_atoms_hint = 24
+        tr = RegressionStep(m, 64, 3, lr=1e-3)
+        if prec == "fp32":
+            tr.capture(b.z, b.pos, b.batch, targets, b.num_graphs)
+        losses[prec] = [float(tr.step(b.z, b.pos, b.batch, targets, b.num_graphs)) for _ in range(4)]
+        tr.check()
+    for a, r in zip(losses["fp32"], losses["exact"]):
+        assert abs(a - r) <= 2e-5 * abs(r)
