@@ -139,6 +139,125 @@ gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda, c
   }
 }
 
+// Vectorised variant of gemm_f32_kernel for 16-byte aligned operands (every node linear and its gradients): the tiles
+// are fetched as float4 along the contiguous dimension, and the global loads of tile k + 1 are issued into registers
+// before the FMAs of tile k, so their latency hides behind the arithmetic (the scalar kernel above exposes it in every
+// 16-wide k step).  Same tiling, same per-thread accumulation order over k: results equal the scalar kernel's bit for bit.
+// Needs lda % 4 == ldb % 4 == 0, K % 4 == 0, 16-byte aligned A / B, and M % 4 == 0 (TA) / N % 4 == 0 (!TB).
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gemm_f32_vec_kernel(int M, int N, int K, const float* __restrict__ A, int64_t lda, const float* __restrict__ B,
+                    int64_t ldb, float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int act,
+                    const float* __restrict__ residual, int64_t ldr, float* __restrict__ partial, int kchunk) {
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * kchunk;
+  const int kend = min(K, kbeg + kchunk);
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  float4 ra[2], rb;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int e = tid + r * GEMM_THREADS;
+      ra[r] = zero4;
+      if (TA) {
+        const int m = (e & 31) * 4, k = e >> 5;
+        if (m0 + m < M && k0 + k < kend) ra[r] = __ldg(reinterpret_cast<const float4*>(A + (int64_t)(k0 + k) * lda + m0 + m));
+      } else {
+        const int k = (e & 3) * 4, m = e >> 2;
+        if (m0 + m < M && k0 + k < kend) ra[r] = __ldg(reinterpret_cast<const float4*>(A + (int64_t)(m0 + m) * lda + k0 + k));
+      }
+    }
+    rb = zero4;
+    if (TB) {
+      const int k = (tid & 3) * 4, n = tid >> 2;
+      if (n0 + n < N && k0 + k < kend) rb = __ldg(reinterpret_cast<const float4*>(B + (int64_t)(n0 + n) * ldb + k0 + k));
+    } else {
+      const int n = (tid & 15) * 4, k = tid >> 4;
+      if (n0 + n < N && k0 + k < kend) rb = __ldg(reinterpret_cast<const float4*>(B + (int64_t)(k0 + k) * ldb + n0 + n));
+    }
+  };
+  auto stage = [&]() {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int e = tid + r * GEMM_THREADS;
+      if (TA) {
+        const int m = (e & 31) * 4, k = e >> 5;
+        *reinterpret_cast<float4*>(&As[k][m]) = ra[r];
+      } else {
+        const int k = (e & 3) * 4, m = e >> 2;
+        As[k + 0][m] = ra[r].x; As[k + 1][m] = ra[r].y; As[k + 2][m] = ra[r].z; As[k + 3][m] = ra[r].w;
+      }
+    }
+    if (TB) {
+      const int k = (tid & 3) * 4, n = tid >> 2;
+      Bs[k + 0][n] = rb.x; Bs[k + 1][n] = rb.y; Bs[k + 2][n] = rb.z; Bs[k + 3][n] = rb.w;
+    } else {
+      const int n = (tid & 15) * 4, k = tid >> 4;
+      *reinterpret_cast<float4*>(&Bs[k][n]) = rb;
+    }
+  };
+
+  if (kbeg < kend) fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    stage();
+    __syncthreads();
+    if (k0 + BK < kend) fetch(k0 + BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const int gn0 = n0 + tx * 4;
+  if (gridDim.z > 1) {
+    float* P = partial + (int64_t)blockIdx.z * M * N;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int gm = m0 + ty * 8 + i;
+      if (gm >= M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (gn0 + j < N) P[(int64_t)gm * N + gn0 + j] = acc[i][j];
+    }
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int gm = m0 + ty * 8 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = gn0 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[gn];
+      v = apply_act(v, act);
+      if (residual) v += residual[(int64_t)gm * ldr + gn];
+      C[(int64_t)gm * ldc + gn] = v;
+    }
+  }
+}
+
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, int64_t M, int64_t N,
                                      float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int act,
                                      const float* __restrict__ residual, int64_t ldr) {
@@ -315,7 +434,20 @@ extern "C" int cmp_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_
     float* Cb = C + mb * ldc;
     const float* Rb = residual ? residual + mb * ldr : nullptr;
     float* Pb = partial;  // split-K is only planned for short problems (single band)
-    if (!transA && transB)
+    static const bool force_scalar = [] { const char* e = getenv("CMP_GEMM_SCALAR"); return e && e[0] && e[0] != '0'; }();
+    const bool vec = !force_scalar && (lda % 4 == 0) && (ldb % 4 == 0) && (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(Ab) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && (transA ? (Mb % 4 == 0 && mb % 4 == 0) : true) &&
+                     (transB ? true : N % 4 == 0);
+    if (vec && !transA && transB)
+      gemm_f32_vec_kernel<false, true><<<g, GEMM_THREADS, 0, st>>>((int)Mb, (int)N, (int)K, Ab, lda, B, ldb, Cb, ldc,
+                                                                  bias, act, Rb, ldr, Pb, p.kchunk);
+    else if (vec && !transA && !transB)
+      gemm_f32_vec_kernel<false, false><<<g, GEMM_THREADS, 0, st>>>((int)Mb, (int)N, (int)K, Ab, lda, B, ldb, Cb, ldc,
+                                                                   bias, act, Rb, ldr, Pb, p.kchunk);
+    else if (vec)
+      gemm_f32_vec_kernel<true, false><<<g, GEMM_THREADS, 0, st>>>((int)Mb, (int)N, (int)K, Ab, lda, B, ldb, Cb, ldc,
+                                                                  bias, act, Rb, ldr, Pb, p.kchunk);
+    else if (!transA && transB)
       gemm_f32_kernel<false, true><<<g, GEMM_THREADS, 0, st>>>((int)Mb, (int)N, (int)K, Ab, lda, B, ldb, Cb, ldc, bias,
                                                               act, Rb, ldr, Pb, p.kchunk);
     else if (!transA && !transB)
