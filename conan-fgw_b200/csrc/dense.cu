@@ -272,6 +272,46 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, i
   C[m * ldc + n] = v;
 }
 
+// M * N % 4 == 0, N % 4 == 0 and 16-byte aligned rows: 16 lanes per float4 of the output - lane l adds partials l, l + 16,
+// ... in order, the 16 lane sums are then added in lane order (fixed order: deterministic; the scalar kernel above walks
+// all S partials in one dependent chain per thread, 18 us for the node-linear weight gradients of cfg 2)
+__global__ void __launch_bounds__(256)
+splitk_reduce_vec4_kernel(const float4* __restrict__ partial, int S, int64_t total4, int N4, float* __restrict__ C,
+                          int64_t ldc, const float* __restrict__ bias, int act, const float* __restrict__ residual,
+                          int64_t ldr) {
+  __shared__ float4 part[16][16];
+  const int f = threadIdx.x & 15, l = threadIdx.x >> 4;
+  const int64_t t4 = (int64_t)blockIdx.x * 16 + f;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t4 < total4) {
+#pragma unroll 4
+    for (int c = l; c < S; c += 16) {
+      const float4 v = __ldg(partial + (int64_t)c * total4 + t4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  part[l][f] = s;
+  __syncthreads();
+  if (l == 0 && t4 < total4) {
+    float4 r = part[0][f];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+      const float4 v = part[k][f];
+      r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+    }
+    const int64_t m = t4 / N4;
+    const int n = (int)(t4 - m * N4) * 4;
+    float o[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (bias) o[j] += bias[n + j];
+      o[j] = apply_act(o[j], act);
+      if (residual) o[j] += residual[m * ldr + n + j];
+    }
+    *reinterpret_cast<float4*>(C + m * ldc + n) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 struct SplitPlan {
   int S;
   int kchunk;
@@ -315,16 +355,62 @@ __global__ void colsum_stage1_kernel(const float* __restrict__ X, int64_t ldx, i
   }
 }
 
-__global__ void colsum_stage2_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out) {
-  int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// N % 4 == 0, ldx % 4 == 0, 16-byte aligned X: a warp reads 512 contiguous bytes of a row, 8 rows in flight per thread
+__global__ void __launch_bounds__(32 * CS_ROWS)
+colsum_stage1_vec4_kernel(const float* __restrict__ X, int64_t ldx, int64_t M, int N4, int rows_per_chunk,
+                          float4* __restrict__ partial) {
+  __shared__ float4 red[CS_ROWS][32];
+  const int n4 = blockIdx.x * 32 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk;
+  const int64_t r1 = (r0 + rows_per_chunk > M) ? M : r0 + rows_per_chunk;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n4 < N4) {
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8 * CS_ROWS) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t rr = r + (int64_t)u * CS_ROWS;
+        v[u] = (rr < r1) ? __ldg(reinterpret_cast<const float4*>(X + rr * ldx) + n4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n4 < N4) {
+    float4 t = red[0][threadIdx.x];
+#pragma unroll
+    for (int y = 1; y < CS_ROWS; ++y) {
+      const float4 v = red[y][threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    partial[(int64_t)blockIdx.y * N4 + n4] = t;
+  }
+}
+
+// 8 lanes per column: lane l adds chunks l, l + 8, ... in order, then the lane sums in lane order
+__global__ void __launch_bounds__(256)
+colsum_stage2_lanes_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out) {
+  __shared__ float part[8][32];
+  const int f = threadIdx.x & 31, l = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + f;
   float t = 0.0f;
-  for (int c = 0; c < chunks; ++c) t += partial[(int64_t)c * N + n];
-  out[n] = t;
+  if (n < N)
+#pragma unroll 4
+    for (int c = l; c < chunks; c += 8) t += __ldg(partial + (int64_t)c * N + n);
+  part[l][f] = t;
+  __syncthreads();
+  if (l == 0 && n < N) {
+    float r = part[0][f];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r += part[k][f];
+    out[n] = r;
+  }
 }
 
 int colsum_chunks(int64_t M) {
-  int64_t c = ceil_div(M, 512);
+  int64_t c = ceil_div(M, 128);
   if (c < 1) c = 1;
   if (c > 1024) c = 1024;
   return (int)c;
@@ -460,8 +546,12 @@ extern "C" int cmp_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_
   }
   if (p.S > 1) {
     int64_t total = M * N;
-    splitk_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(partial, p.S, M, N, C, ldc, bias, act,
-                                                                        residual, ldr);
+    if (N % 4 == 0 && ldc % 4 == 0 && ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(partial)) & 15) == 0)
+      splitk_reduce_vec4_kernel<<<(unsigned)ceil_div(total / 4, 16), 256, 0, st>>>(
+          reinterpret_cast<const float4*>(partial), p.S, total / 4, (int)(N / 4), C, ldc, bias, act, residual, ldr);
+    else
+      splitk_reduce_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(partial, p.S, M, N, C, ldc, bias, act,
+                                                                          residual, ldr);
     CMP_LAUNCH_CHECK("cmp_gemm_f32(split-K reduce)");
   }
   return CMP_OK;
@@ -487,12 +577,18 @@ extern "C" int cmp_colsum_f32(const float* X, int64_t ldx, int64_t M, int64_t N,
   CMP_REQUIRE(workspace && workspace_bytes >= (size_t)chunks * N * sizeof(float), CMP_EWORKSPACE,
               "cmp_colsum_f32: workspace too small");
   int rows_per_chunk = (int)ceil_div(M, chunks);
-  dim3 grid((unsigned)ceil_div(N, 32), (unsigned)chunks);
-  colsum_stage1_kernel<<<grid, dim3(32, CS_ROWS), 0, st>>>(X, ldx, M, (int)N, rows_per_chunk,
-                                                          reinterpret_cast<float*>(workspace));
+  if (N % 4 == 0 && ldx % 4 == 0 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(workspace)) & 15) == 0) {
+    dim3 grid((unsigned)ceil_div(N / 4, 32), (unsigned)chunks);
+    colsum_stage1_vec4_kernel<<<grid, dim3(32, CS_ROWS), 0, st>>>(X, ldx, M, (int)(N / 4), rows_per_chunk,
+                                                                 reinterpret_cast<float4*>(workspace));
+  } else {
+    dim3 grid((unsigned)ceil_div(N, 32), (unsigned)chunks);
+    colsum_stage1_kernel<<<grid, dim3(32, CS_ROWS), 0, st>>>(X, ldx, M, (int)N, rows_per_chunk,
+                                                            reinterpret_cast<float*>(workspace));
+  }
   CMP_LAUNCH_CHECK("cmp_colsum_f32(stage1)");
-  colsum_stage2_kernel<<<(unsigned)ceil_div(N, 128), 128, 0, st>>>(reinterpret_cast<float*>(workspace), chunks, (int)N,
-                                                                  out);
+  colsum_stage2_lanes_kernel<<<(unsigned)ceil_div(N, 32), 256, 0, st>>>(reinterpret_cast<float*>(workspace), chunks,
+                                                                       (int)N, out);
   CMP_LAUNCH_CHECK("cmp_colsum_f32(stage2)");
   return CMP_OK;
 }

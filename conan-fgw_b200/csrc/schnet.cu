@@ -37,35 +37,55 @@ __global__ void embedding_fwd_kernel(const int64_t* __restrict__ z, int64_t N, c
   }
 }
 
+// H % 4 == 0: one float4 per thread
+__global__ void embedding_fwd_vec4_kernel(const int64_t* __restrict__ z, int64_t N, const float4* __restrict__ w, int V,
+                                          int H4, float4* __restrict__ out, int* status) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * H4) return;
+  const int64_t i = idx / H4;
+  const int c = (int)(idx - i * H4);
+  const int64_t zi = __ldg(z + i);
+  if (zi < 0 || zi >= V) {
+    if (c == 0) atomicOr(status, CMP_STATUS_BAD_ATOMIC_NUMBER);
+    out[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else {
+    out[idx] = __ldg(w + zi * H4 + c);
+  }
+}
+
 // stage 1: each CTA owns a contiguous chunk of atoms and accumulates dweight rows in shared memory
-// sequentially (fixed order); stage 2 sums the chunk partials in chunk order.
+// sequentially (fixed order); stage 2 sums the chunk partials in a fixed order.
+// The chunk's atomic numbers are staged in shared memory once, and the gradient rows of 32 atoms are loaded together
+// (the loop used to expose one global-memory latency per 8 atoms: 29 us at cfg 2); the accumulation keeps the atom order.
 __global__ void embedding_bwd_stage1(const int64_t* __restrict__ z, int64_t N, const float* __restrict__ dout, int V,
                                      int H, int chunk, float* __restrict__ partial) {
-  extern __shared__ float acc[];  // [V][H]
-  for (int t = threadIdx.x; t < V * H; t += blockDim.x) acc[t] = 0.0f;
+  extern __shared__ __align__(16) float acc[];  // [V][H] | int zs[chunk]
+  int* zs = reinterpret_cast<int*>(acc + (size_t)V * H);
+  const int total = V * H;
+  const int64_t i0 = (int64_t)blockIdx.x * chunk;
+  const int cnt = (int)((i0 + chunk > N ? N : i0 + chunk) - i0);
+  for (int t = threadIdx.x; t < total; t += blockDim.x) acc[t] = 0.0f;
+  for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+    const int64_t zz = __ldg(z + i0 + t);
+    zs[t] = (zz >= 0 && zz < V) ? (int)zz : -1;
+  }
   __syncthreads();
-  int64_t i0 = (int64_t)blockIdx.x * chunk;
-  int64_t i1 = i0 + chunk;
-  if (i1 > N) i1 = N;
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
-    // global loads of 8 atoms are issued together; the shared-memory accumulation keeps the atom order
-    for (int64_t i = i0; i < i1; i += 8) {
-      int64_t zz[8];
-      float dd[8];
+    const float* src = dout + i0 * H + c;
+    for (int i = 0; i < cnt; i += 32) {
+      float dd[32];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const bool ok = i + u < i1;
-        zz[u] = ok ? z[i + u] : -1;
-        dd[u] = ok ? dout[(i + u) * H + c] : 0.0f;
+      for (int u = 0; u < 32; ++u) dd[u] = (i + u < cnt) ? __ldg(src + (int64_t)(i + u) * H) : 0.0f;
+#pragma unroll
+      for (int u = 0; u < 32; ++u) {
+        const int zq = (i + u < cnt) ? zs[i + u] : -1;
+        if (zq >= 0) acc[zq * H + c] += dd[u];
       }
-#pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (zz[u] >= 0 && zz[u] < V) acc[zz[u] * H + c] += dd[u];
     }
   }
   __syncthreads();
-  float* P = partial + (int64_t)blockIdx.x * V * H;
-  for (int t = threadIdx.x; t < V * H; t += blockDim.x) P[t] = acc[t];
+  float* P = partial + (int64_t)blockIdx.x * total;
+  for (int t = threadIdx.x; t < total; t += blockDim.x) P[t] = acc[t];
 }
 
 __global__ void embedding_bwd_stage2(const float* __restrict__ partial, int chunks, int V, int H, int padding_idx,
@@ -76,6 +96,36 @@ __global__ void embedding_bwd_stage2(const float* __restrict__ partial, int chun
   for (int c = 0; c < chunks; ++c) s += partial[(int64_t)c * V * H + t];
   if (t / H == padding_idx) s = 0.0f;
   dweight[t] = s;
+}
+
+// V * H % 4 == 0: a CTA sums 64 consecutive values (16 float4) with 16 chunk lanes per value - lane l adds chunks l, l + 16,
+// ... in order, then the 16 lane sums are added in lane order (a fixed order: deterministic)
+__global__ void __launch_bounds__(256)
+embedding_bwd_stage2_vec4(const float4* __restrict__ partial, int chunks, int total4, int H, int padding_idx,
+                          float4* __restrict__ dweight) {
+  __shared__ float4 part[16][16];
+  const int f = threadIdx.x & 15, l = threadIdx.x >> 4;
+  const int t4 = blockIdx.x * 16 + f;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t4 < total4) {
+#pragma unroll 4
+    for (int c = l; c < chunks; c += 16) {
+      const float4 v = __ldg(partial + (int64_t)c * total4 + t4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  part[l][f] = s;
+  __syncthreads();
+  if (l == 0 && t4 < total4) {
+    float4 r = part[0][f];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+      const float4 v = part[k][f];
+      r.x += v.x; r.y += v.y; r.z += v.z; r.w += v.w;
+    }
+    if ((t4 * 4) / H == padding_idx) r = make_float4(0.f, 0.f, 0.f, 0.f);   // H % 4 == 0: a float4 never straddles rows
+    dweight[t4] = r;
+  }
 }
 
 int embedding_chunk(int64_t N) {
@@ -208,7 +258,11 @@ extern "C" int cmp_embedding_fwd(const int64_t* z, int64_t N, const float* weigh
   CMP_REQUIRE(N >= 0 && V >= 1 && H >= 1, CMP_EINVAL, "cmp_embedding_fwd: bad size");
   if (N == 0) return CMP_OK;
   CMP_REQUIRE(z && weight && out && status, CMP_EINVAL, "cmp_embedding_fwd: null pointer");
-  embedding_fwd_kernel<<<grid1d(N * H), 256, 0, as_stream(stream)>>>(z, N, weight, V, H, out, status);
+  if (H % 4 == 0 && ((reinterpret_cast<uintptr_t>(weight) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+    embedding_fwd_vec4_kernel<<<(unsigned)ceil_div(N * (H / 4), 256), 256, 0, as_stream(stream)>>>(
+        z, N, reinterpret_cast<const float4*>(weight), V, H / 4, reinterpret_cast<float4*>(out), status);
+  else
+    embedding_fwd_kernel<<<grid1d(N * H), 256, 0, as_stream(stream)>>>(z, N, weight, V, H, out, status);
   CMP_LAUNCH_CHECK("cmp_embedding_fwd");
   return CMP_OK;
 }
@@ -230,9 +284,9 @@ extern "C" int cmp_embedding_bwd(const int64_t* z, int64_t N, const float* dout,
     return CMP_OK;
   }
   CMP_REQUIRE(z && dout, CMP_EINVAL, "cmp_embedding_bwd: null pointer");
-  size_t smem = (size_t)V * H * sizeof(float);
-  CMP_REQUIRE(smem <= 227 * 1024, CMP_EUNSUPPORTED, "cmp_embedding_bwd: V*H*4 = %zu bytes exceeds shared memory", smem);
   int chunk = embedding_chunk(N);
+  size_t smem = (size_t)V * H * sizeof(float) + (size_t)chunk * sizeof(int);
+  CMP_REQUIRE(smem <= 227 * 1024, CMP_EUNSUPPORTED, "cmp_embedding_bwd: V*H*4 = %zu bytes exceeds shared memory", smem);
   int chunks = (int)ceil_div(N, chunk);
   CMP_REQUIRE(workspace && workspace_bytes >= (size_t)chunks * V * H * sizeof(float), CMP_EWORKSPACE,
               "cmp_embedding_bwd: workspace too small");
@@ -245,8 +299,12 @@ extern "C" int cmp_embedding_bwd(const int64_t* z, int64_t N, const float* dout,
   int threads = H < 256 ? ((H + 31) / 32) * 32 : 256;
   embedding_bwd_stage1<<<chunks, threads, smem, st>>>(z, N, dout, V, H, chunk, reinterpret_cast<float*>(workspace));
   CMP_LAUNCH_CHECK("cmp_embedding_bwd(stage1)");
-  embedding_bwd_stage2<<<(unsigned)ceil_div((int64_t)V * H, 256), 256, 0, st>>>(reinterpret_cast<float*>(workspace),
-                                                                               chunks, V, H, padding_idx, dweight);
+  if (H % 4 == 0 && (reinterpret_cast<uintptr_t>(dweight) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0)
+    embedding_bwd_stage2_vec4<<<(unsigned)ceil_div((int64_t)V * H / 4, 16), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(workspace), chunks, V * H / 4, H, padding_idx, reinterpret_cast<float4*>(dweight));
+  else
+    embedding_bwd_stage2<<<(unsigned)ceil_div((int64_t)V * H, 256), 256, 0, st>>>(reinterpret_cast<float*>(workspace),
+                                                                                 chunks, V, H, padding_idx, dweight);
   CMP_LAUNCH_CHECK("cmp_embedding_bwd(stage2)");
   return CMP_OK;
 }
