@@ -172,7 +172,7 @@ def _prepack(modules, dense_only=False, x3_hint=True):
             if isinstance(m, InteractionBlock) and m.conv.precision == "fp32" and m.mlp[0].weight.is_cuda and x3_hint:
                 # fp32-grade fused kernels: hi + lo images of the dense forward and of the weight-gradient kernel
                 W1, b1, W2, b2 = m.mlp[0].weight, m.mlp[0].bias, m.mlp[2].weight, m.mlp[2].bias
-                if fused_supported(W1.shape[0], W1.shape[1]) and m.conv._standard_mlp():
+                if fused_native(W1.shape[0], W1.shape[1]) and m.conv._standard_mlp():
                     skip.update((W1.data_ptr(), W2.data_ptr()))
                     if W1.data_ptr() not in cache:
                         dev = W1.device
@@ -184,7 +184,7 @@ def _prepack(modules, dense_only=False, x3_hint=True):
                         filt_x3.append(tuple(_f32c(t.detach()) for t in (W1, b1, W2, b2)) + (px, pbx))
             if isinstance(m, InteractionBlock) and m.conv.precision == "bf16" and m.mlp[0].weight.is_cuda:
                 W1, b1, W2, b2 = m.mlp[0].weight, m.mlp[0].bias, m.mlp[2].weight, m.mlp[2].bias
-                if fused_supported(W1.shape[0], W1.shape[1]):
+                if fused_native(W1.shape[0], W1.shape[1]):
                     skip.update((W1.data_ptr(), W2.data_ptr()))
                     if W1.data_ptr() not in cache:
                         dev = W1.device
@@ -1013,13 +1013,50 @@ def _fused_weight_grads(g, xprime, W1, b1, W2, graph, offset, coeff, cutoff, x3=
     return dW1, db1, dW2, db2
 
 
+FB = 128     # filter channels of the fused kernels (one TMEM lane / one epilogue thread per channel)
+
+
 def cfconv_fused(xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff, x3=False):
-    return _CFConvFusedFn.apply(xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff, x3)
+    """Fused geometric CFConv.  ``num_filters`` = 128 runs one kernel per direction; 256 / 384 / 512 (ConAN's classification
+    models use F = 256, ``conan_fgw/src/model/common.py:513-522``) are composed from the same kernels, because the
+    aggregate is linear in the filter and the filter's second Linear splits over blocks of 128 hidden channels:
+
+        agg[:, o] = sum_k  CFConv(x'[:, o];  W1[k], b1[k],  W2[o, k],  b2[o] if k == 0 else 0)
+
+    (o, k = 128-channel blocks of the output / hidden filter channels).  (F / 128)^2 launches per direction instead of
+    one - the same tensor-pipe work as a native F-wide kernel, the Gaussians and the first Linear evaluated F / 128 times
+    too often - but still no ``[E, *]`` tensor and no host sync; gradients follow through autograd over the slices."""
+    F = W1.shape[0]
+    if F == FB:
+        return _CFConvFusedFn.apply(xprime, W1, b1, W2, b2, graph, offset, coeff, cutoff, x3)
+    if F % FB != 0:
+        raise _lib.ConanMPError(f"fused CFConv: num_filters must be a multiple of {FB} (got {F})")
+    nb = F // FB
+    zero_b2 = torch.zeros(FB, dtype=torch.float32, device=xprime.device)
+    w1k = [(W1[k * FB:(k + 1) * FB], b1[k * FB:(k + 1) * FB]) for k in range(nb)]      # row slices: contiguous views
+    outs = []
+    for o in range(nb):
+        xo = xprime[:, o * FB:(o + 1) * FB].contiguous()
+        acc = None
+        for k in range(nb):
+            W2ok = W2[o * FB:(o + 1) * FB, k * FB:(k + 1) * FB].contiguous()
+            b2o = b2[o * FB:(o + 1) * FB] if k == 0 else zero_b2
+            term = _CFConvFusedFn.apply(xo, w1k[k][0], w1k[k][1], W2ok, b2o, graph, offset, coeff, cutoff, x3)
+            acc = term if acc is None else acc + term
+        outs.append(acc)
+    return torch.cat(outs, dim=1)
+
+
+def fused_native(num_filters, num_gaussians) -> bool:
+    """Shapes the fused kernels serve in ONE launch (and the grouped weight packs prepare images for)."""
+    return bool(_lib.lib().cmp_cfconv_tc_supported(int(num_filters), int(num_gaussians))) and \
+        bool(_lib.lib().cmp_device_is_sm100())
 
 
 def fused_supported(num_filters, num_gaussians) -> bool:
-    return bool(_lib.lib().cmp_cfconv_tc_supported(int(num_filters), int(num_gaussians))) and \
-        bool(_lib.lib().cmp_device_is_sm100())
+    """Shapes ``cfconv_fused`` serves: the native one, or a multiple of it composed from 128-channel blocks."""
+    F = int(num_filters)
+    return F % FB == 0 and FB <= F <= 4 * FB and fused_native(FB, num_gaussians)
 
 
 class _SegmentSumFn(Function):

@@ -490,3 +490,66 @@ def test_chained_trunk_equals_per_layer_launches():
         tol = 2e-4 if ".mlp." in k else 5e-5
         assert rel_err(res[True][1][k], g) < tol, k
     assert res[True][2] < res[False][2]
+
+
+# ---- ConAN's classification shape (common.py:513-522: H = 512, F = 256, Ng = 10, T = 3) through the fused kernels -----------
+# num_filters = 256 is composed from 128-channel blocks of the same kernels (ops.cfconv_fused); Ng = 10 is one K step.
+@pytest.mark.parametrize("F,Ng", [(256, 10), (256, 50), (384, 10), (128, 10)])
+def test_wide_filter_layer_matches_exact_message_path(F, Ng):
+    _need_sm100()
+    torch.manual_seed(F + Ng)
+    b = syn.make_batch(3, 2, 40, seed=F).to(DEV)
+    nl = cmp.build_neighbor_list(b.pos, b.batch, 10.0, max_atoms=40)
+    blk = cmp.InteractionBlock(64, Ng, F, 10.0).to(DEV)
+    with torch.no_grad():
+        blk.mlp[0].bias.add_(0.1 * torch.randn(F, device=DEV))
+        blk.mlp[2].bias.add_(0.1 * torch.randn(F, device=DEV))
+    gs = cmp.GaussianSmearing(0.0, 10.0, Ng).to(DEV)
+    params = [blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight, blk.mlp[2].bias]
+    xp = torch.randn(b.z.numel(), F, device=DEV)
+    g = torch.randn(b.z.numel(), F, device=DEV)
+    assert ops.fused_supported(F, Ng)
+
+    xq = xp.clone().requires_grad_(True)
+    want = ops.cfconv_message(xq, blk.conv.filter(gs(nl.edge_weight())), nl, 10.0)
+    want_g = torch.autograd.grad(want, [xq] + params, g)
+    for x3, tol, tol_g in ((False, TOL_BF16, 2e-2), (True, 1e-5, 1e-5)):
+        xr = xp.clone().requires_grad_(True)
+        got = ops.cfconv_fused(xr, *params, nl, gs.offset, gs.coeff, 10.0, x3=x3)
+        got_g = torch.autograd.grad(got, [xr] + params, g)
+        nl.check()
+        assert got.shape == want.shape
+        assert rel_err(got, want) < tol, x3
+        for name, a, r in zip(("dx", "dW1", "db1", "dW2", "db2"), got_g, want_g):
+            assert a.shape == r.shape
+            assert rel_err(a, r) < tol_g, (x3, name)
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_classification_shape_runs_the_fused_kernels(prec):
+    """tests/test_gpu_schnet.py::test_classification_shape in the fused modes: no [E, *] tensor, no exact message kernel."""
+    _need_sm100()
+    o, c = make(4, hidden_channels=512, num_filters=256, num_gaussians=10, num_interactions=3)
+    c.set_precision(prec)
+    c.max_atoms_hint = 20
+    b = syn.make_batch(2, 2, 20, seed=5)
+    lib = cmp._lib
+    lib.timer = lib.KernelTimer(["cmp_cfconv_dense_fwd", "cmp_cfconv_dense_x3_fwd", "cmp_cfconv_message_fwd"])
+    try:
+        out_o = o(b.z, b.pos, b.batch)
+        out_c = c(b.z.to(DEV), b.pos.to(DEV), b.batch.to(DEV))
+        out_o.pow(2).mean().backward()
+        out_c.pow(2).mean().backward()
+        c.check_status()
+        torch.cuda.synchronize()
+        seen = {k: v[0] for k, v in lib.timer.summary().items()}
+    finally:
+        lib.timer = None
+    fused = "cmp_cfconv_dense_fwd" if prec == "bf16" else "cmp_cfconv_dense_x3_fwd"
+    assert seen.get(fused, 0) == 3 * 4 * 2          # 3 blocks x (256 / 128)^2 launches x (forward + d x')
+    assert seen.get("cmp_cfconv_message_fwd", 0) == 0
+    tol, tol_g = (TOL_BF16, 2e-2) if prec == "bf16" else (1e-5, 2e-5)
+    assert rel_err(out_c, out_o) < tol
+    for (k, po), (_, pc) in zip(o.named_parameters(), c.named_parameters()):
+        if po.grad is not None:
+            assert rel_err(pc.grad, po.grad) < tol_g, k
