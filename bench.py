@@ -45,6 +45,7 @@ NCU_DRAM_BYTES_PER_LAUNCH = {"cmp_cfconv_dense_fwd": 9481984, "cmp_cfconv_dense_
                              "cmp_cfconv_fused_bwd_weights_pairs": 13398784 + 764672, "cmp_cfconv_fused_fwd": 15000000}
 FWD_KERNELS = ("cmp_cfconv_dense_fwd", "cmp_cfconv_dense_x3_fwd", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd")
 DTYPE_X3 = "f32-grade: f16 / bf16 hi + lo filter-MLP operands, three tcgen05 passes, f32 accumulation and epilogues; f32 elsewhere (node linears: exact SIMT, or split-bf16 tcgen05 with CMP_FP32_NODE_TC=1)"
+CLS_MODEL_CFG = dict(hidden_channels=512, num_filters=256, num_interactions=3, num_gaussians=10, cutoff=10.0)
 TOL_FP32 = ("embeddings 1e-5 (measured 3e-6), gradients 2e-5 (measured 1.3e-5) vs the fp64 oracle on 6-block trunks: "
             "fp32-grade fused CFConv kernels, exact node linears (profiles/r02_x3_errors.md)")
 TOL_FP32_TC = ("embeddings 2.5e-5 (measured 1.9e-5), gradients 6e-5 (measured 4.1e-5): fp32-grade fused CFConv kernels, "
@@ -294,7 +295,8 @@ def visnet_secondary(cmp, dev, threads):
 # GPU path
 # -----------------------------------------------------------------------------------------------
 
-def measure_schnet_workload(workload, molecules, cutoff, steps, dev, world, rank, flush, pk, label, scaling=None):
+def measure_schnet_workload(workload, molecules, cutoff, steps, dev, world, rank, flush, pk, label, scaling=None,
+                            model_cfg=None, precision="bf16"):
     """Another SchNet workload of BASELINE.json measured like the headline: `molecules` molecules on THIS rank, training
     step replayed from a CUDA graph, CUDA events, max over ranks; then an eager pass with events around every launch
     for the forward CFConv kernel's share of the tensor roofline.  Returns the entry on rank 0, None elsewhere."""
@@ -306,15 +308,16 @@ def measure_schnet_workload(workload, molecules, cutoff, steps, dev, world, rank
 
     c = cmp.synthetic.CONFIGS[workload]
     K, n = c["num_conformers"], c["atoms"]
-    cfg = dict(MODEL_CFG, cutoff=cutoff)
+    cfg = dict(model_cfg or MODEL_CFG, cutoff=cutoff)
     b = cmp.synthetic.make_batch(molecules, K, n, seed=4321 + rank).to(dev)
     G = b.num_graphs
     tg = torch.Generator().manual_seed(17 + rank)
     targets = torch.randn(molecules, 1, generator=tg).to(dev)
     torch.manual_seed(0)
-    model = cmp.SchNetNoSum(None, **cfg).to(dev).set_precision("bf16")
+    model = cmp.SchNetNoSum(None, **cfg).to(dev).set_precision(precision)
     model.max_atoms_hint = n
     trainer = RegressionStep(model, cfg["hidden_channels"] // 2, K, lr=1e-3)
+    graphed = precision != "exact"          # the exact kernels sync once per step (edge count): not capturable
 
     def step():
         return trainer.step(b.z, b.pos, b.batch, targets, G)
@@ -325,10 +328,11 @@ def measure_schnet_workload(workload, molecules, cutoff, steps, dev, world, rank
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(3):
+    for _ in range(3 if graphed else 1):
         step()
-    trainer.capture(b.z, b.pos, b.batch, targets, G)
-    step()
+    if graphed:
+        trainer.capture(b.z, b.pos, b.batch, targets, G)
+        step()
     sync_all()
     evs = []
     for _ in range(steps):
@@ -344,21 +348,23 @@ def measure_schnet_workload(workload, molecules, cutoff, steps, dev, world, rank
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     # forward CFConv kernel, timed per launch in an eager pass of the same step
-    graph, trainer._graph = trainer._graph, None
+    graph, trainer._graph = getattr(trainer, "_graph", None), None
     _lib.timer = _lib.KernelTimer(list(FWD_KERNELS))
-    ksteps = 3
+    ksteps = 3 if graphed else 1
     for _ in range(ksteps):
         step()
     torch.cuda.synchronize()
     summ = _lib.timer.summary()
     _lib.timer = None
     trainer._graph = graph
+    trainer.check()
     E = int(model.interaction_graph.neighbor_list(b.pos, b.batch, G).E)
     sync_all()
     del trainer, model
     if rank != 0:
         return None
-    per_edge = 2.0 * (cfg["num_gaussians"] * cfg["num_filters"] + cfg["num_filters"] ** 2)
+    fb = min(cfg["num_filters"], 128)       # wider filters run as (F / 128)^2 launches of the 128-channel kernels
+    per_edge = 2.0 * (cfg["num_gaussians"] * fb + fb * fb)
     top = max((k for k in FWD_KERNELS if k in summ), key=lambda k: summ[k][1], default=None)
     fwd = None
     if top is not None and summ[top][1] > 0:
@@ -369,6 +375,10 @@ def measure_schnet_workload(workload, molecules, cutoff, steps, dev, world, rank
     entry = {"workload": label, "conformers_per_gpu": G, "atoms_per_conformer": n, "edges_per_gpu": E, "cutoff": cutoff,
              "n_gpus": world, "value": world * G * steps / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / steps,
              "steps": steps, "forward_cfconv_roofline": fwd}
+    if model_cfg is not None or precision != "bf16":
+        entry["model"] = {k: cfg[k] for k in ("hidden_channels", "num_filters", "num_gaussians", "num_interactions")}
+        entry["precision"] = precision
+        entry["cuda_graph"] = graphed
     if scaling:
         entry["scaling"] = scaling
     return entry
@@ -588,14 +598,23 @@ def run_ours(args):
             c5 = cmp.synthetic.CONFIGS["cfg5_cov2_stress"]
             jobs = [("cfg4_bace_cls", c4["num_molecules"], 10.0, "cfg4_bace_cls (full batch, SchNet defaults)", None),
                     ("cfg5_cov2_stress", c5["num_molecules"] // 8, 10.0, "cfg5_cov2_stress (1/8 shard, cutoff 10 A)", None),
-                    ("cfg5_cov2_stress", c5["num_molecules"] // 8, 5.0, "cfg5_cov2_stress (1/8 shard, cutoff 5 A)", None)]
+                    ("cfg5_cov2_stress", c5["num_molecules"] // 8, 5.0, "cfg5_cov2_stress (1/8 shard, cutoff 5 A)", None),
+                    # ConAN's own classification model (conan_fgw/src/model/common.py:513-522) on the cfg 4 batch: the
+                    # F = 256 filter runs as 2 x 2 launches of the 128-channel fused kernels; exact mode beside it
+                    ("cfg4_bace_cls", c4["num_molecules"], 10.0,
+                     "cfg4_bace_cls, ConAN classification model (H=512, F=256, Ng=10, T=3), fused f16 mode", None,
+                     CLS_MODEL_CFG, "bf16"),
+                    ("cfg4_bace_cls", c4["num_molecules"], 10.0,
+                     "cfg4_bace_cls, ConAN classification model (H=512, F=256, Ng=10, T=3), exact mode", None,
+                     CLS_MODEL_CFG, "exact")]
         else:
             c4 = cmp.synthetic.CONFIGS["cfg4_bace_cls"]
             jobs = [("cfg4_bace_cls", c4["num_molecules"] // world, 10.0,
                      f"cfg4_bace_cls strong scaling ({c4['num_molecules']} molecules over {world} GPUs)", "strong")]
-        for wl, mol, cut, label, sc in jobs:
+        for wl, mol, cut, label, sc, *more in jobs:
             try:
-                ent = measure_schnet_workload(wl, mol, cut, xs, dev, world, rank, flush, pk0, label, sc)
+                ent = measure_schnet_workload(wl, mol, cut, xs if (not more or more[1] != "exact") else 2, dev, world, rank,
+                                              flush, pk0, label, sc, *more)
             except Exception as exc:      # a sweep entry must never take the headline line down with it
                 ent = {"workload": label, "error": repr(exc)}
             if rank == 0:
