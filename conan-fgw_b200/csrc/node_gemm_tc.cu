@@ -99,6 +99,7 @@ __device__ __forceinline__ void convert_tile(const float* __restrict__ X, int64_
                                                       tc::pack_bf16x2(l[4], l[5]), tc::pack_bf16x2(l[6], l[7]));
    }
   }
+  if (warp >= total) after_loads();   // narrow tiles leave some warps without work: they still owe the one call
   if (ones_chunk >= 0) {
     // two extra chunks (16 channels): chunk ones_chunk = {1,0,...}, ones_chunk + 1 = 0
     const int t = warp * 32 + lane;
@@ -538,6 +539,198 @@ __global__ void __launch_bounds__(NTC, 1) node_chain_kernel(const __grid_constan
   if (warp == 0) tc::tmem_dealloc(tmem_base, 64);
 }
 
+// Two-stream variant (CMP_CHAIN_TWO_STREAMS=1; NOT the default): the 16 compute warps form two groups of 8, each with its own MMA-issuing warp, its
+// own operand images (32 atoms) and 32 TMEM columns.  Group g walks tiles 2 * blockIdx.x + g, + 2 * gridDim.x, ... of 32
+// atoms; the groups share the weight images and never synchronise with each other, so the global loads / conversions /
+// epilogues of one stream overlap the MMA round trips of the other.  Same arithmetic per element: results are
+// bit-identical to the one-stream kernel.  Measured at cfg 2: 27.5 us against 26.7 us per launch under ncu, i.e. NO gain
+// (profiles/r02_node_chain_kernels.md): the kernel is not bound by the serial phases of a tile but by its instruction
+// count (8.7 M warp instructions per launch = ~120 per element: the channel-per-thread epilogue issues one 4-byte access
+// per atom for residual / saved activation / output, plus the hi + lo conversions) at 40 % issue utilisation with
+// `long_scoreboard` as the dominant stall.  Kept for cross-checking; the next step is an epilogue that moves 16-byte rows.
+constexpr int TMC = 32;            // atoms per tile and stream
+constexpr int CWG = 8;             // compute warps per stream: 4 TMEM lane quarters x 2 halves of 16 atoms
+constexpr int NTC2 = 2 * CWG * 32 + 64;
+__global__ void __launch_bounds__(NTC2, 1) node_chain2_kernel(const __grid_constant__ ChainParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bars[MAXS + 4];   // wbar[s] | xready[g] | dready[g]
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t w_off[MAXS + 1];
+  w_off[0] = 0;
+#pragma unroll
+  for (int s = 0; s < MAXS; ++s) w_off[s + 1] = w_off[s] + (s < p.nstages ? 2u * 128u * (uint32_t)p.st[s].K * 2u : 0u);
+
+  if (tid == 0) {
+    for (int s = 0; s < MAXS; ++s) tc::mbar_init(&bars[s], 1);
+    for (int g = 0; g < 2; ++g) {
+      tc::mbar_init(&bars[MAXS + g], CWG * 32);
+      tc::mbar_init(&bars[MAXS + 2 + g], 1);
+    }
+    tc::mbar_fence_init();
+  }
+  __syncwarp();
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 64);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int64_t ntiles = (p.M + TMC - 1) / TMC;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp >= 2 * CWG) {
+    const int g = warp - 2 * CWG;
+    if (lane == 0) {
+      if (g == 0) {
+        for (int s = 0; s < p.nstages; ++s) {
+          const uint32_t bytes = w_off[s + 1] - w_off[s];
+          tc::mbar_arrive_expect_tx(&bars[s], bytes);
+          tc::bulk_g2s(smem + w_off[s], p.st[s].w_img, bytes, &bars[s]);
+        }
+      }
+      uint8_t* sXh = smem + w_off[MAXS] + (uint32_t)g * (2u * TMC * MAXC * 2u);
+      const uint32_t aXh = tc::smem_u32(sXh), aXl = aXh + TMC * MAXC * 2;
+      const uint32_t tD = tmem_base + (uint32_t)g * TMC;
+      uint32_t n = 0;   // operand images consumed so far
+      bool waited = false;
+      for (int64_t ti = 2 * (int64_t)blockIdx.x + g; ti < ntiles; ti += 2 * (int64_t)gridDim.x) {
+        for (int s = 0; s < p.nstages; ++s, ++n) {
+          const int K = p.st[s].K;
+          const uint32_t sbo = (uint32_t)(K >> 3) * 128;
+          const uint32_t aWh = tc::smem_u32(smem + w_off[s]), aWl = aWh + 128u * (uint32_t)K * 2u;
+          if (!waited) tc::mbar_wait(&bars[s], 0);
+          tc::mbar_wait(&bars[MAXS + g], n & 1);
+          tc::tc_fence_after();
+          const uint32_t idesc = tc::umma_idesc_f16(128, TMC, 1, 0, s == 0 ? 0 : 1);
+          const int ks_n = K >> 4;
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a = (pass == 2) ? aWl : aWh;
+            const uint32_t b = (pass == 1) ? aXl : aXh;
+            for (int ks = 0; ks < ks_n; ++ks)
+              tc::umma_f16(tD, tc::umma_smem_desc(a + ks * 256, 128, sbo), tc::umma_smem_desc(b + ks * 256, 128, sbo), idesc,
+                           (pass | ks) != 0);
+          }
+          tc::umma_commit(&bars[MAXS + 2 + g]);
+        }
+        waited = true;
+      }
+      // the thread that issued the weight copies must not leave before they have landed
+      if (g == 0 && !waited)
+        for (int s = 0; s < p.nstages; ++s) tc::mbar_wait(&bars[s], 0);
+    }
+    __syncwarp();
+  } else {
+    const int g = warp / CWG, wg = warp % CWG;
+    const int wq = wg & 3, h = wg >> 2;
+    const int chan = wq * 32 + lane;
+    uint8_t* sXh = smem + w_off[MAXS] + (uint32_t)g * (2u * TMC * MAXC * 2u);
+    uint8_t* sXl = sXh + TMC * MAXC * 2;
+    const uint32_t tD = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)g * TMC;
+    uint32_t n = 0;
+    for (int64_t ti = 2 * (int64_t)blockIdx.x + g; ti < ntiles; ti += 2 * (int64_t)gridDim.x) {
+      const int64_t m0 = ti * TMC;
+      // as in the one-stream kernel: the previous tile's last read-out of TMEM (after its last MMAs) precedes this barrier
+      auto images_free = [&]() {
+        if (n > 0) tc::named_bar_sync(1 + g, CWG * 32);
+      };
+      convert_tile<TMC, CWG>(p.X, p.ldx, nullptr, 0, m0, p.M, p.st[0].K, (uint32_t)(p.st[0].K >> 3) * 128, sXh, sXl, -1, wg, lane,
+                             images_free);
+      tc::fence_proxy_async();
+      tc::mbar_arrive(&bars[MAXS + g]);
+      for (int s = 0; s < p.nstages; ++s, ++n) {
+        const int Nout = p.st[s].Nout, act = p.st[s].act;
+        const bool live = chan < Nout;
+        const float bias = (p.st[s].bias && live) ? __ldg(p.st[s].bias + chan) : 0.0f;
+        const bool feeds = s + 1 < p.nstages;
+        const uint32_t sbo_n = (uint32_t)(Nout >> 3) * 128;   // K of the next stage = Nout of this one
+        const int64_t ldr = p.st[s].ldr, lds = p.st[s].lds, ldo = p.st[s].ldo;
+        const float* res_p = p.st[s].residual ? p.st[s].residual + m0 * ldr + chan : nullptr;
+        const float* ys_p = p.st[s].scale_y ? p.st[s].scale_y + m0 * lds + chan : nullptr;
+        float* out_p = p.st[s].out ? p.st[s].out + m0 * ldo + chan : nullptr;
+        const int rows = (int)min((int64_t)TMC, p.M - m0);    // atoms of this tile that exist
+        const int c0 = h * 16;             // this warp's 16 atoms of the tile
+        const bool full = live && rows == TMC;
+        const int ir = (int)ldr, is = (int)lds, io = (int)ldo;
+        float v[16], r[16], y[16];
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            r[j] = res_p ? __ldg(res_p + (c0 + j) * ir) : 0.0f;
+            y[j] = ys_p ? __ldg(ys_p + (c0 + j) * is) : 1e30f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const bool ok = live && (c0 + j) < rows;
+            r[j] = (res_p && ok) ? __ldg(res_p + (c0 + j) * ir) : 0.0f;
+            y[j] = (ys_p && ok) ? __ldg(ys_p + (c0 + j) * is) : 1e30f;
+          }
+        }
+        tc::mbar_wait(&bars[MAXS + 2 + g], n & 1);
+        tc::tc_fence_after();
+        tc::tmem_ld16(tD + c0, v);
+        tc::tmem_wait_ld();
+        if (act == CMP_ACT_SSP) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = v[j] + bias;
+            const float t = ex2_approx(-1.4426950408889634f * fabsf(x));
+            v[j] = fmaf(tc::fast_lg2(1.0f + t) - 1.0f, kLn2, fmaxf(x, 0.0f));
+          }
+        } else if (act == CMP_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = silu(v[j] + bias);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += bias;
+        }
+        if (ys_p) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= 1.0f - 0.5f * ex2_approx(-1.4426950408889634f * y[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += r[j];
+        if (out_p && live) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) out_p[(c0 + j) * io] = v[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c0 + j < rows) out_p[(c0 + j) * io] = v[j];
+          }
+        }
+        if (feeds && live) {
+#pragma unroll
+          for (int g8 = 0; g8 < 2; ++g8) {
+            float hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float x = (full || c0 + g8 * 8 + j < rows) ? v[g8 * 8 + j] : 0.0f;
+              hi[j] = __bfloat162float(__float2bfloat16_rn(x));
+              lo[j] = x - hi[j];
+            }
+            const uint32_t off = (uint32_t)chan * 16 + (uint32_t)((c0 >> 3) + g8) * sbo_n;
+            *reinterpret_cast<uint4*>(sXh + off) = make_uint4(tc::pack_bf16x2(hi[0], hi[1]), tc::pack_bf16x2(hi[2], hi[3]),
+                                                              tc::pack_bf16x2(hi[4], hi[5]), tc::pack_bf16x2(hi[6], hi[7]));
+            *reinterpret_cast<uint4*>(sXl + off) = make_uint4(tc::pack_bf16x2(lo[0], lo[1]), tc::pack_bf16x2(lo[2], lo[3]),
+                                                              tc::pack_bf16x2(lo[4], lo[5]), tc::pack_bf16x2(lo[6], lo[7]));
+          }
+        }
+        tc::tc_fence_before();
+        if (feeds) {
+          tc::fence_proxy_async();
+          tc::mbar_arrive(&bars[MAXS + g]);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem_base, 64);
+}
+
 // ---- grouped launch: many weight-gradient problems share one grid (the node linears of a whole backward pass) ----
 constexpr int MAX_GROUP = 32;
 constexpr int PART_STRIDE = 128 * (MAXC + 16);      // floats per CTA in the grouped workspace
@@ -740,21 +933,32 @@ extern "C" int cmp_node_chain_fwd(const float* X, int64_t ldx, int64_t M, const 
   }
   CMP_REQUIRE(p.st[nstages - 1].out != nullptr, CMP_EINVAL, "cmp_node_chain_fwd: the last stage needs an output");
   for (int s = nstages; s < MAXS; ++s) p.st[s] = ChainStage{};
-  const size_t smem = w_bytes + (size_t)2 * TMF * MAXC * 2;
+  const size_t smem = w_bytes + (size_t)2 * TMF * MAXC * 2;       // = 2 streams x 2 images x TMC atoms for the two-stream kernel
+  static_assert(2 * TMC == TMF, "both chain kernels use the same operand-image bytes");
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(node_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             MAXS * 2 * 128 * MAXC * 2 + 2 * TMF * MAXC * 2) != cudaSuccess) {
+    const int max_smem = MAXS * 2 * 128 * MAXC * 2 + 2 * TMF * MAXC * 2;
+    if (cudaFuncSetAttribute(node_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(node_chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
       (void)cudaGetLastError();
       set_error("cmp_node_chain_fwd: cannot opt in to shared memory");
       return CMP_ECUDA;
     }
     attr_set = true;
   }
-  const int64_t ntiles = ceil_div(M, TMF);
-  const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
-  CMP_REQUIRE(launch_pdl(node_chain_kernel, dim3(grid), dim3(NTC), smem, as_stream(stream), p) == cudaSuccess, CMP_ECUDA,
-              "cmp_node_chain_fwd: launch failed");
+  // CMP_CHAIN_TWO_STREAMS=1: the two-stream kernel (two independent streams of 32-atom tiles per CTA), same results
+  static const bool two_streams = [] { const char* e = getenv("CMP_CHAIN_TWO_STREAMS"); return e && e[0] && e[0] != '0'; }();
+  if (!two_streams) {
+    const int64_t ntiles = ceil_div(M, TMF);
+    const int grid = (int)(ntiles < sm_count() ? ntiles : sm_count());
+    CMP_REQUIRE(launch_pdl(node_chain_kernel, dim3(grid), dim3(NTC), smem, as_stream(stream), p) == cudaSuccess, CMP_ECUDA,
+                "cmp_node_chain_fwd: launch failed");
+  } else {
+    const int64_t npairs = ceil_div(ceil_div(M, TMC), 2);
+    const int grid = (int)(npairs < sm_count() ? npairs : sm_count());
+    CMP_REQUIRE(launch_pdl(node_chain2_kernel, dim3(grid), dim3(NTC2), smem, as_stream(stream), p) == cudaSuccess, CMP_ECUDA,
+                "cmp_node_chain_fwd: launch failed");
+  }
   CMP_LAUNCH_CHECK("cmp_node_chain_fwd");
   return CMP_OK;
 }
