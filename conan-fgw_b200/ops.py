@@ -111,9 +111,12 @@ def linear(x, weight, bias=None, act=ACT_NONE, residual=None, tc=False):
     """``tc=True``: split-bf16 tcgen05 kernels (bf16 mode); else the exact-fp32 SIMT GEMM."""
     if tc and node_tc_supported(weight.shape[1], weight.shape[0]):
         return _LinearTCFn.apply(x, weight, bias, act, residual)
-    if (tc and act == ACT_NONE and weight.shape[0] % 16 == 0 and weight.shape[1] % 16 == 0
-            and bool(_lib.lib().cmp_device_is_sm100())):
-        return _LinearTCBlockedFn.apply(x, weight, bias, residual)
+    if (tc and weight.shape[0] % 16 == 0 and weight.shape[1] % 16 == 0 and bool(_lib.lib().cmp_device_is_sm100())):
+        if act == ACT_NONE:
+            return _LinearTCBlockedFn.apply(x, weight, bias, residual)
+        # wide layer with an activation (CFConv.lin2 of the H = 512 models): blocked GEMM, then the activation kernel
+        y = _ActFn.apply(_LinearTCBlockedFn.apply(x, weight, bias, None), act)
+        return y if residual is None else y + residual
     return _LinearFn.apply(x, weight, bias, act, residual)
 
 
