@@ -40,8 +40,11 @@ UNIT = "conformers/s"
 CPU_SAMPLE_MOLECULES = 64            # cpu_baseline leg of our own arm: a bounded sample (about 10 s of CPU work)
 REFERENCE_BUDGET_S = 240.0           # --impl reference: the whole run (warm-up + timed steps) stays within this
 # measured once per round under ncu (never a timing source): DRAM traffic per launch at the default workload
-# (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r02_dense_ws_kernel.metrics.csv, r01_pair_bwd_kernel.metrics.csv)
-NCU_DRAM_BYTES_PER_LAUNCH = {"cmp_cfconv_dense_fwd": 9481984, "cmp_cfconv_dense_bwd_weights": None, "cmp_cfconv_pair_fwd": 12547584,
+# (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r02_dense_ws_kernel.metrics.csv, r02_dense_bwd_kernel.metrics.csv,
+# r02_x3_fwd_kernel.metrics.csv, r02_x3_bwd_kernel.metrics.csv, r01_pair_bwd_kernel.metrics.csv)
+NCU_DRAM_BYTES_PER_LAUNCH = {"cmp_cfconv_dense_fwd": 9481984, "cmp_cfconv_dense_bwd_weights": 18723328 + 437504,
+                             "cmp_cfconv_dense_x3_fwd": 9512192, "cmp_cfconv_dense_bwd_x3_weights": 18353152 + 256,
+                             "cmp_cfconv_pair_fwd": 12547584,
                              "cmp_cfconv_fused_bwd_weights_pairs": 13398784 + 764672, "cmp_cfconv_fused_fwd": 15000000}
 FWD_KERNELS = ("cmp_cfconv_dense_fwd", "cmp_cfconv_dense_x3_fwd", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd")
 DTYPE_X3 = "f32-grade: f16 / bf16 hi + lo filter-MLP operands, three tcgen05 passes, f32 accumulation and epilogues; f32 elsewhere (node linears: exact SIMT, or split-bf16 tcgen05 with CMP_FP32_NODE_TC=1)"
@@ -700,8 +703,9 @@ def run_ours(args):
         # DRAM bytes of ONE launch of the dominant kernel from the committed `ncu --set full` capture of this workload
         # (dram__bytes_read.sum + dram__bytes_write.sum); null when the dominant kernel has no capture under profiles/
         "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(top) if WORKLOAD == "cfg2_lipo_train" else None,
-        "traffic_source": "profiles/r02_dense_ws_kernel.metrics.csv (forward), profiles/r01_pair_bwd_kernel.metrics.csv "
-                          "(weight gradients): ncu --set full, cfg 2; algorithmic bytes of the dense forward: x' 8.8 MB read "
+        "traffic_source": "profiles/r02_dense_ws_kernel.metrics.csv (forward), profiles/r02_dense_bwd_kernel.metrics.csv (weight "
+                          "gradients), profiles/r02_x3_{fwd,bwd}_kernel.metrics.csv (fp32-grade kernels), r01_pair_bwd_kernel.metrics.csv "
+                          "(round-1 pair kernel): ncu --set full, cfg 2; algorithmic bytes of the dense forward: x' 8.8 MB read "
                           "+ positions / adjacency 0.5 MB (the 8.8 MB of agg stay in L2)",
         "peak_source": pk["source"] + ", " + peak_kind,
         "launches_timed": n_l, "kernel_ms_per_step": k_ms / ksteps, "avg_launch_us": 1e3 * k_ms / max(n_l, 1),
