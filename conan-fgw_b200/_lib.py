@@ -72,11 +72,12 @@ SIGNATURES = {
     "cmp_gather_rows": (I, [P, P, L, I, P, P]),
     "cmp_vis_edge_embed_fwd": (I, [P, P, P, P, L, I, P, P]),
     "cmp_vis_edge_embed_bwd": (I, [P, P, P, P, P, L, I, P, P, P]),
-    "cmp_vis_message_fwd": (I, [P, P, P, P, P, P, P, P, L, I, I, P, P, P]),
-    "cmp_vis_message_bwd": (I, [P, P, P, P, P, P, P, P, P, P, L, I, I, P, P, P, P, P, P]),
-    "cmp_vis_vecagg_fwd": (I, [P, P, P, P, P, L, I, P, P]),
-    "cmp_vis_vecagg_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, P, P, P]),
-    "cmp_vis_edge_update_fwd": (I, [P, P, P, P, P, P, L, I, P, P, P]),
+    "cmp_vis_message_fwd": (I, [P, P, P, P, P, P, P, P, L, I, I, I, P, P, P]),
+    "cmp_vis_message_bwd": (I, [P, P, P, P, P, P, P, P, P, P, L, I, I, I, P, P, P, P, P, P]),
+    "cmp_vis_vecagg_fwd": (I, [P, P, P, P, P, L, I, I, P, P]),
+    "cmp_vis_vecagg_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, I, P, P, P]),
+    "cmp_vis_edge_update_fwd": (I, [P, P, P, P, P, P, L, I, I, P, P, P]),
+    "cmp_vis_edge_update_bwd_prep": (I, [P, P, P, L, I, P, P, P]),
     "cmp_vis_edge_update_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, P, P, P]),
     "cmp_debug_set_fwd_timestamps": (None, [P]),
     "cmp_debug_set_bwd_timestamps": (None, [P]),

@@ -104,11 +104,15 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
 // out[i] = sum_{e in row i} x[perm ? perm[e] : e]      (perm = eid_t for the source-sorted transpose)
 __global__ void csr_segment_sum_kernel(const float* __restrict__ x, const int32_t* __restrict__ rowptr,
                                        const int32_t* __restrict__ perm, int64_t N, int C, float* __restrict__ out) {
-  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // one warp per (row, 32-channel slice): C / 32 times the warps of a warp-per-row mapping (the rows of a small batch
+  // do not fill the GPU, and the edge loop of a row is a serial chain)
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int slices = (C + 31) >> 5;
+  const int64_t row = wid / slices;
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
   const int b = rowptr[row], e = rowptr[row + 1];
-  for (int c = lane; c < C; c += 32) {
+  for (int c = (int)(wid - row * slices) * 32 + lane; c < C; c += C) {     // a single iteration
     float acc = 0.0f;
     for (int k = b; k < e; ++k) acc += x[(int64_t)(perm ? perm[k] : k) * C + c];
     out[row * C + c] = acc;
@@ -163,7 +167,9 @@ __global__ void __launch_bounds__(256)
 vis_message_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                        const float* __restrict__ dk, const float* __restrict__ dv, const float* __restrict__ C,
                        const int32_t* __restrict__ col, const int32_t* __restrict__ erow, int64_t E, int H, int heads,
-                       float* __restrict__ m, float* __restrict__ attn_pre) {
+                       int pre_act, float* __restrict__ m, float* __restrict__ attn_pre) {
+  // pre_act: dk / dv hold the PRE-activations of tgv.py:622-629 (the outputs of dk_proj / dv_proj): SiLU is applied here,
+  // so the activated [E, H] tensors never exist in HBM
   extern __shared__ float sh[];   // [warps][heads]
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -176,7 +182,10 @@ vis_message_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
   // head sums: each lane accumulates its channels, then adds into the head slot (fixed lane order via serialised loop)
   for (int h = 0; h < heads; ++h) {
     float s = 0.0f;
-    for (int c = h * hd + lane; c < (h + 1) * hd; c += 32) s += q[i * H + c] * k[j * H + c] * dk[e * H + c];
+    for (int c = h * hd + lane; c < (h + 1) * hd; c += 32) {
+      const float dkc = pre_act ? silu(dk[e * H + c]) : dk[e * H + c];
+      s += q[i * H + c] * k[j * H + c] * dkc;
+    }
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) hs[h] = s;
   }
@@ -185,7 +194,8 @@ vis_message_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
   for (int h = lane; h < heads; h += 32) attn_pre[e * heads + h] = hs[h];
   for (int c = lane; c < H; c += 32) {
     const float s = hs[c / hd];
-    m[e * H + c] = v[j * H + c] * dv[e * H + c] * (silu(s) * ce);
+    const float dvc = pre_act ? silu(dv[e * H + c]) : dv[e * H + c];
+    m[e * H + c] = v[j * H + c] * dvc * (silu(s) * ce);
   }
 }
 
@@ -193,9 +203,9 @@ __global__ void __launch_bounds__(256)
 vis_message_bwd_kernel(const float* __restrict__ gm, const float* __restrict__ q, const float* __restrict__ k,
                        const float* __restrict__ v, const float* __restrict__ dk, const float* __restrict__ dv,
                        const float* __restrict__ C, const float* __restrict__ attn_pre, const int32_t* __restrict__ col,
-                       const int32_t* __restrict__ erow, int64_t E, int H, int heads, float* __restrict__ g_dk,
-                       float* __restrict__ g_dv, float* __restrict__ geq, float* __restrict__ gek,
-                       float* __restrict__ gev) {
+                       const int32_t* __restrict__ erow, int64_t E, int H, int heads, int pre_act,
+                       float* __restrict__ g_dk, float* __restrict__ g_dv, float* __restrict__ geq,
+                       float* __restrict__ gek, float* __restrict__ gev) {
   extern __shared__ float sh[];   // [warps][heads]  d(loss)/d(pre-activation)
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
@@ -206,7 +216,8 @@ vis_message_bwd_kernel(const float* __restrict__ gm, const float* __restrict__ q
   const float ce = C[e];
   for (int h = 0; h < heads; ++h) {
     float ga = 0.0f;   // d/d attn[h]
-    for (int c = h * hd + lane; c < (h + 1) * hd; c += 32) ga += gm[e * H + c] * v[j * H + c] * dv[e * H + c];
+    for (int c = h * hd + lane; c < (h + 1) * hd; c += 32)
+      ga += gm[e * H + c] * v[j * H + c] * (pre_act ? silu(dv[e * H + c]) : dv[e * H + c]);
     for (int o = 16; o; o >>= 1) ga += __shfl_xor_sync(0xffffffffu, ga, o);
     if (lane == 0) gs[h] = ga * ce * silu_grad(attn_pre[e * heads + h]);
   }
@@ -215,30 +226,37 @@ vis_message_bwd_kernel(const float* __restrict__ gm, const float* __restrict__ q
     const int h = c / hd;
     const float a = silu(attn_pre[e * heads + h]) * ce;
     const float g = gm[e * H + c];
-    const float qi = q[i * H + c], kj = k[j * H + c], vj = v[j * H + c], dkc = dk[e * H + c], dvc = dv[e * H + c];
+    const float qi = q[i * H + c], kj = k[j * H + c], vj = v[j * H + c];
+    const float dkp = dk[e * H + c], dvp = dv[e * H + c];
+    const float dkc = pre_act ? silu(dkp) : dkp, dvc = pre_act ? silu(dvp) : dvp;
     gev[e * H + c] = g * dvc * a;
-    g_dv[e * H + c] = g * vj * a;
+    g_dv[e * H + c] = g * vj * a * (pre_act ? silu_grad(dvp) : 1.0f);      // gradient of the pre-activation when pre_act
     const float s = gs[h];
     geq[e * H + c] = s * kj * dkc;
     gek[e * H + c] = s * qi * dkc;
-    g_dk[e * H + c] = s * qi * kj;
+    g_dk[e * H + c] = s * qi * kj * (pre_act ? silu_grad(dkp) : 1.0f);
   }
 }
 
 // ---- ViS_MP vector message + aggregation (tgv.py:650-651, 672): vagg[i] = sum_e vec[j] * s1[e] + s2[e] * dhat[e] ----
 __global__ void __launch_bounds__(256)
 vis_vecagg_fwd_kernel(const float* __restrict__ vec, const float* __restrict__ s12, const float* __restrict__ dhat,
-                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N, int H,
+                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N, int H, int pre_act,
                       float* __restrict__ vagg) {
-  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // one warp per (row, 32-channel slice): H / 32 times the warps of a warp-per-row mapping (the rows of a small batch
+  // do not fill the GPU, and the edge loop of a row is a serial chain)
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int slices = (H + 31) >> 5;
+  const int64_t row = wid / slices;
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
   const int b = rowptr[row], e = rowptr[row + 1];
-  for (int c = lane; c < H; c += 32) {
+  for (int c = (int)(wid - row * slices) * 32 + lane; c < H; c += H) {     // a single iteration
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
     for (int kk = b; kk < e; ++kk) {
       const int64_t j = col[kk];
-      const float s1 = s12[(int64_t)kk * 2 * H + c], s2 = s12[(int64_t)kk * 2 * H + H + c];
+      float s1 = s12[(int64_t)kk * 2 * H + c], s2 = s12[(int64_t)kk * 2 * H + H + c];
+      if (pre_act) { s1 = silu(s1); s2 = silu(s2); }     // s12 = the output of s_proj (tgv.py:649): SiLU applied here
       a0 += vec[(j * 3 + 0) * H + c] * s1 + s2 * dhat[3 * kk + 0];
       a1 += vec[(j * 3 + 1) * H + c] * s1 + s2 * dhat[3 * kk + 1];
       a2 += vec[(j * 3 + 2) * H + c] * s1 + s2 * dhat[3 * kk + 2];
@@ -253,17 +271,27 @@ vis_vecagg_fwd_kernel(const float* __restrict__ vec, const float* __restrict__ s
 __global__ void __launch_bounds__(256)
 vis_vecagg_bwd_s_kernel(const float* __restrict__ g, const float* __restrict__ vec, const float* __restrict__ dhat,
                         const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N, int H,
-                        float* __restrict__ g_s12) {
-  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                        const float* __restrict__ s12_pre, float* __restrict__ g_s12) {
+  // one warp per (row, 32-channel slice): H / 32 times the warps of a warp-per-row mapping (the rows of a small batch
+  // do not fill the GPU, and the edge loop of a row is a serial chain)
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int slices = (H + 31) >> 5;
+  const int64_t row = wid / slices;
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
   const int b = rowptr[row], e = rowptr[row + 1];
-  for (int c = lane; c < H; c += 32) {
+  for (int c = (int)(wid - row * slices) * 32 + lane; c < H; c += H) {     // a single iteration
     const float g0 = g[(row * 3 + 0) * H + c], g1 = g[(row * 3 + 1) * H + c], g2 = g[(row * 3 + 2) * H + c];
     for (int kk = b; kk < e; ++kk) {
       const int64_t j = col[kk];
-      g_s12[(int64_t)kk * 2 * H + c] = g0 * vec[(j * 3 + 0) * H + c] + g1 * vec[(j * 3 + 1) * H + c] + g2 * vec[(j * 3 + 2) * H + c];
-      g_s12[(int64_t)kk * 2 * H + H + c] = g0 * dhat[3 * kk + 0] + g1 * dhat[3 * kk + 1] + g2 * dhat[3 * kk + 2];
+      float gs1 = g0 * vec[(j * 3 + 0) * H + c] + g1 * vec[(j * 3 + 1) * H + c] + g2 * vec[(j * 3 + 2) * H + c];
+      float gs2 = g0 * dhat[3 * kk + 0] + g1 * dhat[3 * kk + 1] + g2 * dhat[3 * kk + 2];
+      if (s12_pre) {     // gradients of the pre-activations
+        gs1 *= silu_grad(s12_pre[(int64_t)kk * 2 * H + c]);
+        gs2 *= silu_grad(s12_pre[(int64_t)kk * 2 * H + H + c]);
+      }
+      g_s12[(int64_t)kk * 2 * H + c] = gs1;
+      g_s12[(int64_t)kk * 2 * H + H + c] = gs2;
     }
   }
 }
@@ -271,17 +299,22 @@ vis_vecagg_bwd_s_kernel(const float* __restrict__ g, const float* __restrict__ v
 // gradient of vec at the SOURCE atoms (warp per source row of the transpose)
 __global__ void __launch_bounds__(256)
 vis_vecagg_bwd_vec_kernel(const float* __restrict__ g, const float* __restrict__ s12, const int32_t* __restrict__ rowptr_t,
-                          const int32_t* __restrict__ col_t, const int32_t* __restrict__ eid_t, int64_t N, int H,
+                          const int32_t* __restrict__ col_t, const int32_t* __restrict__ eid_t, int64_t N, int H, int pre_act,
                           float* __restrict__ g_vec) {
-  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // one warp per (row, 32-channel slice): H / 32 times the warps of a warp-per-row mapping (the rows of a small batch
+  // do not fill the GPU, and the edge loop of a row is a serial chain)
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int slices = (H + 31) >> 5;
+  const int64_t row = wid / slices;
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
   const int b = rowptr_t[row], e = rowptr_t[row + 1];
-  for (int c = lane; c < H; c += 32) {
+  for (int c = (int)(wid - row * slices) * 32 + lane; c < H; c += H) {     // a single iteration
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
     for (int kk = b; kk < e; ++kk) {
       const int64_t i = col_t[kk];
-      const float s1 = s12[(int64_t)eid_t[kk] * 2 * H + c];
+      float s1 = s12[(int64_t)eid_t[kk] * 2 * H + c];
+      if (pre_act) s1 = silu(s1);
       a0 += g[(i * 3 + 0) * H + c] * s1;
       a1 += g[(i * 3 + 1) * H + c] * s1;
       a2 += g[(i * 3 + 2) * H + c] * s1;
@@ -297,7 +330,7 @@ vis_vecagg_bwd_vec_kernel(const float* __restrict__ g, const float* __restrict__
 __global__ void __launch_bounds__(256)
 vis_edge_update_fwd_kernel(const float* __restrict__ wt, const float* __restrict__ ws, const float* __restrict__ dhat,
                            const float* __restrict__ fpa, const int32_t* __restrict__ col,
-                           const int32_t* __restrict__ erow, int64_t E, int H, float* __restrict__ df,
+                           const int32_t* __restrict__ erow, int64_t E, int H, int pre_act, float* __restrict__ df,
                            float* __restrict__ wdot) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = E * H;
@@ -312,7 +345,20 @@ vis_edge_update_fwd_kernel(const float* __restrict__ wt, const float* __restrict
     const float a = t0 * d0 + t1 * d1 + t2 * d2, b = s0 * d0 + s1 * d1 + s2 * d2;
     const float w = t0 * s0 + t1 * s1 + t2 * s2 - a * b;
     wdot[t] = w;
-    df[t] = fpa[t] * w;
+    df[t] = (pre_act ? silu(fpa[t]) : fpa[t]) * w;     // pre_act: fpa = the output of f_proj (tgv.py:659), SiLU applied here
+  }
+}
+
+// backward of df = act(fpa) * wdot w.r.t. its two factors:  g_fpa = g * wdot [* silu'(fpa)],  gw = g * act(fpa)
+__global__ void vis_edge_update_bwd_prep_kernel(const float* __restrict__ g, const float* __restrict__ fpa,
+                                                const float* __restrict__ wdot, int64_t n, int pre_act,
+                                                float* __restrict__ g_fpa, float* __restrict__ gw) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; t < n; t += stride) {
+    const float gv = g[t], f = fpa[t];
+    g_fpa[t] = gv * wdot[t] * (pre_act ? silu_grad(f) : 1.0f);
+    gw[t] = gv * (pre_act ? silu(f) : f);
   }
 }
 
@@ -322,11 +368,15 @@ __global__ void __launch_bounds__(256)
 vis_edge_update_bwd_kernel(const float* __restrict__ gw, const float* __restrict__ other, const float* __restrict__ dhat,
                            const int32_t* __restrict__ rowptr, const int32_t* __restrict__ nbr,
                            const int32_t* __restrict__ eid, int64_t N, int H, float* __restrict__ out) {
-  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // one warp per (row, 32-channel slice): H / 32 times the warps of a warp-per-row mapping (the rows of a small batch
+  // do not fill the GPU, and the edge loop of a row is a serial chain)
+  const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int slices = (H + 31) >> 5;
+  const int64_t row = wid / slices;
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
   const int b = rowptr[row], e = rowptr[row + 1];
-  for (int c = lane; c < H; c += 32) {
+  for (int c = (int)(wid - row * slices) * 32 + lane; c < H; c += H) {     // a single iteration
     float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
     for (int kk = b; kk < e; ++kk) {
       const int64_t o = nbr[kk];
@@ -397,7 +447,7 @@ extern "C" int cmp_csr_segment_sum(const float* x, const int32_t* rowptr, const 
   CMP_REQUIRE(N >= 0 && C >= 1, CMP_EINVAL, "cmp_csr_segment_sum: bad size");
   if (N == 0) return CMP_OK;
   CMP_REQUIRE(rowptr && out, CMP_EINVAL, "cmp_csr_segment_sum: null pointer");
-  csr_segment_sum_kernel<<<warp_rows_grid(N), 256, 0, as_stream(stream)>>>(x, rowptr, perm, N, C, out);
+  csr_segment_sum_kernel<<<warp_rows_grid(N * ((C + 31) / 32)), 256, 0, as_stream(stream)>>>(x, rowptr, perm, N, C, out);
   CMP_LAUNCH_CHECK("cmp_csr_segment_sum");
   return CMP_OK;
 }
@@ -434,66 +484,79 @@ extern "C" int cmp_vis_edge_embed_bwd(const float* g, const float* x, const floa
 
 extern "C" int cmp_vis_message_fwd(const float* q, const float* k, const float* v, const float* dk, const float* dv,
                                    const float* C, const int32_t* col, const int32_t* erow, int64_t E, int H, int heads,
-                                   float* m, float* attn_pre, cmp_stream_t stream) {
+                                   int pre_act, float* m, float* attn_pre, cmp_stream_t stream) {
   CMP_REQUIRE(E >= 0 && H >= 1 && heads >= 1 && H % heads == 0 && heads <= 64, CMP_EINVAL, "cmp_vis_message_fwd: bad size");
   if (E == 0) return CMP_OK;
   CMP_REQUIRE(q && k && v && dk && dv && C && col && erow && m && attn_pre, CMP_EINVAL, "cmp_vis_message_fwd: null pointer");
   vis_message_fwd_kernel<<<(unsigned)ceil_div(E, 8), 256, 8 * heads * sizeof(float), as_stream(stream)>>>(
-      q, k, v, dk, dv, C, col, erow, E, H, heads, m, attn_pre);
+      q, k, v, dk, dv, C, col, erow, E, H, heads, pre_act, m, attn_pre);
   CMP_LAUNCH_CHECK("cmp_vis_message_fwd");
   return CMP_OK;
 }
 
 extern "C" int cmp_vis_message_bwd(const float* gm, const float* q, const float* k, const float* v, const float* dk,
                                    const float* dv, const float* C, const float* attn_pre, const int32_t* col,
-                                   const int32_t* erow, int64_t E, int H, int heads, float* g_dk, float* g_dv, float* geq,
-                                   float* gek, float* gev, cmp_stream_t stream) {
+                                   const int32_t* erow, int64_t E, int H, int heads, int pre_act, float* g_dk, float* g_dv,
+                                   float* geq, float* gek, float* gev, cmp_stream_t stream) {
   CMP_REQUIRE(E >= 0 && H >= 1 && heads >= 1 && H % heads == 0 && heads <= 64, CMP_EINVAL, "cmp_vis_message_bwd: bad size");
   if (E == 0) return CMP_OK;
   CMP_REQUIRE(gm && q && k && v && dk && dv && C && attn_pre && col && erow && g_dk && g_dv && geq && gek && gev,
               CMP_EINVAL, "cmp_vis_message_bwd: null pointer");
   vis_message_bwd_kernel<<<(unsigned)ceil_div(E, 8), 256, 8 * heads * sizeof(float), as_stream(stream)>>>(
-      gm, q, k, v, dk, dv, C, attn_pre, col, erow, E, H, heads, g_dk, g_dv, geq, gek, gev);
+      gm, q, k, v, dk, dv, C, attn_pre, col, erow, E, H, heads, pre_act, g_dk, g_dv, geq, gek, gev);
   CMP_LAUNCH_CHECK("cmp_vis_message_bwd");
   return CMP_OK;
 }
 
 extern "C" int cmp_vis_vecagg_fwd(const float* vec, const float* s12, const float* dhat, const int32_t* rowptr,
-                                  const int32_t* col, int64_t N, int H, float* vagg, cmp_stream_t stream) {
+                                  const int32_t* col, int64_t N, int H, int pre_act, float* vagg, cmp_stream_t stream) {
   CMP_REQUIRE(N >= 0 && H >= 1, CMP_EINVAL, "cmp_vis_vecagg_fwd: bad size");
   if (N == 0) return CMP_OK;
   CMP_REQUIRE(vec && rowptr && vagg, CMP_EINVAL, "cmp_vis_vecagg_fwd: null pointer");
-  vis_vecagg_fwd_kernel<<<warp_rows_grid(N), 256, 0, as_stream(stream)>>>(vec, s12, dhat, rowptr, col, N, H, vagg);
+  vis_vecagg_fwd_kernel<<<warp_rows_grid(N * ((H + 31) / 32)), 256, 0, as_stream(stream)>>>(vec, s12, dhat, rowptr, col, N, H, pre_act, vagg);
   CMP_LAUNCH_CHECK("cmp_vis_vecagg_fwd");
   return CMP_OK;
 }
 
 extern "C" int cmp_vis_vecagg_bwd(const float* g, const float* vec, const float* s12, const float* dhat,
                                   const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t, const int32_t* col_t,
-                                  const int32_t* eid_t, int64_t N, int H, float* g_s12, float* g_vec, cmp_stream_t stream) {
+                                  const int32_t* eid_t, int64_t N, int H, int pre_act, float* g_s12, float* g_vec,
+                                  cmp_stream_t stream) {
   CMP_REQUIRE(N >= 0 && H >= 1, CMP_EINVAL, "cmp_vis_vecagg_bwd: bad size");
   if (N == 0) return CMP_OK;
   CMP_REQUIRE(g && vec && rowptr && rowptr_t && col_t && eid_t, CMP_EINVAL, "cmp_vis_vecagg_bwd: null pointer");
   if (g_s12) {
-    vis_vecagg_bwd_s_kernel<<<warp_rows_grid(N), 256, 0, as_stream(stream)>>>(g, vec, dhat, rowptr, col, N, H, g_s12);
+    vis_vecagg_bwd_s_kernel<<<warp_rows_grid(N * ((H + 31) / 32)), 256, 0, as_stream(stream)>>>(g, vec, dhat, rowptr, col, N, H,
+                                                                              pre_act ? s12 : nullptr, g_s12);
     CMP_LAUNCH_CHECK("cmp_vis_vecagg_bwd(s)");
   }
   if (g_vec) {
-    vis_vecagg_bwd_vec_kernel<<<warp_rows_grid(N), 256, 0, as_stream(stream)>>>(g, s12, rowptr_t, col_t, eid_t, N, H,
-                                                                                g_vec);
+    vis_vecagg_bwd_vec_kernel<<<warp_rows_grid(N * ((H + 31) / 32)), 256, 0, as_stream(stream)>>>(g, s12, rowptr_t, col_t, eid_t, N, H,
+                                                                                pre_act, g_vec);
     CMP_LAUNCH_CHECK("cmp_vis_vecagg_bwd(vec)");
   }
   return CMP_OK;
 }
 
 extern "C" int cmp_vis_edge_update_fwd(const float* wt, const float* ws, const float* dhat, const float* fpa,
-                                       const int32_t* col, const int32_t* erow, int64_t E, int H, float* df, float* wdot,
-                                       cmp_stream_t stream) {
+                                       const int32_t* col, const int32_t* erow, int64_t E, int H, int pre_act, float* df,
+                                       float* wdot, cmp_stream_t stream) {
   CMP_REQUIRE(E >= 0 && H >= 1, CMP_EINVAL, "cmp_vis_edge_update_fwd: bad size");
   if (E == 0) return CMP_OK;
   CMP_REQUIRE(wt && ws && dhat && fpa && col && erow && df && wdot, CMP_EINVAL, "cmp_vis_edge_update_fwd: null pointer");
-  vis_edge_update_fwd_kernel<<<grid1d(E * H), 256, 0, as_stream(stream)>>>(wt, ws, dhat, fpa, col, erow, E, H, df, wdot);
+  vis_edge_update_fwd_kernel<<<grid1d(E * H), 256, 0, as_stream(stream)>>>(wt, ws, dhat, fpa, col, erow, E, H, pre_act, df,
+                                                                           wdot);
   CMP_LAUNCH_CHECK("cmp_vis_edge_update_fwd");
+  return CMP_OK;
+}
+
+extern "C" int cmp_vis_edge_update_bwd_prep(const float* g, const float* fpa, const float* wdot, int64_t n, int pre_act,
+                                            float* g_fpa, float* gw, cmp_stream_t stream) {
+  CMP_REQUIRE(n >= 0, CMP_EINVAL, "cmp_vis_edge_update_bwd_prep: bad size");
+  if (n == 0) return CMP_OK;
+  CMP_REQUIRE(g && fpa && wdot && g_fpa && gw, CMP_EINVAL, "cmp_vis_edge_update_bwd_prep: null pointer");
+  vis_edge_update_bwd_prep_kernel<<<grid1d(n), 256, 0, as_stream(stream)>>>(g, fpa, wdot, n, pre_act, g_fpa, gw);
+  CMP_LAUNCH_CHECK("cmp_vis_edge_update_bwd_prep");
   return CMP_OK;
 }
 
@@ -505,10 +568,10 @@ extern "C" int cmp_vis_edge_update_bwd(const float* gw, const float* wt, const f
   if (N == 0) return CMP_OK;
   CMP_REQUIRE(gw && wt && ws && dhat && rowptr && col && rowptr_t && col_t && eid_t && g_wt && g_ws, CMP_EINVAL,
               "cmp_vis_edge_update_bwd: null pointer");
-  vis_edge_update_bwd_kernel<<<warp_rows_grid(N), 256, 0, as_stream(stream)>>>(gw, ws, dhat, rowptr, col, nullptr, N, H,
+  vis_edge_update_bwd_kernel<<<warp_rows_grid(N * ((H + 31) / 32)), 256, 0, as_stream(stream)>>>(gw, ws, dhat, rowptr, col, nullptr, N, H,
                                                                               g_wt);
   CMP_LAUNCH_CHECK("cmp_vis_edge_update_bwd(wt)");
-  vis_edge_update_bwd_kernel<<<warp_rows_grid(N), 256, 0, as_stream(stream)>>>(gw, wt, dhat, rowptr_t, col_t, eid_t, N, H,
+  vis_edge_update_bwd_kernel<<<warp_rows_grid(N * ((H + 31) / 32)), 256, 0, as_stream(stream)>>>(gw, wt, dhat, rowptr_t, col_t, eid_t, N, H,
                                                                               g_ws);
   CMP_LAUNCH_CHECK("cmp_vis_edge_update_bwd(ws)");
   return CMP_OK;

@@ -153,14 +153,16 @@ class _EdgeEmbedFn(Function):
 
 class _MessageFn(Function):
     @staticmethod
-    def forward(ctx, q, k, v, dk, dv, C, graph, heads):
+    def forward(ctx, q, k, v, dk, dv, C, graph, heads, pre_act=False):
+        """``pre_act``: ``dk`` / ``dv`` are the outputs of ``dk_proj`` / ``dv_proj``; their SiLU (tgv.py:622-629) is applied
+        inside the kernels and the returned gradients are those of the pre-activations."""
         q, k, v, dk, dv = (_c(t) for t in (q, k, v, dk, dv))
         E, H = dk.shape
         m = torch.empty_like(dk)
         pre = torch.empty(E, heads, dtype=torch.float32, device=dk.device)
         call("cmp_vis_message_fwd", ptr(q), ptr(k), ptr(v), ptr(dk), ptr(dv), ptr(C), ptr(graph.col), ptr(graph.erow()),
-             E, H, heads, ptr(m), ptr(pre))
-        ctx.graph, ctx.heads = graph, heads
+             E, H, heads, int(pre_act), ptr(m), ptr(pre))
+        ctx.graph, ctx.heads, ctx.pre_act = graph, heads, int(pre_act)
         ctx.save_for_backward(q, k, v, dk, dv, C, pre)
         return m
 
@@ -172,21 +174,23 @@ class _MessageFn(Function):
         E, H = dk.shape
         g_dk, g_dv, geq, gek, gev = (torch.empty_like(dk) for _ in range(5))
         call("cmp_vis_message_bwd", ptr(gm), ptr(q), ptr(k), ptr(v), ptr(dk), ptr(dv), ptr(C), ptr(pre), ptr(graph.col),
-             ptr(graph.erow()), E, H, ctx.heads, ptr(g_dk), ptr(g_dv), ptr(geq), ptr(gek), ptr(gev))
+             ptr(graph.erow()), E, H, ctx.heads, ctx.pre_act, ptr(g_dk), ptr(g_dv), ptr(geq), ptr(gek), ptr(gev))
         dq = _segsum(geq, graph.rowptr, None, graph.N)                     # q is gathered at the target
         dkn = _segsum(gek, graph.rowptr_t, graph.eid_t, graph.N)          # k, v at the source
         dvn = _segsum(gev, graph.rowptr_t, graph.eid_t, graph.N)
-        return dq, dkn, dvn, g_dk, g_dv, None, None, None
+        return dq, dkn, dvn, g_dk, g_dv, None, None, None, None
 
 
 class _VecAggFn(Function):
     @staticmethod
-    def forward(ctx, vec, s12, dhat, graph):
+    def forward(ctx, vec, s12, dhat, graph, pre_act=False):
+        """``pre_act``: ``s12`` is the output of ``s_proj`` (tgv.py:649), SiLU applied inside the kernels."""
         vec, s12 = _c(vec), _c(s12)
         N, _, H = vec.shape
         out = torch.empty_like(vec)
-        call("cmp_vis_vecagg_fwd", ptr(vec), ptr(s12), ptr(dhat), ptr(graph.rowptr), ptr(graph.col), N, H, ptr(out))
-        ctx.graph = graph
+        call("cmp_vis_vecagg_fwd", ptr(vec), ptr(s12), ptr(dhat), ptr(graph.rowptr), ptr(graph.col), N, H, int(pre_act),
+             ptr(out))
+        ctx.graph, ctx.pre_act = graph, int(pre_act)
         ctx.save_for_backward(vec, s12, dhat)
         return out
 
@@ -199,20 +203,21 @@ class _VecAggFn(Function):
         g_s12 = torch.empty_like(s12)
         g_vec = torch.empty_like(vec)
         call("cmp_vis_vecagg_bwd", ptr(g), ptr(vec), ptr(s12), ptr(dhat), ptr(graph.rowptr), ptr(graph.col),
-             ptr(graph.rowptr_t), ptr(graph.col_t), ptr(graph.eid_t), N, H, ptr(g_s12), ptr(g_vec))
-        return g_vec, g_s12, None, None
+             ptr(graph.rowptr_t), ptr(graph.col_t), ptr(graph.eid_t), N, H, ctx.pre_act, ptr(g_s12), ptr(g_vec))
+        return g_vec, g_s12, None, None, None
 
 
 class _EdgeUpdateFn(Function):
     @staticmethod
-    def forward(ctx, wt, ws, dhat, fpa, graph):
+    def forward(ctx, wt, ws, dhat, fpa, graph, pre_act=False):
+        """``pre_act``: ``fpa`` is the output of ``f_proj`` (tgv.py:659), SiLU applied inside the kernels."""
         wt, ws, fpa = _c(wt), _c(ws), _c(fpa)
         E, H = fpa.shape
         df = torch.empty_like(fpa)
         wdot = torch.empty_like(fpa)
         call("cmp_vis_edge_update_fwd", ptr(wt), ptr(ws), ptr(dhat), ptr(fpa), ptr(graph.col), ptr(graph.erow()), E, H,
-             ptr(df), ptr(wdot))
-        ctx.graph = graph
+             int(pre_act), ptr(df), ptr(wdot))
+        ctx.graph, ctx.pre_act = graph, int(pre_act)
         ctx.save_for_backward(wt, ws, dhat, fpa, wdot)
         return df
 
@@ -222,13 +227,13 @@ class _EdgeUpdateFn(Function):
         graph = ctx.graph
         g = _c(g)
         N, _, H = wt.shape
-        g_fpa = g * wdot
-        gw = (g * fpa).contiguous()
+        g_fpa, gw = torch.empty_like(fpa), torch.empty_like(fpa)
+        call("cmp_vis_edge_update_bwd_prep", ptr(g), ptr(fpa), ptr(wdot), fpa.numel(), ctx.pre_act, ptr(g_fpa), ptr(gw))
         g_wt = torch.empty_like(wt)
         g_ws = torch.empty_like(ws)
         call("cmp_vis_edge_update_bwd", ptr(gw), ptr(wt), ptr(ws), ptr(dhat), ptr(graph.rowptr), ptr(graph.col),
              ptr(graph.rowptr_t), ptr(graph.col_t), ptr(graph.eid_t), N, H, ptr(g_wt), ptr(g_ws))
-        return g_wt, g_ws, None, g_fpa, None
+        return g_wt, g_ws, None, g_fpa, None, None
 
 
 def layer_norm(x, module: nn.LayerNorm):
@@ -432,23 +437,28 @@ class ViS_MP(nn.Module):
             torch.nn.init.xavier_uniform_(self.w_trg_proj.weight)
         torch.nn.init.xavier_uniform_(self.vec_proj.weight)
 
-    def forward(self, x, vec, edge_index, r_ij, f_ij, d_ij):
+    def forward(self, x, vec, edge_index, r_ij, f_ij, d_ij, cutoff_values=None):
+        """``cutoff_values``: ``CosineCutoff(r_ij)`` when the caller already has it (every layer of a block uses the same
+        cutoff on the same distances - ViSNetBlock evaluates it once instead of once per layer, tgv.py:645)."""
         graph = _graph_of(edge_index)
         H = self.hidden_channels
-        C = self.cutoff(r_ij).contiguous()
+        C = cutoff_values if cutoff_values is not None else self.cutoff(r_ij).contiguous()
         d_ij = _c(d_ij)
         x = layer_norm(x, self.layernorm)
         vec = self.vec_layernorm(vec)
         q, k, v = self.q_proj(x), self.k_proj(x), self.v_proj(x)
-        dk = ops.silu(self.dk_proj(f_ij))
-        dv = ops.silu(self.dv_proj(f_ij))
+        # the SiLUs on the four edge-sized projections (dk, dv, s12, f_proj: tgv.py:622-629,649,659) are applied INSIDE
+        # the kernels that consume them: the activated [E, H] / [E, 2H] tensors never exist and 8 activation launches per
+        # layer (forward + backward) disappear
+        dk = self.dk_proj(f_ij)
+        dv = self.dv_proj(f_ij)
         vec1, vec2, vec3 = torch.split(self.vec_proj(vec), H, dim=-1)
         vec_dot = (vec1 * vec2).sum(dim=1)
 
-        m = _MessageFn.apply(q, k, v, dk, dv, C, graph, self.num_heads)          # [E, H]  v_j * dv * attn
-        s12 = ops.silu(self.s_proj(m))                                           # [E, 2H] = [s1 | s2]
+        m = _MessageFn.apply(q, k, v, dk, dv, C, graph, self.num_heads, True)    # [E, H]  v_j * silu(dv) * attn
+        s12 = self.s_proj(m)                                                     # [E, 2H] = pre-activations of [s1 | s2]
         x_agg = _SegSumFn.apply(m, graph)
-        vec_agg = _VecAggFn.apply(vec, s12, d_ij, graph)
+        vec_agg = _VecAggFn.apply(vec, s12, d_ij, graph, True)
 
         o1, o2, o3 = torch.split(self.o_proj(x_agg), H, dim=1)
         dx = vec_dot * o2 + o3
@@ -457,8 +467,7 @@ class ViS_MP(nn.Module):
             return dx, dvec, None
         # w_trg / w_src are bias-free linears: apply them once per atom instead of once per edge (tgv.py:657-658)
         wt, ws = self.w_trg_proj(vec), self.w_src_proj(vec)
-        fpa = ops.silu(self.f_proj(f_ij))
-        df = _EdgeUpdateFn.apply(wt, ws, d_ij, fpa, graph)
+        df = _EdgeUpdateFn.apply(wt, ws, d_ij, self.f_proj(f_ij), graph, True)
         return dx, dvec, df
 
 
@@ -516,12 +525,14 @@ class ViSNetBlock(nn.Module):
         x = self.neighbor_embedding(z, x, edge_index, edge_weight, rbf)
         vec = torch.zeros(x.size(0), ((self.lmax + 1) ** 2) - 1, x.size(1), dtype=x.dtype, device=x.device)
         edge_attr = self.edge_embedding(edge_index, rbf, x)
+        # every layer applies the same CosineCutoff to the same distances (tgv.py:645): evaluated once per forward
+        cut = self.vis_mp_layers[0].cutoff(edge_weight).contiguous()
         for attn in self.vis_mp_layers[:-1]:
-            dx, dvec, dedge = attn(x, vec, edge_index, edge_weight, edge_attr, edge_vec)
+            dx, dvec, dedge = attn(x, vec, edge_index, edge_weight, edge_attr, edge_vec, cutoff_values=cut)
             x = x + dx
             vec = vec + dvec
             edge_attr = edge_attr + dedge
-        dx, dvec, _ = self.vis_mp_layers[-1](x, vec, edge_index, edge_weight, edge_attr, edge_vec)
+        dx, dvec, _ = self.vis_mp_layers[-1](x, vec, edge_index, edge_weight, edge_attr, edge_vec, cutoff_values=cut)
         x = x + dx
         vec = vec + dvec
         x = layer_norm(x, self.out_norm)

@@ -522,28 +522,37 @@ int cmp_vis_edge_embed_fwd(const float* x, const float* ep, const int32_t* col, 
 int cmp_vis_edge_embed_bwd(const float* g, const float* x, const float* ep, const int32_t* col,
                            const int32_t* erow, int64_t E, int H, float* gep, float* t_out,
                            cmp_stream_t stream);
-/* ViS_MP.message scalar part (tgv.py:644-648): attn = silu(sum_d q_i k_j dk) * C, m = v_j dv attn. */
+/* ViS_MP.message scalar part (tgv.py:644-648): attn = silu(sum_d q_i k_j dk) * C, m = v_j dv attn.
+ * pre_act != 0: dk / dv are the OUTPUTS of dk_proj / dv_proj (tgv.py:622-629); their SiLU is applied inside the kernel
+ * and g_dk / g_dv are the gradients of those pre-activations (no activated [E, H] tensor in HBM, no activation launch). */
 int cmp_vis_message_fwd(const float* q, const float* k, const float* v, const float* dk,
                         const float* dv, const float* C, const int32_t* col, const int32_t* erow,
-                        int64_t E, int H, int heads, float* m, float* attn_pre, cmp_stream_t stream);
+                        int64_t E, int H, int heads, int pre_act, float* m, float* attn_pre,
+                        cmp_stream_t stream);
 int cmp_vis_message_bwd(const float* gm, const float* q, const float* k, const float* v,
                         const float* dk, const float* dv, const float* C, const float* attn_pre,
-                        const int32_t* col, const int32_t* erow, int64_t E, int H, int heads,
+                        const int32_t* col, const int32_t* erow, int64_t E, int H, int heads, int pre_act,
                         float* g_dk, float* g_dv, float* geq, float* gek, float* gev,
                         cmp_stream_t stream);
 /* ViS_MP vector message + aggregation (tgv.py:650-651,672):
- * vagg[i] = sum_e vec[j] * s1[e] + s2[e] * dhat[e], s12 = [s1 | s2] per edge. */
+ * vagg[i] = sum_e vec[j] * s1[e] + s2[e] * dhat[e], s12 = [s1 | s2] per edge.
+ * pre_act != 0: s12 is the OUTPUT of s_proj (tgv.py:649), SiLU applied inside; g_s12 = gradient of the pre-activation. */
 int cmp_vis_vecagg_fwd(const float* vec, const float* s12, const float* dhat, const int32_t* rowptr,
-                       const int32_t* col, int64_t N, int H, float* vagg, cmp_stream_t stream);
+                       const int32_t* col, int64_t N, int H, int pre_act, float* vagg, cmp_stream_t stream);
 int cmp_vis_vecagg_bwd(const float* g, const float* vec, const float* s12, const float* dhat,
                        const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t,
-                       const int32_t* col_t, const int32_t* eid_t, int64_t N, int H, float* g_s12,
+                       const int32_t* col_t, const int32_t* eid_t, int64_t N, int H, int pre_act, float* g_s12,
                        float* g_vec, cmp_stream_t stream);
 /* ViS_MP.edge_update (tgv.py:655-661) with w_trg / w_src applied at the nodes (bias-free linears):
  * wdot = wt_i . ws_j - (wt_i . dhat)(ws_j . dhat);  df = fpa * wdot. */
+/* pre_act != 0: fpa is the OUTPUT of f_proj (tgv.py:659), SiLU applied inside.
+ * cmp_vis_edge_update_bwd_prep: the two per-edge factors of the backward in one pass over n = E * H values,
+ * g_fpa = g * wdot [* silu'(fpa)] and gw = g * act(fpa) (the input of cmp_vis_edge_update_bwd). */
 int cmp_vis_edge_update_fwd(const float* wt, const float* ws, const float* dhat, const float* fpa,
-                            const int32_t* col, const int32_t* erow, int64_t E, int H, float* df,
+                            const int32_t* col, const int32_t* erow, int64_t E, int H, int pre_act, float* df,
                             float* wdot, cmp_stream_t stream);
+int cmp_vis_edge_update_bwd_prep(const float* g, const float* fpa, const float* wdot, int64_t n, int pre_act,
+                                 float* g_fpa, float* gw, cmp_stream_t stream);
 int cmp_vis_edge_update_bwd(const float* gw, const float* wt, const float* ws, const float* dhat,
                             const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t,
                             const int32_t* col_t, const int32_t* eid_t, int64_t N, int H, float* g_wt,
