@@ -177,6 +177,37 @@ vis_message_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
   if (e >= E) return;
   const int hd = H / heads;
   const int64_t i = erow[e], j = col[e];
+  if (hd == 16 && (H & 31) == 0 && H <= 256) {
+    // ConAN's shape (H = 128, 8 heads): lane l owns channels r * 32 + l, i.e. head 2 r + (l >> 4); every head sum is a
+    // butterfly inside a 16-lane half, all H / 32 of them in flight at once (the generic loop below walks the heads one
+    // after the other with half the lanes idle).  Same butterfly order per head: bit-identical results.
+    const int R = H >> 5;
+    const float ce = C[e];
+    float p[8], vv[8], dvc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r < R) {
+        const int c = r * 32 + lane;
+        const float dkp = dk[e * H + c], dvp = dv[e * H + c];
+        p[r] = q[i * H + c] * k[j * H + c] * (pre_act ? silu(dkp) : dkp);
+        vv[r] = v[j * H + c];
+        dvc[r] = pre_act ? silu(dvp) : dvp;
+      }
+    }
+#pragma unroll
+    for (int o = 8; o; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < R) p[r] += __shfl_xor_sync(0xffffffffu, p[r], o);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r < R) {
+        if ((lane & 15) == 0) attn_pre[e * heads + 2 * r + (lane >> 4)] = p[r];
+        m[e * H + r * 32 + lane] = vv[r] * dvc[r] * (silu(p[r]) * ce);
+      }
+    }
+    return;
+  }
   for (int h = lane; h < heads; h += 32) hs[h] = 0.0f;
   __syncwarp();
   // head sums: each lane accumulates its channels, then adds into the head slot (fixed lane order via serialised loop)
@@ -214,6 +245,42 @@ vis_message_bwd_kernel(const float* __restrict__ gm, const float* __restrict__ q
   const int hd = H / heads;
   const int64_t i = erow[e], j = col[e];
   const float ce = C[e];
+  if (hd == 16 && (H & 31) == 0 && H <= 256) {     // as in the forward kernel: all head sums in flight at once
+    const int R = H >> 5;
+    float ga[8], g[8], qi[8], kj[8], vj[8], dkp[8], dvp[8], dkc[8], dvc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r < R) {
+        const int c = r * 32 + lane;
+        g[r] = gm[e * H + c];
+        qi[r] = q[i * H + c]; kj[r] = k[j * H + c]; vj[r] = v[j * H + c];
+        dkp[r] = dk[e * H + c]; dvp[r] = dv[e * H + c];
+        dkc[r] = pre_act ? silu(dkp[r]) : dkp[r];
+        dvc[r] = pre_act ? silu(dvp[r]) : dvp[r];
+        ga[r] = g[r] * vj[r] * dvc[r];
+      }
+    }
+#pragma unroll
+    for (int o = 8; o; o >>= 1)
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+        if (r < R) ga[r] += __shfl_xor_sync(0xffffffffu, ga[r], o);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (r < R) {
+        const int c = r * 32 + lane;
+        const float ap = attn_pre[e * heads + 2 * r + (lane >> 4)];
+        const float sg = ga[r] * ce * silu_grad(ap);
+        const float a = silu(ap) * ce;
+        gev[e * H + c] = g[r] * dvc[r] * a;
+        g_dv[e * H + c] = g[r] * vj[r] * a * (pre_act ? silu_grad(dvp[r]) : 1.0f);
+        geq[e * H + c] = sg * kj[r] * dkc[r];
+        gek[e * H + c] = sg * qi[r] * dkc[r];
+        g_dk[e * H + c] = sg * qi[r] * kj[r] * (pre_act ? silu_grad(dkp[r]) : 1.0f);
+      }
+    }
+    return;
+  }
   for (int h = 0; h < heads; ++h) {
     float ga = 0.0f;   // d/d attn[h]
     for (int c = h * hd + lane; c < (h + 1) * hd; c += 32)
