@@ -258,6 +258,37 @@ gemm_f32_vec_kernel(int M, int N, int K, const float* __restrict__ A, int64_t ld
   }
 }
 
+// Tiny problems (the regression head of a training step: [128, 64] x [64, 1] and its two gradient GEMMs): one thread per
+// output element walks K with eight loads in flight - the tiled kernels above spend 10-20 us on 16-wide k steps with two
+// block barriers each for a few thousand multiply-adds.  Same ascending-k summation order per output.
+__global__ void __launch_bounds__(256)
+gemm_f32_small_kernel(int M, int N, int K, const float* __restrict__ A, int64_t sam, int64_t sak,
+                      const float* __restrict__ B, int64_t sbk, int64_t sbn, float* __restrict__ C, int64_t ldc,
+                      const float* __restrict__ bias, int act, const float* __restrict__ residual, int64_t ldr) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  const int m = idx / N, n = idx - m * N;
+  const float* a = A + (int64_t)m * sam;
+  const float* b = B + (int64_t)n * sbn;
+  float acc = 0.0f;
+  int k = 0;
+  for (; k + 8 <= K; k += 8) {
+    float av[8], bv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      av[u] = __ldg(a + (int64_t)(k + u) * sak);
+      bv[u] = __ldg(b + (int64_t)(k + u) * sbk);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = fmaf(av[u], bv[u], acc);
+  }
+  for (; k < K; ++k) acc = fmaf(__ldg(a + (int64_t)k * sak), __ldg(b + (int64_t)k * sbk), acc);
+  if (bias) acc += bias[n];
+  acc = apply_act(acc, act);
+  if (residual) acc += residual[(int64_t)m * ldr + n];
+  C[(int64_t)m * ldc + n] = acc;
+}
+
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int S, int64_t M, int64_t N,
                                      float* __restrict__ C, int64_t ldc, const float* __restrict__ bias, int act,
                                      const float* __restrict__ residual, int64_t ldr) {
@@ -500,6 +531,16 @@ extern "C" int cmp_gemm_f32(int transA, int transB, int64_t M, int64_t N, int64_
   CMP_REQUIRE(C && (K == 0 || (A && B)), CMP_EINVAL, "cmp_gemm_f32: null pointer");
   CMP_REQUIRE(!(transA && transB), CMP_EUNSUPPORTED, "cmp_gemm_f32: transA && transB is not provided");
   CMP_REQUIRE(act >= CMP_ACT_NONE && act <= CMP_ACT_SILU, CMP_EINVAL, "cmp_gemm_f32: unknown activation %d", act);
+  cudaStream_t st0 = as_stream(stream);
+  if (M * N <= 16384 && K <= 1024) {
+    // op(A)[m, k] = A[m * sam + k * sak], op(B)[k, n] = B[k * sbk + n * sbn]
+    const int64_t sam = transA ? 1 : lda, sak = transA ? lda : 1;
+    const int64_t sbk = transB ? 1 : ldb, sbn = transB ? ldb : 1;
+    gemm_f32_small_kernel<<<(unsigned)ceil_div(M * N, 256), 256, 0, st0>>>((int)M, (int)N, (int)K, A, sam, sak, B, sbk, sbn, C,
+                                                                           ldc, bias, act, residual, ldr);
+    CMP_LAUNCH_CHECK("cmp_gemm_f32(small)");
+    return CMP_OK;
+  }
   SplitPlan p = (K > 0) ? plan_split(M, N, K) : SplitPlan{1, BK};
   float* partial = nullptr;
   if (p.S > 1) {

@@ -19,6 +19,15 @@ cases = [
     ("dW   = dY^T X        [128,17280]x[17280,128]", lambda: ops.gemm(dy, x, True, False), lambda: dy.double().t() @ x.double()),
     ("head Y = X W^T       [17280,128]x[64,128]^T ", lambda: ops.gemm(x, w[:64], False, True), lambda: x.double() @ w[:64].double().t()),
 ]
+# the regression head of dp.RegressionStep: [128 molecules, 64] -> [128, 1] and its two gradient GEMMs
+xm = torch.randn(128, 64, device=DEV)
+wh = torch.randn(1, 64, device=DEV) * 0.1
+dyh = torch.randn(128, 1, device=DEV)
+cases += [
+    ("head fwd  [128,64]x[1,64]^T                  ", lambda: ops.gemm(xm, wh, False, True), lambda: xm.double() @ wh.double().t()),
+    ("head dX   [128,1]x[1,64]                     ", lambda: ops.gemm(dyh, wh, False, False), lambda: dyh.double() @ wh.double()),
+    ("head dW   [128,1]^T x [128,64]               ", lambda: ops.gemm(dyh, xm, True, False), lambda: dyh.double().t() @ xm.double()),
+]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
 for name, fn, ref in cases:
     out = fn()
@@ -36,5 +45,5 @@ for name, fn, ref in cases:
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
     ts.sort()
-    flops = 2.0 * out.numel() * (x.shape[0] if "dW" in name else H)
+    flops = 2.0 * out.numel() * (x.shape[0] if name.startswith("dW") else H)
     print(f"{name}: median {ts[5]:7.1f} us  ({flops / ts[5] * 1e-6:5.1f} TFLOP/s)  rel err vs fp64 {err:.1e}  checksum {float(out.double().sum()):.10e}")
