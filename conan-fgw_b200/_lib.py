@@ -42,6 +42,9 @@ SIGNATURES = {
     "cmp_embedding_bwd": (I, [P, L, P, I, I, I, P, P, S, P]),
     "cmp_cfconv_message_fwd": (I, [P, P, P, P, P, L, I, F, P, P]),
     "cmp_cfconv_message_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, F, P, P, P]),
+    "cmp_regression_head_max_channels": (I, []),
+    "cmp_regression_head_fwd": (I, [P, L, L, I, I, P, P, P, P, P, P]),
+    "cmp_regression_head_bwd": (I, [P, L, L, I, I, P, P, P, P, L, P, P, P]),
     "cmp_segment_sum_fwd": (I, [P, P, L, I, P, P]),
     "cmp_segment_sum_bwd": (I, [P, P, L, I, P, P]),
     "cmp_adam_step": (I, [P, P, P, P, L, F, F, F, F, F, I, F, P]),

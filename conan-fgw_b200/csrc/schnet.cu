@@ -239,6 +239,94 @@ int grid1d(int64_t n, int per_block = 256) {
 }
 
 }  // namespace
+
+// ---- regression head of a ConAN training step in two launches (schnet_based_models.py:242 conformer mean,
+// :17-29 linear head, model/common.py:288 MSE):  mol[b] = mean_k emb[b K + k];  pred[b] = w . mol[b] + bias;
+// loss = mean_b (pred[b] - target[b])^2.  Replaces ~20 launches on tensors of a few KB (segment mean, tiny GEMMs and
+// their gradients, MSE forward / backward, fills).  One CTA: sums run in a fixed order (deterministic).
+constexpr int HEAD_THREADS = 1024;      // one CTA of 32 warps: a warp per molecule, lanes over the channels (coalesced rows)
+constexpr int HEAD_WARPS = HEAD_THREADS / 32;
+constexpr int HEAD_MAXC = 512;          // channels per lane: HEAD_MAXC / 32
+
+__global__ void __launch_bounds__(HEAD_THREADS)
+regression_head_fwd_kernel(const float* __restrict__ emb, int64_t ld, int B, int K, int C, const float* __restrict__ w,
+                           const float* __restrict__ bias, const float* __restrict__ target, float* __restrict__ err,
+                           float* __restrict__ loss) {
+  __shared__ float red[HEAD_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float invK = 1.0f / (float)K;
+  const float b0 = bias ? bias[0] : 0.0f;
+  float sq = 0.0f;     // lane 0 of every warp: squared errors of its molecules, in molecule order
+  for (int b = warp; b < B; b += HEAD_WARPS) {
+    float part = 0.0f;
+    for (int c = lane; c < C; c += 32) {
+      float m = 0.0f;
+      for (int k = 0; k < K; ++k) m += emb[((int64_t)b * K + k) * ld + c];
+      part = fmaf(m * invK, w[c], part);
+    }
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    const float e = part + b0 - target[b];
+    if (lane == 0) err[b] = e;
+    sq += e * e;
+  }
+  if (lane == 0) red[warp] = sq;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int i = 0; i < HEAD_WARPS; ++i) t += red[i];     // fixed order: deterministic
+    loss[0] = t / (float)B;
+  }
+}
+
+// d loss / d pred[b] = gscale * 2 err[b] / B.  A warp per molecule writes its d emb rows and keeps its share of dw in
+// registers (lane c); the per-warp shares are added in warp order.
+__global__ void __launch_bounds__(HEAD_THREADS)
+regression_head_bwd_kernel(const float* __restrict__ emb, int64_t ld, int B, int K, int C, const float* __restrict__ w,
+                           const float* __restrict__ err, const float* __restrict__ gscale, float* __restrict__ d_emb,
+                           int64_t ldd, float* __restrict__ dw, float* __restrict__ db) {
+  extern __shared__ float part[];      // [HEAD_WARPS][C] | [HEAD_WARPS]
+  float* pdb = part + HEAD_WARPS * C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float gs = (gscale ? gscale[0] : 1.0f) * 2.0f / (float)B;
+  const float invK = 1.0f / (float)K;
+  float acc[HEAD_MAXC / 32];
+#pragma unroll
+  for (int r = 0; r < HEAD_MAXC / 32; ++r) acc[r] = 0.0f;
+  float accb = 0.0f;
+  for (int b = warp; b < B; b += HEAD_WARPS) {
+    const float gl = gs * err[b];
+    accb += gl;
+#pragma unroll
+    for (int r = 0; r < HEAD_MAXC / 32; ++r) {
+      const int c = r * 32 + lane;
+      if (c < C) {
+        float m = 0.0f;
+        for (int k = 0; k < K; ++k) m += emb[((int64_t)b * K + k) * ld + c];
+        acc[r] = fmaf(gl, m * invK, acc[r]);
+        const float d = gl * invK * w[c];
+        for (int k = 0; k < K; ++k) d_emb[((int64_t)b * K + k) * ldd + c] = d;
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < HEAD_MAXC / 32; ++r) {
+    const int c = r * 32 + lane;
+    if (c < C) part[warp * C + c] = acc[r];
+  }
+  if (lane == 0) pdb[warp] = accb;
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += HEAD_THREADS) {
+    float t = 0.0f;
+    for (int i = 0; i < HEAD_WARPS; ++i) t += part[i * C + c];
+    dw[c] = t;
+  }
+  if (db && threadIdx.x == HEAD_THREADS - 1) {
+    float t = 0.0f;
+    for (int i = 0; i < HEAD_WARPS; ++i) t += pdb[i];
+    db[0] = t;
+  }
+}
+
 }  // namespace cmp
 
 using namespace cmp;
@@ -406,5 +494,39 @@ extern "C" int cmp_edge_message_bwd(const float* g, const float* x, const float*
                                                             scale);
     CMP_LAUNCH_CHECK("cmp_edge_message_bwd(dx)");
   }
+  return CMP_OK;
+}
+
+extern "C" int cmp_regression_head_max_channels(void) { return cmp::HEAD_MAXC; }
+
+extern "C" int cmp_regression_head_fwd(const float* emb, int64_t ld, int64_t B, int K, int C, const float* w,
+                                       const float* bias, const float* target, float* err, float* loss,
+                                       cmp_stream_t stream) {
+  CMP_REQUIRE(B >= 1 && K >= 1 && C >= 1 && B <= (1 << 20) && C <= cmp::HEAD_MAXC, CMP_EINVAL,
+              "cmp_regression_head_fwd: bad size");
+  CMP_REQUIRE(emb && w && target && err && loss, CMP_EINVAL, "cmp_regression_head_fwd: null pointer");
+  cmp::regression_head_fwd_kernel<<<1, cmp::HEAD_THREADS, 0, cmp::as_stream(stream)>>>(emb, ld, (int)B, K, C, w, bias,
+                                                                                    target, err, loss);
+  CMP_LAUNCH_CHECK("cmp_regression_head_fwd");
+  return CMP_OK;
+}
+
+extern "C" int cmp_regression_head_bwd(const float* emb, int64_t ld, int64_t B, int K, int C, const float* w,
+                                       const float* err, const float* gscale, float* d_emb, int64_t ldd, float* dw,
+                                       float* db, cmp_stream_t stream) {
+  CMP_REQUIRE(B >= 1 && K >= 1 && C >= 1 && B <= (1 << 20) && C <= cmp::HEAD_MAXC, CMP_EINVAL,
+              "cmp_regression_head_bwd: bad size");
+  CMP_REQUIRE(emb && w && err && d_emb && dw, CMP_EINVAL, "cmp_regression_head_bwd: null pointer");
+  const size_t smem = (size_t)cmp::HEAD_WARPS * (C + 1) * sizeof(float);
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(cmp::regression_head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+          cudaSuccess) {
+    (void)cudaGetLastError();
+    cmp::set_error("cmp_regression_head_bwd: cannot opt in to %zu bytes of shared memory", smem);
+    return CMP_ECUDA;
+  }
+  cmp::regression_head_bwd_kernel<<<1, cmp::HEAD_THREADS, smem, cmp::as_stream(stream)>>>(emb, ld, (int)B, K, C, w, err,
+                                                                                       gscale, d_emb, ldd, dw, db);
+  CMP_LAUNCH_CHECK("cmp_regression_head_bwd");
   return CMP_OK;
 }

@@ -89,6 +89,11 @@ class FlatParameters:
                       weight_decay, grad_scale)
 
 
+# conformer mean -> linear head -> MSE of RegressionStep.loss as one fused forward / backward launch each
+# (ops.regression_head_loss); False = the separate segment-mean / GEMM / torch MSE ops (kept for cross-checking)
+FUSED_HEAD = True
+
+
 class RegressionStep:
     """One ConAN-style regression training step around the backbone:
     backbone -> [G, H/2] -> mean over the K conformers of a molecule (``schnet_based_models.py:242``)
@@ -109,6 +114,10 @@ class RegressionStep:
 
     def loss(self, z, pos, batch, targets, num_graphs):
         emb = self.backbone(z, pos, batch, num_graphs=num_graphs, **self.backbone_kwargs)          # [G, H/2]
+        if (FUSED_HEAD and emb.is_cuda and self.head.out_features == 1 and emb.shape[1] <= 512
+                and emb.shape[0] // self.K <= 1024):     # one CTA walks the molecules: larger batches keep the separate ops
+            # conformer mean -> linear head -> MSE (and the whole backward of the three) in two launches
+            return ops.regression_head_loss(emb, self.head.weight, self.head.bias, targets, self.K)
         mol = ops.conformers_mean(emb, self.K)                               # conformers of a molecule are consecutive
         pred = self.head(mol)
         return torch.nn.functional.mse_loss(pred, targets)

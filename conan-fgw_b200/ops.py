@@ -1108,6 +1108,46 @@ def conformers_mean(x, num_conformers: int):
     return segment_sum(x, seg, G // K) * (1.0 / K)
 
 
+class _RegressionHeadLossFn(Function):
+    """conformer mean -> Linear(C, 1) -> MSE as ONE forward and ONE backward launch (``cmp_regression_head_fwd/bwd``)."""
+
+    @staticmethod
+    def forward(ctx, emb, weight, bias, targets, K):
+        emb = _f32c(emb)
+        G, C = emb.shape
+        if G % K != 0:
+            raise ValueError("regression_head_loss: the number of conformers must be a multiple of K")
+        B = G // K
+        w, t = _f32c(weight.reshape(-1)), _f32c(targets.reshape(-1))
+        if w.numel() != C or t.numel() != B:
+            raise ValueError("regression_head_loss: weight must be [1, C] and targets [B] or [B, 1]")
+        err = torch.empty(B, dtype=torch.float32, device=emb.device)
+        loss = torch.empty((), dtype=torch.float32, device=emb.device)
+        call("cmp_regression_head_fwd", ptr(emb), emb.stride(0), B, int(K), C, ptr(w), ptr(bias), ptr(t), ptr(err), ptr(loss))
+        ctx.K, ctx.has_bias, ctx.wshape = int(K), bias is not None, weight.shape
+        ctx.save_for_backward(emb, w, err)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        emb, w, err = ctx.saved_tensors
+        G, C = emb.shape
+        B = G // ctx.K
+        g = _f32c(g.reshape(1))
+        d_emb = torch.empty_like(emb)
+        dw = torch.empty(C, dtype=torch.float32, device=emb.device)
+        db = torch.empty(1, dtype=torch.float32, device=emb.device) if ctx.has_bias else None
+        call("cmp_regression_head_bwd", ptr(emb), emb.stride(0), B, ctx.K, C, ptr(w), ptr(err), ptr(g), ptr(d_emb),
+             d_emb.stride(0), ptr(dw), ptr(db))
+        return d_emb, dw.reshape(ctx.wshape), db, None, None
+
+
+def regression_head_loss(emb, weight, bias, targets, num_conformers: int):
+    """``mse_loss(linear(conformers_mean(emb, K), weight, bias), targets)`` for a one-output head (ConAN's regression
+    head: ``schnet_based_models.py:17-29,242``, ``model/common.py:288``) in two kernel launches."""
+    return _RegressionHeadLossFn.apply(emb, weight, bias, targets, int(num_conformers))
+
+
 def segments_from_batch(batch, num_graphs=None, status=None):
     """Segment pointers of a SORTED index vector.  An unsorted index cannot be served by the segment kernels (PyG's
     scatter would accept it): it is reported - through ``status`` when the caller supplies its own word (sync-free

@@ -170,6 +170,18 @@ int cmp_cfconv_message_bwd(const float* g, const float* xprime, const float* fil
                            int64_t N, int F, float cutoff, float* dfilt, float* dxprime,
                            cmp_stream_t stream);
 
+/* Regression head of a ConAN training step in two launches instead of ~20 on KB-sized tensors
+ * (schnet_based_models.py:242 conformer mean, :17-29 linear head, model/common.py:288 MSE):
+ *   mol[b] = mean_k emb[b K + k];  pred[b] = w . mol[b] + bias;  loss = mean_b (pred[b] - target[b])^2
+ * fwd: err[b] = pred[b] - target[b] (kept for the backward), loss[0].  bwd: d_emb[B K, C], dw[C], db[1] for an upstream
+ * gradient gscale[0] of the loss (device scalar; NULL = 1).  emb has B * K rows (conformers of a molecule consecutive). */
+int cmp_regression_head_max_channels(void);   /* C <= this (512) */
+int cmp_regression_head_fwd(const float* emb, int64_t ld, int64_t B, int K, int C, const float* w,
+                            const float* bias, const float* target, float* err, float* loss,
+                            cmp_stream_t stream);
+int cmp_regression_head_bwd(const float* emb, int64_t ld, int64_t B, int K, int C, const float* w,
+                            const float* err, const float* gscale, float* d_emb, int64_t ldd, float* dw,
+                            float* db, cmp_stream_t stream);
 /* Sum readout over sorted segments (PyG SumAggregation; sns.py:184,353) and its
  * backward (broadcast of dout[g] to the atoms of g). */
 int cmp_segment_sum_fwd(const float* x, const int32_t* seg_ptr, int64_t G, int C, float* out,
