@@ -81,6 +81,8 @@ SIGNATURES = {
     "cmp_vis_vecagg_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, I, P, P, P]),
     "cmp_vis_edge_update_fwd": (I, [P, P, P, P, P, P, L, I, I, P, P, P]),
     "cmp_vis_edge_update_bwd_prep": (I, [P, P, P, L, I, P, P, P]),
+    "cmp_vis_node_update_fwd": (I, [P, P, P, L, I, P, P, P]),
+    "cmp_vis_node_update_bwd": (I, [P, P, P, P, L, I, P, P, P]),
     "cmp_vis_edge_update_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, P, P, P]),
     "cmp_debug_set_fwd_timestamps": (None, [P]),
     "cmp_debug_set_bwd_timestamps": (None, [P]),

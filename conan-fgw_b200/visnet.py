@@ -236,6 +236,31 @@ class _EdgeUpdateFn(Function):
         return g_wt, g_ws, None, g_fpa, None, None
 
 
+class _NodeUpdateFn(Function):
+    """``dx = (vec1 * vec2).sum(1) * o2 + o3``,  ``dvec = vec3 * o1[:, None] + vec_agg`` (tgv.py:616-627) with
+    ``vec1 | vec2 | vec3 = vec_proj(vec)`` and ``o1 | o2 | o3 = o_proj(x_agg)`` in one kernel per direction."""
+
+    @staticmethod
+    def forward(ctx, vp, o, vec_agg):
+        vp, o, vec_agg = _c(vp), _c(o), _c(vec_agg)
+        N, _, H = vec_agg.shape
+        dx = torch.empty(N, H, dtype=torch.float32, device=o.device)
+        dvec = torch.empty_like(vec_agg)
+        call("cmp_vis_node_update_fwd", ptr(vp), ptr(o), ptr(vec_agg), N, H, ptr(dx), ptr(dvec))
+        ctx.save_for_backward(vp, o)
+        return dx, dvec
+
+    @staticmethod
+    def backward(ctx, g_dx, g_dvec):
+        vp, o = ctx.saved_tensors
+        N, H3 = o.shape
+        H = H3 // 3
+        g_dx, g_dvec = _c(g_dx), _c(g_dvec)
+        g_vp, g_o = torch.empty_like(vp), torch.empty_like(o)
+        call("cmp_vis_node_update_bwd", ptr(g_dx), ptr(g_dvec), ptr(vp), ptr(o), N, H, ptr(g_vp), ptr(g_o))
+        return g_vp, g_o, g_dvec
+
+
 def layer_norm(x, module: nn.LayerNorm):
     return _LayerNormFn.apply(x, module.weight, module.bias, module.eps)
 
@@ -452,17 +477,15 @@ class ViS_MP(nn.Module):
         # layer (forward + backward) disappear
         dk = self.dk_proj(f_ij)
         dv = self.dv_proj(f_ij)
-        vec1, vec2, vec3 = torch.split(self.vec_proj(vec), H, dim=-1)
-        vec_dot = (vec1 * vec2).sum(dim=1)
+        vp = self.vec_proj(vec)                                                  # [N, 3, 3H] = vec1 | vec2 | vec3
 
         m = _MessageFn.apply(q, k, v, dk, dv, C, graph, self.num_heads, True)    # [E, H]  v_j * silu(dv) * attn
         s12 = self.s_proj(m)                                                     # [E, 2H] = pre-activations of [s1 | s2]
         x_agg = _SegSumFn.apply(m, graph)
         vec_agg = _VecAggFn.apply(vec, s12, d_ij, graph, True)
 
-        o1, o2, o3 = torch.split(self.o_proj(x_agg), H, dim=1)
-        dx = vec_dot * o2 + o3
-        dvec = vec3 * o1.unsqueeze(1) + vec_agg
+        # (vec1 * vec2).sum(1) * o2 + o3  and  vec3 * o1 + vec_agg  (tgv.py:616-627) in one kernel per direction
+        dx, dvec = _NodeUpdateFn.apply(vp, self.o_proj(x_agg), vec_agg)
         if self.last_layer:
             return dx, dvec, None
         # w_trg / w_src are bias-free linears: apply them once per atom instead of once per edge (tgv.py:657-658)

@@ -570,6 +570,15 @@ int cmp_vis_edge_update_bwd(const float* gw, const float* wt, const float* ws, c
                             const int32_t* col_t, const int32_t* eid_t, int64_t N, int H, float* g_wt,
                             float* g_ws, cmp_stream_t stream);
 
+/* ViS_MP node update (tgv.py:616-627), the element-wise tail of a layer in one kernel per direction:
+ *   vp[N, 3, 3H] = vec_proj(vec) = [vec1 | vec2 | vec3],  o[N, 3H] = o_proj(x_agg) = [o1 | o2 | o3]
+ *   dx = (sum_d vec1 vec2) o2 + o3,   dvec[d] = vec3[d] o1 + vagg[d]
+ * bwd: g_vp[N, 3, 3H], g_o[N, 3H] from g_dx[N, H], g_dvec[N, 3, H] (the gradient of vagg is g_dvec itself). */
+int cmp_vis_node_update_fwd(const float* vp, const float* o, const float* vagg, int64_t N, int H, float* dx,
+                            float* dvec, cmp_stream_t stream);
+int cmp_vis_node_update_bwd(const float* g_dx, const float* g_dvec, const float* vp, const float* o, int64_t N,
+                            int H, float* g_vp, float* g_o, cmp_stream_t stream);
+
 /* Debug hook: when non-NULL, CTA 0 / pipeline 0 of cmp_cfconv_fused_fwd stores 8 clock64() phase
  * timestamps per tile (first 32 tiles) into this device buffer of 256 int64. */
 void cmp_debug_set_fwd_timestamps(void* buf);
