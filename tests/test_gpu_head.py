@@ -25,7 +25,7 @@ def test_fused_head_matches_the_three_separate_ops(B, K, C, bias):
     got = ops.regression_head_loss(e2, w, b, t, K)
     gg = torch.autograd.grad(3.0 * got, [e2, w] + ([b] if bias else []))      # upstream gradient != 1
     assert got.shape == want.shape
-    assert abs(float(got) - float(want)) <= 2e-6 * abs(float(want))
+    assert abs(float(got.detach()) - float(want.detach())) <= 2e-6 * abs(float(want.detach()))
     for a, r in zip(gg, gw):
         assert a.shape == r.shape
         assert rel_err(a, r) < 2e-6
