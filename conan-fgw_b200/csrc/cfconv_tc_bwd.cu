@@ -965,6 +965,7 @@ __device__ __forceinline__ void dense_df_rect(const float (&gr)[16], const float
 
 __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_bwd_kernel(const __grid_constant__ DenseBwdParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ float s_db[NG * 2 * 2 * F];     // db2 | db1 partials of (group, half), combined in the drain
   // wbar | per group: r_ready, d1_ready, f_ready, dda_ready, h_ready, w_done
   __shared__ uint64_t bars[1 + NG * 6];
   __shared__ uint32_t tmem_base_s;
@@ -1297,41 +1298,69 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) cfconv_dense_bwd_kernel(const 
       if (ti + 1 < t1) w.next(p);
     }
 
-    // ---- drain: accumulators -> this pipeline's partial block ----
-    float* part = p.partial + u * (int64_t)PART_FLOATS;
+    // ---- drain: the accumulators of BOTH groups are added in registers (same TMEM lanes = same channel rows, a thread
+    // reads the other group's columns as easily as its own) and leave the CTA as ONE partial block: half the partial
+    // traffic and half the work of the reduction kernel.  Group g, half h owns a quarter of the columns.
     const bool any = t0 < t1;
     if (any) {
       tc::mbar_wait(b + 5, (it - 1) & 1);
       tc::tc_fence_after();
     }
-    for (int c0 = h * 64; c0 < h * 64 + 64; c0 += 16) {       // dW2[f = chan][k]: columns [h*64, h*64+64)
-      float v[16];
-      if (any) {
-        tc::tmem_ld16(tW2 + c0, v);
-        tc::tmem_wait_ld();
-      } else {
+    s_db[(g * 2 + h) * 2 * F + chan] = db2;
+    s_db[(g * 2 + h) * 2 * F + F + chan] = db1;
+    tc::tc_fence_before();
+    tc::named_bar_sync(NG + 1, NG * GT);      // both groups: every MMA finished, every db partial visible
+    tc::tc_fence_after();
+    bool any_g[NG];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+    for (int gg = 0; gg < NG; ++gg) {
+      const int64_t uu = (int64_t)blockIdx.x * NG + gg;
+      any_g[gg] = uu * T / U < (uu + 1) * T / U;
+    }
+    float* part = p.partial + (int64_t)blockIdx.x * PART_FLOATS;
+    const uint32_t tLane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const int qd = g * 2 + h;                                    // column quarter of this warp
+    for (int c0 = qd * 32; c0 < qd * 32 + 32; c0 += 16) {        // dW2[f = chan][k]
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+#pragma unroll
+      for (int gg = 0; gg < NG; ++gg) {
+        if (any_g[gg]) {
+          float t[16];
+          tc::tmem_ld16(tLane + gg * 256 + 64 + c0, t);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += t[j];
+        }
       }
 #pragma unroll
       for (int j = 0; j < 16; j += 4)
         *reinterpret_cast<float4*>(part + chan * F + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
-    for (int c0 = h * 32; c0 < h * 32 + 32; c0 += 16) {       // dW1[k = chan][j]: columns [h*32, h*32+32)
+    {                                                            // dW1[k = chan][j]: 16 of the 64 columns
+      const int c0 = qd * 16;
       float v[16];
-      if (any) {
-        tc::tmem_ld16(tW1 + c0, v);
-        tc::tmem_wait_ld();
-      } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+      for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+#pragma unroll
+      for (int gg = 0; gg < NG; ++gg) {
+        if (any_g[gg]) {
+          float t[16];
+          tc::tmem_ld16(tLane + gg * 256 + 192 + c0, t);
+          tc::tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] += t[j];
+        }
       }
 #pragma unroll
       for (int j = 0; j < 16; j += 4)
         *reinterpret_cast<float4*>(part + F * F + chan * K1 + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
-    part[F * F + F * K1 + h * F + chan] = db2;
-    part[F * F + F * K1 + 2 * F + h * F + chan] = db1;
+    if (g == 0) {       // db2 / db1: the two halves stay separate slots (the reduction adds them), the groups are added here
+      part[F * F + F * K1 + h * F + chan] = s_db[(0 * 2 + h) * 2 * F + chan] + s_db[(1 * 2 + h) * 2 * F + chan];
+      part[F * F + F * K1 + 2 * F + h * F + chan] = s_db[(0 * 2 + h) * 2 * F + F + chan] + s_db[(1 * 2 + h) * 2 * F + F + chan];
+    }
   }
 
   tc::tc_fence_before();
@@ -2489,8 +2518,8 @@ extern "C" int cmp_cfconv_dense_bwd_weights(const float* g, const float* xprime,
     cfconv_dense_bwd_kernel<<<grid, CTA_THREADS, D_SMEM_BYTES, st>>>(p);
   CMP_LAUNCH_CHECK("cmp_cfconv_dense_bwd_weights");
   const int total = F * F + F * K1 + 2 * F;
-  reduce_partials_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(p.partial, ws ? grid : grid * NG, num_gaussians, dW1,
-                                                                    db1, dW2, db2);
+  // one partial block per CTA in both variants (the default kernel adds its two groups in the drain)
+  reduce_partials_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(p.partial, grid, num_gaussians, dW1, db1, dW2, db2);
   CMP_LAUNCH_CHECK("cmp_cfconv_dense_bwd_weights");
   return CMP_OK;
 }
