@@ -148,7 +148,18 @@ class RegressionStep:
         the library is stream-ordered and sync-free on the bf16 path).  Later ``step`` calls with tensors of the same
         shapes copy their inputs into the static buffers and replay it; the gradient all-reduce and Adam follow
         eagerly.  Shapes are fixed per capture: a training loop keeps one graph per (N, G) bucket."""
-        self._static = [t.clone() for t in (z, pos, batch, targets)]
+        # the static inputs are views of ONE device buffer (256-byte aligned slots): a loader that collates into the pinned
+        # twin of that layout (``host_staging``) uploads a whole step with a single H2D copy (``upload``)
+        srcs = [t.contiguous() for t in (z, pos, batch, targets)]
+        offs, total = [], 0
+        for t in srcs:
+            offs.append(total)
+            total += (t.numel() * t.element_size() + 255) // 256 * 256
+        self._static_buf = torch.empty(max(total, 256), dtype=torch.uint8, device=srcs[0].device)
+        self._static_layout = [(o, t.numel() * t.element_size(), t.dtype, tuple(t.shape)) for o, t in zip(offs, srcs)]
+        self._static = [self._static_buf[o:o + nb].view(dt).view(shape) for o, nb, dt, shape in self._static_layout]
+        for dst, src in zip(self._static, srcs):
+            dst.copy_(src)
         self._static_G = int(num_graphs)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -166,6 +177,18 @@ class RegressionStep:
         finally:
             _lib.timer = prev
         return self
+
+    def host_staging(self):
+        """``(buffer, [z, pos, batch, targets])``: a pinned host buffer with the layout of the captured step's input
+        buffer and typed views of its four slots.  Fill the views (e.g. in the collate function), then ``upload(buffer)``."""
+        buf = torch.empty(self._static_buf.numel(), dtype=torch.uint8).pin_memory()
+        views = [buf[o:o + nb].view(dt).view(shape) for o, nb, dt, shape in self._static_layout]
+        return buf, views
+
+    def upload(self, host_buffer):
+        """One asynchronous H2D copy of a whole step's inputs into the captured graph's input buffers."""
+        self._static_buf.copy_(host_buffer, non_blocking=True)
+        return self._static
 
     def step(self, z, pos, batch, targets, num_graphs):
         g = getattr(self, "_graph", None)
