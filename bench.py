@@ -42,7 +42,7 @@ REFERENCE_BUDGET_S = 240.0           # --impl reference: the whole run (warm-up 
 # measured once per round under ncu (never a timing source): DRAM traffic per launch at the default workload
 # (dram__bytes_read.sum + dram__bytes_write.sum; profiles/r02_dense_ws_kernel.metrics.csv, r02_dense_bwd_kernel.metrics.csv,
 # r02_x3_fwd_kernel.metrics.csv, r02_x3_bwd_kernel.metrics.csv, r01_pair_bwd_kernel.metrics.csv)
-NCU_DRAM_BYTES_PER_LAUNCH = {"cmp_cfconv_dense_fwd": 9481984, "cmp_cfconv_dense_bwd_weights": 18723328 + 437504,
+NCU_DRAM_BYTES_PER_LAUNCH = {"cmp_cfconv_dense_fwd": 9466368, "cmp_cfconv_dense_bwd_weights": 18334464 + 36096,
                              "cmp_cfconv_dense_x3_fwd": 9512192, "cmp_cfconv_dense_bwd_x3_weights": 18353152 + 256,
                              "cmp_cfconv_pair_fwd": 12547584,
                              "cmp_cfconv_fused_bwd_weights_pairs": 13398784 + 764672, "cmp_cfconv_fused_fwd": 15000000}
