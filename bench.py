@@ -49,7 +49,7 @@ NCU_DRAM_BYTES_PER_LAUNCH = {"cmp_cfconv_dense_fwd": 9466368, "cmp_cfconv_dense_
 FWD_KERNELS = ("cmp_cfconv_dense_fwd", "cmp_cfconv_dense_x3_fwd", "cmp_cfconv_fused_fwd", "cmp_cfconv_pair_fwd")
 DTYPE_X3 = "f32-grade: f16 / bf16 hi + lo filter-MLP operands, three tcgen05 passes, f32 accumulation and epilogues; f32 elsewhere (node linears: exact SIMT, or split-bf16 tcgen05 with CMP_FP32_NODE_TC=1)"
 CLS_MODEL_CFG = dict(hidden_channels=512, num_filters=256, num_interactions=3, num_gaussians=10, cutoff=10.0)
-TOL_FP32 = ("embeddings 1e-5 (measured 3e-6), gradients 2e-5 (measured 1.3e-5) vs the fp64 oracle on 6-block trunks: "
+TOL_FP32 = ("embeddings 1e-5 (measured 3e-6), gradients 2e-5 (measured 1.3e-5 .. 1.6e-5) vs the fp64 oracle on 6-block trunks: "
             "fp32-grade fused CFConv kernels, exact node linears (profiles/r02_x3_errors.md)")
 TOL_FP32_TC = ("embeddings 2.5e-5 (measured 1.9e-5), gradients 6e-5 (measured 4.1e-5): fp32-grade fused CFConv kernels, "
                "split-bf16 node linears (profiles/r02_x3_errors.md)")

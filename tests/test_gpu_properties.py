@@ -184,3 +184,38 @@ def test_fused_mode_gradients_at_the_bench_size():
     assert rel_err(got, want) < 5e-3 and row_rel_err(got, want) < 5e-3
     worst = max((rel_err(p.grad, ref[k]), k) for k, p in m.named_parameters() if k in ref)
     assert worst[0] < 7.5e-3, worst
+
+
+def test_fp32_grade_fused_mode_at_the_bench_size():
+    """The fp32-grade fused mode (three-pass tcgen05 kernels, `fp32` precision with a promised atom bound) against the
+    exact kernels on the FULL cfg 2 batch (640 conformers, 449 K edges, T = 6): embeddings within 1e-5 (also per conformer
+    row, 2e-5), every parameter gradient within 2e-5 - the stated tolerances of the mode."""
+    if not cmp._lib.lib().cmp_device_is_sm100():
+        pytest.skip("tcgen05 kernels need an sm_100 device")
+    from conftest import row_rel_err
+
+    b = syn.make_config_batch("cfg2_lipo_train").to(DEV)
+    m = _model("exact")
+    want = m(b.z, b.pos, b.batch, num_graphs=b.num_graphs)
+    want.pow(2).mean().backward()
+    ref = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.set_precision("fp32")
+    m.max_atoms_hint = 27
+    m.zero_grad()
+    lib = cmp._lib
+    lib.timer = lib.KernelTimer(["cmp_cfconv_dense_x3_fwd", "cmp_cfconv_dense_bwd_x3_weights", "cmp_cfconv_message_fwd"])
+    try:
+        got = m(b.z, b.pos, b.batch, num_graphs=b.num_graphs)
+        got.pow(2).mean().backward()
+        m.check_status()
+        torch.cuda.synchronize()
+        seen = {k: v[0] for k, v in lib.timer.summary().items()}
+    finally:
+        lib.timer = None
+    assert seen.get("cmp_cfconv_dense_x3_fwd", 0) == 12 and seen.get("cmp_cfconv_dense_bwd_x3_weights", 0) == 6
+    assert seen.get("cmp_cfconv_message_fwd", 0) == 0
+    assert rel_err(got, want) < 1e-5 and row_rel_err(got, want) < 2e-5
+    worst = max((rel_err(p.grad, ref[k]), k) for k, p in m.named_parameters() if k in ref)
+    assert worst[0] < 2e-5, worst
+    print(f"fp32-grade fused mode at cfg 2: embeddings {rel_err(got, want):.2e} (rows {row_rel_err(got, want):.2e}), "
+          f"worst gradient {worst[0]:.2e} ({worst[1]})")
